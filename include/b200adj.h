@@ -1,0 +1,131 @@
+/*
+ * b200adj.h -- C ABI of libb200adj.so, the B200-native (sm_100a) ensemble continuous-adjoint engine.
+ *
+ * This is the drop-in boundary for ONE hot path of SciML/SciMLSensitivity.jl v7.112.3: the reverse-mode
+ * continuous adjoint (InterpolatingAdjoint / GaussAdjoint / QuadratureAdjoint / BacksolveAdjoint) evaluated
+ * over an ensemble of independent trajectories.  The reference is pure Julia and has no FFI for this path;
+ * the entry points below are what a `ccall` layer binds from a new
+ *     SciMLBase._concrete_solve_adjoint(prob, alg, sensealg::B200Adjoint{Inner}, u0, p, originator, args...; kw...)
+ * method (shape of /root/reference/src/concrete_solve.jl:523-543,1041 and of the extension precedent
+ * ext/SciMLSensitivityMooncakeExt.jl:123-240).  See INTEGRATION.md for the Julia stub.
+ *
+ * Rules: plain C types only; every call returns int32 (0 = ok, <0 = error, see B200ADJ_ERR_*); no exceptions,
+ * no callbacks into the host language, no global mutable state; a handle is single-owner (not thread-safe),
+ * one handle per GPU.  The library has NO CPU fallback: b200adj_create fails with B200ADJ_ERR_NO_DEVICE when no
+ * CUDA device is usable.
+ *
+ * Layouts (trajectory-minor SoA, element type per cfg.dtype):
+ *   u0[d][N]   p[P] (shared_p=1) or p[P][N]   saved[K][d][N]   dLdu[K][d][N]
+ *   du0[d][N]  dp[P] (shared_p=1: summed over the N members of this handle) or dp[P][N]
+ *   dW[S][m][N] Wiener increments (SDE steppers), S = round((t1-t0)/dt)
+ */
+#ifndef B200ADJ_H
+#define B200ADJ_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* rhs_family: named RHS families whose f, (df/du)'lam and (df/dp)'lam are hand-differentiated device code.
+ * Replaces the AD back-ends behind vecjacobian! (src/derivative_wrappers.jl:256-267, :435-1163). */
+enum {
+    B200ADJ_FAM_LV = 0,         /* Lotka-Volterra d=2 P=4   (test/Core1/concrete_solve_derivatives.jl:106-127) */
+    B200ADJ_FAM_LORENZ = 1,     /* Lorenz d=3 P=3           (test/Core3/adjoint.jl:1160-1167)                  */
+    B200ADJ_FAM_ROBERTSON = 2,  /* Robertson d=3 P=3        (test/Core2/stiff_adjoints.jl:256-263, 3-param)    */
+    B200ADJ_FAM_SDE_LV = 3,     /* LV drift + diag noise g_i = p[4+i] u_i, d=2 P=6 m=2 (Core1/...:737-760)      */
+    B200ADJ_FAM_MLP = 4,        /* 2 -> H -> H -> 2 tanh MLP (docs/src/Benchmark.md:49-52), P = H*H+7H+2        */
+    B200ADJ_FAM_SDE_LINEAR = 5  /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
+};
+/* sensealg: which *SensitivityFunction / driver is run (src/sensitivity_algorithms.jl:254-278,378-405,486-510,591-611) */
+enum { B200ADJ_SA_INTERPOLATING = 0, B200ADJ_SA_GAUSS = 1, B200ADJ_SA_QUADRATURE = 2, B200ADJ_SA_BACKSOLVE = 3 };
+/* stepper: the `alg` handed to solve() for both the forward and the adjoint problem (src/sensitivity_interface.jl:487-491) */
+enum { B200ADJ_ST_TSIT5_FIXED = 0, B200ADJ_ST_ROSENBROCK23 = 1, B200ADJ_ST_EM = 2, B200ADJ_ST_EULER_HEUN = 3 };
+enum { B200ADJ_F64 = 0, B200ADJ_F32 = 1, B200ADJ_BF16_F32ACC = 2 };
+/* cost_kind: how the discrete cotangent dgdu_discrete(out,u,p,t,i) is obtained at save time t_k
+ * (ReverseLossCallback, src/adjoint_common.jl:754-821).  EXPLICIT = read column k of the array passed to
+ * b200adj_reverse (the rrule pullback's Delta, src/concrete_solve.jl:778-947); AFFINE = a*u(t_k)+b evaluated
+ * in-kernel (the dg(out,u,p,t,i) = out .= u .- 2 of test/Core3/adjoint.jl:1169-1171 is a=1, b=-2). */
+enum { B200ADJ_COST_EXPLICIT = 0, B200ADJ_COST_AFFINE = 1 };
+
+/* flags */
+#define B200ADJ_FLAG_NO_START            1u   /* skip the jump at t0 (src/adjoint_common.jl:761)                    */
+#define B200ADJ_FLAG_NO_CHECKPOINTING    2u   /* BacksolveAdjoint(checkpointing=false)                              */
+#define B200ADJ_FLAG_CKPT_EVERY_STEP     4u   /* Backsolve: checkpoints = sol.t (direct interface default,         */
+                                              /* src/sensitivity_interface.jl:433) instead of the save times        */
+#define B200ADJ_FLAG_STORED_NOISE        8u   /* SDE: keep dW[S][m][N] in HBM (reference behaviour, reverse(sol.W)) */
+                                              /* instead of regenerating it from the Philox counter in reverse      */
+
+/* error codes */
+#define B200ADJ_OK                 0
+#define B200ADJ_ERR_INVALID       -1   /* null pointer / bad enum / inconsistent sizes                     */
+#define B200ADJ_ERR_UNSUPPORTED   -2   /* valid for the reference, not built here: delegate to reference   */
+#define B200ADJ_ERR_NO_DEVICE     -3   /* no usable CUDA device (there is no CPU fallback)                 */
+#define B200ADJ_ERR_CUDA          -4   /* CUDA runtime error, text in b200adj_last_error                   */
+#define B200ADJ_ERR_STATE         -5   /* reverse before forward, etc.                                     */
+#define B200ADJ_ERR_OOM           -6
+
+typedef struct b200adj_cfg {
+    int32_t rhs_family, sensealg, stepper, dtype;
+    int32_t d, P, m, K;
+    int64_t N;                       /* ensemble members owned by THIS handle (this GPU's shard)          */
+    double  t0, t1, dt;              /* fixed step (ST_TSIT5_FIXED / EM / EULER_HEUN), initial dt hint else */
+    double  abstol, reltol;          /* adaptive steppers: forward and adjoint solves                      */
+    double  quad_abstol, quad_reltol;/* QuadratureAdjoint quadgk tolerances (src/sensitivity_algorithms.jl:493-503) */
+    const double* saveat;            /* K ascending save times (host pointer, copied by create)            */
+    int32_t shared_p;                /* 1: one p for all members, dp summed; 0: per-member p and dp        */
+    int32_t buffers_on_device;       /* 1: all data pointers passed to forward/reverse are device pointers */
+    int32_t device;                  /* CUDA device ordinal                                                */
+    int32_t cost_kind;
+    double  cost_a, cost_b;
+    uint64_t seed;                   /* Philox seed for SDE Wiener increments                              */
+    int64_t traj_offset;             /* global index of member 0 (keeps Philox streams shard-independent)  */
+    int32_t checkpoint_every;        /* reserved (1 = every step)                                          */
+    uint32_t flags;
+    int32_t mlp_hidden;              /* FAM_MLP hidden width                                               */
+    int32_t block_threads;           /* 0 = library default; tuning knob                                   */
+} b200adj_cfg;
+
+/* create: validates cfg, allocates checkpoints/partials on cfg.device, uploads tableaux.  Replaces the set-up done
+ * by ODEAdjointProblem / SDEAdjointProblem + adjointdiffcache (src/interpolating_adjoint.jl:307-451,
+ * src/gauss_adjoint.jl:275-423, src/quadrature_adjoint.jl:93-214, src/backsolve_adjoint.jl:123-419,
+ * src/adjoint_common.jl:42-469). */
+int32_t b200adj_create(const b200adj_cfg* cfg, void** handle);
+
+/* forward: batched forward solve of all members, keeps per-step checkpoints in HBM, writes the primal at saveat.
+ * Replaces the forward solve + sol(ts) of src/concrete_solve.jl:689-770.  saved may be NULL; status[N] (int32,
+ * 0 = ok, 1 = non-finite state) may be NULL.  dW_in (SDE only, may be NULL): use these increments instead of Philox. */
+int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void* dW_in, void* saved, int32_t* status);
+
+/* reverse: the fused reverse pass (adjoint RHS + VJPs + quadrature + RK update + jumps, all members), then the
+ * deterministic reduction of dp.  Replaces _adjoint_sensitivities (src/sensitivity_interface.jl:426-526,
+ * src/gauss_adjoint.jl:766-870, src/quadrature_adjoint.jl:510-633) and everything it calls per stage
+ * (sense functors, split_states, vecjacobian!, vec_pjac!, ReverseLossCallback).  dLdu may be NULL when
+ * cfg.cost_kind != EXPLICIT. */
+int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp);
+
+/* Change what the NEXT reverse pass computes without redoing the forward pass (checkpoints are sensealg-agnostic):
+ * the reference's adjoint_sensitivities(sol, alg; t, dgdu_discrete, sensealg, no_start, checkpoints) takes these per
+ * call on an existing `sol` (src/sensitivity_interface.jl:373-526).  K < 0 keeps the current save times. */
+int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost_kind, double cost_a, double cost_b,
+                                    uint32_t flags, int32_t K, const double* t);
+
+/* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
+int32_t b200adj_get_noise(void* handle, void* dW_out);
+
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's private stream) */
+int32_t b200adj_set_stream(void* handle, void* cuda_stream);
+/* block until all work queued by this handle has finished */
+int32_t b200adj_synchronize(void* handle);
+/* number of kernels this handle has launched so far (bench.py's gpu_launches) */
+int64_t b200adj_launch_count(void* handle);
+/* adaptive steppers: per-member accepted step counts of the last forward / reverse solves (device or host per cfg) */
+int32_t b200adj_get_step_counts(void* handle, int32_t* fwd_steps, int32_t* rev_steps);
+
+int32_t b200adj_destroy(void* handle);
+const char* b200adj_last_error(void* handle);   /* handle may be NULL: last create() error of this thread */
+uint32_t b200adj_version(void);                 /* 0xMMmmpp */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,179 @@
+"""ctypes binding of libb200adj.so (include/b200adj.h) and the in-tree build recipe.
+
+The product path has NO CPU fallback: `load()` raises if the CUDA extension is missing, and `Handle` raises
+`B200AdjError` on every non-zero status the C ABI returns.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+_CSRC = os.path.join(_PKG, "csrc")
+LIB_PATH = os.path.join(_PKG, "libb200adj.so")
+
+FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5}
+SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3}
+ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3}
+DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
+COST = {"explicit": 0, "affine": 1}
+FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE = 1, 2, 4, 8
+ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
+
+EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_get_noise", "b200adj_set_stream",
+           "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_destroy",
+           "b200adj_last_error", "b200adj_version"]
+
+
+class B200AdjError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"b200adj error {code} ({ERR.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("rhs_family", C.c_int32), ("sensealg", C.c_int32), ("stepper", C.c_int32), ("dtype", C.c_int32),
+        ("d", C.c_int32), ("P", C.c_int32), ("m", C.c_int32), ("K", C.c_int32),
+        ("N", C.c_int64),
+        ("t0", C.c_double), ("t1", C.c_double), ("dt", C.c_double),
+        ("abstol", C.c_double), ("reltol", C.c_double),
+        ("quad_abstol", C.c_double), ("quad_reltol", C.c_double),
+        ("saveat", C.POINTER(C.c_double)),
+        ("shared_p", C.c_int32), ("buffers_on_device", C.c_int32), ("device", C.c_int32), ("cost_kind", C.c_int32),
+        ("cost_a", C.c_double), ("cost_b", C.c_double),
+        ("seed", C.c_uint64), ("traj_offset", C.c_int64),
+        ("checkpoint_every", C.c_int32), ("flags", C.c_uint32), ("mlp_hidden", C.c_int32), ("block_threads", C.c_int32),
+    ]
+
+
+def nvcc_path():
+    return shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into scimlsensitivity.jl_b200/libb200adj.so (in-tree, travels with gpurun)."""
+    srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_ROOT, "include", "b200adj.h"))
+    if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
+        return LIB_PATH
+    cus = [s for s in srcs if s.endswith(".cu")]
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-o", LIB_PATH] + cus
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    with open(os.path.join(_PKG, "ptxas.log"), "w") as f:
+        f.write(res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
+    if verbose:
+        print(res.stderr[-2000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the engine has no CPU fallback)")
+        lib = C.CDLL(LIB_PATH)
+        lib.b200adj_create.argtypes = [C.POINTER(Cfg), C.POINTER(C.c_void_p)]
+        lib.b200adj_create.restype = C.c_int32
+        lib.b200adj_forward.argtypes = [C.c_void_p] * 6
+        lib.b200adj_forward.restype = C.c_int32
+        lib.b200adj_reverse.argtypes = [C.c_void_p] * 4
+        lib.b200adj_reverse.restype = C.c_int32
+        lib.b200adj_set_reverse_options.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_uint32,
+                                                    C.c_int32, C.c_void_p]
+        lib.b200adj_set_reverse_options.restype = C.c_int32
+        lib.b200adj_get_noise.argtypes = [C.c_void_p, C.c_void_p]
+        lib.b200adj_get_noise.restype = C.c_int32
+        lib.b200adj_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        lib.b200adj_set_stream.restype = C.c_int32
+        lib.b200adj_synchronize.argtypes = [C.c_void_p]
+        lib.b200adj_synchronize.restype = C.c_int32
+        lib.b200adj_launch_count.argtypes = [C.c_void_p]
+        lib.b200adj_launch_count.restype = C.c_int64
+        lib.b200adj_get_step_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200adj_get_step_counts.restype = C.c_int32
+        lib.b200adj_destroy.argtypes = [C.c_void_p]
+        lib.b200adj_destroy.restype = C.c_int32
+        lib.b200adj_last_error.argtypes = [C.c_void_p]
+        lib.b200adj_last_error.restype = C.c_char_p
+        lib.b200adj_version.restype = C.c_uint32
+        _lib = lib
+    return _lib
+
+
+def _addr(x):
+    """Raw address of a numpy array, a torch tensor, an int, or None."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Handle:
+    """Owner of one b200adj handle (one GPU, one ensemble shard)."""
+
+    def __init__(self, cfg: Cfg, saveat):
+        import numpy as np
+        self._lib = load()
+        self._saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+        cfg.K = len(self._saveat)
+        cfg.saveat = self._saveat.ctypes.data_as(C.POINTER(C.c_double))
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        rc = self._lib.b200adj_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise B200AdjError(rc, self._lib.b200adj_last_error(None).decode())
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200AdjError(rc, self._lib.b200adj_last_error(self._h).decode())
+
+    def forward(self, u0, p, saved=None, status=None, dW=None):
+        self._check(self._lib.b200adj_forward(self._h, _addr(u0), _addr(p), _addr(dW), _addr(saved), _addr(status)))
+
+    def reverse(self, dLdu, du0, dp):
+        self._check(self._lib.b200adj_reverse(self._h, _addr(dLdu), _addr(du0), _addr(dp)))
+
+    def set_reverse_options(self, sensealg, cost_kind, cost_a, cost_b, flags, t=None):
+        import numpy as np
+        if t is None:
+            K, tp = -1, None
+        else:
+            self._t = np.ascontiguousarray(t, dtype=np.float64)
+            K, tp = len(self._t), self._t.ctypes.data
+        self._check(self._lib.b200adj_set_reverse_options(self._h, sensealg, cost_kind, cost_a, cost_b, flags, K, tp))
+
+    def get_noise(self, out):
+        self._check(self._lib.b200adj_get_noise(self._h, _addr(out)))
+
+    def set_stream(self, stream_ptr):
+        self._check(self._lib.b200adj_set_stream(self._h, stream_ptr))
+
+    def synchronize(self):
+        self._check(self._lib.b200adj_synchronize(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self._lib.b200adj_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            self._lib.b200adj_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

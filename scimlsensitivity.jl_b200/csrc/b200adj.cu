@@ -1,0 +1,515 @@
+// b200adj.cu -- C ABI (include/b200adj.h) of the B200-native ensemble continuous-adjoint engine.
+// Handle management, validation, host<->device staging and kernel dispatch.  No torch types, no CPU fallback.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200adj.h"
+#include "ode_tsit5.cuh"
+#include "sde_em.cuh"
+
+using namespace b200adj;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct Handle {
+    b200adj_cfg cfg;
+    std::vector<double> saveat;
+    std::vector<int32_t> save_of_step;
+    int S = 0;
+    int block = 64, grid = 0;
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    // device memory owned by the handle
+    double* d_ckpt = nullptr;         // [S+1][d][N]
+    double* d_noise = nullptr;        // [S][m][N] (SDE, stored-noise mode)
+    double* d_partials = nullptr;     // [grid][P]
+    unsigned int* d_ticket = nullptr;
+    int32_t* d_save_of_step = nullptr;
+    // staging (buffers_on_device == 0)
+    double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
+    int32_t* s_status = nullptr;
+    const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
+    bool have_forward = false;
+    bool noise_valid = false;
+    int64_t launches = 0;
+    std::string err;
+};
+
+#define CUDA_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+            return B200ADJ_ERR_CUDA;                                                           \
+        }                                                                                      \
+    } while (0)
+
+int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
+    switch (c.rhs_family) {
+    case B200ADJ_FAM_LV: *d = 2; *P = 4; *m = 0; return 0;
+    case B200ADJ_FAM_LORENZ: *d = 3; *P = 3; *m = 0; return 0;
+    case B200ADJ_FAM_ROBERTSON: *d = 3; *P = 3; *m = 0; return 0;
+    case B200ADJ_FAM_SDE_LV: *d = 2; *P = 6; *m = 2; return 0;
+    case B200ADJ_FAM_SDE_LINEAR: *d = 2; *P = 2; *m = 2; return 0;
+    default: return -1;
+    }
+}
+
+// Tsit5 dense-output weights b_j(theta): quartics, expanded once in long double from the published factored form
+// (Tsitouras 2011) and evaluated by Horner.
+void tsit5_weights(double th, double* w) {
+    typedef long double LD;
+    static bool init = false;
+    static double R[7][5];   // coefficients of theta^0..theta^4
+    if (!init) {
+        auto mul = [](const LD* a, int na, const LD* b, int nb, LD* out) {
+            for (int i = 0; i < na + nb - 1; i++) out[i] = 0;
+            for (int i = 0; i < na; i++) for (int j = 0; j < nb; j++) out[i + j] += a[i] * b[j];
+        };
+        LD t1[2] = {0, 1};
+        {   LD a[2] = {-1.3299890189751412L, 1}, q[3] = {0.7139816917074209L, -1.4364028541716351L, 1}, x[3], y[5];
+            mul(t1, 2, a, 2, x); mul(x, 3, q, 3, y);
+            for (int i = 0; i < 5; i++) R[0][i] = (double)(-1.0530884977290216L * y[i]); }
+        auto sq_quad = [&](int row, LD c, LD s, LD wq) {      // c * th^2 * (th^2 - s th + wq)
+            R[row][0] = 0; R[row][1] = 0; R[row][2] = (double)(c * wq); R[row][3] = (double)(-c * s); R[row][4] = (double)c; };
+        auto sq_roots = [&](int row, LD c, LD r1, LD r2) {    // c * (th - r1)(th - r2) * th^2
+            R[row][0] = 0; R[row][1] = 0; R[row][2] = (double)(c * r1 * r2); R[row][3] = (double)(-c * (r1 + r2)); R[row][4] = (double)c; };
+        sq_quad(1, 0.1017L, 2.1966568338249754L, 1.2949852507374631L);
+        sq_quad(2, 2.490627285651252793L, 2.38535645472061657L, 1.57803468208092486L);
+        sq_roots(3, -16.54810288924490272L, 1.21712927295533244L, 0.61620406037800089L);
+        sq_roots(4, 47.37952196281928122L, 1.203071208372362603L, 0.658047292653547382L);
+        sq_roots(5, -34.87065786149660974L, 1.2L, 0.666666666666666667L);
+        sq_roots(6, 2.5L, 1.0L, 0.6L);
+        init = true;
+    }
+    for (int j = 0; j < 7; j++) w[j] = (((R[j][4] * th + R[j][3]) * th + R[j][2]) * th + R[j][1]) * th + R[j][0];
+}
+
+int upload_tsit5(Handle* h) {
+    Tsit5Consts c;
+    memset(&c, 0, sizeof(c));
+    const double A[7][6] = {
+        {0},
+        {0.161},
+        {-0.008480655492356989, 0.335480655492357},
+        {2.8971530571054935, -6.359448489975075, 4.3622954328695815},
+        {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},
+        {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383},
+        {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+    const double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+    memcpy(c.A, A, sizeof(A)); memcpy(c.C, C, sizeof(C));
+    for (int s = 1; s <= 4; s++) tsit5_weights(1.0 - C[s], c.Bst[s - 1]);
+    const double a = sqrt(0.6);
+    const double thq[3] = {0.5 * (1.0 - a), 0.5, 0.5 * (1.0 + a)};
+    for (int g = 0; g < 3; g++) tsit5_weights(thq[g], c.Bq[g]);
+    c.GW[0] = 5.0 / 9.0; c.GW[1] = 8.0 / 9.0; c.GW[2] = 5.0 / 9.0;
+    CUDA_TRY(h, cudaMemcpyToSymbol(c_ts, &c, sizeof(c)));
+    return 0;
+}
+
+bool is_sde(const b200adj_cfg& c) { return c.stepper == B200ADJ_ST_EM || c.stepper == B200ADJ_ST_EULER_HEUN; }
+
+// ---------------- kernel dispatch ----------------
+template <class Fam, bool SHARED_P, int BLOCK>
+void launch_fwd_t(Handle* h, const OdeFwdArgs& a) {
+    tsit5_forward_kernel<Fam, SHARED_P, BLOCK><<<h->grid, BLOCK, 0, h->stream>>>(a);
+}
+template <class Fam>
+int launch_fwd(Handle* h, const OdeFwdArgs& a) {
+    const bool sp = h->cfg.shared_p;
+    switch (h->block) {
+    case 32: sp ? launch_fwd_t<Fam, true, 32>(h, a) : launch_fwd_t<Fam, false, 32>(h, a); break;
+    case 64: sp ? launch_fwd_t<Fam, true, 64>(h, a) : launch_fwd_t<Fam, false, 64>(h, a); break;
+    case 128: sp ? launch_fwd_t<Fam, true, 128>(h, a) : launch_fwd_t<Fam, false, 128>(h, a); break;
+    default: return B200ADJ_ERR_INVALID;
+    }
+    h->launches++;
+    return 0;
+}
+template <class Fam, int SA, bool SHARED_P, int COST>
+int launch_rev_b(Handle* h, const OdeRevArgs& a) {
+    switch (h->block) {
+    case 32: tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, 32><<<h->grid, 32, 0, h->stream>>>(a); break;
+    case 64: tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, 64><<<h->grid, 64, 0, h->stream>>>(a); break;
+    case 128: tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, 128><<<h->grid, 128, 0, h->stream>>>(a); break;
+    default: return B200ADJ_ERR_INVALID;
+    }
+    h->launches++;
+    return 0;
+}
+template <class Fam, int SA>
+int launch_rev_sa(Handle* h, const OdeRevArgs& a) {
+    const bool sp = h->cfg.shared_p;
+    const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (sp) return ex ? launch_rev_b<Fam, SA, true, COST_EXPLICIT>(h, a) : launch_rev_b<Fam, SA, true, COST_AFFINE>(h, a);
+    return ex ? launch_rev_b<Fam, SA, false, COST_EXPLICIT>(h, a) : launch_rev_b<Fam, SA, false, COST_AFFINE>(h, a);
+}
+template <class Fam>
+int launch_rev(Handle* h, const OdeRevArgs& a) {
+    switch (h->cfg.sensealg) {
+    case B200ADJ_SA_INTERPOLATING: return launch_rev_sa<Fam, SA_INTERP>(h, a);
+    case B200ADJ_SA_GAUSS: return launch_rev_sa<Fam, SA_GAUSS>(h, a);
+    case B200ADJ_SA_BACKSOLVE: return launch_rev_sa<Fam, SA_BACKSOLVE>(h, a);
+    default: return B200ADJ_ERR_UNSUPPORTED;
+    }
+}
+
+template <class Fam, bool EH>
+int launch_sde_fwd_f(Handle* h, const SdeFwdArgs& a) {
+    const bool sp = h->cfg.shared_p;
+    switch (h->block) {
+    case 32: sp ? sde_forward_kernel<Fam, EH, true, 32><<<h->grid, 32, 0, h->stream>>>(a) : sde_forward_kernel<Fam, EH, false, 32><<<h->grid, 32, 0, h->stream>>>(a); break;
+    case 64: sp ? sde_forward_kernel<Fam, EH, true, 64><<<h->grid, 64, 0, h->stream>>>(a) : sde_forward_kernel<Fam, EH, false, 64><<<h->grid, 64, 0, h->stream>>>(a); break;
+    case 128: sp ? sde_forward_kernel<Fam, EH, true, 128><<<h->grid, 128, 0, h->stream>>>(a) : sde_forward_kernel<Fam, EH, false, 128><<<h->grid, 128, 0, h->stream>>>(a); break;
+    default: return B200ADJ_ERR_INVALID;
+    }
+    h->launches++;
+    return 0;
+}
+template <class Fam, bool EH, bool SHARED_P, int COST>
+int launch_sde_rev_b(Handle* h, const SdeRevArgs& a) {
+    switch (h->block) {
+    case 32: sde_backsolve_kernel<Fam, EH, SHARED_P, COST, 32><<<h->grid, 32, 0, h->stream>>>(a); break;
+    case 64: sde_backsolve_kernel<Fam, EH, SHARED_P, COST, 64><<<h->grid, 64, 0, h->stream>>>(a); break;
+    case 128: sde_backsolve_kernel<Fam, EH, SHARED_P, COST, 128><<<h->grid, 128, 0, h->stream>>>(a); break;
+    default: return B200ADJ_ERR_INVALID;
+    }
+    h->launches++;
+    return 0;
+}
+template <class Fam, bool EH>
+int launch_sde_rev_f(Handle* h, const SdeRevArgs& a) {
+    const bool sp = h->cfg.shared_p;
+    const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (sp) return ex ? launch_sde_rev_b<Fam, EH, true, COST_EXPLICIT>(h, a) : launch_sde_rev_b<Fam, EH, true, COST_AFFINE>(h, a);
+    return ex ? launch_sde_rev_b<Fam, EH, false, COST_EXPLICIT>(h, a) : launch_sde_rev_b<Fam, EH, false, COST_AFFINE>(h, a);
+}
+
+size_t esz(const b200adj_cfg&) { return sizeof(double); }
+
+void free_all(Handle* h) {
+    cudaSetDevice(h->cfg.device);
+    cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
+    cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
+    cudaFree(h->s_status);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t b200adj_version(void) { return 0x000100u; }
+
+const char* b200adj_last_error(void* handle) {
+    if (!handle) return g_create_error.c_str();
+    return ((Handle*)handle)->err.c_str();
+}
+
+int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
+    if (!cfg || !handle) { g_create_error = "null cfg/handle"; return B200ADJ_ERR_INVALID; }
+    *handle = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || cfg->device < 0 || cfg->device >= ndev) {
+        g_create_error = "no usable CUDA device (libb200adj has no CPU fallback)";
+        return B200ADJ_ERR_NO_DEVICE;
+    }
+    int d, P, m;
+    if (fam_dims(*cfg, &d, &P, &m)) { g_create_error = "rhs_family not built (MLP / unknown)"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (cfg->d != d || cfg->P != P) { g_create_error = "cfg.d / cfg.P do not match rhs_family"; return B200ADJ_ERR_INVALID; }
+    if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || !(cfg->dt > 0) || !(cfg->t1 > cfg->t0)) {
+        g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
+    if (cfg->dtype != B200ADJ_F64) { g_create_error = "dtype: only F64 is built for this family"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (cfg->cost_kind != B200ADJ_COST_EXPLICIT && cfg->cost_kind != B200ADJ_COST_AFFINE) { g_create_error = "bad cost_kind"; return B200ADJ_ERR_INVALID; }
+    const bool sde = is_sde(*cfg);
+    if (sde) {
+        if (m == 0) { g_create_error = "SDE stepper needs an SDE family"; return B200ADJ_ERR_INVALID; }
+        if (cfg->sensealg != B200ADJ_SA_BACKSOLVE) { g_create_error = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    } else {
+        if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
+        if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (cfg->sensealg == B200ADJ_SA_QUADRATURE) { g_create_error = "QuadratureAdjoint not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (cfg->sensealg < 0 || cfg->sensealg > 3) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
+    }
+    // fixed-step grid: the horizon must be a whole number of steps and every save time must be a grid point.
+    // (Off-grid tstops split a step in the reference; that case is delegated back to the reference path.)
+    const double span = cfg->t1 - cfg->t0;
+    const double Sf = span / cfg->dt;
+    const long long S = llround(Sf);
+    if (S < 1 || S > 2000000000LL || fabs(S * cfg->dt - span) > 1e-9 * fmax(1.0, fabs(span))) {
+        g_create_error = "(t1-t0) is not a whole number of dt steps"; return B200ADJ_ERR_UNSUPPORTED; }
+    std::vector<int32_t> sos((size_t)S + 1, -1);
+    for (int k = 0; k < cfg->K; k++) {
+        const double tk = cfg->saveat[k];
+        const long long n = llround((tk - cfg->t0) / cfg->dt);
+        if (n < 0 || n > S || fabs(cfg->t0 + n * cfg->dt - tk) > 1e-9 * fmax(1.0, fabs(tk))) {
+            g_create_error = "saveat entry is not on the dt grid"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (sos[n] != -1) { g_create_error = "duplicate save times are not supported"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (k > 0 && !(tk > cfg->saveat[k - 1])) { g_create_error = "saveat must be ascending"; return B200ADJ_ERR_INVALID; }
+        sos[n] = k;
+    }
+    int block = cfg->block_threads ? cfg->block_threads : 64;
+    if (block != 32 && block != 64 && block != 128) { g_create_error = "block_threads must be 32, 64 or 128"; return B200ADJ_ERR_INVALID; }
+
+    Handle* h = new Handle();
+    h->cfg = *cfg; h->cfg.m = m;
+    h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
+    h->cfg.saveat = h->saveat.data();
+    h->save_of_step = sos;
+    h->S = (int)S; h->block = block;
+    h->grid = (int)((cfg->N + block - 1) / block);
+#define CREATE_TRY(expr)                                                                         \
+    do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                                       \
+        g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+        int32_t rc = (_e == cudaErrorMemoryAllocation) ? B200ADJ_ERR_OOM : B200ADJ_ERR_CUDA;     \
+        free_all(h); delete h; return rc; } } while (0)
+    CREATE_TRY(cudaSetDevice(cfg->device));
+    CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const size_t N = (size_t)cfg->N, e = esz(*cfg);
+    CREATE_TRY(cudaMalloc(&h->d_ckpt, ((size_t)S + 1) * d * N * e));
+    CREATE_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * P * sizeof(double)));
+    CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+    CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+    CREATE_TRY(cudaMalloc(&h->d_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
+    CREATE_TRY(cudaMemcpy(h->d_save_of_step, sos.data(), ((size_t)S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    if (sde) CREATE_TRY(cudaMalloc(&h->d_noise, (size_t)S * m * N * e));
+    if (!cfg->buffers_on_device) {
+        const size_t pn = cfg->shared_p ? (size_t)P : (size_t)P * N;
+        CREATE_TRY(cudaMalloc(&h->s_u0, d * N * e));
+        CREATE_TRY(cudaMalloc(&h->s_p, pn * e));
+        CREATE_TRY(cudaMalloc(&h->s_du0, d * N * e));
+        CREATE_TRY(cudaMalloc(&h->s_dp, pn * e));
+        CREATE_TRY(cudaMalloc(&h->s_status, N * sizeof(int32_t)));
+        if (cfg->K > 0) {
+            CREATE_TRY(cudaMalloc(&h->s_saved, (size_t)cfg->K * d * N * e));
+            if (cfg->cost_kind == B200ADJ_COST_EXPLICIT) CREATE_TRY(cudaMalloc(&h->s_dLdu, (size_t)cfg->K * d * N * e));
+        }
+    }
+#undef CREATE_TRY
+    if (!sde) { int rc = upload_tsit5(h); if (rc) { g_create_error = h->err; free_all(h); delete h; return rc; } }
+    *handle = h;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost_kind, double cost_a, double cost_b,
+                                    uint32_t flags, int32_t K, const double* t) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    b200adj_cfg& c = h->cfg;
+    if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
+    if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE) { h->err = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (!is_sde(c) && sensealg == B200ADJ_SA_QUADRATURE && c.stepper == B200ADJ_ST_TSIT5_FIXED && false) { h->err = "unsupported"; return B200ADJ_ERR_UNSUPPORTED; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    if (K >= 0) {
+        if (K > 0 && !t) { h->err = "null t"; return B200ADJ_ERR_INVALID; }
+        std::vector<int32_t> sos((size_t)h->S + 1, -1);
+        for (int k = 0; k < K; k++) {
+            const long long n = llround((t[k] - c.t0) / c.dt);
+            if (n < 0 || n > h->S || fabs(c.t0 + n * c.dt - t[k]) > 1e-9 * fmax(1.0, fabs(t[k]))) { h->err = "t entry is not on the dt grid"; return B200ADJ_ERR_UNSUPPORTED; }
+            if (sos[n] != -1) { h->err = "duplicate save times are not supported"; return B200ADJ_ERR_UNSUPPORTED; }
+            sos[n] = k;
+        }
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        CUDA_TRY(h, cudaMemcpy(h->d_save_of_step, sos.data(), sos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        h->save_of_step = sos;
+        h->saveat.assign(t, t + K);
+        c.saveat = h->saveat.data();
+        if (!c.buffers_on_device && K > c.K) {
+            cudaFree(h->s_dLdu); h->s_dLdu = nullptr;
+        }
+        if (!c.buffers_on_device && cost_kind == B200ADJ_COST_EXPLICIT && K > 0 && !h->s_dLdu)
+            CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)K * c.d * (size_t)c.N * esz(c)));
+        c.K = K;
+    } else if (!c.buffers_on_device && cost_kind == B200ADJ_COST_EXPLICIT && c.K > 0 && !h->s_dLdu) {
+        CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)c.K * c.d * (size_t)c.N * esz(c)));
+    }
+    c.sensealg = sensealg; c.cost_kind = cost_kind; c.cost_a = cost_a; c.cost_b = cost_b;
+    c.flags = (c.flags & B200ADJ_FLAG_STORED_NOISE) | (flags & ~B200ADJ_FLAG_STORED_NOISE);
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_stream(void* handle, void* cuda_stream) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_synchronize(void* handle) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return B200ADJ_OK;
+}
+
+int64_t b200adj_launch_count(void* handle) { return handle ? ((Handle*)handle)->launches : -1; }
+
+int32_t b200adj_get_step_counts(void* handle, int32_t*, int32_t*) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    ((Handle*)handle)->err = "fixed-step handle: step count is S for every member";
+    return B200ADJ_ERR_UNSUPPORTED;
+}
+
+int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void* dW_in, void* saved, int32_t* status) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    if (!u0 || !p) { h->err = "null u0/p"; return B200ADJ_ERR_INVALID; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    const size_t N = (size_t)c.N, e = esz(c);
+    const size_t pn = c.shared_p ? (size_t)c.P : (size_t)c.P * N;
+    const double *du0 = (const double*)u0, *dp = (const double*)p;
+    double* dsaved = (double*)saved;
+    int32_t* dstatus = status;
+    if (!c.buffers_on_device) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->s_u0, u0, c.d * N * e, cudaMemcpyHostToDevice, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(h->s_p, p, pn * e, cudaMemcpyHostToDevice, h->stream));
+        du0 = h->s_u0; dp = h->s_p;
+        dsaved = (saved && c.K > 0) ? h->s_saved : nullptr;
+        dstatus = status ? h->s_status : nullptr;
+    }
+    h->cur_p = dp;
+    int rc = 0;
+    if (!is_sde(c)) {
+        OdeFwdArgs a;
+        a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
+        a.status = dstatus; a.N = c.N; a.S = h->S; a.h = c.dt;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_fwd<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_fwd<Lorenz>(h, a); break;
+        case B200ADJ_FAM_ROBERTSON: rc = launch_fwd<Robertson>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    } else {
+        SdeFwdArgs a;
+        a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
+        a.status = dstatus; a.N = c.N; a.S = h->S; a.h = c.dt; a.seed = c.seed; a.traj_offset = c.traj_offset;
+        // noise: (1) caller-supplied increments (parity tests, reference-style NoiseGrid) are copied into the handle;
+        // (2) STORED_NOISE: Philox increments are written out by the forward kernel; (3) default: Philox, regenerated
+        // by the reverse kernel (no HBM traffic for the noise).
+        a.noise_in = nullptr; a.noise_out = nullptr;
+        if (dW_in) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->d_noise, dW_in, (size_t)h->S * c.m * N * e,
+                                        c.buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+            a.noise_in = h->d_noise; h->noise_valid = true;
+        } else if (c.flags & B200ADJ_FLAG_STORED_NOISE) {
+            a.noise_out = h->d_noise; h->noise_valid = true;
+        } else {
+            h->noise_valid = false;
+        }
+        const bool eh = c.stepper == B200ADJ_ST_EULER_HEUN;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_fwd_f<SdeLotkaVolterra<false>, true>(h, a) : launch_sde_fwd_f<SdeLotkaVolterra<false>, false>(h, a); break;
+        case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_fwd_f<SdeLinear2<false>, true>(h, a) : launch_sde_fwd_f<SdeLinear2<false>, false>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    }
+    if (rc) { h->err = "forward dispatch failed"; return rc; }
+    CUDA_TRY(h, cudaGetLastError());
+    if (!c.buffers_on_device) {
+        if (saved && c.K > 0) CUDA_TRY(h, cudaMemcpyAsync(saved, h->s_saved, (size_t)c.K * c.d * N * e, cudaMemcpyDeviceToHost, h->stream));
+        if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->s_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    h->have_forward = true;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    if (!h->have_forward) { h->err = "reverse called before forward"; return B200ADJ_ERR_STATE; }
+    if (!du0 || !dp) { h->err = "null du0/dp"; return B200ADJ_ERR_INVALID; }
+    if (c.cost_kind == B200ADJ_COST_EXPLICIT && c.K > 0 && !dLdu) { h->err = "COST_EXPLICIT needs dLdu"; return B200ADJ_ERR_INVALID; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    const size_t N = (size_t)c.N, e = esz(c);
+    const size_t pn = c.shared_p ? (size_t)c.P : (size_t)c.P * N;
+    const double* dL = (const double*)dLdu;
+    double *ddu0 = (double*)du0, *ddp = (double*)dp;
+    if (!c.buffers_on_device) {
+        if (c.cost_kind == B200ADJ_COST_EXPLICIT && c.K > 0) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->s_dLdu, dLdu, (size_t)c.K * c.d * N * e, cudaMemcpyHostToDevice, h->stream));
+            dL = h->s_dLdu;
+        }
+        ddu0 = h->s_du0; ddp = h->s_dp;
+    }
+    int rc = 0;
+    if (!is_sde(c)) {
+        OdeRevArgs a;
+        a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
+        a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
+        a.N = c.N; a.S = h->S; a.h = c.dt; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+        a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
+                  ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_rev<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_rev<Lorenz>(h, a); break;
+        case B200ADJ_FAM_ROBERTSON: rc = launch_rev<Robertson>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    } else {
+        SdeRevArgs a;
+        a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
+        a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
+        a.N = c.N; a.S = h->S; a.h = c.dt; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+        a.flags = ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) | ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
+        a.seed = c.seed; a.traj_offset = c.traj_offset;
+        a.noise = h->noise_valid ? h->d_noise : nullptr;
+        const bool eh = c.stepper == B200ADJ_ST_EULER_HEUN;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_rev_f<SdeLotkaVolterra<false>, true>(h, a) : launch_sde_rev_f<SdeLotkaVolterra<true>, false>(h, a); break;
+        case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_rev_f<SdeLinear2<false>, true>(h, a) : launch_sde_rev_f<SdeLinear2<true>, false>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    }
+    if (rc) { h->err = "reverse dispatch failed (sensealg/family not built)"; return rc; }
+    CUDA_TRY(h, cudaGetLastError());
+    if (!c.buffers_on_device) {
+        CUDA_TRY(h, cudaMemcpyAsync(du0, h->s_du0, c.d * N * e, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaMemcpyAsync(dp, h->s_dp, pn * e, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    }
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_get_noise(void* handle, void* dW_out) {
+    if (!handle || !dW_out) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    if (!is_sde(c) || !h->have_forward) { h->err = "no SDE forward pass to report"; return B200ADJ_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    const size_t bytes = (size_t)h->S * c.m * (size_t)c.N * esz(c);
+    if (!h->noise_valid) {
+        // regenerate from the Philox counter into the handle's buffer
+        SdeNoiseArgs a; a.out = h->d_noise; a.N = c.N; a.S = h->S; a.h = c.dt; a.seed = c.seed; a.traj_offset = c.traj_offset; a.m = c.m;
+        const int64_t total = (int64_t)h->S * c.N;
+        sde_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(a);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(dW_out, h->d_noise, bytes, c.buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_destroy(void* handle) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->stream);
+    free_all(h);
+    delete h;
+    return B200ADJ_OK;
+}
+
+}  // extern "C"

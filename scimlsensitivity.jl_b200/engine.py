@@ -1,0 +1,122 @@
+"""Host-side driver of one device handle: buffer plumbing (numpy host buffers or torch CUDA tensors), cfg assembly.
+
+PyTorch is used here only for device memory and streams (and torch.distributed in distributed.py); all arithmetic
+is in libb200adj.so.
+"""
+import numpy as np
+
+from . import _lib
+from .problems import FAMILIES, AffineCost
+
+
+def _is_torch(x):
+    return hasattr(x, "data_ptr") and hasattr(x, "device")
+
+
+class DeviceEnsemble:
+    """One ensemble shard on one GPU: forward(u0, p) -> saved, reverse(dLdu) -> (du0, dp)."""
+
+    def __init__(self, family, sensealg, stepper, N, saveat, tspan, dt, *, shared_p=True, cost=None,
+                 on_device=False, device=0, no_start=False, checkpointing=True, ckpt_every_step=False,
+                 stored_noise=False, seed=0, traj_offset=0, block_threads=0, abstol=1e-6, reltol=1e-3,
+                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64"):
+        d, P, m = FAMILIES[family]
+        cfg = _lib.Cfg()
+        cfg.rhs_family, cfg.sensealg, cfg.stepper, cfg.dtype = _lib.FAM[family], _lib.SA[sensealg], _lib.ST[stepper], _lib.DTYPE[dtype]
+        cfg.d, cfg.P, cfg.m, cfg.N = d, P, m, int(N)
+        cfg.t0, cfg.t1, cfg.dt = float(tspan[0]), float(tspan[1]), float(dt)
+        cfg.abstol, cfg.reltol, cfg.quad_abstol, cfg.quad_reltol = abstol, reltol, quad_abstol, quad_reltol
+        cfg.shared_p, cfg.buffers_on_device, cfg.device = int(shared_p), int(on_device), int(device)
+        if isinstance(cost, AffineCost):
+            cfg.cost_kind, cfg.cost_a, cfg.cost_b = _lib.COST["affine"], float(cost.a), float(cost.b)
+        else:
+            cfg.cost_kind = _lib.COST["explicit"]
+        cfg.seed, cfg.traj_offset = int(seed), int(traj_offset)
+        cfg.checkpoint_every = 1
+        flags = 0
+        if no_start:
+            flags |= _lib.FLAG_NO_START
+        if not checkpointing:
+            flags |= _lib.FLAG_NO_CHECKPOINTING
+        if ckpt_every_step:
+            flags |= _lib.FLAG_CKPT_EVERY_STEP
+        if stored_noise:
+            flags |= _lib.FLAG_STORED_NOISE
+        cfg.flags, cfg.block_threads = flags, int(block_threads)
+        self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
+        self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)
+        self.S = int(round((cfg.t1 - cfg.t0) / cfg.dt))
+        self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+        self.handle = _lib.Handle(cfg, self.saveat)
+        self._keep = []
+
+    # ---- buffers ----
+    def _empty(self, *shape, dtype="f64"):
+        if self.on_device:
+            import torch
+            return torch.empty(shape, dtype=torch.float64 if dtype == "f64" else torch.int32, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype=np.float64 if dtype == "f64" else np.int32)
+
+    def _prep(self, x, shape):
+        if self.on_device:
+            import torch
+            if not _is_torch(x):
+                x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=f"cuda:{self.device}")
+            x = x.to(dtype=torch.float64).contiguous()
+            assert tuple(x.shape) == tuple(shape), (tuple(x.shape), shape)
+            return x
+        if _is_torch(x):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == tuple(shape), (x.shape, shape)
+        return x
+
+    def use_current_torch_stream(self):
+        import torch
+        self.handle.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- passes ----
+    def forward(self, u0, p, dW=None, want_saved=True, want_status=True, saved_out=None):
+        u0 = self._prep(u0, (self.d, self.N))
+        p = self._prep(p, (self.P,) if self.shared_p else (self.P, self.N))
+        if dW is not None:
+            dW = self._prep(dW, (self.S, self.m, self.N))
+        saved = saved_out if saved_out is not None else (self._empty(self.K, self.d, self.N) if (want_saved and self.K > 0) else None)
+        status = self._empty(self.N, dtype="i32") if want_status else None
+        self._keep = [u0, p, dW]                      # p must stay alive until reverse (device mode reads it in place)
+        self.handle.forward(u0, p, saved, status, dW)
+        return saved, status
+
+    def reverse(self, dLdu=None, du0_out=None, dp_out=None):
+        if dLdu is not None:
+            dLdu = self._prep(dLdu, (self.K, self.d, self.N))
+        du0 = du0_out if du0_out is not None else self._empty(self.d, self.N)
+        dp = dp_out if dp_out is not None else (self._empty(self.P) if self.shared_p else self._empty(self.P, self.N))
+        self.handle.reverse(dLdu, du0, dp)
+        return du0, dp
+
+    def set_reverse(self, sensealg, cost=None, no_start=False, checkpointing=True, ckpt_every_step=False, t=None):
+        """Re-target the next reverse pass (sensealg / cost / save times) without re-running the forward pass."""
+        flags = 0
+        if no_start:
+            flags |= _lib.FLAG_NO_START
+        if not checkpointing:
+            flags |= _lib.FLAG_NO_CHECKPOINTING
+        if ckpt_every_step:
+            flags |= _lib.FLAG_CKPT_EVERY_STEP
+        if isinstance(cost, AffineCost):
+            ck, a, b = _lib.COST["affine"], float(cost.a), float(cost.b)
+        else:
+            ck, a, b = _lib.COST["explicit"], 0.0, 0.0
+        self.handle.set_reverse_options(_lib.SA[sensealg], ck, a, b, flags, t)
+        if t is not None:
+            self.saveat = np.ascontiguousarray(t, dtype=np.float64)
+            self.K = len(self.saveat)
+
+    def noise(self):
+        out = self._empty(self.S, self.m, self.N)
+        self.handle.get_noise(out)
+        return out
+
+    def close(self):
+        self.handle.close()

@@ -1,0 +1,138 @@
+"""Problem, algorithm and solution types on the host side.
+
+These mirror the UPSTREAM SciMLBase / OrdinaryDiffEq / StochasticDiffEq objects the reference's hot path is handed
+(ODEProblem, SDEProblem, EnsembleProblem, Tsit5(), Rosenbrock23(), EM(), EulerHeun()),
+reduced to what the device path needs.  The RHS is a NAMED family (string) instead of a Julia closure: the device
+code for f and its VJPs is hand-written per family (csrc/families.cuh), which is the plug-in seam user-supplied
+`ODEFunction(f; vjp, vjp_p)` occupies in the reference (src/derivative_wrappers.jl:284-359).
+"""
+from dataclasses import dataclass, field
+from typing import Any, Callable, Optional, Sequence
+
+import numpy as np
+
+FAMILIES = {
+    # name: (d, P, m)
+    "lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "sde_linear": (2, 2, 2),
+}
+
+
+class AdjointSensitivityParameterCompatibilityError(TypeError):
+    """src/sensitivity_interface.jl:25-29"""
+
+    def __init__(self):
+        super().__init__("Adjoint sensitivity analysis functionality requires being able to solve a differential "
+                         "equation defined by the parameter struct `p`: `p` must be a flat floating-point array "
+                         "(or None) on the B200 path")
+
+
+@dataclass
+class ODEProblem:
+    f: str                       # named RHS family
+    u0: Any
+    tspan: tuple
+    p: Any = None
+    callback: Any = None
+    mass_matrix: Any = None
+    kwargs: dict = field(default_factory=dict)
+    is_sde = False
+
+
+@dataclass
+class SDEProblem:
+    f: str                       # named drift+diffusion family (diagonal noise)
+    u0: Any
+    tspan: tuple
+    p: Any = None
+    callback: Any = None
+    seed: int = 0
+    noise: Any = None            # explicit Wiener increments dW[S][m][N] (NoiseGrid-like)
+    kwargs: dict = field(default_factory=dict)
+    is_sde = True
+
+
+@dataclass
+class EnsembleProblem:
+    """EnsembleProblem(prob; prob_func).  `prob_func(prob, i)` -> (u0_i, p_i or None) is evaluated on the host to
+    materialise u0[d, N] (and optionally p[P, N]) as in test/Core4/ensembles.jl:22-24; alternatively pass the
+    arrays directly with `u0s` / `ps`."""
+    prob: Any
+    prob_func: Optional[Callable] = None
+    u0s: Any = None              # [d, N]
+    ps: Any = None               # [P, N] per-member parameters (None => shared prob.p)
+
+
+# ---- solver algorithms ----
+@dataclass(frozen=True)
+class Tsit5:
+    adaptive: bool = False
+    dt: float = 0.0
+    code = "tsit5_fixed"
+
+
+@dataclass(frozen=True)
+class Rosenbrock23:
+    code = "rosenbrock23"
+
+
+@dataclass(frozen=True)
+class EM:
+    dt: float = 0.0
+    code = "em"
+
+
+@dataclass(frozen=True)
+class EulerHeun:
+    dt: float = 0.0
+    code = "euler_heun"
+
+
+# ---- ensemble algorithms ----
+@dataclass(frozen=True)
+class EnsembleB200:
+    """Batched device solve of the whole ensemble (the dispatch the reference lacks; SURVEY.md finding 2).
+    With torch.distributed initialised the members are sharded contiguously over ranks (one process per GPU)."""
+    device: Optional[int] = None
+    buffers_on_device: Optional[bool] = None   # None: infer from the input arrays
+    reuse_handle: bool = False                 # keep ONE device handle per configuration across solve() calls (the
+                                               # previous solution's checkpoints are overwritten by the next solve)
+
+
+@dataclass
+class EnsembleSolution:
+    """Result of `solve(EnsembleProblem, alg, EnsembleB200(); ...)`: u[K, d, N] at ts[K] (sensitivity_solution)."""
+    prob: Any
+    alg: Any
+    t: np.ndarray
+    u: Any
+    retcode: Any = None          # int32[N]: 0 = Success, 1 = Unstable (non-finite)
+    dense: bool = True
+    engine: Any = None           # live device handle (checkpoints) for the reverse pass
+    u0: Any = None
+    p: Any = None
+
+    def __len__(self):
+        return self.u.shape[-1]
+
+
+@dataclass(frozen=True)
+class AffineCost:
+    """dgdu_discrete(out, u, p, t, i) = a*u + b evaluated in-kernel; `dg(out,u,p,t,i) = out .= u .- 2`
+    (test/Core3/adjoint.jl:1169-1171) is AffineCost(1.0, -2.0).  Loss = sum_k sum_j (a/2 u^2 + b u)."""
+    a: float = 0.0
+    b: float = 1.0
+
+
+def saveat_to_times(saveat, tspan):
+    """saveat::Number -> t0:saveat:t1 with the end point appended (src/concrete_solve.jl:718-725, 2827-2831);
+    arrays are sorted (:752-756)."""
+    t0, t1 = float(tspan[0]), float(tspan[1])
+    if np.isscalar(saveat):
+        n = int(np.floor((t1 - t0) / saveat * (1 + 1e-12)))
+        ts = t0 + saveat * np.arange(n + 1)
+        if abs(ts[-1] - t1) > 1e-12 * max(1.0, abs(t1)):
+            ts = np.append(ts, t1)
+        else:
+            ts[-1] = t1
+        return ts
+    return np.sort(np.asarray(saveat, dtype=np.float64))

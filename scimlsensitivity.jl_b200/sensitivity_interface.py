@@ -1,0 +1,74 @@
+"""Direct interface: adjoint_sensitivities(sol, alg; t, dgdu_discrete, sensealg, ...) -> (du0, dp).
+
+Mirrors /root/reference/src/sensitivity_interface.jl:373-526 (and the Gauss / Quadrature twins
+src/gauss_adjoint.jl:766-870, src/quadrature_adjoint.jl:510-633) for an ensemble solution produced by
+`solve(EnsembleProblem, alg, EnsembleB200(); ...)`: same keyword names, same defaults, same return convention
+(`du0`, and `dp` as a ROW: shape (1, P) for shared parameters, like the reference's `dp'`,
+src/sensitivity_interface.jl:503-507).  For an ensemble `du0` is [d, N]; with per-member parameters `dp` is [P, N].
+"""
+import numpy as np
+
+from .problems import AdjointSensitivityParameterCompatibilityError, AffineCost
+from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, InterpolatingAdjoint,
+                                     QuadratureAdjoint, sensealg_name)
+
+
+def _check_params(p):
+    """src/sensitivity_interface.jl:438-443"""
+    if p is None:
+        raise ValueError("Your model does not have parameters, and thus it is impossible to calculate the derivative "
+                         "of the solution with respect to the parameters.")
+    if hasattr(p, "dtype"):
+        if "float" not in str(p.dtype):
+            raise AdjointSensitivityParameterCompatibilityError()
+        return
+    try:
+        arr = np.asarray(p)
+    except Exception:
+        raise AdjointSensitivityParameterCompatibilityError()
+    if arr.dtype.kind != "f":
+        raise AdjointSensitivityParameterCompatibilityError()
+
+
+def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete=None, dgdp_discrete=None,
+                          dgdu_continuous=None, dgdp_continuous=None, g=None, no_start=False,
+                          abstol=1.0e-6, reltol=1.0e-3, checkpoints=None, corfunc_analytical=None, callback=None,
+                          row_dp=True, **kwargs):
+    """dgdu_discrete: an `AffineCost` (evaluated in-kernel) or an array Delta[K, d, N] of cotangents at `t`."""
+    if sensealg is None:
+        sensealg = InterpolatingAdjoint()          # reference default (src/sensitivity_interface.jl:375)
+    inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else sensealg
+    if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint)):
+        raise TypeError("adjoint_sensitivities: sensealg must be one of the continuous adjoints")
+    if callback is not None or getattr(sol.prob.prob if hasattr(sol.prob, "prob") else sol.prob, "callback", None) is not None:
+        raise NotImplementedError("callbacks/events are not supported on the B200 path (SURVEY.md App. E): "
+                                  "delegate to the reference implementation")
+    if dgdu_continuous is not None or dgdp_continuous is not None or g is not None:
+        raise NotImplementedError("continuous cost functionals are not built on the B200 path yet")
+    if dgdp_discrete is not None:
+        raise NotImplementedError("dgdp_discrete is not built on the B200 path yet")
+    if dgdu_discrete is None:
+        # src/interpolating_adjoint.jl:321-326
+        raise ValueError("Either `dgdu_discrete`, `dgdp_discrete`, `dgdu_continuous`, `dgdp_continuous`, or `g` "
+                         "must be specified.")
+    _check_params(sol.p)
+    eng = sol.engine
+    if eng is None:
+        raise RuntimeError("solution carries no live device handle")
+    ts = sol.t if t is None else np.asarray(t, dtype=np.float64)
+    name = sensealg_name(inner)
+    # Backsolve through the direct interface: checkpoints default to sol.t = every forward step
+    # (src/sensitivity_interface.jl:433); pass `checkpoints=ts` for the rrule behaviour.
+    every = False
+    checkpointing = True
+    if isinstance(inner, BacksolveAdjoint):
+        checkpointing = inner.checkpointing
+        every = checkpoints is None
+    cost = dgdu_discrete if isinstance(dgdu_discrete, AffineCost) else None
+    eng.set_reverse(name, cost=cost, no_start=no_start, checkpointing=checkpointing, ckpt_every_step=every, t=ts)
+    du0, dp = eng.reverse(None if cost is not None else dgdu_discrete)
+    from .distributed import allreduce_dp
+    dp = allreduce_dp(dp, eng)
+    if row_dp and eng.shared_p:
+        dp = dp.reshape(1, -1)
+    return du0, dp
