@@ -50,7 +50,7 @@ def peaks():
 
 class ClockSampler:
     """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
@@ -59,12 +59,14 @@ class ClockSampler:
     def start(self):
         try:
             self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.device)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """t_begin/t_end: wall-clock (time.time()) bounds of the timed region; samples outside are dropped."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -80,6 +82,10 @@ class ClockSampler:
             if len(c) < 9:
                 continue
             try:
+                if t_begin is not None:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    if ts < t_begin - 0.02 or ts > t_end + 0.02:
+                        continue
                 sm.append(float(c[1])); mx.append(float(c[2]))
             except ValueError:
                 continue
@@ -181,15 +187,16 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        step_device()
-    barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
     launches0 = eng.handle.launch_count
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
     barrier()
+    wall0 = time.time()
     ev[0].record()
     for i in range(args.steps):
         eng.handle.forward(u0_d, p_d, None, None, None)
@@ -200,11 +207,12 @@ def run_ours(args):
             dist.all_reduce(dp_d)
         ev[3 * i + 3].record()
     barrier()
+    wall1 = time.time()
     total_ms = ev[0].elapsed_time(ev[-1])
     fwd_ms = float(np.mean([ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)]))
     rev_ms = float(np.mean([ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)]))
     launches = eng.handle.launch_count - launches0 + (args.steps if world > 1 else 0)
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     t = torch.tensor([total_ms, fwd_ms, rev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -284,7 +292,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members", type=int, default=0, help="override members per GPU (default 65536) / reference sample")

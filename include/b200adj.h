@@ -112,7 +112,9 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
 /* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
 int32_t b200adj_get_noise(void* handle, void* dW_out);
 
-/* run on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's private stream) */
+/* run on a caller-owned CUDA stream (cudaStream_t passed as void*; NULL = the handle's private non-blocking stream;
+ * pass cudaStreamLegacy (0x1) for the legacy default stream).  With buffers_on_device=1 every call is asynchronous on
+ * that stream; with host buffers forward/reverse return after their D2H copies completed. */
 int32_t b200adj_set_stream(void* handle, void* cuda_stream);
 /* block until all work queued by this handle has finished */
 int32_t b200adj_synchronize(void* handle);

@@ -49,6 +49,10 @@ class DeviceEnsemble:
         self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
         self.handle = _lib.Handle(cfg, self.saveat)
         self._keep = []
+        if self.on_device:
+            # device-pointer mode is asynchronous: run on torch's current stream so tensor producers/consumers order
+            # correctly with the kernels (host-buffer mode synchronises inside the C ABI instead)
+            self.use_current_torch_stream()
 
     # ---- buffers ----
     def _empty(self, *shape, dtype="f64"):
@@ -73,7 +77,8 @@ class DeviceEnsemble:
 
     def use_current_torch_stream(self):
         import torch
-        self.handle.set_stream(torch.cuda.current_stream(self.device).cuda_stream)
+        ptr = torch.cuda.current_stream(self.device).cuda_stream
+        self.handle.set_stream(ptr if ptr else 1)          # 0 is the legacy default stream: pass cudaStreamLegacy (0x1)
 
     # ---- passes ----
     def forward(self, u0, p, dW=None, want_saved=True, want_status=True, saved_out=None):
