@@ -33,7 +33,7 @@ enum {
     B200ADJ_FAM_LORENZ = 1,     /* Lorenz d=3 P=3           (test/Core3/adjoint.jl:1160-1167)                  */
     B200ADJ_FAM_ROBERTSON = 2,  /* Robertson d=3 P=3        (test/Core2/stiff_adjoints.jl:256-263, 3-param)    */
     B200ADJ_FAM_SDE_LV = 3,     /* LV drift + diag noise g_i = p[4+i] u_i, d=2 P=6 m=2 (Core1/...:737-760)      */
-    B200ADJ_FAM_MLP = 4,        /* 2 -> H -> H -> 2 tanh MLP (docs/src/Benchmark.md:49-52), P = H*H+7H+2        */
+    B200ADJ_FAM_MLP = 4,        /* 2 -> H -> H -> 2 tanh MLP (docs/src/Benchmark.md:49-52), P = H*H+6H+2        */
     B200ADJ_FAM_SDE_LINEAR = 5  /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
 };
 /* sensealg: which *SensitivityFunction / driver is run (src/sensitivity_algorithms.jl:254-278,378-405,486-510,591-611) */
@@ -126,6 +126,7 @@ int32_t b200adj_get_step_counts(void* handle, int32_t* fwd_steps, int32_t* rev_s
 int32_t b200adj_destroy(void* handle);
 const char* b200adj_last_error(void* handle);   /* handle may be NULL: last create() error of this thread */
 uint32_t b200adj_version(void);                 /* 0xMMmmpp */
+uint32_t b200adj_sizeof_cfg(void);              /* sizeof(b200adj_cfg): lets a binding verify its struct mirror */
 
 #ifdef __cplusplus
 }

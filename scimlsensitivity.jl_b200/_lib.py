@@ -23,7 +23,7 @@ ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -
 
 EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_destroy",
-           "b200adj_last_error", "b200adj_version"]
+           "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg"]
 
 
 class B200AdjError(RuntimeError):
@@ -105,6 +105,9 @@ def load():
         lib.b200adj_last_error.argtypes = [C.c_void_p]
         lib.b200adj_last_error.restype = C.c_char_p
         lib.b200adj_version.restype = C.c_uint32
+        lib.b200adj_sizeof_cfg.restype = C.c_uint32
+        if lib.b200adj_sizeof_cfg() != C.sizeof(Cfg):
+            raise ImportError(f"b200adj_cfg layout mismatch: C {lib.b200adj_sizeof_cfg()} vs ctypes {C.sizeof(Cfg)}")
         _lib = lib
     return _lib
 

@@ -207,6 +207,7 @@ void free_all(Handle* h) {
 extern "C" {
 
 uint32_t b200adj_version(void) { return 0x000100u; }
+uint32_t b200adj_sizeof_cfg(void) { return (uint32_t)sizeof(b200adj_cfg); }
 
 const char* b200adj_last_error(void* handle) {
     if (!handle) return g_create_error.c_str();

@@ -1,0 +1,111 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/b200adj.h declares (no compute calls
+without a GPU), the product path fails loudly without a device, and the host layer mirrors the reference's plugin
+surface (names, defaults, error behaviour)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import scimlsensitivity_jl_b200 as b
+from scimlsensitivity_jl_b200 import _lib
+from scimlsensitivity_jl_b200.problems import saveat_to_times
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "b200adj.h")).read()
+    declared = set(re.findall(r"\b(b200adj_[a-z_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    lib = _lib.load()
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.b200adj_version() >= 0x000100
+
+
+def test_cfg_struct_layout_matches_header():
+    """The ctypes mirror must have the C struct's size: 8-byte alignment, 4 x int32 at the end."""
+    hdr = open(os.path.join(ROOT, "include", "b200adj.h")).read()
+    body = hdr[hdr.index("typedef struct b200adj_cfg {"):hdr.index("} b200adj_cfg;")]
+    names = re.findall(r"(\w+)\s*(?:,|;)", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
+    fields = [n for n, _ in _lib.Cfg._fields_]
+    assert [n for n in names if n in fields] == fields
+    assert C.sizeof(_lib.Cfg) == _lib.load().b200adj_sizeof_cfg() == 168
+
+
+@pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")
+def test_no_cpu_fallback_without_device():
+    with pytest.raises(b.B200AdjError) as ei:
+        b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", 8, np.linspace(0, 1, 11), (0.0, 1.0), 0.01)
+    assert ei.value.code == -3 and "no CPU fallback" in str(ei.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "scimlsensitivity.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "liboracle" not in txt and "adjoint_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_sensealg_structs_mirror_reference_defaults():
+    # src/sensitivity_algorithms.jl:254-278, 378-405, 486-510, 591-611
+    assert b.BacksolveAdjoint().checkpointing is True and b.BacksolveAdjoint().noisemixing is False
+    assert b.InterpolatingAdjoint().checkpointing is False
+    q = b.QuadratureAdjoint()
+    assert (q.abstol, q.reltol) == (1e-6, 1e-3)
+    assert b.GaussAdjoint().checkpointing is False
+    for A in (b.BacksolveAdjoint, b.InterpolatingAdjoint, b.QuadratureAdjoint, b.GaussAdjoint):
+        a = A()
+        assert a.autojacvec is None and b.get_chunksize(a) == 0 and b.alg_autodiff(a) is True and b.diff_type(a) == "central"
+        a2 = b.setvjp(a, b.ReverseDiffVJP(True))
+        assert a2.autojacvec == b.ReverseDiffVJP(True) and type(a2) is A and b.get_jacvec(a2) is True
+    w = b.B200Adjoint(b.GaussAdjoint())
+    assert b.setvjp(w, b.B200VJP()).inner.autojacvec == b.B200VJP()
+    assert b.ischeckpointing(b.BacksolveAdjoint()) and not b.ischeckpointing(b.InterpolatingAdjoint())
+    assert b.isnoisemixing(b.BacksolveAdjoint(noisemixing=True))
+    with pytest.raises(TypeError):
+        b.B200Adjoint(inner="nope")
+
+
+def test_saveat_semantics():
+    # saveat::Number -> t0:saveat:t1 (+ end point) src/concrete_solve.jl:718-725
+    ts = saveat_to_times(0.1, (0.0, 10.0))
+    assert len(ts) == 101 and ts[0] == 0.0 and ts[-1] == 10.0
+    ts = saveat_to_times(0.3, (0.0, 1.0))
+    assert np.allclose(ts, [0.0, 0.3, 0.6, 0.9, 1.0])
+    assert np.array_equal(saveat_to_times([0.5, 0.1, 0.3], (0.0, 1.0)), [0.1, 0.3, 0.5])     # sorted (:752-756)
+
+
+def test_parameter_compatibility_errors():
+    # src/sensitivity_interface.jl:25-29 / src/concrete_solve.jl:544-549
+    prob = b.EnsembleProblem(b.ODEProblem("lorenz", [1.0, 0, 0], (0.0, 1.0), np.array([10, 28, 3])), u0s=np.ones((3, 4)))
+    with pytest.raises(b.AdjointSensitivityParameterCompatibilityError):
+        b.solve(prob, b.Tsit5(dt=0.01), saveat=0.1)
+    prob = b.EnsembleProblem(b.ODEProblem("lorenz", [1.0, 0, 0], (0.0, 1.0), None), u0s=np.ones((3, 4)))
+    with pytest.raises(ValueError):
+        b.solve(prob, b.Tsit5(dt=0.01), saveat=0.1)
+    prob = b.EnsembleProblem(b.ODEProblem("lorenz", [1.0, 0, 0], (0.0, 1.0), np.ones(3), callback=object()), u0s=np.ones((3, 4)))
+    with pytest.raises(NotImplementedError):
+        b.solve(prob, b.Tsit5(dt=0.01), saveat=0.1)
+    prob = b.EnsembleProblem(b.ODEProblem("lorenz", [1.0, 0, 0], (0.0, 1.0), np.ones(3)), u0s=np.ones((3, 4)))
+    with pytest.raises(NotImplementedError):
+        b.solve(prob, b.Tsit5(adaptive=True), saveat=0.1)
+    with pytest.raises(KeyError):
+        b.solve(b.EnsembleProblem(b.ODEProblem("nope", [1.0], (0.0, 1.0), np.ones(3)), u0s=np.ones((1, 4))), b.Tsit5(dt=0.01), saveat=0.1)
+
+
+def test_shard_bounds_partition():
+    N = 65537
+    for G in (1, 2, 3, 8):
+        b_ = [b.shard_bounds(N, g, G) for g in range(G)]
+        assert b_[0][0] == 0 and b_[-1][1] == N and all(b_[i][1] == b_[i + 1][0] for i in range(G - 1))
+        assert max(h - l for l, h in b_) - min(h - l for l, h in b_) <= 1
