@@ -11,7 +11,7 @@ import subprocess
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
-LIB_PATH = os.path.join(_PKG, "libb200adj.so")
+LIB_PATH = os.environ.get("B200ADJ_LIB", os.path.join(_PKG, "libb200adj.so"))   # env override: tuning experiments only
 
 FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5}
 SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3}

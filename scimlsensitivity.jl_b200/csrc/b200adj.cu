@@ -24,6 +24,7 @@ struct Handle {
     std::vector<double> saveat;
     std::vector<int32_t> save_of_step;
     int S = 0;
+    int64_t Npad = 0;
     int block = 64, grid = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // device memory owned by the handle
@@ -39,6 +40,7 @@ struct Handle {
     bool have_forward = false;
     bool noise_valid = false;
     int64_t launches = 0;
+    Tsit5Tables tb;
     std::string err;
 };
 
@@ -92,9 +94,8 @@ void tsit5_weights(double th, double* w) {
     for (int j = 0; j < 7; j++) w[j] = (((R[j][4] * th + R[j][3]) * th + R[j][2]) * th + R[j][1]) * th + R[j][0];
 }
 
-int upload_tsit5(Handle* h) {
-    Tsit5Consts c;
-    memset(&c, 0, sizeof(c));
+// Step-size-scaled Tsit5 tables for one handle (passed to the kernels by value, i.e. through the constant bank).
+void build_tsit5_tables(double h, Tsit5Tables* t) {
     const double A[7][6] = {
         {0},
         {0.161},
@@ -104,14 +105,14 @@ int upload_tsit5(Handle* h) {
         {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383},
         {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
     const double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
-    memcpy(c.A, A, sizeof(A)); memcpy(c.C, C, sizeof(C));
-    for (int s = 1; s <= 4; s++) tsit5_weights(1.0 - C[s], c.Bst[s - 1]);
+    memset(t, 0, sizeof(*t));
+    for (int s = 0; s < 7; s++) for (int j = 0; j < 6; j++) t->hA[s][j] = h * A[s][j];
+    double w[7];
+    for (int s = 1; s <= 4; s++) { tsit5_weights(1.0 - C[s], w); for (int j = 0; j < 7; j++) t->hBst[s - 1][j] = h * w[j]; }
     const double a = sqrt(0.6);
     const double thq[3] = {0.5 * (1.0 - a), 0.5, 0.5 * (1.0 + a)};
-    for (int g = 0; g < 3; g++) tsit5_weights(thq[g], c.Bq[g]);
-    c.GW[0] = 5.0 / 9.0; c.GW[1] = 8.0 / 9.0; c.GW[2] = 5.0 / 9.0;
-    CUDA_TRY(h, cudaMemcpyToSymbol(c_ts, &c, sizeof(c)));
-    return 0;
+    for (int g = 0; g < 3; g++) { tsit5_weights(thq[g], w); for (int j = 0; j < 7; j++) t->hBq[g][j] = h * w[j]; }
+    t->hGW[0] = 0.5 * h * (5.0 / 9.0); t->hGW[1] = 0.5 * h * (8.0 / 9.0); t->hGW[2] = 0.5 * h * (5.0 / 9.0);
 }
 
 bool is_sde(const b200adj_cfg& c) { return c.stepper == B200ADJ_ST_EM || c.stepper == B200ADJ_ST_EULER_HEUN; }
@@ -275,7 +276,9 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     h->stream = h->own_stream;
     const size_t N = (size_t)cfg->N, e = esz(*cfg);
-    CREATE_TRY(cudaMalloc(&h->d_ckpt, ((size_t)S + 1) * d * N * e));
+    const size_t Npad = ((N + block - 1) / block) * block;     // padded checkpoint pitch (whole TMA rows per block)
+    h->Npad = (int64_t)Npad;
+    CREATE_TRY(cudaMalloc(&h->d_ckpt, ((size_t)S + 1) * d * Npad * e));
     CREATE_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * P * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
     CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
@@ -295,7 +298,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         }
     }
 #undef CREATE_TRY
-    if (!sde) { int rc = upload_tsit5(h); if (rc) { g_create_error = h->err; free_all(h); delete h; return rc; } }
+    if (!sde) build_tsit5_tables(cfg->dt, &h->tb);
     *handle = h;
     return B200ADJ_OK;
 }
@@ -383,7 +386,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     if (!is_sde(c)) {
         OdeFwdArgs a;
         a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
-        a.status = dstatus; a.N = c.N; a.S = h->S; a.h = c.dt;
+        a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_fwd<Lorenz>(h, a); break;
@@ -449,7 +452,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         OdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
-        a.N = c.N; a.S = h->S; a.h = c.dt; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+        a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
         a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
                   ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
         switch (c.rhs_family) {

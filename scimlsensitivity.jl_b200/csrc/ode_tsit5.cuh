@@ -14,6 +14,12 @@
 //   ReverseLossCallback  src/adjoint_common.jl:754-821 (lambda += dgdu at t_k, FSAL k1 recomputed)
 //   backsolve_checkpoint_callbacks  src/backsolve_adjoint.jl:523-546
 // and the upstream Tsit5 perform_step! / dense interpolant.
+//
+// Arithmetic notes.  (1) The step size is folded into the tableau on the host (hA = h*A, hBst = h*b(theta_s),
+// hBq = h*b(theta_q)) and the tables travel as kernel PARAMETERS, i.e. they sit in the constant bank and feed DFMA
+// directly as c[][] operands: one FMA per tableau entry, no register cost, no __constant__ symbol shared between
+// handles.  (2) The adjoint derivative is carried with the opposite sign, ka' = +J'lam, so that the reverse step
+// lam + (-h) * sum a_sj (-J'lam_j) becomes lam + sum hA_sj ka'_j with the SAME table as the forward stages.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -21,14 +27,12 @@
 
 namespace b200adj {
 
-struct Tsit5Consts {
-    double A[7][6];     // A[s][j] (row 6 = b weights)
-    double C[7];
-    double Bst[4][7];   // dense-output weights b_j(theta) at theta = 1 - c_s for adjoint stages s = 2..5
-    double Bq[3][7];    // dense-output weights at theta = (1 -/+ sqrt(.6))/2, 1/2  (3-pt Gauss-Legendre nodes)
-    double GW[3];       // Gauss-Legendre weights 5/9, 8/9, 5/9
+struct Tsit5Tables {
+    double hA[7][6];    // h * A[s][j] (row 6 = h * b)
+    double hBst[4][7];  // h * b_j(theta) at theta = 1 - c_s for adjoint stages s = 1..4 (0-based)
+    double hBq[3][7];   // h * b_j(theta) at theta = (1 -/+ sqrt(.6))/2, 1/2  (3-pt Gauss-Legendre nodes)
+    double hGW[3];      // (h/2) * Gauss-Legendre weights 5/9, 8/9, 5/9
 };
-__constant__ Tsit5Consts c_ts;
 
 enum { SA_INTERP = 0, SA_GAUSS = 1, SA_QUAD = 2, SA_BACKSOLVE = 3 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
@@ -41,8 +45,9 @@ struct OdeFwdArgs {
     const int32_t* save_of_step;  // [S+1]: save index k at grid point n, or -1
     int32_t* status;         // [N] or null
     int64_t N;
+    int64_t Npad;            // checkpoint row pitch: N rounded up to the block size (every block owns full 16B-aligned rows)
     int32_t S;
-    double h;
+    Tsit5Tables tb;
 };
 
 struct OdeRevArgs {
@@ -56,10 +61,11 @@ struct OdeRevArgs {
     double* dp;              // [P] final (shared_p)
     unsigned int* ticket;    // last-block-done counter
     int64_t N;
+    int64_t Npad;            // checkpoint row pitch
     int32_t S;
-    double h;
     double cost_a, cost_b;
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step
+    Tsit5Tables tb;
 };
 
 template <int D> __device__ __forceinline__ void load_state(const double* base, int64_t N, int64_t i, double* u) {
@@ -71,24 +77,50 @@ template <int D> __device__ __forceinline__ void store_state(double* base, int64
     for (int j = 0; j < D; j++) base[(int64_t)j * N + i] = u[j];
 }
 
-// stage value  u + h * sum_{j<s} A[s][j] k_j   (same association order as the oracle)
-template <int D, int S_> __device__ __forceinline__ void tsit5_stage(const double* u, const double (*k)[D], double h, double* out) {
+// ---- TMA (bulk async copy) + mbarrier primitives: HBM -> shared memory staging of the forward checkpoints ----
+// SASS: UBLKCP.S.G (cp.async.bulk) / SYNCS.ARRIVE.TRANS64 (expect_tx) / SYNCS.PHASECHK (try_wait).
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE%=;\n"
+        "bra LAB_WAIT%=;\n"
+        "LAB_DONE%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// stage value  u + sum_{j<S_} hA[S_][j] k_j
+template <int D, int S_> __device__ __forceinline__ void tsit5_stage(const Tsit5Tables& tb, const double* u, const double (*k)[D], double* out) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        double acc = 0.0;
+        double acc = u[i];
 #pragma unroll
-        for (int j = 0; j < S_; j++) acc = fma(c_ts.A[S_][j], k[j][i], acc);
-        out[i] = fma(h, acc, u[i]);
+        for (int j = 0; j < S_; j++) acc = fma(tb.hA[S_][j], k[j][i], acc);
+        out[i] = acc;
     }
 }
-// dense output  u + h * sum_j w[j] k_j
-template <int D> __device__ __forceinline__ void tsit5_dense(const double* u, const double (*k)[D], double h, const double* w, double* out) {
+// dense output  u + sum_j w[j] k_j   (w already scaled by h)
+template <int D> __device__ __forceinline__ void tsit5_dense(const double* u, const double (*k)[D], const double* w, double* out) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        double acc = 0.0;
+        double acc = u[i];
 #pragma unroll
         for (int j = 0; j < 7; j++) acc = fma(w[j], k[j][i], acc);
-        out[i] = fma(h, acc, u[i]);
+        out[i] = acc;
     }
 }
 
@@ -97,7 +129,7 @@ template <int D> __device__ __forceinline__ void tsit5_dense(const double* u, co
 // reverse pass recomputes the 6 stages from u_n, 24 B/step instead of 192 B/step of HBM traffic).
 // ------------------------------------------------------------------------------------------------------------
 template <class Fam, bool SHARED_P, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) tsit5_forward_kernel(OdeFwdArgs a) {
+__global__ void __launch_bounds__(BLOCK) tsit5_forward_kernel(const __grid_constant__ OdeFwdArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
     const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool active = gi < a.N;
@@ -107,27 +139,23 @@ __global__ void __launch_bounds__(BLOCK) tsit5_forward_kernel(OdeFwdArgs a) {
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * a.N + i);
     double u[D], k[7][D], tmp[D];
     load_state<D>(a.u0, a.N, i, u);
-    const int64_t stride = (int64_t)D * a.N;
-    if (active) {
-        store_state<D>(a.ckpt, a.N, i, u);
-        if (a.saved) { int ks = a.save_of_step[0]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
-    }
+    const int64_t stride = (int64_t)D * a.N, cstride = (int64_t)D * a.Npad;
+    // checkpoints: padded pitch, threads past N shadow member N-1 and fill the pad columns (keeps TMA rows whole)
+    store_state<D>(a.ckpt, a.Npad, gi, u);
+    if (active && a.saved) { int ks = a.save_of_step[0]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
     Fam::f(u, p, k[0]);
-    const double h = a.h;
     for (int n = 0; n < a.S; n++) {
-        tsit5_stage<D, 1>(u, k, h, tmp); Fam::f(tmp, p, k[1]);
-        tsit5_stage<D, 2>(u, k, h, tmp); Fam::f(tmp, p, k[2]);
-        tsit5_stage<D, 3>(u, k, h, tmp); Fam::f(tmp, p, k[3]);
-        tsit5_stage<D, 4>(u, k, h, tmp); Fam::f(tmp, p, k[4]);
-        tsit5_stage<D, 5>(u, k, h, tmp); Fam::f(tmp, p, k[5]);
-        tsit5_stage<D, 6>(u, k, h, tmp);
+        tsit5_stage<D, 1>(a.tb, u, k, tmp); Fam::f(tmp, p, k[1]);
+        tsit5_stage<D, 2>(a.tb, u, k, tmp); Fam::f(tmp, p, k[2]);
+        tsit5_stage<D, 3>(a.tb, u, k, tmp); Fam::f(tmp, p, k[3]);
+        tsit5_stage<D, 4>(a.tb, u, k, tmp); Fam::f(tmp, p, k[4]);
+        tsit5_stage<D, 5>(a.tb, u, k, tmp); Fam::f(tmp, p, k[5]);
+        tsit5_stage<D, 6>(a.tb, u, k, tmp);
 #pragma unroll
         for (int j = 0; j < D; j++) u[j] = tmp[j];
         Fam::f(u, p, k[0]);                      // FSAL: k7 of this step = k1 of the next
-        if (active) {
-            store_state<D>(a.ckpt + (int64_t)(n + 1) * stride, a.N, i, u);
-            if (a.saved) { int ks = a.save_of_step[n + 1]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
-        }
+        store_state<D>(a.ckpt + (int64_t)(n + 1) * cstride, a.Npad, gi, u);
+        if (active && a.saved) { int ks = a.save_of_step[n + 1]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
     }
     if (active && a.status) {
         bool ok = true;
@@ -178,17 +206,33 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, d
     }
 }
 
+template <int D, int COST, class Args>
+__device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t stride, int64_t N, int64_t i, const double* y, double* lam) {
+    if (COST == COST_EXPLICIT) {
+#pragma unroll
+        for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a, y[j], a.cost_b);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // Fused reverse pass.  SA in {SA_INTERP, SA_GAUSS, SA_BACKSOLVE}.
+// Register cap: 65536 members / 148 SMs = 443 threads per SM must be resident at once, otherwise a second, nearly
+// empty wave doubles the kernel time (every thread runs the full time loop): 448 threads/SM => <= 144 registers.
 // ------------------------------------------------------------------------------------------------------------
+#ifndef B200_REV_MAXREG
+#define B200_REV_MAXREG 128
+#endif
 template <class Fam, int SA, bool SHARED_P, int COST, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) tsit5_reverse_kernel(OdeRevArgs a) {
+__global__ void __maxnreg__(BLOCK == 128 ? 128 : B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
     const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool active = gi < a.N;
     const int64_t i = active ? gi : a.N - 1;
-    const int64_t N = a.N, stride = (int64_t)D * N;
-    const double h = a.h, hr = -a.h;      // reverse step
+    const int64_t N = a.N, stride = (int64_t)D * N, Npad = a.Npad, cstride = (int64_t)D * Npad;
+    const Tsit5Tables& tb = a.tb;
     double p[P];
 #pragma unroll
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * N + i);
@@ -199,120 +243,120 @@ __global__ void __launch_bounds__(BLOCK) tsit5_reverse_kernel(OdeRevArgs a) {
 #pragma unroll
     for (int q = 0; q < P; q++) mu[q] = 0.0;
 
-    double uhi[D];                        // u_{n+1} (checkpoint) -- for Backsolve: the backward-integrated y
-    load_state<D>(a.ckpt + (int64_t)a.S * stride, N, i, uhi);
-
-    // jump at t = T (PresetTimeCallback fires at initialisation when T is a save time)
-    {
-        int ks = a.save_of_step[a.S];
-        if (ks >= 0) {
-            if (COST == COST_EXPLICIT) {
-#pragma unroll
-                for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
-            } else {
-#pragma unroll
-                for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a, uhi[j], a.cost_b);
-            }
-        }
-    }
-
     if (SA == SA_BACKSOLVE) {
-        // z = [lam; mu; y]; dy/dt = f(y) integrated backwards (src/backsolve_adjoint.jl:32-61)
+        // z = [lam; mu; y]; dy/dt = f(y) integrated backwards (src/backsolve_adjoint.jl:32-61).
+        // ky' = -f(y), kl' = +J'lam so that both use the +h tables.
+        double y[D];
+        load_state<D>(a.ckpt + (int64_t)a.S * cstride, Npad, gi, y);
+        { int ks = a.save_of_step[a.S]; if (ks >= 0) add_cotangent<D, COST>(a, ks, stride, N, i, y, lam); }
         double ky[7][D], kl[7][D], ys[D], ls[D], dg[P];
         const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
         bool fsal = false;
         for (int n = a.S - 1; n >= 0; n--) {
             if (!fsal) {
-                Fam::f(uhi, p, ky[0]);
-                Fam::vjp_u(uhi, p, lam, kl[0]);
+                Fam::f(y, p, ky[0]);
 #pragma unroll
-                for (int j = 0; j < D; j++) kl[0][j] = -kl[0][j];
+                for (int j = 0; j < D; j++) ky[0][j] = -ky[0][j];
+                Fam::vjp_u(y, p, lam, kl[0]);
             }
-            // stage 1 contribution to mu: -(df/dp)' lam
-            double mus[P];
-            Fam::vjp_p(uhi, p, lam, dg);
+            Fam::vjp_p(y, p, lam, dg);                 // mu' = -F'lam, reverse step: mu += h * sum b_j F'(y_j) lam_j
 #pragma unroll
-            for (int q = 0; q < P; q++) mus[q] = -c_ts.A[6][0] * dg[q];
-#define B200_BS_STAGE(S_)                                                         \
-            tsit5_stage<D, S_>(uhi, ky, hr, ys); tsit5_stage<D, S_>(lam, kl, hr, ls);   \
-            Fam::f(ys, p, ky[S_]); Fam::vjp_u(ys, p, ls, kl[S_]);                  \
-            _Pragma("unroll") for (int j = 0; j < D; j++) kl[S_][j] = -kl[S_][j];  \
-            if (S_ < 6) { Fam::vjp_p(ys, p, ls, dg);                               \
-                _Pragma("unroll") for (int q = 0; q < P; q++) mus[q] = fma(-c_ts.A[6][S_ < 6 ? S_ : 0], dg[q], mus[q]); }
+            for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][0], dg[q], mu[q]);
+#define B200_BS_STAGE(S_)                                                                 \
+            tsit5_stage<D, S_>(tb, y, ky, ys); tsit5_stage<D, S_>(tb, lam, kl, ls);       \
+            Fam::f(ys, p, ky[S_]);                                                        \
+            _Pragma("unroll") for (int j = 0; j < D; j++) ky[S_][j] = -ky[S_][j];         \
+            Fam::vjp_u(ys, p, ls, kl[S_]);                                                \
+            if (S_ < 6) { Fam::vjp_p(ys, p, ls, dg);                                      \
+                _Pragma("unroll") for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][S_ < 6 ? S_ : 0], dg[q], mu[q]); }
             B200_BS_STAGE(1) B200_BS_STAGE(2) B200_BS_STAGE(3) B200_BS_STAGE(4) B200_BS_STAGE(5) B200_BS_STAGE(6)
 #undef B200_BS_STAGE
             // after stage 6: ys, ls hold the new state (c7 = 1, row 6 = b), ky[6], kl[6] are the FSAL derivatives
 #pragma unroll
-            for (int j = 0; j < D; j++) { uhi[j] = ys[j]; lam[j] = ls[j]; ky[0][j] = ky[6][j]; kl[0][j] = kl[6][j]; }
-#pragma unroll
-            for (int q = 0; q < P; q++) mu[q] = fma(hr, mus[q], mu[q]);
+            for (int j = 0; j < D; j++) { y[j] = ys[j]; lam[j] = ls[j]; ky[0][j] = ky[6][j]; kl[0][j] = kl[6][j]; }
             fsal = true;
-            // callbacks at t_n: checkpoint reset first, then the loss jump (CallbackSet order, backsolve_adjoint.jl:545)
+            // callbacks at t_n: checkpoint reset first, then the loss jump (CallbackSet order, backsolve_adjoint.jl:545);
+            // no_start never skips the jump for Backsolve (src/adjoint_common.jl:761)
             const int ks = a.save_of_step[n];
-            if (ckpt_on && (every || ks >= 0)) { load_state<D>(a.ckpt + (int64_t)n * stride, N, i, uhi); fsal = false; }
-            if (ks >= 0 && !((a.flags & 1u) && n == 0 && false)) {   // no_start never skips for Backsolve (adjoint_common.jl:761)
-                if (COST == COST_EXPLICIT) {
-#pragma unroll
-                    for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a, uhi[j], a.cost_b);
-                }
-                fsal = false;
-            }
+            if (ckpt_on && (every || ks >= 0)) { load_state<D>(a.ckpt + (int64_t)n * cstride, Npad, gi, y); fsal = false; }
+            if (ks >= 0) { add_cotangent<D, COST>(a, ks, stride, N, i, y, lam); fsal = false; }
         }
     } else {
-        double kf7[D];                         // f(u_{n+1}) = forward k7 of step n (= forward k1 of step n+1)
-        Fam::f(uhi, p, kf7);
-        double ka1[D];                         // adjoint FSAL stage
-        bool fsal = false;
-        double ulo[D];
-        load_state<D>(a.ckpt + (int64_t)(a.S - 1) * stride, N, i, ulo);
-        for (int n = a.S - 1; n >= 0; n--) {
-            // prefetch the next checkpoint one full step ahead (hides HBM latency behind ~450 DFMAs)
-            double unext[D];
-            {
-                const int nn = n > 0 ? n - 1 : 0;
-                load_state<D>(a.ckpt + (int64_t)nn * stride, N, i, unext);
-            }
-            // ---- forward stage recompute on [t_n, t_{n+1}]: the dense-output data of this step ----
-            double kf[7][D], tmp[D];
-            Fam::f(ulo, p, kf[0]);
-            tsit5_stage<D, 1>(ulo, kf, h, tmp); Fam::f(tmp, p, kf[1]);
-            tsit5_stage<D, 2>(ulo, kf, h, tmp); Fam::f(tmp, p, kf[2]);
-            tsit5_stage<D, 3>(ulo, kf, h, tmp); Fam::f(tmp, p, kf[3]);
-            tsit5_stage<D, 4>(ulo, kf, h, tmp); Fam::f(tmp, p, kf[4]);
-            tsit5_stage<D, 5>(ulo, kf, h, tmp); Fam::f(tmp, p, kf[5]);
+        double kf[7][D];                       // forward stages of the current step; kf[6] = f(u_{n+1}) carried over
+        double ka[7][D];                       // adjoint stages (+J'lam); ka[0] carried over (FSAL) unless a jump hit
+        double ulo[D], uhi[D];                 // uhi (= u_{n+1}) is live only for SA_INTERP
+        // Forward checkpoints are staged HBM -> shared memory by TMA bulk copies, CH steps per stage, NST stages in
+        // flight, completion tracked by one mbarrier per stage.  A register prefetch does not survive the register
+        // cap (ptxas sinks the LDG next to its use and every step then eats a full DRAM latency -- 32% of all
+        // warp-stall samples in the first ncu profile); the async copy cannot be sunk and costs no registers.
+        constexpr int CH = 2, NST = 2;
+        __shared__ alignas(128) double s_ck[NST][CH][D][BLOCK];
+        __shared__ alignas(8) uint64_t s_bar[NST];
+        const int NC = (a.S + CH - 1) / CH;    // chunk k holds steps n = S-1-(k*CH+j), j = 0..CH-1
+        const double* ck_col = a.ckpt + (int64_t)blockIdx.x * BLOCK;
+        auto issue_chunk = [&](int k) {
+            const int st = k % NST;
+            const int cnt = min(CH, a.S - k * CH);
+            mbar_expect_tx(&s_bar[st], (uint32_t)(cnt * D * BLOCK * sizeof(double)));
+            for (int j = 0; j < cnt; j++) {
+                const int nn = a.S - 1 - (k * CH + j);
 #pragma unroll
-            for (int j = 0; j < D; j++) kf[6][j] = kf7[j];
+                for (int dd = 0; dd < D; dd++)
+                    tma_load_1d(&s_ck[st][j][dd][0], ck_col + ((int64_t)nn * D + dd) * Npad, BLOCK * sizeof(double), &s_bar[st]);
+            }
+        };
+        if (threadIdx.x == 0) {
+            for (int st = 0; st < NST; st++) mbar_init(&s_bar[st], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) for (int k = 0; k < NST && k < NC; k++) issue_chunk(k);
+
+        load_state<D>(a.ckpt + (int64_t)a.S * cstride, Npad, gi, uhi);
+        {
+            // jump at t = T (PresetTimeCallback fires at initialisation when T is a save time)
+            int ks = a.save_of_step[a.S];
+            if (ks >= 0) add_cotangent<D, COST>(a, ks, stride, N, i, uhi, lam);
+            Fam::f(uhi, p, kf[6]);
+            Fam::vjp_u(uhi, p, lam, ka[0]);    // y(T) = u_S
+        }
+        for (int n = a.S - 1; n >= 0; n--) {
+            const int c = a.S - 1 - n, k = c / CH, jj = c % CH, st = k % NST;
+            if (jj == 0) mbar_wait(&s_bar[st], (uint32_t)((k / NST) & 1));
+#pragma unroll
+            for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[st][jj][dd][threadIdx.x];
+            if (jj == CH - 1 || n == 0) {
+                __syncthreads();               // every thread has read this stage: hand it back to the TMA producer
+                if (threadIdx.x == 0 && k + NST < NC) issue_chunk(k + NST);
+            }
+
+            // ---- forward stage recompute on [t_n, t_{n+1}]: the dense-output data of this step ----
+            double tmp[D];
+            Fam::f(ulo, p, kf[0]);
+            tsit5_stage<D, 1>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[1]);
+            tsit5_stage<D, 2>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[2]);
+            tsit5_stage<D, 3>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[3]);
+            tsit5_stage<D, 4>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[4]);
+            tsit5_stage<D, 5>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[5]);
 
             // ---- adjoint Tsit5 step t_{n+1} -> t_n; stage s evaluated at y(t_{n+1} - c_s h) ----
-            double ka[7][D], ls[D], y[D], dg[P];
-            if (!fsal) {
-                Fam::vjp_u(uhi, p, lam, ka[0]);           // y(t_{n+1}) = u_{n+1} (right-continuous lookup at a knot)
-#pragma unroll
-                for (int j = 0; j < D; j++) ka[0][j] = -ka[0][j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < D; j++) ka[0][j] = ka1[j];
-            }
-            double mus[P];
+            double ls[D], y[D], dg[P];
             if (SA == SA_INTERP) {
+                // mu' = -F'lam integrated with the same tableau: mu += h * sum_j b_j F'(y_j) lam_j ; stage 1 at y = u_{n+1}
                 Fam::vjp_p(uhi, p, lam, dg);
 #pragma unroll
-                for (int q = 0; q < P; q++) mus[q] = -c_ts.A[6][0] * dg[q];
+                for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][0], dg[q], mu[q]);
             }
-#define B200_ADJ_STAGE(S_, YEXPR)                                                      \
-            tsit5_stage<D, S_>(lam, ka, hr, ls);                                       \
-            YEXPR;                                                                     \
-            Fam::vjp_u(y, p, ls, ka[S_]);                                              \
-            _Pragma("unroll") for (int j = 0; j < D; j++) ka[S_][j] = -ka[S_][j];      \
-            if (SA == SA_INTERP && S_ < 6) { Fam::vjp_p(y, p, ls, dg);                 \
-                _Pragma("unroll") for (int q = 0; q < P; q++) mus[q] = fma(-c_ts.A[6][S_ < 6 ? S_ : 0], dg[q], mus[q]); }
-            B200_ADJ_STAGE(1, tsit5_dense<D>(ulo, kf, h, c_ts.Bst[0], y))
-            B200_ADJ_STAGE(2, tsit5_dense<D>(ulo, kf, h, c_ts.Bst[1], y))
-            B200_ADJ_STAGE(3, tsit5_dense<D>(ulo, kf, h, c_ts.Bst[2], y))
-            B200_ADJ_STAGE(4, tsit5_dense<D>(ulo, kf, h, c_ts.Bst[3], y))
+#define B200_ADJ_STAGE(S_, YEXPR)                                                          \
+            tsit5_stage<D, S_>(tb, lam, ka, ls);                                           \
+            YEXPR;                                                                         \
+            Fam::vjp_u(y, p, ls, ka[S_]);                                                  \
+            if (SA == SA_INTERP && S_ < 6) { Fam::vjp_p(y, p, ls, dg);                     \
+                _Pragma("unroll") for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][S_ < 6 ? S_ : 0], dg[q], mu[q]); }
+            B200_ADJ_STAGE(1, tsit5_dense<D>(ulo, kf, tb.hBst[0], y))
+            B200_ADJ_STAGE(2, tsit5_dense<D>(ulo, kf, tb.hBst[1], y))
+            B200_ADJ_STAGE(3, tsit5_dense<D>(ulo, kf, tb.hBst[2], y))
+            B200_ADJ_STAGE(4, tsit5_dense<D>(ulo, kf, tb.hBst[3], y))
             B200_ADJ_STAGE(5, _Pragma("unroll") for (int j = 0; j < D; j++) y[j] = ulo[j])
             B200_ADJ_STAGE(6, _Pragma("unroll") for (int j = 0; j < D; j++) y[j] = ulo[j])
 #undef B200_ADJ_STAGE
@@ -321,41 +365,27 @@ __global__ void __launch_bounds__(BLOCK) tsit5_reverse_kernel(OdeRevArgs a) {
             if (SA == SA_GAUSS) {
                 // 3-point Gauss-Legendre over this step, pre-jump lambda from the adjoint step's own dense output,
                 // y from the forward dense output: dp += (h/2) w_q (df/dp)'(y_q) lam_q  (gauss_adjoint.jl:745-759)
-                double lq[D], acc[P];
-#pragma unroll
-                for (int q = 0; q < P; q++) acc[q] = 0.0;
+                double lq[D];
 #pragma unroll
                 for (int g = 0; g < 3; g++) {
-                    tsit5_dense<D>(lam, ka, hr, c_ts.Bq[g], lq);
-                    tsit5_dense<D>(ulo, kf, h, c_ts.Bq[2 - g], y);
+                    tsit5_dense<D>(lam, ka, tb.hBq[g], lq);
+                    tsit5_dense<D>(ulo, kf, tb.hBq[2 - g], y);
                     Fam::vjp_p(y, p, lq, dg);
 #pragma unroll
-                    for (int q = 0; q < P; q++) acc[q] = fma(c_ts.GW[g], dg[q], acc[q]);
+                    for (int q = 0; q < P; q++) mu[q] = fma(tb.hGW[g], dg[q], mu[q]);
                 }
-#pragma unroll
-                for (int q = 0; q < P; q++) mu[q] = fma(0.5 * h, acc[q], mu[q]);
-            } else {
-#pragma unroll
-                for (int q = 0; q < P; q++) mu[q] = fma(hr, mus[q], mu[q]);
             }
 #pragma unroll
-            for (int j = 0; j < D; j++) { lam[j] = ls[j]; ka1[j] = ka[6][j]; }
-            fsal = true;
+            for (int j = 0; j < D; j++) { lam[j] = ls[j]; ka[0][j] = ka[6][j]; kf[6][j] = kf[0][j]; }
 
-            // ---- jump at t_n (ReverseLossCallback): lam += dgdu(t_k), FSAL invalidated ----
+            // ---- jump at t_n (ReverseLossCallback): lam += dgdu(t_k), FSAL invalidated => recompute ka[0] ----
             const int ks = a.save_of_step[n];
             if (ks >= 0 && !((a.flags & 1u) && n == 0)) {
-                if (COST == COST_EXPLICIT) {
-#pragma unroll
-                    for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a, ulo[j], a.cost_b);
-                }
-                fsal = false;
+                add_cotangent<D, COST>(a, ks, stride, N, i, ulo, lam);
+                Fam::vjp_u(ulo, p, lam, ka[0]);
             }
 #pragma unroll
-            for (int j = 0; j < D; j++) { uhi[j] = ulo[j]; kf7[j] = kf[0][j]; ulo[j] = unext[j]; }
+            for (int j = 0; j < D; j++) uhi[j] = ulo[j];
         }
     }
 
