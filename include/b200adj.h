@@ -55,6 +55,8 @@ enum { B200ADJ_COST_EXPLICIT = 0, B200ADJ_COST_AFFINE = 1 };
 #define B200ADJ_FLAG_STORED_NOISE        8u   /* SDE: keep dW[S][m][N] in HBM (reference behaviour, reverse(sol.W)) */
                                               /* instead of regenerating it from the Philox counter in reverse      */
 
+#define B200ADJ_FLAG_TRACE              16u   /* record (smid, start, end) of every block of the reverse kernel      */
+
 /* error codes */
 #define B200ADJ_OK                 0
 #define B200ADJ_ERR_INVALID       -1   /* null pointer / bad enum / inconsistent sizes                     */
@@ -122,6 +124,10 @@ int32_t b200adj_synchronize(void* handle);
 int64_t b200adj_launch_count(void* handle);
 /* adaptive steppers: per-member accepted step counts of the last forward / reverse solves (device or host per cfg) */
 int32_t b200adj_get_step_counts(void* handle, int32_t* fwd_steps, int32_t* rev_steps);
+
+/* tracing (needs B200ADJ_FLAG_TRACE at create): out[nblocks][3] = (SM id, %globaltimer ns at block start, at block end)
+ * of the last reverse launch; call with out = NULL to query nblocks.  Host pointer always. */
+int32_t b200adj_get_block_trace(void* handle, uint64_t* out, int32_t* nblocks);
 
 int32_t b200adj_destroy(void* handle);
 const char* b200adj_last_error(void* handle);   /* handle may be NULL: last create() error of this thread */

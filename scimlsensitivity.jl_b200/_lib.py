@@ -18,11 +18,11 @@ SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3}
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3}
 DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
 COST = {"explicit": 0, "affine": 1}
-FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE = 1, 2, 4, 8
+FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE = 1, 2, 4, 8, 16
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
 EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_get_noise", "b200adj_set_stream",
-           "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_destroy",
+           "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg"]
 
 
@@ -100,6 +100,8 @@ def load():
         lib.b200adj_launch_count.restype = C.c_int64
         lib.b200adj_get_step_counts.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200adj_get_step_counts.restype = C.c_int32
+        lib.b200adj_get_block_trace.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        lib.b200adj_get_block_trace.restype = C.c_int32
         lib.b200adj_destroy.argtypes = [C.c_void_p]
         lib.b200adj_destroy.restype = C.c_int32
         lib.b200adj_last_error.argtypes = [C.c_void_p]
@@ -159,6 +161,15 @@ class Handle:
 
     def get_noise(self, out):
         self._check(self._lib.b200adj_get_noise(self._h, _addr(out)))
+
+    def block_trace(self):
+        """[nblocks, 3] uint64: (SM id, start ns, end ns) of every block of the last reverse launch (FLAG_TRACE)."""
+        import numpy as np
+        n = C.c_int32()
+        self._check(self._lib.b200adj_get_block_trace(self._h, None, C.byref(n)))
+        out = np.zeros((n.value, 3), dtype=np.uint64)
+        self._check(self._lib.b200adj_get_block_trace(self._h, out.ctypes.data, C.byref(n)))
+        return out
 
     def set_stream(self, stream_ptr):
         self._check(self._lib.b200adj_set_stream(self._h, stream_ptr))

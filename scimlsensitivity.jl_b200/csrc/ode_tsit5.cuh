@@ -65,6 +65,7 @@ struct OdeRevArgs {
     int32_t S;
     double cost_a, cost_b;
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step
+    unsigned long long* trace;   // optional [gridDim][3] = (smid, globaltimer at block start, at block end) or null
     Tsit5Tables tb;
 };
 
@@ -128,10 +129,10 @@ template <int D> __device__ __forceinline__ void tsit5_dense(const double* u, co
 // Forward ensemble solve, fixed-step Tsit5, writes every step's state (the dense solution is NOT stored: the
 // reverse pass recomputes the 6 stages from u_n, 24 B/step instead of 192 B/step of HBM traffic).
 // ------------------------------------------------------------------------------------------------------------
-template <class Fam, bool SHARED_P, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) tsit5_forward_kernel(const __grid_constant__ OdeFwdArgs a) {
+template <class Fam, bool SHARED_P>
+__global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constant__ OdeFwdArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
-    const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gi < a.N;
     const int64_t i = active ? gi : a.N - 1;
     double p[P];
@@ -167,9 +168,10 @@ __global__ void __launch_bounds__(BLOCK) tsit5_forward_kernel(const __grid_const
 
 // deterministic block reduction of P per-thread values -> partials[block][P]; the last block to finish sums the
 // partials in index order (fixed order => bitwise reproducible for a given grid), no floating-point atomics.
-template <int P, int BLOCK>
+template <int P>
 __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, double* dp, unsigned int* ticket) {
-    __shared__ double s_red[(BLOCK / 32) * P];
+    __shared__ double s_red[16 * P];               // up to 512 threads per block
+    const int nwarps = (int)(blockDim.x >> 5);
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -182,7 +184,7 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, d
     __syncthreads();
     if (threadIdx.x < P) {
         double v = 0.0;
-        for (int w = 0; w < BLOCK / 32; w++) v += s_red[w * P + threadIdx.x];
+        for (int w = 0; w < nwarps; w++) v += s_red[w * P + threadIdx.x];
         partials[(int64_t)blockIdx.x * P + threadIdx.x] = v;
     }
     __threadfence();
@@ -195,7 +197,7 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, d
     if (s_last) {
         __threadfence();
         // P x gridDim sums; each warp-lane strides over blocks in a fixed pattern, then a fixed shuffle tree
-        for (int q = warp; q < P; q += BLOCK / 32) {
+        for (int q = warp; q < P; q += nwarps) {
             double v = 0.0;
             for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (int64_t)b * P + q);
 #pragma unroll
@@ -225,14 +227,26 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
 #ifndef B200_REV_MAXREG
 #define B200_REV_MAXREG 128
 #endif
-template <class Fam, int SA, bool SHARED_P, int COST, int BLOCK>
-__global__ void __maxnreg__(BLOCK == 128 ? 128 : B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgs a) {
+#ifndef REV_CH_DEF
+#define REV_CH_DEF 2
+#endif
+constexpr int REV_CH = REV_CH_DEF, REV_NST = 2;     // TMA pipeline: steps per stage (= block barrier period), stages in flight
+template <int D> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(double); }
+template <class Fam, int SA, bool SHARED_P, int COST>
+__global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
+    const int BLOCK = (int)blockDim.x;
     const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool active = gi < a.N;
     const int64_t i = active ? gi : a.N - 1;
     const int64_t N = a.N, stride = (int64_t)D * N, Npad = a.Npad, cstride = (int64_t)D * Npad;
     const Tsit5Tables& tb = a.tb;
+    if (a.trace && threadIdx.x == 0) {
+        unsigned int smid; unsigned long long t;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[blockIdx.x * 3 + 0] = smid; a.trace[blockIdx.x * 3 + 1] = t;
+    }
     double p[P];
 #pragma unroll
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * N + i);
@@ -289,20 +303,25 @@ __global__ void __maxnreg__(BLOCK == 128 ? 128 : B200_REV_MAXREG) tsit5_reverse_
         // flight, completion tracked by one mbarrier per stage.  A register prefetch does not survive the register
         // cap (ptxas sinks the LDG next to its use and every step then eats a full DRAM latency -- 32% of all
         // warp-stall samples in the first ncu profile); the async copy cannot be sunk and costs no registers.
-        constexpr int CH = 2, NST = 2;
-        __shared__ alignas(128) double s_ck[NST][CH][D][BLOCK];
-        __shared__ alignas(8) uint64_t s_bar[NST];
+        // The block-wide barrier that recycles a stage every CH steps also keeps all warps of the SM in lockstep: the
+        // warp arbiter favours high warp ids, and free-running warps drift apart by >2x over the 1000 steps (block
+        // trace: 0.94 .. 2.2 ms for identical work) so the stragglers finish latency-bound; per-warp pipelines with
+        // a coarse barrier measured slower as well (2.12-2.21 ms vs 1.98 ms) -- lockstep warps share the I-cache.
+        constexpr int CH = REV_CH, NST = REV_NST;
+        extern __shared__ __align__(128) double s_ck[];          // [NST][CH][D][BLOCK]
+        __shared__ __align__(8) uint64_t s_bar[NST];
+        const uint32_t row_bytes = (uint32_t)(BLOCK * sizeof(double));
         const int NC = (a.S + CH - 1) / CH;    // chunk k holds steps n = S-1-(k*CH+j), j = 0..CH-1
         const double* ck_col = a.ckpt + (int64_t)blockIdx.x * BLOCK;
         auto issue_chunk = [&](int k) {
             const int st = k % NST;
             const int cnt = min(CH, a.S - k * CH);
-            mbar_expect_tx(&s_bar[st], (uint32_t)(cnt * D * BLOCK * sizeof(double)));
+            mbar_expect_tx(&s_bar[st], (uint32_t)(cnt * D) * row_bytes);
             for (int j = 0; j < cnt; j++) {
                 const int nn = a.S - 1 - (k * CH + j);
 #pragma unroll
                 for (int dd = 0; dd < D; dd++)
-                    tma_load_1d(&s_ck[st][j][dd][0], ck_col + ((int64_t)nn * D + dd) * Npad, BLOCK * sizeof(double), &s_bar[st]);
+                    tma_load_1d(&s_ck[(size_t)((st * CH + j) * D + dd) * BLOCK], ck_col + ((int64_t)nn * D + dd) * Npad, row_bytes, &s_bar[st]);
             }
         };
         if (threadIdx.x == 0) {
@@ -324,7 +343,7 @@ __global__ void __maxnreg__(BLOCK == 128 ? 128 : B200_REV_MAXREG) tsit5_reverse_
             const int c = a.S - 1 - n, k = c / CH, jj = c % CH, st = k % NST;
             if (jj == 0) mbar_wait(&s_bar[st], (uint32_t)((k / NST) & 1));
 #pragma unroll
-            for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[st][jj][dd][threadIdx.x];
+            for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[(size_t)((st * CH + jj) * D + dd) * BLOCK + threadIdx.x];
             if (jj == CH - 1 || n == 0) {
                 __syncthreads();               // every thread has read this stage: hand it back to the TMA producer
                 if (threadIdx.x == 0 && k + NST < NC) issue_chunk(k + NST);
@@ -390,12 +409,17 @@ __global__ void __maxnreg__(BLOCK == 128 ? 128 : B200_REV_MAXREG) tsit5_reverse_
     }
 
     if (active) store_state<D>(a.du0, N, i, lam);
+    if (a.trace && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        a.trace[blockIdx.x * 3 + 2] = t;
+    }
     if (SHARED_P) {
         if (!active) {
 #pragma unroll
             for (int q = 0; q < P; q++) mu[q] = 0.0;
         }
-        reduce_dp<P, BLOCK>(mu, a.partials, a.dp, a.ticket);
+        reduce_dp<P>(mu, a.partials, a.dp, a.ticket);
     } else if (active) {
 #pragma unroll
         for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = mu[q];

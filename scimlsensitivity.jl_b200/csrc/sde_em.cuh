@@ -80,8 +80,9 @@ __global__ void sde_noise_kernel(SdeNoiseArgs a) {
     }
 }
 
-template <class Fam, bool EULER_HEUN, bool SHARED_P, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) sde_forward_kernel(SdeFwdArgs a) {
+template <class Fam, bool EULER_HEUN, bool SHARED_P>
+__global__ void __launch_bounds__(512) sde_forward_kernel(SdeFwdArgs a) {
+    const int BLOCK = (int)blockDim.x;
     constexpr int D = Fam::D, P = Fam::P, M = Fam::M;
     static_assert(M == D, "diagonal noise: one Wiener process per state");
     const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
@@ -140,8 +141,9 @@ __device__ __forceinline__ void sde_adj_terms(const double* lam, const double* y
     for (int q = 0; q < P; q++) { am[q] = -am[q]; bm[q] = -bm[q]; }
 }
 
-template <class Fam, bool EULER_HEUN, bool SHARED_P, int COST, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) sde_backsolve_kernel(SdeRevArgs a) {
+template <class Fam, bool EULER_HEUN, bool SHARED_P, int COST>
+__global__ void __launch_bounds__(512) sde_backsolve_kernel(SdeRevArgs a) {
+    const int BLOCK = (int)blockDim.x;
     constexpr int D = Fam::D, P = Fam::P, M = Fam::M;
     const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
     const bool active = gi < a.N;
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(BLOCK) sde_backsolve_kernel(SdeRevArgs a) {
 #pragma unroll
             for (int q = 0; q < P; q++) mu[q] = 0.0;
         }
-        reduce_dp<P, BLOCK>(mu, a.partials, a.dp, a.ticket);
+        reduce_dp<P>(mu, a.partials, a.dp, a.ticket);
     } else if (active) {
 #pragma unroll
         for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = mu[q];

@@ -19,7 +19,7 @@ class DeviceEnsemble:
     def __init__(self, family, sensealg, stepper, N, saveat, tspan, dt, *, shared_p=True, cost=None,
                  on_device=False, device=0, no_start=False, checkpointing=True, ckpt_every_step=False,
                  stored_noise=False, seed=0, traj_offset=0, block_threads=0, abstol=1e-6, reltol=1e-3,
-                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64"):
+                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False):
         d, P, m = FAMILIES[family]
         cfg = _lib.Cfg()
         cfg.rhs_family, cfg.sensealg, cfg.stepper, cfg.dtype = _lib.FAM[family], _lib.SA[sensealg], _lib.ST[stepper], _lib.DTYPE[dtype]
@@ -42,6 +42,8 @@ class DeviceEnsemble:
             flags |= _lib.FLAG_CKPT_EVERY_STEP
         if stored_noise:
             flags |= _lib.FLAG_STORED_NOISE
+        if trace:
+            flags |= _lib.FLAG_TRACE
         cfg.flags, cfg.block_threads = flags, int(block_threads)
         self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
         self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)
