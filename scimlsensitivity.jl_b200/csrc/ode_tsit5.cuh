@@ -228,7 +228,7 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
 #define B200_REV_MAXREG 128
 #endif
 #ifndef REV_CH_DEF
-#define REV_CH_DEF 2
+#define REV_CH_DEF 4
 #endif
 constexpr int REV_CH = REV_CH_DEF, REV_NST = 2;     // TMA pipeline: steps per stage (= block barrier period), stages in flight
 template <int D> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(double); }
@@ -358,6 +358,9 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             tsit5_stage<D, 4>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[4]);
             tsit5_stage<D, 5>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[5]);
 
+#ifdef REV_MIDSYNC
+            __syncthreads();
+#endif
             // ---- adjoint Tsit5 step t_{n+1} -> t_n; stage s evaluated at y(t_{n+1} - c_s h) ----
             double ls[D], y[D], dg[P];
             if (SA == SA_INTERP) {
@@ -381,6 +384,9 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #undef B200_ADJ_STAGE
             // ls = lambda(t_n) (row 6 of A is b), ka[6] = FSAL derivative at (t_n, ls, u_n)
 
+#ifdef REV_MIDSYNC
+            __syncthreads();
+#endif
             if (SA == SA_GAUSS) {
                 // 3-point Gauss-Legendre over this step, pre-jump lambda from the adjoint step's own dense output,
                 // y from the forward dense output: dp += (h/2) w_q (df/dp)'(y_q) lam_q  (gauss_adjoint.jl:745-759)
