@@ -40,6 +40,27 @@ def make_inputs(N, offset=0):
     return np.ascontiguousarray(u0), p
 
 
+def host_cores():
+    """cores this process may actually run on (the box reports 128 CPUs but the cgroup/affinity mask is smaller)"""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the reverse kernel from the committed ncu summary (per launch)"""
+    path = os.path.join(ROOT, "profiles", "r1_reverse_ncu_summary.json")
+    try:
+        with open(path) as f:
+            m = json.load(f)
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+        r, w = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
+        return r["value"] * scale[r["unit"]] + w["value"] * scale[w["unit"]]
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -124,7 +145,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = host_cores()
     sample = args.members or 8192
     times = []
     for i in range(args.warmup + args.steps):
@@ -255,7 +276,7 @@ def run_ours(args):
         alg_bytes = ALG_BYTES_PER_MEMBER_STEP * N * S
         achieved = alg_bytes / (rev_ms * 1e-3) / 1e9
         compulsory = 8.0 * (S * 3 + 3 + W["nsave"] * 0) * N     # checkpoint read + du0 write (affine cost: no cotangent read)
-        threads = os.cpu_count() or 1
+        threads = host_cores()
         cpu_sample = 8192
         cpu_oracle_rate(256, threads)                      # warm the library / thread pool
         cpu_rate, cpu_s = cpu_oracle_rate(cpu_sample, threads)
@@ -269,7 +290,8 @@ def run_ours(args):
                        "block_threads": args.block or 64},
             "phases_ms": {"forward": fwd_ms, "reverse": rev_ms, "allreduce": max(0.0, ms_per_step - fwd_ms - rev_ms)},
             "roofline": {"bound": "hbm", "kernel": "tsit5_reverse_kernel<Lorenz,GAUSS>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic() if (N == W["members_per_gpu"]) else None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_member_step": ALG_BYTES_PER_MEMBER_STEP,
                          "compulsory_bytes_per_launch": compulsory,
                          "note": "per-step accounting of SURVEY 8d (state counted as if it lived in HBM between steps); the time "
