@@ -287,7 +287,7 @@ def run_ours(args):
             "config": {"workload": "C2 Lorenz d=3 P=3 N=65536/GPU GaussAdjoint Tsit5 fixed dt=0.01 T=10 saveat=0.1 dgdu=u-2 shared p",
                        "members_per_gpu": N, "S": S, "K": W["nsave"], "parallelism": f"ensemble-shard x{world}",
                        "l2": "per-step working set = 1.57 GB of checkpoints per GPU (>> 126 MB L2), no explicit flush",
-                       "block_threads": args.block or 64},
+                       "block_threads": args.block or "auto: ceil32(N / (n_SM * waves)) = 448, one block per SM"},
             "phases_ms": {"forward": fwd_ms, "reverse": rev_ms, "allreduce": max(0.0, ms_per_step - fwd_ms - rev_ms)},
             "roofline": {"bound": "hbm", "kernel": "tsit5_reverse_kernel<Lorenz,GAUSS>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak,

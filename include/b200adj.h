@@ -111,6 +111,11 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp);
 int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost_kind, double cost_a, double cost_b,
                                     uint32_t flags, int32_t K, const double* t);
 
+/* Tolerances of the NEXT reverse pass on an adaptive handle: the adjoint solve's abstol/reltol (the reference takes them
+ * as keywords of adjoint_sensitivities, src/sensitivity_interface.jl:432; default = the forward solve's) and the quadgk
+ * tolerances of QuadratureAdjoint (sensealg.abstol/.reltol, src/quadrature_adjoint.jl:517).  Values <= 0 keep the current. */
+int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_reltol, double quad_abstol, double quad_reltol);
+
 /* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
 int32_t b200adj_get_noise(void* handle, void* dW_out);
 

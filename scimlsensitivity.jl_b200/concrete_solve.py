@@ -64,7 +64,7 @@ def _step_size(alg, kwargs):
         raise NotImplementedError("adaptive Tsit5 is not built on the B200 path yet (SURVEY.md 8f rank 3): use "
                                   "Tsit5(adaptive=False, dt=...)")
     if isinstance(alg, Rosenbrock23):
-        raise NotImplementedError("Rosenbrock23 is not built on the B200 path yet")
+        return 0.0                                  # adaptive: error-controlled steps (abstol / reltol keywords)
     if not dt or dt <= 0:
         raise ValueError("fixed-step solve needs dt > 0")
     return float(dt)
@@ -97,6 +97,8 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     _check_params(p)
     N_global = u0.shape[1]
     shared_p = (np.ndim(p) == 1) if not _is_torch(p) else (p.dim() == 1)
+    if saveat is None and isinstance(alg, Rosenbrock23):
+        raise ValueError("adaptive solve on the B200 path needs explicit saveat times")
     ts = saveat_to_times(saveat if saveat is not None else _step_size(alg, kwargs), prob.tspan)
     if not save_start and len(ts) and ts[0] == prob.tspan[0]:
         ts = ts[1:]
@@ -120,13 +122,15 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     block = getattr(sensealg, "block_threads", 0) if isinstance(sensealg, B200Adjoint) else 0
     stored = getattr(sensealg, "stored_noise", False) if isinstance(sensealg, B200Adjoint) else False
     key = (prob.f, alg.code, hi - lo, ts.tobytes(), tuple(prob.tspan), _step_size(alg, kwargs), shared_p, on_device, device,
-           getattr(prob, "seed", 0), lo, block, stored)
+           getattr(prob, "seed", 0), lo, block, stored, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3))
     eng = _HANDLE_CACHE.get(key) if ensemblealg.reuse_handle else None
     if eng is None:
         eng = DeviceEnsemble(prob.f, sensealg_name(inner), alg.code, hi - lo, ts, prob.tspan, _step_size(alg, kwargs),
                              shared_p=shared_p, on_device=on_device, device=device,
                              seed=getattr(prob, "seed", 0), traj_offset=lo, block_threads=block, stored_noise=stored,
-                             quad_abstol=getattr(inner, "abstol", 1e-6), quad_reltol=getattr(inner, "reltol", 1e-3))
+                             quad_abstol=getattr(inner, "abstol", 1e-6), quad_reltol=getattr(inner, "reltol", 1e-3),
+                             abstol=kwargs.get("abstol", 1e-6), reltol=kwargs.get("reltol", 1e-3),
+                             max_steps=kwargs.get("maxiters", 0))
         if ensemblealg.reuse_handle:
             _HANDLE_CACHE[key] = eng
     dW = getattr(prob, "noise", None)

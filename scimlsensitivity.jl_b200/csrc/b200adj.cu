@@ -12,6 +12,7 @@
 #include "../../include/b200adj.h"
 #include "ode_tsit5.cuh"
 #include "sde_em.cuh"
+#include "ros23.cuh"
 
 using namespace b200adj;
 
@@ -34,6 +35,11 @@ struct Handle {
     unsigned long long* d_trace = nullptr;   // [grid][3] block trace (B200ADJ_FLAG_TRACE)
     unsigned int* d_ticket = nullptr;
     int32_t* d_save_of_step = nullptr;
+    // adaptive Rosenbrock23 path: per-member dense forward / reverse solutions
+    bool adaptive = false; int maxs = 0;
+    double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
+    double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
+    int32_t *r_fn = nullptr, *r_rn = nullptr;
     // staging (buffers_on_device == 0)
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
@@ -175,10 +181,55 @@ int launch_sde_rev_f(Handle* h, const SdeRevArgs& a) {
     return ex ? launch_sde_rev_b<Fam, EH, false, COST_EXPLICIT>(h, a) : launch_sde_rev_b<Fam, EH, false, COST_AFFINE>(h, a);
 }
 
+template <class Fam>
+int launch_ros_fwd(Handle* h, const RosArgs& a) {
+    if (h->cfg.shared_p) ros23_forward_kernel<Fam, true><<<h->grid, h->block, 0, h->stream>>>(a);
+    else ros23_forward_kernel<Fam, false><<<h->grid, h->block, 0, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+template <class Fam, int SA>
+int launch_ros_rev_sa(Handle* h, const RosArgs& a) {
+    const bool sp = h->cfg.shared_p, ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (sp) { if (ex) ros23_reverse_kernel<Fam, SA, true, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
+              else ros23_reverse_kernel<Fam, SA, true, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
+    else { if (ex) ros23_reverse_kernel<Fam, SA, false, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
+           else ros23_reverse_kernel<Fam, SA, false, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
+    h->launches++;
+    return 0;
+}
+template <class Fam>
+int launch_ros_rev(Handle* h, const RosArgs& a) {
+    if (h->cfg.sensealg == B200ADJ_SA_GAUSS) return launch_ros_rev_sa<Fam, SA_GAUSS>(h, a);
+    if (h->cfg.sensealg != B200ADJ_SA_QUADRATURE) return B200ADJ_ERR_UNSUPPORTED;
+    int rc = launch_ros_rev_sa<Fam, SA_QUAD>(h, a);
+    if (rc) return rc;
+    const int qb = 128, qg = (int)((h->cfg.N + qb - 1) / qb);
+    if ((size_t)qg > (size_t)h->grid * 2) return B200ADJ_ERR_INVALID;
+    if (h->cfg.shared_p) ros23_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(a);
+    else ros23_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+RosArgs ros_args(Handle* h) {
+    const b200adj_cfg& c = h->cfg;
+    RosArgs a;
+    memset(&a, 0, sizeof(a));
+    a.saveat = h->d_saveat; a.partials = h->d_partials; a.ticket = h->d_ticket;
+    a.ft = h->r_ft; a.fu = h->r_fu; a.fk = h->r_fk; a.fn = h->r_fn;
+    a.rt0 = h->r_rt0; a.rh = h->r_rh; a.rz = h->r_rz; a.rk = h->r_rk; a.rn = h->r_rn;
+    a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.abstol = c.abstol; a.reltol = c.reltol;
+    a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+    a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    return a;
+}
+
 size_t esz(const b200adj_cfg&) { return sizeof(double); }
 
 void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
+    cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
+    cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn);
     cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status);
@@ -208,7 +259,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     int d, P, m;
     if (fam_dims(*cfg, &d, &P, &m)) { g_create_error = "rhs_family not built (MLP / unknown)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->d != d || cfg->P != P) { g_create_error = "cfg.d / cfg.P do not match rhs_family"; return B200ADJ_ERR_INVALID; }
-    if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || !(cfg->dt > 0) || !(cfg->t1 > cfg->t0)) {
+    const bool ros = cfg->stepper == B200ADJ_ST_ROSENBROCK23;
+    if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || (!ros && !(cfg->dt > 0)) || !(cfg->t1 > cfg->t0)) {
         g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
     if (cfg->dtype != B200ADJ_F64) { g_create_error = "dtype: only F64 is built for this family"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->cost_kind != B200ADJ_COST_EXPLICIT && cfg->cost_kind != B200ADJ_COST_AFFINE) { g_create_error = "bad cost_kind"; return B200ADJ_ERR_INVALID; }
@@ -218,9 +270,63 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (cfg->sensealg != B200ADJ_SA_BACKSOLVE) { g_create_error = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     } else {
         if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
-        if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (cfg->sensealg == B200ADJ_SA_QUADRATURE) { g_create_error = "QuadratureAdjoint not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
         if (cfg->sensealg < 0 || cfg->sensealg > 3) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
+        if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (!ros && cfg->sensealg == B200ADJ_SA_QUADRATURE) { g_create_error = "QuadratureAdjoint needs the adaptive Rosenbrock23 stepper on the device path"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "Rosenbrock23 needs abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
+    }
+    if (ros) {
+        // adaptive path: save times are arbitrary ascending points of [t0, t1] (tstops of the reverse solve)
+        for (int k = 0; k < cfg->K; k++) {
+            if (cfg->saveat[k] < cfg->t0 || cfg->saveat[k] > cfg->t1 || (k > 0 && !(cfg->saveat[k] > cfg->saveat[k - 1]))) {
+                g_create_error = "saveat must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }
+        }
+        Handle* h = new Handle();
+        h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true;
+        h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
+        h->cfg.saveat = h->saveat.data();
+        h->maxs = cfg->checkpoint_every > 1 ? cfg->checkpoint_every : 2048;      // per-member step capacity
+        h->block = cfg->block_threads ? cfg->block_threads : 128;
+        if (h->block < 32 || h->block > 256 || (h->block % 32)) { g_create_error = "block_threads must be a multiple of 32 in [32, 256] for Rosenbrock23"; delete h; return B200ADJ_ERR_INVALID; }
+        h->grid = (int)((cfg->N + h->block - 1) / h->block);
+#define CREATE_TRY(expr)                                                                         \
+        do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                                   \
+            g_create_error = std::string(#expr) + ": " + cudaGetErrorString(_e);                 \
+            int32_t rc = (_e == cudaErrorMemoryAllocation) ? B200ADJ_ERR_OOM : B200ADJ_ERR_CUDA; \
+            free_all(h); delete h; return rc; } } while (0)
+        CREATE_TRY(cudaSetDevice(cfg->device));
+        CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+        h->stream = h->own_stream;
+        const size_t N = (size_t)cfg->N, MS = (size_t)h->maxs, e = sizeof(double);
+        CREATE_TRY(cudaMalloc(&h->r_ft, (MS + 1) * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_fu, (MS + 1) * d * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_fk, MS * 2 * d * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_fn, N * sizeof(int32_t)));
+        CREATE_TRY(cudaMalloc(&h->r_rt0, MS * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_rh, MS * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_rz, MS * d * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_rk, MS * 2 * d * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_rn, N * sizeof(int32_t)));
+        CREATE_TRY(cudaMalloc(&h->d_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
+        if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * 2 * P * sizeof(double)));
+        CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
+        CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
+        if (!cfg->buffers_on_device) {
+            const size_t pn = cfg->shared_p ? (size_t)P : (size_t)P * N;
+            CREATE_TRY(cudaMalloc(&h->s_u0, d * N * e));
+            CREATE_TRY(cudaMalloc(&h->s_p, pn * e));
+            CREATE_TRY(cudaMalloc(&h->s_du0, d * N * e));
+            CREATE_TRY(cudaMalloc(&h->s_dp, pn * e));
+            CREATE_TRY(cudaMalloc(&h->s_status, N * sizeof(int32_t)));
+            if (cfg->K > 0) {
+                CREATE_TRY(cudaMalloc(&h->s_saved, (size_t)cfg->K * d * N * e));
+                if (cfg->cost_kind == B200ADJ_COST_EXPLICIT) CREATE_TRY(cudaMalloc(&h->s_dLdu, (size_t)cfg->K * d * N * e));
+            }
+        }
+#undef CREATE_TRY
+        *handle = h;
+        return B200ADJ_OK;
     }
     // fixed-step grid: the horizon must be a whole number of steps and every save time must be a grid point.
     // (Off-grid tstops split a step in the reference; that case is delegated back to the reference path.)
@@ -312,6 +418,22 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE) { h->err = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (!is_sde(c) && sensealg == B200ADJ_SA_QUADRATURE && c.stepper == B200ADJ_ST_TSIT5_FIXED && false) { h->err = "unsupported"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
+    if (h->adaptive) {
+        if (sensealg != B200ADJ_SA_GAUSS && sensealg != B200ADJ_SA_QUADRATURE) { h->err = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (K >= 0) {
+            for (int k = 0; k < K; k++)
+                if (t[k] < c.t0 || t[k] > c.t1 || (k > 0 && !(t[k] > t[k - 1]))) { h->err = "t must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            if (K > c.K) { cudaFree(h->d_saveat); h->d_saveat = nullptr; CUDA_TRY(h, cudaMalloc(&h->d_saveat, (size_t)K * sizeof(double))); cudaFree(h->s_dLdu); h->s_dLdu = nullptr; }
+            if (K > 0) CUDA_TRY(h, cudaMemcpy(h->d_saveat, t, (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+            h->saveat.assign(t, t + K); c.saveat = h->saveat.data(); c.K = K;
+        }
+        if (!c.buffers_on_device && cost_kind == B200ADJ_COST_EXPLICIT && c.K > 0 && !h->s_dLdu)
+            CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)c.K * c.d * (size_t)c.N * esz(c)));
+        c.sensealg = sensealg; c.cost_kind = cost_kind; c.cost_a = cost_a; c.cost_b = cost_b;
+        c.flags = (c.flags & (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE)) | (flags & ~(B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE));
+        return B200ADJ_OK;
+    }
     if (K >= 0) {
         if (K > 0 && !t) { h->err = "null t"; return B200ADJ_ERR_INVALID; }
         std::vector<int32_t> sos((size_t)h->S + 1, -1);
@@ -340,6 +462,16 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     return B200ADJ_OK;
 }
 
+int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_reltol, double quad_abstol, double quad_reltol) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    if (adj_abstol > 0) h->adj_abstol = adj_abstol;
+    if (adj_reltol > 0) h->adj_reltol = adj_reltol;
+    if (quad_abstol > 0) h->cfg.quad_abstol = quad_abstol;
+    if (quad_reltol > 0) h->cfg.quad_reltol = quad_reltol;
+    return B200ADJ_OK;
+}
+
 int32_t b200adj_set_stream(void* handle, void* cuda_stream) {
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
@@ -357,10 +489,16 @@ int32_t b200adj_synchronize(void* handle) {
 
 int64_t b200adj_launch_count(void* handle) { return handle ? ((Handle*)handle)->launches : -1; }
 
-int32_t b200adj_get_step_counts(void* handle, int32_t*, int32_t*) {
+int32_t b200adj_get_step_counts(void* handle, int32_t* fwd_steps, int32_t* rev_steps) {
     if (!handle) return B200ADJ_ERR_INVALID;
-    ((Handle*)handle)->err = "fixed-step handle: step count is S for every member";
-    return B200ADJ_ERR_UNSUPPORTED;
+    Handle* h = (Handle*)handle;
+    if (!h->adaptive) { h->err = "fixed-step handle: step count is S for every member"; return B200ADJ_ERR_UNSUPPORTED; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const cudaMemcpyKind kind = h->cfg.buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (fwd_steps) CUDA_TRY(h, cudaMemcpyAsync(fwd_steps, h->r_fn, (size_t)h->cfg.N * sizeof(int32_t), kind, h->stream));
+    if (rev_steps) CUDA_TRY(h, cudaMemcpyAsync(rev_steps, h->r_rn, (size_t)h->cfg.N * sizeof(int32_t), kind, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return B200ADJ_OK;
 }
 
 int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void* dW_in, void* saved, int32_t* status) {
@@ -383,7 +521,16 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     }
     h->cur_p = dp;
     int rc = 0;
-    if (!is_sde(c)) {
+    if (h->adaptive) {
+        RosArgs a = ros_args(h);
+        a.u0 = du0; a.p = dp; a.saved = c.K > 0 ? dsaved : nullptr; a.status = dstatus;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_ros_fwd<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_ros_fwd<Lorenz>(h, a); break;
+        case B200ADJ_FAM_ROBERTSON: rc = launch_ros_fwd<Robertson>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    } else if (!is_sde(c)) {
         OdeFwdArgs a;
         a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
         a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb;
@@ -448,7 +595,18 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         ddu0 = h->s_du0; ddp = h->s_dp;
     }
     int rc = 0;
-    if (!is_sde(c)) {
+    if (h->adaptive) {
+        RosArgs a = ros_args(h);
+        a.p = h->cur_p; a.dLdu = dL; a.du0 = ddu0; a.dp_members = ddp; a.dp = ddp;
+        if (h->adj_abstol > 0) a.abstol = h->adj_abstol;
+        if (h->adj_reltol > 0) a.reltol = h->adj_reltol;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_ros_rev<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_ros_rev<Lorenz>(h, a); break;
+        case B200ADJ_FAM_ROBERTSON: rc = launch_ros_rev<Robertson>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    } else if (!is_sde(c)) {
         OdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;

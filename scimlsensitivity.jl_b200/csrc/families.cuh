@@ -23,6 +23,14 @@ struct LotkaVolterra {
         T xy = u[0] * u[1];
         dg[0] = u[0] * l[0]; dg[1] = -xy * l[0]; dg[2] = -u[1] * l[1]; dg[3] = xy * l[1];
     }
+    template <class T> __device__ __forceinline__ static void jac(const T* u, const T* p, T (*J)[2]) {
+        J[0][0] = p[0] - p[1] * u[1]; J[0][1] = -p[1] * u[0];
+        J[1][0] = p[3] * u[1];        J[1][1] = -p[2] + p[3] * u[0];
+    }
+    template <class T> __device__ __forceinline__ static void djac(const T* p, const T* yd, T (*J)[2]) {
+        J[0][0] = -p[1] * yd[1]; J[0][1] = -p[1] * yd[0];
+        J[1][0] = p[3] * yd[1];  J[1][1] = p[3] * yd[0];
+    }
 };
 
 struct Lorenz {
@@ -39,6 +47,16 @@ struct Lorenz {
     }
     template <class T> __device__ __forceinline__ static void vjp_p(const T* u, const T* p, const T* l, T* dg) {
         dg[0] = (u[1] - u[0]) * l[0]; dg[1] = u[0] * l[1]; dg[2] = -u[2] * l[2];
+    }
+    template <class T> __device__ __forceinline__ static void jac(const T* u, const T* p, T (*J)[3]) {
+        J[0][0] = -p[0];       J[0][1] = p[0]; J[0][2] = 0;
+        J[1][0] = p[1] - u[2]; J[1][1] = -1;   J[1][2] = -u[0];
+        J[2][0] = u[1];        J[2][1] = u[0]; J[2][2] = -p[2];
+    }
+    template <class T> __device__ __forceinline__ static void djac(const T* p, const T* yd, T (*J)[3]) {
+        J[0][0] = 0;      J[0][1] = 0;     J[0][2] = 0;
+        J[1][0] = -yd[2]; J[1][1] = 0;     J[1][2] = -yd[0];
+        J[2][0] = yd[1];  J[2][1] = yd[0]; J[2][2] = 0;
     }
 };
 

@@ -1,0 +1,464 @@
+// ros23.cuh -- adaptive Rosenbrock23 ensemble kernels (stiff problems, BASELINE config C3): forward solve with a
+// per-member dense solution, adaptive reverse adjoint solve (GaussAdjoint: 1-point Gauss per accepted step;
+// QuadratureAdjoint: dense lambda + adaptive Gauss-Kronrod per data interval).  One member per thread; every member
+// has its own step sequence (independent error control), so control flow diverges per lane -- the members of a warp
+// are neighbouring perturbations of the same problem and stay within a few steps of each other.
+//
+// Reference functions replaced:
+//   sense functor (lambda only)     src/quadrature_adjoint.jl:35-46, src/gauss_adjoint.jl:118-128
+//   adjoint Jacobian -J(y(t))'      src/quadrature_adjoint.jl:170-192 ; d/dt of the adjoint RHS through sol(t)  :67-71
+//   dense reverse solve             src/quadrature_adjoint.jl:527-530
+//   AdjointSensitivityIntegrand     src/quadrature_adjoint.jl:486-502 ; interval loop :537-616 (quadgk per data interval)
+//   GaussIntegrand / IntegratingSumCallback   src/gauss_adjoint.jl:745-759, :809-852
+//   ReverseLossCallback             src/adjoint_common.jl:754-821
+// Upstream arithmetic restated: Rosenbrock23 (ode23s form, d = 1/(2+sqrt 2), e32 = 6+sqrt 2),
+// its 2nd-order dense output, the I-controller (exponent 1/3, gamma 0.9, q in [0.1, 5]), QuadGK G7/K15 bisection.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "families.cuh"
+#include "ode_tsit5.cuh"
+
+namespace b200adj {
+
+struct RosArgs {
+    // problem
+    const double* u0; const double* p; const double* saveat;      // saveat[K] ascending (device)
+    const double* dLdu;                                           // [K][D][N] (COST_EXPLICIT)
+    double* saved;                                                // [K][D][N] or null
+    int32_t* status;                                              // [N] or null: 0 ok, 1 non-finite, 2 max steps
+    double* du0; double* dp_members; double* partials; double* dp; unsigned int* ticket;
+    // forward dense solution (handle-owned)
+    double* ft; double* fu; double* fk; int32_t* fn;              // [MAXS+1][N], [MAXS+1][D][N], [MAXS][2][D][N], [N]
+    // reverse dense solution (QuadratureAdjoint)
+    double* rt0; double* rh; double* rz; double* rk; int32_t* rn; // [MAXS][N], [MAXS][N], [MAXS][D][N], [MAXS][2][D][N], [N]
+    double* lam0;                                                 // [D][N] lambda(t0) handed from the reverse to the quadrature kernel
+    int64_t N; int32_t K; int32_t maxs;
+    double t0, t1, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
+    uint32_t flags;                                               // bit0 no_start
+};
+
+__device__ constexpr double ROS_D = 0.29289321881345247559915563789515;
+__device__ constexpr double ROS_E32 = 6.0 + 1.4142135623730951;
+__device__ constexpr double EPS100 = 100 * 2.220446049250313e-16;
+
+// ---- small dense LU with partial pivoting (W = I - h d J) ----
+template <int D> __device__ __forceinline__ bool lu_factor(double (*A)[D], int* piv) {
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+        int pr = c; double mx = fabs(A[c][c]);
+#pragma unroll
+        for (int r = c + 1; r < D; r++) if (fabs(A[r][c]) > mx) { mx = fabs(A[r][c]); pr = r; }
+        piv[c] = pr;
+        if (mx == 0.0) return false;
+        if (pr != c) {
+#pragma unroll
+            for (int j = 0; j < D; j++) { double t = A[c][j]; A[c][j] = A[pr][j]; A[pr][j] = t; }
+        }
+#pragma unroll
+        for (int r = c + 1; r < D; r++) {
+            double f = A[r][c] / A[c][c]; A[r][c] = f;
+#pragma unroll
+            for (int j = c + 1; j < D; j++) A[r][j] -= f * A[c][j];
+        }
+    }
+    return true;
+}
+template <int D> __device__ __forceinline__ void lu_solve(const double (*A)[D], const int* piv, double* b) {
+#pragma unroll
+    for (int c = 0; c < D; c++) {
+        int pr = piv[c];
+        if (pr != c) { double t = b[c]; b[c] = b[pr]; b[pr] = t; }
+#pragma unroll
+        for (int r = c + 1; r < D; r++) b[r] -= A[r][c] * b[c];
+    }
+#pragma unroll
+    for (int r = D - 1; r >= 0; r--) {
+        double s = b[r];
+#pragma unroll
+        for (int j = r + 1; j < D; j++) s -= A[r][j] * b[j];
+        b[r] = s / A[r][r];
+    }
+}
+
+__device__ __forceinline__ double step_factor_I(double EEst) {
+    double q = pow(fmax(EEst, 1e-300), 1.0 / 3.0) / 0.9;
+    return fmax(0.1, fmin(5.0, q));
+}
+__device__ __forceinline__ double tstop_snap(double tnext, double tstop) {
+    double tol = EPS100 * fmax(fabs(tnext), fabs(tstop));
+    return (fabs(tnext - tstop) <= tol) ? tstop : tnext;
+}
+
+// ---- forward dense solution of one member: sol(y, t, continuity) and its time derivative ----
+template <int D>
+struct FwdDense {
+    const double* ft; const double* fu; const double* fk; int64_t N, i; int n;
+    __device__ __forceinline__ double T(int idx) const { return ft[(int64_t)idx * N + i]; }
+    __device__ __forceinline__ void eval(double t, bool right, double* y, double* yd) const {
+        int lo = 0, hi = n, iv;
+        if (right) { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) <= t) lo = mid; else hi = mid; } iv = lo; if (iv > n - 1) iv = n - 1; }
+        else { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) >= t) hi = mid; else lo = mid; } iv = hi - 1; if (iv < 0) iv = 0; }
+        const double ta = T(iv), h = T(iv + 1) - ta;
+        const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
+        const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
+        const double d1 = (1 - 2 * th) / (1 - 2 * ROS_D), d2 = (2 * th - 2 * ROS_D) / (1 - 2 * ROS_D);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const double u = fu[((int64_t)iv * D + j) * N + i];
+            const double k1 = fk[(((int64_t)iv * 2 + 0) * D + j) * N + i], k2 = fk[(((int64_t)iv * 2 + 1) * D + j) * N + i];
+            y[j] = u + h * (c1 * k1 + c2 * k2);
+            if (yd) yd[j] = d1 * k1 + d2 * k2;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+template <class Fam, bool SHARED_P>
+__global__ void __launch_bounds__(256) ros23_forward_kernel(RosArgs a) {
+    constexpr int D = Fam::D, P = Fam::P;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const int64_t N = a.N;
+    double p[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+    double u[D], f0[D], k1[D], k2[D], k3[D], f1[D], un[D], fn[D], tmp[D], err[D], W[D][D];
+    int piv[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) { u[j] = a.u0[(int64_t)j * N + i]; a.fu[(int64_t)j * N + i] = u[j]; }
+    a.ft[i] = a.t0;
+    Fam::f(u, p, f0);
+    double t = a.t0, h = 1e-6 * (a.t1 - a.t0);
+    int n = 0, ksave = 0, stat = 0;
+    long iters = 0;
+    // save times at or before t0
+    while (a.saved && ksave < a.K && a.saveat[ksave] <= a.t0) {
+#pragma unroll
+        for (int j = 0; j < D; j++) a.saved[((int64_t)ksave * D + j) * N + i] = u[j];
+        ksave++;
+    }
+    while (t < a.t1) {
+        if (++iters > 10000000L || n >= a.maxs) { stat = 2; break; }
+        bool last = false;
+        if (t + h >= a.t1 || fabs(t + h - a.t1) < 100 * 2.22e-16 * fabs(a.t1)) { h = a.t1 - t; last = true; }
+        // W = I - h d J ; autonomous families: dT = 0
+        Fam::jac(u, p, W);
+#pragma unroll
+        for (int r = 0; r < D; r++)
+#pragma unroll
+            for (int c = 0; c < D; c++) W[r][c] = (r == c ? 1.0 : 0.0) - h * ROS_D * W[r][c];
+        if (!lu_factor<D>(W, piv)) { stat = 1; break; }
+#pragma unroll
+        for (int j = 0; j < D; j++) k1[j] = f0[j];
+        lu_solve<D>(W, piv, k1);
+#pragma unroll
+        for (int j = 0; j < D; j++) tmp[j] = u[j] + 0.5 * h * k1[j];
+        Fam::f(tmp, p, f1);
+#pragma unroll
+        for (int j = 0; j < D; j++) k2[j] = f1[j] - k1[j];
+        lu_solve<D>(W, piv, k2);
+#pragma unroll
+        for (int j = 0; j < D; j++) { k2[j] += k1[j]; un[j] = u[j] + h * k2[j]; }
+        Fam::f(un, p, fn);
+#pragma unroll
+        for (int j = 0; j < D; j++) k3[j] = fn[j] - ROS_E32 * (k2[j] - f1[j]) - 2 * (k1[j] - f0[j]);
+        lu_solve<D>(W, piv, k3);
+        double e2 = 0;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            err[j] = h / 6.0 * (k1[j] - 2 * k2[j] + k3[j]);
+            const double sc = a.abstol + a.reltol * fmax(fabs(u[j]), fabs(un[j]));
+            e2 += (err[j] / sc) * (err[j] / sc);
+        }
+        const double EEst = sqrt(e2 / D);
+        const double q = step_factor_I(EEst);
+        if (EEst <= 1.0) {
+            const double tn = last ? a.t1 : t + h;
+            // primal at save times inside (t, tn] from this step's dense output (sol(ts), left-continuous lookup)
+            while (a.saved && ksave < a.K && a.saveat[ksave] <= tn) {
+                const double hh = tn - t, th = (hh == 0.0) ? 1.0 : (a.saveat[ksave] - t) / hh;
+                const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
+#pragma unroll
+                for (int j = 0; j < D; j++) a.saved[((int64_t)ksave * D + j) * N + i] = u[j] + hh * (c1 * k1[j] + c2 * k2[j]);
+                ksave++;
+            }
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                a.fk[(((int64_t)n * 2 + 0) * D + j) * N + i] = k1[j];
+                a.fk[(((int64_t)n * 2 + 1) * D + j) * N + i] = k2[j];
+                a.fu[((int64_t)(n + 1) * D + j) * N + i] = un[j];
+                u[j] = un[j]; f0[j] = fn[j];
+            }
+            t = tn; a.ft[(int64_t)(n + 1) * N + i] = t;
+            n++;
+        }
+        h = h / q;
+    }
+    a.fn[i] = n;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < D; j++) ok = ok && isfinite(u[j]);
+    if (!ok && stat == 0) stat = 1;
+    if (a.status) a.status[i] = stat;
+}
+
+// adjoint RHS  dlam = -J(y(t))' lam  (right-continuous forward lookup) and, on request, its Jacobian / time derivative
+template <class Fam, int D>
+__device__ __forceinline__ void adj_rhs(const FwdDense<D>& sol, const double* p, double t, const double* lam, double* out) {
+    double y[D];
+    sol.eval(t, true, y, nullptr);
+    Fam::vjp_u(y, p, lam, out);
+#pragma unroll
+    for (int j = 0; j < D; j++) out[j] = -out[j];
+}
+
+template <class Fam, int SA, bool SHARED_P, int COST>
+__global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
+    constexpr int D = Fam::D, P = Fam::P;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gi < a.N;
+    const int64_t i = active ? gi : a.N - 1;
+    const int64_t N = a.N;
+    double p[P], acc[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; acc[q] = 0.0; }
+    FwdDense<D> sol{a.ft, a.fu, a.fk, N, i, a.fn[i]};
+    double z[D], zn[D], f0[D], k1[D], k2[D], k3[D], f1[D], fnr[D], tmp[D], W[D][D], dT[D];
+    int piv[D];
+#pragma unroll
+    for (int j = 0; j < D; j++) z[j] = 0.0;
+    const double T = a.t1, t0 = a.t0;
+    double t = T;
+    int cur = a.K - 1, nrev = 0;
+    bool fsal_ok = false;
+    auto jump_if_at = [&](double tt) {
+        while (cur >= 0 && fabs(a.saveat[cur] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
+            if (!((a.flags & 1u) && cur == 0)) {
+                double y[D];
+                if (COST == COST_EXPLICIT) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[j] += a.dLdu[((int64_t)cur * D + j) * N + i];
+                } else {
+                    sol.eval(a.saveat[cur], true, y, nullptr);
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[j] += a.cost_a * y[j] + a.cost_b;
+                }
+            }
+            cur--; fsal_ok = false;
+        }
+    };
+    jump_if_at(t);
+    double h = -1e-4 * (T - t0);
+    long iters = 0;
+    while (t > t0 && sol.n > 0) {
+        if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) break;
+        double tstop = t0;
+        if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
+        double tn = tstop_snap(t + h, tstop);
+        if (tn < tstop) tn = tstop;
+        const double hs = tn - t;
+        if (!fsal_ok) adj_rhs<Fam, D>(sol, p, t, z, f0);
+        // Jacobian of the adjoint RHS wrt lambda (-J') and its time derivative -(dJ/dt)' lambda, ydot from the interpolant
+        {
+            double y[D], yd[D], J[D][D], dJ[D][D];
+            sol.eval(t, true, y, yd);
+            Fam::jac(y, p, J); Fam::djac(p, yd, dJ);
+#pragma unroll
+            for (int r = 0; r < D; r++) {
+                double s = 0;
+#pragma unroll
+                for (int c = 0; c < D; c++) { W[r][c] = (r == c ? 1.0 : 0.0) - hs * ROS_D * (-J[c][r]); s -= dJ[c][r] * z[c]; }
+                dT[r] = s;
+            }
+        }
+        if (!lu_factor<D>(W, piv)) break;
+#pragma unroll
+        for (int j = 0; j < D; j++) k1[j] = f0[j] + hs * ROS_D * dT[j];
+        lu_solve<D>(W, piv, k1);
+#pragma unroll
+        for (int j = 0; j < D; j++) tmp[j] = z[j] + 0.5 * hs * k1[j];
+        adj_rhs<Fam, D>(sol, p, t + 0.5 * hs, tmp, f1);
+#pragma unroll
+        for (int j = 0; j < D; j++) k2[j] = f1[j] - k1[j];
+        lu_solve<D>(W, piv, k2);
+#pragma unroll
+        for (int j = 0; j < D; j++) { k2[j] += k1[j]; zn[j] = z[j] + hs * k2[j]; }
+        adj_rhs<Fam, D>(sol, p, t + hs, zn, fnr);
+#pragma unroll
+        for (int j = 0; j < D; j++) k3[j] = fnr[j] - ROS_E32 * (k2[j] - f1[j]) - 2 * (k1[j] - f0[j]) + hs * ROS_D * dT[j];
+        lu_solve<D>(W, piv, k3);
+        double e2 = 0;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            const double e = hs / 6.0 * (k1[j] - 2 * k2[j] + k3[j]);
+            const double sc = a.abstol + a.reltol * fmax(fabs(z[j]), fabs(zn[j]));
+            e2 += (e / sc) * (e / sc);
+        }
+        const double EEst = sqrt(e2 / D);
+        const double q = step_factor_I(EEst);
+        if (EEst > 1.0) { h = hs / q; fsal_ok = true; continue; }
+        h = hs / q;
+        if (SA == SA_GAUSS) {
+            // IntegratingSumCallback, n = (alg_order+1) div 2 = 1 node: midpoint, weight 2, scale (tn - t)/2, integrand -F'lam
+            const double tj = 0.5 * (tn + t), th = (tj - t) / hs;
+            const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
+            double lq[D], y[D], dg[P];
+#pragma unroll
+            for (int j = 0; j < D; j++) lq[j] = z[j] + hs * (c1 * k1[j] + c2 * k2[j]);
+            sol.eval(tj, false, y, nullptr);
+            Fam::vjp_p(y, p, lq, dg);
+#pragma unroll
+            for (int q2 = 0; q2 < P; q2++) acc[q2] += (0.5 * (tn - t)) * 2.0 * (-dg[q2]);
+        } else if (active) {
+            a.rt0[(int64_t)nrev * N + i] = t; a.rh[(int64_t)nrev * N + i] = hs;
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                a.rz[((int64_t)nrev * D + j) * N + i] = z[j];
+                a.rk[(((int64_t)nrev * 2 + 0) * D + j) * N + i] = k1[j];
+                a.rk[(((int64_t)nrev * 2 + 1) * D + j) * N + i] = k2[j];
+            }
+        }
+        nrev++;
+#pragma unroll
+        for (int j = 0; j < D; j++) { z[j] = zn[j]; f0[j] = fnr[j]; }
+        fsal_ok = true;
+        t = tn;
+        jump_if_at(t);
+    }
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < D; j++) a.du0[(int64_t)j * N + i] = z[j];
+        if (SA == SA_QUAD) a.rn[i] = nrev;
+    }
+    if (SA == SA_GAUSS) {
+        if (SHARED_P) {
+            if (!active) {
+#pragma unroll
+                for (int q = 0; q < P; q++) acc[q] = 0.0;
+            }
+            reduce_dp<P>(acc, a.partials, a.dp, a.ticket);
+        } else if (active) {
+#pragma unroll
+            for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = acc[q];
+        }
+    }
+}
+
+// ---- QuadGK (7,15) ----
+__device__ const double XGK[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
+    0.864864423359769072789712788640926, 0.741531185599394439863864773280788, 0.586087235467691130294144838258730,
+    0.405845151377397166906606412076961, 0.207784955007898467600689403773245, 0.0};
+__device__ const double WGK[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
+    0.104790010322250183839876322541518, 0.140653259715525918745189590510238, 0.169004726639267902826583426598550,
+    0.190350578064785409913256402421014, 0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
+__device__ const double WG[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
+    0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
+
+template <class Fam, int D, int P>
+struct QuadCtx {
+    FwdDense<D> sol; const double* rt0; const double* rh; const double* rz; const double* rk; int nrev; int64_t N, i; const double* p;
+    // AdjointSensitivityIntegrand: out = (df/dp)(y(t))' lam(t), y left-continuous, lam from the dense reverse solution
+    __device__ __forceinline__ void operator()(double t, double* out) const {
+        double y[D], lam[D];
+        sol.eval(t, false, y, nullptr);
+        int lo = 0, hi = nrev - 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (rt0[(int64_t)mid * N + i] + rh[(int64_t)mid * N + i] <= t) hi = mid; else lo = mid + 1; }
+        const double ts = rt0[(int64_t)lo * N + i], h = rh[(int64_t)lo * N + i], th = (t - ts) / h;
+        const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
+#pragma unroll
+        for (int j = 0; j < D; j++)
+            lam[j] = rz[((int64_t)lo * D + j) * N + i] + h * (c1 * rk[(((int64_t)lo * 2 + 0) * D + j) * N + i] + c2 * rk[(((int64_t)lo * 2 + 1) * D + j) * N + i]);
+        Fam::vjp_p(y, p, lam, out);
+    }
+};
+
+template <int P, class F>
+__device__ __forceinline__ void gk15(const F& f, double a, double b, double* Ik, double* err) {
+    const double c = 0.5 * (a + b), hl = 0.5 * (b - a);
+    double Ig[P], w1[P], w2[P];
+    f(c, w1);
+#pragma unroll
+    for (int q = 0; q < P; q++) { Ik[q] = WGK[7] * w1[q]; Ig[q] = WG[3] * w1[q]; }
+    for (int j = 0; j < 7; j++) {
+        f(c - hl * XGK[j], w1); f(c + hl * XGK[j], w2);
+#pragma unroll
+        for (int q = 0; q < P; q++) {
+            Ik[q] += WGK[j] * (w1[q] + w2[q]);
+            if (j & 1) Ig[q] += WG[j / 2] * (w1[q] + w2[q]);
+        }
+    }
+    double e2 = 0;
+#pragma unroll
+    for (int q = 0; q < P; q++) { Ik[q] *= hl; Ig[q] *= hl; e2 += (Ik[q] - Ig[q]) * (Ik[q] - Ig[q]); }
+    *err = sqrt(e2);
+}
+
+constexpr int QGK_MAXSEG = 96;
+// adaptive quadgk over [a,b]: bisect the largest-error segment until E <= max(atol, rtol*|I|) (2-norm)
+template <int P, class F>
+__device__ void quadgk(const F& f, double a, double b, double atol, double rtol, double* out) {
+    double sa[QGK_MAXSEG], sb[QGK_MAXSEG], se[QGK_MAXSEG], sI[QGK_MAXSEG][P];
+    int n = 1;
+    sa[0] = a; sb[0] = b;
+    gk15<P>(f, a, b, sI[0], &se[0]);
+    for (;;) {
+        double E = 0, nI = 0;
+#pragma unroll
+        for (int q = 0; q < P; q++) { double s = 0; for (int k = 0; k < n; k++) s += sI[k][q]; out[q] = s; nI += s * s; }
+        for (int k = 0; k < n; k++) E += se[k];
+        nI = sqrt(nI);
+        if (E <= fmax(atol, rtol * nI) || n + 1 > QGK_MAXSEG) break;
+        int w = 0;
+        for (int k = 1; k < n; k++) if (se[k] > se[w]) w = k;
+        const double mid = 0.5 * (sa[w] + sb[w]);
+        if (!(mid > fmin(sa[w], sb[w]) && mid < fmax(sa[w], sb[w]))) break;
+        sa[n] = mid; sb[n] = sb[w]; sb[w] = mid;
+        gk15<P>(f, sa[w], sb[w], sI[w], &se[w]);
+        gk15<P>(f, sa[n], sb[n], sI[n], &se[n]);
+        n++;
+    }
+}
+
+template <class Fam, bool SHARED_P>
+__global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
+    constexpr int D = Fam::D, P = Fam::P;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gi < a.N;
+    const int64_t i = active ? gi : a.N - 1;
+    const int64_t N = a.N;
+    double p[P], res[P], part[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; res[q] = 0.0; }
+    QuadCtx<Fam, D, P> ctx{FwdDense<D>{a.ft, a.fu, a.fk, N, i, a.fn[i]}, a.rt0, a.rh, a.rz, a.rk, a.rn[i], N, i, p};
+    const int K = a.K;
+    if (ctx.nrev > 0) {
+        if (K == 0) { quadgk<P>(ctx, a.t0, a.t1, a.quad_abstol, a.quad_reltol, res); }
+        else {
+            if (a.saveat[K - 1] != a.t1) { quadgk<P>(ctx, a.saveat[K - 1], a.t1, a.quad_abstol, a.quad_reltol, part);
+#pragma unroll
+                for (int q = 0; q < P; q++) res[q] += part[q]; }
+            for (int k = K - 2; k >= 0; k--) {
+                if (a.saveat[k] == a.saveat[k + 1]) continue;
+                quadgk<P>(ctx, a.saveat[k], a.saveat[k + 1], a.quad_abstol, a.quad_reltol, part);
+#pragma unroll
+                for (int q = 0; q < P; q++) res[q] += part[q];
+            }
+            if (a.saveat[0] != a.t0) { quadgk<P>(ctx, a.t0, a.saveat[0], a.quad_abstol, a.quad_reltol, part);
+#pragma unroll
+                for (int q = 0; q < P; q++) res[q] += part[q]; }
+        }
+    }
+    if (SHARED_P) {
+        if (!active) {
+#pragma unroll
+            for (int q = 0; q < P; q++) res[q] = 0.0;
+        }
+        reduce_dp<P>(res, a.partials, a.dp, a.ticket);
+    } else if (active) {
+#pragma unroll
+        for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = res[q];
+    }
+}
+
+}  // namespace b200adj

@@ -19,7 +19,7 @@ class DeviceEnsemble:
     def __init__(self, family, sensealg, stepper, N, saveat, tspan, dt, *, shared_p=True, cost=None,
                  on_device=False, device=0, no_start=False, checkpointing=True, ckpt_every_step=False,
                  stored_noise=False, seed=0, traj_offset=0, block_threads=0, abstol=1e-6, reltol=1e-3,
-                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False):
+                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False, max_steps=0):
         d, P, m = FAMILIES[family]
         cfg = _lib.Cfg()
         cfg.rhs_family, cfg.sensealg, cfg.stepper, cfg.dtype = _lib.FAM[family], _lib.SA[sensealg], _lib.ST[stepper], _lib.DTYPE[dtype]
@@ -32,7 +32,7 @@ class DeviceEnsemble:
         else:
             cfg.cost_kind = _lib.COST["explicit"]
         cfg.seed, cfg.traj_offset = int(seed), int(traj_offset)
-        cfg.checkpoint_every = 1
+        cfg.checkpoint_every = int(max_steps) if max_steps else 1      # adaptive handles: per-member step capacity
         flags = 0
         if no_start:
             flags |= _lib.FLAG_NO_START
@@ -47,7 +47,8 @@ class DeviceEnsemble:
         cfg.flags, cfg.block_threads = flags, int(block_threads)
         self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
         self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)
-        self.S = int(round((cfg.t1 - cfg.t0) / cfg.dt))
+        self.adaptive = stepper == "rosenbrock23"
+        self.S = 0 if self.adaptive else int(round((cfg.t1 - cfg.t0) / cfg.dt))
         self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
         self.handle = _lib.Handle(cfg, self.saveat)
         self._keep = []
@@ -119,6 +120,12 @@ class DeviceEnsemble:
         if t is not None:
             self.saveat = np.ascontiguousarray(t, dtype=np.float64)
             self.K = len(self.saveat)
+
+    def step_counts(self):
+        """(forward, reverse) accepted-step counts per member of an adaptive handle."""
+        f, r = self._empty(self.N, dtype="i32"), self._empty(self.N, dtype="i32")
+        self.handle.step_counts(f, r)
+        return f, r
 
     def noise(self):
         out = self._empty(self.S, self.m, self.N)

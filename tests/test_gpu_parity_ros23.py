@@ -1,0 +1,71 @@
+"""Adaptive Rosenbrock23 (stiff) path on the device against the oracle: forward dense solve, adaptive reverse solve,
+GaussAdjoint (1-point per step) and QuadratureAdjoint (dense lambda + adaptive Gauss-Kronrod per data interval).
+BASELINE config C3 (Robertson, QuadratureAdjoint, Rosenbrock23) asks <= 1e-5 relative; both sides take the same
+accept/reject decisions, observed agreement ~1e-10."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import scimlsensitivity_jl_b200 as b
+from oracle import oracle as O
+
+
+def _rel(a, ref):
+    return np.abs(np.asarray(a) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+def _robertson(N, seed=0, shared=False):
+    rng = np.random.default_rng(seed)
+    u0 = np.repeat(np.array([[1.0], [0.0], [0.0]]), N, 1)
+    k = np.array([0.04, 3e7, 1e4])
+    if shared:
+        return u0, k
+    return u0, k[:, None] * np.exp(0.05 * rng.standard_normal((3, N)))
+
+
+@pytest.mark.parametrize("sensealg", ["quadrature", "gauss"])
+@pytest.mark.parametrize("shared_p", [False, True])
+@pytest.mark.parametrize("cost", ["affine", "explicit"])
+def test_robertson_ros23(sensealg, shared_p, cost):
+    N, T = 100, 100.0
+    saveat = np.logspace(-2, 2, 10); saveat[-1] = T
+    u0, k = _robertson(N, shared=shared_p)
+    tol = dict(abstol=1e-8, reltol=1e-8)
+    cfg = O.make_cfg("robertson", sensealg, "rosenbrock23", N, saveat, 0.0, T, cost=("affine", 1.0, 0.0), shared_p=shared_p,
+                     quad_abstol=1e-10, quad_reltol=1e-10, **tol)
+    ref = O.gradient(cfg, saveat, u0, k)
+    eng = b.DeviceEnsemble("robertson", sensealg, "rosenbrock23", N, saveat, (0.0, T), 0.0, shared_p=shared_p,
+                           cost=b.AffineCost(1.0, 0.0) if cost == "affine" else None, quad_abstol=1e-10, quad_reltol=1e-10, **tol)
+    saved, status = eng.forward(u0, k)
+    assert (status == 0).all()
+    assert np.abs(saved - ref["saved"]).max() < 1e-11
+    du0, dp = eng.reverse(None if cost == "affine" else saved)
+    fsteps, rsteps = eng.step_counts()
+    assert np.array_equal(fsteps, ref["steps"])                 # identical accept/reject sequence
+    assert _rel(du0, ref["du0"]) < 1e-7
+    # dp components span 10 orders of magnitude (d/dk2 ~ 1e-9): compare per parameter
+    refdp, gdp = np.atleast_2d(ref["dp"].T).T.reshape(3, -1), np.atleast_2d(np.asarray(dp).T).T.reshape(3, -1)
+    for q in range(3):
+        assert _rel(gdp[q], refdp[q]) < 1e-6, (q, gdp[q][:3], refdp[q][:3])
+    eng.close()
+
+
+def test_lorenz_ros23_nonstiff_and_public_api():
+    """Rosenbrock23 on a non-stiff problem through the public API (test/Core2/stiff_adjoints.jl:204-252 uses stiff
+    solvers on a non-stiff LV/Lorenz-like problem and asks the sensealgs to agree at rtol 1e-2)."""
+    N, T = 64, 1.0
+    rng = np.random.default_rng(2)
+    u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N))
+    p = np.array([10.0, 28.0, 8.0 / 3.0])
+    t = np.linspace(0.1, T, 10)
+    prob = b.EnsembleProblem(b.ODEProblem("lorenz", u0[:, 0], (0.0, T), p), u0s=u0)
+    sol = b.solve(prob, b.Rosenbrock23(), saveat=t, abstol=1e-8, reltol=1e-8, sensealg=b.B200Adjoint(b.QuadratureAdjoint(abstol=1e-10, reltol=1e-10)))
+    res = {}
+    for inner, name in ((b.QuadratureAdjoint(abstol=1e-10, reltol=1e-10), "quadrature"), (b.GaussAdjoint(), "gauss")):
+        du0, dp = b.adjoint_sensitivities(sol, b.Rosenbrock23(), t=t, dgdu_discrete=b.AffineCost(1.0, -2.0), sensealg=inner, abstol=1e-8, reltol=1e-8)
+        cfg = O.make_cfg("lorenz", name, "rosenbrock23", N, t, 0.0, T, abstol=1e-8, reltol=1e-8, cost=("affine", 1.0, -2.0), quad_abstol=1e-10, quad_reltol=1e-10)
+        ref = O.gradient(cfg, t, u0, p)
+        assert _rel(du0, ref["du0"]) < 1e-7 and _rel(dp.ravel(), ref["dp"]) < 1e-7
+        res[name] = dp.ravel()
+    assert _rel(res["gauss"], res["quadrature"]) < 1e-2
