@@ -696,26 +696,33 @@ static void gk15(integrand_fn f, void* ctx, int P, double a, double b, double* I
     for (int q = 0; q < P; q++) { Ik[q] *= hl; Ig[q] *= hl; e2 += (Ik[q] - Ig[q]) * (Ik[q] - Ig[q]); }
     *err = sqrt(e2);
 }
+/* QuadGK.jl's adapt loop: pop the largest-error segment, bisect, and update the running totals INCREMENTALLY
+ * (I = (I - s.I) + s1.I + s2.I, E likewise); the running I is what is returned. */
 long oracle_quadgk(integrand_fn f, void* ctx, int P, double a, double b, double atol, double rtol, double* out) {
     int cap = 64, n = 1; long evals = 15;
     gkseg* S = (gkseg*)malloc(sizeof(gkseg) * cap);
-    double* w1 = (double*)malloc(sizeof(double) * P * 3), *w2 = w1 + P, *Ig = w2 + P;
+    double* w1 = (double*)malloc(sizeof(double) * P * 5), *w2 = w1 + P, *Ig = w2 + P, *Il = Ig + P, *Ir = Il + P;
     S[0].a = a; S[0].b = b; S[0].I = (double*)malloc(sizeof(double) * P);
     gk15(f, ctx, P, a, b, S[0].I, &S[0].err, w1, w2, Ig);
+    double E = S[0].err;
+    for (int q = 0; q < P; q++) out[q] = S[0].I[q];
     for (;;) {
-        double E = 0, nI = 0;
-        for (int q = 0; q < P; q++) { double s = 0; for (int i = 0; i < n; i++) s += S[i].I[q]; out[q] = s; nI += s * s; }
-        for (int i = 0; i < n; i++) E += S[i].err;
+        double nI = 0;
+        for (int q = 0; q < P; q++) nI += out[q] * out[q];
         nI = sqrt(nI);
-        if (E <= fmax(atol, rtol * nI) || evals > 10000000 || n > 100000) break;
+        if (E <= fmax(atol, rtol * nI) || evals > 10000000 || n > 1000000) break;
         int w = 0; for (int i = 1; i < n; i++) if (S[i].err > S[w].err) w = i;
         double mid = 0.5 * (S[w].a + S[w].b);
         if (!(mid > fmin(S[w].a, S[w].b) && mid < fmax(S[w].a, S[w].b))) break;
         if (n + 1 > cap) { cap *= 2; S = (gkseg*)realloc(S, sizeof(gkseg) * cap); }
-        S[n].a = mid; S[n].b = S[w].b; S[n].I = (double*)malloc(sizeof(double) * P);
-        S[w].b = mid;
-        gk15(f, ctx, P, S[w].a, S[w].b, S[w].I, &S[w].err, w1, w2, Ig);
-        gk15(f, ctx, P, S[n].a, S[n].b, S[n].I, &S[n].err, w1, w2, Ig);
+        double el, er;
+        gk15(f, ctx, P, S[w].a, mid, Il, &el, w1, w2, Ig);
+        gk15(f, ctx, P, mid, S[w].b, Ir, &er, w1, w2, Ig);
+        E += (el + er) - S[w].err;
+        S[n].I = (double*)malloc(sizeof(double) * P);
+        for (int q = 0; q < P; q++) { out[q] += (Il[q] + Ir[q]) - S[w].I[q]; S[w].I[q] = Il[q]; S[n].I[q] = Ir[q]; }
+        S[n].a = mid; S[n].b = S[w].b; S[n].err = er;
+        S[w].b = mid; S[w].err = el;
         n++; evals += 30;
     }
     for (int i = 0; i < n; i++) free(S[i].I);

@@ -39,7 +39,8 @@ struct Handle {
     bool adaptive = false; int maxs = 0;
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
-    int32_t *r_fn = nullptr, *r_rn = nullptr;
+    int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
+    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0;
     // staging (buffers_on_device == 0)
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
@@ -218,6 +219,7 @@ RosArgs ros_args(Handle* h) {
     a.saveat = h->d_saveat; a.partials = h->d_partials; a.ticket = h->d_ticket;
     a.ft = h->r_ft; a.fu = h->r_fu; a.fk = h->r_fk; a.fn = h->r_fn;
     a.rt0 = h->r_rt0; a.rh = h->r_rh; a.rz = h->r_rz; a.rk = h->r_rk; a.rn = h->r_rn;
+    a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.qidx = h->r_qidx; a.maxseg = h->maxseg;
     a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.abstol = c.abstol; a.reltol = c.reltol;
     a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
     a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
@@ -229,7 +231,7 @@ size_t esz(const b200adj_cfg&) { return sizeof(double); }
 void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
-    cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn);
+    cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
     cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status);
@@ -285,7 +287,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true;
         h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
         h->cfg.saveat = h->saveat.data();
-        h->maxs = cfg->checkpoint_every > 1 ? cfg->checkpoint_every : 2048;      // per-member step capacity
+        h->maxs = cfg->checkpoint_every > 1 ? cfg->checkpoint_every : 4096;      // per-member step capacity (forward and dense reverse)
         h->block = cfg->block_threads ? cfg->block_threads : 128;
         if (h->block < 32 || h->block > 256 || (h->block % 32)) { g_create_error = "block_threads must be a multiple of 32 in [32, 256] for Rosenbrock23"; delete h; return B200ADJ_ERR_INVALID; }
         h->grid = (int)((cfg->N + h->block - 1) / h->block);
@@ -307,6 +309,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         CREATE_TRY(cudaMalloc(&h->r_rz, MS * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_rk, MS * 2 * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_rn, N * sizeof(int32_t)));
+        h->maxseg = 2 * h->maxs;                                              // quadgk segment capacity per member
+        CREATE_TRY(cudaMalloc(&h->r_qseg, (size_t)h->maxseg * (2 + P) * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_qkey, (size_t)h->maxseg * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_qidx, (size_t)h->maxseg * N * sizeof(int32_t)));
         CREATE_TRY(cudaMalloc(&h->d_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
         if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * 2 * P * sizeof(double)));

@@ -32,7 +32,7 @@ struct RosArgs {
     double* ft; double* fu; double* fk; int32_t* fn;              // [MAXS+1][N], [MAXS+1][D][N], [MAXS][2][D][N], [N]
     // reverse dense solution (QuadratureAdjoint)
     double* rt0; double* rh; double* rz; double* rk; int32_t* rn; // [MAXS][N], [MAXS][N], [MAXS][D][N], [MAXS][2][D][N], [N]
-    double* lam0;                                                 // [D][N] lambda(t0) handed from the reverse to the quadrature kernel
+    double* qseg; double* qkey; int32_t* qidx; int32_t maxseg;   // quadgk segment store [maxseg][2+P][N], heap [maxseg][N]
     int64_t N; int32_t K; int32_t maxs;
     double t0, t1, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
     uint32_t flags;                                               // bit0 no_start
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
     const double T = a.t1, t0 = a.t0;
     double t = T;
     int cur = a.K - 1, nrev = 0;
-    bool fsal_ok = false;
+    bool fsal_ok = false, overflow = false;
     auto jump_if_at = [&](double tt) {
         while (cur >= 0 && fabs(a.saveat[cur] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
             if (!((a.flags & 1u) && cur == 0)) {
@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
     double h = -1e-4 * (T - t0);
     long iters = 0;
     while (t > t0 && sol.n > 0) {
-        if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) break;
+        if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) { overflow = true; break; }
         double tstop = t0;
         if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
         double tn = tstop_snap(t + h, tstop);
@@ -327,9 +327,10 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
         jump_if_at(t);
     }
     if (active) {
+        // a member whose dense reverse solution did not fit (max steps) fails loudly: NaN gradient, never a silent partial
 #pragma unroll
-        for (int j = 0; j < D; j++) a.du0[(int64_t)j * N + i] = z[j];
-        if (SA == SA_QUAD) a.rn[i] = nrev;
+        for (int j = 0; j < D; j++) a.du0[(int64_t)j * N + i] = overflow ? __longlong_as_double(0x7ff8000000000000LL) : z[j];
+        if (SA == SA_QUAD) a.rn[i] = overflow ? -1 : nrev;
     }
     if (SA == SA_GAUSS) {
         if (SHARED_P) {
@@ -394,30 +395,71 @@ __device__ __forceinline__ void gk15(const F& f, double a, double b, double* Ik,
     *err = sqrt(e2);
 }
 
-constexpr int QGK_MAXSEG = 96;
-// adaptive quadgk over [a,b]: bisect the largest-error segment until E <= max(atol, rtol*|I|) (2-norm)
+// Segment store of one member's adaptive quadrature, in a handle-owned global scratch (member-minor):
+//   seg [maxseg][2+P][N] = (a, b, I[P]) per segment id, key [maxseg][N] / idx [maxseg][N] = binary max-heap on the error.
+// QuadGK bisects the largest-error segment; a heap gives the same argmax as the oracle's linear scan (no ties in
+// practice) at O(log n) per bisection -- the dense reverse solution is only C1 at step boundaries, so a 1e-10 tolerance
+// drives thousands of segments per data interval.
+struct QuadScratch { double* seg; double* key; int32_t* idx; int maxseg; int64_t N, i; };
+
+// adaptive quadgk over [a,b]: bisect the largest-error segment until E <= max(atol, rtol*|I|) (2-norm).  false = out of
+// segment capacity.
 template <int P, class F>
-__device__ void quadgk(const F& f, double a, double b, double atol, double rtol, double* out) {
-    double sa[QGK_MAXSEG], sb[QGK_MAXSEG], se[QGK_MAXSEG], sI[QGK_MAXSEG][P];
-    int n = 1;
-    sa[0] = a; sb[0] = b;
-    gk15<P>(f, a, b, sI[0], &se[0]);
-    for (;;) {
-        double E = 0, nI = 0;
+__device__ bool quadgk(const F& f, double a, double b, double atol, double rtol, double* out, const QuadScratch& q) {
+    const int64_t N = q.N, i = q.i;
+    auto SEG = [&](int k, int c) -> double& { return q.seg[((int64_t)k * (2 + P) + c) * N + i]; };
+    auto KEY = [&](int k) -> double& { return q.key[(int64_t)k * N + i]; };
+    auto IDX = [&](int k) -> int32_t& { return q.idx[(int64_t)k * N + i]; };
+    double I[P], Itot[P], e, Etot;
+    gk15<P>(f, a, b, I, &e);
+    SEG(0, 0) = a; SEG(0, 1) = b;
 #pragma unroll
-        for (int q = 0; q < P; q++) { double s = 0; for (int k = 0; k < n; k++) s += sI[k][q]; out[q] = s; nI += s * s; }
-        for (int k = 0; k < n; k++) E += se[k];
+    for (int c = 0; c < P; c++) { SEG(0, 2 + c) = I[c]; Itot[c] = I[c]; }
+    KEY(0) = e; IDX(0) = 0; Etot = e;
+    int nseg = 1;
+    bool ok = true;
+    for (;;) {
+        double nI = 0;
+#pragma unroll
+        for (int c = 0; c < P; c++) nI += Itot[c] * Itot[c];
         nI = sqrt(nI);
-        if (E <= fmax(atol, rtol * nI) || n + 1 > QGK_MAXSEG) break;
-        int w = 0;
-        for (int k = 1; k < n; k++) if (se[k] > se[w]) w = k;
-        const double mid = 0.5 * (sa[w] + sb[w]);
-        if (!(mid > fmin(sa[w], sb[w]) && mid < fmax(sa[w], sb[w]))) break;
-        sa[n] = mid; sb[n] = sb[w]; sb[w] = mid;
-        gk15<P>(f, sa[w], sb[w], sI[w], &se[w]);
-        gk15<P>(f, sa[n], sb[n], sI[n], &se[n]);
-        n++;
+        if (Etot <= fmax(atol, rtol * nI)) break;
+        if (nseg + 1 > q.maxseg) { ok = false; break; }
+        const int w = IDX(0);
+        const double aw = SEG(w, 0), bw = SEG(w, 1), ew = KEY(0);
+        const double mid = 0.5 * (aw + bw);
+        if (!(mid > fmin(aw, bw) && mid < fmax(aw, bw))) break;
+        double Il[P], Ir[P], el, er;
+        gk15<P>(f, aw, mid, Il, &el);
+        gk15<P>(f, mid, bw, Ir, &er);
+        Etot += (el + er) - ew;
+#pragma unroll
+        for (int c = 0; c < P; c++) { Itot[c] += (Il[c] + Ir[c]) - SEG(w, 2 + c); SEG(w, 2 + c) = Il[c]; SEG(nseg, 2 + c) = Ir[c]; }
+        SEG(w, 1) = mid; SEG(nseg, 0) = mid; SEG(nseg, 1) = bw;
+        // root <- left half, sift down
+        int hpos = 0; double hk = el; int hi_ = w;
+        for (;;) {
+            int l = 2 * hpos + 1, r = l + 1, m = hpos; double mk = hk;
+            if (l < nseg && KEY(l) > mk) { m = l; mk = KEY(l); }
+            if (r < nseg && KEY(r) > mk) { m = r; mk = KEY(r); }
+            if (m == hpos) break;
+            KEY(hpos) = KEY(m); IDX(hpos) = IDX(m); hpos = m;
+        }
+        KEY(hpos) = hk; IDX(hpos) = hi_;
+        // push right half, sift up
+        hpos = nseg; hk = er; hi_ = nseg;
+        while (hpos > 0) {
+            int par = (hpos - 1) >> 1;
+            if (KEY(par) >= hk) break;
+            KEY(hpos) = KEY(par); IDX(hpos) = IDX(par); hpos = par;
+        }
+        KEY(hpos) = hk; IDX(hpos) = hi_;
+        nseg++;
     }
+    // QuadGK returns the running total
+#pragma unroll
+    for (int c = 0; c < P; c++) out[c] = Itot[c];
+    return ok;
 }
 
 template <class Fam, bool SHARED_P>
@@ -432,22 +474,31 @@ __global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
     for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; res[q] = 0.0; }
     QuadCtx<Fam, D, P> ctx{FwdDense<D>{a.ft, a.fu, a.fk, N, i, a.fn[i]}, a.rt0, a.rh, a.rz, a.rk, a.rn[i], N, i, p};
     const int K = a.K;
-    if (ctx.nrev > 0) {
-        if (K == 0) { quadgk<P>(ctx, a.t0, a.t1, a.quad_abstol, a.quad_reltol, res); }
+    const QuadScratch qs{a.qseg, a.qkey, a.qidx, a.maxseg, N, i};
+    bool ok = true;
+    if (ctx.nrev < 0) {
+#pragma unroll
+        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
+    } else if (ctx.nrev > 0) {
+        if (K == 0) { ok = quadgk<P>(ctx, a.t0, a.t1, a.quad_abstol, a.quad_reltol, res, qs); }
         else {
-            if (a.saveat[K - 1] != a.t1) { quadgk<P>(ctx, a.saveat[K - 1], a.t1, a.quad_abstol, a.quad_reltol, part);
+            if (a.saveat[K - 1] != a.t1) { ok = quadgk<P>(ctx, a.saveat[K - 1], a.t1, a.quad_abstol, a.quad_reltol, part, qs) && ok;
 #pragma unroll
                 for (int q = 0; q < P; q++) res[q] += part[q]; }
             for (int k = K - 2; k >= 0; k--) {
                 if (a.saveat[k] == a.saveat[k + 1]) continue;
-                quadgk<P>(ctx, a.saveat[k], a.saveat[k + 1], a.quad_abstol, a.quad_reltol, part);
+                ok = quadgk<P>(ctx, a.saveat[k], a.saveat[k + 1], a.quad_abstol, a.quad_reltol, part, qs) && ok;
 #pragma unroll
                 for (int q = 0; q < P; q++) res[q] += part[q];
             }
-            if (a.saveat[0] != a.t0) { quadgk<P>(ctx, a.t0, a.saveat[0], a.quad_abstol, a.quad_reltol, part);
+            if (a.saveat[0] != a.t0) { ok = quadgk<P>(ctx, a.t0, a.saveat[0], a.quad_abstol, a.quad_reltol, part, qs) && ok;
 #pragma unroll
                 for (int q = 0; q < P; q++) res[q] += part[q]; }
         }
+    }
+    if (!ok) {           // out of segment capacity: fail loudly
+#pragma unroll
+        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
     }
     if (SHARED_P) {
         if (!active) {
