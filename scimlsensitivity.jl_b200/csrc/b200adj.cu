@@ -13,6 +13,7 @@
 #include "ode_tsit5.cuh"
 #include "sde_em.cuh"
 #include "ros23.cuh"
+#include "mlp.cuh"
 
 using namespace b200adj;
 
@@ -68,6 +69,7 @@ int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
     case B200ADJ_FAM_ROBERTSON: *d = 3; *P = 3; *m = 0; return 0;
     case B200ADJ_FAM_SDE_LV: *d = 2; *P = 6; *m = 2; return 0;
     case B200ADJ_FAM_SDE_LINEAR: *d = 2; *P = 2; *m = 2; return 0;
+    case B200ADJ_FAM_MLP: if (c.mlp_hidden != MLP_H) return -1; *d = MLP_D; *P = MLP_P; *m = 0; return 0;
     default: return -1;
     }
 }
@@ -226,7 +228,40 @@ RosArgs ros_args(Handle* h) {
     return a;
 }
 
-size_t esz(const b200adj_cfg&) { return sizeof(double); }
+template <class T>
+int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
+    MlpArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.u0 = (const T*)u0; a.p = (const T*)p; a.ckpt = (T*)h->d_ckpt; a.saved = (T*)saved; a.save_of_step = h->d_save_of_step;
+    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
+    const size_t smem = sizeof(MlpSmem<T>);
+    if (cudaFuncSetAttribute(mlp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+    mlp_forward_kernel<T><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+template <class T>
+int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
+    const b200adj_cfg& c = h->cfg;
+    MlpArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.p = (const T*)h->cur_p; a.ckpt = (T*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const T*)dLdu;
+    a.du0 = (T*)du0; a.partials = (T*)h->d_partials; a.dp = (T*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
+    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    const size_t smem = sizeof(MlpSmem<T>);
+    if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
+        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COST_EXPLICIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_reverse_kernel<T, COST_EXPLICIT><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
+    } else {
+        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COST_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_reverse_kernel<T, COST_AFFINE><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
+    }
+    mlp_reduce_kernel<T><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const T*)h->d_partials, (T*)dp, h->grid);
+    h->launches += 2;
+    return 0;
+}
+
+size_t esz(const b200adj_cfg& c) { return c.dtype == B200ADJ_F32 ? sizeof(float) : sizeof(double); }
 
 void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
@@ -264,7 +299,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     const bool ros = cfg->stepper == B200ADJ_ST_ROSENBROCK23;
     if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || (!ros && !(cfg->dt > 0)) || !(cfg->t1 > cfg->t0)) {
         g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
-    if (cfg->dtype != B200ADJ_F64) { g_create_error = "dtype: only F64 is built for this family"; return B200ADJ_ERR_UNSUPPORTED; }
+    const bool mlp = cfg->rhs_family == B200ADJ_FAM_MLP;
+    if (cfg->dtype != B200ADJ_F64 && !(mlp && cfg->dtype == B200ADJ_F32)) { g_create_error = "dtype: F64 (all families) or F32 (MLP family) are built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (mlp && (cfg->stepper != B200ADJ_ST_TSIT5_FIXED || cfg->sensealg != B200ADJ_SA_INTERPOLATING || !cfg->shared_p)) {
+        g_create_error = "MLP family: InterpolatingAdjoint + fixed-step Tsit5 + shared parameters are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->cost_kind != B200ADJ_COST_EXPLICIT && cfg->cost_kind != B200ADJ_COST_AFFINE) { g_create_error = "bad cost_kind"; return B200ADJ_ERR_INVALID; }
     const bool sde = is_sde(*cfg);
     if (sde) {
@@ -367,6 +405,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (block > 512) block = 512;
     }
     if (block < 32 || block > 512 || (block % 32) != 0) { g_create_error = "block_threads must be a multiple of 32 in [32, 512]"; return B200ADJ_ERR_INVALID; }
+    if (mlp) block = MLP_TB;      // members per block (the kernels run MLP_THREADS threads per block)
 
     Handle* h = new Handle();
     h->cfg = *cfg; h->cfg.m = m;
@@ -422,7 +461,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     b200adj_cfg& c = h->cfg;
     if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE) { h->err = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
-    if (!is_sde(c) && sensealg == B200ADJ_SA_QUADRATURE && c.stepper == B200ADJ_ST_TSIT5_FIXED && false) { h->err = "unsupported"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (!h->adaptive && !is_sde(c) && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "QuadratureAdjoint needs the adaptive Rosenbrock23 stepper on the device path"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
         if (sensealg != B200ADJ_SA_GAUSS && sensealg != B200ADJ_SA_QUADRATURE) { h->err = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -536,6 +576,9 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         case B200ADJ_FAM_ROBERTSON: rc = launch_ros_fwd<Robertson>(h, a); break;
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
+    } else if (c.rhs_family == B200ADJ_FAM_MLP) {
+        rc = c.dtype == B200ADJ_F32 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
+                                    : mlp_forward_launch<double>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
     } else if (!is_sde(c)) {
         OdeFwdArgs a;
         a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
@@ -612,6 +655,8 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         case B200ADJ_FAM_ROBERTSON: rc = launch_ros_rev<Robertson>(h, a); break;
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
+    } else if (c.rhs_family == B200ADJ_FAM_MLP) {
+        rc = c.dtype == B200ADJ_F32 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
     } else if (!is_sde(c)) {
         OdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;

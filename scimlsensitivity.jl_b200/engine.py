@@ -32,6 +32,9 @@ class DeviceEnsemble:
         else:
             cfg.cost_kind = _lib.COST["explicit"]
         cfg.seed, cfg.traj_offset = int(seed), int(traj_offset)
+        cfg.mlp_hidden = 64 if family == "mlp" else 0
+        self.dtype = dtype
+        self.np_dtype = np.float32 if dtype == "f32" else np.float64
         cfg.checkpoint_every = int(max_steps) if max_steps else 1      # adaptive handles: per-member step capacity
         flags = 0
         if no_start:
@@ -58,23 +61,24 @@ class DeviceEnsemble:
             self.use_current_torch_stream()
 
     # ---- buffers ----
-    def _empty(self, *shape, dtype="f64"):
+    def _empty(self, *shape, dtype="real"):
         if self.on_device:
             import torch
-            return torch.empty(shape, dtype=torch.float64 if dtype == "f64" else torch.int32, device=f"cuda:{self.device}")
-        return np.empty(shape, dtype=np.float64 if dtype == "f64" else np.int32)
+            td = torch.int32 if dtype == "i32" else (torch.float32 if self.dtype == "f32" else torch.float64)
+            return torch.empty(shape, dtype=td, device=f"cuda:{self.device}")
+        return np.empty(shape, dtype=np.int32 if dtype == "i32" else self.np_dtype)
 
     def _prep(self, x, shape):
         if self.on_device:
             import torch
             if not _is_torch(x):
-                x = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=f"cuda:{self.device}")
-            x = x.to(dtype=torch.float64).contiguous()
+                x = torch.as_tensor(np.ascontiguousarray(x, dtype=self.np_dtype), device=f"cuda:{self.device}")
+            x = x.to(dtype=torch.float32 if self.dtype == "f32" else torch.float64).contiguous()
             assert tuple(x.shape) == tuple(shape), (tuple(x.shape), shape)
             return x
         if _is_torch(x):
             x = x.detach().cpu().numpy()
-        x = np.ascontiguousarray(x, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=self.np_dtype)
         assert x.shape == tuple(shape), (x.shape, shape)
         return x
 

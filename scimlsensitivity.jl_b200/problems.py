@@ -14,6 +14,7 @@ import numpy as np
 FAMILIES = {
     # name: (d, P, m)
     "lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "sde_linear": (2, 2, 2),
+    "mlp": (2, 4482, 0),         # 2 -> 64 -> 64 -> 2 tanh MLP, p = [W1, b1, W2, b2, W3, b3] column-major flattened
 }
 
 

@@ -1,0 +1,55 @@
+"""Neural-ODE family (MLP 2->64->64->2, shared weights, BASELINE config C4): InterpolatingAdjoint, fixed-step Tsit5,
+batched-state kernels, against the fp64 oracle.  fp64 path: 1e-9; fp32 path: 1e-5 on dp (BASELINE C4's fp32 bound)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import scimlsensitivity_jl_b200 as b
+from oracle import oracle as O
+
+H = 64
+P = H * H + 6 * H + 2
+
+
+def _weights(seed=1):
+    rng = np.random.default_rng(seed)
+    W1 = rng.standard_normal((H, 2)) / np.sqrt(2); W2 = rng.standard_normal((H, H)) / np.sqrt(H); W3 = rng.standard_normal((2, H)) / np.sqrt(H)
+    b1, b2, b3 = 0.1 * rng.standard_normal(H), 0.1 * rng.standard_normal(H), 0.1 * rng.standard_normal(2)
+    return np.concatenate([W1.ravel(order="F"), b1, W2.ravel(order="F"), b2, W3.ravel(order="F"), b3])
+
+
+def _rel(a, ref):
+    return np.abs(np.asarray(a, dtype=np.float64) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.mark.parametrize("dtype,tol_u,tol_p", [("f64", 1e-9, 1e-9), ("f32", 2e-5, 1e-5)])
+@pytest.mark.parametrize("cost", ["affine", "explicit"])
+@pytest.mark.parametrize("N", [100, 4096])
+def test_mlp_interpolating_parity(dtype, tol_u, tol_p, cost, N):
+    T, dt = 1.5, 0.05
+    saveat = np.linspace(0.05, T, 30)
+    rng = np.random.default_rng(0)
+    u0 = rng.uniform(-2, 2, (2, N)); p = _weights()
+    assert p.size == P
+    cfg = O.make_cfg("mlp", "interpolating", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
+    ref = O.gradient(cfg, saveat, u0, p)
+    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype=dtype,
+                           cost=b.AffineCost(1.0, -0.5) if cost == "affine" else None)
+    saved, status = eng.forward(u0, p)
+    assert (status == 0).all()
+    assert np.abs(saved - ref["saved"]).max() < (1e-11 if dtype == "f64" else 2e-5)
+    du0, dp = eng.reverse(None if cost == "affine" else saved - 0.5)
+    assert dp.shape == (P,)
+    assert _rel(du0, ref["du0"]) < tol_u
+    assert _rel(dp, ref["dp"]) < tol_p
+    eng.close()
+
+
+def test_mlp_unsupported_combinations_fail_loudly():
+    saveat = np.linspace(0.05, 1.5, 30)
+    with pytest.raises(b.B200AdjError) as ei:
+        b.DeviceEnsemble("mlp", "gauss", "tsit5_fixed", 64, saveat, (0.0, 1.5), 0.05)
+    assert ei.value.code == -2
+    with pytest.raises(b.B200AdjError):
+        b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", 64, saveat, (0.0, 1.5), 0.05, shared_p=False)
