@@ -311,6 +311,88 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_secondary(args):
+    """--workload c3|c4|c5: the other BASELINE configs (parity-test cases; reported for context, same JSON shape)."""
+    import torch
+    import scimlsensitivity_jl_b200 as b
+    from oracle import oracle as O
+    torch.cuda.set_device(0)
+    w = args.workload
+    rng = np.random.default_rng(WORKLOAD["seed"])
+    threads = host_cores()
+    if w == "c3":
+        N = args.members or 16384
+        T = 100.0
+        saveat = np.logspace(-2, 2, 10); saveat[-1] = T
+        u0 = np.repeat(np.array([[1.0], [0.0], [0.0]]), N, 1)
+        p = np.array([0.04, 3e7, 1e4])[:, None] * np.exp(0.05 * rng.standard_normal((3, N)))
+        kw = dict(abstol=1e-8, reltol=1e-8, quad_abstol=1e-10, quad_reltol=1e-10)
+        eng = b.DeviceEnsemble("robertson", "quadrature", "rosenbrock23", N, saveat, (0.0, T), 0.0, shared_p=False, on_device=True,
+                               cost=b.AffineCost(1.0, 0.0), max_steps=8192, **kw)
+        ocfg = lambda n: O.make_cfg("robertson", "quadrature", "rosenbrock23", n, saveat, 0.0, T, cost=("affine", 1.0, 0.0), shared_p=False, **kw)
+        name, dtype, sample = "C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves", "f64", 256
+    elif w == "c4":
+        N = args.members or 4096
+        T, dt = 1.5, 0.05
+        saveat = np.linspace(0.05, T, 30)
+        u0 = rng.uniform(-2, 2, (2, N))
+        H = 64
+        p = np.concatenate([(rng.standard_normal((H, 2)) / np.sqrt(2)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                            (rng.standard_normal((H, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                            (rng.standard_normal((2, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(2)])
+        dtype = args.dtype or "f32"
+        eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, on_device=True, dtype=dtype, cost=b.AffineCost(1.0, -0.5))
+        ocfg = lambda n: O.make_cfg("mlp", "interpolating", "tsit5_fixed", n, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
+        name, sample = "C4 MLP 2->64->64->2 shared weights P=4482, InterpolatingAdjoint, Tsit5 fixed dt=0.05, T=1.5, 30 saves", 512
+    else:
+        N = args.members or 131072
+        T, dt = 1.0, 0.01
+        saveat = np.linspace(0.0, T, 101)
+        u0 = np.ones((2, N)); p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
+        eng = b.DeviceEnsemble("sde_lv", "backsolve", "em", N, saveat, (0.0, T), dt, on_device=True, cost=b.AffineCost(0.0, 1.0), seed=20260923)
+        ocfg = lambda n: O.make_cfg("sde_lv", "backsolve", "em", n, saveat, 0.0, T, dt=dt, cost=("affine", 0.0, 1.0))
+        name, dtype, sample = "C5 SDE-LV diag noise d=2 P=6, BacksolveAdjoint (Ito transformed drift), EM dt=0.01, T=1, saveat 0.01, Philox noise regenerated", "f64", 8192
+    td = torch.float32 if dtype == "f32" else torch.float64
+    u0_d = torch.tensor(u0, device="cuda", dtype=td); p_d = torch.tensor(p, device="cuda", dtype=td)
+    du0_d = torch.empty(u0.shape, dtype=td, device="cuda"); dp_d = torch.empty(p.shape, dtype=td, device="cuda")
+
+    def step():
+        eng.handle.forward(u0_d, p_d, None, None, None)
+        eng.handle.reverse(None, du0_d, dp_d)
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
+    l0 = eng.handle.launch_count
+    ev[0].record()
+    for i in range(args.steps):
+        eng.handle.forward(u0_d, p_d, None, None, None); ev[2 * i + 1].record()
+        eng.handle.reverse(None, du0_d, dp_d); ev[2 * i + 2].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[-1]) / args.steps
+    fwd = float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]))
+    rev = float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]))
+    # CPU oracle on a bounded sample of the same workload
+    cfgs = ocfg(sample)
+    dW = None
+    if w == "c5":
+        dW = np.sqrt(dt) * rng.standard_normal((100, 2, sample))
+    pc = p if p.ndim == 1 else p[:, :sample]
+    O.gradient(ocfg(min(sample, 16)), saveat, u0[:, :min(sample, 16)], p if p.ndim == 1 else p[:, :min(sample, 16)], dW=None if dW is None else dW[:, :, :min(sample, 16)], want_saved=False, nthreads=threads)
+    t0 = time.perf_counter()
+    ref = O.gradient(cfgs, saveat, u0[:, :sample], pc, dW=dW, want_saved=False, nthreads=threads)
+    cpu_s = time.perf_counter() - t0
+    line = {"metric": "ensemble adjoint trajectories/sec", "value": N / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": {"workload": name, "members_per_gpu": N},
+            "phases_ms": {"forward": fwd, "reverse": rev},
+            "cpu_baseline": {"value": sample / cpu_s, "unit": "trajectories/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} members of the same workload, one gradient, {cpu_s:.2f} s wall"},
+            "gpu_launches": int(eng.handle.launch_count - l0)}
+    print(json.dumps(line))
+    eng.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -318,12 +400,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members", type=int, default=0, help="override members per GPU (default 65536) / reference sample")
-    ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
+    ap.add_argument("--block", type=int, default=0, help="CUDA block size override (multiple of 32, <= 512)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
+    ap.add_argument("--dtype", default="", help="c4 only: f32 (default) or f64")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload != "c2":
+        run_secondary(args)
     else:
         run_ours(args)
 
