@@ -41,7 +41,7 @@ struct Handle {
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
     int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
-    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0;
+    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0;
     // staging (buffers_on_device == 0)
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
@@ -207,8 +207,8 @@ int launch_ros_rev(Handle* h, const RosArgs& a) {
     if (h->cfg.sensealg != B200ADJ_SA_QUADRATURE) return B200ADJ_ERR_UNSUPPORTED;
     int rc = launch_ros_rev_sa<Fam, SA_QUAD>(h, a);
     if (rc) return rc;
-    const int qb = 128, qg = (int)((h->cfg.N + qb - 1) / qb);
-    if ((size_t)qg > (size_t)h->grid * 2) return B200ADJ_ERR_INVALID;
+    const int qb = 128, qg = (int)((h->cfg.N + (qb / 32) - 1) / (qb / 32));      // one warp per member
+    if ((size_t)qg > h->qpartials_blocks) return B200ADJ_ERR_INVALID;
     if (h->cfg.shared_p) ros23_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(a);
     else ros23_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(a);
     h->launches++;
@@ -353,7 +353,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         CREATE_TRY(cudaMalloc(&h->r_qidx, (size_t)h->maxseg * N * sizeof(int32_t)));
         CREATE_TRY(cudaMalloc(&h->d_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
         if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
-        CREATE_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * 2 * P * sizeof(double)));
+        h->qpartials_blocks = (N + 3) / 4 + 1;                                  // quadrature kernel: 4 members (warps) per block
+        CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpartials_blocks > (size_t)h->grid ? h->qpartials_blocks : (size_t)h->grid) * P * sizeof(double)));
         CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
         CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
         if (!cfg->buffers_on_device) {

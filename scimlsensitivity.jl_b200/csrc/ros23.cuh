@@ -374,50 +374,70 @@ struct QuadCtx {
     }
 };
 
+// ---- warp-cooperative Gauss-Kronrod: one WARP per member ----
+// A bisection evaluates the (7,15) rule on both halves = 30 integrand evaluations: lanes 0..14 take the 15 Kronrod nodes
+// of the left half, lanes 16..30 those of the right half (lanes 15, 31 idle), each with its own dense-solution lookup;
+// the weighted sums are reduced with shuffles inside each 16-lane half.  Node order inside a half: lane l -> abscissa
+// sign(l-7) * XGK[min(l,14-l)] (ascending in t).
 template <int P, class F>
-__device__ __forceinline__ void gk15(const F& f, double a, double b, double* Ik, double* err) {
+__device__ __forceinline__ void gk15_pair(const F& f, double a0, double b0, double a1, double b1, int lane,
+                                          double* I0, double* e0, double* I1, double* e1) {
+    const int half = lane >> 4, l = lane & 15;
+    const double a = half ? a1 : a0, b = half ? b1 : b0;
     const double c = 0.5 * (a + b), hl = 0.5 * (b - a);
-    double Ig[P], w1[P], w2[P];
-    f(c, w1);
+    double vk[P], vg[P];
 #pragma unroll
-    for (int q = 0; q < P; q++) { Ik[q] = WGK[7] * w1[q]; Ig[q] = WG[3] * w1[q]; }
-    for (int j = 0; j < 7; j++) {
-        f(c - hl * XGK[j], w1); f(c + hl * XGK[j], w2);
+    for (int q = 0; q < P; q++) { vk[q] = 0; vg[q] = 0; }
+    if (l < 15) {
+        const int j = l < 7 ? l : 14 - l;                      // 0..7 (7 = centre)
+        const double x = (l < 7 ? -XGK[j] : XGK[j]);
+        double w[P];
+        f(c + hl * x, w);
+        const double wk = WGK[j], wg = (j == 7) ? WG[3] : ((j & 1) ? WG[j >> 1] : 0.0);
 #pragma unroll
-        for (int q = 0; q < P; q++) {
-            Ik[q] += WGK[j] * (w1[q] + w2[q]);
-            if (j & 1) Ig[q] += WG[j / 2] * (w1[q] + w2[q]);
-        }
+        for (int q = 0; q < P; q++) { vk[q] = wk * w[q]; vg[q] = wg * w[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < P; q++) {
+#pragma unroll
+        for (int off = 8; off > 0; off >>= 1) { vk[q] += __shfl_xor_sync(0xffffffffu, vk[q], off); vg[q] += __shfl_xor_sync(0xffffffffu, vg[q], off); }
     }
     double e2 = 0;
 #pragma unroll
-    for (int q = 0; q < P; q++) { Ik[q] *= hl; Ig[q] *= hl; e2 += (Ik[q] - Ig[q]) * (Ik[q] - Ig[q]); }
-    *err = sqrt(e2);
+    for (int q = 0; q < P; q++) { vk[q] *= hl; vg[q] *= hl; e2 += (vk[q] - vg[q]) * (vk[q] - vg[q]); }
+    const double e = sqrt(e2);
+    // broadcast both halves' results to every lane
+#pragma unroll
+    for (int q = 0; q < P; q++) { I0[q] = __shfl_sync(0xffffffffu, vk[q], 0); I1[q] = __shfl_sync(0xffffffffu, vk[q], 16); }
+    *e0 = __shfl_sync(0xffffffffu, e, 0); *e1 = __shfl_sync(0xffffffffu, e, 16);
 }
 
 // Segment store of one member's adaptive quadrature, in a handle-owned global scratch (member-minor):
 //   seg [maxseg][2+P][N] = (a, b, I[P]) per segment id, key [maxseg][N] / idx [maxseg][N] = binary max-heap on the error.
 // QuadGK bisects the largest-error segment; a heap gives the same argmax as the oracle's linear scan (no ties in
 // practice) at O(log n) per bisection -- the dense reverse solution is only C1 at step boundaries, so a 1e-10 tolerance
-// drives thousands of segments per data interval.
+// drives thousands of segments per data interval.  All lanes of the warp run the heap logic on identical values
+// (uniform loads); lane 0 does the stores.
 struct QuadScratch { double* seg; double* key; int32_t* idx; int maxseg; int64_t N, i; };
 
-// adaptive quadgk over [a,b]: bisect the largest-error segment until E <= max(atol, rtol*|I|) (2-norm).  false = out of
-// segment capacity.
+// adaptive quadgk over [a,b] by one warp: bisect the largest-error segment until E <= max(atol, rtol*|I|) (2-norm);
+// running totals updated incrementally and returned (QuadGK.jl).  false = out of segment capacity.
 template <int P, class F>
-__device__ bool quadgk(const F& f, double a, double b, double atol, double rtol, double* out, const QuadScratch& q) {
+__device__ bool quadgk_warp(const F& f, double a, double b, double atol, double rtol, double* out, const QuadScratch& q, int lane) {
     const int64_t N = q.N, i = q.i;
-    auto SEG = [&](int k, int c) -> double& { return q.seg[((int64_t)k * (2 + P) + c) * N + i]; };
-    auto KEY = [&](int k) -> double& { return q.key[(int64_t)k * N + i]; };
-    auto IDX = [&](int k) -> int32_t& { return q.idx[(int64_t)k * N + i]; };
-    double I[P], Itot[P], e, Etot;
-    gk15<P>(f, a, b, I, &e);
-    SEG(0, 0) = a; SEG(0, 1) = b;
+    auto SEG = [&](int k, int c) -> double* { return &q.seg[((int64_t)k * (2 + P) + c) * N + i]; };
+    auto KEY = [&](int k) -> double* { return &q.key[(int64_t)k * N + i]; };
+    auto IDX = [&](int k) -> int32_t* { return &q.idx[(int64_t)k * N + i]; };
+    const bool wr = lane == 0;
+    double I[P], Idummy[P], Itot[P], e, edummy, Etot;
+    gk15_pair<P>(f, a, b, a, b, lane, I, &e, Idummy, &edummy);
+    if (wr) { *SEG(0, 0) = a; *SEG(0, 1) = b; *KEY(0) = e; *IDX(0) = 0; }
 #pragma unroll
-    for (int c = 0; c < P; c++) { SEG(0, 2 + c) = I[c]; Itot[c] = I[c]; }
-    KEY(0) = e; IDX(0) = 0; Etot = e;
+    for (int c = 0; c < P; c++) { if (wr) *SEG(0, 2 + c) = I[c]; Itot[c] = I[c]; }
+    Etot = e;
     int nseg = 1;
     bool ok = true;
+    __syncwarp();
     for (;;) {
         double nI = 0;
 #pragma unroll
@@ -425,47 +445,55 @@ __device__ bool quadgk(const F& f, double a, double b, double atol, double rtol,
         nI = sqrt(nI);
         if (Etot <= fmax(atol, rtol * nI)) break;
         if (nseg + 1 > q.maxseg) { ok = false; break; }
-        const int w = IDX(0);
-        const double aw = SEG(w, 0), bw = SEG(w, 1), ew = KEY(0);
+        const int w = *IDX(0);
+        const double aw = *SEG(w, 0), bw = *SEG(w, 1), ew = *KEY(0);
         const double mid = 0.5 * (aw + bw);
         if (!(mid > fmin(aw, bw) && mid < fmax(aw, bw))) break;
         double Il[P], Ir[P], el, er;
-        gk15<P>(f, aw, mid, Il, &el);
-        gk15<P>(f, mid, bw, Ir, &er);
+        gk15_pair<P>(f, aw, mid, mid, bw, lane, Il, &el, Ir, &er);
         Etot += (el + er) - ew;
 #pragma unroll
-        for (int c = 0; c < P; c++) { Itot[c] += (Il[c] + Ir[c]) - SEG(w, 2 + c); SEG(w, 2 + c) = Il[c]; SEG(nseg, 2 + c) = Ir[c]; }
-        SEG(w, 1) = mid; SEG(nseg, 0) = mid; SEG(nseg, 1) = bw;
-        // root <- left half, sift down
-        int hpos = 0; double hk = el; int hi_ = w;
-        for (;;) {
-            int l = 2 * hpos + 1, r = l + 1, m = hpos; double mk = hk;
-            if (l < nseg && KEY(l) > mk) { m = l; mk = KEY(l); }
-            if (r < nseg && KEY(r) > mk) { m = r; mk = KEY(r); }
-            if (m == hpos) break;
-            KEY(hpos) = KEY(m); IDX(hpos) = IDX(m); hpos = m;
+        for (int c = 0; c < P; c++) {
+            Itot[c] += (Il[c] + Ir[c]) - *SEG(w, 2 + c);
         }
-        KEY(hpos) = hk; IDX(hpos) = hi_;
-        // push right half, sift up
-        hpos = nseg; hk = er; hi_ = nseg;
-        while (hpos > 0) {
-            int par = (hpos - 1) >> 1;
-            if (KEY(par) >= hk) break;
-            KEY(hpos) = KEY(par); IDX(hpos) = IDX(par); hpos = par;
+        __syncwarp();
+        if (wr) {
+#pragma unroll
+            for (int c = 0; c < P; c++) { *SEG(w, 2 + c) = Il[c]; *SEG(nseg, 2 + c) = Ir[c]; }
+            *SEG(w, 1) = mid; *SEG(nseg, 0) = mid; *SEG(nseg, 1) = bw;
+            // root <- left half, sift down
+            int hpos = 0; double hk = el; int hid = w;
+            for (;;) {
+                int l = 2 * hpos + 1, r = l + 1, m = hpos; double mk = hk;
+                if (l < nseg) { const double kl = *KEY(l); if (kl > mk) { m = l; mk = kl; } }
+                if (r < nseg) { const double kr = *KEY(r); if (kr > mk) { m = r; mk = kr; } }
+                if (m == hpos) break;
+                *KEY(hpos) = *KEY(m); *IDX(hpos) = *IDX(m); hpos = m;
+            }
+            *KEY(hpos) = hk; *IDX(hpos) = hid;
+            // push right half, sift up
+            hpos = nseg; hk = er; hid = nseg;
+            while (hpos > 0) {
+                int par = (hpos - 1) >> 1;
+                if (*KEY(par) >= hk) break;
+                *KEY(hpos) = *KEY(par); *IDX(hpos) = *IDX(par); hpos = par;
+            }
+            *KEY(hpos) = hk; *IDX(hpos) = hid;
         }
-        KEY(hpos) = hk; IDX(hpos) = hi_;
+        __syncwarp();
         nseg++;
     }
-    // QuadGK returns the running total
 #pragma unroll
     for (int c = 0; c < P; c++) out[c] = Itot[c];
     return ok;
 }
 
+// one warp per member; block = 4 warps
 template <class Fam, bool SHARED_P>
 __global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
-    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int64_t gi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // member index of this warp
     const bool active = gi < a.N;
     const int64_t i = active ? gi : a.N - 1;
     const int64_t N = a.N;
@@ -480,18 +508,18 @@ __global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
 #pragma unroll
         for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
     } else if (ctx.nrev > 0) {
-        if (K == 0) { ok = quadgk<P>(ctx, a.t0, a.t1, a.quad_abstol, a.quad_reltol, res, qs); }
+        if (K == 0) { ok = quadgk_warp<P>(ctx, a.t0, a.t1, a.quad_abstol, a.quad_reltol, res, qs, lane); }
         else {
-            if (a.saveat[K - 1] != a.t1) { ok = quadgk<P>(ctx, a.saveat[K - 1], a.t1, a.quad_abstol, a.quad_reltol, part, qs) && ok;
+            if (a.saveat[K - 1] != a.t1) { ok = quadgk_warp<P>(ctx, a.saveat[K - 1], a.t1, a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
 #pragma unroll
                 for (int q = 0; q < P; q++) res[q] += part[q]; }
             for (int k = K - 2; k >= 0; k--) {
                 if (a.saveat[k] == a.saveat[k + 1]) continue;
-                ok = quadgk<P>(ctx, a.saveat[k], a.saveat[k + 1], a.quad_abstol, a.quad_reltol, part, qs) && ok;
+                ok = quadgk_warp<P>(ctx, a.saveat[k], a.saveat[k + 1], a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
 #pragma unroll
                 for (int q = 0; q < P; q++) res[q] += part[q];
             }
-            if (a.saveat[0] != a.t0) { ok = quadgk<P>(ctx, a.t0, a.saveat[0], a.quad_abstol, a.quad_reltol, part, qs) && ok;
+            if (a.saveat[0] != a.t0) { ok = quadgk_warp<P>(ctx, a.t0, a.saveat[0], a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
 #pragma unroll
                 for (int q = 0; q < P; q++) res[q] += part[q]; }
         }
@@ -500,13 +528,14 @@ __global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
 #pragma unroll
         for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
     }
+    // lane 0 of every warp holds the member's result: per-member store, or a block/grid reduction over the lane-0 values
     if (SHARED_P) {
-        if (!active) {
+        if (!active || lane != 0) {
 #pragma unroll
             for (int q = 0; q < P; q++) res[q] = 0.0;
         }
         reduce_dp<P>(res, a.partials, a.dp, a.ticket);
-    } else if (active) {
+    } else if (active && lane == 0) {
 #pragma unroll
         for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = res[q];
     }
