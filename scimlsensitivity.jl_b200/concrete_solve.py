@@ -106,11 +106,14 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
         ts = ts[:-1]
     on_device = ensemblealg.buffers_on_device if ensemblealg.buffers_on_device is not None else _is_torch(u0)
     rank, world = distributed.world()
-    lo, hi = distributed.shard_bounds(N_global)
-    if world > 1:
-        u0 = u0[:, lo:hi]
-        if not shared_p:
-            p = p[:, lo:hi]
+    if ensemblealg.presharded:
+        lo, hi = rank * N_global, (rank + 1) * N_global          # the inputs are this rank's shard already
+    else:
+        lo, hi = distributed.shard_bounds(N_global)
+        if world > 1:
+            u0 = u0[:, lo:hi]
+            if not shared_p:
+                p = p[:, lo:hi]
     device = ensemblealg.device
     if device is None:
         if _is_torch(u0) and u0.is_cuda:
@@ -134,7 +137,7 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
         if ensemblealg.reuse_handle:
             _HANDLE_CACHE[key] = eng
     dW = getattr(prob, "noise", None)
-    if dW is not None and world > 1:
+    if dW is not None and world > 1 and not ensemblealg.presharded:
         dW = dW[:, :, lo:hi]
     saved, status = eng.forward(u0, p, dW=dW, want_saved=save_on)
     return EnsembleSolution(prob=eprob, alg=alg, t=ts, u=saved, retcode=status, dense=True, engine=eng, u0=u0, p=p)

@@ -95,6 +95,8 @@ class EnsembleB200:
     With torch.distributed initialised the members are sharded contiguously over ranks (one process per GPU)."""
     device: Optional[int] = None
     buffers_on_device: Optional[bool] = None   # None: infer from the input arrays
+    presharded: bool = False                   # True: the arrays passed in are already THIS rank's shard (no slicing; dp is
+                                               # still all-reduced, Philox member offset = rank * local N)
     reuse_handle: bool = False                 # keep ONE device handle per configuration across solve() calls (the
                                                # previous solution's checkpoints are overwritten by the next solve)
 
