@@ -14,6 +14,7 @@
 #include "sde_em.cuh"
 #include "ros23.cuh"
 #include "mlp.cuh"
+#include "tsit5_quad.cuh"
 
 using namespace b200adj;
 
@@ -33,6 +34,8 @@ struct Handle {
     double* d_ckpt = nullptr;         // [S+1][d][N]
     double* d_noise = nullptr;        // [S][m][N] (SDE, stored-noise mode)
     double* d_partials = nullptr;     // [grid][P]
+    double* d_adj_dense = nullptr;    // QuadratureAdjoint, fixed-step Tsit5: [S][8][d][Npad]
+    size_t qpart_blocks_fixed = 0;
     unsigned long long* d_trace = nullptr;   // [grid][3] block trace (B200ADJ_FLAG_TRACE)
     unsigned int* d_ticket = nullptr;
     int32_t* d_save_of_step = nullptr;
@@ -41,7 +44,7 @@ struct Handle {
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
     int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
-    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0;
+    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
     // staging (buffers_on_device == 0)
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
@@ -76,7 +79,7 @@ int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
 
 // Tsit5 dense-output weights b_j(theta): quartics, expanded once in long double from the published factored form
 // (Tsitouras 2011) and evaluated by Horner.
-void tsit5_weights(double th, double* w) {
+void tsit5_weights(double th, double* w, double (*Rout)[4] = nullptr) {
     typedef long double LD;
     static bool init = false;
     static double R[7][5];   // coefficients of theta^0..theta^4
@@ -101,7 +104,8 @@ void tsit5_weights(double th, double* w) {
         sq_roots(6, 2.5L, 1.0L, 0.6L);
         init = true;
     }
-    for (int j = 0; j < 7; j++) w[j] = (((R[j][4] * th + R[j][3]) * th + R[j][2]) * th + R[j][1]) * th + R[j][0];
+    if (Rout) for (int j = 0; j < 7; j++) for (int m = 0; m < 4; m++) Rout[j][m] = R[j][m + 1];
+    if (w) for (int j = 0; j < 7; j++) w[j] = (((R[j][4] * th + R[j][3]) * th + R[j][2]) * th + R[j][1]) * th + R[j][0];
 }
 
 // Step-size-scaled Tsit5 tables for one handle (passed to the kernels by value, i.e. through the constant bank).
@@ -159,6 +163,39 @@ int launch_rev(Handle* h, const OdeRevArgs& a) {
     case B200ADJ_SA_INTERPOLATING: return launch_rev_sa<Fam, SA_INTERP>(h, a);
     case B200ADJ_SA_GAUSS: return launch_rev_sa<Fam, SA_GAUSS>(h, a);
     case B200ADJ_SA_BACKSOLVE: return launch_rev_sa<Fam, SA_BACKSOLVE>(h, a);
+    case B200ADJ_SA_QUADRATURE: {
+        const b200adj_cfg& c = h->cfg;
+        const size_t N = (size_t)c.N;
+        // lazily allocate the dense reverse solution and the quadgk scratch (only QuadratureAdjoint needs them)
+        if (!h->d_adj_dense && cudaMalloc(&h->d_adj_dense, (size_t)h->S * 8 * c.d * (size_t)h->Npad * sizeof(double)) != cudaSuccess) return B200ADJ_ERR_OOM;
+        if (!h->r_qseg) {
+            h->maxseg = 4096;
+            if (cudaMalloc(&h->r_qseg, (size_t)h->maxseg * (2 + c.P) * N * sizeof(double)) != cudaSuccess) return B200ADJ_ERR_OOM;
+            if (cudaMalloc(&h->r_qkey, (size_t)h->maxseg * N * sizeof(double)) != cudaSuccess) return B200ADJ_ERR_OOM;
+            if (cudaMalloc(&h->r_qidx, (size_t)h->maxseg * N * sizeof(int32_t)) != cudaSuccess) return B200ADJ_ERR_OOM;
+            if (!h->d_saveat && cudaMalloc(&h->d_saveat, sizeof(double) * (size_t)(c.K > 0 ? c.K : 1)) != cudaSuccess) return B200ADJ_ERR_OOM;
+        }
+        if (c.K > 0) {
+            if (h->saveat_dev_K < c.K) { cudaFree(h->d_saveat); h->d_saveat = nullptr; if (cudaMalloc(&h->d_saveat, sizeof(double) * (size_t)c.K) != cudaSuccess) return B200ADJ_ERR_OOM; h->saveat_dev_K = c.K; }
+            if (cudaMemcpyAsync(h->d_saveat, h->saveat.data(), sizeof(double) * (size_t)c.K, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        }
+        OdeRevArgs ar = a; ar.adj_dense = h->d_adj_dense;
+        int rc = launch_rev_sa<Fam, SA_QUAD>(h, ar);
+        if (rc) return rc;
+        Tsit5QuadArgs q;
+        memset(&q, 0, sizeof(q));
+        q.ckpt = h->d_ckpt; q.adj_dense = h->d_adj_dense; q.p = a.p; q.saveat = h->d_saveat;
+        q.dp_members = a.dp_members; q.partials = h->d_partials; q.dp = a.dp; q.ticket = h->d_ticket;
+        q.qseg = h->r_qseg; q.qkey = h->r_qkey; q.qidx = h->r_qidx; q.maxseg = h->maxseg;
+        q.N = c.N; q.Npad = h->Npad; q.S = h->S; q.K = c.K; q.t0 = c.t0; q.t1 = c.t1; q.h = c.dt;
+        q.quad_abstol = c.quad_abstol; q.quad_reltol = c.quad_reltol; q.tb = h->tb;
+        tsit5_weights(0.0, nullptr, q.R);
+        const int qb = 128, qg = (int)((c.N + 3) / 4);
+        if (c.shared_p) tsit5_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(q);
+        else tsit5_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(q);
+        h->launches++;
+        return 0;
+    }
     default: return B200ADJ_ERR_UNSUPPORTED;
     }
 }
@@ -267,7 +304,7 @@ void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
-    cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
+    cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -312,7 +349,6 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
         if (cfg->sensealg < 0 || cfg->sensealg > 3) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (!ros && cfg->sensealg == B200ADJ_SA_QUADRATURE) { g_create_error = "QuadratureAdjoint needs the adaptive Rosenbrock23 stepper on the device path"; return B200ADJ_ERR_UNSUPPORTED; }
         if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "Rosenbrock23 needs abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
     }
     if (ros) {
@@ -427,7 +463,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     const size_t Npad = ((N + block - 1) / block) * block;     // padded checkpoint pitch (whole TMA rows per block)
     h->Npad = (int64_t)Npad;
     CREATE_TRY(cudaMalloc(&h->d_ckpt, ((size_t)S + 1) * d * Npad * e));
-    CREATE_TRY(cudaMalloc(&h->d_partials, (size_t)h->grid * P * sizeof(double)));
+    h->qpart_blocks_fixed = (N + 3) / 4 + 1;
+    CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpart_blocks_fixed > (size_t)h->grid ? h->qpart_blocks_fixed : (size_t)h->grid) * P * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
     CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
     CREATE_TRY(cudaMalloc(&h->d_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
@@ -463,7 +500,6 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE) { h->err = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
-    if (!h->adaptive && !is_sde(c) && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "QuadratureAdjoint needs the adaptive Rosenbrock23 stepper on the device path"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
         if (sensealg != B200ADJ_SA_GAUSS && sensealg != B200ADJ_SA_QUADRATURE) { h->err = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }

@@ -65,6 +65,7 @@ struct OdeRevArgs {
     int32_t S;
     double cost_a, cost_b;
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step
+    double* adj_dense;       // SA_QUAD: [S][8][D][Npad] = (lambda at the start of reverse step n, ka'[0..6]) per step
     unsigned long long* trace;   // optional [gridDim][3] = (smid, globaltimer at block start, at block end) or null
     Tsit5Tables tb;
 };
@@ -387,6 +388,17 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #ifdef REV_MIDSYNC
             __syncthreads();
 #endif
+            if (SA == SA_QUAD) {
+                // QuadratureAdjoint: keep the dense reverse solution of this step (adj_sol with save_everystep,
+                // src/quadrature_adjoint.jl:527-530): start value (post-jump lambda(t_{n+1})) and the 7 stage derivatives
+                double* row = a.adj_dense + (int64_t)n * 8 * cstride + gi;
+#pragma unroll
+                for (int j = 0; j < D; j++) row[(int64_t)j * Npad] = lam[j];
+#pragma unroll
+                for (int s_ = 0; s_ < 7; s_++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) row[((int64_t)(1 + s_) * D + j) * Npad] = ka[s_][j];
+            }
             if (SA == SA_GAUSS) {
                 // 3-point Gauss-Legendre over this step, pre-jump lambda from the adjoint step's own dense output,
                 // y from the forward dense output: dp += (h/2) w_q (df/dp)'(y_q) lam_q  (gauss_adjoint.jl:745-759)

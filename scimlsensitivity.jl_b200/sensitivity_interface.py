@@ -66,11 +66,12 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
         every = checkpoints is None
     cost = dgdu_discrete if isinstance(dgdu_discrete, AffineCost) else None
     eng.set_reverse(name, cost=cost, no_start=no_start, checkpointing=checkpointing, ckpt_every_step=every, t=ts)
-    if getattr(eng, "adaptive", False):
-        # adjoint solve tolerances are keywords of adjoint_sensitivities (src/sensitivity_interface.jl:432); quadgk
-        # tolerances come from the sensealg (src/quadrature_adjoint.jl:517)
-        eng.handle.set_tolerances(abstol, reltol, getattr(inner, "abstol", 0.0) if isinstance(inner, QuadratureAdjoint) else 0.0,
-                                  getattr(inner, "reltol", 0.0) if isinstance(inner, QuadratureAdjoint) else 0.0)
+    # adjoint solve tolerances are keywords of adjoint_sensitivities (src/sensitivity_interface.jl:432; used by the adaptive
+    # steppers only); quadgk tolerances come from the sensealg (src/quadrature_adjoint.jl:517)
+    is_quad = isinstance(inner, QuadratureAdjoint)
+    if getattr(eng, "adaptive", False) or is_quad:
+        eng.handle.set_tolerances(abstol if getattr(eng, "adaptive", False) else 0.0, reltol if getattr(eng, "adaptive", False) else 0.0,
+                                  inner.abstol if is_quad else 0.0, inner.reltol if is_quad else 0.0)
     du0, dp = eng.reverse(None if cost is not None else dgdu_discrete)
     from .distributed import allreduce_dp
     dp = allreduce_dp(dp, eng)

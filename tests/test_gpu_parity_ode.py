@@ -42,6 +42,8 @@ CASES = [
     ("lv", "gauss", 10.0, 0.05, 101, {}),
     ("lv", "interpolating", 10.0, 0.05, 101, {}),
     ("lv", "backsolve", 10.0, 0.05, 101, {"ckpt_every_step": False}),
+    ("lorenz", "quadrature", 2.0, 0.01, 21, {}),
+    ("lv", "quadrature", 10.0, 0.05, 101, {}),
     ("robertson", "gauss", 1.0, 0.001, 11, {}),
     ("robertson", "interpolating", 1.0, 0.001, 11, {}),
 ]
@@ -60,17 +62,19 @@ def test_ode_parity(family, sensealg, T, dt, nsave, kw, cost, shared_p):
     every = kw.get("ckpt_every_step", False)
     ocost = ("affine", 1.0, -2.0)
     cfg = O.make_cfg(family, sensealg, "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=ocost, shared_p=shared_p,
-                     ckpt_every_step=every)
+                     ckpt_every_step=every, quad_abstol=1e-9, quad_reltol=1e-9)
     ref = O.gradient(cfg, saveat, u0, p)
     eng = b.DeviceEnsemble(family, sensealg, "tsit5_fixed", N, saveat, (0.0, T), dt, shared_p=shared_p,
-                           cost=b.AffineCost(1.0, -2.0) if cost == "affine" else None, ckpt_every_step=every)
+                           cost=b.AffineCost(1.0, -2.0) if cost == "affine" else None, ckpt_every_step=every,
+                           quad_abstol=1e-9, quad_reltol=1e-9)
     saved, status = eng.forward(u0, p)
     assert (status == 0).all()
     assert np.abs(saved - ref["saved"]).max() <= 1e-10 * max(1.0, np.abs(ref["saved"]).max())
     dL = None if cost == "affine" else (saved - 2.0)
     du0, dp = eng.reverse(dL)
     assert _rel(du0, ref["du0"]) < RTOL
-    assert _rel(dp, ref["dp"]) < RTOL
+    # QuadratureAdjoint: adaptive Gauss-Kronrod is path dependent at the level of its own error estimate (1e-9 here)
+    assert _rel(dp, ref["dp"]) < (1e-7 if sensealg == "quadrature" else RTOL)
     eng.close()
 
 
@@ -84,15 +88,17 @@ def test_device_buffers_and_reverse_retarget():
                            cost=b.AffineCost(1.0, -2.0))
     saved, status = eng.forward(torch.tensor(u0, device="cuda"), torch.tensor(p, device="cuda"))
     res = {}
-    for sa in ["gauss", "interpolating", "backsolve"]:
+    for sa in ["gauss", "interpolating", "backsolve", "quadrature"]:
         eng.set_reverse(sa, cost=b.AffineCost(1.0, -2.0), ckpt_every_step=True)
+        eng.handle.set_tolerances(0.0, 0.0, 1e-10, 1e-10)
         du0, dp = eng.reverse()
         res[sa] = (du0.cpu().numpy(), dp.cpu().numpy())
         cfg = O.make_cfg("lorenz", sa, "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0), ckpt_every_step=True)
         ref = O.gradient(cfg, saveat, u0, p, want_saved=False)
-        assert _rel(res[sa][0], ref["du0"]) < RTOL and _rel(res[sa][1], ref["dp"]) < RTOL
+        assert _rel(res[sa][0], ref["du0"]) < RTOL and _rel(res[sa][1], ref["dp"]) < (1e-7 if sa == "quadrature" else RTOL)
     # the reference's own relation: all sensealgs agree (test/Core3/adjoint.jl:366-404), here at the dt=0.01 truncation level
     assert _rel(res["interpolating"][1], res["gauss"][1]) < 1e-5
+    assert _rel(res["quadrature"][1], res["gauss"][1]) < 1e-5
     # fewer save times on the same forward pass
     t2 = saveat[::5]
     eng.set_reverse("gauss", cost=b.AffineCost(1.0, -2.0), t=t2)
