@@ -90,10 +90,11 @@ def test_device_buffers_and_reverse_retarget():
     res = {}
     for sa in ["gauss", "interpolating", "backsolve", "quadrature"]:
         eng.set_reverse(sa, cost=b.AffineCost(1.0, -2.0), ckpt_every_step=True)
-        eng.handle.set_tolerances(0.0, 0.0, 1e-10, 1e-10)
+        eng.handle.set_tolerances(0.0, 0.0, 1e-9, 1e-9)
         du0, dp = eng.reverse()
         res[sa] = (du0.cpu().numpy(), dp.cpu().numpy())
-        cfg = O.make_cfg("lorenz", sa, "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0), ckpt_every_step=True)
+        cfg = O.make_cfg("lorenz", sa, "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0), ckpt_every_step=True,
+                         quad_abstol=1e-9, quad_reltol=1e-9)
         ref = O.gradient(cfg, saveat, u0, p, want_saved=False)
         assert _rel(res[sa][0], ref["du0"]) < RTOL and _rel(res[sa][1], ref["dp"]) < (1e-7 if sa == "quadrature" else RTOL)
     # the reference's own relation: all sensealgs agree (test/Core3/adjoint.jl:366-404), here at the dt=0.01 truncation level
