@@ -15,6 +15,7 @@
 #include "ros23.cuh"
 #include "mlp.cuh"
 #include "tsit5_quad.cuh"
+#include "mlp_umma.cuh"
 
 using namespace b200adj;
 
@@ -35,6 +36,7 @@ struct Handle {
     double* d_noise = nullptr;        // [S][m][N] (SDE, stored-noise mode)
     double* d_partials = nullptr;     // [grid][P]
     double* d_adj_dense = nullptr;    // QuadratureAdjoint, fixed-step Tsit5: [S][8][d][Npad]
+    void *d_tapeA = nullptr, *d_tapeB = nullptr; float* d_umma_partials = nullptr; int umma_ctas = 0; int64_t Ktot = 0;   // MLP bf16 mode
     size_t qpart_blocks_fixed = 0;
     unsigned long long* d_trace = nullptr;   // [grid][3] block trace (B200ADJ_FLAG_TRACE)
     unsigned int* d_ticket = nullptr;
@@ -286,25 +288,36 @@ int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
     a.du0 = (T*)du0; a.partials = (T*)h->d_partials; a.dp = (T*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
     a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
     const size_t smem = sizeof(MlpSmem<T>);
-    if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
-        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COST_EXPLICIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        mlp_reverse_kernel<T, COST_EXPLICIT><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
-    } else {
-        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COST_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        mlp_reverse_kernel<T, COST_AFFINE><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
-    }
+    a.tapeA = h->d_tapeA; a.tapeB = h->d_tapeB; a.Ktot = h->Ktot; a.Npad = h->Npad;
+    const bool tape = h->d_tapeA != nullptr;
+#define B200_MLP_REV(COSTV, TAPEV)                                                                                          \
+    do {                                                                                                                    \
+        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COSTV, TAPEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA; \
+        mlp_reverse_kernel<T, COSTV, TAPEV><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);                                  \
+    } while (0)
+    const bool ex = c.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (tape) { if (ex) B200_MLP_REV(COST_EXPLICIT, true); else B200_MLP_REV(COST_AFFINE, true); }
+    else { if (ex) B200_MLP_REV(COST_EXPLICIT, false); else B200_MLP_REV(COST_AFFINE, false); }
+#undef B200_MLP_REV
     mlp_reduce_kernel<T><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const T*)h->d_partials, (T*)dp, h->grid);
     h->launches += 2;
+    if (tape) {
+        // hidden-layer weight gradient on the tensor cores: dW2 = TA x TB' over K = 6 S Npad (bf16 in, fp32 TMEM accumulate)
+        UmmaArgs u; u.TA = (const __nv_bfloat16*)h->d_tapeA; u.TB = (const __nv_bfloat16*)h->d_tapeB; u.partials = h->d_umma_partials; u.Ktot = h->Ktot;
+        mlp_dw2_umma_kernel<<<h->umma_ctas, 128, 0, h->stream>>>(u);
+        mlp_dw2_reduce_kernel<<<16, 256, 0, h->stream>>>(h->d_umma_partials, (float*)dp + MLP_OW2, h->umma_ctas);
+        h->launches += 2;
+    }
     return 0;
 }
 
-size_t esz(const b200adj_cfg& c) { return c.dtype == B200ADJ_F32 ? sizeof(float) : sizeof(double); }
+size_t esz(const b200adj_cfg& c) { return c.dtype == B200ADJ_F64 ? sizeof(double) : sizeof(float); }   // BF16_F32ACC: fp32 buffers at the ABI
 
 void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
-    cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
+    cudaFree(h->d_tapeA); cudaFree(h->d_tapeB); cudaFree(h->d_umma_partials); cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -337,7 +350,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || (!ros && !(cfg->dt > 0)) || !(cfg->t1 > cfg->t0)) {
         g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
     const bool mlp = cfg->rhs_family == B200ADJ_FAM_MLP;
-    if (cfg->dtype != B200ADJ_F64 && !(mlp && cfg->dtype == B200ADJ_F32)) { g_create_error = "dtype: F64 (all families) or F32 (MLP family) are built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (cfg->dtype != B200ADJ_F64 && !(mlp && (cfg->dtype == B200ADJ_F32 || cfg->dtype == B200ADJ_BF16_F32ACC))) {
+        g_create_error = "dtype: F64 (all families), F32 / BF16_F32ACC (MLP family) are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (mlp && (cfg->stepper != B200ADJ_ST_TSIT5_FIXED || cfg->sensealg != B200ADJ_SA_INTERPOLATING || !cfg->shared_p)) {
         g_create_error = "MLP family: InterpolatingAdjoint + fixed-step Tsit5 + shared parameters are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->cost_kind != B200ADJ_COST_EXPLICIT && cfg->cost_kind != B200ADJ_COST_AFFINE) { g_create_error = "bad cost_kind"; return B200ADJ_ERR_INVALID; }
@@ -470,6 +484,13 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     CREATE_TRY(cudaMalloc(&h->d_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
     CREATE_TRY(cudaMemcpy(h->d_save_of_step, sos.data(), ((size_t)S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (sde) CREATE_TRY(cudaMalloc(&h->d_noise, (size_t)S * m * N * e));
+    if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC) {
+        h->Ktot = (int64_t)6 * S * (int64_t)Npad;                              // Npad is a multiple of 32 => Ktot % 64 == 0
+        h->umma_ctas = nsm;
+        CREATE_TRY(cudaMalloc(&h->d_tapeA, (size_t)64 * h->Ktot * 2));
+        CREATE_TRY(cudaMalloc(&h->d_tapeB, (size_t)64 * h->Ktot * 2));
+        CREATE_TRY(cudaMalloc(&h->d_umma_partials, (size_t)h->umma_ctas * 4096 * sizeof(float)));
+    }
     if (cfg->flags & B200ADJ_FLAG_TRACE) {
         CREATE_TRY(cudaMalloc(&h->d_trace, (size_t)h->grid * 3 * sizeof(unsigned long long)));
         CREATE_TRY(cudaMemset(h->d_trace, 0, (size_t)h->grid * 3 * sizeof(unsigned long long)));
@@ -614,7 +635,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = c.dtype == B200ADJ_F32 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
+        rc = c.dtype != B200ADJ_F64 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
                                     : mlp_forward_launch<double>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
     } else if (!is_sde(c)) {
         OdeFwdArgs a;
@@ -693,7 +714,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = c.dtype == B200ADJ_F32 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
+        rc = c.dtype != B200ADJ_F64 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
     } else if (!is_sde(c)) {
         OdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;

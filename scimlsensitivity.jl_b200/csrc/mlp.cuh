@@ -15,6 +15,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cuda_bf16.h>
 #include "ode_tsit5.cuh"
 
 namespace b200adj {
@@ -28,6 +29,7 @@ template <class T> struct MlpArgs {
     const T* u0; const T* p; T* ckpt; T* saved; const int32_t* save_of_step; int32_t* status;
     const T* dLdu; T* du0; T* partials; T* dp;     // partials [grid][P]
     int64_t N; int32_t S; double cost_a, cost_b; uint32_t flags;
+    void* tapeA; void* tapeB; int64_t Ktot, Npad;     // bf16 mode: K-major operand tapes [64][Ktot], Ktot = 6 S Npad
     Tsit5Tables tb;
 };
 
@@ -130,10 +132,25 @@ template <class T> struct MlpGrad {
 };
 
 // grad += c * F(y)' L  with the activations of the last forward/backward pair (s.y, s.L, s.H1, s.H2, s.D1, s.D2), members >= nvalid masked
-template <class T>
-__device__ __forceinline__ void mlp_accumulate(const MlpSmem<T>& s, MlpGrad<T>& g, T c, int nvalid) {
+template <class T, bool TAPE>
+__device__ __forceinline__ void mlp_accumulate(const MlpSmem<T>& s, MlpGrad<T>& g, T c, int nvalid,
+                                               __nv_bfloat16* tapeA, __nv_bfloat16* tapeB, int64_t Ktot, int64_t kbase) {
     const int i0 = (threadIdx.x / 16) * 4, j0 = (threadIdx.x % 16) * 4, t = threadIdx.x;
-    for (int b = 0; b < nvalid; b++) {
+    if (TAPE) {
+        // dW2 goes to the tensor cores: write this point's operands (c * Delta2 and H1, 64 rows x 32 members each) as
+        // K-major bf16; thread -> (row, 8-member segment) -> one 16 B store per tape; members past nvalid contribute 0
+        const int row = t >> 2, seg = (t & 3) * 8;
+        __align__(16) __nv_bfloat16 va[8], vb[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const bool ok = seg + q < nvalid;
+            va[q] = __float2bfloat16(ok ? (float)(c * s.D2[row][seg + q]) : 0.f);
+            vb[q] = __float2bfloat16(ok ? (float)s.H1[row][seg + q] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(tapeA + (int64_t)row * Ktot + kbase + seg) = *reinterpret_cast<const uint4*>(va);
+        *reinterpret_cast<uint4*>(tapeB + (int64_t)row * Ktot + kbase + seg) = *reinterpret_cast<const uint4*>(vb);
+    }
+    for (int b = 0; b < (TAPE ? 0 : nvalid); b++) {
         T d[4], h[4];
 #pragma unroll
         for (int r = 0; r < 4; r++) { d[r] = c * s.D2[i0 + r][b]; h[r] = s.H1[j0 + r][b]; }
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_forward_kernel(const __grid_c
 }
 
 // ---- fused reverse pass, InterpolatingAdjoint ----
-template <class T, int COST>
+template <class T, int COST, bool TAPE>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_constant__ MlpArgs<T> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MlpSmem<T>& s = *reinterpret_cast<MlpSmem<T>*>(smem_raw);
@@ -273,7 +290,8 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
             mlp_forward<T>(s);
             mlp_backward<T>(s);
             if (own) s.ka[st][c][b] = s.JTL[c][b];
-            mlp_accumulate<T>(s, g, (T)tb.hA[6][st], nvalid);
+            mlp_accumulate<T, TAPE>(s, g, (T)tb.hA[6][st], nvalid, (__nv_bfloat16*)a.tapeA, (__nv_bfloat16*)a.tapeB, a.Ktot,
+                                    ((int64_t)(a.S - 1 - n) * 6 + st) * a.Npad + base);
             __syncthreads();
         }
         // lambda(t_n) = lam + sum_j h b_j ka_j ; jump at t_n ; shift

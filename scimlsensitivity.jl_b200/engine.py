@@ -34,7 +34,7 @@ class DeviceEnsemble:
         cfg.seed, cfg.traj_offset = int(seed), int(traj_offset)
         cfg.mlp_hidden = 64 if family == "mlp" else 0
         self.dtype = dtype
-        self.np_dtype = np.float32 if dtype == "f32" else np.float64
+        self.np_dtype = np.float64 if dtype == "f64" else np.float32      # bf16_f32acc: fp32 buffers at the ABI
         cfg.checkpoint_every = int(max_steps) if max_steps else 1      # adaptive handles: per-member step capacity
         flags = 0
         if no_start:
@@ -64,7 +64,7 @@ class DeviceEnsemble:
     def _empty(self, *shape, dtype="real"):
         if self.on_device:
             import torch
-            td = torch.int32 if dtype == "i32" else (torch.float32 if self.dtype == "f32" else torch.float64)
+            td = torch.int32 if dtype == "i32" else (torch.float64 if self.dtype == "f64" else torch.float32)
             return torch.empty(shape, dtype=td, device=f"cuda:{self.device}")
         return np.empty(shape, dtype=np.int32 if dtype == "i32" else self.np_dtype)
 
@@ -73,7 +73,7 @@ class DeviceEnsemble:
             import torch
             if not _is_torch(x):
                 x = torch.as_tensor(np.ascontiguousarray(x, dtype=self.np_dtype), device=f"cuda:{self.device}")
-            x = x.to(dtype=torch.float32 if self.dtype == "f32" else torch.float64).contiguous()
+            x = x.to(dtype=torch.float64 if self.dtype == "f64" else torch.float32).contiguous()
             assert tuple(x.shape) == tuple(shape), (tuple(x.shape), shape)
             return x
         if _is_torch(x):
