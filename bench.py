@@ -166,7 +166,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def run_ours(args):
@@ -306,7 +306,7 @@ def run_ours(args):
             "clocks": clocks,
             "dp": dp_check,
         }
-        print(json.dumps(line))
+        emit(line)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
@@ -390,8 +390,28 @@ def run_secondary(args):
             "cpu_baseline": {"value": sample / cpu_s, "unit": "trajectories/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} members of the same workload, one gradient, {cpu_s:.2f} s wall"},
             "gpu_launches": int(eng.handle.launch_count - l0)}
-    print(json.dumps(line))
+    emit(line)
     eng.close()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Everything libraries print (NCCL's version banner, torchrun notices) goes to stderr; stdout carries exactly the
+    one JSON line, written through the saved descriptor by emit()."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -407,6 +427,7 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     elif args.workload != "c2":
