@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("B200ADJ_LIB", os.path.join(_PKG, "libb200adj.so"))   
 
 FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5}
 SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3}
-ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3}
+ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
 DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
 COST = {"explicit": 0, "affine": 1}
 FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE = 1, 2, 4, 8, 16

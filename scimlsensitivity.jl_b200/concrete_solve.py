@@ -60,11 +60,8 @@ def _materialise(eprob, trajectories):
 
 def _step_size(alg, kwargs):
     dt = kwargs.get("dt", getattr(alg, "dt", 0.0))
-    if isinstance(alg, Tsit5) and (alg.adaptive or kwargs.get("adaptive", False)):
-        raise NotImplementedError("adaptive Tsit5 is not built on the B200 path yet (SURVEY.md 8f rank 3): use "
-                                  "Tsit5(adaptive=False, dt=...)")
-    if isinstance(alg, Rosenbrock23):
-        return 0.0                                  # adaptive: error-controlled steps (abstol / reltol keywords)
+    if isinstance(alg, Rosenbrock23) or (isinstance(alg, Tsit5) and alg.adaptive):
+        return float(dt or 0.0)                     # adaptive: error-controlled steps (abstol / reltol keywords); dt = initial step hint
     if not dt or dt <= 0:
         raise ValueError("fixed-step solve needs dt > 0")
     return float(dt)
@@ -97,7 +94,7 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     _check_params(p)
     N_global = u0.shape[1]
     shared_p = (np.ndim(p) == 1) if not _is_torch(p) else (p.dim() == 1)
-    if saveat is None and isinstance(alg, Rosenbrock23):
+    if saveat is None and (isinstance(alg, Rosenbrock23) or (isinstance(alg, Tsit5) and alg.adaptive)):
         raise ValueError("adaptive solve on the B200 path needs explicit saveat times")
     ts = saveat_to_times(saveat if saveat is not None else _step_size(alg, kwargs), prob.tspan)
     if not save_start and len(ts) and ts[0] == prob.tspan[0]:

@@ -16,6 +16,7 @@
 #include "mlp.cuh"
 #include "tsit5_quad.cuh"
 #include "mlp_umma.cuh"
+#include "tsit5_adaptive.cuh"
 
 using namespace b200adj;
 
@@ -42,7 +43,7 @@ struct Handle {
     unsigned int* d_ticket = nullptr;
     int32_t* d_save_of_step = nullptr;
     // adaptive Rosenbrock23 path: per-member dense forward / reverse solutions
-    bool adaptive = false; int maxs = 0;
+    bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
     int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
@@ -253,6 +254,68 @@ int launch_ros_rev(Handle* h, const RosArgs& a) {
     h->launches++;
     return 0;
 }
+T5aArgs t5a_args(Handle* h) {
+    const b200adj_cfg& c = h->cfg;
+    T5aArgs a;
+    memset(&a, 0, sizeof(a));
+    a.saveat = h->d_saveat; a.partials = h->d_partials; a.ticket = h->d_ticket;
+    a.ft = h->r_ft; a.fu = h->r_fu; a.fk = h->r_fk; a.fn = h->r_fn;
+    a.rt0 = h->r_rt0; a.rh = h->r_rh; a.rz = h->r_rz; a.rk = h->r_rk; a.rn = h->r_rn;
+    a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.qidx = h->r_qidx; a.maxseg = h->maxseg;
+    a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.dt0 = c.dt; a.abstol = c.abstol; a.reltol = c.reltol;
+    a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+    a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    const double A[7][6] = {
+        {0},
+        {0.161},
+        {-0.008480655492356989, 0.335480655492357},
+        {2.8971530571054935, -6.359448489975075, 4.3622954328695815},
+        {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525},
+        {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383},
+        {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774}};
+    const double C[7] = {0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0};
+    const double BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                          0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
+    memcpy(a.A, A, sizeof(A)); memcpy(a.C, C, sizeof(C)); memcpy(a.BT, BT, sizeof(BT));
+    tsit5_weights(0.0, nullptr, a.R);
+    return a;
+}
+template <class Fam>
+int launch_t5a_fwd(Handle* h, const T5aArgs& a) {
+    if (h->cfg.shared_p) t5a_forward_kernel<Fam, true><<<h->grid, h->block, 0, h->stream>>>(a);
+    else t5a_forward_kernel<Fam, false><<<h->grid, h->block, 0, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+template <class Fam, int SA>
+int launch_t5a_rev_sa(Handle* h, const T5aArgs& a) {
+    const bool sp = h->cfg.shared_p, ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (sp) { if (ex) t5a_reverse_kernel<Fam, SA, true, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
+              else t5a_reverse_kernel<Fam, SA, true, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
+    else { if (ex) t5a_reverse_kernel<Fam, SA, false, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
+           else t5a_reverse_kernel<Fam, SA, false, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
+    h->launches++;
+    return 0;
+}
+template <class Fam>
+int launch_t5a_rev(Handle* h, const T5aArgs& a) {
+    switch (h->cfg.sensealg) {
+    case B200ADJ_SA_INTERPOLATING: return launch_t5a_rev_sa<Fam, SA_INTERP>(h, a);
+    case B200ADJ_SA_GAUSS: return launch_t5a_rev_sa<Fam, SA_GAUSS>(h, a);
+    case B200ADJ_SA_QUADRATURE: {
+        int rc = launch_t5a_rev_sa<Fam, SA_QUAD>(h, a);
+        if (rc) return rc;
+        const int qb = 128, qg = (int)((h->cfg.N + 3) / 4);
+        if ((size_t)qg > h->qpartials_blocks) return B200ADJ_ERR_INVALID;
+        if (h->cfg.shared_p) t5a_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(a);
+        else t5a_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(a);
+        h->launches++;
+        return 0;
+    }
+    default: return B200ADJ_ERR_UNSUPPORTED;
+    }
+}
+
 RosArgs ros_args(Handle* h) {
     const b200adj_cfg& c = h->cfg;
     RosArgs a;
@@ -346,7 +409,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     int d, P, m;
     if (fam_dims(*cfg, &d, &P, &m)) { g_create_error = "rhs_family not built (MLP / unknown)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->d != d || cfg->P != P) { g_create_error = "cfg.d / cfg.P do not match rhs_family"; return B200ADJ_ERR_INVALID; }
-    const bool ros = cfg->stepper == B200ADJ_ST_ROSENBROCK23;
+    const bool t5a = cfg->stepper == B200ADJ_ST_TSIT5_ADAPTIVE;
+    const bool ros = cfg->stepper == B200ADJ_ST_ROSENBROCK23 || t5a;      // per-member adaptive framework
     if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || (!ros && !(cfg->dt > 0)) || !(cfg->t1 > cfg->t0)) {
         g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
     const bool mlp = cfg->rhs_family == B200ADJ_FAM_MLP;
@@ -363,7 +427,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
         if (cfg->sensealg < 0 || cfg->sensealg > 3) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "Rosenbrock23 needs abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
+        if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
+        if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (ros && cfg->sensealg == B200ADJ_SA_BACKSOLVE) { g_create_error = "adaptive steppers: Interpolating (Tsit5) / Gauss / Quadrature are built"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (ros && !t5a && cfg->sensealg == B200ADJ_SA_INTERPOLATING) { g_create_error = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     }
     if (ros) {
         // adaptive path: save times are arbitrary ascending points of [t0, t1] (tstops of the reverse solve)
@@ -372,7 +439,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
                 g_create_error = "saveat must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }
         }
         Handle* h = new Handle();
-        h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true;
+        h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true; h->nk = t5a ? 7 : 2;
         h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
         h->cfg.saveat = h->saveat.data();
         h->maxs = cfg->checkpoint_every > 1 ? cfg->checkpoint_every : 4096;      // per-member step capacity (forward and dense reverse)
@@ -390,12 +457,12 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         const size_t N = (size_t)cfg->N, MS = (size_t)h->maxs, e = sizeof(double);
         CREATE_TRY(cudaMalloc(&h->r_ft, (MS + 1) * N * e));
         CREATE_TRY(cudaMalloc(&h->r_fu, (MS + 1) * d * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_fk, MS * 2 * d * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_fk, MS * h->nk * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_fn, N * sizeof(int32_t)));
         CREATE_TRY(cudaMalloc(&h->r_rt0, MS * N * e));
         CREATE_TRY(cudaMalloc(&h->r_rh, MS * N * e));
         CREATE_TRY(cudaMalloc(&h->r_rz, MS * d * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_rk, MS * 2 * d * N * e));
+        CREATE_TRY(cudaMalloc(&h->r_rk, MS * h->nk * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_rn, N * sizeof(int32_t)));
         h->maxseg = 2 * h->maxs;                                              // quadgk segment capacity per member
         CREATE_TRY(cudaMalloc(&h->r_qseg, (size_t)h->maxseg * (2 + P) * N * e));
@@ -523,7 +590,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
-        if (sensealg != B200ADJ_SA_GAUSS && sensealg != B200ADJ_SA_QUADRATURE) { h->err = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (sensealg == B200ADJ_SA_BACKSOLVE || (sensealg == B200ADJ_SA_INTERPOLATING && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE)) {
+            h->err = "adaptive steppers: Interpolating (Tsit5) / Gauss / Quadrature are built"; return B200ADJ_ERR_UNSUPPORTED; }
         if (K >= 0) {
             for (int k = 0; k < K; k++)
                 if (t[k] < c.t0 || t[k] > c.t1 || (k > 0 && !(t[k] > t[k - 1]))) { h->err = "t must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }
@@ -625,7 +693,16 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     }
     h->cur_p = dp;
     int rc = 0;
-    if (h->adaptive) {
+    if (h->adaptive && c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE) {
+        T5aArgs a = t5a_args(h);
+        a.u0 = du0; a.p = dp; a.saved = c.K > 0 ? dsaved : nullptr; a.status = dstatus;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_t5a_fwd<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_t5a_fwd<Lorenz>(h, a); break;
+        case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_fwd<Robertson>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    } else if (h->adaptive) {
         RosArgs a = ros_args(h);
         a.u0 = du0; a.p = dp; a.saved = c.K > 0 ? dsaved : nullptr; a.status = dstatus;
         switch (c.rhs_family) {
@@ -702,7 +779,18 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         ddu0 = h->s_du0; ddp = h->s_dp;
     }
     int rc = 0;
-    if (h->adaptive) {
+    if (h->adaptive && c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE) {
+        T5aArgs a = t5a_args(h);
+        a.p = h->cur_p; a.dLdu = dL; a.du0 = ddu0; a.dp_members = ddp; a.dp = ddp;
+        if (h->adj_abstol > 0) a.abstol = h->adj_abstol;
+        if (h->adj_reltol > 0) a.reltol = h->adj_reltol;
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_t5a_rev<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_t5a_rev<Lorenz>(h, a); break;
+        case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_rev<Robertson>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
+    } else if (h->adaptive) {
         RosArgs a = ros_args(h);
         a.p = h->cur_p; a.dLdu = dL; a.du0 = ddu0; a.dp_members = ddp; a.dp = ddp;
         if (h->adj_abstol > 0) a.abstol = h->adj_abstol;

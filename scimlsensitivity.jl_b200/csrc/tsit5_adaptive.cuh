@@ -1,0 +1,357 @@
+// tsit5_adaptive.cuh -- error-controlled Tsit5 (the reference's default non-stiff solver, BASELINE config C1) on the
+// per-member adaptive framework of ros23.cuh: forward solve with a per-member dense solution (t_n, u_n, k1..k7), adaptive
+// reverse adjoint solve for InterpolatingAdjoint (z = [lambda; mu]), GaussAdjoint (3-point Gauss-Legendre per accepted
+// step) and QuadratureAdjoint (dense lambda, then ros23.cuh::quadgk_warp).  One member per thread.
+//
+// Reference functions replaced: src/interpolating_adjoint.jl:150-174, src/gauss_adjoint.jl:118-128, :745-759,
+// src/quadrature_adjoint.jl:35-46, :486-502, :537-616, split_states sol(y,t,continuity=:right), ReverseLossCallback
+// src/adjoint_common.jl:754-821.  Upstream arithmetic restated: Tsit5 tableau, embedded error
+// weights, 4th-order dense output, PI controller (beta1 = 7/50, beta2 = 2/25, gamma = 0.9, q in [1/10, 5], qoldinit 1e-4).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "families.cuh"
+#include "ode_tsit5.cuh"
+#include "ros23.cuh"
+
+namespace b200adj {
+
+struct T5aArgs {
+    const double* u0; const double* p; const double* saveat; const double* dLdu;
+    double* saved; int32_t* status;
+    double* du0; double* dp_members; double* partials; double* dp; unsigned int* ticket;
+    double* ft; double* fu; double* fk; int32_t* fn;              // forward dense: [MAXS+1][N], [MAXS+1][D][N], [MAXS][7][D][N], [N]
+    double* rt0; double* rh; double* rz; double* rk; int32_t* rn; // reverse dense (Quadrature): [MAXS][N] x2, [MAXS][D][N], [MAXS][7][D][N], [N]
+    double* qseg; double* qkey; int32_t* qidx; int32_t maxseg;
+    int64_t N; int32_t K; int32_t maxs;
+    double t0, t1, dt0, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
+    uint32_t flags;
+    double A[7][6];         // Tsit5 tableau (row 6 = b)
+    double C[7];
+    double BT[7];           // embedded error weights b - bhat
+    double R[7][4];         // dense-output polynomials: b_j(theta) = sum_m R[j][m] theta^(m+1)
+};
+
+__device__ __forceinline__ void t5_weights(const T5aArgs& a, double th, double* w) {
+#pragma unroll
+    for (int j = 0; j < 7; j++) w[j] = th * (a.R[j][0] + th * (a.R[j][1] + th * (a.R[j][2] + th * a.R[j][3])));
+}
+
+// forward dense solution of one member
+template <int D>
+struct T5Dense {
+    const T5aArgs& a; int64_t i; int n;
+    __device__ __forceinline__ double T(int idx) const { return a.ft[(int64_t)idx * a.N + i]; }
+    __device__ __forceinline__ void eval(double t, bool right, double* y) const {
+        int lo = 0, hi = n, iv;
+        if (right) { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) <= t) lo = mid; else hi = mid; } iv = lo; if (iv > n - 1) iv = n - 1; }
+        else { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) >= t) hi = mid; else lo = mid; } iv = hi - 1; if (iv < 0) iv = 0; }
+        const double ta = T(iv), h = T(iv + 1) - ta;
+        const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
+        double w[7];
+        t5_weights(a, th, w);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 7; s++) acc += w[s] * a.fk[(((int64_t)iv * 7 + s) * D + j) * a.N + i];
+            y[j] = a.fu[((int64_t)iv * D + j) * a.N + i] + h * acc;
+        }
+    }
+};
+
+// one Tsit5 step of length h from (t, z) with k[0] = rhs(t, z) given; fills k[1..6], znew
+template <int L, class RHS>
+__device__ __forceinline__ void t5_step(const T5aArgs& a, const RHS& rhs, double t, double h, const double* z, double (*k)[L], double* zn) {
+    double tmp[L];
+#pragma unroll
+    for (int s = 1; s < 7; s++) {
+#pragma unroll
+        for (int c = 0; c < L; c++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; j++) if (j < s) acc += a.A[s][j] * k[j][c];
+            tmp[c] = z[c] + h * acc;
+        }
+        if (s == 6) {
+#pragma unroll
+            for (int c = 0; c < L; c++) zn[c] = tmp[c];
+        }
+        rhs(t + a.C[s] * h, tmp, k[s]);
+    }
+}
+template <int L>
+__device__ __forceinline__ double t5_error(const T5aArgs& a, double h, const double* z, const double* zn, const double (*k)[L]) {
+    double e2 = 0;
+#pragma unroll
+    for (int c = 0; c < L; c++) {
+        double e = 0;
+#pragma unroll
+        for (int j = 0; j < 7; j++) e += a.BT[j] * k[j][c];
+        e *= h;
+        const double sc = a.abstol + a.reltol * fmax(fabs(z[c]), fabs(zn[c]));
+        e2 += (e / sc) * (e / sc);
+    }
+    return sqrt(e2 / L);
+}
+
+template <class Fam, bool SHARED_P>
+__global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant__ T5aArgs a) {
+    constexpr int D = Fam::D, P = Fam::P;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.N) return;
+    const int64_t N = a.N;
+    double p[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+    double u[D], un[D], k[7][D];
+#pragma unroll
+    for (int j = 0; j < D; j++) { u[j] = a.u0[(int64_t)j * N + i]; a.fu[(int64_t)j * N + i] = u[j]; }
+    a.ft[i] = a.t0;
+    auto rhs = [&](double, const double* x, double* dx) { Fam::f(x, p, dx); };
+    Fam::f(u, p, k[0]);
+    double t = a.t0, h = a.dt0 > 0 ? a.dt0 : 1e-3 * (a.t1 - a.t0), qold = 1e-4;
+    int n = 0, ksave = 0, stat = 0;
+    long iters = 0;
+    while (a.saved && ksave < a.K && a.saveat[ksave] <= a.t0) {
+#pragma unroll
+        for (int j = 0; j < D; j++) a.saved[((int64_t)ksave * D + j) * N + i] = u[j];
+        ksave++;
+    }
+    while (t < a.t1) {
+        if (++iters > 10000000L || n >= a.maxs) { stat = 2; break; }
+        bool last = false;
+        if (t + h >= a.t1 || fabs(t + h - a.t1) < 100 * 2.22e-16 * fabs(a.t1)) { h = a.t1 - t; last = true; }
+        t5_step<D>(a, rhs, t, h, u, k, un);
+        const double EEst = t5_error<D>(a, h, u, un, k);
+        const double q11 = pow(fmax(EEst, 1e-300), 7.0 / 50.0);
+        double q = q11 / pow(qold, 2.0 / 25.0);
+        q = fmax(1.0 / 10.0, fmin(5.0, q / 0.9));
+        if (EEst <= 1.0) {
+            const double tn = last ? a.t1 : t + h;
+            while (a.saved && ksave < a.K && a.saveat[ksave] <= tn) {
+                const double hh = tn - t, th = (hh == 0.0) ? 1.0 : (a.saveat[ksave] - t) / hh;
+                double w[7];
+                t5_weights(a, th, w);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 7; s++) acc += w[s] * k[s][j];
+                    a.saved[((int64_t)ksave * D + j) * N + i] = u[j] + hh * acc;
+                }
+                ksave++;
+            }
+#pragma unroll
+            for (int s = 0; s < 7; s++)
+#pragma unroll
+                for (int j = 0; j < D; j++) a.fk[(((int64_t)n * 7 + s) * D + j) * N + i] = k[s][j];
+#pragma unroll
+            for (int j = 0; j < D; j++) { a.fu[((int64_t)(n + 1) * D + j) * N + i] = un[j]; u[j] = un[j]; k[0][j] = k[6][j]; }
+            t = tn; a.ft[(int64_t)(n + 1) * N + i] = t;
+            n++;
+            qold = fmax(EEst, 1e-4);
+            h = h / q;
+        } else {
+            h = h / fmin(5.0, q11 / 0.9);
+        }
+    }
+    a.fn[i] = n;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < D; j++) ok = ok && isfinite(u[j]);
+    if (!ok && stat == 0) stat = 1;
+    if (a.status) a.status[i] = stat;
+}
+
+// reverse adjoint solve.  SA_INTERP: z = [lambda; mu] (L = D + P); SA_GAUSS / SA_QUAD: z = lambda (L = D)
+template <class Fam, int SA, bool SHARED_P, int COST>
+__global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant__ T5aArgs a) {
+    constexpr int D = Fam::D, P = Fam::P, L = (SA == SA_INTERP) ? D + P : D;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gi < a.N;
+    const int64_t i = active ? gi : a.N - 1;
+    const int64_t N = a.N;
+    double p[P], acc[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; acc[q] = 0.0; }
+    T5Dense<D> sol{a, i, a.fn[i]};
+    double z[L], zn[L], k[7][L];
+#pragma unroll
+    for (int c = 0; c < L; c++) z[c] = 0.0;
+    // adjoint RHS: dlam = -J(y(t))' lam, dmu = -F(y(t))' lam  (right-continuous forward lookup)
+    auto rhs = [&](double tt, const double* x, double* dx) {
+        double y[D];
+        sol.eval(tt, true, y);
+        Fam::vjp_u(y, p, x, dx);
+#pragma unroll
+        for (int j = 0; j < D; j++) dx[j] = -dx[j];
+        if (SA == SA_INTERP) {
+            double dg[P];
+            Fam::vjp_p(y, p, x, dg);
+#pragma unroll
+            for (int q = 0; q < P; q++) dx[D + q] = -dg[q];
+        }
+    };
+    const double T = a.t1, t0 = a.t0;
+    double t = T;
+    int cur = a.K - 1, nrev = 0;
+    bool fsal_ok = false, overflow = false;
+    auto jump_if_at = [&](double tt) {
+        while (cur >= 0 && fabs(a.saveat[cur] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
+            if (!((a.flags & 1u) && cur == 0)) {
+                if (COST == COST_EXPLICIT) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[j] += a.dLdu[((int64_t)cur * D + j) * N + i];
+                } else {
+                    double y[D];
+                    sol.eval(a.saveat[cur], true, y);
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[j] += a.cost_a * y[j] + a.cost_b;
+                }
+            }
+            cur--; fsal_ok = false;
+        }
+    };
+    jump_if_at(t);
+    double h = a.dt0 > 0 ? -a.dt0 : -1e-4 * (T - t0), qold = 1e-4;
+    long iters = 0;
+    while (t > t0 && sol.n > 0) {
+        if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) { overflow = true; break; }
+        double tstop = t0;
+        if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
+        double tn = tstop_snap(t + h, tstop);
+        if (tn < tstop) tn = tstop;
+        const double hs = tn - t;
+        if (!fsal_ok) rhs(t, z, k[0]);
+        t5_step<L>(a, rhs, t, hs, z, k, zn);
+        const double EEst = t5_error<L>(a, hs, z, zn, k);
+        const double q11 = pow(fmax(EEst, 1e-300), 7.0 / 50.0);
+        const double q = fmax(0.1, fmin(5.0, q11 / pow(qold, 2.0 / 25.0) / 0.9));
+        if (EEst > 1.0) { h = hs / fmin(5.0, q11 / 0.9); fsal_ok = true; continue; }
+        qold = fmax(EEst, 1e-4); h = hs / q;
+        if (SA == SA_GAUSS) {
+            const double gx[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};
+            const double gw[3] = {0.5555555555555556, 0.8888888888888888, 0.5555555555555556};
+#pragma unroll
+            for (int g = 0; g < 3; g++) {
+                const double tj = 0.5 * (tn - t) * gx[g] + 0.5 * (tn + t), th = (tj - t) / hs;
+                double w[7], lq[D], y[D], dg[P];
+                t5_weights(a, th, w);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    double s_ = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 7; s++) s_ += w[s] * k[s][j];
+                    lq[j] = z[j] + hs * s_;
+                }
+                sol.eval(tj, false, y);
+                Fam::vjp_p(y, p, lq, dg);
+#pragma unroll
+                for (int q2 = 0; q2 < P; q2++) acc[q2] += (0.5 * (tn - t)) * gw[g] * (-dg[q2]);
+            }
+        } else if (SA == SA_QUAD && active) {
+            a.rt0[(int64_t)nrev * N + i] = t; a.rh[(int64_t)nrev * N + i] = hs;
+#pragma unroll
+            for (int j = 0; j < D; j++) a.rz[((int64_t)nrev * D + j) * N + i] = z[j];
+#pragma unroll
+            for (int s = 0; s < 7; s++)
+#pragma unroll
+                for (int j = 0; j < D; j++) a.rk[(((int64_t)nrev * 7 + s) * D + j) * N + i] = k[s][j];
+        }
+        nrev++;
+#pragma unroll
+        for (int c = 0; c < L; c++) { z[c] = zn[c]; k[0][c] = k[6][c]; }
+        fsal_ok = true;
+        t = tn;
+        jump_if_at(t);
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < D; j++) a.du0[(int64_t)j * N + i] = overflow ? qnan : z[j];
+        if (SA == SA_QUAD) a.rn[i] = overflow ? -1 : nrev;
+    }
+    if (SA != SA_QUAD) {
+        double out[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) out[q] = overflow ? qnan : (SA == SA_INTERP ? z[D + (SA == SA_INTERP ? q : 0)] : acc[q]);
+        if (SHARED_P) {
+            if (!active) {
+#pragma unroll
+                for (int q = 0; q < P; q++) out[q] = 0.0;
+            }
+            reduce_dp<P>(out, a.partials, a.dp, a.ticket);
+        } else if (active) {
+#pragma unroll
+            for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = out[q];
+        }
+    }
+}
+
+// QuadratureAdjoint integrand on the two dense solutions
+template <class Fam, int D, int P>
+struct T5aQuadCtx {
+    const T5aArgs& a; T5Dense<D> sol; int nrev; int64_t i; const double* p;
+    __device__ __forceinline__ void operator()(double t, double* out) const {
+        double y[D], lam[D], w[7];
+        sol.eval(t, false, y);
+        int lo = 0, hi = nrev - 1;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (a.rt0[(int64_t)mid * a.N + i] + a.rh[(int64_t)mid * a.N + i] <= t) hi = mid; else lo = mid + 1; }
+        const double ts = a.rt0[(int64_t)lo * a.N + i], h = a.rh[(int64_t)lo * a.N + i];
+        t5_weights(a, (t - ts) / h, w);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double s_ = 0.0;
+#pragma unroll
+            for (int s = 0; s < 7; s++) s_ += w[s] * a.rk[(((int64_t)lo * 7 + s) * D + j) * a.N + i];
+            lam[j] = a.rz[((int64_t)lo * D + j) * a.N + i] + h * s_;
+        }
+        Fam::vjp_p(y, p, lam, out);
+    }
+};
+
+template <class Fam, bool SHARED_P>
+__global__ void __launch_bounds__(128) t5a_quadrature_kernel(const __grid_constant__ T5aArgs a) {
+    constexpr int D = Fam::D, P = Fam::P;
+    const int lane = threadIdx.x & 31;
+    const int64_t gi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const bool active = gi < a.N;
+    const int64_t i = active ? gi : a.N - 1;
+    double p[P], res[P], part[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * a.N + i]; res[q] = 0.0; }
+    T5aQuadCtx<Fam, D, P> ctx{a, T5Dense<D>{a, i, a.fn[i]}, a.rn[i], i, p};
+    const QuadScratch qs{a.qseg, a.qkey, a.qidx, a.maxseg, a.N, i};
+    const int K = a.K;
+    bool ok = ctx.nrev >= 0;
+    auto add = [&](double lo, double hi) {
+        ok = quadgk_warp<P>(ctx, lo, hi, a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
+#pragma unroll
+        for (int q = 0; q < P; q++) res[q] += part[q];
+    };
+    if (ctx.nrev > 0) {
+        if (K == 0) add(a.t0, a.t1);
+        else {
+            if (a.saveat[K - 1] != a.t1) add(a.saveat[K - 1], a.t1);
+            for (int k = K - 2; k >= 0; k--) if (a.saveat[k] != a.saveat[k + 1]) add(a.saveat[k], a.saveat[k + 1]);
+            if (a.saveat[0] != a.t0) add(a.t0, a.saveat[0]);
+        }
+    }
+    if (!ok) {
+#pragma unroll
+        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    if (SHARED_P) {
+        if (!active || lane != 0) {
+#pragma unroll
+            for (int q = 0; q < P; q++) res[q] = 0.0;
+        }
+        reduce_dp<P>(res, a.partials, a.dp, a.ticket);
+    } else if (active && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * a.N + i] = res[q];
+    }
+}
+
+}  // namespace b200adj

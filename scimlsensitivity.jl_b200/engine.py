@@ -50,7 +50,7 @@ class DeviceEnsemble:
         cfg.flags, cfg.block_threads = flags, int(block_threads)
         self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
         self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)
-        self.adaptive = stepper == "rosenbrock23"
+        self.adaptive = stepper in ("rosenbrock23", "tsit5_adaptive")
         self.S = 0 if self.adaptive else int(round((cfg.t1 - cfg.t0) / cfg.dt))
         self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
         self.handle = _lib.Handle(cfg, self.saveat)

@@ -66,9 +66,12 @@ class EnsembleProblem:
 # ---- solver algorithms ----
 @dataclass(frozen=True)
 class Tsit5:
-    adaptive: bool = False
+    adaptive: bool = False       # False: fixed step dt; True: error-controlled (abstol / reltol keywords of solve)
     dt: float = 0.0
-    code = "tsit5_fixed"
+
+    @property
+    def code(self):
+        return "tsit5_adaptive" if self.adaptive else "tsit5_fixed"
 
 
 @dataclass(frozen=True)

@@ -1,0 +1,67 @@
+"""Error-controlled Tsit5 on the device (BASELINE config C1: Lotka-Volterra d=2, single trajectory, InterpolatingAdjoint,
+Tsit5, u0=[1,1], p=[1.5,1,3,1], T=10, saveat=0.1, loss=sum(sol); test/Core1/concrete_solve_derivatives.jl:106-157) and
+ensembles of it, against the oracle's adaptive Tsit5 (PI controller) and against differentiation through the solver."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import scimlsensitivity_jl_b200 as b
+from oracle import oracle as O
+
+
+def _rel(a, ref):
+    return np.abs(np.asarray(a) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+@pytest.mark.parametrize("sensealg", ["interpolating", "gauss", "quadrature"])
+@pytest.mark.parametrize("N", [1, 100])
+def test_c1_lotka_volterra_adaptive(sensealg, N):
+    T = 10.0
+    saveat = np.linspace(0.0, T, 101)
+    rng = np.random.default_rng(0)
+    u0 = np.ones((2, N)) * (np.exp(0.1 * rng.standard_normal((2, N))) if N > 1 else 1.0)
+    p = np.array([1.5, 1.0, 3.0, 1.0])
+    tol = dict(abstol=1e-10, reltol=1e-10)
+    cfg = O.make_cfg("lv", sensealg, "tsit5_adaptive", N, saveat, 0.0, T, cost=("affine", 0.0, 1.0), quad_abstol=1e-10, quad_reltol=1e-10, **tol)
+    ref = O.gradient(cfg, saveat, u0, p)
+    eng = b.DeviceEnsemble("lv", sensealg, "tsit5_adaptive", N, saveat, (0.0, T), 0.0, cost=b.AffineCost(0.0, 1.0),
+                           quad_abstol=1e-10, quad_reltol=1e-10, max_steps=8192, **tol)
+    saved, status = eng.forward(u0, p)
+    assert (status == 0).all()
+    fsteps, _ = eng.step_counts()
+    assert np.array_equal(fsteps, ref["steps"])                       # same accept/reject sequence as the oracle
+    assert np.abs(saved - ref["saved"]).max() < 1e-11
+    du0, dp = eng.reverse()
+    assert _rel(du0, ref["du0"]) < 1e-8 and _rel(dp, ref["dp"]) < (1e-7 if sensealg == "quadrature" else 1e-8)
+    if N == 1:
+        # C1's own bar: the gradient through the solver (finite differences of the oracle's forward solve), <= 1e-8 rel
+        cfgl = O.make_cfg("lv", "interpolating", "tsit5_adaptive", 1, saveat, 0.0, T, abstol=1e-13, reltol=1e-13, cost=("affine", 0.0, 1.0))
+        g = np.zeros(4)
+        for i in range(4):
+            e = np.zeros(4); e[i] = 1e-5
+            L = lambda q: O.loss(cfgl, saveat, u0, q)[0]
+            g[i] = (-L(p + 2 * e) + 8 * L(p + e) - 8 * L(p - e) + L(p - 2 * e)) / (12e-5)
+        assert _rel(dp, g) < 1e-8
+        assert abs(dp[0] - 8.3053) < 5e-4                             # test/Core6/forward_prob_kwargs.jl:28-30
+    eng.close()
+
+
+def test_adaptive_tsit5_public_api_lorenz():
+    """test/Core3/adjoint.jl:1157-1241 (Lorenz, adaptive Tsit5, dg = u - 2 at 0:0.1:10): Interpolating == Gauss == Quadrature."""
+    N, T = 32, 10.0
+    rng = np.random.default_rng(1)
+    u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.01 * rng.standard_normal((3, N))
+    p = np.array([10.0, 28.0, 8.0 / 3.0])
+    t = np.linspace(0.0, T, 101)
+    prob = b.EnsembleProblem(b.ODEProblem("lorenz", u0[:, 0], (0.0, T), p), u0s=u0)
+    alg = b.Tsit5(adaptive=True)
+    sol = b.solve(prob, alg, saveat=t, abstol=1e-12, reltol=1e-12, maxiters=16384)
+    res = {}
+    for inner, name in ((b.InterpolatingAdjoint(), "interpolating"), (b.GaussAdjoint(), "gauss"), (b.QuadratureAdjoint(abstol=1e-9, reltol=1e-9), "quadrature")):
+        du0, dp = b.adjoint_sensitivities(sol, alg, t=t, dgdu_discrete=b.AffineCost(1.0, -2.0), sensealg=inner, abstol=1e-12, reltol=1e-12)
+        cfg = O.make_cfg("lorenz", name, "tsit5_adaptive", N, t, 0.0, T, abstol=1e-12, reltol=1e-12, cost=("affine", 1.0, -2.0), quad_abstol=1e-9, quad_reltol=1e-9)
+        ref = O.gradient(cfg, t, u0, p)
+        assert _rel(du0, ref["du0"]) < 1e-6 and _rel(dp.ravel(), ref["dp"]) < 1e-6          # chaotic: rounding amplified ~1e4
+        res[name] = dp.ravel()
+    assert _rel(res["gauss"], res["interpolating"]) < 1e-6 and _rel(res["quadrature"], res["interpolating"]) < 1e-6
