@@ -504,7 +504,10 @@ __global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
     const int K = a.K;
     const QuadScratch qs{a.qseg, a.qkey, a.qidx, a.maxseg, N, i};
     bool ok = true;
-    if (ctx.nrev < 0) {
+    // warps past N shadow member N-1 for the block reduction only: they must NOT run the quadrature (they would share
+    // member N-1's segment scratch with its real warp)
+    if (!active) {
+    } else if (ctx.nrev < 0) {
 #pragma unroll
         for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
     } else if (ctx.nrev > 0) {

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(128) t5a_quadrature_kernel(const __grid_consta
 #pragma unroll
         for (int q = 0; q < P; q++) res[q] += part[q];
     };
-    if (ctx.nrev > 0) {
+    if (active && ctx.nrev > 0) {       // warps past N only take part in the block reduction
         if (K == 0) add(a.t0, a.t1);
         else {
             if (a.saveat[K - 1] != a.t1) add(a.saveat[K - 1], a.t1);

@@ -79,7 +79,9 @@ __global__ void __launch_bounds__(128) tsit5_quadrature_kernel(const __grid_cons
 #pragma unroll
         for (int q = 0; q < P; q++) res[q] += part[q];
     };
-    if (K == 0) add(a.t0, a.t1);
+    // warps past N only take part in the block reduction (they would share member N-1's segment scratch otherwise)
+    if (!active) {
+    } else if (K == 0) add(a.t0, a.t1);
     else {
         if (a.saveat[K - 1] != a.t1) add(a.saveat[K - 1], a.t1);
         for (int k = K - 2; k >= 0; k--) if (a.saveat[k] != a.saveat[k + 1]) add(a.saveat[k], a.saveat[k + 1]);

@@ -96,9 +96,10 @@ def test_parameter_compatibility_errors():
     prob = b.EnsembleProblem(b.ODEProblem("lorenz", [1.0, 0, 0], (0.0, 1.0), np.ones(3), callback=object()), u0s=np.ones((3, 4)))
     with pytest.raises(NotImplementedError):
         b.solve(prob, b.Tsit5(dt=0.01), saveat=0.1)
+    assert b.Tsit5(adaptive=True).code == "tsit5_adaptive" and b.Tsit5(dt=0.1).code == "tsit5_fixed"
     prob = b.EnsembleProblem(b.ODEProblem("lorenz", [1.0, 0, 0], (0.0, 1.0), np.ones(3)), u0s=np.ones((3, 4)))
-    with pytest.raises(NotImplementedError):
-        b.solve(prob, b.Tsit5(adaptive=True), saveat=0.1)
+    with pytest.raises(ValueError):
+        b.solve(prob, b.Tsit5(adaptive=True))              # adaptive solves need explicit save times
     with pytest.raises(KeyError):
         b.solve(b.EnsembleProblem(b.ODEProblem("nope", [1.0], (0.0, 1.0), np.ones(3)), u0s=np.ones((1, 4))), b.Tsit5(dt=0.01), saveat=0.1)
 

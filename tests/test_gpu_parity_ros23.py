@@ -28,7 +28,7 @@ def _robertson(N, seed=0, shared=False):
 @pytest.mark.parametrize("shared_p", [False, True])
 @pytest.mark.parametrize("cost", ["affine", "explicit"])
 def test_robertson_ros23(sensealg, shared_p, cost):
-    N, T = 100, 100.0
+    N, T = 101, 100.0          # not a multiple of the 4 members per quadrature block
     saveat = np.logspace(-2, 2, 10); saveat[-1] = T
     u0, k = _robertson(N, shared=shared_p)
     tol = dict(abstol=1e-8, reltol=1e-8)
