@@ -117,6 +117,12 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
  * tolerances of QuadratureAdjoint (sensealg.abstol/.reltol, src/quadrature_adjoint.jl:517).  Values <= 0 keep the current. */
 int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_reltol, double quad_abstol, double quad_reltol);
 
+/* Continuous cost functional (dgdu_continuous / dgdp_continuous of adjoint_sensitivities; accumulate_cost!,
+ * src/derivative_wrappers.jl:1411-1442): named family g(u) = a/2 |u|^2 + b sum(u), i.e. dgdu_continuous = a u + b,
+ * dgdp_continuous = 0, added to the adjoint RHS of the NEXT reverse pass (on top of the discrete cost, if any).
+ * Built for the fixed-step Tsit5 path; enabled = 0 switches it off. */
+int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b);
+
 /* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
 int32_t b200adj_get_noise(void* handle, void* dW_out);
 

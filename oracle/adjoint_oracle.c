@@ -58,7 +58,8 @@ typedef struct {
     int32_t checkpointing;                  /* Backsolve: reset y at checkpoints          */
     int32_t backsolve_ckpt_every_step;      /* 1: checkpoints = all forward steps (sol.t) */
     int32_t mlp_hidden;                     /* FAM_MLP: hidden width (64)                 */
-    int32_t reserved;
+    int32_t cont_cost;                      /* 1: continuous cost g(u) = ca/2 |u|^2 + cb sum(u) is present (accumulate_cost!) */
+    double cont_a, cont_b;
 } oracle_cfg;
 
 /* =====================================================================================
@@ -593,6 +594,7 @@ typedef struct {
     int sensealg; int ito;
     double* y; double* dgtmp;
     long nrhs;
+    int cont; double ca, cb;      /* continuous cost: dlam -= dgdu_continuous(y) (src/derivative_wrappers.jl:1411-1442) */
 } adj_ctx;
 
 /* z layout: Interp [lam(d); mu(P)], Gauss/Quad [lam(d)], Backsolve [lam(d); mu(P); y(d)] */
@@ -604,6 +606,7 @@ static void adj_rhs(double t, const double* z, double* dz, void* c) {
         const double* y = z + d + P;                       /* y read from the state (backsolve_adjoint.jl:78-90) */
         vjp(y, x->p, t, z, dz, dz + d, &F->ctx);
         for (int i = 0; i < d + P; i++) dz[i] = -dz[i];      /* :56-57 */
+        if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca * y[i] + x->cb;
         (x->ito ? F->f_ito : F->f)(y, x->p, t, dz + d + P, &F->ctx);  /* dy = f(y) */
     } else {
         dense_eval(x->sol, t, 1, x->y, NULL);              /* sol(y,t,continuity=:right) */
@@ -614,6 +617,7 @@ static void adj_rhs(double t, const double* z, double* dz, void* c) {
             vjp(x->y, x->p, t, z, dz, NULL, &F->ctx);        /* gauss_adjoint.jl:123, quadrature_adjoint.jl:41 */
             for (int i = 0; i < d; i++) dz[i] = -dz[i];
         }
+        if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca * x->y[i] + x->cb;   /* accumulate_cost!: dlam -= g_u */
     }
 }
 /* Jacobian and time derivative of adj_rhs for Rosenbrock23 on the adjoint ODE (Gauss/Quad state = lam):
@@ -760,7 +764,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     double* k = (double*)malloc(sizeof(double) * 7 * L);
     double* ybuf = (double*)malloc(sizeof(double) * (d + 2 * P + 4 * d + 8));
     double* gu = ybuf + d, *lamq = gu + d, *dlq = lamq + d, *integ = dlq + d, *acc = integ + P;
-    adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0};
+    adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0, cfg->cont_cost, cfg->cont_a, cfg->cont_b};
     for (int q = 0; q < P; q++) acc[q] = 0;
     adjdense_t adj; int have_adj = (sa == SA_QUADRATURE);
     if (have_adj) adjdense_init(&adj, L, ros ? DENSE_ROS23 : DENSE_TSIT5);
@@ -1067,6 +1071,35 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
 
 /* scalar loss of COST_AFFINE, L = sum_k sum_j (a/2 u^2 + b u), and explicit-cotangent-free forward solve:
  * used by the tests to differentiate THROUGH the solver by finite differences (the ForwardDiff relation). */
+typedef struct { const dense_t* sol; double ca, cb; int d; double* y; } gint_ctx;
+static void g_integrand(double t, double* out, void* c) {
+    gint_ctx* x = (gint_ctx*)c; double s = 0;
+    dense_eval(x->sol, t, 0, x->y, NULL);
+    for (int j = 0; j < x->d; j++) s += 0.5 * x->ca * x->y[j] * x->y[j] + x->cb * x->y[j];
+    out[0] = s;
+}
+/* integral of the continuous cost along one member's dense forward solution (quadgk per step, tight tolerance) */
+int oracle_continuous_loss(const oracle_cfg* cfg, const double* u0, const double* p, double* out_members, int nthreads) {
+    family_t F; int rc = family_init(&F, cfg); if (rc) return rc;
+    const int d = F.d, P = F.P; const int64_t N = cfg->N;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < N; i++) {
+        double pm[16], um[8], y[8], part; dense_t sol;
+        for (int q = 0; q < P && q < 16; q++) pm[q] = cfg->shared_p ? p[q] : p[(size_t)q * N + i];
+        for (int j = 0; j < d; j++) um[j] = u0[(size_t)j * N + i];
+        forward_dense_member(cfg, &F, pm, um, &sol);
+        gint_ctx gc = {&sol, cfg->cont_a, cfg->cont_b, d, y};
+        double tot = 0;
+        for (int n = 0; n < sol.n; n++) { oracle_quadgk(g_integrand, &gc, 1, sol.t[n], sol.t[n + 1], 1e-14, 1e-13, &part); tot += part; }
+        out_members[i] = tot;
+        dense_free(&sol);
+    }
+    return 0;
+}
+
 int oracle_ensemble_loss(const oracle_cfg* cfg, const double* saveat, const double* u0, const double* p,
                          const double* dW, double* loss_members /* [N] */, int nthreads) {
     const int d = cfg->d, K = cfg->K; const int64_t N = cfg->N;
@@ -1078,6 +1111,12 @@ int oracle_ensemble_loss(const oracle_cfg* cfg, const double* saveat, const doub
         loss_members[i] = s;
     }
     free(saved);
+    if (rc == 0 && cfg->cont_cost) {
+        double* ci = (double*)malloc(sizeof(double) * N);
+        rc = oracle_continuous_loss(cfg, u0, p, ci, nthreads);
+        for (int64_t i = 0; i < N; i++) loss_members[i] += ci[i];
+        free(ci);
+    }
     return rc;
 }
 

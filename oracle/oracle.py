@@ -29,7 +29,8 @@ class OracleCfg(C.Structure):
         ("quad_abstol", C.c_double), ("quad_reltol", C.c_double),
         ("cost_a", C.c_double), ("cost_b", C.c_double),
         ("shared_p", C.c_int32), ("no_start", C.c_int32), ("checkpointing", C.c_int32),
-        ("backsolve_ckpt_every_step", C.c_int32), ("mlp_hidden", C.c_int32), ("reserved", C.c_int32),
+        ("backsolve_ckpt_every_step", C.c_int32), ("mlp_hidden", C.c_int32), ("cont_cost", C.c_int32),
+        ("cont_a", C.c_double), ("cont_b", C.c_double),
     ]
 
 
@@ -59,7 +60,7 @@ def _ptr(a):
 
 def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, reltol=1e-3, quad_abstol=1e-10,
              quad_reltol=1e-10, cost=("explicit",), shared_p=True, no_start=False, checkpointing=True,
-             ckpt_every_step=False, d=None, P=None, mlp_hidden=0):
+             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None):
     if family == "mlp":
         d = 2
         H = mlp_hidden
@@ -78,6 +79,8 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
     cfg.quad_abstol, cfg.quad_reltol = quad_abstol, quad_reltol
     cfg.shared_p, cfg.no_start, cfg.checkpointing = int(shared_p), int(no_start), int(checkpointing)
     cfg.backsolve_ckpt_every_step, cfg.mlp_hidden = int(ckpt_every_step), mlp_hidden
+    if cont_cost is not None:      # continuous cost g(u) = a/2 |u|^2 + b sum(u)
+        cfg.cont_cost, cfg.cont_a, cfg.cont_b = 1, float(cont_cost[0]), float(cont_cost[1])
     return cfg
 
 

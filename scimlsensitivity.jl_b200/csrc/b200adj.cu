@@ -45,6 +45,7 @@ struct Handle {
     // adaptive Rosenbrock23 path: per-member dense forward / reverse solutions
     bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
+    bool cont_on = false; double cont_a = 0, cont_b = 0;   // continuous cost family
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
     int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
     double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
@@ -634,6 +635,15 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     return B200ADJ_OK;
 }
 
+int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    if (enabled && (h->adaptive || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
+        h->err = "continuous cost: built for the fixed-step Tsit5 ODE path only"; return B200ADJ_ERR_UNSUPPORTED; }
+    h->cont_on = enabled != 0; h->cont_a = a; h->cont_b = b;
+    return B200ADJ_OK;
+}
+
 int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_reltol, double quad_abstol, double quad_reltol) {
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
@@ -809,7 +819,8 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
         a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.trace = h->d_trace;
         a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
-                  ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
+                  ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u) | (h->cont_on ? 8u : 0u);
+        a.cont_a = h->cont_a; a.cont_b = h->cont_b;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_rev<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_rev<Lorenz>(h, a); break;

@@ -64,7 +64,8 @@ struct OdeRevArgs {
     int64_t Npad;            // checkpoint row pitch
     int32_t S;
     double cost_a, cost_b;
-    uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step
+    double cont_a, cont_b;   // continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u):  dlam -= dgdu_continuous(y)  (flags bit3)
+    uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step, bit3 continuous cost
     double* adj_dense;       // SA_QUAD: [S][8][D][Npad] = (lambda at the start of reverse step n, ka'[0..6]) per step
     unsigned long long* trace;   // optional [gridDim][3] = (smid, globaltimer at block start, at block end) or null
     Tsit5Tables tb;
@@ -209,6 +210,15 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, d
     }
 }
 
+// accumulate_cost! (src/derivative_wrappers.jl:1411-1442): with ka' = -dlam/dt the continuous cost adds +dgdu_continuous(y)
+template <int D, class Args>
+__device__ __forceinline__ void add_continuous(const Args& a, const double* y, double* ka) {
+    if (a.flags & 8u) {
+#pragma unroll
+        for (int j = 0; j < D; j++) ka[j] += fma(a.cont_a, y[j], a.cont_b);
+    }
+}
+
 template <int D, int COST, class Args>
 __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t stride, int64_t N, int64_t i, const double* y, double* lam) {
     if (COST == COST_EXPLICIT) {
@@ -273,6 +283,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < D; j++) ky[0][j] = -ky[0][j];
                 Fam::vjp_u(y, p, lam, kl[0]);
+                add_continuous<D>(a, y, kl[0]);
             }
             Fam::vjp_p(y, p, lam, dg);                 // mu' = -F'lam, reverse step: mu += h * sum b_j F'(y_j) lam_j
 #pragma unroll
@@ -281,7 +292,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             tsit5_stage<D, S_>(tb, y, ky, ys); tsit5_stage<D, S_>(tb, lam, kl, ls);       \
             Fam::f(ys, p, ky[S_]);                                                        \
             _Pragma("unroll") for (int j = 0; j < D; j++) ky[S_][j] = -ky[S_][j];         \
-            Fam::vjp_u(ys, p, ls, kl[S_]);                                                \
+            Fam::vjp_u(ys, p, ls, kl[S_]); add_continuous<D>(a, ys, kl[S_]);              \
             if (S_ < 6) { Fam::vjp_p(ys, p, ls, dg);                                      \
                 _Pragma("unroll") for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][S_ < 6 ? S_ : 0], dg[q], mu[q]); }
             B200_BS_STAGE(1) B200_BS_STAGE(2) B200_BS_STAGE(3) B200_BS_STAGE(4) B200_BS_STAGE(5) B200_BS_STAGE(6)
@@ -339,6 +350,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (ks >= 0) add_cotangent<D, COST>(a, ks, stride, N, i, uhi, lam);
             Fam::f(uhi, p, kf[6]);
             Fam::vjp_u(uhi, p, lam, ka[0]);    // y(T) = u_S
+            add_continuous<D>(a, uhi, ka[0]);
         }
         for (int n = a.S - 1; n >= 0; n--) {
             const int c = a.S - 1 - n, k = c / CH, jj = c % CH, st = k % NST;
@@ -373,7 +385,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #define B200_ADJ_STAGE(S_, YEXPR)                                                          \
             tsit5_stage<D, S_>(tb, lam, ka, ls);                                           \
             YEXPR;                                                                         \
-            Fam::vjp_u(y, p, ls, ka[S_]);                                                  \
+            Fam::vjp_u(y, p, ls, ka[S_]); add_continuous<D>(a, y, ka[S_]);                 \
             if (SA == SA_INTERP && S_ < 6) { Fam::vjp_p(y, p, ls, dg);                     \
                 _Pragma("unroll") for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][S_ < 6 ? S_ : 0], dg[q], mu[q]); }
             B200_ADJ_STAGE(1, tsit5_dense<D>(ulo, kf, tb.hBst[0], y))
@@ -420,6 +432,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (ks >= 0 && !((a.flags & 1u) && n == 0)) {
                 add_cotangent<D, COST>(a, ks, stride, N, i, ulo, lam);
                 Fam::vjp_u(ulo, p, lam, ka[0]);
+                add_continuous<D>(a, ulo, ka[0]);
             }
 #pragma unroll
             for (int j = 0; j < D; j++) uhi[j] = ulo[j];

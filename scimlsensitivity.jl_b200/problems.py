@@ -129,6 +129,15 @@ class AffineCost:
     b: float = 1.0
 
 
+@dataclass(frozen=True)
+class QuadraticRunningCost:
+    """Continuous cost g(u, p, t) = a/2 |u|^2 + b sum(u): dgdu_continuous = a u + b, dgdp_continuous = 0, evaluated
+    in-kernel at every adjoint stage (accumulate_cost!, src/derivative_wrappers.jl:1411-1442;
+    test/Core7/mixed_costs.jl:19-110).  Loss contribution = integral of g over the time span."""
+    a: float = 0.0
+    b: float = 0.0
+
+
 def saveat_to_times(saveat, tspan):
     """saveat::Number -> t0:saveat:t1 with the end point appended (src/concrete_solve.jl:718-725, 2827-2831);
     arrays are sorted (:752-756)."""

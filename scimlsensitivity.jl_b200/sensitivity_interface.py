@@ -8,7 +8,7 @@ src/sensitivity_interface.jl:503-507).  For an ensemble `du0` is [d, N]; with pe
 """
 import numpy as np
 
-from .problems import AdjointSensitivityParameterCompatibilityError, AffineCost
+from .problems import AdjointSensitivityParameterCompatibilityError, AffineCost, QuadraticRunningCost
 from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, InterpolatingAdjoint,
                                      QuadratureAdjoint, sensealg_name)
 
@@ -43,11 +43,13 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
     if callback is not None or getattr(sol.prob.prob if hasattr(sol.prob, "prob") else sol.prob, "callback", None) is not None:
         raise NotImplementedError("callbacks/events are not supported on the B200 path (SURVEY.md App. E): "
                                   "delegate to the reference implementation")
-    if dgdu_continuous is not None or dgdp_continuous is not None or g is not None:
-        raise NotImplementedError("continuous cost functionals are not built on the B200 path yet")
+    if dgdp_continuous is not None or g is not None:
+        raise NotImplementedError("dgdp_continuous / g are not built on the B200 path (named cost families only)")
+    if dgdu_continuous is not None and not isinstance(dgdu_continuous, QuadraticRunningCost):
+        raise NotImplementedError("dgdu_continuous must be a QuadraticRunningCost on the B200 path")
     if dgdp_discrete is not None:
         raise NotImplementedError("dgdp_discrete is not built on the B200 path yet")
-    if dgdu_discrete is None:
+    if dgdu_discrete is None and dgdu_continuous is None:
         # src/interpolating_adjoint.jl:321-326
         raise ValueError("Either `dgdu_discrete`, `dgdp_discrete`, `dgdu_continuous`, `dgdp_continuous`, or `g` "
                          "must be specified.")
@@ -56,6 +58,8 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
     if eng is None:
         raise RuntimeError("solution carries no live device handle")
     ts = sol.t if t is None else np.asarray(t, dtype=np.float64)
+    if dgdu_discrete is None:
+        ts = np.zeros(0)                                   # continuous cost only: no jumps (discrete = false in the reference)
     name = sensealg_name(inner)
     # Backsolve through the direct interface: checkpoints default to sol.t = every forward step
     # (src/sensitivity_interface.jl:433); pass `checkpoints=ts` for the rrule behaviour.
@@ -65,7 +69,12 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
         checkpointing = inner.checkpointing
         every = checkpoints is None
     cost = dgdu_discrete if isinstance(dgdu_discrete, AffineCost) else None
+    if dgdu_discrete is None:
+        cost = AffineCost(0.0, 0.0)
     eng.set_reverse(name, cost=cost, no_start=no_start, checkpointing=checkpointing, ckpt_every_step=every, t=ts)
+    if dgdu_continuous is not None or getattr(eng, "_cont_on", False):
+        eng.handle.set_continuous_cost(dgdu_continuous is not None, getattr(dgdu_continuous, "a", 0.0), getattr(dgdu_continuous, "b", 0.0))
+        eng._cont_on = dgdu_continuous is not None
     # adjoint solve tolerances are keywords of adjoint_sensitivities (src/sensitivity_interface.jl:432; used by the adaptive
     # steppers only); quadgk tolerances come from the sensealg (src/quadrature_adjoint.jl:517)
     is_quad = isinstance(inner, QuadratureAdjoint)

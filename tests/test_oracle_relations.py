@@ -277,3 +277,22 @@ def test_sde_lv_euler_heun_matches_differentiation_through_discrete_solver():
     r = O.gradient(cfg, saveat, u0, p, dW=dW)
     g = _fd_grad(lambda q: O.loss(cfg, saveat, u0, q, dW=dW).sum(), p, h=1e-5)
     assert np.allclose(r["dp"], g, rtol=1e-4)
+
+
+def test_continuous_cost_all_sensealgs_match_differentiation_of_the_integral():
+    """a10 accumulate_cost! (src/derivative_wrappers.jl:1411-1442): continuous cost g = a/2|u|^2 + b sum(u) mixed with a
+    discrete cost; Backsolve / Interpolating / Quadrature (and Gauss) agree with the derivative of
+    sum_k l(u(t_k)) + int g dt through the solver (test/Core7/mixed_costs.jl:19-110, test/Core7/adjoint_param.jl:17-48)."""
+    saveat = np.linspace(0, 2, 5)
+    res = {}
+    for sa in SENSEALGS:
+        cfg = O.make_cfg("lv", sa, "tsit5_fixed", 1, saveat, 0.0, 2.0, dt=0.002, cost=("affine", 0.0, 1.0), cont_cost=(1.0, -0.3),
+                         quad_abstol=1e-13, quad_reltol=1e-13, ckpt_every_step=True)
+        res[sa] = O.gradient(cfg, saveat, LV_U0, LV_P)
+    for sa in SENSEALGS[1:]:
+        assert np.allclose(res[sa]["dp"], res["interpolating"]["dp"], rtol=1e-9)
+        assert np.allclose(res[sa]["du0"], res["interpolating"]["du0"], rtol=1e-9)
+    cfg = O.make_cfg("lv", "interpolating", "tsit5_fixed", 1, saveat, 0.0, 2.0, dt=0.002, cost=("affine", 0.0, 1.0), cont_cost=(1.0, -0.3))
+    gp = _fd_grad(lambda p: O.loss(cfg, saveat, LV_U0, p)[0], LV_P)
+    gu = _fd_grad(lambda u: O.loss(cfg, saveat, u, LV_P)[0], LV_U0)
+    assert np.allclose(res["interpolating"]["dp"], gp, rtol=1e-8) and np.allclose(res["interpolating"]["du0"], gu, rtol=1e-8)
