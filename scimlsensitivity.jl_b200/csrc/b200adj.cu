@@ -146,11 +146,15 @@ int launch_fwd(Handle* h, const OdeFwdArgs& a) {
 template <class Fam, int SA, bool SHARED_P, int COST>
 int launch_rev_b(Handle* h, const OdeRevArgs& a) {
     const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D>(h->block);
-    if (smem > 40 * 1024) {      // static smem (barriers, reduction scratch) rides on top of the dynamic tile
-        cudaError_t e = cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return B200ADJ_ERR_CUDA;
+    // the continuous-cost variant is a separate instantiation: the headline kernel keeps its register budget
+    if (h->cont_on) {
+        if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true><<<h->grid, h->block, smem, h->stream>>>(a);
+    } else {
+        // static smem (barriers, reduction scratch) rides on top of the dynamic tile
+        if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false><<<h->grid, h->block, smem, h->stream>>>(a);
     }
-    tsit5_reverse_kernel<Fam, SA, SHARED_P, COST><<<h->grid, h->block, smem, h->stream>>>(a);
     h->launches++;
     return 0;
 }

@@ -211,9 +211,9 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, d
 }
 
 // accumulate_cost! (src/derivative_wrappers.jl:1411-1442): with ka' = -dlam/dt the continuous cost adds +dgdu_continuous(y)
-template <int D, class Args>
+template <int D, bool CONT, class Args>
 __device__ __forceinline__ void add_continuous(const Args& a, const double* y, double* ka) {
-    if (a.flags & 8u) {
+    if (CONT) {
 #pragma unroll
         for (int j = 0; j < D; j++) ka[j] += fma(a.cont_a, y[j], a.cont_b);
     }
@@ -243,7 +243,7 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
 #endif
 constexpr int REV_CH = REV_CH_DEF, REV_NST = 2;     // TMA pipeline: steps per stage (= block barrier period), stages in flight
 template <int D> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(double); }
-template <class Fam, int SA, bool SHARED_P, int COST>
+template <class Fam, int SA, bool SHARED_P, int COST, bool CONT>
 __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
     const int BLOCK = (int)blockDim.x;
@@ -283,7 +283,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #pragma unroll
                 for (int j = 0; j < D; j++) ky[0][j] = -ky[0][j];
                 Fam::vjp_u(y, p, lam, kl[0]);
-                add_continuous<D>(a, y, kl[0]);
+                add_continuous<D, CONT>(a, y, kl[0]);
             }
             Fam::vjp_p(y, p, lam, dg);                 // mu' = -F'lam, reverse step: mu += h * sum b_j F'(y_j) lam_j
 #pragma unroll
@@ -292,7 +292,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             tsit5_stage<D, S_>(tb, y, ky, ys); tsit5_stage<D, S_>(tb, lam, kl, ls);       \
             Fam::f(ys, p, ky[S_]);                                                        \
             _Pragma("unroll") for (int j = 0; j < D; j++) ky[S_][j] = -ky[S_][j];         \
-            Fam::vjp_u(ys, p, ls, kl[S_]); add_continuous<D>(a, ys, kl[S_]);              \
+            Fam::vjp_u(ys, p, ls, kl[S_]); add_continuous<D, CONT>(a, ys, kl[S_]);              \
             if (S_ < 6) { Fam::vjp_p(ys, p, ls, dg);                                      \
                 _Pragma("unroll") for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][S_ < 6 ? S_ : 0], dg[q], mu[q]); }
             B200_BS_STAGE(1) B200_BS_STAGE(2) B200_BS_STAGE(3) B200_BS_STAGE(4) B200_BS_STAGE(5) B200_BS_STAGE(6)
@@ -350,7 +350,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (ks >= 0) add_cotangent<D, COST>(a, ks, stride, N, i, uhi, lam);
             Fam::f(uhi, p, kf[6]);
             Fam::vjp_u(uhi, p, lam, ka[0]);    // y(T) = u_S
-            add_continuous<D>(a, uhi, ka[0]);
+            add_continuous<D, CONT>(a, uhi, ka[0]);
         }
         for (int n = a.S - 1; n >= 0; n--) {
             const int c = a.S - 1 - n, k = c / CH, jj = c % CH, st = k % NST;
@@ -385,7 +385,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #define B200_ADJ_STAGE(S_, YEXPR)                                                          \
             tsit5_stage<D, S_>(tb, lam, ka, ls);                                           \
             YEXPR;                                                                         \
-            Fam::vjp_u(y, p, ls, ka[S_]); add_continuous<D>(a, y, ka[S_]);                 \
+            Fam::vjp_u(y, p, ls, ka[S_]); add_continuous<D, CONT>(a, y, ka[S_]);                 \
             if (SA == SA_INTERP && S_ < 6) { Fam::vjp_p(y, p, ls, dg);                     \
                 _Pragma("unroll") for (int q = 0; q < P; q++) mu[q] = fma(tb.hA[6][S_ < 6 ? S_ : 0], dg[q], mu[q]); }
             B200_ADJ_STAGE(1, tsit5_dense<D>(ulo, kf, tb.hBst[0], y))
@@ -432,7 +432,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (ks >= 0 && !((a.flags & 1u) && n == 0)) {
                 add_cotangent<D, COST>(a, ks, stride, N, i, ulo, lam);
                 Fam::vjp_u(ulo, p, lam, ka[0]);
-                add_continuous<D>(a, ulo, ka[0]);
+                add_continuous<D, CONT>(a, ulo, ka[0]);
             }
 #pragma unroll
             for (int j = 0; j < D; j++) uhi[j] = ulo[j];

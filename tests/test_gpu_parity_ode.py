@@ -153,9 +153,9 @@ def test_full_size_properties():
     import math
     tot = np.array([math.fsum(dpm[q]) for q in range(3)])
     assert _rel(dp, tot) < 1e-12
-    assert np.array_equal(du0m.cpu().numpy(), du0)
+    assert _rel(du0m.cpu().numpy(), du0) < 1e-12      # different template instantiation: same arithmetic, FMA contraction may differ
     # (3) explicit cotangent path == in-kernel affine cost
     eng.set_reverse("gauss", cost=None)
     du0e, dpe = eng.reverse(saved - 2.0)
-    assert np.array_equal(du0e.cpu().numpy(), du0) and np.array_equal(dpe.cpu().numpy(), dp)
+    assert _rel(du0e.cpu().numpy(), du0) < 1e-12 and _rel(dpe.cpu().numpy(), dp) < 1e-12
     eng.close(); eng2.close()
