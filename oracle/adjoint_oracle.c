@@ -938,7 +938,13 @@ static void sde_adj_diffusion_apply(const family_t* F, const double* p, double t
 static int adjoint_sde_member(const oracle_cfg* cfg, const family_t* F, const double* p, const double* us, const double* dW, int S,
                               const double* ts, const double* dL, double* du0, double* dp) {
     const int d = F->d, P = F->P, L = 2 * d + P, K = cfg->K;
-    const int ito = (cfg->stepper == ST_EM);           /* backsolve_adjoint.jl:327-345 */
+    /* InterpolatingAdjoint (src/interpolating_adjoint.jl:453-613): z = [lam; mu], y(t) = sol(t) from the saved forward
+     * solution (the reverse solve steps on the forward grid, src/sensitivity_interface.jl:484-486, so y is the stored
+     * u_n), drift = sol.prob.f WITHOUT the Ito transformation (:525-533).  BacksolveAdjoint: z = [lam; mu; y], Ito ->
+     * transformed drift (backsolve_adjoint.jl:327-345).  Both share this loop; for Interpolating the y slots are
+     * overwritten from the forward solution before every drift/diffusion evaluation. */
+    const int interp = (cfg->sensealg == SA_INTERPOLATING);
+    const int ito = (cfg->stepper == ST_EM) && !interp;
     double h = cfg->dt;
     double* z = (double*)calloc(L, sizeof(double)), *a = (double*)malloc(sizeof(double) * L), *b = (double*)malloc(sizeof(double) * L);
     double* zb = (double*)malloc(sizeof(double) * L), *a2 = (double*)malloc(sizeof(double) * L), *b2 = (double*)malloc(sizeof(double) * L);
@@ -949,7 +955,7 @@ static int adjoint_sde_member(const oracle_cfg* cfg, const family_t* F, const do
         double t = cfg->t0 + n * h; if (n == S) t = cfg->t1;
         /* callbacks at grid point n: checkpoint reset (y <- sol(t)) then loss jump */
         int is_save = (cur >= 0 && fabs(ts[cur] - t) <= 1e-9 * fmax(1.0, fabs(t)));
-        if (cfg->checkpointing && (cfg->backsolve_ckpt_every_step || is_save)) memcpy(z + d + P, us + (size_t)n * d, sizeof(double) * d);
+        if (interp || (cfg->checkpointing && (cfg->backsolve_ckpt_every_step || is_save))) memcpy(z + d + P, us + (size_t)n * d, sizeof(double) * d);
         if (is_save) {
             cost_grad(cfg, dL ? dL + (size_t)cur * d : NULL, z + d + P, gu);
             for (int i = 0; i < d; i++) z[i] += gu[i];
@@ -963,6 +969,7 @@ static int adjoint_sde_member(const oracle_cfg* cfg, const family_t* F, const do
         if (cfg->stepper == ST_EM) for (int i = 0; i < L; i++) z[i] = z[i] - h * a[i] + b[i];
         else {
             for (int i = 0; i < L; i++) zb[i] = z[i] - h * a[i] + b[i];
+            if (interp) memcpy(zb + d + P, us + (size_t)(n - 1) * d, sizeof(double) * d);      /* y(t_{n-1}) = sol(t_{n-1}) */
             sde_adj_drift(F, p, ito, t - h, zb, a2);
             sde_adj_diffusion_apply(F, p, t - h, zb, dWr, b2, dgm);
             for (int i = 0; i < L; i++) z[i] = z[i] - 0.5 * h * (a[i] + a2[i]) + 0.5 * (b[i] + b2[i]);
@@ -998,7 +1005,7 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
     family_t F; int rc = family_init(&F, cfg); if (rc) return rc;
     const int d = F.d, P = F.P, K = cfg->K; const int64_t N = cfg->N;
     int S = 0;
-    if (is_sde(cfg)) { S = (int)llround((cfg->t1 - cfg->t0) / cfg->dt); if (cfg->sensealg != SA_BACKSOLVE) return -6; }
+    if (is_sde(cfg)) { S = (int)llround((cfg->t1 - cfg->t0) / cfg->dt); if (cfg->sensealg != SA_BACKSOLVE && cfg->sensealg != SA_INTERPOLATING) return -6; }
     int err = 0;
     double* dp_members = (double*)calloc((size_t)N * P, sizeof(double));
 #ifdef _OPENMP

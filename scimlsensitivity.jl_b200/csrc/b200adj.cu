@@ -215,18 +215,18 @@ int launch_sde_fwd_f(Handle* h, const SdeFwdArgs& a) {
     h->launches++;
     return 0;
 }
-template <class Fam, bool EH, bool SHARED_P, int COST>
+template <class Fam, bool EH, bool SHARED_P, int COST, bool INTERP>
 int launch_sde_rev_b(Handle* h, const SdeRevArgs& a) {
-    sde_backsolve_kernel<Fam, EH, SHARED_P, COST><<<h->grid, h->block, 0, h->stream>>>(a);
+    sde_backsolve_kernel<Fam, EH, SHARED_P, COST, INTERP><<<h->grid, h->block, 0, h->stream>>>(a);
     h->launches++;
     return 0;
 }
-template <class Fam, bool EH>
+template <class Fam, bool EH, bool INTERP>
 int launch_sde_rev_f(Handle* h, const SdeRevArgs& a) {
     const bool sp = h->cfg.shared_p;
     const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (sp) return ex ? launch_sde_rev_b<Fam, EH, true, COST_EXPLICIT>(h, a) : launch_sde_rev_b<Fam, EH, true, COST_AFFINE>(h, a);
-    return ex ? launch_sde_rev_b<Fam, EH, false, COST_EXPLICIT>(h, a) : launch_sde_rev_b<Fam, EH, false, COST_AFFINE>(h, a);
+    if (sp) return ex ? launch_sde_rev_b<Fam, EH, true, COST_EXPLICIT, INTERP>(h, a) : launch_sde_rev_b<Fam, EH, true, COST_AFFINE, INTERP>(h, a);
+    return ex ? launch_sde_rev_b<Fam, EH, false, COST_EXPLICIT, INTERP>(h, a) : launch_sde_rev_b<Fam, EH, false, COST_AFFINE, INTERP>(h, a);
 }
 
 template <class Fam>
@@ -427,7 +427,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     const bool sde = is_sde(*cfg);
     if (sde) {
         if (m == 0) { g_create_error = "SDE stepper needs an SDE family"; return B200ADJ_ERR_INVALID; }
-        if (cfg->sensealg != B200ADJ_SA_BACKSOLVE) { g_create_error = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (cfg->sensealg != B200ADJ_SA_BACKSOLVE && cfg->sensealg != B200ADJ_SA_INTERPOLATING) { g_create_error = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     } else {
         if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
         if (cfg->sensealg < 0 || cfg->sensealg > 3) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
@@ -591,7 +591,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     Handle* h = (Handle*)handle;
     b200adj_cfg& c = h->cfg;
     if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
-    if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE) { h->err = "SDE: only BacksolveAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
@@ -840,10 +840,20 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         a.seed = c.seed; a.traj_offset = c.traj_offset;
         a.noise = h->noise_valid ? h->d_noise : nullptr;
         const bool eh = c.stepper == B200ADJ_ST_EULER_HEUN;
-        switch (c.rhs_family) {
-        case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_rev_f<SdeLotkaVolterra<false>, true>(h, a) : launch_sde_rev_f<SdeLotkaVolterra<true>, false>(h, a); break;
-        case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_rev_f<SdeLinear2<false>, true>(h, a) : launch_sde_rev_f<SdeLinear2<true>, false>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        const bool interp = c.sensealg == B200ADJ_SA_INTERPOLATING;
+        // Backsolve + Ito solver (EM): transformed drift; InterpolatingAdjoint: the problem's own drift
+        if (interp) {
+            switch (c.rhs_family) {
+            case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_rev_f<SdeLotkaVolterra<false>, true, true>(h, a) : launch_sde_rev_f<SdeLotkaVolterra<false>, false, true>(h, a); break;
+            case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_rev_f<SdeLinear2<false>, true, true>(h, a) : launch_sde_rev_f<SdeLinear2<false>, false, true>(h, a); break;
+            default: rc = B200ADJ_ERR_UNSUPPORTED;
+            }
+        } else {
+            switch (c.rhs_family) {
+            case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_rev_f<SdeLotkaVolterra<false>, true, false>(h, a) : launch_sde_rev_f<SdeLotkaVolterra<true>, false, false>(h, a); break;
+            case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_rev_f<SdeLinear2<false>, true, false>(h, a) : launch_sde_rev_f<SdeLinear2<true>, false, false>(h, a); break;
+            default: rc = B200ADJ_ERR_UNSUPPORTED;
+            }
         }
     }
     if (rc) { h->err = "reverse dispatch failed (sensealg/family not built)"; return rc; }

@@ -141,7 +141,11 @@ __device__ __forceinline__ void sde_adj_terms(const double* lam, const double* y
     for (int q = 0; q < P; q++) { am[q] = -am[q]; bm[q] = -bm[q]; }
 }
 
-template <class Fam, bool EULER_HEUN, bool SHARED_P, int COST>
+// INTERP = false: BacksolveAdjoint, z = [lam; mu; y] (y integrated backwards, reset at checkpoints).
+// INTERP = true : InterpolatingAdjoint (src/interpolating_adjoint.jl:453-613), z = [lam; mu]; y(t) is read from the saved
+//                 forward solution at every grid point (the reverse solve steps on the forward grid) and the drift is the
+//                 problem's f without the Ito transformation (the caller instantiates Fam with ITO = false).
+template <class Fam, bool EULER_HEUN, bool SHARED_P, int COST, bool INTERP>
 __global__ void __launch_bounds__(512) sde_backsolve_kernel(SdeRevArgs a) {
     const int BLOCK = (int)blockDim.x;
     constexpr int D = Fam::D, P = Fam::P, M = Fam::M;
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(512) sde_backsolve_kernel(SdeRevArgs a) {
     for (int n = a.S; n >= 0; n--) {
         // callbacks at grid point n: checkpoint reset, then the loss jump
         const int ks = a.save_of_step[n];
-        if (ckpt_on && (every || ks >= 0)) load_state<D>(a.ckpt + (int64_t)n * stride, N, i, y);
+        if (INTERP || (ckpt_on && (every || ks >= 0))) load_state<D>(a.ckpt + (int64_t)n * stride, N, i, y);
         if (ks >= 0) {
             if (COST == COST_EXPLICIT) {
 #pragma unroll
@@ -191,6 +195,7 @@ __global__ void __launch_bounds__(512) sde_backsolve_kernel(SdeRevArgs a) {
             double l2[D], y2[D], al2[D], am2[P], ay2[D], bl2[D], bm2[P], by2[D];
 #pragma unroll
             for (int j = 0; j < D; j++) { l2[j] = lam[j] - h * al[j] + bl[j]; y2[j] = y[j] - h * ay[j] + by[j]; }
+            if (INTERP) load_state<D>(a.ckpt + (int64_t)(n - 1) * stride, N, i, y2);      // y(t_{n-1}) = sol(t_{n-1})
             sde_adj_terms<Fam, D, P>(l2, y2, p, w, al2, am2, ay2, bl2, bm2, by2);
 #pragma unroll
             for (int j = 0; j < D; j++) {

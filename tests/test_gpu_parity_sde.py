@@ -48,6 +48,34 @@ def test_sde_backsolve_parity(family, p, stepper, mode, shared_p):
     eng.close()
 
 
+@pytest.mark.parametrize("stepper", ["em", "euler_heun"])
+@pytest.mark.parametrize("shared_p", [True, False])
+def test_sde_interpolating_parity(stepper, shared_p):
+    """SDEAdjointProblem for InterpolatingAdjoint (src/interpolating_adjoint.jl:453-613): z = [lam; mu], y from the saved
+    forward solution, untransformed drift; same Wiener increments on both sides."""
+    N, T, dt = 130, 1.0, 0.01
+    saveat = np.linspace(0.0, T, 21)
+    rng = np.random.default_rng(8)
+    u0 = np.ones((2, N)) * np.exp(0.05 * rng.standard_normal((2, N)))
+    p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
+    if not shared_p:
+        p = p[:, None] * np.exp(0.02 * rng.standard_normal((6, N)))
+    eng = b.DeviceEnsemble("sde_lv", "interpolating", stepper, N, saveat, (0.0, T), dt, shared_p=shared_p, cost=b.AffineCost(1.0, -1.0), seed=3)
+    saved, _ = eng.forward(u0, p)
+    dW = eng.noise()
+    du0, dp = eng.reverse()
+    cfg = O.make_cfg("sde_lv", "interpolating", stepper, N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -1.0), shared_p=shared_p)
+    ref = O.gradient(cfg, saveat, u0, p, dW=dW)
+    assert _rel(du0, ref["du0"]) < 1e-9 and _rel(dp, ref["dp"]) < 1e-9
+    # retarget the same forward pass to BacksolveAdjoint: a different algorithm (transformed drift for EM), different numbers
+    eng.set_reverse("backsolve", cost=b.AffineCost(1.0, -1.0))
+    du0b, dpb = eng.reverse()
+    cfgb = O.make_cfg("sde_lv", "backsolve", stepper, N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -1.0), shared_p=shared_p)
+    refb = O.gradient(cfgb, saveat, u0, p, dW=dW)
+    assert _rel(dpb, refb["dp"]) < 1e-9
+    eng.close()
+
+
 def test_sde_noise_is_shard_independent():
     """Philox streams are keyed by the GLOBAL member index: two shards reproduce the unsharded increments."""
     N, T, dt = 128, 0.1, 0.01
