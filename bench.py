@@ -246,7 +246,7 @@ def run_ours(args):
     # ---------------- end-to-end arm (`e2e`): public API, host buffers ----------------
     u0_pin = torch.tensor(u0_h).pin_memory(); p_pin = torch.tensor(p_h).pin_memory()
     prob = b.EnsembleProblem(b.ODEProblem(W["family"], u0_h[:, 0], (0.0, W["T"]), p_pin.numpy()), u0s=u0_pin.numpy())
-    ealg = b.EnsembleB200(device=local, buffers_on_device=False, reuse_handle=True, presharded=True)   # each rank owns its members
+    ealg = b.EnsembleB200(device=local, buffers_on_device=False, reuse_handle=True, presharded=True, pin_outputs=True)   # each rank owns its members
     alg = b.Tsit5(dt=W["dt"])
 
     def step_e2e():

@@ -130,7 +130,7 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
                              seed=getattr(prob, "seed", 0), traj_offset=lo, block_threads=block, stored_noise=stored,
                              quad_abstol=getattr(inner, "abstol", 1e-6), quad_reltol=getattr(inner, "reltol", 1e-3),
                              abstol=kwargs.get("abstol", 1e-6), reltol=kwargs.get("reltol", 1e-3),
-                             max_steps=kwargs.get("maxiters", 0))
+                             max_steps=kwargs.get("maxiters", 0), pin_outputs=ensemblealg.pin_outputs)
         if ensemblealg.reuse_handle:
             _HANDLE_CACHE[key] = eng
     dW = getattr(prob, "noise", None)

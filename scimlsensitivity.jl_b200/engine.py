@@ -19,7 +19,7 @@ class DeviceEnsemble:
     def __init__(self, family, sensealg, stepper, N, saveat, tspan, dt, *, shared_p=True, cost=None,
                  on_device=False, device=0, no_start=False, checkpointing=True, ckpt_every_step=False,
                  stored_noise=False, seed=0, traj_offset=0, block_threads=0, abstol=1e-6, reltol=1e-3,
-                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False, max_steps=0):
+                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False, max_steps=0, pin_outputs=False):
         d, P, m = FAMILIES[family]
         cfg = _lib.Cfg()
         cfg.rhs_family, cfg.sensealg, cfg.stepper, cfg.dtype = _lib.FAM[family], _lib.SA[sensealg], _lib.ST[stepper], _lib.DTYPE[dtype]
@@ -55,6 +55,7 @@ class DeviceEnsemble:
         self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
         self.handle = _lib.Handle(cfg, self.saveat)
         self._keep = []
+        self.pin_outputs, self._pinned = bool(pin_outputs), {}
         if self.on_device:
             # device-pointer mode is asynchronous: run on torch's current stream so tensor producers/consumers order
             # correctly with the kernels (host-buffer mode synchronises inside the C ABI instead)
@@ -66,7 +67,16 @@ class DeviceEnsemble:
             import torch
             td = torch.int32 if dtype == "i32" else (torch.float64 if self.dtype == "f64" else torch.float32)
             return torch.empty(shape, dtype=td, device=f"cuda:{self.device}")
-        return np.empty(shape, dtype=np.int32 if dtype == "i32" else self.np_dtype)
+        npdt = np.int32 if dtype == "i32" else self.np_dtype
+        if self.pin_outputs:
+            # page-locked result buffers, allocated once per shape and REUSED by later calls on this handle (true async D2H
+            # instead of a staged pageable copy); callers that keep results across calls must copy them
+            key = (tuple(shape), np.dtype(npdt).str)
+            if key not in self._pinned:
+                import torch
+                self._pinned[key] = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(npdt).name), pin_memory=True)
+            return self._pinned[key].numpy()
+        return np.empty(shape, dtype=npdt)
 
     def _prep(self, x, shape):
         if self.on_device:

@@ -100,6 +100,7 @@ class EnsembleB200:
     buffers_on_device: Optional[bool] = None   # None: infer from the input arrays
     presharded: bool = False                   # True: the arrays passed in are already THIS rank's shard (no slicing; dp is
                                                # still all-reduced, Philox member offset = rank * local N)
+    pin_outputs: bool = False                  # host-buffer mode: results land in page-locked buffers owned (and reused) by the handle
     reuse_handle: bool = False                 # keep ONE device handle per configuration across solve() calls (the
                                                # previous solution's checkpoints are overwritten by the next solve)
 
