@@ -43,9 +43,21 @@ def make_inputs(N, offset=0):
 def host_cores():
     """cores this process may actually run on (the box reports 128 CPUs but the cgroup/affinity mask is smaller)"""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:                                                     # cgroup v2 CPU quota (the GPU boxes show 128 CPUs but grant fewer)
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(np.ceil(int(quota) / int(period)))))
+    except Exception:
+        try:                                                 # cgroup v1
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = max(1, min(n, int(np.ceil(q / per))))
+        except Exception:
+            pass
+    return n
 
 
 def ncu_traffic():
