@@ -71,7 +71,7 @@ def best_threads():
         cap = host_cores()
         cands = sorted({c for c in (4, 8, 16, 32, 64, 128, cap) if c <= cap}) or [1]
         cpu_oracle_rate(256, cands[0])                        # load the library
-        rates = {c: cpu_oracle_rate(max(1024, 16 * c), c)[0] for c in cands}
+        rates = {c: cpu_oracle_rate(max(1024, 16 * c), c, repeats=2)[0] for c in cands}
         _BEST_THREADS = max(rates, key=rates.get)
         sys.stderr.write(f"[bench] oracle threads probe: {rates} -> {_BEST_THREADS}\n")
     return _BEST_THREADS
