@@ -1,0 +1,95 @@
+"""Edge cases of the reference's seam on the device: a single member, a single save time at t1
+(`only_end`, vector cotangent), no save times at all with a continuous cost, save_start / save_end dropping the end points,
+many tiny steps, a ragged ensemble just past a block boundary, repeated forward/reverse on one handle, matrix-shaped u0."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+import scimlsensitivity_jl_b200 as b
+from oracle import oracle as O
+
+
+def _rel(a, ref):
+    return np.abs(np.asarray(a) - ref).max() / max(np.abs(ref).max(), 1e-300)
+
+
+P_LV = np.array([1.5, 1.0, 3.0, 1.0])
+
+
+def test_single_member_and_only_end_vector_cotangent():
+    """only_end: one output at t1, Delta may be a vector (src/concrete_solve.jl:716, 783-814)."""
+    u0 = np.array([[1.0], [1.0]])
+    prob = b.ODEProblem("lv", u0[:, 0], (0.0, 3.0), P_LV)
+    out, pullback = b._concrete_solve_adjoint(prob, b.Tsit5(dt=0.01), b.B200Adjoint(b.InterpolatingAdjoint()), u0, P_LV, None,
+                                              saveat=[3.0], save_start=False)
+    assert out.u.shape == (1, 2, 1)
+    tang = pullback(np.ones((2, 1)))                               # vector-shaped cotangent for the single output
+    cfg = O.make_cfg("lv", "interpolating", "tsit5_fixed", 1, [3.0], 0.0, 3.0, dt=0.01, cost=("affine", 0.0, 1.0))
+    ref = O.gradient(cfg, [3.0], u0, P_LV)
+    assert _rel(tang[3], ref["du0"]) < 1e-9 and _rel(tang[4], ref["dp"]) < 1e-9
+
+
+def test_save_start_save_end_false_and_saveat_number():
+    N = 7
+    rng = np.random.default_rng(0)
+    u0 = np.exp(0.1 * rng.standard_normal((2, N)))
+    prob = b.ODEProblem("lv", u0[:, 0], (0.0, 1.0), P_LV)
+    out, pullback = b._concrete_solve_adjoint(prob, b.Tsit5(dt=0.01), b.B200Adjoint(b.GaussAdjoint()), u0, P_LV, None,
+                                              saveat=0.25, save_start=False, save_end=False)
+    assert np.allclose(out.t, [0.25, 0.5, 0.75]) and out.u.shape == (3, 2, N)
+    tang = pullback(2.0 * out.u)
+    cfg = O.make_cfg("lv", "gauss", "tsit5_fixed", N, out.t, 0.0, 1.0, dt=0.01, cost=("affine", 2.0, 0.0))
+    ref = O.gradient(cfg, out.t, u0, P_LV)
+    assert _rel(tang[3], ref["du0"]) < 1e-9 and _rel(tang[4], ref["dp"]) < 1e-9
+
+
+def test_ragged_block_boundaries_and_matrix_u0():
+    """N = 1, 31, 33, 149 (one past the SM count), 449 (one past the default block), with u0 given as d x N matrix."""
+    saveat = np.linspace(0.0, 1.0, 11)
+    for N in (1, 31, 33, 149, 449):
+        rng = np.random.default_rng(N)
+        u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N))
+        p = np.array([10.0, 28.0, 8.0 / 3.0])
+        eng = b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", N, saveat, (0.0, 1.0), 0.01, cost=b.AffineCost(1.0, -2.0))
+        eng.forward(u0, p)
+        du0, dp = eng.reverse()
+        cfg = O.make_cfg("lorenz", "gauss", "tsit5_fixed", N, saveat, 0.0, 1.0, dt=0.01, cost=("affine", 1.0, -2.0))
+        ref = O.gradient(cfg, saveat, u0, p, want_saved=False)
+        assert _rel(du0, ref["du0"]) < 1e-9 and _rel(dp, ref["dp"]) < 1e-9, N
+        eng.close()
+
+
+def test_many_small_steps_and_handle_reuse():
+    """S = 20000 steps (dt = 1e-4); the same handle serves several forward/reverse pairs with different inputs."""
+    N = 40
+    saveat = np.array([0.5, 1.0, 2.0])
+    eng = b.DeviceEnsemble("lv", "interpolating", "tsit5_fixed", N, saveat, (0.0, 2.0), 1e-4, cost=b.AffineCost(0.0, 1.0))
+    for seed in (0, 1):
+        rng = np.random.default_rng(seed)
+        u0 = np.exp(0.1 * rng.standard_normal((2, N)))
+        p = P_LV * (1.0 + 0.05 * seed)
+        saved, status = eng.forward(u0, p)
+        du0, dp = eng.reverse()
+        cfg = O.make_cfg("lv", "interpolating", "tsit5_fixed", N, saveat, 0.0, 2.0, dt=1e-4, cost=("affine", 0.0, 1.0))
+        ref = O.gradient(cfg, saveat, u0, p)
+        assert np.abs(saved - ref["saved"]).max() < 1e-10
+        assert _rel(du0, ref["du0"]) < 1e-8 and _rel(dp, ref["dp"]) < 1e-8
+    eng.close()
+
+
+def test_state_errors():
+    saveat = np.linspace(0.0, 1.0, 3)
+    eng = b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", 4, saveat, (0.0, 1.0), 0.01)
+    with pytest.raises(b.B200AdjError) as ei:                       # reverse before forward
+        eng.reverse(np.zeros((3, 2, 4)))
+    assert ei.value.code == -5
+    eng.forward(np.ones((2, 4)), P_LV)
+    with pytest.raises(b.B200AdjError) as ei:                       # explicit cost but no cotangent array
+        eng.handle.reverse(None, np.zeros((2, 4)), np.zeros(4))
+    assert ei.value.code == -1
+    eng.close()
+    with pytest.raises(b.B200AdjError):                             # bad block size
+        b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", 4, saveat, (0.0, 1.0), 0.01, block_threads=48)
+    with pytest.raises(b.B200AdjError):                             # descending save times
+        b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", 4, saveat[::-1].copy(), (0.0, 1.0), 0.01)
