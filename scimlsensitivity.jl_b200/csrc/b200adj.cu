@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 
 #include <string>
 #include <vector>
@@ -269,7 +270,8 @@ T5aArgs t5a_args(Handle* h) {
     a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.qidx = h->r_qidx; a.maxseg = h->maxseg;
     a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.dt0 = c.dt; a.abstol = c.abstol; a.reltol = c.reltol;
     a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
-    a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
+              ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
     const double A[7][6] = {
         {0},
         {0.161},
@@ -307,6 +309,7 @@ int launch_t5a_rev(Handle* h, const T5aArgs& a) {
     switch (h->cfg.sensealg) {
     case B200ADJ_SA_INTERPOLATING: return launch_t5a_rev_sa<Fam, SA_INTERP>(h, a);
     case B200ADJ_SA_GAUSS: return launch_t5a_rev_sa<Fam, SA_GAUSS>(h, a);
+    case B200ADJ_SA_BACKSOLVE: return launch_t5a_rev_sa<Fam, SA_BACKSOLVE>(h, a);
     case B200ADJ_SA_QUADRATURE: {
         int rc = launch_t5a_rev_sa<Fam, SA_QUAD>(h, a);
         if (rc) return rc;
@@ -434,8 +437,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
         if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (ros && cfg->sensealg == B200ADJ_SA_BACKSOLVE) { g_create_error = "adaptive steppers: Interpolating (Tsit5) / Gauss / Quadrature are built"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (ros && !t5a && cfg->sensealg == B200ADJ_SA_INTERPOLATING) { g_create_error = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (ros && !t5a && (cfg->sensealg == B200ADJ_SA_INTERPOLATING || cfg->sensealg == B200ADJ_SA_BACKSOLVE)) {
+            g_create_error = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     }
     if (ros) {
         // adaptive path: save times are arbitrary ascending points of [t0, t1] (tstops of the reverse solve)
@@ -558,7 +561,9 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     if (sde) CREATE_TRY(cudaMalloc(&h->d_noise, (size_t)S * m * N * e));
     if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC) {
         h->Ktot = (int64_t)6 * S * (int64_t)Npad;                              // Npad is a multiple of 32 => Ktot % 64 == 0
-        h->umma_ctas = nsm;
+        // several CTAs per SM (24.7 KB smem, 64 TMEM columns each): the single-stage load->MMA->wait loop of one CTA is
+        // latency-bound, co-resident CTAs overlap each other's phases
+        { const char* e_ = getenv("B200ADJ_UMMA_CTAS_PER_SM"); h->umma_ctas = nsm * (e_ ? atoi(e_) : 4); }
         CREATE_TRY(cudaMalloc(&h->d_tapeA, (size_t)64 * h->Ktot * 2));
         CREATE_TRY(cudaMalloc(&h->d_tapeB, (size_t)64 * h->Ktot * 2));
         CREATE_TRY(cudaMalloc(&h->d_umma_partials, (size_t)h->umma_ctas * 4096 * sizeof(float)));
@@ -595,8 +600,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
-        if (sensealg == B200ADJ_SA_BACKSOLVE || (sensealg == B200ADJ_SA_INTERPOLATING && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE)) {
-            h->err = "adaptive steppers: Interpolating (Tsit5) / Gauss / Quadrature are built"; return B200ADJ_ERR_UNSUPPORTED; }
+        if ((sensealg == B200ADJ_SA_BACKSOLVE || sensealg == B200ADJ_SA_INTERPOLATING) && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) {
+            h->err = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
         if (K >= 0) {
             for (int k = 0; k < K; k++)
                 if (t[k] < c.t0 || t[k] > c.t1 || (k > 0 && !(t[k] > t[k - 1]))) { h->err = "t must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }

@@ -164,10 +164,15 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
     if (a.status) a.status[i] = stat;
 }
 
-// reverse adjoint solve.  SA_INTERP: z = [lambda; mu] (L = D + P); SA_GAUSS / SA_QUAD: z = lambda (L = D)
+// reverse adjoint solve.  SA_INTERP: z = [lambda; mu] (L = D + P); SA_GAUSS / SA_QUAD: z = lambda (L = D);
+// SA_BACKSOLVE: z = [lambda; mu; y] (L = 2D + P), y integrated backwards and reset from the forward solution at the
+// checkpoints (every forward knot = sol.t, the direct-interface default, or the save times), which are tstops of the reverse
+// solve (src/backsolve_adjoint.jl:32-61, :523-546; src/sensitivity_interface.jl:433, :484-486; the reference's own
+// Lorenz check, test/Core3/adjoint.jl:1157-1241)
 template <class Fam, int SA, bool SHARED_P, int COST>
 __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant__ T5aArgs a) {
-    constexpr int D = Fam::D, P = Fam::P, L = (SA == SA_INTERP) ? D + P : D;
+    constexpr int D = Fam::D, P = Fam::P, L = (SA == SA_INTERP) ? D + P : (SA == SA_BACKSOLVE ? 2 * D + P : D);
+    constexpr int YO = (SA == SA_BACKSOLVE) ? D + P : 0;          // offset of y inside z (Backsolve)
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gi < a.N;
     const int64_t i = active ? gi : a.N - 1;
@@ -182,29 +187,61 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     // adjoint RHS: dlam = -J(y(t))' lam, dmu = -F(y(t))' lam  (right-continuous forward lookup)
     auto rhs = [&](double tt, const double* x, double* dx) {
         double y[D];
-        sol.eval(tt, true, y);
+        if (SA == SA_BACKSOLVE) {
+#pragma unroll
+            for (int j = 0; j < D; j++) y[j] = x[YO + j];          // y is part of the state
+        } else sol.eval(tt, true, y);
         Fam::vjp_u(y, p, x, dx);
 #pragma unroll
         for (int j = 0; j < D; j++) dx[j] = -dx[j];
-        if (SA == SA_INTERP) {
+        if (SA == SA_INTERP || SA == SA_BACKSOLVE) {
             double dg[P];
             Fam::vjp_p(y, p, x, dg);
 #pragma unroll
             for (int q = 0; q < P; q++) dx[D + q] = -dg[q];
         }
+        if (SA == SA_BACKSOLVE) Fam::f(y, p, dx + YO);            // dy/dt = f(y)
     };
     const double T = a.t1, t0 = a.t0;
     double t = T;
-    int cur = a.K - 1, nrev = 0;
+    int cur = a.K - 1, nrev = 0, ck = sol.n;
     bool fsal_ok = false, overflow = false;
+    const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
+    if (SA == SA_BACKSOLVE) {
+#pragma unroll
+        for (int j = 0; j < D; j++) z[YO + j] = a.fu[((int64_t)sol.n * D + j) * N + i];     // y(T) = sol.u[end]
+    }
+    // Backsolve checkpoint callback (runs before the loss jump, CallbackSet order): y <- sol(t) at a checkpoint
+    auto ckpt_if_at = [&](double tt) {
+        if (SA != SA_BACKSOLVE || !ckpt_on) return;
+        const double tol = EPS100 * fmax(fabs(tt), 1.0);
+        if (every) {
+            while (ck >= 0 && sol.T(ck) > tt + tol) ck--;
+            if (ck >= 0 && fabs(sol.T(ck) - tt) <= tol) {
+#pragma unroll
+                for (int j = 0; j < D; j++) z[YO + j] = a.fu[((int64_t)ck * D + j) * N + i];
+                fsal_ok = false;
+            }
+        } else if (cur >= 0 && fabs(a.saveat[cur] - tt) <= tol) {
+            double y[D];
+            sol.eval(a.saveat[cur], false, y);
+#pragma unroll
+            for (int j = 0; j < D; j++) z[YO + j] = y[j];
+            fsal_ok = false;
+        }
+    };
     auto jump_if_at = [&](double tt) {
         while (cur >= 0 && fabs(a.saveat[cur] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
-            if (!((a.flags & 1u) && cur == 0)) {
+            if (!((a.flags & 1u) && cur == 0 && SA != SA_BACKSOLVE)) {
                 if (COST == COST_EXPLICIT) {
 #pragma unroll
                     for (int j = 0; j < D; j++) z[j] += a.dLdu[((int64_t)cur * D + j) * N + i];
                 } else {
                     double y[D];
+                    if (SA == SA_BACKSOLVE) {
+#pragma unroll
+                        for (int j = 0; j < D; j++) y[j] = z[YO + j];
+                    } else
                     sol.eval(a.saveat[cur], true, y);
 #pragma unroll
                     for (int j = 0; j < D; j++) z[j] += a.cost_a * y[j] + a.cost_b;
@@ -213,6 +250,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
             cur--; fsal_ok = false;
         }
     };
+    ckpt_if_at(t);
     jump_if_at(t);
     double h = a.dt0 > 0 ? -a.dt0 : -1e-4 * (T - t0), qold = 1e-4;
     long iters = 0;
@@ -220,6 +258,11 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) { overflow = true; break; }
         double tstop = t0;
         if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
+        if (SA == SA_BACKSOLVE && ckpt_on && every) {            // every forward knot is a tstop of the reverse solve
+            int c2 = ck;
+            while (c2 >= 0 && sol.T(c2) >= t - EPS100 * fmax(fabs(t), 1.0)) c2--;
+            if (c2 >= 0 && sol.T(c2) > tstop) tstop = sol.T(c2);
+        }
         double tn = tstop_snap(t + h, tstop);
         if (tn < tstop) tn = tstop;
         const double hs = tn - t;
@@ -264,6 +307,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         for (int c = 0; c < L; c++) { z[c] = zn[c]; k[0][c] = k[6][c]; }
         fsal_ok = true;
         t = tn;
+        ckpt_if_at(t);
         jump_if_at(t);
     }
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
@@ -275,7 +319,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     if (SA != SA_QUAD) {
         double out[P];
 #pragma unroll
-        for (int q = 0; q < P; q++) out[q] = overflow ? qnan : (SA == SA_INTERP ? z[D + (SA == SA_INTERP ? q : 0)] : acc[q]);
+        for (int q = 0; q < P; q++) out[q] = overflow ? qnan : ((SA == SA_INTERP || SA == SA_BACKSOLVE) ? z[(L > D ? D : 0) + (L > D ? q : 0)] : acc[q]);
         if (SHARED_P) {
             if (!active) {
 #pragma unroll

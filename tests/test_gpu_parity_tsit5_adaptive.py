@@ -47,6 +47,32 @@ def test_c1_lotka_volterra_adaptive(sensealg, N):
     eng.close()
 
 
+def test_lorenz_checkpointed_backsolve_equals_interpolating():
+    """The reference's own Lorenz check (test/Core3/adjoint.jl:1157-1241): adaptive Tsit5 forward solve, dg = u - 2 at
+    0:0.1:10, BacksolveAdjoint (checkpoints = sol.t, and = every 10th ... here: the save times) == InterpolatingAdjoint
+    at rtol 1e-5 / 1e-4, on the device and against the oracle."""
+    N, T = 16, 10.0
+    rng = np.random.default_rng(2)
+    u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.001 * rng.standard_normal((3, N))
+    p = np.array([10.0, 28.0, 8.0 / 3.0])
+    t = np.linspace(0.0, T, 101)
+    tol = dict(abstol=1e-9, reltol=1e-9)
+    res = {}
+    for sa, every in (("interpolating", False), ("backsolve", True), ("backsolve", False)):
+        eng = b.DeviceEnsemble("lorenz", sa, "tsit5_adaptive", N, t, (0.0, T), 0.0, cost=b.AffineCost(1.0, -2.0), ckpt_every_step=every,
+                               max_steps=16384, **tol)
+        eng.forward(u0, p)
+        du0, dp = eng.reverse()
+        cfg = O.make_cfg("lorenz", sa, "tsit5_adaptive", N, t, 0.0, T, cost=("affine", 1.0, -2.0), ckpt_every_step=every, **tol)
+        ref = O.gradient(cfg, t, u0, p)
+        assert _rel(du0, ref["du0"]) < 1e-6 and _rel(dp, ref["dp"]) < 1e-6, (sa, every)
+        res[(sa, every)] = (du0, dp)
+        eng.close()
+    assert _rel(res[("backsolve", True)][1], res[("interpolating", False)][1]) < 1e-5
+    assert _rel(res[("backsolve", True)][0], res[("interpolating", False)][0]) < 1e-5
+    assert _rel(res[("backsolve", False)][1], res[("interpolating", False)][1]) < 1e-4
+
+
 def test_adaptive_tsit5_public_api_lorenz():
     """test/Core3/adjoint.jl:1157-1241 (Lorenz, adaptive Tsit5, dg = u - 2 at 0:0.1:10): Interpolating == Gauss == Quadrature."""
     N, T = 32, 10.0
