@@ -137,6 +137,14 @@ void build_tsit5_tables(double h, Tsit5Tables* t) {
 bool is_sde(const b200adj_cfg& c) { return c.stepper == B200ADJ_ST_EM || c.stepper == B200ADJ_ST_EULER_HEUN; }
 
 // ---------------- kernel dispatch (block size is a runtime value) ----------------
+// Threads per block for `slots` member slots: whole warp rows (multiples of 128 threads) with travelling warp groups
+// in the top row when the slot count would leave the SM's four sub-partitions unbalanced (tsit5_reverse_kernel);
+// B200ADJ_NO_ROTATE=1 launches exactly `slots` threads (tuning / A-B runs).
+static int balanced_threads(int slots) {
+    static const bool no_rotate = getenv("B200ADJ_NO_ROTATE") && atoi(getenv("B200ADJ_NO_ROTATE")) != 0;
+    if (!no_rotate && slots > 128 && (slots % 128) != 0) return ((slots + 127) / 128) * 128;
+    return slots;
+}
 template <class Fam>
 int launch_fwd(Handle* h, const OdeFwdArgs& a) {
     if (h->cfg.shared_p) tsit5_forward_kernel<Fam, true><<<h->grid, h->block, 0, h->stream>>>(a);
@@ -145,16 +153,19 @@ int launch_fwd(Handle* h, const OdeFwdArgs& a) {
     return 0;
 }
 template <class Fam, int SA, bool SHARED_P, int COST>
-int launch_rev_b(Handle* h, const OdeRevArgs& a) {
+int launch_rev_b(Handle* h, const OdeRevArgs& a0) {
+    OdeRevArgs a = a0;
+    a.slots = h->block;
+    const int threads = SA == SA_BACKSOLVE ? h->block : balanced_threads(h->block);
     const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D>(h->block);
     // the continuous-cost variant is a separate instantiation: the headline kernel keeps its register budget
     if (h->cont_on) {
         if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true><<<h->grid, h->block, smem, h->stream>>>(a);
+        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true><<<h->grid, threads, smem, h->stream>>>(a);
     } else {
         // static smem (barriers, reduction scratch) rides on top of the dynamic tile
         if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false><<<h->grid, h->block, smem, h->stream>>>(a);
+        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false><<<h->grid, threads, smem, h->stream>>>(a);
     }
     h->launches++;
     return 0;

@@ -63,6 +63,7 @@ struct OdeRevArgs {
     int64_t N;
     int64_t Npad;            // checkpoint row pitch
     int32_t S;
+    int32_t slots;           // member slots per block (= checkpoint tile width); blockDim.x > slots => the top warp row rotates
     double cost_a, cost_b;
     double cont_a, cont_b;   // continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u):  dlam -= dgdu_continuous(y)  (flags bit3)
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step, bit3 continuous cost
@@ -127,6 +128,10 @@ template <int D> __device__ __forceinline__ void tsit5_dense(const double* u, co
     }
 }
 
+// producer/consumer named barriers (ids 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 // ------------------------------------------------------------------------------------------------------------
 // Forward ensemble solve, fixed-step Tsit5, writes every step's state (the dense solution is NOT stored: the
 // reverse pass recomputes the 6 stages from u_n, 24 B/step instead of 192 B/step of HBM traffic).
@@ -147,6 +152,8 @@ __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constan
     store_state<D>(a.ckpt, a.Npad, gi, u);
     if (active && a.saved) { int ks = a.save_of_step[0]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
     Fam::f(u, p, k[0]);
+    // (travelling warp groups as in the reverse kernel were tried here: the rotation itself gains 3%, the extra control
+    // flow costs the free-running loop 8% -- profiles/r1_tuning_log.md -- so the forward kernel launches `slots` threads)
     for (int n = 0; n < a.S; n++) {
         tsit5_stage<D, 1>(a.tb, u, k, tmp); Fam::f(tmp, p, k[1]);
         tsit5_stage<D, 2>(a.tb, u, k, tmp); Fam::f(tmp, p, k[2]);
@@ -242,14 +249,35 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
 #define REV_CH_DEF 4
 #endif
 constexpr int REV_CH = REV_CH_DEF, REV_NST = 2;     // TMA pipeline: steps per stage (= block barrier period), stages in flight
+static_assert(REV_CH_DEF <= 4, "hand-over barrier ids are keyed by step & 3: the block barrier period must not exceed 4 steps");
 template <int D> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(double); }
 template <class Fam, int SA, bool SHARED_P, int COST, bool CONT>
 __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
-    const int BLOCK = (int)blockDim.x;
-    const int64_t gi = (int64_t)blockIdx.x * BLOCK + threadIdx.x;
-    const bool active = gi < a.N;
-    const int64_t i = active ? gi : a.N - 1;
+    // BLOCK = member slots of this block.  When the slot count is not a multiple of 4 warps the SM's four sub-partitions
+    // (one fp64 pipe each; warp w lives on sub-partition w % 4 -- tuning/smsp_map.cu) would carry unequal warp counts for
+    // the whole solve: 448 slots = 4,4,3,3 warps, and the kernel runs at the pace of the 4-warp sub-partitions (measured:
+    // 448 and 512 slots take the same 2.02 ms, 384 slots 1.58 ms).  The host then launches whole warp rows
+    // (blockDim.x = 128 * ceil(BLOCK / 128)) and the rw = (BLOCK / 32) % 4 warp groups of the top row travel round the
+    // four sub-partitions, one hop per time step: group q4+e is advanced through step c by warp q4 + ((e + c) & 3), which
+    // takes the group's live state from its predecessor through shared memory (producer/consumer named barriers) and
+    // hands it on after the step.  Every sub-partition then carries q4/4 + rw/4 warps of work on average.
+    const int BLOCK = a.slots;
+    const bool rot = (int)blockDim.x > BLOCK;
+    const int wid = (int)(threadIdx.x >> 5), q4 = (BLOCK >> 7) << 2, rw = (BLOCK >> 5) & 3;
+    const bool top = rot && wid >= q4;
+    auto group_of = [&](int c) -> int {           // member group this warp advances through step counter c (-1: resting)
+        if (!top) return wid;
+        const int e = ((wid - q4) - c) & 3;
+        return e < rw ? q4 + e : -1;
+    };
+    int grp = group_of(0);
+    // global member index of this thread's current slot (the group changes per step for the travelling warps)
+    auto member_gi = [&]() -> int64_t { return (int64_t)blockIdx.x * BLOCK + grp * 32 + (int)(threadIdx.x & 31); };
+    auto member_i = [&]() -> int64_t { const int64_t g = member_gi(); return (grp >= 0 && g < a.N) ? g : a.N - 1; };
+    int64_t gi = member_gi();
+    bool active = grp >= 0 && gi < a.N;
+    int64_t i = active ? gi : a.N - 1;
     const int64_t N = a.N, stride = (int64_t)D * N, Npad = a.Npad, cstride = (int64_t)D * Npad;
     const Tsit5Tables& tb = a.tb;
     if (a.trace && threadIdx.x == 0) {
@@ -343,7 +371,14 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
         __syncthreads();
         if (threadIdx.x == 0) for (int k = 0; k < NST && k < NC; k++) issue_chunk(k);
 
-        load_state<D>(a.ckpt + (int64_t)a.S * cstride, Npad, gi, uhi);
+        constexpr int NV = 4 * D + P;          // rotating state: lam, mu, ka[0], kf[6], uhi
+        __shared__ double s_mig[3 * NV * 32];
+        __shared__ double s_migp[SHARED_P ? 1 : 3 * P * 32];          // per-member parameters of the travelling groups
+        if (!SHARED_P && top && grp >= 0) {
+#pragma unroll
+            for (int q = 0; q < P; q++) s_migp[((grp - q4) * P + q) * 32 + (threadIdx.x & 31)] = p[q];
+        }
+        load_state<D>(a.ckpt + (int64_t)a.S * cstride, Npad, grp >= 0 ? gi : 0, uhi);
         {
             // jump at t = T (PresetTimeCallback fires at initialisation when T is a save time)
             int ks = a.save_of_step[a.S];
@@ -354,13 +389,34 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
         }
         for (int n = a.S - 1; n >= 0; n--) {
             const int c = a.S - 1 - n, k = c / CH, jj = c % CH, st = k % NST;
-            if (jj == 0) mbar_wait(&s_bar[st], (uint32_t)((k / NST) & 1));
+            if (top) {
+                const int lane = (int)(threadIdx.x & 31);
+                grp = group_of(c);
+                if (c > 0 && grp >= 0) {       // take the group over from the warp that advanced it through step c-1
+                    // barrier id keyed by (group, step & 3): resting warps run ahead of the group by up to one barrier
+                    // window (CH = 4 steps), so consecutive hand-overs of one group must not share an id
+                    named_bar_sync(1 + (grp - q4) * 4 + (c & 3), 64);
+                    const double* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;
 #pragma unroll
-            for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[(size_t)((st * CH + jj) * D + dd) * BLOCK + threadIdx.x];
+                    for (int j = 0; j < D; j++) { lam[j] = m[j * 32]; ka[0][j] = m[(D + j) * 32]; kf[6][j] = m[(2 * D + j) * 32]; uhi[j] = m[(3 * D + j) * 32]; }
+#pragma unroll
+                    for (int q = 0; q < P; q++) mu[q] = m[(4 * D + q) * 32];
+                    if (!SHARED_P) {
+#pragma unroll
+                        for (int q = 0; q < P; q++) p[q] = s_migp[((grp - q4) * P + q) * 32 + lane];
+                    }
+                }
+            }
+            if (jj == 0) mbar_wait(&s_bar[st], (uint32_t)((k / NST) & 1));
+            if (grp >= 0) {
+#pragma unroll
+                for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[(size_t)((st * CH + jj) * D + dd) * BLOCK + grp * 32 + (threadIdx.x & 31)];
+            }
             if (jj == CH - 1 || n == 0) {
                 __syncthreads();               // every thread has read this stage: hand it back to the TMA producer
                 if (threadIdx.x == 0 && k + NST < NC) issue_chunk(k + NST);
             }
+            if (grp < 0) continue;             // resting warp of the rotating row: barriers only
 
             // ---- forward stage recompute on [t_n, t_{n+1}]: the dense-output data of this step ----
             double tmp[D];
@@ -403,7 +459,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (SA == SA_QUAD) {
                 // QuadratureAdjoint: keep the dense reverse solution of this step (adj_sol with save_everystep,
                 // src/quadrature_adjoint.jl:527-530): start value (post-jump lambda(t_{n+1})) and the 7 stage derivatives
-                double* row = a.adj_dense + (int64_t)n * 8 * cstride + gi;
+                double* row = a.adj_dense + (int64_t)n * 8 * cstride + member_gi();
 #pragma unroll
                 for (int j = 0; j < D; j++) row[(int64_t)j * Npad] = lam[j];
 #pragma unroll
@@ -430,15 +486,26 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             // ---- jump at t_n (ReverseLossCallback): lam += dgdu(t_k), FSAL invalidated => recompute ka[0] ----
             const int ks = a.save_of_step[n];
             if (ks >= 0 && !((a.flags & 1u) && n == 0)) {
-                add_cotangent<D, COST>(a, ks, stride, N, i, ulo, lam);
+                add_cotangent<D, COST>(a, ks, stride, N, member_i(), ulo, lam);
                 Fam::vjp_u(ulo, p, lam, ka[0]);
                 add_continuous<D, CONT>(a, ulo, ka[0]);
             }
 #pragma unroll
             for (int j = 0; j < D; j++) uhi[j] = ulo[j];
+            if (top && n > 0) {                // hand the group on to the next warp of the ring
+                const int lane = (int)(threadIdx.x & 31);
+                double* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;
+#pragma unroll
+                for (int j = 0; j < D; j++) { m[j * 32] = lam[j]; m[(D + j) * 32] = ka[0][j]; m[(2 * D + j) * 32] = kf[6][j]; m[(3 * D + j) * 32] = uhi[j]; }
+#pragma unroll
+                for (int q = 0; q < P; q++) m[(4 * D + q) * 32] = mu[q];
+                __threadfence_block();
+                named_bar_arrive(1 + (grp - q4) * 4 + ((c + 1) & 3), 64);
+            }
         }
     }
 
+    gi = member_gi(); active = grp >= 0 && gi < a.N; i = active ? gi : a.N - 1;       // final holder of each group
     if (active) store_state<D>(a.du0, N, i, lam);
     if (a.trace && threadIdx.x == 0) {
         unsigned long long t;
