@@ -342,7 +342,7 @@ def run_ours(args):
 
 
 def run_secondary(args):
-    """--workload c3|c4|c5: the other BASELINE configs (parity-test cases; reported for context, same JSON shape)."""
+    """--workload c2f32|c3|c4|c5: the other BASELINE configs (parity-test cases; reported for context, same JSON shape)."""
     import torch
     import scimlsensitivity_jl_b200 as b
     from oracle import oracle as O
@@ -361,6 +361,16 @@ def run_secondary(args):
                                cost=b.AffineCost(1.0, 0.0), max_steps=8192, **kw)
         ocfg = lambda n: O.make_cfg("robertson", "quadrature", "rosenbrock23", n, saveat, 0.0, T, cost=("affine", 1.0, 0.0), shared_p=False, **kw)
         name, dtype, sample = "C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves", "f64", 256
+    elif w == "c2f32":
+        # the fp32 throughput variant of C2: same ensemble, T = 1 (S = 100, K = 11), fp32 state and tables
+        N = args.members or 65536
+        T, dt = 1.0, 0.01
+        saveat = np.linspace(0.0, T, 11)
+        u0, p = make_inputs(N)
+        dtype = "f32"
+        eng = b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", N, saveat, (0.0, T), dt, on_device=True, dtype=dtype, cost=b.AffineCost(1.0, -2.0))
+        ocfg = lambda n: O.make_cfg("lorenz", "gauss", "tsit5_fixed", n, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0))
+        name, sample = "C2-fp32 Lorenz d=3 P=3 GaussAdjoint Tsit5 fixed dt=0.01 T=1 saveat=0.1 dgdu=u-2 shared p, fp32 state (fp64 oracle on the CPU side)", 16384
     elif w == "c4":
         N = args.members or 4096
         T, dt = 1.5, 0.05
@@ -451,7 +461,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members", type=int, default=0, help="override members per GPU (default 65536) / reference sample")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (multiple of 32, <= 512)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c2f32", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
     ap.add_argument("--dtype", default="", help="c4 only: f32 (default) or f64")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -152,6 +152,46 @@ int launch_fwd(Handle* h, const OdeFwdArgs& a) {
     h->launches++;
     return 0;
 }
+// ---- fp32 variant of the fixed-step path (LV / Lorenz; Interpolating / Gauss / Backsolve; no continuous cost) ----
+template <class T, class S> static void cast_tables(const S& src, T* dst) {
+    for (int i = 0; i < 7; i++) for (int j = 0; j < 6; j++) dst->hA[i][j] = (float)src.hA[i][j];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 7; j++) dst->hBst[i][j] = (float)src.hBst[i][j];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 7; j++) dst->hBq[i][j] = (float)src.hBq[i][j];
+    for (int i = 0; i < 3; i++) dst->hGW[i] = (float)src.hGW[i];
+}
+template <class Fam>
+int launch_fwd_f32(Handle* h, const OdeFwdArgsT<float>& a) {
+    if (h->cfg.shared_p) tsit5_forward_kernel<Fam, true, float><<<h->grid, h->block, 0, h->stream>>>(a);
+    else tsit5_forward_kernel<Fam, false, float><<<h->grid, h->block, 0, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+template <class Fam, int SA, bool SHARED_P, int COST>
+int launch_rev_f32_b(Handle* h, OdeRevArgsT<float> a) {
+    a.slots = h->block;
+    const int threads = SA == SA_BACKSOLVE ? h->block : balanced_threads(h->block);
+    const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D, float>(h->block);
+    if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+    tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float><<<h->grid, threads, smem, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+template <class Fam, int SA>
+int launch_rev_f32_sa(Handle* h, const OdeRevArgsT<float>& a) {
+    const bool sp = h->cfg.shared_p;
+    const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (sp) return ex ? launch_rev_f32_b<Fam, SA, true, COST_EXPLICIT>(h, a) : launch_rev_f32_b<Fam, SA, true, COST_AFFINE>(h, a);
+    return ex ? launch_rev_f32_b<Fam, SA, false, COST_EXPLICIT>(h, a) : launch_rev_f32_b<Fam, SA, false, COST_AFFINE>(h, a);
+}
+template <class Fam>
+int launch_rev_f32(Handle* h, const OdeRevArgsT<float>& a) {
+    switch (h->cfg.sensealg) {
+    case B200ADJ_SA_INTERPOLATING: return launch_rev_f32_sa<Fam, SA_INTERP>(h, a);
+    case B200ADJ_SA_GAUSS: return launch_rev_f32_sa<Fam, SA_GAUSS>(h, a);
+    case B200ADJ_SA_BACKSOLVE: return launch_rev_f32_sa<Fam, SA_BACKSOLVE>(h, a);
+    default: return B200ADJ_ERR_UNSUPPORTED;
+    }
+}
 template <class Fam, int SA, bool SHARED_P, int COST>
 int launch_rev_b(Handle* h, const OdeRevArgs& a0) {
     OdeRevArgs a = a0;
@@ -433,8 +473,12 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || (!ros && !(cfg->dt > 0)) || !(cfg->t1 > cfg->t0)) {
         g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
     const bool mlp = cfg->rhs_family == B200ADJ_FAM_MLP;
-    if (cfg->dtype != B200ADJ_F64 && !(mlp && (cfg->dtype == B200ADJ_F32 || cfg->dtype == B200ADJ_BF16_F32ACC))) {
-        g_create_error = "dtype: F64 (all families), F32 / BF16_F32ACC (MLP family) are built"; return B200ADJ_ERR_UNSUPPORTED; }
+    // F32: the MLP family and the fixed-step Tsit5 ODE path of LV / Lorenz (the fp32 throughput variant)
+    const bool f32_ode = cfg->dtype == B200ADJ_F32 && cfg->stepper == B200ADJ_ST_TSIT5_FIXED &&
+                         (cfg->rhs_family == B200ADJ_FAM_LV || cfg->rhs_family == B200ADJ_FAM_LORENZ);
+    if (f32_ode && cfg->sensealg == B200ADJ_SA_QUADRATURE) { g_create_error = "F32: Interpolating / Gauss / Backsolve (QuadratureAdjoint is F64 only)"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (cfg->dtype != B200ADJ_F64 && !f32_ode && !(mlp && (cfg->dtype == B200ADJ_F32 || cfg->dtype == B200ADJ_BF16_F32ACC))) {
+        g_create_error = "dtype: F64 (all families), F32 (MLP; LV / Lorenz with fixed-step Tsit5), BF16_F32ACC (MLP) are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (mlp && (cfg->stepper != B200ADJ_ST_TSIT5_FIXED || cfg->sensealg != B200ADJ_SA_INTERPOLATING || !cfg->shared_p)) {
         g_create_error = "MLP family: InterpolatingAdjoint + fixed-step Tsit5 + shared parameters are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->cost_kind != B200ADJ_COST_EXPLICIT && cfg->cost_kind != B200ADJ_COST_AFFINE) { g_create_error = "bad cost_kind"; return B200ADJ_ERR_INVALID; }
@@ -609,6 +653,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (c.dtype == B200ADJ_F32 && c.rhs_family != B200ADJ_FAM_MLP && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "F32: QuadratureAdjoint is F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
         if ((sensealg == B200ADJ_SA_BACKSOLVE || sensealg == B200ADJ_SA_INTERPOLATING) && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) {
@@ -744,6 +789,16 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
         rc = c.dtype != B200ADJ_F64 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
                                     : mlp_forward_launch<double>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
+    } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
+        OdeFwdArgsT<float> a;
+        a.u0 = (const float*)du0; a.p = (const float*)dp; a.ckpt = (float*)h->d_ckpt; a.saved = c.K > 0 ? (float*)dsaved : nullptr;
+        a.save_of_step = h->d_save_of_step; a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S;
+        cast_tables(h->tb, &a.tb);
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_fwd_f32<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_fwd_f32<Lorenz>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
     } else if (!is_sde(c)) {
         OdeFwdArgs a;
         a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
@@ -833,6 +888,21 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
         rc = c.dtype != B200ADJ_F64 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
+    } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
+        if (h->cont_on) { h->err = "continuous cost: F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
+        OdeRevArgsT<float> a;
+        memset(&a, 0, sizeof(a));
+        a.ckpt = (const float*)h->d_ckpt; a.p = (const float*)h->cur_p; a.dLdu = (const float*)dL; a.save_of_step = h->d_save_of_step;
+        a.du0 = (float*)ddu0; a.dp_members = (float*)ddp; a.partials = h->d_partials; a.dp = (float*)ddp; a.ticket = h->d_ticket;
+        a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.cost_a = (float)c.cost_a; a.cost_b = (float)c.cost_b; a.trace = h->d_trace;
+        cast_tables(h->tb, &a.tb);
+        a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
+                  ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
+        switch (c.rhs_family) {
+        case B200ADJ_FAM_LV: rc = launch_rev_f32<LotkaVolterra>(h, a); break;
+        case B200ADJ_FAM_LORENZ: rc = launch_rev_f32<Lorenz>(h, a); break;
+        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        }
     } else if (!is_sde(c)) {
         OdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;

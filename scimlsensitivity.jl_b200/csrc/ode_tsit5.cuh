@@ -27,56 +27,60 @@
 
 namespace b200adj {
 
-struct Tsit5Tables {
-    double hA[7][6];    // h * A[s][j] (row 6 = h * b)
-    double hBst[4][7];  // h * b_j(theta) at theta = 1 - c_s for adjoint stages s = 1..4 (0-based)
-    double hBq[3][7];   // h * b_j(theta) at theta = (1 -/+ sqrt(.6))/2, 1/2  (3-pt Gauss-Legendre nodes)
-    double hGW[3];      // (h/2) * Gauss-Legendre weights 5/9, 8/9, 5/9
+// R = real type of the solve: double (all paths) or float (the fp32 throughput variant of the fixed-step ODE path)
+template <class R> struct Tsit5TablesT {
+    R hA[7][6];    // h * A[s][j] (row 6 = h * b)
+    R hBst[4][7];  // h * b_j(theta) at theta = 1 - c_s for adjoint stages s = 1..4 (0-based)
+    R hBq[3][7];   // h * b_j(theta) at theta = (1 -/+ sqrt(.6))/2, 1/2  (3-pt Gauss-Legendre nodes)
+    R hGW[3];      // (h/2) * Gauss-Legendre weights 5/9, 8/9, 5/9
 };
+using Tsit5Tables = Tsit5TablesT<double>;
 
 enum { SA_INTERP = 0, SA_GAUSS = 1, SA_QUAD = 2, SA_BACKSOLVE = 3 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
 
-struct OdeFwdArgs {
-    const double* u0;        // [D][N]
-    const double* p;         // [P] or [P][N]
-    double* ckpt;            // [S+1][D][N]
-    double* saved;           // [K][D][N] or null
+template <class R> struct OdeFwdArgsT {
+    const R* u0;        // [D][N]
+    const R* p;         // [P] or [P][N]
+    R* ckpt;            // [S+1][D][N]
+    R* saved;           // [K][D][N] or null
     const int32_t* save_of_step;  // [S+1]: save index k at grid point n, or -1
     int32_t* status;         // [N] or null
     int64_t N;
     int64_t Npad;            // checkpoint row pitch: N rounded up to the block size (every block owns full 16B-aligned rows)
     int32_t S;
-    Tsit5Tables tb;
+    Tsit5TablesT<R> tb;
 };
+using OdeFwdArgs = OdeFwdArgsT<double>;
 
-struct OdeRevArgs {
-    const double* ckpt;      // [S+1][D][N]
-    const double* p;         // [P] or [P][N]
-    const double* dLdu;      // [K][D][N] (COST_EXPLICIT)
+template <class R> struct OdeRevArgsT {
+    const R* ckpt;      // [S+1][D][N]
+    const R* p;         // [P] or [P][N]
+    const R* dLdu;      // [K][D][N] (COST_EXPLICIT)
     const int32_t* save_of_step;
-    double* du0;             // [D][N]
-    double* dp_members;      // [P][N] when !shared_p
+    R* du0;             // [D][N]
+    R* dp_members;      // [P][N] when !shared_p
     double* partials;        // [gridDim][P] block partial sums (shared_p)
-    double* dp;              // [P] final (shared_p)
+    R* dp;              // [P] final (shared_p)
     unsigned int* ticket;    // last-block-done counter
     int64_t N;
     int64_t Npad;            // checkpoint row pitch
     int32_t S;
     int32_t slots;           // member slots per block (= checkpoint tile width); blockDim.x > slots => the top warp row rotates
-    double cost_a, cost_b;
-    double cont_a, cont_b;   // continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u):  dlam -= dgdu_continuous(y)  (flags bit3)
+    R cost_a, cost_b;
+    R cont_a, cont_b;   // continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u):  dlam -= dgdu_continuous(y)  (flags bit3)
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step, bit3 continuous cost
-    double* adj_dense;       // SA_QUAD: [S][8][D][Npad] = (lambda at the start of reverse step n, ka'[0..6]) per step
+    R* adj_dense;       // SA_QUAD: [S][8][D][Npad] = (lambda at the start of reverse step n, ka'[0..6]) per step
     unsigned long long* trace;   // optional [gridDim][3] = (smid, globaltimer at block start, at block end) or null
-    Tsit5Tables tb;
+    Tsit5TablesT<R> tb;
 };
+using OdeRevArgs = OdeRevArgsT<double>;
 
-template <int D> __device__ __forceinline__ void load_state(const double* base, int64_t N, int64_t i, double* u) {
+template <int D, class R> __device__ __forceinline__ void load_state(const R* base, int64_t N, int64_t i, R* u) {
 #pragma unroll
     for (int j = 0; j < D; j++) u[j] = __ldg(base + (int64_t)j * N + i);
 }
-template <int D> __device__ __forceinline__ void store_state(double* base, int64_t N, int64_t i, const double* u) {
+template <int D, class R> __device__ __forceinline__ void store_state(R* base, int64_t N, int64_t i, const R* u) {
 #pragma unroll
     for (int j = 0; j < D; j++) base[(int64_t)j * N + i] = u[j];
 }
@@ -108,20 +112,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // stage value  u + sum_{j<S_} hA[S_][j] k_j
-template <int D, int S_> __device__ __forceinline__ void tsit5_stage(const Tsit5Tables& tb, const double* u, const double (*k)[D], double* out) {
+template <int D, int S_, class R> __device__ __forceinline__ void tsit5_stage(const Tsit5TablesT<R>& tb, const R* u, const R (*k)[D], R* out) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        double acc = u[i];
+        R acc = u[i];
 #pragma unroll
         for (int j = 0; j < S_; j++) acc = fma(tb.hA[S_][j], k[j][i], acc);
         out[i] = acc;
     }
 }
 // dense output  u + sum_j w[j] k_j   (w already scaled by h)
-template <int D> __device__ __forceinline__ void tsit5_dense(const double* u, const double (*k)[D], const double* w, double* out) {
+template <int D, class R> __device__ __forceinline__ void tsit5_dense(const R* u, const R (*k)[D], const R* w, R* out) {
 #pragma unroll
     for (int i = 0; i < D; i++) {
-        double acc = u[i];
+        R acc = u[i];
 #pragma unroll
         for (int j = 0; j < 7; j++) acc = fma(w[j], k[j][i], acc);
         out[i] = acc;
@@ -136,16 +140,16 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm vol
 // Forward ensemble solve, fixed-step Tsit5, writes every step's state (the dense solution is NOT stored: the
 // reverse pass recomputes the 6 stages from u_n, 24 B/step instead of 192 B/step of HBM traffic).
 // ------------------------------------------------------------------------------------------------------------
-template <class Fam, bool SHARED_P>
-__global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constant__ OdeFwdArgs a) {
+template <class Fam, bool SHARED_P, class R = double>
+__global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constant__ OdeFwdArgsT<R> a) {
     constexpr int D = Fam::D, P = Fam::P;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = gi < a.N;
     const int64_t i = active ? gi : a.N - 1;
-    double p[P];
+    R p[P];
 #pragma unroll
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * a.N + i);
-    double u[D], k[7][D], tmp[D];
+    R u[D], k[7][D], tmp[D];
     load_state<D>(a.u0, a.N, i, u);
     const int64_t stride = (int64_t)D * a.N, cstride = (int64_t)D * a.Npad;
     // checkpoints: padded pitch, threads past N shadow member N-1 and fill the pad columns (keeps TMA rows whole)
@@ -177,8 +181,8 @@ __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constan
 
 // deterministic block reduction of P per-thread values -> partials[block][P]; the last block to finish sums the
 // partials in index order (fixed order => bitwise reproducible for a given grid), no floating-point atomics.
-template <int P>
-__device__ __forceinline__ void reduce_dp(const double* acc, double* partials, double* dp, unsigned int* ticket) {
+template <int P, class RO>
+__device__ __forceinline__ void reduce_dp(const double* acc, double* partials, RO* dp, unsigned int* ticket) {
     __shared__ double s_red[16 * P];               // up to 512 threads per block
     const int nwarps = (int)(blockDim.x >> 5);
     __shared__ bool s_last;
@@ -211,23 +215,23 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, d
             for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (int64_t)b * P + q);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) dp[q] = v;
+            if (lane == 0) dp[q] = (RO)v;
         }
         if (threadIdx.x == 0) *ticket = 0;   // re-arm for the next launch
     }
 }
 
 // accumulate_cost! (src/derivative_wrappers.jl:1411-1442): with ka' = -dlam/dt the continuous cost adds +dgdu_continuous(y)
-template <int D, bool CONT, class Args>
-__device__ __forceinline__ void add_continuous(const Args& a, const double* y, double* ka) {
+template <int D, bool CONT, class Args, class R>
+__device__ __forceinline__ void add_continuous(const Args& a, const R* y, R* ka) {
     if (CONT) {
 #pragma unroll
         for (int j = 0; j < D; j++) ka[j] += fma(a.cont_a, y[j], a.cont_b);
     }
 }
 
-template <int D, int COST, class Args>
-__device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t stride, int64_t N, int64_t i, const double* y, double* lam) {
+template <int D, int COST, class Args, class R>
+__device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t stride, int64_t N, int64_t i, const R* y, R* lam) {
     if (COST == COST_EXPLICIT) {
 #pragma unroll
         for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
@@ -250,9 +254,9 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
 #endif
 constexpr int REV_CH = REV_CH_DEF, REV_NST = 2;     // TMA pipeline: steps per stage (= block barrier period), stages in flight
 static_assert(REV_CH_DEF <= 4, "hand-over barrier ids are keyed by step & 3: the block barrier period must not exceed 4 steps");
-template <int D> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(double); }
-template <class Fam, int SA, bool SHARED_P, int COST, bool CONT>
-__global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgs a) {
+template <int D, class R = double> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(R); }
+template <class Fam, int SA, bool SHARED_P, int COST, bool CONT, class R = double>
+__global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgsT<R> a) {
     constexpr int D = Fam::D, P = Fam::P;
     // BLOCK = member slots of this block.  When the slot count is not a multiple of 4 warps the SM's four sub-partitions
     // (one fp64 pipe each; warp w lives on sub-partition w % 4 -- tuning/smsp_map.cu) would carry unequal warp counts for
@@ -279,18 +283,18 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
     bool active = grp >= 0 && gi < a.N;
     int64_t i = active ? gi : a.N - 1;
     const int64_t N = a.N, stride = (int64_t)D * N, Npad = a.Npad, cstride = (int64_t)D * Npad;
-    const Tsit5Tables& tb = a.tb;
+    const Tsit5TablesT<R>& tb = a.tb;
     if (a.trace && threadIdx.x == 0) {
         unsigned int smid; unsigned long long t;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         a.trace[blockIdx.x * 3 + 0] = smid; a.trace[blockIdx.x * 3 + 1] = t;
     }
-    double p[P];
+    R p[P];
 #pragma unroll
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * N + i);
 
-    double lam[D], mu[P];                 // mu: dG/dp accumulator (Gauss quadrature sum, or the augmented state)
+    R lam[D], mu[P];                 // mu: dG/dp accumulator (Gauss quadrature sum, or the augmented state)
 #pragma unroll
     for (int j = 0; j < D; j++) lam[j] = 0.0;
 #pragma unroll
@@ -299,10 +303,10 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
     if (SA == SA_BACKSOLVE) {
         // z = [lam; mu; y]; dy/dt = f(y) integrated backwards (src/backsolve_adjoint.jl:32-61).
         // ky' = -f(y), kl' = +J'lam so that both use the +h tables.
-        double y[D];
+        R y[D];
         load_state<D>(a.ckpt + (int64_t)a.S * cstride, Npad, gi, y);
         { int ks = a.save_of_step[a.S]; if (ks >= 0) add_cotangent<D, COST>(a, ks, stride, N, i, y, lam); }
-        double ky[7][D], kl[7][D], ys[D], ls[D], dg[P];
+        R ky[7][D], kl[7][D], ys[D], ls[D], dg[P];
         const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
         bool fsal = false;
         for (int n = a.S - 1; n >= 0; n--) {
@@ -336,9 +340,9 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (ks >= 0) { add_cotangent<D, COST>(a, ks, stride, N, i, y, lam); fsal = false; }
         }
     } else {
-        double kf[7][D];                       // forward stages of the current step; kf[6] = f(u_{n+1}) carried over
-        double ka[7][D];                       // adjoint stages (+J'lam); ka[0] carried over (FSAL) unless a jump hit
-        double ulo[D], uhi[D];                 // uhi (= u_{n+1}) is live only for SA_INTERP
+        R kf[7][D];                       // forward stages of the current step; kf[6] = f(u_{n+1}) carried over
+        R ka[7][D];                       // adjoint stages (+J'lam); ka[0] carried over (FSAL) unless a jump hit
+        R ulo[D], uhi[D];                 // uhi (= u_{n+1}) is live only for SA_INTERP
         // Forward checkpoints are staged HBM -> shared memory by TMA bulk copies, CH steps per stage, NST stages in
         // flight, completion tracked by one mbarrier per stage.  A register prefetch does not survive the register
         // cap (ptxas sinks the LDG next to its use and every step then eats a full DRAM latency -- 32% of all
@@ -348,11 +352,12 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
         // trace: 0.94 .. 2.2 ms for identical work) so the stragglers finish latency-bound; per-warp pipelines with
         // a coarse barrier measured slower as well (2.12-2.21 ms vs 1.98 ms) -- lockstep warps share the I-cache.
         constexpr int CH = REV_CH, NST = REV_NST;
-        extern __shared__ __align__(128) double s_ck[];          // [NST][CH][D][BLOCK]
+        extern __shared__ __align__(128) unsigned char s_ck_raw[];
+        R* const s_ck = reinterpret_cast<R*>(s_ck_raw);      // [NST][CH][D][BLOCK]
         __shared__ __align__(8) uint64_t s_bar[NST];
-        const uint32_t row_bytes = (uint32_t)(BLOCK * sizeof(double));
+        const uint32_t row_bytes = (uint32_t)(BLOCK * sizeof(R));      // BLOCK % 32 == 0 => a multiple of 16 B in both precisions
         const int NC = (a.S + CH - 1) / CH;    // chunk k holds steps n = S-1-(k*CH+j), j = 0..CH-1
-        const double* ck_col = a.ckpt + (int64_t)blockIdx.x * BLOCK;
+        const R* ck_col = a.ckpt + (int64_t)blockIdx.x * BLOCK;
         auto issue_chunk = [&](int k) {
             const int st = k % NST;
             const int cnt = min(CH, a.S - k * CH);
@@ -372,8 +377,8 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
         if (threadIdx.x == 0) for (int k = 0; k < NST && k < NC; k++) issue_chunk(k);
 
         constexpr int NV = 4 * D + P;          // rotating state: lam, mu, ka[0], kf[6], uhi
-        __shared__ double s_mig[3 * NV * 32];
-        __shared__ double s_migp[SHARED_P ? 1 : 3 * P * 32];          // per-member parameters of the travelling groups
+        __shared__ R s_mig[3 * NV * 32];
+        __shared__ R s_migp[SHARED_P ? 1 : 3 * P * 32];          // per-member parameters of the travelling groups
         if (!SHARED_P && top && grp >= 0) {
 #pragma unroll
             for (int q = 0; q < P; q++) s_migp[((grp - q4) * P + q) * 32 + (threadIdx.x & 31)] = p[q];
@@ -396,7 +401,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
                     // barrier id keyed by (group, step & 3): resting warps run ahead of the group by up to one barrier
                     // window (CH = 4 steps), so consecutive hand-overs of one group must not share an id
                     named_bar_sync(1 + (grp - q4) * 4 + (c & 3), 64);
-                    const double* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;
+                    const R* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;
 #pragma unroll
                     for (int j = 0; j < D; j++) { lam[j] = m[j * 32]; ka[0][j] = m[(D + j) * 32]; kf[6][j] = m[(2 * D + j) * 32]; uhi[j] = m[(3 * D + j) * 32]; }
 #pragma unroll
@@ -419,7 +424,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (grp < 0) continue;             // resting warp of the rotating row: barriers only
 
             // ---- forward stage recompute on [t_n, t_{n+1}]: the dense-output data of this step ----
-            double tmp[D];
+            R tmp[D];
             Fam::f(ulo, p, kf[0]);
             tsit5_stage<D, 1>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[1]);
             tsit5_stage<D, 2>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[2]);
@@ -431,7 +436,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             __syncthreads();
 #endif
             // ---- adjoint Tsit5 step t_{n+1} -> t_n; stage s evaluated at y(t_{n+1} - c_s h) ----
-            double ls[D], y[D], dg[P];
+            R ls[D], y[D], dg[P];
             if (SA == SA_INTERP) {
                 // mu' = -F'lam integrated with the same tableau: mu += h * sum_j b_j F'(y_j) lam_j ; stage 1 at y = u_{n+1}
                 Fam::vjp_p(uhi, p, lam, dg);
@@ -459,7 +464,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (SA == SA_QUAD) {
                 // QuadratureAdjoint: keep the dense reverse solution of this step (adj_sol with save_everystep,
                 // src/quadrature_adjoint.jl:527-530): start value (post-jump lambda(t_{n+1})) and the 7 stage derivatives
-                double* row = a.adj_dense + (int64_t)n * 8 * cstride + member_gi();
+                R* row = a.adj_dense + (int64_t)n * 8 * cstride + member_gi();
 #pragma unroll
                 for (int j = 0; j < D; j++) row[(int64_t)j * Npad] = lam[j];
 #pragma unroll
@@ -470,7 +475,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             if (SA == SA_GAUSS) {
                 // 3-point Gauss-Legendre over this step, pre-jump lambda from the adjoint step's own dense output,
                 // y from the forward dense output: dp += (h/2) w_q (df/dp)'(y_q) lam_q  (gauss_adjoint.jl:745-759)
-                double lq[D];
+                R lq[D];
 #pragma unroll
                 for (int g = 0; g < 3; g++) {
                     tsit5_dense<D>(lam, ka, tb.hBq[g], lq);
@@ -494,7 +499,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             for (int j = 0; j < D; j++) uhi[j] = ulo[j];
             if (top && n > 0) {                // hand the group on to the next warp of the ring
                 const int lane = (int)(threadIdx.x & 31);
-                double* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;
+                R* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;
 #pragma unroll
                 for (int j = 0; j < D; j++) { m[j * 32] = lam[j]; m[(D + j) * 32] = ka[0][j]; m[(2 * D + j) * 32] = kf[6][j]; m[(3 * D + j) * 32] = uhi[j]; }
 #pragma unroll
@@ -517,7 +522,10 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #pragma unroll
             for (int q = 0; q < P; q++) mu[q] = 0.0;
         }
-        reduce_dp<P>(mu, a.partials, a.dp, a.ticket);
+        double mud[P];                         // block / grid reduction in fp64 for both precisions
+#pragma unroll
+        for (int q = 0; q < P; q++) mud[q] = (double)mu[q];
+        reduce_dp<P>(mud, a.partials, a.dp, a.ticket);
     } else if (active) {
 #pragma unroll
         for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = mu[q];

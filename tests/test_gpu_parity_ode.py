@@ -159,3 +159,42 @@ def test_full_size_properties():
     du0e, dpe = eng.reverse(saved - 2.0)
     assert _rel(du0e.cpu().numpy(), du0) < 1e-12 and _rel(dpe.cpu().numpy(), dp) < 1e-12
     eng.close(); eng2.close()
+
+
+# ---- fp32 variant of the fixed-step path ("C2 fp32, T = 1") -----------------------------------------
+@pytest.mark.parametrize("family", ["lorenz", "lv"])
+@pytest.mark.parametrize("sa", ["interpolating", "gauss", "backsolve"])
+@pytest.mark.parametrize("shared_p", [True, False])
+def test_fp32_variant_vs_fp64_oracle(family, sa, shared_p):
+    """fp32 state / tables / tile, fp64 block reduction.  Tolerance: 2e-4 relative to the fp64 oracle at T = 1 (100 steps of
+    fp32 rounding, eps = 6e-8, amplified by the adjoint's growth over the horizon; measured 1e-6 .. 3e-5)."""
+    N, T, dt = 1000, 1.0, 0.01
+    rng = np.random.default_rng(5)
+    if family == "lorenz":
+        u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N)); p0 = np.array([10.0, 28.0, 8.0 / 3.0])
+    else:
+        u0 = 1.0 + 0.1 * rng.standard_normal((2, N)); p0 = np.array([1.5, 1.0, 3.0, 1.0])
+    p = p0 if shared_p else p0[:, None] * (1.0 + 0.01 * rng.standard_normal((len(p0), N)))
+    t = np.linspace(0.0, T, 11)
+    for cost in (("affine", 1.0, -2.0), ("explicit",)):
+        dL = None if cost[0] == "affine" else rng.standard_normal((len(t), u0.shape[0], N))
+        eng = b.DeviceEnsemble(family, sa, "tsit5_fixed", N, t, (0.0, T), dt, shared_p=shared_p, dtype="f32",
+                               cost=b.AffineCost(1.0, -2.0) if cost[0] == "affine" else None)
+        saved, _ = eng.forward(u0.astype(np.float32), p.astype(np.float32))
+        du0, dp = eng.reverse(None if dL is None else dL.astype(np.float32))
+        assert saved.dtype == np.float32 and du0.dtype == np.float32 and dp.dtype == np.float32
+        cfg = O.make_cfg(family, sa, "tsit5_fixed", N, t, 0.0, T, dt=dt, cost=cost, shared_p=shared_p)
+        ref = O.gradient(cfg, t, u0.astype(np.float32).astype(np.float64), np.asarray(p, dtype=np.float32).astype(np.float64),
+                         dLdu=None if dL is None else dL.astype(np.float32).astype(np.float64))
+        assert _rel(saved, ref["saved"]) < 2e-5
+        assert _rel(du0, ref["du0"]) < 2e-4, (cost[0], _rel(du0, ref["du0"]))
+        assert _rel(dp, ref["dp"]) < 2e-4, (cost[0], _rel(dp, ref["dp"]))
+        eng.close()
+
+
+def test_fp32_rejects_quadrature_and_continuous_cost():
+    t = np.linspace(0.0, 1.0, 11)
+    with pytest.raises(Exception):
+        b.DeviceEnsemble("lorenz", "quadrature", "tsit5_fixed", 64, t, (0.0, 1.0), 0.01, dtype="f32")
+    with pytest.raises(Exception):
+        b.DeviceEnsemble("robertson", "gauss", "tsit5_fixed", 64, t, (0.0, 1.0), 0.01, dtype="f32")
