@@ -123,6 +123,16 @@ int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_relto
  * Built for the fixed-step Tsit5 path; enabled = 0 switches it off. */
 int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b);
 
+/* Preset-time events of the hybrid system (DiscreteCallback / PresetTimeCallback of the reference with
+ * save_positions = (false, false); reverse-pass treatment of src/callback_tracking.jl:232-480): at each times[e] the state
+ * of every member becomes u <- scale[e][:] .* u + shift[e][:] ("u[1] += 2", "u[1] = 2" of
+ * test/Callbacks1/discrete_callbacks.jl:263-293 are (1, 2) and (0, 2)).  The event times become tstops of the forward and
+ * of the reverse solve; the reverse pass applies lam(tau-) = scale .* lam(tau+) after the loss jump of the same time (a
+ * save time that coincides with an event records the post-event state).  times ascending, strictly inside (t0, t1);
+ * host pointers; E = 0 removes the events.  Built for the adaptive Tsit5 stepper with Interpolating / Gauss / Backsolve
+ * (the reference's QuadratureAdjoint has no callback support either); call before b200adj_forward. */
+int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift);
+
 /* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
 int32_t b200adj_get_noise(void* handle, void* dW_out);
 

@@ -60,6 +60,14 @@ typedef struct {
     int32_t mlp_hidden;                     /* FAM_MLP: hidden width (64)                 */
     int32_t cont_cost;                      /* 1: continuous cost g(u) = ca/2 |u|^2 + cb sum(u) is present (accumulate_cost!) */
     double cont_a, cont_b;
+    /* preset-time events (DiscreteCallback / PresetTimeCallback with save_positions = (false,false), the hybrid-system
+     * adjoint of src/callback_tracking.jl:232-480 for the affine affect family u <- scale .* u + shift; same events for
+     * every member; times strictly inside (t0, t1), ascending; adaptive Tsit5 only).  A save time that coincides with
+     * an event time records the POST-event state (OrdinaryDiffEq saves after the affect when save_positions is false). */
+    int32_t n_events, _pad;
+    const double* ev_times;                 /* [E]    */
+    const double* ev_scale;                 /* [E][d] */
+    const double* ev_shift;                 /* [E][d] */
 } oracle_cfg;
 
 /* =====================================================================================
@@ -457,7 +465,7 @@ static void forward_tsit5_fixed(const family_t* F, const double* p, const double
 /* Adaptive Tsit5 forward solve (PI controller beta1=7/50, beta2=2/25, gamma=0.9, qmin=1/5, qmax=10;
  * [UPSTREAM OrdinaryDiffEq defaults], error norm = RMS of err/(abstol+reltol*max(|u|,|unew|))). */
 static int forward_tsit5_adaptive(const family_t* F, const double* p, const double* u0, double t0, double t1,
-                                  double abstol, double reltol, double dt0, dense_t* S) {
+                                  double abstol, double reltol, double dt0, dense_t* S, const oracle_cfg* evc) {
     int d = F->d; fwd_ctx c = {F, p, 0};
     dense_init(S, d, DENSE_TSIT5, 256);
     double* k = (double*)malloc(sizeof(double) * 7 * d), *tmp = (double*)malloc(sizeof(double) * d), *un = (double*)malloc(sizeof(double) * d);
@@ -465,10 +473,12 @@ static int forward_tsit5_adaptive(const family_t* F, const double* p, const doub
     fwd_rhs(t0, u0, k, &c);
     double t = t0, h = dt0 > 0 ? dt0 : 1e-3 * (t1 - t0), qold = 1e-4;
     int n = 0, iters = 0;
+    const int E = evc ? evc->n_events : 0; int ev = 0;      /* next event (tstop) ahead of t */
     while (t < t1) {
         if (++iters > 10000000) { free(k); free(tmp); free(un); return -1; }
         int last = 0;
-        if (t + h >= t1 || fabs(t + h - t1) < 100 * 2.22e-16 * fabs(t1)) { h = t1 - t; last = 1; }
+        const double tend = (ev < E) ? evc->ev_times[ev] : t1;      /* event times are tstops of the forward solve */
+        if (t + h >= tend || fabs(t + h - tend) < 100 * 2.22e-16 * fabs(tend)) { h = tend - t; last = 1; }
         dense_grow(S);
         const double* u = S->u + (size_t)n * d;
         tsit5_step(fwd_rhs, &c, d, t, h, u, k, un, tmp);
@@ -484,10 +494,16 @@ static int forward_tsit5_adaptive(const family_t* F, const double* p, const doub
         double q = q11 / pow(qold, 2.0 / 25.0);
         q = fmax(1.0 / 10.0, fmin(1.0 / (1.0 / 5.0), q / 0.9));
         if (EEst <= 1.0) {
-            memcpy(S->k + (size_t)n * 7 * d, k, sizeof(double) * 7 * d);
-            memcpy(S->u + (size_t)(n + 1) * d, un, sizeof(double) * d);
-            t = last ? t1 : t + h; S->t[n + 1] = t;
+            memcpy(S->k + (size_t)n * 7 * d, k, sizeof(double) * 7 * d);     /* k7 = f(u^-) stays with the step that ends at the event */
+            t = last ? tend : t + h; S->t[n + 1] = t;
             memcpy(k, k + 6 * d, sizeof(double) * d);
+            if (last && ev < E) {
+                /* affect!: u <- scale .* u + shift; the next step starts from the post-event state, FSAL re-evaluated */
+                for (int i = 0; i < d; i++) un[i] = evc->ev_scale[(size_t)ev * d + i] * un[i] + evc->ev_shift[(size_t)ev * d + i];
+                fwd_rhs(t, un, k, &c);
+                ev++;
+            }
+            memcpy(S->u + (size_t)(n + 1) * d, un, sizeof(double) * d);
             n++; S->n = n;
             qold = fmax(EEst, 1e-4);
             h = h / q;
@@ -595,6 +611,7 @@ typedef struct {
     double* y; double* dgtmp;
     long nrhs;
     int cont; double ca, cb;      /* continuous cost: dlam -= dgdu_continuous(y) (src/derivative_wrappers.jl:1411-1442) */
+    double tev;                   /* event time the reverse solve has just crossed: y(tev) is the LEFT limit from here on */
 } adj_ctx;
 
 /* z layout: Interp [lam(d); mu(P)], Gauss/Quad [lam(d)], Backsolve [lam(d); mu(P); y(d)] */
@@ -609,7 +626,7 @@ static void adj_rhs(double t, const double* z, double* dz, void* c) {
         if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca * y[i] + x->cb;
         (x->ito ? F->f_ito : F->f)(y, x->p, t, dz + d + P, &F->ctx);  /* dy = f(y) */
     } else {
-        dense_eval(x->sol, t, 1, x->y, NULL);              /* sol(y,t,continuity=:right) */
+        dense_eval(x->sol, t, t != x->tev, x->y, NULL);    /* sol(y,t,continuity=:right); the left limit at an event just crossed */
         if (x->sensealg == SA_INTERPOLATING) {
             vjp(x->y, x->p, t, z, dz, dz + d, &F->ctx);
             for (int i = 0; i < d + P; i++) dz[i] = -dz[i];  /* interpolating_adjoint.jl:166-170 */
@@ -764,7 +781,9 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     double* k = (double*)malloc(sizeof(double) * 7 * L);
     double* ybuf = (double*)malloc(sizeof(double) * (d + 2 * P + 4 * d + 8));
     double* gu = ybuf + d, *lamq = gu + d, *dlq = lamq + d, *integ = dlq + d, *acc = integ + P;
-    adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0, cfg->cont_cost, cfg->cont_a, cfg->cont_b};
+    adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0, cfg->cont_cost, cfg->cont_a, cfg->cont_b, INFINITY};
+    int evc = cfg->n_events - 1;     /* next event below t */
+    if (cfg->n_events > 0 && (cfg->stepper != ST_TSIT5_ADAPTIVE || sa == SA_QUADRATURE)) return -11;
     for (int q = 0; q < P; q++) acc[q] = 0;
     adjdense_t adj; int have_adj = (sa == SA_QUADRATURE);
     if (have_adj) adjdense_init(&adj, L, ros ? DENSE_ROS23 : DENSE_TSIT5);
@@ -793,8 +812,17 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
             if (ck >= 0 && fabs(sol->t[ck] - (tt)) <= 100 * 2.220446049250313e-16 * fmax(fabs(tt), 1.0)) { \
                 memcpy(z + d + P, sol->u + (size_t)ck * d, sizeof(double) * d); fsal_ok = 0; }             \
         } else if (cur >= 0 && fabs(ts[cur] - (tt)) <= 100 * 2.220446049250313e-16 * fmax(fabs(tt), 1.0)) { \
-            dense_eval(sol, ts[cur], 0, z + d + P, NULL); fsal_ok = 0;                                     \
+            dense_eval(sol, ts[cur], (evc >= 0 && cfg->ev_times[evc] == ts[cur]), z + d + P, NULL); fsal_ok = 0; /* post-event state at a coinciding event */ \
         }                                                                                                  \
+    }
+    /* reverse affect of a preset-time event (callback_tracking.jl:232-480 for u <- s .* u + c): lam(tau-) = s .* lam(tau+);
+     * Backsolve takes y(tau-) from the forward solution (the reference stores it as `uleft` in the TrackedAffect).
+     * Runs after the checkpoint reset and the loss jump of the same time (the saved state at tau is post-event). */
+#define APPLY_EVENT_IF_AT(tt)                                                                              \
+    while (evc >= 0 && fabs(cfg->ev_times[evc] - (tt)) <= 100 * 2.220446049250313e-16 * fmax(fabs(tt), 1.0)) { \
+        for (int i = 0; i < d; i++) z[i] *= cfg->ev_scale[(size_t)evc * d + i];                            \
+        if (sa == SA_BACKSOLVE) dense_eval(sol, cfg->ev_times[evc], 0, z + d + P, NULL);                   \
+        ctx.tev = (tt); evc--; fsal_ok = 0;                                                                \
     }
     int fsal_ok = 0;
     APPLY_CKPT_IF_AT(t);
@@ -810,6 +838,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
            per-step checkpoints every forward knot is a tstop as well. */
         double tstop = t0;
         if (cur >= 0 && ts[cur] < t && ts[cur] > tstop) tstop = ts[cur];
+        if (evc >= 0 && cfg->ev_times[evc] < t && cfg->ev_times[evc] > tstop) tstop = cfg->ev_times[evc];
         if (sa == SA_BACKSOLVE && cfg->checkpointing && cfg->backsolve_ckpt_every_step) {
             int c2 = ck; while (c2 >= 0 && sol->t[c2] >= t - 100 * 2.220446049250313e-16 * fmax(fabs(t), 1.0)) c2--;
             if (c2 >= 0 && sol->t[c2] > tstop) tstop = sol->t[c2];
@@ -868,6 +897,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
         if (!adaptive) h = -fabs(cfg->dt);
         APPLY_CKPT_IF_AT(t);
         APPLY_JUMP_IF_AT(t);
+        APPLY_EVENT_IF_AT(t);
     }
     if (rc == 0) {
         for (int i = 0; i < d; i++) du0[i] = z[i];
@@ -990,7 +1020,7 @@ static int is_sde(const oracle_cfg* c) { return c->stepper == ST_EM || c->steppe
 static int forward_dense_member(const oracle_cfg* cfg, const family_t* F, const double* p, const double* u0, dense_t* S) {
     switch (cfg->stepper) {
     case ST_TSIT5_FIXED: forward_tsit5_fixed(F, p, u0, cfg->t0, cfg->t1, cfg->dt, S); return 0;
-    case ST_TSIT5_ADAPTIVE: return forward_tsit5_adaptive(F, p, u0, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, cfg->dt, S);
+    case ST_TSIT5_ADAPTIVE: return forward_tsit5_adaptive(F, p, u0, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, cfg->dt, S, cfg);
     case ST_ROSENBROCK23: return forward_ros23(F, p, u0, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, S);
     default: return -5;
     }
@@ -1025,7 +1055,11 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
             if (r == 0) {
                 if (steps_out) steps_out[i] = sol.n;
                 double y[8];
-                if (saved) for (int k = 0; k < K; k++) { dense_eval(&sol, saveat[k], 0, y, NULL); for (int j = 0; j < d; j++) saved[((size_t)k * d + j) * N + i] = y[j]; }
+                if (saved) for (int k = 0; k < K; k++) {
+                    int at_ev = 0;
+                    for (int e = 0; e < cfg->n_events; e++) if (cfg->ev_times[e] == saveat[k]) at_ev = 1;
+                    dense_eval(&sol, saveat[k], at_ev, y, NULL);
+                    for (int j = 0; j < d; j++) saved[((size_t)k * d + j) * N + i] = y[j]; }
                 if (du0) {
                     if (cfg->cost_kind == COST_EXPLICIT) {
                         dLm = (double*)malloc(sizeof(double) * K * d);

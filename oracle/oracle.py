@@ -31,6 +31,8 @@ class OracleCfg(C.Structure):
         ("shared_p", C.c_int32), ("no_start", C.c_int32), ("checkpointing", C.c_int32),
         ("backsolve_ckpt_every_step", C.c_int32), ("mlp_hidden", C.c_int32), ("cont_cost", C.c_int32),
         ("cont_a", C.c_double), ("cont_b", C.c_double),
+        ("n_events", C.c_int32), ("_pad", C.c_int32),
+        ("ev_times", C.c_void_p), ("ev_scale", C.c_void_p), ("ev_shift", C.c_void_p),
     ]
 
 
@@ -60,7 +62,7 @@ def _ptr(a):
 
 def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, reltol=1e-3, quad_abstol=1e-10,
              quad_reltol=1e-10, cost=("explicit",), shared_p=True, no_start=False, checkpointing=True,
-             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None):
+             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None):
     if family == "mlp":
         d = 2
         H = mlp_hidden
@@ -81,6 +83,12 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
     cfg.backsolve_ckpt_every_step, cfg.mlp_hidden = int(ckpt_every_step), mlp_hidden
     if cont_cost is not None:      # continuous cost g(u) = a/2 |u|^2 + b sum(u)
         cfg.cont_cost, cfg.cont_a, cfg.cont_b = 1, float(cont_cost[0]), float(cont_cost[1])
+    if events is not None:         # preset-time events: (times[E], scale[E, d], shift[E, d]), u <- scale * u + shift
+        et, es, ec = (np.ascontiguousarray(x, dtype=np.float64) for x in events)
+        assert es.shape == (len(et), d) and ec.shape == (len(et), d)
+        cfg._keep = (et, es, ec)   # the struct holds raw pointers
+        cfg.n_events = len(et)
+        cfg.ev_times, cfg.ev_scale, cfg.ev_shift = et.ctypes.data, es.ctypes.data, ec.ctypes.data
     return cfg
 
 

@@ -10,7 +10,7 @@ from .concrete_solve import (ChainRulesOriginator, NoTangent, ReverseDiffOrigina
                              _concrete_solve_adjoint, solve)
 from .distributed import allreduce_dp, shard_bounds
 from .engine import DeviceEnsemble
-from .problems import (EM, AdjointSensitivityParameterCompatibilityError, AffineCost, EnsembleB200, EnsembleProblem,
+from .problems import (EM, AdjointSensitivityParameterCompatibilityError, AffineAffect, AffineCost, PresetTimeCallback, EnsembleB200, EnsembleProblem,
                        EnsembleSolution, EulerHeun, FAMILIES, ODEProblem, QuadraticRunningCost, Rosenbrock23, SDEProblem, Tsit5)
 from .sensitivity_algorithms import (B200Adjoint, B200VJP, BacksolveAdjoint, EnzymeVJP, GaussAdjoint,
                                      InterpolatingAdjoint, MooncakeVJP, QuadratureAdjoint, ReactantVJP,

@@ -21,7 +21,7 @@ COST = {"explicit": 0, "affine": 1}
 FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE = 1, 2, 4, 8, 16
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
-EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_get_noise", "b200adj_set_stream",
+EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_events", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg"]
 
@@ -94,6 +94,8 @@ def load():
         lib.b200adj_set_tolerances.restype = C.c_int32
         lib.b200adj_set_continuous_cost.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double]
         lib.b200adj_set_continuous_cost.restype = C.c_int32
+        lib.b200adj_set_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200adj_set_events.restype = C.c_int32
         lib.b200adj_get_noise.argtypes = [C.c_void_p, C.c_void_p]
         lib.b200adj_get_noise.restype = C.c_int32
         lib.b200adj_set_stream.argtypes = [C.c_void_p, C.c_void_p]
@@ -168,6 +170,15 @@ class Handle:
 
     def set_continuous_cost(self, enabled, a=0.0, b=0.0):
         self._check(self._lib.b200adj_set_continuous_cost(self._h, int(bool(enabled)), float(a), float(b)))
+
+    def set_events(self, times, scale, shift):
+        """Preset-time events u <- scale[e] * u + shift[e] at times[e] (host arrays; empty = none)."""
+        import numpy as np
+        t = np.ascontiguousarray(times, dtype=np.float64).reshape(-1)
+        E = len(t)
+        sc = np.ascontiguousarray(scale, dtype=np.float64).reshape(E, -1)
+        sh = np.ascontiguousarray(shift, dtype=np.float64).reshape(E, -1)
+        self._check(self._lib.b200adj_set_events(self._h, E, t.ctypes.data if E else None, sc.ctypes.data if E else None, sh.ctypes.data if E else None))
 
     def step_counts(self, fwd, rev):
         self._check(self._lib.b200adj_get_step_counts(self._h, _addr(fwd), _addr(rev)))

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import distributed
 from .engine import DeviceEnsemble, _is_torch
-from .problems import (EM, AffineCost, EnsembleB200, EnsembleProblem, EnsembleSolution, EulerHeun, FAMILIES, ODEProblem,
+from .problems import (EM, AffineCost, PresetTimeCallback, EnsembleB200, EnsembleProblem, EnsembleSolution, EulerHeun, FAMILIES, ODEProblem,
                        Rosenbrock23, SDEProblem, Tsit5, saveat_to_times)
 from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, InterpolatingAdjoint,
                                      QuadratureAdjoint, sensealg_name)
@@ -77,8 +77,17 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
         eprob = EnsembleProblem(eprob)
     ensemblealg = ensemblealg or EnsembleB200()
     prob = eprob.prob
-    if prob.callback is not None or "callback" in kwargs:
-        raise NotImplementedError("callbacks are not supported on the B200 path (SURVEY.md App. E)")
+    callback = kwargs.pop("callback", None) or prob.callback
+    if callback is not None:
+        # the device path carries one callback family: preset-time affine affects on the adaptive Tsit5 stepper
+        if not isinstance(callback, PresetTimeCallback):
+            raise NotImplementedError("callbacks: only PresetTimeCallback(tstops, AffineAffect) is carried on the B200 path "
+                                      "(SURVEY.md App. E); delegate other callbacks to the reference implementation")
+        if tuple(callback.save_positions) != (False, False):
+            raise NotImplementedError("PresetTimeCallback: save_positions = (false, false) only")
+        if not (isinstance(alg, Tsit5) and alg.adaptive):
+            raise NotImplementedError("PresetTimeCallback: built for the adaptive Tsit5 stepper")
+    kwargs.pop("tstops", None)                     # the callback's own times are the tstops
     if getattr(prob, "mass_matrix", None) is not None:
         raise NotImplementedError("mass matrices / DAEs are not supported on the B200 path")
     if prob.f not in FAMILIES:
@@ -121,8 +130,10 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else (sensealg or InterpolatingAdjoint())
     block = getattr(sensealg, "block_threads", 0) if isinstance(sensealg, B200Adjoint) else 0
     stored = getattr(sensealg, "stored_noise", False) if isinstance(sensealg, B200Adjoint) else False
+    ev = callback.tables(d) if callback is not None else None
     key = (prob.f, alg.code, hi - lo, ts.tobytes(), tuple(prob.tspan), _step_size(alg, kwargs), shared_p, on_device, device,
-           getattr(prob, "seed", 0), lo, block, stored, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3))
+           getattr(prob, "seed", 0), lo, block, stored, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3),
+           None if ev is None else tuple(x.tobytes() for x in ev))
     eng = _HANDLE_CACHE.get(key) if ensemblealg.reuse_handle else None
     if eng is None:
         eng = DeviceEnsemble(prob.f, sensealg_name(inner), alg.code, hi - lo, ts, prob.tspan, _step_size(alg, kwargs),
@@ -131,6 +142,8 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
                              quad_abstol=getattr(inner, "abstol", 1e-6), quad_reltol=getattr(inner, "reltol", 1e-3),
                              abstol=kwargs.get("abstol", 1e-6), reltol=kwargs.get("reltol", 1e-3),
                              max_steps=kwargs.get("maxiters", 0), pin_outputs=ensemblealg.pin_outputs)
+        if ev is not None:
+            eng.set_events(*ev)
         if ensemblealg.reuse_handle:
             _HANDLE_CACHE[key] = eng
     dW = getattr(prob, "noise", None)

@@ -54,6 +54,7 @@ struct Handle {
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
     const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
+    int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr;      // preset-time events (adaptive Tsit5)
     bool have_forward = false;
     bool noise_valid = false;
     int64_t launches = 0;
@@ -336,6 +337,7 @@ T5aArgs t5a_args(Handle* h) {
                           0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
     memcpy(a.A, A, sizeof(A)); memcpy(a.C, C, sizeof(C)); memcpy(a.BT, BT, sizeof(BT));
     tsit5_weights(0.0, nullptr, a.R);
+    a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c;
     return a;
 }
 template <class Fam>
@@ -441,7 +443,7 @@ void free_all(Handle* h) {
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
     cudaFree(h->d_tapeA); cudaFree(h->d_tapeB); cudaFree(h->d_umma_partials); cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
-    cudaFree(h->s_status);
+    cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -653,6 +655,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (h->nev > 0 && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: QuadratureAdjoint has no callback support"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.dtype == B200ADJ_F32 && c.rhs_family != B200ADJ_FAM_MLP && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "F32: QuadratureAdjoint is F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
@@ -706,6 +709,31 @@ int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, dou
     if (enabled && (h->adaptive || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
         h->err = "continuous cost: built for the fixed-step Tsit5 ODE path only"; return B200ADJ_ERR_UNSUPPORTED; }
     h->cont_on = enabled != 0; h->cont_a = a; h->cont_b = b;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    if (E < 0 || (E > 0 && (!times || !scale || !shift))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
+    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) { h->err = "events: built for the adaptive Tsit5 stepper"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (E > 0 && c.sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: Interpolating / Gauss / Backsolve (QuadratureAdjoint has no callback support)"; return B200ADJ_ERR_UNSUPPORTED; }
+    for (int e = 0; e < E; e++)
+        if (!(times[e] > c.t0 && times[e] < c.t1) || (e > 0 && !(times[e] > times[e - 1]))) { h->err = "events: times must be ascending and strictly inside (t0, t1)"; return B200ADJ_ERR_INVALID; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c);
+    h->d_ev_t = h->d_ev_s = h->d_ev_c = nullptr; h->nev = 0; h->have_forward = false;
+    if (E > 0) {
+        CUDA_TRY(h, cudaMalloc(&h->d_ev_t, (size_t)E * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->d_ev_s, (size_t)E * c.d * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->d_ev_c, (size_t)E * c.d * sizeof(double)));
+        CUDA_TRY(h, cudaMemcpy(h->d_ev_t, times, (size_t)E * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->d_ev_s, scale, (size_t)E * c.d * sizeof(double), cudaMemcpyHostToDevice));
+        CUDA_TRY(h, cudaMemcpy(h->d_ev_c, shift, (size_t)E * c.d * sizeof(double), cudaMemcpyHostToDevice));
+        h->nev = E;
+    }
     return B200ADJ_OK;
 }
 

@@ -26,6 +26,9 @@ struct T5aArgs {
     int64_t N; int32_t K; int32_t maxs;
     double t0, t1, dt0, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
     uint32_t flags;
+    // preset-time events u <- scale .* u + shift (the hybrid-system adjoint of src/callback_tracking.jl:232-480 for the
+    // affine affect family, save_positions = (false, false)): same events for every member, times ascending in (t0, t1)
+    int32_t nev; const double* ev_t; const double* ev_s; const double* ev_c;      // [E], [E][D], [E][D]
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
     double BT[7];           // embedded error weights b - bhat
@@ -118,18 +121,22 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
         for (int j = 0; j < D; j++) a.saved[((int64_t)ksave * D + j) * N + i] = u[j];
         ksave++;
     }
+    int ev = 0;                                   // next event ahead of t (event times are tstops of the forward solve)
     while (t < a.t1) {
         if (++iters > 10000000L || n >= a.maxs) { stat = 2; break; }
         bool last = false;
-        if (t + h >= a.t1 || fabs(t + h - a.t1) < 100 * 2.22e-16 * fabs(a.t1)) { h = a.t1 - t; last = true; }
+        const double tend = ev < a.nev ? a.ev_t[ev] : a.t1;
+        if (t + h >= tend || fabs(t + h - tend) < 100 * 2.22e-16 * fabs(tend)) { h = tend - t; last = true; }
         t5_step<D>(a, rhs, t, h, u, k, un);
         const double EEst = t5_error<D>(a, h, u, un, k);
         const double q11 = pow(fmax(EEst, 1e-300), 7.0 / 50.0);
         double q = q11 / pow(qold, 2.0 / 25.0);
         q = fmax(1.0 / 10.0, fmin(5.0, q / 0.9));
         if (EEst <= 1.0) {
-            const double tn = last ? a.t1 : t + h;
-            while (a.saved && ksave < a.K && a.saveat[ksave] <= tn) {
+            const double tn = last ? tend : t + h;
+            const bool at_event = last && ev < a.nev;
+            // a save time that coincides with an event records the post-event state (saved after the affect, below)
+            while (a.saved && ksave < a.K && (a.saveat[ksave] < tn || (a.saveat[ksave] == tn && !at_event))) {
                 const double hh = tn - t, th = (hh == 0.0) ? 1.0 : (a.saveat[ksave] - t) / hh;
                 double w[7];
                 t5_weights(a, th, w);
@@ -146,6 +153,18 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
             for (int s = 0; s < 7; s++)
 #pragma unroll
                 for (int j = 0; j < D; j++) a.fk[(((int64_t)n * 7 + s) * D + j) * N + i] = k[s][j];
+            if (at_event) {
+                // affect!: the next step starts from the post-event state; k7 = f(u^-) stays with the step just stored
+#pragma unroll
+                for (int j = 0; j < D; j++) un[j] = a.ev_s[ev * D + j] * un[j] + a.ev_c[ev * D + j];
+                Fam::f(un, p, k[6]);
+                ev++;
+                while (a.saved && ksave < a.K && a.saveat[ksave] == tn) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) a.saved[((int64_t)ksave * D + j) * N + i] = un[j];
+                    ksave++;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < D; j++) { a.fu[((int64_t)(n + 1) * D + j) * N + i] = un[j]; u[j] = un[j]; k[0][j] = k[6][j]; }
             t = tn; a.ft[(int64_t)(n + 1) * N + i] = t;
@@ -184,13 +203,14 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     double z[L], zn[L], k[7][L];
 #pragma unroll
     for (int c = 0; c < L; c++) z[c] = 0.0;
+    double tev = INFINITY;                        // event time just crossed (y(tev) = left limit from there on)
     // adjoint RHS: dlam = -J(y(t))' lam, dmu = -F(y(t))' lam  (right-continuous forward lookup)
     auto rhs = [&](double tt, const double* x, double* dx) {
         double y[D];
         if (SA == SA_BACKSOLVE) {
 #pragma unroll
             for (int j = 0; j < D; j++) y[j] = x[YO + j];          // y is part of the state
-        } else sol.eval(tt, true, y);
+        } else sol.eval(tt, tt != tev, y);                         // the left limit at an event the solve has just crossed
         Fam::vjp_u(y, p, x, dx);
 #pragma unroll
         for (int j = 0; j < D; j++) dx[j] = -dx[j];
@@ -204,7 +224,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     };
     const double T = a.t1, t0 = a.t0;
     double t = T;
-    int cur = a.K - 1, nrev = 0, ck = sol.n;
+    int cur = a.K - 1, nrev = 0, ck = sol.n, evc = a.nev - 1;
     bool fsal_ok = false, overflow = false;
     const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
     if (SA == SA_BACKSOLVE) {
@@ -224,10 +244,25 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
             }
         } else if (cur >= 0 && fabs(a.saveat[cur] - tt) <= tol) {
             double y[D];
-            sol.eval(a.saveat[cur], false, y);
+            sol.eval(a.saveat[cur], evc >= 0 && a.ev_t[evc] == a.saveat[cur], y);      // post-event state at a coinciding event
 #pragma unroll
             for (int j = 0; j < D; j++) z[YO + j] = y[j];
             fsal_ok = false;
+        }
+    };
+    // reverse affect of a preset-time event: lam(tau-) = scale .* lam(tau+); Backsolve takes y(tau-) from the forward
+    // solution (the reference keeps it as `uleft` of the TrackedAffect).  Runs after the checkpoint reset and the loss jump.
+    auto event_if_at = [&](double tt) {
+        while (evc >= 0 && fabs(a.ev_t[evc] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
+#pragma unroll
+            for (int j = 0; j < D; j++) z[j] *= a.ev_s[evc * D + j];
+            if (SA == SA_BACKSOLVE) {
+                double y[D];
+                sol.eval(a.ev_t[evc], false, y);
+#pragma unroll
+                for (int j = 0; j < D; j++) z[YO + j] = y[j];
+            }
+            tev = tt; evc--; fsal_ok = false;
         }
     };
     auto jump_if_at = [&](double tt) {
@@ -258,6 +293,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) { overflow = true; break; }
         double tstop = t0;
         if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
+        if (evc >= 0 && a.ev_t[evc] < t && a.ev_t[evc] > tstop) tstop = a.ev_t[evc];
         if (SA == SA_BACKSOLVE && ckpt_on && every) {            // every forward knot is a tstop of the reverse solve
             int c2 = ck;
             while (c2 >= 0 && sol.T(c2) >= t - EPS100 * fmax(fabs(t), 1.0)) c2--;
@@ -309,6 +345,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         t = tn;
         ckpt_if_at(t);
         jump_if_at(t);
+        event_if_at(t);
     }
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
     if (active) {

@@ -51,6 +51,7 @@ class DeviceEnsemble:
         self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
         self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)
         self.adaptive = stepper in ("rosenbrock23", "tsit5_adaptive")
+        self.events = None
         self.S = 0 if self.adaptive else int(round((cfg.t1 - cfg.t0) / cfg.dt))
         self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
         self.handle = _lib.Handle(cfg, self.saveat)
@@ -116,6 +117,18 @@ class DeviceEnsemble:
         dp = dp_out if dp_out is not None else (self._empty(self.P) if self.shared_p else self._empty(self.P, self.N))
         self.handle.reverse(dLdu, du0, dp)
         return du0, dp
+
+    def set_events(self, times, scale, shift):
+        """Preset-time events of the hybrid system (adaptive Tsit5): u <- scale[e] * u + shift[e] at times[e]; call
+        before forward()."""
+        times = np.asarray(times, dtype=np.float64).reshape(-1)
+        E = len(times)
+        scale = np.asarray(scale, dtype=np.float64).reshape(E, -1) if E else np.zeros((0, self.d))
+        shift = np.asarray(shift, dtype=np.float64).reshape(E, -1) if E else np.zeros((0, self.d))
+        if E and (scale.shape[1] != self.d or shift.shape[1] != self.d):
+            raise ValueError("events: scale and shift must be [E, d]")
+        self.handle.set_events(times, scale, shift)
+        self.events = (times, scale, shift)
 
     def set_reverse(self, sensealg, cost=None, no_start=False, checkpointing=True, ckpt_every_step=False, t=None):
         """Re-target the next reverse pass (sensealg / cost / save times) without re-running the forward pass."""

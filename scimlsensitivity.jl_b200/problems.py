@@ -7,7 +7,7 @@ code for f and its VJPs is hand-written per family (csrc/families.cuh), which is
 `ODEFunction(f; vjp, vjp_p)` occupies in the reference (src/derivative_wrappers.jl:284-359).
 """
 from dataclasses import dataclass, field
-from typing import Any, Callable, Optional, Sequence
+from typing import Any, Callable, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -152,3 +152,34 @@ def saveat_to_times(saveat, tspan):
             ts[-1] = t1
         return ts
     return np.sort(np.asarray(saveat, dtype=np.float64))
+
+
+# ---- callbacks: the named affect family the device path carries ---------------------------------
+@dataclass(frozen=True)
+class AffineAffect:
+    """affect!(integrator): integrator.u .= scale .* integrator.u .+ shift  (per component).  "u[1] += 2" is
+    AffineAffect(scale=[1, 1], shift=[2, 0]); "u[1] = 2" is AffineAffect(scale=[0, 1], shift=[2, 0])
+    (test/Callbacks1/discrete_callbacks.jl:263-293)."""
+    scale: Any
+    shift: Any
+
+
+@dataclass(frozen=True)
+class PresetTimeCallback:
+    """DiffEqCallbacks.PresetTimeCallback(tstops, affect!) / a DiscreteCallback with condition `t in tstops` and those
+    tstops passed to solve: the affect fires at the preset times, which become tstops of the forward and reverse solves.
+    `affect` is one AffineAffect for every time or a list with one per time.  save_positions = (false, false) is the only
+    mode carried on the device (no extra saved points)."""
+    tstops: Any
+    affect: Any
+    save_positions: Tuple[bool, bool] = (False, False)
+
+    def tables(self, d):
+        t = np.asarray(self.tstops, dtype=np.float64).reshape(-1)
+        order = np.argsort(t, kind="stable")
+        aff = self.affect if isinstance(self.affect, (list, tuple)) else [self.affect] * len(t)
+        if len(aff) != len(t):
+            raise ValueError("PresetTimeCallback: one affect per time (or a single affect)")
+        sc = np.stack([np.broadcast_to(np.asarray(a.scale, dtype=np.float64), (d,)) for a in aff]) if len(t) else np.zeros((0, d))
+        sh = np.stack([np.broadcast_to(np.asarray(a.shift, dtype=np.float64), (d,)) for a in aff]) if len(t) else np.zeros((0, d))
+        return t[order], sc[order], sh[order]

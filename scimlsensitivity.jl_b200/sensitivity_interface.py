@@ -40,9 +40,13 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else sensealg
     if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint)):
         raise TypeError("adjoint_sensitivities: sensealg must be one of the continuous adjoints")
-    if callback is not None or getattr(sol.prob.prob if hasattr(sol.prob, "prob") else sol.prob, "callback", None) is not None:
-        raise NotImplementedError("callbacks/events are not supported on the B200 path (SURVEY.md App. E): "
-                                  "delegate to the reference implementation")
+    # events: the forward solution carries them (PresetTimeCallback passed to solve, like the reference's tracked callbacks
+    # inside sol.prob.kwargs); a different callback for the reverse pass alone is meaningless
+    if callback is not None and getattr(sol.engine, "events", None) is None:
+        raise NotImplementedError("pass the PresetTimeCallback to solve(); other callbacks/events are not carried on the "
+                                  "B200 path (SURVEY.md App. E): delegate to the reference implementation")
+    if getattr(sol.engine, "events", None) is not None and isinstance(inner, QuadratureAdjoint):
+        raise NotImplementedError("QuadratureAdjoint does not support callbacks")
     if dgdp_continuous is not None or g is not None:
         raise NotImplementedError("dgdp_continuous / g are not built on the B200 path (named cost families only)")
     if dgdu_continuous is not None and not isinstance(dgdu_continuous, QuadraticRunningCost):

@@ -1,0 +1,101 @@
+"""Preset-time events (DiscreteCallback / PresetTimeCallback) on the adaptive Tsit5 path: device vs oracle, and the
+reference's own relations (test/Callbacks1/discrete_callbacks.jl:200-231): every sensealg agrees with differentiation
+through the solver, Backsolve == Interpolating == Gauss."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import scimlsensitivity_jl_b200 as b
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, ref):
+    return float(np.max(np.abs(np.asarray(a) - ref)) / (np.max(np.abs(ref)) + 1e-300))
+
+
+CASES = {
+    # affect!(integrator) = integrator.u[1] += 2.0 at t == 5            (discrete_callbacks.jl:263-269)
+    "add_single": ([5.0], [[1.0, 1.0]], [[2.0, 0.0]]),
+    # affecttimes = [2.03, 4.0, 8.0], u[1] += 2.0                        (:270-276)
+    "add_multi": ([2.03, 4.0, 8.0], [[1.0, 1.0]] * 3, [[2.0, 0.0]] * 3),
+    # integrator.u[1] = 2.0 at t == 5                                    (:286-292)
+    "set_single": ([5.0], [[0.0, 1.0]], [[2.0, 0.0]]),
+    # callbacks with no effect                                           (:249-262)
+    "no_effect": ([5.0], [[1.0, 1.0]], [[0.0, 0.0]]),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("sa,every", [("interpolating", False), ("gauss", False), ("backsolve", True), ("backsolve", False)])
+def test_events_device_vs_oracle(case, sa, every):
+    ev = CASES[case]
+    N = 40
+    rng = np.random.default_rng(11)
+    u0 = 1.0 + 0.05 * rng.standard_normal((2, N))
+    p = np.array([1.5, 1.0, 3.0, 1.0])
+    t = np.arange(0.0, 10.0001, 0.5)                     # savingtimes = 0.5; t = 5 and 4, 8 coincide with events
+    tol = dict(abstol=1e-10, reltol=1e-10)
+    eng = b.DeviceEnsemble("lv", sa, "tsit5_adaptive", N, t, (0.0, 10.0), 0.0, cost=b.AffineCost(0.0, 1.0), ckpt_every_step=every,
+                           max_steps=8192, **tol)
+    eng.set_events(*ev)
+    saved, status = eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    cfg = O.make_cfg("lv", sa, "tsit5_adaptive", N, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), ckpt_every_step=every, events=ev, **tol)
+    ref = O.gradient(cfg, t, u0, p)
+    assert (np.asarray(status) == 0).all()
+    assert _rel(saved, ref["saved"]) < 1e-9
+    assert _rel(du0, ref["du0"]) < 1e-7 and _rel(dp, ref["dp"]) < 1e-7
+    # the saved state AT an event time is the post-event state
+    if case == "set_single":
+        assert np.allclose(np.asarray(saved)[10, 0, :], 2.0, atol=1e-12)
+    eng.close()
+
+
+def test_events_match_differentiation_through_the_solver():
+    """g(sol) = sum(sol): gradient == finite differences of the loss through the (oracle) solver, all sensealgs equal."""
+    ev = CASES["add_multi"]
+    t = np.arange(0.0, 10.0001, 0.5)
+    u0 = np.ones((2, 1)); p = np.array([1.5, 1.0, 3.0, 1.0])
+    tol = dict(abstol=1e-12, reltol=1e-12)
+    lcfg = O.make_cfg("lv", "interpolating", "tsit5_adaptive", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), events=ev, **tol)
+    e = 1e-6
+    fd_p = np.array([(O.loss(lcfg, t, u0, p + e * np.eye(4)[q])[0] - O.loss(lcfg, t, u0, p - e * np.eye(4)[q])[0]) / (2 * e) for q in range(4)])
+    fd_u = np.array([(O.loss(lcfg, t, u0 + e * np.eye(2)[j][:, None], p)[0] - O.loss(lcfg, t, u0 - e * np.eye(2)[j][:, None], p)[0]) / (2 * e) for j in range(2)])
+    res = {}
+    for sa in ("interpolating", "gauss", "backsolve"):
+        eng = b.DeviceEnsemble("lv", sa, "tsit5_adaptive", 1, t, (0.0, 10.0), 0.0, cost=b.AffineCost(0.0, 1.0), ckpt_every_step=True,
+                               max_steps=16384, **tol)
+        eng.set_events(*ev)
+        eng.forward(u0, p)
+        du0, dp = eng.reverse()
+        assert _rel(dp, fd_p) < 1e-6 and _rel(np.asarray(du0)[:, 0], fd_u) < 1e-6, sa
+        res[sa] = (np.asarray(du0).copy(), np.asarray(dp).copy())
+        eng.close()
+    assert _rel(res["backsolve"][1], res["interpolating"][1]) < 1e-7          # du01 ~ du03 rtol 1e-7 (:222-232)
+    assert _rel(res["gauss"][1], res["interpolating"][1]) < 1e-7
+
+
+def test_events_public_api_and_rejections():
+    t = np.arange(0.0, 10.0001, 0.5)
+    prob = b.ODEProblem("lv", np.ones(2), (0.0, 10.0), np.array([1.5, 1.0, 3.0, 1.0]))
+    cb = b.PresetTimeCallback([5.0], b.AffineAffect([1.0, 1.0], [2.0, 0.0]))
+    sol = b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=True), b.EnsembleB200(), trajectories=3, saveat=t, callback=cb, abstol=1e-10, reltol=1e-10)
+    du0, dp = b.adjoint_sensitivities(sol, b.Tsit5(adaptive=True), sensealg=b.InterpolatingAdjoint(), t=t, dgdu_discrete=b.AffineCost(0.0, 1.0),
+                                      abstol=1e-10, reltol=1e-10)
+    cfg = O.make_cfg("lv", "interpolating", "tsit5_adaptive", 3, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), abstol=1e-10, reltol=1e-10,
+                     events=([5.0], [[1.0, 1.0]], [[2.0, 0.0]]))
+    ref = O.gradient(cfg, t, np.ones((2, 3)), np.array([1.5, 1.0, 3.0, 1.0]))
+    assert _rel(np.asarray(dp).reshape(-1), ref["dp"]) < 1e-7
+    with pytest.raises(NotImplementedError):
+        b.adjoint_sensitivities(sol, b.Tsit5(adaptive=True), sensealg=b.QuadratureAdjoint(), t=t, dgdu_discrete=b.AffineCost(0.0, 1.0))
+    with pytest.raises(NotImplementedError):
+        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=False, dt=0.01), b.EnsembleB200(), trajectories=3, saveat=t, callback=cb)
+    with pytest.raises(Exception):       # event time outside (t0, t1)
+        eng = b.DeviceEnsemble("lv", "gauss", "tsit5_adaptive", 4, t, (0.0, 10.0), 0.0)
+        eng.set_events([10.0], [[1.0, 1.0]], [[0.0, 0.0]])

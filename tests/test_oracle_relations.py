@@ -296,3 +296,36 @@ def test_continuous_cost_all_sensealgs_match_differentiation_of_the_integral():
     gp = _fd_grad(lambda p: O.loss(cfg, saveat, LV_U0, p)[0], LV_P)
     gu = _fd_grad(lambda u: O.loss(cfg, saveat, u, LV_P)[0], LV_U0)
     assert np.allclose(res["interpolating"]["dp"], gp, rtol=1e-8) and np.allclose(res["interpolating"]["du0"], gu, rtol=1e-8)
+
+
+# ---- preset-time events (hybrid-system adjoint; test/Callbacks1/discrete_callbacks.jl:200-231, :249-293) -------------
+@pytest.mark.parametrize("events", [
+    ([5.0], [[1.0, 1.0]], [[2.0, 0.0]]),                       # u[1] += 2 at t == 5
+    ([2.03, 4.0, 8.0], [[1.0, 1.0]] * 3, [[2.0, 0.0]] * 3),      # at multiple time points
+    ([5.0], [[0.0, 1.0]], [[2.0, 0.0]]),                       # u[1] = 2
+])
+def test_event_adjoint_equals_differentiation_through_the_solver(events):
+    """g(sol) = sum(sol) with saveat 0.5 on LV, adaptive Tsit5 at 1e-12: every sensealg reproduces the finite-difference
+    gradient of the loss through the hybrid solve, and Backsolve / Gauss agree with Interpolating at rtol 1e-7."""
+    t = np.arange(0.0, 10.0001, 0.5)
+    u0 = np.ones((2, 1)); p = np.array([1.5, 1.0, 3.0, 1.0])
+    tol = dict(abstol=1e-12, reltol=1e-12)
+    lcfg = O.make_cfg("lv", "interpolating", "tsit5_adaptive", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), events=events, **tol)
+    e = 1e-6
+    fd_p = np.array([(O.loss(lcfg, t, u0, p + e * np.eye(4)[q])[0] - O.loss(lcfg, t, u0, p - e * np.eye(4)[q])[0]) / (2 * e) for q in range(4)])
+    fd_u = np.array([(O.loss(lcfg, t, u0 + e * np.eye(2)[j][:, None], p)[0] - O.loss(lcfg, t, u0 - e * np.eye(2)[j][:, None], p)[0]) / (2 * e) for j in range(2)])
+    res = {}
+    for sa, every in (("interpolating", False), ("gauss", False), ("backsolve", True), ("backsolve", False)):
+        cfg = O.make_cfg("lv", sa, "tsit5_adaptive", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), events=events, ckpt_every_step=every, **tol)
+        r = O.gradient(cfg, t, u0, p)
+        assert np.max(np.abs(r["dp"] - fd_p)) / np.max(np.abs(fd_p)) < 1e-6, sa
+        assert np.max(np.abs(r["du0"][:, 0] - fd_u)) / np.max(np.abs(fd_u)) < 1e-6, sa
+        res[(sa, every)] = r
+    for key in (("gauss", False), ("backsolve", True), ("backsolve", False)):
+        assert np.allclose(res[key]["dp"], res[("interpolating", False)]["dp"], rtol=1e-7)
+    # the saved state at an event time is the post-event state
+    if events[1][0][0] == 0.0:
+        assert abs(res[("interpolating", False)]["saved"][10, 0, 0] - 2.0) < 1e-13
+    # QuadratureAdjoint has no callback support
+    with pytest.raises(RuntimeError):
+        O.gradient(O.make_cfg("lv", "quadrature", "tsit5_adaptive", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), events=events, **tol), t, u0, p)
