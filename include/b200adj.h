@@ -37,7 +37,8 @@ enum {
     B200ADJ_FAM_SDE_LINEAR = 5  /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
 };
 /* sensealg: which *SensitivityFunction / driver is run (src/sensitivity_algorithms.jl:254-278,378-405,486-510,591-611) */
-enum { B200ADJ_SA_INTERPOLATING = 0, B200ADJ_SA_GAUSS = 1, B200ADJ_SA_QUADRATURE = 2, B200ADJ_SA_BACKSOLVE = 3 };
+enum { B200ADJ_SA_INTERPOLATING = 0, B200ADJ_SA_GAUSS = 1, B200ADJ_SA_QUADRATURE = 2, B200ADJ_SA_BACKSOLVE = 3,
+       B200ADJ_SA_GAUSSKRONROD = 4 /* GaussKronrodAdjoint (src/sensitivity_algorithms.jl:689-703, src/gauss_adjoint.jl:820-825): adaptive steppers */ };
 /* stepper: the `alg` handed to solve() for both the forward and the adjoint problem (src/sensitivity_interface.jl:487-491) */
 enum { B200ADJ_ST_TSIT5_FIXED = 0, B200ADJ_ST_ROSENBROCK23 = 1, B200ADJ_ST_EM = 2, B200ADJ_ST_EULER_HEUN = 3,
        B200ADJ_ST_TSIT5_ADAPTIVE = 4 /* error-controlled Tsit5 (PI controller), abstol/reltol; cfg.dt > 0 = initial step */ };
@@ -129,9 +130,13 @@ int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, dou
  * test/Callbacks1/discrete_callbacks.jl:263-293 are (1, 2) and (0, 2)).  The event times become tstops of the forward and
  * of the reverse solve; the reverse pass applies lam(tau-) = scale .* lam(tau+) after the loss jump of the same time (a
  * save time that coincides with an event records the post-event state).  times ascending, strictly inside (t0, t1);
- * host pointers; E = 0 removes the events.  Built for the adaptive Tsit5 stepper with Interpolating / Gauss / Backsolve
+ * host pointers; E = 0 removes the events.  pscale / pshift [E][P] (both NULL = none): parameter-changing affect
+ * p <- pscale[e][:] .* p + pshift[e][:] at the same times (integrator.p .= 2 .* integrator.p .- 0.5, :294-303; the reverse
+ * pass scales the accumulated dG/dp by pscale and continues with the pre-event parameters -- reset_p,
+ * src/interpolating_adjoint.jl:748-823).  Built for the adaptive Tsit5 stepper with Interpolating / Gauss / Backsolve
  * (the reference's QuadratureAdjoint has no callback support either); call before b200adj_forward. */
-int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift);
+int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift,
+                           const double* pscale, const double* pshift);
 
 /* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
 int32_t b200adj_get_noise(void* handle, void* dW_out);

@@ -42,7 +42,7 @@
 
 /* ---- enums: values shared (by convention, not by include) with include/b200adj.h ---- */
 enum { FAM_LV = 0, FAM_LORENZ = 1, FAM_ROBERTSON = 2, FAM_SDE_LV = 3, FAM_MLP = 4, FAM_SDE_LINEAR = 5 };
-enum { SA_INTERPOLATING = 0, SA_GAUSS = 1, SA_QUADRATURE = 2, SA_BACKSOLVE = 3 };
+enum { SA_INTERPOLATING = 0, SA_GAUSS = 1, SA_QUADRATURE = 2, SA_BACKSOLVE = 3, SA_GAUSSKRONROD = 4 };
 enum { ST_TSIT5_FIXED = 0, ST_ROSENBROCK23 = 1, ST_EM = 2, ST_EULER_HEUN = 3, ST_TSIT5_ADAPTIVE = 4 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
 
@@ -68,7 +68,15 @@ typedef struct {
     const double* ev_times;                 /* [E]    */
     const double* ev_scale;                 /* [E][d] */
     const double* ev_shift;                 /* [E][d] */
+    const double* ev_pscale;                /* [E][P] or NULL: parameter-changing affect p <- pscale .* p + pshift        */
+    const double* ev_pshift;                /* (integrator.p .= 2 .* integrator.p .- 0.5, discrete_callbacks.jl:294-303)  */
 } oracle_cfg;
+/* parameters in force after the first `upto` events */
+static void event_params(const oracle_cfg* c, int P, int upto, const double* p0, double* out) {
+    for (int q = 0; q < P; q++) out[q] = p0[q];
+    if (!c->ev_pscale) return;
+    for (int e = 0; e < upto; e++) for (int q = 0; q < P; q++) out[q] = c->ev_pscale[(size_t)e * P + q] * out[q] + c->ev_pshift[(size_t)e * P + q];
+}
 
 /* =====================================================================================
  * RHS families: f, hand-differentiated VJPs (what derivative_wrappers.jl's AD back-ends
@@ -466,7 +474,10 @@ static void forward_tsit5_fixed(const family_t* F, const double* p, const double
  * [UPSTREAM OrdinaryDiffEq defaults], error norm = RMS of err/(abstol+reltol*max(|u|,|unew|))). */
 static int forward_tsit5_adaptive(const family_t* F, const double* p, const double* u0, double t0, double t1,
                                   double abstol, double reltol, double dt0, dense_t* S, const oracle_cfg* evc) {
-    int d = F->d; fwd_ctx c = {F, p, 0};
+    int d = F->d;
+    double pcur[64];                                   /* parameters in force (events may change them) */
+    for (int q = 0; q < F->P && q < 64; q++) pcur[q] = p[q];
+    fwd_ctx c = {F, (evc && evc->n_events > 0 && evc->ev_pscale) ? pcur : p, 0};
     dense_init(S, d, DENSE_TSIT5, 256);
     double* k = (double*)malloc(sizeof(double) * 7 * d), *tmp = (double*)malloc(sizeof(double) * d), *un = (double*)malloc(sizeof(double) * d);
     memcpy(S->u, u0, sizeof(double) * d); S->t[0] = t0;
@@ -500,8 +511,9 @@ static int forward_tsit5_adaptive(const family_t* F, const double* p, const doub
             if (last && ev < E) {
                 /* affect!: u <- scale .* u + shift; the next step starts from the post-event state, FSAL re-evaluated */
                 for (int i = 0; i < d; i++) un[i] = evc->ev_scale[(size_t)ev * d + i] * un[i] + evc->ev_shift[(size_t)ev * d + i];
-                fwd_rhs(t, un, k, &c);
                 ev++;
+                if (evc->ev_pscale) event_params(evc, F->P, ev, p, pcur);
+                fwd_rhs(t, un, k, &c);
             }
             memcpy(S->u + (size_t)(n + 1) * d, un, sizeof(double) * d);
             n++; S->n = n;
@@ -769,13 +781,66 @@ static const double GL3_W[3] = {0.5555555555555556, 0.8888888888888888, 0.555555
  *   (src/sensitivity_interface.jl:426-526, src/gauss_adjoint.jl:766-870, src/quadrature_adjoint.jl:510-633)
  * ts[K] ascending save times; dL[K*d] cotangents for this member (or NULL for COST_AFFINE)
  * ===================================================================================== */
-static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const double* p, const dense_t* sol,
+/* ---- GaussKronrodAdjoint: IntegratingGKSumCallback [UPSTREAM DiffEqCallbacks >= 4.18, not vendored; restated from its
+ * published source].  After every accepted step of the reverse solve the integrand is integrated over [tprev, t] with a
+ * Gauss-Kronrod pair of n = div(alg_order + 1, 2) Gauss points (Tsit5: G3/K7, Rosenbrock23: G1/K3) evaluated with the
+ * integrator's own interpolant; if sum(abs(K - G)) >= tol (1e-7, the callback's default) the interval is bisected and
+ * both halves are integrated recursively, otherwise K is added to the running sum (gauss_adjoint.jl:820-825). ---- */
+static const double GK7_X[7] = {-0.960491268708020283423507092629080, -0.774596669241483377035853079956480, -0.405845151377397166906606412076961, 0.0,
+                                0.405845151377397166906606412076961, 0.774596669241483377035853079956480, 0.960491268708020283423507092629080};
+static const double GK7_W[7] = {0.104656226026467265193823857192073, 0.268488089868333440728569280666710, 0.401397414775962222905051818618432,
+                                0.450916538658474142345110087045571, 0.401397414775962222905051818618432, 0.268488089868333440728569280666710,
+                                0.104656226026467265193823857192073};
+static const double GK7_G[3] = {0.555555555555555555555555555555556, 0.888888888888888888888888888888889, 0.555555555555555555555555555555556};
+static const double GK3_X[3] = {-0.774596669241483377035853079956480, 0.0, 0.774596669241483377035853079956480};
+static const double GK3_W[3] = {0.555555555555555555555555555555556, 0.888888888888888888888888888888889, 0.555555555555555555555555555555556};
+static const double GK3_G[1] = {2.0};
+#define GK_TOL 1e-7
+typedef void (*gk_node_fn)(double tj, double* out /*[P]*/, void* ctx);
+static void integrate_gk(gk_node_fn f, void* ctx, int P, int order, double bl, double br, double* accum, int depth) {
+    const int np = 2 * order + 1;
+    const double* X = order == 3 ? GK7_X : GK3_X; const double* W = order == 3 ? GK7_W : GK3_W; const double* G = order == 3 ? GK7_G : GK3_G;
+    double K[64], Gs[64], v[64];
+    for (int q = 0; q < P; q++) { K[q] = 0; Gs[q] = 0; }
+    for (int i = 0; i < np; i++) {
+        double tj = 0.5 * (br - bl) * X[i] + 0.5 * (bl + br);
+        f(tj, v, ctx);
+        for (int q = 0; q < P; q++) K[q] += W[i] * v[q];
+        if (i % 2 == 1) for (int q = 0; q < P; q++) Gs[q] += G[i / 2] * v[q];      /* every second Kronrod point is a Gauss point */
+    }
+    double err = 0;
+    for (int q = 0; q < P; q++) { K[q] *= 0.5 * (br - bl); Gs[q] *= 0.5 * (br - bl); err += fabs(K[q] - Gs[q]); }
+    if (err < GK_TOL || depth >= 30) { for (int q = 0; q < P; q++) accum[q] += K[q]; return; }
+    const double mid = 0.5 * (bl + br);
+    integrate_gk(f, ctx, P, order, bl, mid, accum, depth + 1);
+    integrate_gk(f, ctx, P, order, mid, br, accum, depth + 1);
+}
+typedef struct { const family_t* F; const double* p; const dense_t* sol; int ros, d, L; double t, hs; const double* z; const double* k; double* y; double* lamq; double* dlq; } gkstep_ctx;
+static void gkstep_node(double tj, double* out, void* c) {
+    gkstep_ctx* x = (gkstep_ctx*)c; const int d = x->d;
+    const double th = (tj - x->t) / x->hs;
+    if (!x->ros) tsit5_dense(d, th, x->hs, x->z, x->k, x->lamq);
+    else { const double c1 = th * (1 - th) / (1 - 2 * 0.29289321881345247559915563789515), c2 = th * (th - 2 * 0.29289321881345247559915563789515) / (1 - 2 * 0.29289321881345247559915563789515);
+           for (int i = 0; i < d; i++) x->lamq[i] = x->z[i] + x->hs * (c1 * x->k[i] + c2 * x->k[x->L + i]); }
+    dense_eval(x->sol, tj, 0, x->y, NULL);
+    x->F->vjp(x->y, x->p, tj, x->lamq, x->dlq, out, &x->F->ctx);
+    for (int q = 0; q < x->F->P; q++) out[q] = -out[q];                            /* GaussIntegrand: out = -F'lam */
+}
+
+static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const double* p_in, const dense_t* sol,
                               const double* ts, const double* dL, double* du0, double* dp, long* nrhs_out) {
     const int d = F->d, P = F->P, K = cfg->K, sa = cfg->sensealg;
+    /* parameters in force on the segment the reverse solve is in: after all events at t = T, re-derived from the caller's p
+     * at every event crossed (the reference's reset_p, src/interpolating_adjoint.jl:748-823) */
+    double pcur_small[64]; double* pcur = pcur_small; int p_events = (cfg->n_events > 0 && cfg->ev_pscale != NULL);
+    if (p_events && P > 64) return -13;
+    if (p_events) event_params(cfg, P, cfg->n_events, p_in, pcur);
+    const double* p = p_events ? pcur : p_in;
     const int L = (sa == SA_INTERPOLATING) ? d + P : (sa == SA_BACKSOLVE ? 2 * d + P : d);
     const int ros = (cfg->stepper == ST_ROSENBROCK23);
     const int adaptive = (cfg->stepper == ST_TSIT5_ADAPTIVE) || ros;
-    if (ros && !(sa == SA_GAUSS || sa == SA_QUADRATURE)) return -10;
+    if (ros && !(sa == SA_GAUSS || sa == SA_QUADRATURE || sa == SA_GAUSSKRONROD)) return -10;
+    if (sa == SA_GAUSSKRONROD && !adaptive) return -12;          /* built for the adaptive steppers */
     double T = cfg->t1, t0 = cfg->t0;
     double* z = (double*)calloc(L, sizeof(double)), *zn = (double*)malloc(sizeof(double) * L), *tmp = (double*)malloc(sizeof(double) * L);
     double* k = (double*)malloc(sizeof(double) * 7 * L);
@@ -822,6 +887,13 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     while (evc >= 0 && fabs(cfg->ev_times[evc] - (tt)) <= 100 * 2.220446049250313e-16 * fmax(fabs(tt), 1.0)) { \
         for (int i = 0; i < d; i++) z[i] *= cfg->ev_scale[(size_t)evc * d + i];                            \
         if (sa == SA_BACKSOLVE) dense_eval(sol, cfg->ev_times[evc], 0, z + d + P, NULL);                   \
+        if (p_events) {   /* p+ = s_p .* p- + c_p: dG/dp- = s_p .* dG/dp+ (+ what accumulates below tau with p-) */ \
+            for (int q = 0; q < P; q++) {                                                                  \
+                if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) z[d + q] *= cfg->ev_pscale[(size_t)evc * P + q]; \
+                else acc[q] *= cfg->ev_pscale[(size_t)evc * P + q];                                        \
+            }                                                                                              \
+            event_params(cfg, P, evc, p_in, pcur);                                                         \
+        }                                                                                                  \
         ctx.tev = (tt); evc--; fsal_ok = 0;                                                                \
     }
     int fsal_ok = 0;
@@ -889,6 +961,10 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
                 for (int q = 0; q < P; q++) acc[q] += (0.5 * (tn - t)) * gw[j] * (-integ[q]);   /* out = -F'lam; scale (t-tprev)/2 */
             }
         }
+        if (sa == SA_GAUSSKRONROD) {
+            gkstep_ctx gc = {F, p, sol, ros, d, L, t, hs, z, k, ybuf, lamq, dlq};
+            integrate_gk(gkstep_node, &gc, P, ros ? 1 : 3, t, tn, acc, 0);
+        }
         if (have_adj) adjdense_push(&adj, t, hs, z, k);
         memcpy(z, zn, sizeof(double) * L);
         if (!ros) { memcpy(k, k + 6 * L, sizeof(double) * L); } else memcpy(f0, fnr, sizeof(double) * L);
@@ -902,7 +978,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     if (rc == 0) {
         for (int i = 0; i < d; i++) du0[i] = z[i];
         if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) for (int q = 0; q < P; q++) dp[q] = z[d + q];
-        else if (sa == SA_GAUSS) for (int q = 0; q < P; q++) dp[q] = acc[q];
+        else if (sa == SA_GAUSS || sa == SA_GAUSSKRONROD) for (int q = 0; q < P; q++) dp[q] = acc[q];
         else {
             /* QuadratureAdjoint interval loop (quadrature_adjoint.jl:537-616) */
             quad_ctx qc = {F, p, sol, &adj, ybuf, lamq, dlq};

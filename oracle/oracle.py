@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
 FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5}
-SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3}
+SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kronrod": 4}
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
 FAM_DIMS = {"lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2)}
 
@@ -33,6 +33,7 @@ class OracleCfg(C.Structure):
         ("cont_a", C.c_double), ("cont_b", C.c_double),
         ("n_events", C.c_int32), ("_pad", C.c_int32),
         ("ev_times", C.c_void_p), ("ev_scale", C.c_void_p), ("ev_shift", C.c_void_p),
+        ("ev_pscale", C.c_void_p), ("ev_pshift", C.c_void_p),
     ]
 
 
@@ -84,11 +85,16 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
     if cont_cost is not None:      # continuous cost g(u) = a/2 |u|^2 + b sum(u)
         cfg.cont_cost, cfg.cont_a, cfg.cont_b = 1, float(cont_cost[0]), float(cont_cost[1])
     if events is not None:         # preset-time events: (times[E], scale[E, d], shift[E, d]), u <- scale * u + shift
-        et, es, ec = (np.ascontiguousarray(x, dtype=np.float64) for x in events)
+        et, es, ec = (np.ascontiguousarray(x, dtype=np.float64) for x in events[:3])
         assert es.shape == (len(et), d) and ec.shape == (len(et), d)
-        cfg._keep = (et, es, ec)   # the struct holds raw pointers
+        cfg._keep = [et, es, ec]   # the struct holds raw pointers
         cfg.n_events = len(et)
         cfg.ev_times, cfg.ev_scale, cfg.ev_shift = et.ctypes.data, es.ctypes.data, ec.ctypes.data
+        if len(events) == 5 and events[3] is not None:     # parameter-changing affect p <- pscale * p + pshift
+            ps, pc = (np.ascontiguousarray(x, dtype=np.float64) for x in events[3:5])
+            assert ps.shape == (len(et), P) and pc.shape == (len(et), P)
+            cfg._keep += [ps, pc]
+            cfg.ev_pscale, cfg.ev_pshift = ps.ctypes.data, pc.ctypes.data
     return cfg
 
 

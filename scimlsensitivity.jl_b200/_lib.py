@@ -14,7 +14,7 @@ _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("B200ADJ_LIB", os.path.join(_PKG, "libb200adj.so"))   # env override: tuning experiments only
 
 FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5}
-SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3}
+SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kronrod": 4}
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
 DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
 COST = {"explicit": 0, "affine": 1}
@@ -94,7 +94,7 @@ def load():
         lib.b200adj_set_tolerances.restype = C.c_int32
         lib.b200adj_set_continuous_cost.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double]
         lib.b200adj_set_continuous_cost.restype = C.c_int32
-        lib.b200adj_set_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200adj_set_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200adj_set_events.restype = C.c_int32
         lib.b200adj_get_noise.argtypes = [C.c_void_p, C.c_void_p]
         lib.b200adj_get_noise.restype = C.c_int32
@@ -171,14 +171,21 @@ class Handle:
     def set_continuous_cost(self, enabled, a=0.0, b=0.0):
         self._check(self._lib.b200adj_set_continuous_cost(self._h, int(bool(enabled)), float(a), float(b)))
 
-    def set_events(self, times, scale, shift):
-        """Preset-time events u <- scale[e] * u + shift[e] at times[e] (host arrays; empty = none)."""
+    def set_events(self, times, scale, shift, pscale=None, pshift=None):
+        """Preset-time events u <- scale[e] * u + shift[e] (and optionally p <- pscale[e] * p + pshift[e]) at times[e]
+        (host arrays; empty = none)."""
         import numpy as np
         t = np.ascontiguousarray(times, dtype=np.float64).reshape(-1)
         E = len(t)
         sc = np.ascontiguousarray(scale, dtype=np.float64).reshape(E, -1)
         sh = np.ascontiguousarray(shift, dtype=np.float64).reshape(E, -1)
-        self._check(self._lib.b200adj_set_events(self._h, E, t.ctypes.data if E else None, sc.ctypes.data if E else None, sh.ctypes.data if E else None))
+        ps = pc = None
+        if pscale is not None and E:
+            ps = np.ascontiguousarray(pscale, dtype=np.float64).reshape(E, -1)
+            pc = np.ascontiguousarray(pshift, dtype=np.float64).reshape(E, -1)
+        self._check(self._lib.b200adj_set_events(self._h, E, t.ctypes.data if E else None, sc.ctypes.data if E else None,
+                                                 sh.ctypes.data if E else None, None if ps is None else ps.ctypes.data,
+                                                 None if pc is None else pc.ctypes.data))
 
     def step_counts(self, fwd, rev):
         self._check(self._lib.b200adj_get_step_counts(self._h, _addr(fwd), _addr(rev)))

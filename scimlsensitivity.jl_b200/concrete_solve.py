@@ -13,7 +13,7 @@ from . import distributed
 from .engine import DeviceEnsemble, _is_torch
 from .problems import (EM, AffineCost, PresetTimeCallback, EnsembleB200, EnsembleProblem, EnsembleSolution, EulerHeun, FAMILIES, ODEProblem,
                        Rosenbrock23, SDEProblem, Tsit5, saveat_to_times)
-from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, InterpolatingAdjoint,
+from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, GaussKronrodAdjoint, InterpolatingAdjoint,
                                      QuadratureAdjoint, sensealg_name)
 from .sensitivity_interface import _check_params, adjoint_sensitivities
 
@@ -130,7 +130,7 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else (sensealg or InterpolatingAdjoint())
     block = getattr(sensealg, "block_threads", 0) if isinstance(sensealg, B200Adjoint) else 0
     stored = getattr(sensealg, "stored_noise", False) if isinstance(sensealg, B200Adjoint) else False
-    ev = callback.tables(d) if callback is not None else None
+    ev = callback.tables(d, P) if callback is not None else None
     key = (prob.f, alg.code, hi - lo, ts.tobytes(), tuple(prob.tspan), _step_size(alg, kwargs), shared_p, on_device, device,
            getattr(prob, "seed", 0), lo, block, stored, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3),
            None if ev is None else tuple(x.tobytes() for x in ev))
@@ -157,7 +157,7 @@ def _concrete_solve_adjoint(prob, alg, sensealg, u0, p, originator=None, *args, 
                             saveat=None, save_idxs=None, **kwargs):
     """-> (out, pullback).  `sensealg` is B200Adjoint(inner) (or a bare continuous adjoint)."""
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else sensealg
-    if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint)):
+    if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint, GaussKronrodAdjoint)):
         raise TypeError("_concrete_solve_adjoint(B200 path): continuous adjoints only")
     _check_params(p)                                                   # :544-549
     eprob = prob if isinstance(prob, EnsembleProblem) else EnsembleProblem(prob)

@@ -54,7 +54,7 @@ struct Handle {
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
     const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
-    int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr;      // preset-time events (adaptive Tsit5)
+    int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr, *d_ev_ps = nullptr, *d_ev_pc = nullptr;      // preset-time events (adaptive Tsit5)
     bool have_forward = false;
     bool noise_valid = false;
     int64_t launches = 0;
@@ -302,6 +302,7 @@ int launch_ros_rev_sa(Handle* h, const RosArgs& a) {
 template <class Fam>
 int launch_ros_rev(Handle* h, const RosArgs& a) {
     if (h->cfg.sensealg == B200ADJ_SA_GAUSS) return launch_ros_rev_sa<Fam, SA_GAUSS>(h, a);
+    if (h->cfg.sensealg == B200ADJ_SA_GAUSSKRONROD) return launch_ros_rev_sa<Fam, SA_GK>(h, a);
     if (h->cfg.sensealg != B200ADJ_SA_QUADRATURE) return B200ADJ_ERR_UNSUPPORTED;
     int rc = launch_ros_rev_sa<Fam, SA_QUAD>(h, a);
     if (rc) return rc;
@@ -337,7 +338,7 @@ T5aArgs t5a_args(Handle* h) {
                           0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
     memcpy(a.A, A, sizeof(A)); memcpy(a.C, C, sizeof(C)); memcpy(a.BT, BT, sizeof(BT));
     tsit5_weights(0.0, nullptr, a.R);
-    a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c;
+    a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
     return a;
 }
 template <class Fam>
@@ -363,6 +364,7 @@ int launch_t5a_rev(Handle* h, const T5aArgs& a) {
     case B200ADJ_SA_INTERPOLATING: return launch_t5a_rev_sa<Fam, SA_INTERP>(h, a);
     case B200ADJ_SA_GAUSS: return launch_t5a_rev_sa<Fam, SA_GAUSS>(h, a);
     case B200ADJ_SA_BACKSOLVE: return launch_t5a_rev_sa<Fam, SA_BACKSOLVE>(h, a);
+    case B200ADJ_SA_GAUSSKRONROD: return launch_t5a_rev_sa<Fam, SA_GK>(h, a);
     case B200ADJ_SA_QUADRATURE: {
         int rc = launch_t5a_rev_sa<Fam, SA_QUAD>(h, a);
         if (rc) return rc;
@@ -443,7 +445,7 @@ void free_all(Handle* h) {
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
     cudaFree(h->d_tapeA); cudaFree(h->d_tapeB); cudaFree(h->d_umma_partials); cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
-    cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c);
+    cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -490,7 +492,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (cfg->sensealg != B200ADJ_SA_BACKSOLVE && cfg->sensealg != B200ADJ_SA_INTERPOLATING) { g_create_error = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     } else {
         if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
-        if (cfg->sensealg < 0 || cfg->sensealg > 3) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
+        if (cfg->sensealg < 0 || cfg->sensealg > 4) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
+        if (cfg->sensealg == B200ADJ_SA_GAUSSKRONROD && !ros) { g_create_error = "GaussKronrodAdjoint: built for the adaptive steppers (Tsit5 adaptive, Rosenbrock23)"; return B200ADJ_ERR_UNSUPPORTED; }
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
         if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -652,7 +655,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
     b200adj_cfg& c = h->cfg;
-    if (sensealg < 0 || sensealg > 3 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
+    if (sensealg < 0 || sensealg > 4 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
+    if (sensealg == B200ADJ_SA_GAUSSKRONROD && !h->adaptive) { h->err = "GaussKronrodAdjoint: built for the adaptive steppers"; return B200ADJ_ERR_UNSUPPORTED; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (h->nev > 0 && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: QuadratureAdjoint has no callback support"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -712,19 +716,20 @@ int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, dou
     return B200ADJ_OK;
 }
 
-int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift) {
+int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift,
+                           const double* pscale, const double* pshift) {
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
     const b200adj_cfg& c = h->cfg;
-    if (E < 0 || (E > 0 && (!times || !scale || !shift))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
+    if (E < 0 || (E > 0 && (!times || !scale || !shift)) || ((pscale == nullptr) != (pshift == nullptr))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
     if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) { h->err = "events: built for the adaptive Tsit5 stepper"; return B200ADJ_ERR_UNSUPPORTED; }
     if (E > 0 && c.sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: Interpolating / Gauss / Backsolve (QuadratureAdjoint has no callback support)"; return B200ADJ_ERR_UNSUPPORTED; }
     for (int e = 0; e < E; e++)
         if (!(times[e] > c.t0 && times[e] < c.t1) || (e > 0 && !(times[e] > times[e - 1]))) { h->err = "events: times must be ascending and strictly inside (t0, t1)"; return B200ADJ_ERR_INVALID; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c);
-    h->d_ev_t = h->d_ev_s = h->d_ev_c = nullptr; h->nev = 0; h->have_forward = false;
+    cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
+    h->d_ev_t = h->d_ev_s = h->d_ev_c = h->d_ev_ps = h->d_ev_pc = nullptr; h->nev = 0; h->have_forward = false;
     if (E > 0) {
         CUDA_TRY(h, cudaMalloc(&h->d_ev_t, (size_t)E * sizeof(double)));
         CUDA_TRY(h, cudaMalloc(&h->d_ev_s, (size_t)E * c.d * sizeof(double)));
@@ -732,6 +737,12 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
         CUDA_TRY(h, cudaMemcpy(h->d_ev_t, times, (size_t)E * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(h, cudaMemcpy(h->d_ev_s, scale, (size_t)E * c.d * sizeof(double), cudaMemcpyHostToDevice));
         CUDA_TRY(h, cudaMemcpy(h->d_ev_c, shift, (size_t)E * c.d * sizeof(double), cudaMemcpyHostToDevice));
+        if (pscale) {
+            CUDA_TRY(h, cudaMalloc(&h->d_ev_ps, (size_t)E * c.P * sizeof(double)));
+            CUDA_TRY(h, cudaMalloc(&h->d_ev_pc, (size_t)E * c.P * sizeof(double)));
+            CUDA_TRY(h, cudaMemcpy(h->d_ev_ps, pscale, (size_t)E * c.P * sizeof(double), cudaMemcpyHostToDevice));
+            CUDA_TRY(h, cudaMemcpy(h->d_ev_pc, pshift, (size_t)E * c.P * sizeof(double), cudaMemcpyHostToDevice));
+        }
         h->nev = E;
     }
     return B200ADJ_OK;

@@ -36,7 +36,7 @@ template <class R> struct Tsit5TablesT {
 };
 using Tsit5Tables = Tsit5TablesT<double>;
 
-enum { SA_INTERP = 0, SA_GAUSS = 1, SA_QUAD = 2, SA_BACKSOLVE = 3 };
+enum { SA_INTERP = 0, SA_GAUSS = 1, SA_QUAD = 2, SA_BACKSOLVE = 3, SA_GK = 4 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
 
 template <class R> struct OdeFwdArgsT {

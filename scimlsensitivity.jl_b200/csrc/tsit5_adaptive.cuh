@@ -29,6 +29,7 @@ struct T5aArgs {
     // preset-time events u <- scale .* u + shift (the hybrid-system adjoint of src/callback_tracking.jl:232-480 for the
     // affine affect family, save_positions = (false, false)): same events for every member, times ascending in (t0, t1)
     int32_t nev; const double* ev_t; const double* ev_s; const double* ev_c;      // [E], [E][D], [E][D]
+    const double* ev_ps; const double* ev_pc;     // [E][P] or null: parameter-changing affect p <- ps .* p + pc (reset_p of the reference)
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
     double BT[7];           // embedded error weights b - bhat
@@ -38,6 +39,18 @@ struct T5aArgs {
 __device__ __forceinline__ void t5_weights(const T5aArgs& a, double th, double* w) {
 #pragma unroll
     for (int j = 0; j < 7; j++) w[j] = th * (a.R[j][0] + th * (a.R[j][1] + th * (a.R[j][2] + th * a.R[j][3])));
+}
+
+// parameters in force after the first `upto` events (p0 = the caller's parameters of this member)
+template <int P>
+__device__ __forceinline__ void t5_event_params(const T5aArgs& a, int upto, const double* p0, double* p) {
+#pragma unroll
+    for (int q = 0; q < P; q++) p[q] = p0[q];
+    if (!a.ev_ps) return;
+    for (int e = 0; e < upto; e++) {
+#pragma unroll
+        for (int q = 0; q < P; q++) p[q] = a.ev_ps[e * P + q] * p[q] + a.ev_pc[e * P + q];
+    }
 }
 
 // forward dense solution of one member
@@ -157,6 +170,10 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                 // affect!: the next step starts from the post-event state; k7 = f(u^-) stays with the step just stored
 #pragma unroll
                 for (int j = 0; j < D; j++) un[j] = a.ev_s[ev * D + j] * un[j] + a.ev_c[ev * D + j];
+                if (a.ev_ps) {
+#pragma unroll
+                    for (int q = 0; q < P; q++) p[q] = a.ev_ps[ev * P + q] * p[q] + a.ev_pc[ev * P + q];
+                }
                 Fam::f(un, p, k[6]);
                 ev++;
                 while (a.saved && ksave < a.K && a.saveat[ksave] == tn) {
@@ -199,6 +216,12 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     double p[P], acc[P];
 #pragma unroll
     for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; acc[q] = 0.0; }
+    if (a.ev_ps) {                                 // the reverse solve starts on the last segment: parameters after all events
+        double p0[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) p0[q] = p[q];
+        t5_event_params<P>(a, a.nev, p0, p);
+    }
     T5Dense<D> sol{a, i, a.fn[i]};
     double z[L], zn[L], k[7][L];
 #pragma unroll
@@ -261,6 +284,19 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
                 sol.eval(a.ev_t[evc], false, y);
 #pragma unroll
                 for (int j = 0; j < D; j++) z[YO + j] = y[j];
+            }
+            if (a.ev_ps) {
+                // p+ = s_p .* p- + c_p: dG/dp- = s_p .* dG/dp+ (+ what accumulates below tau with p-); parameters of the
+                // segment below re-derived from the caller's p
+#pragma unroll
+                for (int q = 0; q < P; q++) {
+                    if (SA == SA_INTERP || SA == SA_BACKSOLVE) z[D + (L > D ? q : 0)] *= a.ev_ps[evc * P + q];
+                    else acc[q] *= a.ev_ps[evc * P + q];
+                }
+                double p0[P];
+#pragma unroll
+                for (int q = 0; q < P; q++) p0[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+                t5_event_params<P>(a, evc, p0, p);
             }
             tev = tt; evc--; fsal_ok = false;
         }
@@ -329,6 +365,25 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
 #pragma unroll
                 for (int q2 = 0; q2 < P; q2++) acc[q2] += (0.5 * (tn - t)) * gw[g] * (-dg[q2]);
             }
+        } else if (SA == SA_GK) {
+            // GaussKronrodAdjoint: error-controlled G3/K7 quadrature of the accepted step (ros23.cuh::integrate_gk_step)
+            auto node = [&](double tj, double* out) {
+                const double th = (tj - t) / hs;
+                double w[7], lq[D], y[D];
+                t5_weights(a, th, w);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    double s_ = 0.0;
+#pragma unroll
+                    for (int s = 0; s < 7; s++) s_ += w[s] * k[s][j];
+                    lq[j] = z[j] + hs * s_;
+                }
+                sol.eval(tj, false, y);
+                Fam::vjp_p(y, p, lq, out);
+#pragma unroll
+                for (int q2 = 0; q2 < P; q2++) out[q2] = -out[q2];
+            };
+            integrate_gk_step<P, 3>(node, t, tn, acc);
         } else if (SA == SA_QUAD && active) {
             a.rt0[(int64_t)nrev * N + i] = t; a.rh[(int64_t)nrev * N + i] = hs;
 #pragma unroll

@@ -118,17 +118,24 @@ class DeviceEnsemble:
         self.handle.reverse(dLdu, du0, dp)
         return du0, dp
 
-    def set_events(self, times, scale, shift):
-        """Preset-time events of the hybrid system (adaptive Tsit5): u <- scale[e] * u + shift[e] at times[e]; call
-        before forward()."""
+    def set_events(self, times, scale, shift, pscale=None, pshift=None):
+        """Preset-time events of the hybrid system (adaptive Tsit5): u <- scale[e] * u + shift[e] and, optionally,
+        p <- pscale[e] * p + pshift[e] at times[e]; call before forward()."""
         times = np.asarray(times, dtype=np.float64).reshape(-1)
         E = len(times)
         scale = np.asarray(scale, dtype=np.float64).reshape(E, -1) if E else np.zeros((0, self.d))
         shift = np.asarray(shift, dtype=np.float64).reshape(E, -1) if E else np.zeros((0, self.d))
         if E and (scale.shape[1] != self.d or shift.shape[1] != self.d):
             raise ValueError("events: scale and shift must be [E, d]")
-        self.handle.set_events(times, scale, shift)
-        self.events = (times, scale, shift)
+        if (pscale is None) != (pshift is None):
+            raise ValueError("events: pscale and pshift come together")
+        if pscale is not None and E:
+            pscale = np.asarray(pscale, dtype=np.float64).reshape(E, -1)
+            pshift = np.asarray(pshift, dtype=np.float64).reshape(E, -1)
+            if pscale.shape[1] != self.P or pshift.shape[1] != self.P:
+                raise ValueError("events: pscale and pshift must be [E, P]")
+        self.handle.set_events(times, scale, shift, pscale, pshift)
+        self.events = (times, scale, shift, pscale, pshift)
 
     def set_reverse(self, sensealg, cost=None, no_start=False, checkpointing=True, ckpt_every_step=False, t=None):
         """Re-target the next reverse pass (sensealg / cost / save times) without re-running the forward pass."""

@@ -162,6 +162,8 @@ class AffineAffect:
     (test/Callbacks1/discrete_callbacks.jl:263-293)."""
     scale: Any
     shift: Any
+    p_scale: Any = None          # parameter-changing affect integrator.p .= p_scale .* integrator.p .+ p_shift
+    p_shift: Any = None          # ("p .= 2p .- 0.5" of discrete_callbacks.jl:294-303 is p_scale=2, p_shift=-0.5)
 
 
 @dataclass(frozen=True)
@@ -174,7 +176,7 @@ class PresetTimeCallback:
     affect: Any
     save_positions: Tuple[bool, bool] = (False, False)
 
-    def tables(self, d):
+    def tables(self, d, P=0):
         t = np.asarray(self.tstops, dtype=np.float64).reshape(-1)
         order = np.argsort(t, kind="stable")
         aff = self.affect if isinstance(self.affect, (list, tuple)) else [self.affect] * len(t)
@@ -182,4 +184,8 @@ class PresetTimeCallback:
             raise ValueError("PresetTimeCallback: one affect per time (or a single affect)")
         sc = np.stack([np.broadcast_to(np.asarray(a.scale, dtype=np.float64), (d,)) for a in aff]) if len(t) else np.zeros((0, d))
         sh = np.stack([np.broadcast_to(np.asarray(a.shift, dtype=np.float64), (d,)) for a in aff]) if len(t) else np.zeros((0, d))
+        if any(a.p_scale is not None or a.p_shift is not None for a in aff):
+            ps = np.stack([np.broadcast_to(np.asarray(1.0 if a.p_scale is None else a.p_scale, dtype=np.float64), (P,)) for a in aff])
+            pc = np.stack([np.broadcast_to(np.asarray(0.0 if a.p_shift is None else a.p_shift, dtype=np.float64), (P,)) for a in aff])
+            return t[order], sc[order], sh[order], ps[order], pc[order]
         return t[order], sc[order], sh[order]

@@ -101,6 +101,17 @@ class GaussAdjoint(AbstractAdjointSensitivityAlgorithm):
 
 
 @dataclass(frozen=True)
+class GaussKronrodAdjoint(AbstractAdjointSensitivityAlgorithm):
+    """src/sensitivity_algorithms.jl:689-703: GaussAdjoint with an error-controlled Gauss-Kronrod quadrature of every
+    accepted reverse step (IntegratingGKSumCallback, src/gauss_adjoint.jl:820-825).  Device: adaptive steppers."""
+    chunk_size: int = 0
+    autodiff: bool = True
+    diff_type: str = "central"
+    autojacvec: Any = None
+    checkpointing: bool = False
+
+
+@dataclass(frozen=True)
 class B200Adjoint(AbstractAdjointSensitivityAlgorithm):
     """`sensealg=B200Adjoint(GaussAdjoint())`: run `inner` on the B200 engine."""
     inner: Any = None
@@ -110,8 +121,8 @@ class B200Adjoint(AbstractAdjointSensitivityAlgorithm):
     def __post_init__(self):
         if self.inner is None:
             object.__setattr__(self, "inner", InterpolatingAdjoint())
-        if not isinstance(self.inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint)):
-            raise TypeError("B200Adjoint wraps one of the four continuous adjoints")
+        if not isinstance(self.inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint, GaussKronrodAdjoint)):
+            raise TypeError("B200Adjoint wraps one of the continuous adjoints")
 
 
 def setvjp(sensealg, vjp):
@@ -149,7 +160,7 @@ def ischeckpointing(alg, sol=None):
         alg = alg.inner
     if isinstance(alg, BacksolveAdjoint):
         return alg.checkpointing
-    if isinstance(alg, (InterpolatingAdjoint, GaussAdjoint)):
+    if isinstance(alg, (InterpolatingAdjoint, GaussAdjoint, GaussKronrodAdjoint)):
         return alg.checkpointing if sol is None else needs_checkpointing(alg, sol)
     return False
 
@@ -161,7 +172,7 @@ def isnoisemixing(alg):
 
 
 def supports_functor_params(alg):
-    return isinstance(alg, GaussAdjoint)
+    return isinstance(alg, (GaussAdjoint, GaussKronrodAdjoint))      # AbstractGAdjoint (src/sensitivity_algorithms.jl:712, :1692-1699)
 
 
 def supports_structured_vjp(vjp):
@@ -169,7 +180,7 @@ def supports_structured_vjp(vjp):
 
 
 SENSEALG_CODE = {InterpolatingAdjoint: "interpolating", GaussAdjoint: "gauss", QuadratureAdjoint: "quadrature",
-                 BacksolveAdjoint: "backsolve"}
+                 BacksolveAdjoint: "backsolve", GaussKronrodAdjoint: "gauss_kronrod"}
 
 
 def sensealg_name(alg):

@@ -9,7 +9,7 @@ src/sensitivity_interface.jl:503-507).  For an ensemble `du0` is [d, N]; with pe
 import numpy as np
 
 from .problems import AdjointSensitivityParameterCompatibilityError, AffineCost, QuadraticRunningCost
-from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, InterpolatingAdjoint,
+from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, GaussKronrodAdjoint, InterpolatingAdjoint,
                                      QuadratureAdjoint, sensealg_name)
 
 
@@ -38,7 +38,7 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
     if sensealg is None:
         sensealg = InterpolatingAdjoint()          # reference default (src/sensitivity_interface.jl:375)
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else sensealg
-    if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint)):
+    if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint, GaussKronrodAdjoint)):
         raise TypeError("adjoint_sensitivities: sensealg must be one of the continuous adjoints")
     # events: the forward solution carries them (PresetTimeCallback passed to solve, like the reference's tracked callbacks
     # inside sol.prob.kwargs); a different callback for the reverse pass alone is meaningless

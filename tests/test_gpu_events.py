@@ -28,6 +28,10 @@ CASES = {
     "set_single": ([5.0], [[0.0, 1.0]], [[2.0, 0.0]]),
     # callbacks with no effect                                           (:249-262)
     "no_effect": ([5.0], [[1.0, 1.0]], [[0.0, 0.0]]),
+    # parameter changing callback: integrator.p .= 2 .* integrator.p .- 0.5 at t == 5.1     (:294-303)
+    "param_change": ([5.1], [[1.0, 1.0]], [[0.0, 0.0]], [[2.0] * 4], [[-0.5] * 4]),
+    # a state kick and a (different) parameter change at different times
+    "mixed": ([2.03, 5.1], [[1.0, 1.0], [1.0, 1.0]], [[2.0, 0.0], [0.0, 0.0]], [[1.0] * 4, [2.0, 1.0, 0.5, 1.0]], [[0.0] * 4, [-0.5, 0.0, 0.1, 0.0]]),
 }
 
 
@@ -57,9 +61,10 @@ def test_events_device_vs_oracle(case, sa, every):
     eng.close()
 
 
-def test_events_match_differentiation_through_the_solver():
+@pytest.mark.parametrize("case", ["add_multi", "param_change", "mixed"])
+def test_events_match_differentiation_through_the_solver(case):
     """g(sol) = sum(sol): gradient == finite differences of the loss through the (oracle) solver, all sensealgs equal."""
-    ev = CASES["add_multi"]
+    ev = CASES[case]
     t = np.arange(0.0, 10.0001, 0.5)
     u0 = np.ones((2, 1)); p = np.array([1.5, 1.0, 3.0, 1.0])
     tol = dict(abstol=1e-12, reltol=1e-12)
@@ -68,7 +73,7 @@ def test_events_match_differentiation_through_the_solver():
     fd_p = np.array([(O.loss(lcfg, t, u0, p + e * np.eye(4)[q])[0] - O.loss(lcfg, t, u0, p - e * np.eye(4)[q])[0]) / (2 * e) for q in range(4)])
     fd_u = np.array([(O.loss(lcfg, t, u0 + e * np.eye(2)[j][:, None], p)[0] - O.loss(lcfg, t, u0 - e * np.eye(2)[j][:, None], p)[0]) / (2 * e) for j in range(2)])
     res = {}
-    for sa in ("interpolating", "gauss", "backsolve"):
+    for sa in ("interpolating", "gauss", "backsolve", "gauss_kronrod"):
         eng = b.DeviceEnsemble("lv", sa, "tsit5_adaptive", 1, t, (0.0, 10.0), 0.0, cost=b.AffineCost(0.0, 1.0), ckpt_every_step=True,
                                max_steps=16384, **tol)
         eng.set_events(*ev)
@@ -84,6 +89,13 @@ def test_events_match_differentiation_through_the_solver():
 def test_events_public_api_and_rejections():
     t = np.arange(0.0, 10.0001, 0.5)
     prob = b.ODEProblem("lv", np.ones(2), (0.0, 10.0), np.array([1.5, 1.0, 3.0, 1.0]))
+    cbp = b.PresetTimeCallback([5.1], b.AffineAffect(1.0, 0.0, p_scale=2.0, p_shift=-0.5))
+    assert [x.shape for x in cbp.tables(2, 4)] == [(1,), (1, 2), (1, 2), (1, 4), (1, 4)]
+    solp = b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=True), b.EnsembleB200(), trajectories=2, saveat=t, callback=cbp, abstol=1e-10, reltol=1e-10)
+    _, dpp = b.adjoint_sensitivities(solp, b.Tsit5(adaptive=True), sensealg=b.GaussAdjoint(), t=t, dgdu_discrete=b.AffineCost(0.0, 1.0), abstol=1e-10, reltol=1e-10)
+    refp = O.gradient(O.make_cfg("lv", "gauss", "tsit5_adaptive", 2, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), abstol=1e-10, reltol=1e-10,
+                                 events=CASES["param_change"]), t, np.ones((2, 2)), np.array([1.5, 1.0, 3.0, 1.0]))
+    assert _rel(np.asarray(dpp).reshape(-1), refp["dp"]) < 1e-7
     cb = b.PresetTimeCallback([5.0], b.AffineAffect([1.0, 1.0], [2.0, 0.0]))
     sol = b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=True), b.EnsembleB200(), trajectories=3, saveat=t, callback=cb, abstol=1e-10, reltol=1e-10)
     du0, dp = b.adjoint_sensitivities(sol, b.Tsit5(adaptive=True), sensealg=b.InterpolatingAdjoint(), t=t, dgdu_discrete=b.AffineCost(0.0, 1.0),

@@ -303,6 +303,7 @@ def test_continuous_cost_all_sensealgs_match_differentiation_of_the_integral():
     ([5.0], [[1.0, 1.0]], [[2.0, 0.0]]),                       # u[1] += 2 at t == 5
     ([2.03, 4.0, 8.0], [[1.0, 1.0]] * 3, [[2.0, 0.0]] * 3),      # at multiple time points
     ([5.0], [[0.0, 1.0]], [[2.0, 0.0]]),                       # u[1] = 2
+    ([5.1], [[1.0, 1.0]], [[0.0, 0.0]], [[2.0] * 4], [[-0.5] * 4]),      # p .= 2p .- 0.5 at t == 5.1 (:294-303)
 ])
 def test_event_adjoint_equals_differentiation_through_the_solver(events):
     """g(sol) = sum(sol) with saveat 0.5 on LV, adaptive Tsit5 at 1e-12: every sensealg reproduces the finite-difference
@@ -329,3 +330,26 @@ def test_event_adjoint_equals_differentiation_through_the_solver(events):
     # QuadratureAdjoint has no callback support
     with pytest.raises(RuntimeError):
         O.gradient(O.make_cfg("lv", "quadrature", "tsit5_adaptive", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), events=events, **tol), t, u0, p)
+
+
+# ---- GaussKronrodAdjoint (src/gauss_adjoint.jl:820-825; IntegratingGKSumCallback restated) ---------------------------
+def test_gauss_kronrod_agrees_with_the_other_adjoints():
+    """Error-controlled G-K quadrature of every reverse step, absolute tolerance 1e-7 per (sub)interval: agrees with
+    GaussAdjoint / QuadratureAdjoint to that accuracy (LV adaptive Tsit5: G3/K7; Robertson Rosenbrock23: G1/K3, where it is
+    closer to the quadgk answer than the 1-point GaussAdjoint -- the reason the sensealg exists)."""
+    t = np.arange(0.0, 10.0001, 0.5)
+    u0 = np.ones((2, 2)); p = np.array([1.5, 1.0, 3.0, 1.0])
+    kw = dict(abstol=1e-10, reltol=1e-10)
+    r = {sa: O.gradient(O.make_cfg("lv", sa, "tsit5_adaptive", 2, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), **kw), t, u0, p)
+         for sa in ("gauss", "gauss_kronrod")}
+    assert np.allclose(r["gauss_kronrod"]["du0"], r["gauss"]["du0"], rtol=1e-12)            # same reverse solve
+    assert np.max(np.abs(r["gauss_kronrod"]["dp"] - r["gauss"]["dp"])) < 2e-5 * np.max(np.abs(r["gauss"]["dp"]))
+    ts = np.logspace(-2, 2, 10); ts[-1] = 100.0
+    u0r = np.repeat(np.array([[1.0], [0.0], [0.0]]), 2, 1); k = np.array([0.04, 3e7, 1e4])
+    rr = {sa: O.gradient(O.make_cfg("robertson", sa, "rosenbrock23", 2, ts, 0.0, 100.0, cost=("affine", 1.0, 0.0), abstol=1e-8, reltol=1e-8,
+                                    quad_abstol=1e-12, quad_reltol=1e-10), ts, u0r, k)["dp"] for sa in ("gauss", "gauss_kronrod", "quadrature")}
+    e_gk = np.max(np.abs(rr["gauss_kronrod"] - rr["quadrature"]) / np.abs(rr["quadrature"]))
+    e_g = np.max(np.abs(rr["gauss"] - rr["quadrature"]) / np.abs(rr["quadrature"]))
+    assert e_gk < 1e-6 and e_gk < e_g
+    with pytest.raises(RuntimeError):       # built for the adaptive steppers
+        O.gradient(O.make_cfg("lv", "gauss_kronrod", "tsit5_fixed", 2, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0)), t, u0, p)
