@@ -15,7 +15,8 @@ from .problems import (EM, AdjointSensitivityParameterCompatibilityError, Affine
 from .sensitivity_algorithms import (B200Adjoint, B200VJP, BacksolveAdjoint, EnzymeVJP, GaussAdjoint, GaussKronrodAdjoint,
                                      InterpolatingAdjoint, MooncakeVJP, QuadratureAdjoint, ReactantVJP,
                                      ReverseDiffVJP, TrackerVJP, VJPChoice, ZygoteVJP, alg_autodiff, diff_type,
-                                     get_chunksize, get_jacvec, ischeckpointing, isnoisemixing, setvjp)
+                                     get_chunksize, get_jacvec, ischeckpointing, isnoisemixing, sensealg_name, setvjp,
+                                     supports_functor_params, supports_structured_vjp)
 from .sensitivity_interface import adjoint_sensitivities
 
 __all__ = [n for n in dir() if not n.startswith("_")] + ["_concrete_solve_adjoint"]

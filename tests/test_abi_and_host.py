@@ -63,7 +63,10 @@ def test_sensealg_structs_mirror_reference_defaults():
     q = b.QuadratureAdjoint()
     assert (q.abstol, q.reltol) == (1e-6, 1e-3)
     assert b.GaussAdjoint().checkpointing is False
-    for A in (b.BacksolveAdjoint, b.InterpolatingAdjoint, b.QuadratureAdjoint, b.GaussAdjoint):
+    # GaussKronrodAdjoint (:689-703) belongs to AbstractGAdjoint (:712) and shares its traits (:1675-1699)
+    assert b.GaussKronrodAdjoint().checkpointing is False and b.supports_functor_params(b.GaussKronrodAdjoint())
+    assert b.sensealg_name(b.B200Adjoint(b.GaussKronrodAdjoint())) == "gauss_kronrod"
+    for A in (b.BacksolveAdjoint, b.InterpolatingAdjoint, b.QuadratureAdjoint, b.GaussAdjoint, b.GaussKronrodAdjoint):
         a = A()
         assert a.autojacvec is None and b.get_chunksize(a) == 0 and b.alg_autodiff(a) is True and b.diff_type(a) == "central"
         a2 = b.setvjp(a, b.ReverseDiffVJP(True))
@@ -110,3 +113,25 @@ def test_shard_bounds_partition():
         b_ = [b.shard_bounds(N, g, G) for g in range(G)]
         assert b_[0][0] == 0 and b_[-1][1] == N and all(b_[i][1] == b_[i + 1][0] for i in range(G - 1))
         assert max(h - l for l, h in b_) - min(h - l for l, h in b_) <= 1
+
+
+def test_preset_time_callback_tables_and_host_side_rejections():
+    """PresetTimeCallback(tstops, AffineAffect): event tables sorted by time, one affect per time or one for all, optional
+    parameter affect; everything else is refused on the host before any device call."""
+    cb = b.PresetTimeCallback([8.0, 2.03, 4.0], [b.AffineAffect([1, 1], [3.0, 0]), b.AffineAffect([1, 1], [1.0, 0]), b.AffineAffect([0, 1], [2.0, 0])])
+    t, sc, sh = cb.tables(2, 4)
+    assert t.tolist() == [2.03, 4.0, 8.0] and sh[:, 0].tolist() == [1.0, 2.0, 3.0] and sc[1].tolist() == [0.0, 1.0]
+    t, sc, sh, ps, pc = b.PresetTimeCallback([5.1], b.AffineAffect(1.0, 0.0, p_scale=2.0, p_shift=-0.5)).tables(2, 4)
+    assert ps.shape == (1, 4) and (ps == 2.0).all() and (pc == -0.5).all() and (sc == 1.0).all()
+    with pytest.raises(ValueError):
+        b.PresetTimeCallback([1.0, 2.0], [b.AffineAffect(1.0, 0.0)]).tables(2, 4)
+    prob = b.ODEProblem("lv", np.ones(2), (0.0, 10.0), np.array([1.5, 1.0, 3.0, 1.0]))
+    ts = np.arange(0.0, 10.01, 0.5)
+    with pytest.raises(NotImplementedError):          # a callback of another kind
+        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=True), b.EnsembleB200(), trajectories=2, saveat=ts, callback=lambda integrator: None)
+    with pytest.raises(NotImplementedError):          # extra saved points are not carried
+        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=True), b.EnsembleB200(), trajectories=2, saveat=ts,
+                callback=b.PresetTimeCallback([5.0], b.AffineAffect(1.0, 0.0), save_positions=(True, True)))
+    with pytest.raises(NotImplementedError):          # fixed-step stepper
+        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=False, dt=0.01), b.EnsembleB200(), trajectories=2, saveat=ts,
+                callback=b.PresetTimeCallback([5.0], b.AffineAffect(1.0, 0.0)))
