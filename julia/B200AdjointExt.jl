@@ -17,10 +17,24 @@ const libb200adj = get(ENV, "B200ADJ_LIB", "libb200adj.so")
 # ---- enums / cfg: field-for-field mirror of b200adj_cfg (168 bytes; checked against b200adj_sizeof_cfg) ----
 @enum Family::Int32 FAM_LV = 0 FAM_LORENZ = 1 FAM_ROBERTSON = 2 FAM_SDE_LV = 3 FAM_MLP = 4 FAM_SDE_LINEAR = 5
 const SA_CODE = Dict(InterpolatingAdjoint => Int32(0), GaussAdjoint => Int32(1), QuadratureAdjoint => Int32(2),
-    BacksolveAdjoint => Int32(3))
-const ST_TSIT5_FIXED, ST_ROSENBROCK23, ST_EM, ST_EULER_HEUN = Int32(0), Int32(1), Int32(2), Int32(3)
+    BacksolveAdjoint => Int32(3), GaussKronrodAdjoint => Int32(4))
+const ST_TSIT5_FIXED, ST_ROSENBROCK23, ST_EM, ST_EULER_HEUN, ST_TSIT5_ADAPTIVE = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
 const COST_EXPLICIT, COST_AFFINE = Int32(0), Int32(1)
 const FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP = UInt32(1), UInt32(2), UInt32(4)
+
+"""
+    B200PresetAffine(tstops, scale, shift; pscale = nothing, pshift = nothing)
+
+The callback family the device path carries: at each `tstops[e]` the affect is `u .= scale[:, e] .* u .+ shift[:, e]` and,
+optionally, `p .= pscale[:, e] .* p .+ pshift[:, e]` (`save_positions = (false, false)`).  It is a plain marker object:
+passed as `callback =` to `solve(...; sensealg = B200Adjoint(...))` it is consumed by the method below; for the reference
+path build the equivalent `PresetTimeCallback(tstops, affect!)`.
+"""
+struct B200PresetAffine
+    tstops::Vector{Float64}; scale::Matrix{Float64}; shift::Matrix{Float64}
+    pscale::Union{Nothing, Matrix{Float64}}; pshift::Union{Nothing, Matrix{Float64}}
+end
+B200PresetAffine(t, s, c; pscale = nothing, pshift = nothing) = B200PresetAffine(collect(Float64, t), s, c, pscale, pshift)
 
 struct B200Cfg
     rhs_family::Int32; sensealg::Int32; stepper::Int32; dtype::Int32
@@ -72,7 +86,7 @@ mutable struct Handle
     end
 end
 
-stepper_code(alg) = nameof(typeof(alg)) === :Tsit5 ? ST_TSIT5_FIXED :
+stepper_code(alg, adaptive = false) = nameof(typeof(alg)) === :Tsit5 ? (adaptive ? ST_TSIT5_ADAPTIVE : ST_TSIT5_FIXED) :
     nameof(typeof(alg)) === :EM ? ST_EM :
     nameof(typeof(alg)) === :EulerHeun ? ST_EULER_HEUN :
     nameof(typeof(alg)) === :Rosenbrock23 ? ST_ROSENBROCK23 : error("B200Adjoint: unsupported solver $(typeof(alg))")
@@ -87,8 +101,17 @@ function SciMLBase._concrete_solve_adjoint(
     # anything the device path does not cover goes to the reference implementation unchanged
     delegate() = SciMLBase._concrete_solve_adjoint(prob, alg, sensealg.inner, u0, p, originator, args...;
         save_start, save_end, saveat, save_idxs, kwargs...)
-    (haskey(kwargs, :callback) || prob.f.mass_matrix !== SciMLBase.I) && return delegate()
-    (p isa AbstractVecOrMat{Float64} && u0 isa AbstractVecOrMat{Float64} && dt !== nothing) || return delegate()
+    prob.f.mass_matrix !== SciMLBase.I && return delegate()
+    # callbacks: the device carries preset-time affine affects (B200PresetAffine marks them, see INTEGRATION.md); anything
+    # else -- continuous callbacks, state-dependent affects, extra saved points -- goes to the reference implementation
+    events = nothing
+    if haskey(kwargs, :callback)
+        cb = kwargs[:callback]
+        (cb isa B200PresetAffine && alg isa Tsit5 && adaptive) || return delegate()
+        events = cb
+    end
+    adaptive = get(kwargs, :adaptive, true) && !(alg isa Union{EM, EulerHeun})       # OrdinaryDiffEq default; fixed step needs dt
+    (p isa AbstractVecOrMat{Float64} && u0 isa AbstractVecOrMat{Float64} && (adaptive || dt !== nothing)) || return delegate()
 
     t0, t1 = prob.tspan
     ts = saveat isa Number ? collect(t0:saveat:t1) : sort(collect(Float64, saveat))          # concrete_solve.jl:718-725,752-756
@@ -101,8 +124,8 @@ function SciMLBase._concrete_solve_adjoint(
     P = shared ? length(p) : size(p, 1)
     flags = sensealg.inner isa BacksolveAdjoint && !sensealg.inner.checkpointing ? FLAG_NO_CHECKPOINTING : UInt32(0)
     (!save_start && !isempty(saveat) && t0 in saveat) && (flags |= FLAG_NO_START)               # concrete_solve.jl:962
-    cfg = GC.@preserve ts B200Cfg(Int32(sensealg.family), SA_CODE[typeof(sensealg.inner).name.wrapper], stepper_code(alg), 0,
-        d, P, prob isa SciMLBase.AbstractSDEProblem ? d : 0, length(ts), N, t0, t1, dt,
+    cfg = GC.@preserve ts B200Cfg(Int32(sensealg.family), SA_CODE[typeof(sensealg.inner).name.wrapper], stepper_code(alg, adaptive), 0,
+        d, P, prob isa SciMLBase.AbstractSDEProblem ? d : 0, length(ts), N, t0, t1, something(dt, 0.0),
         get(kwargs, :abstol, 1e-6), get(kwargs, :reltol, 1e-3),
         sensealg.inner isa QuadratureAdjoint ? sensealg.inner.abstol : 1e-6,
         sensealg.inner isa QuadratureAdjoint ? sensealg.inner.reltol : 1e-3,
@@ -112,6 +135,15 @@ function SciMLBase._concrete_solve_adjoint(
         GC.@preserve ts Handle(cfg)
     catch
         return delegate()                                     # B200ADJ_ERR_UNSUPPORTED etc.
+    end
+    if events !== nothing        # [E], [E][d], [E][d], optional [E][P] x2 (row-major at the ABI = column-major transposed here)
+        E = length(events.tstops)
+        sc, sh = Matrix{Float64}(events.scale), Matrix{Float64}(events.shift)                 # d x E column-major = [E][d]
+        ps = events.pscale === nothing ? C_NULL : pointer(Matrix{Float64}(events.pscale))
+        pc = events.pshift === nothing ? C_NULL : pointer(Matrix{Float64}(events.pshift))
+        GC.@preserve events sc sh check(h.ptr, ccall((:b200adj_set_events, libb200adj), Int32,
+            (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, E, events.tstops, sc, sh, ps, pc))
     end
     K = length(ts)
     saved = Array{Float64}(undef, N, d, K)                    # [K][d][N] in C order
