@@ -102,6 +102,7 @@ function SciMLBase._concrete_solve_adjoint(
     delegate() = SciMLBase._concrete_solve_adjoint(prob, alg, sensealg.inner, u0, p, originator, args...;
         save_start, save_end, saveat, save_idxs, kwargs...)
     prob.f.mass_matrix !== SciMLBase.I && return delegate()
+    adaptive = get(kwargs, :adaptive, true) && !(alg isa Union{EM, EulerHeun})       # OrdinaryDiffEq default; fixed step needs dt
     # callbacks: the device carries preset-time affine affects (B200PresetAffine marks them, see INTEGRATION.md); anything
     # else -- continuous callbacks, state-dependent affects, extra saved points -- goes to the reference implementation
     events = nothing
@@ -110,7 +111,6 @@ function SciMLBase._concrete_solve_adjoint(
         (cb isa B200PresetAffine && alg isa Tsit5 && adaptive) || return delegate()
         events = cb
     end
-    adaptive = get(kwargs, :adaptive, true) && !(alg isa Union{EM, EulerHeun})       # OrdinaryDiffEq default; fixed step needs dt
     (p isa AbstractVecOrMat{Float64} && u0 isa AbstractVecOrMat{Float64} && (adaptive || dt !== nothing)) || return delegate()
 
     t0, t1 = prob.tspan
