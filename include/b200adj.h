@@ -121,7 +121,7 @@ int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_relto
 /* Continuous cost functional (dgdu_continuous / dgdp_continuous of adjoint_sensitivities; accumulate_cost!,
  * src/derivative_wrappers.jl:1411-1442): named family g(u) = a/2 |u|^2 + b sum(u), i.e. dgdu_continuous = a u + b,
  * dgdp_continuous = 0, added to the adjoint RHS of the NEXT reverse pass (on top of the discrete cost, if any).
- * Built for the fixed-step Tsit5 path; enabled = 0 switches it off. */
+ * Built for the Tsit5 paths (fixed step: all four sensealgs; adaptive: + GaussKronrod); enabled = 0 switches it off. */
 int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b);
 
 /* Preset-time events of the hybrid system (DiscreteCallback / PresetTimeCallback of the reference with

@@ -338,6 +338,7 @@ T5aArgs t5a_args(Handle* h) {
                           0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
     memcpy(a.A, A, sizeof(A)); memcpy(a.C, C, sizeof(C)); memcpy(a.BT, BT, sizeof(BT));
     tsit5_weights(0.0, nullptr, a.R);
+    if (h->cont_on) { a.flags |= 8u; a.cont_a = h->cont_a; a.cont_b = h->cont_b; }
     a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
     return a;
 }
@@ -710,8 +711,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
 int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b) {
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
-    if (enabled && (h->adaptive || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
-        h->err = "continuous cost: built for the fixed-step Tsit5 ODE path only"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (enabled && ((h->adaptive && h->cfg.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
+        h->err = "continuous cost: built for the Tsit5 ODE paths (fixed step and adaptive)"; return B200ADJ_ERR_UNSUPPORTED; }
     h->cont_on = enabled != 0; h->cont_a = a; h->cont_b = b;
     return B200ADJ_OK;
 }

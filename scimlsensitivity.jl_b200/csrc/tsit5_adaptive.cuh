@@ -29,6 +29,7 @@ struct T5aArgs {
     // preset-time events u <- scale .* u + shift (the hybrid-system adjoint of src/callback_tracking.jl:232-480 for the
     // affine affect family, save_positions = (false, false)): same events for every member, times ascending in (t0, t1)
     int32_t nev; const double* ev_t; const double* ev_s; const double* ev_c;      // [E], [E][D], [E][D]
+    double cont_a, cont_b;  // flags bit3: continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u), dlam -= dgdu_continuous(y) (accumulate_cost!)
     const double* ev_ps; const double* ev_pc;     // [E][P] or null: parameter-changing affect p <- ps .* p + pc (reset_p of the reference)
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
@@ -237,6 +238,10 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         Fam::vjp_u(y, p, x, dx);
 #pragma unroll
         for (int j = 0; j < D; j++) dx[j] = -dx[j];
+        if (a.flags & 8u) {                                          // src/derivative_wrappers.jl:1411-1442
+#pragma unroll
+            for (int j = 0; j < D; j++) dx[j] -= a.cont_a * y[j] + a.cont_b;
+        }
         if (SA == SA_INTERP || SA == SA_BACKSOLVE) {
             double dg[P];
             Fam::vjp_p(y, p, x, dg);
