@@ -353,3 +353,51 @@ def test_gauss_kronrod_agrees_with_the_other_adjoints():
     assert e_gk < 1e-6 and e_gk < e_g
     with pytest.raises(RuntimeError):       # built for the adaptive steppers
         O.gradient(O.make_cfg("lv", "gauss_kronrod", "tsit5_fixed", 2, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0)), t, u0, p)
+
+
+# ---- an independent implementation: forward (variational) sensitivities with SciPy's DOP853 ---------------------------
+@pytest.mark.parametrize("family", ["lv", "lorenz"])
+def test_gradient_matches_independent_forward_sensitivity_solve(family):
+    """The continuous adjoint of the oracle against forward sensitivity analysis done by a different code base and a
+    different integrator (scipy.integrate.solve_ivp, DOP853, rtol 1e-13) on the augmented system [u; dU/dp; dU/du0]:
+    dL/dp = sum_k dl/du(t_k) . dU/dp(t_k) for l = a/2 |u|^2 + b sum(u).  This is what the reference's own tests do with
+    ForwardDiff / ForwardSensitivity (test/Core3/adjoint.jl:691-705, :865-908), with an integrator we did not write."""
+    from scipy.integrate import solve_ivp
+    if family == "lv":
+        d, P, T = 2, 4, 10.0
+        u0 = np.array([1.0, 1.0]); p = np.array([1.5, 1.0, 3.0, 1.0])
+        f = lambda u, p: np.array([p[0] * u[0] - p[1] * u[0] * u[1], -p[2] * u[1] + p[3] * u[0] * u[1]])
+        J = lambda u, p: np.array([[p[0] - p[1] * u[1], -p[1] * u[0]], [p[3] * u[1], -p[2] + p[3] * u[0]]])
+        Fp = lambda u, p: np.array([[u[0], -u[0] * u[1], 0, 0], [0, 0, -u[1], u[0] * u[1]]])
+    else:
+        d, P, T = 3, 3, 2.0
+        u0 = np.array([1.0, 0.0, 0.0]); p = np.array([10.0, 28.0, 8.0 / 3.0])
+        f = lambda u, p: np.array([p[0] * (u[1] - u[0]), u[0] * (p[1] - u[2]) - u[1], u[0] * u[1] - p[2] * u[2]])
+        J = lambda u, p: np.array([[-p[0], p[0], 0], [p[1] - u[2], -1, -u[0]], [u[1], u[0], -p[2]]])
+        Fp = lambda u, p: np.array([[u[1] - u[0], 0, 0], [0, u[0], 0], [0, 0, -u[2]]])
+    ts = np.linspace(0.0, T, 21)
+    a, bb = 1.0, -2.0
+
+    def rhs(t, x):
+        u = x[:d]; Sp = x[d:d + d * P].reshape(d, P); Su = x[d + d * P:].reshape(d, d)
+        Ju = J(u, p)
+        return np.concatenate([f(u, p), (Ju @ Sp + Fp(u, p)).ravel(), (Ju @ Su).ravel()])
+
+    x0 = np.concatenate([u0, np.zeros(d * P), np.eye(d).ravel()])
+    sol = solve_ivp(rhs, (0.0, T), x0, method="DOP853", t_eval=ts, rtol=1e-13, atol=1e-13)
+    assert sol.success
+    dp_ref = np.zeros(P); du0_ref = np.zeros(d)
+    for k in range(len(ts)):
+        u = sol.y[:d, k]; Sp = sol.y[d:d + d * P, k].reshape(d, P); Su = sol.y[d + d * P:, k].reshape(d, d)
+        g = a * u + bb
+        dp_ref += g @ Sp; du0_ref += g @ Su
+    for sa, stepper, kw in (("interpolating", "tsit5_adaptive", dict(abstol=1e-12, reltol=1e-12)),
+                            ("gauss", "tsit5_adaptive", dict(abstol=1e-12, reltol=1e-12)),
+                            ("quadrature", "tsit5_adaptive", dict(abstol=1e-12, reltol=1e-12, quad_abstol=1e-12, quad_reltol=1e-10)),
+                            ("backsolve", "tsit5_adaptive", dict(abstol=1e-12, reltol=1e-12, ckpt_every_step=True)),
+                            ("gauss", "tsit5_fixed", dict(dt=T / 4000))):
+        cfg = O.make_cfg(family, sa, stepper, 1, ts, 0.0, T, cost=("affine", a, bb), **kw)
+        r = O.gradient(cfg, ts, u0[:, None], p)
+        assert np.max(np.abs(r["saved"][:, :, 0].T - sol.y[:d])) < 1e-8, (sa, stepper)
+        assert np.max(np.abs(r["dp"] - dp_ref)) / np.max(np.abs(dp_ref)) < 2e-8, (sa, stepper, r["dp"], dp_ref)
+        assert np.max(np.abs(r["du0"][:, 0] - du0_ref)) / np.max(np.abs(du0_ref)) < 2e-8, (sa, stepper)
