@@ -401,3 +401,44 @@ def test_gradient_matches_independent_forward_sensitivity_solve(family):
         assert np.max(np.abs(r["saved"][:, :, 0].T - sol.y[:d])) < 1e-8, (sa, stepper)
         assert np.max(np.abs(r["dp"] - dp_ref)) / np.max(np.abs(dp_ref)) < 2e-8, (sa, stepper, r["dp"], dp_ref)
         assert np.max(np.abs(r["du0"][:, 0] - du0_ref)) / np.max(np.abs(du0_ref)) < 2e-8, (sa, stepper)
+
+
+def test_robertson_gradient_matches_independent_stiff_forward_sensitivity_solve():
+    """C3's problem against forward sensitivities integrated by SciPy's Radau (implicit Runge-Kutta, analytic Jacobian of the
+    augmented system, rtol 1e-11): Rosenbrock23 (1e-9) + QuadratureAdjoint / GaussKronrodAdjoint / GaussAdjoint of the oracle
+    (test/Core2/stiff_adjoints.jl:256-322 compares QuadratureAdjoint with ForwardDiff on the same kind of problem)."""
+    from scipy.integrate import solve_ivp
+    k = np.array([0.04, 3e7, 1e4]); u0 = np.array([1.0, 0.0, 0.0]); T = 100.0
+    ts = np.logspace(-2, 2, 10); ts[-1] = T
+    f = lambda y: np.array([-k[0] * y[0] + k[2] * y[1] * y[2], k[0] * y[0] - k[1] * y[1] ** 2 - k[2] * y[1] * y[2], k[1] * y[1] ** 2])
+    J = lambda y: np.array([[-k[0], k[2] * y[2], k[2] * y[1]], [k[0], -2 * k[1] * y[1] - k[2] * y[2], -k[2] * y[1]], [0.0, 2 * k[1] * y[1], 0.0]])
+    Fp = lambda y: np.array([[-y[0], 0.0, y[1] * y[2]], [y[0], -y[1] ** 2, -y[1] * y[2]], [0.0, y[1] ** 2, 0.0]])
+
+    def rhs(t, x):
+        y = x[:3]; S = x[3:].reshape(3, 3)
+        return np.concatenate([f(y), (J(y) @ S + Fp(y)).ravel()])
+
+    def jac(t, x):
+        y = x[:3]; S = x[3:].reshape(3, 3)
+        n = 12; A = np.zeros((n, n)); Jy = J(y)
+        A[:3, :3] = Jy
+        e = 1e-7                                    # d(J S + Fp)/dy by central differences of an analytic expression (exactness is
+        for j in range(3):                          # not needed for the Newton iteration)
+            dy = np.zeros(3); dy[j] = e * max(1.0, abs(y[j]))
+            A[3:, j] = ((J(y + dy) @ S + Fp(y + dy)) - (J(y - dy) @ S + Fp(y - dy))).ravel() / (2 * dy[j])
+        for c in range(3):
+            for r in range(3):
+                for m in range(3):
+                    A[3 + r * 3 + c, 3 + m * 3 + c] = Jy[r, m]
+        return A
+
+    sol = solve_ivp(rhs, (0.0, T), np.concatenate([u0, np.zeros(9)]), method="Radau", jac=jac, t_eval=ts, rtol=1e-11, atol=1e-14)
+    assert sol.success
+    dp_ref = np.zeros(3)
+    for i in range(len(ts)):
+        dp_ref += sol.y[:3, i] @ sol.y[3:, i].reshape(3, 3)            # l = |u|^2 / 2  =>  dl/du = u
+    kw = dict(abstol=1e-9, reltol=1e-9, quad_abstol=1e-13, quad_reltol=1e-10)
+    for sa, tol in (("quadrature", 1e-5), ("gauss_kronrod", 1e-5), ("gauss", 5e-4)):      # Rosenbrock23 is second order: 4e-6 at tol 1e-9
+        r = O.gradient(O.make_cfg("robertson", sa, "rosenbrock23", 1, ts, 0.0, T, cost=("affine", 1.0, 0.0), **kw), ts, u0[:, None], k)
+        assert np.max(np.abs(r["saved"][:, :, 0].T - sol.y[:3])) < 1e-7
+        assert np.max(np.abs(r["dp"] - dp_ref) / np.abs(dp_ref)) < tol, (sa, r["dp"], dp_ref)
