@@ -17,6 +17,7 @@
 #include "mlp.cuh"
 #include "tsit5_quad.cuh"
 #include "mlp_umma.cuh"
+#include "mlp_tc.cuh"
 #include "tsit5_adaptive.cuh"
 
 using namespace b200adj;
@@ -47,6 +48,7 @@ struct Handle {
     bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
     bool cont_on = false; double cont_a = 0, cont_b = 0;   // continuous cost family
+    bool mlp_tc = false;              // BF16_F32ACC: every GEMM-shaped piece of the time loop on tcgen05 (mlp_tc.cuh)
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
     int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
     double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
@@ -406,6 +408,37 @@ int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, in
     h->launches++;
     return 0;
 }
+int mlp_tc_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
+    MlpArgs<float> a;
+    memset(&a, 0, sizeof(a));
+    a.u0 = (const float*)u0; a.p = (const float*)p; a.ckpt = (float*)h->d_ckpt; a.saved = (float*)saved; a.save_of_step = h->d_save_of_step;
+    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
+    const size_t smem = sizeof(TcSmem) + 128;
+    if (cudaFuncSetAttribute(mlp_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+    mlp_tc_forward_kernel<<<(int)((h->cfg.N + TC_M - 1) / TC_M), TC_M, smem, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+int mlp_tc_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
+    const b200adj_cfg& c = h->cfg;
+    MlpArgs<float> a;
+    memset(&a, 0, sizeof(a));
+    a.p = (const float*)h->cur_p; a.ckpt = (float*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const float*)dLdu;
+    a.du0 = (float*)du0; a.partials = (float*)h->d_partials; a.dp = (float*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
+    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    const size_t smem = sizeof(TcSmem) + 128;
+    const int grid = (int)((c.N + TC_M - 1) / TC_M);
+    if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
+        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_EXPLICIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_tc_reverse_kernel<COST_EXPLICIT><<<grid, TC_M, smem, h->stream>>>(a);
+    } else {
+        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_tc_reverse_kernel<COST_AFFINE><<<grid, TC_M, smem, h->stream>>>(a);
+    }
+    mlp_reduce_kernel<float><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const float*)h->d_partials, (float*)dp, grid);
+    h->launches += 2;
+    return 0;
+}
 template <class T>
 int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
     const b200adj_cfg& c = h->cfg;
@@ -620,7 +653,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     CREATE_TRY(cudaMalloc(&h->d_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
     CREATE_TRY(cudaMemcpy(h->d_save_of_step, sos.data(), ((size_t)S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (sde) CREATE_TRY(cudaMalloc(&h->d_noise, (size_t)S * m * N * e));
-    if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC) {
+    // BF16_F32ACC = mlp_tc.cuh (member and gradient GEMMs in the loop on tcgen05, no tapes).  B200ADJ_MLP_TC=0 selects the
+    // earlier formulation (CUDA-core mat-mat products in the loop, bf16 operand tapes, one tcgen05 GEMM for dW2 afterwards).
+    if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC) { const char* e_ = getenv("B200ADJ_MLP_TC"); h->mlp_tc = !(e_ && atoi(e_) == 0); }
+    if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC && !h->mlp_tc) {
         h->Ktot = (int64_t)6 * S * (int64_t)Npad;                              // Npad is a multiple of 32 => Ktot % 64 == 0
         // several CTAs per SM (24.7 KB smem, 64 TMEM columns each): the single-stage load->MMA->wait loop of one CTA is
         // latency-bound, co-resident CTAs overlap each other's phases
@@ -827,7 +863,8 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = c.dtype != B200ADJ_F64 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
+        rc = h->mlp_tc ? mlp_tc_forward_launch(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
+           : c.dtype != B200ADJ_F64 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
                                     : mlp_forward_launch<double>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         OdeFwdArgsT<float> a;
@@ -927,7 +964,8 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = c.dtype != B200ADJ_F64 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
+        rc = h->mlp_tc ? mlp_tc_reverse_launch(h, dL, ddu0, ddp)
+           : c.dtype != B200ADJ_F64 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         if (h->cont_on) { h->err = "continuous cost: F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
         OdeRevArgsT<float> a;

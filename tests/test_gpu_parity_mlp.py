@@ -46,32 +46,52 @@ def test_mlp_interpolating_parity(dtype, tol_u, tol_p, cost, N):
     eng.close()
 
 
+BLOCKS = {"W1": slice(0, 2 * H), "b1": slice(2 * H, 3 * H), "W2": slice(3 * H, 3 * H + H * H), "b2": slice(3 * H + H * H, 4 * H + H * H),
+          "W3": slice(4 * H + H * H, 6 * H + H * H), "b3": slice(6 * H + H * H, P)}
+
+
 @pytest.mark.parametrize("N", [100, 4096])
-def test_mlp_bf16_tensor_core_parameter_vjp(N):
-    """dtype = bf16_f32acc: the hidden-layer weight gradient dW2 (4096 of the 4482 parameters) is contracted on the
-    tensor cores (tcgen05.mma, bf16 operands, fp32 TMEM accumulator) from K-major operand tapes; everything else is the
-    fp32 path.  BASELINE C4: <= 2e-2 relative for the bf16 path."""
+@pytest.mark.parametrize("cost", ["affine", "explicit"])
+def test_mlp_bf16_tensor_core_path(N, cost):
+    """dtype = bf16_f32acc (csrc/mlp_tc.cuh): every GEMM-shaped piece of the time loop -- the hidden-layer products of f and
+    of its VJP, and ALL parameter-gradient contractions over the members -- runs on tcgen05 with bf16 operands and fp32 TMEM
+    accumulators.  BASELINE C4: <= 2e-2 relative to the fp64 oracle for the bf16 path (observed 1e-3 .. 7e-3)."""
     T, dt = 1.5, 0.05
     saveat = np.linspace(0.05, T, 30)
     rng = np.random.default_rng(0)
     u0 = rng.uniform(-2, 2, (2, N)); p = _weights()
-    cfg = O.make_cfg("mlp", "interpolating", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
-    ref = O.gradient(cfg, saveat, u0, p)
-    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype="bf16_f32acc", cost=b.AffineCost(1.0, -0.5))
+    dL = None if cost == "affine" else rng.standard_normal((30, 2, N))
+    cfg = O.make_cfg("mlp", "interpolating", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5) if cost == "affine" else ("explicit",), mlp_hidden=H)
+    ref = O.gradient(cfg, saveat, u0, p, dLdu=dL)
+    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype="bf16_f32acc",
+                           cost=b.AffineCost(1.0, -0.5) if cost == "affine" else None)
     saved, status = eng.forward(u0, p)
+    assert (np.asarray(status) == 0).all()
+    du0, dp = eng.reverse(dL)
+    assert _rel(saved, ref["saved"]) < 1e-2
+    assert _rel(du0, ref["du0"]) < 1e-2
+    for name, sl in BLOCKS.items():
+        assert _rel(np.asarray(dp)[sl], ref["dp"][sl]) < 2e-2, name
+    err = np.abs(np.asarray(dp)[BLOCKS["W2"]] - ref["dp"][BLOCKS["W2"]]) / np.abs(ref["dp"][BLOCKS["W2"]]).max()
+    assert np.sqrt(np.mean(err ** 2)) < 2e-3                           # typical error: bf16 rounding averaged over the contraction
+    # deterministic: same launch, same bits
+    du0b, dpb = eng.reverse(dL)
+    assert np.array_equal(np.asarray(du0), np.asarray(du0b)) and np.array_equal(np.asarray(dp), np.asarray(dpb))
+    eng.close()
+
+
+def test_mlp_bf16_members_not_a_multiple_of_the_tile():
+    """N = 130 = one full 128-member tile + 2: the pad rows of the second tile must contribute nothing to any gradient."""
+    N, T, dt = 130, 1.5, 0.05
+    saveat = np.linspace(0.05, T, 30)
+    rng = np.random.default_rng(3)
+    u0 = rng.uniform(-2, 2, (2, N)); p = _weights()
+    ref = O.gradient(O.make_cfg("mlp", "interpolating", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H), saveat, u0, p)
+    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype="bf16_f32acc", cost=b.AffineCost(1.0, -0.5))
+    eng.forward(u0, p)
     du0, dp = eng.reverse()
-    w2 = slice(3 * H, 3 * H + H * H)
-    assert _rel(du0, ref["du0"]) < 2e-5
-    assert _rel(dp[w2], ref["dp"][w2]) < 2e-2
-    err = np.abs(dp[w2] - ref["dp"][w2]) / np.abs(ref["dp"][w2]).max()
-    assert np.sqrt(np.mean(err ** 2)) < 2e-3                           # typical error: bf16 rounding averaged over K = 6 S N
-    rest = np.r_[0:3 * H, 3 * H + H * H:P]
-    assert _rel(dp[rest], ref["dp"][rest]) < 1e-5                      # the other gradients are the fp32 path
-    # against the fp32 path of the same engine
-    eng32 = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype="f32", cost=b.AffineCost(1.0, -0.5))
-    eng32.forward(u0, p); _, dp32 = eng32.reverse()
-    assert np.array_equal(dp[rest], dp32[rest])
-    eng.close(); eng32.close()
+    assert _rel(du0, ref["du0"]) < 1e-2 and _rel(dp, ref["dp"]) < 2e-2
+    eng.close()
 
 
 def test_mlp_unsupported_combinations_fail_loudly():
