@@ -380,7 +380,7 @@ def run_secondary(args):
         p = np.concatenate([(rng.standard_normal((H, 2)) / np.sqrt(2)).ravel(order="F"), 0.1 * rng.standard_normal(H),
                             (rng.standard_normal((H, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(H),
                             (rng.standard_normal((2, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(2)])
-        dtype = args.dtype or "f32"       # f32 | f64 | bf16_f32acc
+        dtype = args.dtype or "bf16_f32acc"       # bf16_f32acc (the named config: tensor-core VJP) | f32 | f64
         eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, on_device=True, dtype=dtype, cost=b.AffineCost(1.0, -0.5))
         ocfg = lambda n: O.make_cfg("mlp", "interpolating", "tsit5_fixed", n, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
         name, sample = "C4 MLP 2->64->64->2 shared weights P=4482, InterpolatingAdjoint, Tsit5 fixed dt=0.05, T=1.5, 30 saves", 512
@@ -462,7 +462,7 @@ def main():
     ap.add_argument("--members", type=int, default=0, help="override members per GPU (default 65536) / reference sample")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (multiple of 32, <= 512)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c2f32", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
-    ap.add_argument("--dtype", default="", help="c4 only: f32 (default) or f64")
+    ap.add_argument("--dtype", default="", help="c4 only: bf16_f32acc (default), f32 or f64")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
