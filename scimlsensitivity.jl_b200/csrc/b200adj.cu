@@ -174,7 +174,7 @@ int launch_rev_f32_b(Handle* h, OdeRevArgsT<float> a) {
     a.slots = h->block;
     const int threads = SA == SA_BACKSOLVE ? h->block : balanced_threads(h->block);
     const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D, float>(h->block);
-    if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+    if (smem > 30 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
     tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float><<<h->grid, threads, smem, h->stream>>>(a);
     h->launches++;
     return 0;
@@ -203,11 +203,12 @@ int launch_rev_b(Handle* h, const OdeRevArgs& a0) {
     const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D>(h->block);
     // the continuous-cost variant is a separate instantiation: the headline kernel keeps its register budget
     if (h->cont_on) {
-        if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        if (smem > 30 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
         tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true><<<h->grid, threads, smem, h->stream>>>(a);
     } else {
-        // static smem (barriers, reduction scratch) rides on top of the dynamic tile
-        if (smem > 40 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        // static smem (barriers, reduction scratch, 12 KB hand-over buffers of the travelling groups) rides on top of the
+        // dynamic tile: opt in well below the 48 KB default limit
+        if (smem > 30 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
         tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false><<<h->grid, threads, smem, h->stream>>>(a);
     }
     h->launches++;

@@ -93,3 +93,37 @@ def test_state_errors():
         b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", 4, saveat, (0.0, 1.0), 0.01, block_threads=48)
     with pytest.raises(b.B200AdjError):                             # descending save times
         b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", 4, saveat[::-1].copy(), (0.0, 1.0), 0.01)
+
+
+@pytest.mark.parametrize("per_sm", [160, 192, 224, 448])
+@pytest.mark.parametrize("sa", ["gauss", "interpolating", "quadrature"])
+def test_travelling_warp_groups_all_remainders(per_sm, sa):
+    """One block per SM with 5, 6, 7 or 14 warp groups: 1, 2 or 3 groups travel round the four sub-partitions
+    (csrc/ode_tsit5.cuh).  Per-member parameters, so every member's own dp and du0 are compared with the oracle (sampled),
+    and the shared-parameter gradient equals the sum of the per-member ones."""
+    import torch
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    N = nsm * per_sm - 37                      # ragged last block
+    T, dt = 0.5, 0.01
+    rng = np.random.default_rng(per_sm)
+    u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N))
+    p = np.array([10.0, 28.0, 8.0 / 3.0])[:, None] * (1.0 + 0.01 * rng.standard_normal((3, N)))
+    t = np.linspace(0.0, T, 6)
+    kw = dict(quad_abstol=1e-10, quad_reltol=1e-10) if sa == "quadrature" else {}
+    eng = b.DeviceEnsemble("lorenz", sa, "tsit5_fixed", N, t, (0.0, T), dt, shared_p=False, cost=b.AffineCost(1.0, -2.0), **kw)
+    eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    idx = np.r_[0:40, N - 40:N, rng.choice(N, 80, replace=False)]           # first block, ragged last block, random members
+    ref = O.gradient(O.make_cfg("lorenz", sa, "tsit5_fixed", len(idx), t, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0), shared_p=False, **kw),
+                     t, u0[:, idx], p[:, idx])
+    assert _rel(np.asarray(du0)[:, idx], ref["du0"]) < 1e-9
+    assert _rel(np.asarray(dp)[:, idx], ref["dp"]) < (1e-7 if sa == "quadrature" else 1e-9)
+    eng.close()
+    if sa != "quadrature":
+        p0 = np.array([10.0, 28.0, 8.0 / 3.0])
+        e1 = b.DeviceEnsemble("lorenz", sa, "tsit5_fixed", N, t, (0.0, T), dt, shared_p=True, cost=b.AffineCost(1.0, -2.0))
+        e2 = b.DeviceEnsemble("lorenz", sa, "tsit5_fixed", N, t, (0.0, T), dt, shared_p=False, cost=b.AffineCost(1.0, -2.0))
+        e1.forward(u0, p0); e2.forward(u0, np.repeat(p0[:, None], N, 1))
+        _, dps = e1.reverse(); _, dpm = e2.reverse()
+        assert _rel(np.asarray(dps), np.asarray(dpm).sum(axis=1)) < 1e-11
+        e1.close(); e2.close()
