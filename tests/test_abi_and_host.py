@@ -135,3 +135,26 @@ def test_preset_time_callback_tables_and_host_side_rejections():
     with pytest.raises(NotImplementedError):          # fixed-step stepper
         b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=False, dt=0.01), b.EnsembleB200(), trajectories=2, saveat=ts,
                 callback=b.PresetTimeCallback([5.0], b.AffineAffect(1.0, 0.0)))
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver runs first): exactly one JSON line on stdout with the contract's
+    keys, measured on the oracle port; other ranks of a torchrun launch print nothing and exit 0."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--members", "128"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["metric"] == "ensemble adjoint trajectories/sec" and d["higher_is_better"] is True
+    other = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--members", "128"],
+                           capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert other.returncode == 0 and other.stdout.strip() == ""
