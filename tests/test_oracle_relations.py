@@ -442,3 +442,22 @@ def test_robertson_gradient_matches_independent_stiff_forward_sensitivity_solve(
         r = O.gradient(O.make_cfg("robertson", sa, "rosenbrock23", 1, ts, 0.0, T, cost=("affine", 1.0, 0.0), **kw), ts, u0[:, None], k)
         assert np.max(np.abs(r["saved"][:, :, 0].T - sol.y[:3])) < 1e-7
         assert np.max(np.abs(r["dp"] - dp_ref) / np.abs(dp_ref)) < tol, (sa, r["dp"], dp_ref)
+
+
+def test_sde_interpolating_agrees_with_backsolve_and_the_discrete_solver():
+    """SDE InterpolatingAdjoint (src/interpolating_adjoint.jl:453-613: forward states looked up from the stored solution
+    instead of integrating y backwards) against BacksolveAdjoint and against differentiation through the discrete EulerHeun
+    solver with the same noise (the reference compares its SDE sensealgs with each other and with ForwardDiff through the
+    solver at rtol 1e-3 .. 1e-4, test/SDE1/sde_stratonovich.jl:141-207)."""
+    N, dt, S = 2, 0.0025, 400
+    dW = np.sqrt(dt) * np.random.default_rng(7).standard_normal((S, 2, N))
+    saveat = np.linspace(0, 1, 101); u0 = np.ones((2, N)); p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
+    res = {}
+    for sa in ("backsolve", "interpolating"):
+        cfg = O.make_cfg("sde_lv", sa, "euler_heun", N, saveat, 0.0, 1.0, dt=dt, cost=("affine", 0.0, 1.0))
+        res[sa] = O.gradient(cfg, saveat, u0, p, dW=dW)
+    cfg = O.make_cfg("sde_lv", "backsolve", "euler_heun", N, saveat, 0.0, 1.0, dt=dt, cost=("affine", 0.0, 1.0))
+    g = _fd_grad(lambda q: O.loss(cfg, saveat, u0, q, dW=dW).sum(), p, h=1e-5)
+    assert np.allclose(res["interpolating"]["dp"], g, rtol=2e-3)
+    assert np.allclose(res["interpolating"]["dp"], res["backsolve"]["dp"], rtol=2e-3)
+    assert np.allclose(res["interpolating"]["du0"], res["backsolve"]["du0"], rtol=2e-3)
