@@ -288,6 +288,28 @@ static int fam_djac(const family_t* F, const double* p, const double* yd, double
     }
 }
 
+/* Parameter Jacobian F[i*P+q] = df_i/dp_q (the `paramjac` of src/derivative_wrappers.jl:284-340) and its derivative along
+ * ydot, dF[i*P+q] = sum_k d2f_i/dp_q du_k ydot_k: needed when a Rosenbrock method integrates the AUGMENTED adjoint state
+ * (Interpolating / Backsolve), whose Jacobian and time derivative contain F(y(t)). */
+static int fam_pjac(const family_t* F, const double* y, double* Fm) {
+    switch (F->family) {
+    case FAM_LV:      Fm[0] = y[0]; Fm[1] = -y[0] * y[1]; Fm[2] = 0; Fm[3] = 0;   Fm[4] = 0; Fm[5] = 0; Fm[6] = -y[1]; Fm[7] = y[0] * y[1]; return 0;
+    case FAM_LORENZ:  Fm[0] = y[1] - y[0]; Fm[1] = 0; Fm[2] = 0;   Fm[3] = 0; Fm[4] = y[0]; Fm[5] = 0;   Fm[6] = 0; Fm[7] = 0; Fm[8] = -y[2]; return 0;
+    case FAM_ROBERTSON: Fm[0] = -y[0]; Fm[1] = 0; Fm[2] = y[1] * y[2];   Fm[3] = y[0]; Fm[4] = -y[1] * y[1]; Fm[5] = -y[1] * y[2];   Fm[6] = 0; Fm[7] = y[1] * y[1]; Fm[8] = 0; return 0;
+    default: return -1;
+    }
+}
+static int fam_dpjac(const family_t* F, const double* y, const double* yd, double* dF) {
+    switch (F->family) {
+    case FAM_LV: { double s = yd[0] * y[1] + y[0] * yd[1];
+        dF[0] = yd[0]; dF[1] = -s; dF[2] = 0; dF[3] = 0;   dF[4] = 0; dF[5] = 0; dF[6] = -yd[1]; dF[7] = s; return 0; }
+    case FAM_LORENZ: dF[0] = yd[1] - yd[0]; dF[1] = 0; dF[2] = 0;   dF[3] = 0; dF[4] = yd[0]; dF[5] = 0;   dF[6] = 0; dF[7] = 0; dF[8] = -yd[2]; return 0;
+    case FAM_ROBERTSON: { double s = yd[1] * y[2] + y[1] * yd[2], q = 2 * y[1] * yd[1];
+        dF[0] = -yd[0]; dF[1] = 0; dF[2] = s;   dF[3] = yd[0]; dF[4] = -q; dF[5] = -s;   dF[6] = 0; dF[7] = q; dF[8] = 0; return 0; }
+    default: return -1;
+    }
+}
+
 /* =====================================================================================
  * Tsit5 (Tsitouras 2011) tableau and 4th-order dense output  [UPSTREAM OrdinaryDiffEq; SURVEY App. B]
  * ===================================================================================== */
@@ -653,14 +675,40 @@ static void adj_rhs(double t, const double* z, double* dz, void* c) {
  * d/dlam = -J(y(t))^T (src/quadrature_adjoint.jl:170-192), d/dt = -(dJ/dt)^T lam with ydot from the
  * forward interpolant (what ForwardDiff-through-sol(t) yields, src/quadrature_adjoint.jl:67-71). */
 static void adj_jac(double t, const double* z, double* Jout, double* dT, void* c) {
-    adj_ctx* x = (adj_ctx*)c; const family_t* F = x->F; int d = F->d;
-    double y[8], yd[8], J[64], dJ[64];
-    dense_eval(x->sol, t, 1, y, yd);
+    adj_ctx* x = (adj_ctx*)c; const family_t* F = x->F; const int d = F->d, P = F->P;
+    double y[8], yd[8], J[64], dJ[64], Fm[64], dF[64];
+    if (x->sensealg == SA_BACKSOLVE) {
+        /* z = [lam; mu; y], autonomous: dT = 0.  Rows: lam' = -J(y)'lam (- ca y - cb), mu' = -F(y)'lam, y' = f(y). */
+        const int L = 2 * d + P; const double* yy = z + d + P;
+        for (int i = 0; i < L * L; i++) Jout[i] = 0;
+        for (int i = 0; i < L; i++) dT[i] = 0;
+        fam_jac(F, yy, x->p, J); fam_pjac(F, yy, Fm);
+        for (int i = 0; i < d; i++) for (int j = 0; j < d; j++) { Jout[i * L + j] = -J[j * d + i]; Jout[(d + P + i) * L + (d + P + j)] = J[i * d + j]; }
+        for (int q = 0; q < P; q++) for (int j = 0; j < d; j++) Jout[(d + q) * L + j] = -Fm[j * P + q];
+        for (int j = 0; j < d; j++) {               /* column of d/dy_j: Hessian contractions with lam */
+            double e[8] = {0}; e[j] = 1.0;
+            fam_djac(F, x->p, e, dJ); fam_dpjac(F, yy, e, dF);
+            for (int i = 0; i < d; i++) { double a = 0; for (int k = 0; k < d; k++) a -= dJ[k * d + i] * z[k]; Jout[i * L + (d + P + j)] = a - (x->cont && i == j ? x->ca : 0.0); }
+            for (int q = 0; q < P; q++) { double a = 0; for (int k = 0; k < d; k++) a -= dF[k * P + q] * z[k]; Jout[(d + q) * L + (d + P + j)] = a; }
+        }
+        return;
+    }
+    dense_eval(x->sol, t, t != x->tev, y, yd);
     fam_jac(F, y, x->p, J); fam_djac(F, x->p, yd, dJ);
+    const int L = (x->sensealg == SA_INTERPOLATING) ? d + P : d;
+    if (L > d) for (int i = 0; i < L * L; i++) Jout[i] = 0;
     for (int i = 0; i < d; i++) {
         double s = 0;
-        for (int j = 0; j < d; j++) { Jout[i * d + j] = -J[j * d + i]; s -= dJ[j * d + i] * z[j]; }
-        dT[i] = s;
+        for (int j = 0; j < d; j++) { Jout[i * L + j] = -J[j * d + i]; s -= dJ[j * d + i] * z[j]; }
+        dT[i] = s - (x->cont ? x->ca * yd[i] : 0.0);          /* d/dt of -(ca y(t) + cb) */
+    }
+    if (L > d) {                                   /* InterpolatingAdjoint: mu' = -F(y(t))' lam */
+        fam_pjac(F, y, Fm); fam_dpjac(F, y, yd, dF);
+        for (int q = 0; q < P; q++) {
+            double s = 0;
+            for (int j = 0; j < d; j++) { Jout[(d + q) * L + j] = -Fm[j * P + q]; s -= dF[j * P + q] * z[j]; }
+            dT[d + q] = s;
+        }
     }
 }
 
@@ -839,7 +887,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     const int L = (sa == SA_INTERPOLATING) ? d + P : (sa == SA_BACKSOLVE ? 2 * d + P : d);
     const int ros = (cfg->stepper == ST_ROSENBROCK23);
     const int adaptive = (cfg->stepper == ST_TSIT5_ADAPTIVE) || ros;
-    if (ros && !(sa == SA_GAUSS || sa == SA_QUADRATURE || sa == SA_GAUSSKRONROD)) return -10;
+    if (ros && F->family != FAM_LV && F->family != FAM_LORENZ && F->family != FAM_ROBERTSON) return -10;   /* analytic Jacobians of the adjoint system */
     if (sa == SA_GAUSSKRONROD && !adaptive) return -12;          /* built for the adaptive steppers */
     double T = cfg->t1, t0 = cfg->t0;
     double* z = (double*)calloc(L, sizeof(double)), *zn = (double*)malloc(sizeof(double) * L), *tmp = (double*)malloc(sizeof(double) * L);
@@ -903,7 +951,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     double h = -fabs(cfg->dt);
     if (adaptive && cfg->dt <= 0) h = -1e-4 * (T - t0);
     double qold = 1e-4; long iters = 0; int rc = 0;
-    double f0[8], k1r[8], k2r[8], fnr[8], errv[8], work[64 + 48]; int piv[8];
+    double f0[16], k1r[16], k2r[16], fnr[16], errv[16], work[16 * 16 + 6 * 16]; int piv[16];
     while (t > t0) {
         if (++iters > 50000000) { rc = -20; break; }
         /* next tstop: next save time below t (PresetTimeCallback tstops), else t0.  For Backsolve with

@@ -461,3 +461,25 @@ def test_sde_interpolating_agrees_with_backsolve_and_the_discrete_solver():
     assert np.allclose(res["interpolating"]["dp"], g, rtol=2e-3)
     assert np.allclose(res["interpolating"]["dp"], res["backsolve"]["dp"], rtol=2e-3)
     assert np.allclose(res["interpolating"]["du0"], res["backsolve"]["du0"], rtol=2e-3)
+
+
+def test_rosenbrock23_on_the_augmented_adjoint_states():
+    """InterpolatingAdjoint / BacksolveAdjoint integrated by Rosenbrock23 (the reference runs its stiff-solver matrix over all
+    sensealgs, test/Core2/stiff_adjoints.jl:204-252, agreement rtol 1e-2): the Rosenbrock step sees the Jacobian and the
+    time derivative of the augmented state [lam; mu] (and [lam; mu; y]), built from J, dJ/dt, the parameter Jacobian F and
+    dF/dt.  Oracle-only so far (the device has Gauss / GaussKronrod / Quadrature for Rosenbrock23)."""
+    ts = np.logspace(-2, 2, 10); ts[-1] = 100.0
+    u0 = np.array([[1.0], [0.0], [0.0]]); k = np.array([0.04, 3e7, 1e4])
+    kw = dict(abstol=1e-9, reltol=1e-9, quad_abstol=1e-13, quad_reltol=1e-10)
+    r = {sa: O.gradient(O.make_cfg("robertson", sa, "rosenbrock23", 1, ts, 0.0, 100.0, cost=("affine", 1.0, 0.0), **kw), ts, u0, k)
+         for sa in ("quadrature", "interpolating")}
+    assert np.allclose(r["interpolating"]["dp"], r["quadrature"]["dp"], rtol=1e-6)
+    assert np.allclose(r["interpolating"]["du0"], r["quadrature"]["du0"], rtol=1e-6)
+    # non-stiff problem, stiff solver: every sensealg reproduces the tight-tolerance Tsit5 gradient
+    t = np.arange(0.0, 10.01, 0.5)
+    ref = O.gradient(O.make_cfg("lv", "interpolating", "tsit5_adaptive", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), abstol=1e-12, reltol=1e-12), t, LV_U0, LV_P)
+    for sa in ("interpolating", "backsolve", "gauss", "gauss_kronrod", "quadrature"):
+        rr = O.gradient(O.make_cfg("lv", sa, "rosenbrock23", 1, t, 0.0, 10.0, cost=("affine", 0.0, 1.0), abstol=1e-9, reltol=1e-9,
+                                   quad_abstol=1e-12, quad_reltol=1e-10, ckpt_every_step=True), t, LV_U0, LV_P)
+        assert np.max(np.abs(rr["dp"] - ref["dp"])) < 1e-5 * np.max(np.abs(ref["dp"])), sa          # 2nd-order method at 1e-9
+        assert np.max(np.abs(rr["du0"] - ref["du0"])) < 1e-5 * np.max(np.abs(ref["du0"])), sa
