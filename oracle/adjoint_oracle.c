@@ -888,7 +888,6 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     const int ros = (cfg->stepper == ST_ROSENBROCK23);
     const int adaptive = (cfg->stepper == ST_TSIT5_ADAPTIVE) || ros;
     if (ros && F->family != FAM_LV && F->family != FAM_LORENZ && F->family != FAM_ROBERTSON) return -10;   /* analytic Jacobians of the adjoint system */
-    if (sa == SA_GAUSSKRONROD && !adaptive) return -12;          /* built for the adaptive steppers */
     double T = cfg->t1, t0 = cfg->t0;
     double* z = (double*)calloc(L, sizeof(double)), *zn = (double*)malloc(sizeof(double) * L), *tmp = (double*)malloc(sizeof(double) * L);
     double* k = (double*)malloc(sizeof(double) * 7 * L);

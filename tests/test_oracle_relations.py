@@ -351,8 +351,10 @@ def test_gauss_kronrod_agrees_with_the_other_adjoints():
     e_gk = np.max(np.abs(rr["gauss_kronrod"] - rr["quadrature"]) / np.abs(rr["quadrature"]))
     e_g = np.max(np.abs(rr["gauss"] - rr["quadrature"]) / np.abs(rr["quadrature"]))
     assert e_gk < 1e-6 and e_gk < e_g
-    with pytest.raises(RuntimeError):       # built for the adaptive steppers
-        O.gradient(O.make_cfg("lv", "gauss_kronrod", "tsit5_fixed", 2, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0)), t, u0, p)
+    # fixed-step Tsit5 (oracle only; the device carries GaussKronrod on the adaptive steppers): same reverse solve as Gauss
+    rf = {sa: O.gradient(O.make_cfg("lv", sa, "tsit5_fixed", 2, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0)), t, u0, p) for sa in ("gauss", "gauss_kronrod")}
+    assert np.allclose(rf["gauss_kronrod"]["du0"], rf["gauss"]["du0"], rtol=1e-13)
+    assert np.max(np.abs(rf["gauss_kronrod"]["dp"] - rf["gauss"]["dp"])) < 1e-6 * np.max(np.abs(rf["gauss"]["dp"]))
 
 
 # ---- an independent implementation: forward (variational) sensitivities with SciPy's DOP853 ---------------------------
