@@ -469,8 +469,13 @@ static double tstop_snap(double tnext, double tstop) {
 
 /* Fixed-step Tsit5 forward solve, dense (solve(prob, Tsit5(); adaptive=false, dt)).  Grid t0 + n dt,
  * last step shortened to hit t1. */
-static void forward_tsit5_fixed(const family_t* F, const double* p, const double* u0, double t0, double t1, double dt, dense_t* S) {
-    int d = F->d; fwd_ctx c = {F, p, 0};
+/* events (evc): preset times ON the dt grid (the caller's responsibility; the reverse solve finds them by time) */
+static void forward_tsit5_fixed(const family_t* F, const double* p, const double* u0, double t0, double t1, double dt, dense_t* S, const oracle_cfg* evc) {
+    int d = F->d;
+    double pcur[64];
+    for (int q = 0; q < F->P && q < 64; q++) pcur[q] = p[q];
+    const int E = evc ? evc->n_events : 0; int ev = 0;
+    fwd_ctx c = {F, (E > 0 && evc->ev_pscale) ? pcur : p, 0};
     int nest = (int)ceil((t1 - t0) / dt) + 2;
     dense_init(S, d, DENSE_TSIT5, nest);
     double* k = (double*)malloc(sizeof(double) * 7 * d), *tmp = (double*)malloc(sizeof(double) * d), *un = (double*)malloc(sizeof(double) * d);
@@ -480,13 +485,21 @@ static void forward_tsit5_fixed(const family_t* F, const double* p, const double
     while (t < t1) {
         double tn = tstop_snap(t0 + (n + 1) * dt, t1);
         if (tn > t1) tn = t1;
+        const int at_ev = ev < E && fabs(evc->ev_times[ev] - tn) <= 100 * 2.220446049250313e-16 * fmax(fabs(tn), 1.0);
+        if (at_ev) tn = evc->ev_times[ev];       /* the knot IS the event time (the reverse solve stops at exactly this value) */
         double h = tn - t;
         dense_grow(S);
         tsit5_step(fwd_rhs, &c, d, t, h, S->u + (size_t)n * d, k, un, tmp);
         memcpy(S->k + (size_t)n * 7 * d, k, sizeof(double) * 7 * d);
-        memcpy(S->u + (size_t)(n + 1) * d, un, sizeof(double) * d);
         S->t[n + 1] = tn;
         memcpy(k, k + 6 * d, sizeof(double) * d);  /* FSAL */
+        if (at_ev) {
+            for (int i = 0; i < d; i++) un[i] = evc->ev_scale[(size_t)ev * d + i] * un[i] + evc->ev_shift[(size_t)ev * d + i];
+            ev++;
+            if (evc->ev_pscale) event_params(evc, F->P, ev, p, pcur);
+            fwd_rhs(tn, un, k, &c);
+        }
+        memcpy(S->u + (size_t)(n + 1) * d, un, sizeof(double) * d);
         t = tn; n++; S->n = n;
     }
     free(k); free(tmp); free(un);
@@ -895,7 +908,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     double* gu = ybuf + d, *lamq = gu + d, *dlq = lamq + d, *integ = dlq + d, *acc = integ + P;
     adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0, cfg->cont_cost, cfg->cont_a, cfg->cont_b, INFINITY};
     int evc = cfg->n_events - 1;     /* next event below t */
-    if (cfg->n_events > 0 && (cfg->stepper != ST_TSIT5_ADAPTIVE || sa == SA_QUADRATURE)) return -11;
+    if (cfg->n_events > 0 && ((cfg->stepper != ST_TSIT5_ADAPTIVE && cfg->stepper != ST_TSIT5_FIXED) || sa == SA_QUADRATURE)) return -11;
     for (int q = 0; q < P; q++) acc[q] = 0;
     adjdense_t adj; int have_adj = (sa == SA_QUADRATURE);
     if (have_adj) adjdense_init(&adj, L, ros ? DENSE_ROS23 : DENSE_TSIT5);
@@ -1142,7 +1155,7 @@ static int is_sde(const oracle_cfg* c) { return c->stepper == ST_EM || c->steppe
 
 static int forward_dense_member(const oracle_cfg* cfg, const family_t* F, const double* p, const double* u0, dense_t* S) {
     switch (cfg->stepper) {
-    case ST_TSIT5_FIXED: forward_tsit5_fixed(F, p, u0, cfg->t0, cfg->t1, cfg->dt, S); return 0;
+    case ST_TSIT5_FIXED: forward_tsit5_fixed(F, p, u0, cfg->t0, cfg->t1, cfg->dt, S, cfg); return 0;
     case ST_TSIT5_ADAPTIVE: return forward_tsit5_adaptive(F, p, u0, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, cfg->dt, S, cfg);
     case ST_ROSENBROCK23: return forward_ros23(F, p, u0, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, S);
     default: return -5;

@@ -485,3 +485,17 @@ def test_rosenbrock23_on_the_augmented_adjoint_states():
                                    quad_abstol=1e-12, quad_reltol=1e-10, ckpt_every_step=True), t, LV_U0, LV_P)
         assert np.max(np.abs(rr["dp"] - ref["dp"])) < 1e-5 * np.max(np.abs(ref["dp"])), sa          # 2nd-order method at 1e-9
         assert np.max(np.abs(rr["du0"] - ref["du0"])) < 1e-5 * np.max(np.abs(ref["du0"])), sa
+
+
+def test_events_on_the_fixed_step_grid_oracle_only():
+    """Preset-time events whose times lie on the dt grid, fixed-step Tsit5 (oracle only; the device carries events on the
+    adaptive path).  The forward knot at an event is stored as exactly the event time -- t0 + n dt differs from it by an ulp
+    (2.03 = 203 * 0.01) and the reverse solve, which stops at the event time itself, would otherwise read the pre-event
+    state at its last stage above the event (2 % error in the gradient)."""
+    t = np.arange(0.0, 10.0001, 0.5)
+    ev = ([2.03, 5.1], [[1.0, 1.0], [1.0, 1.0]], [[2.0, 0.0], [0.0, 0.0]], [[1.0] * 4, [2.0, 1.0, 0.5, 1.0]], [[0.0] * 4, [-0.5, 0.0, 0.1, 0.0]])
+    lcfg = O.make_cfg("lv", "interpolating", "tsit5_fixed", 1, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0), events=ev)
+    gp = _fd_grad(lambda q: O.loss(lcfg, t, LV_U0, q)[0], LV_P)
+    for sa, every in (("interpolating", False), ("gauss", False), ("backsolve", True)):
+        r = O.gradient(O.make_cfg("lv", sa, "tsit5_fixed", 1, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0), events=ev, ckpt_every_step=every), t, LV_U0, LV_P)
+        assert np.max(np.abs(r["dp"] - gp)) < 1e-7 * np.max(np.abs(gp)), sa
