@@ -58,6 +58,9 @@ enum { B200ADJ_COST_EXPLICIT = 0, B200ADJ_COST_AFFINE = 1 };
                                               /* instead of regenerating it from the Philox counter in reverse      */
 
 #define B200ADJ_FLAG_TRACE              16u   /* record (smid, start, end) of every block of the reverse kernel      */
+#define B200ADJ_FLAG_NO_ROTATE          32u   /* tuning: launch exactly block_threads threads, no travelling warp groups */
+/* flags fixed at create (the others can be changed per reverse pass by b200adj_set_reverse_options) */
+#define B200ADJ_CREATE_FLAGS (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE | B200ADJ_FLAG_NO_ROTATE)
 
 /* error codes */
 #define B200ADJ_OK                 0

@@ -54,20 +54,54 @@ def nvcc_path():
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu for sm_100a into scimlsensitivity.jl_b200/libb200adj.so (in-tree, travels with gpurun)."""
-    srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh"))]
+    from concurrent.futures import ThreadPoolExecutor
+    srcs = [os.path.join(_CSRC, f) for f in sorted(os.listdir(_CSRC)) if f.endswith((".cu", ".cuh", ".inc", ".h"))]
     srcs.append(os.path.join(_ROOT, "include", "b200adj.h"))
     if not force and os.path.exists(LIB_PATH) and all(os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs):
         return LIB_PATH
     cus = [s for s in srcs if s.endswith(".cu")]
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v", "-o", LIB_PATH] + cus
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    objdir = os.path.join(_PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+
+    def deps(cu):
+        """headers a translation unit includes, transitively (quoted includes inside csrc/ and include/)"""
+        seen, todo = set(), [cu]
+        while todo:
+            f = todo.pop()
+            if f in seen or not os.path.exists(f):
+                continue
+            seen.add(f)
+            for line in open(f):
+                if line.startswith('#include "'):
+                    todo.append(os.path.normpath(os.path.join(os.path.dirname(f), line.split('"')[1])))
+        return seen
+
+    def compile_one(cu):
+        obj = os.path.join(objdir, os.path.basename(cu)[:-3] + ".o")
+        log = obj[:-2] + ".log"
+        if not force and os.path.exists(obj) and os.path.exists(log) and all(os.path.getmtime(obj) >= os.path.getmtime(d) for d in deps(cu)):
+            return obj, 0, open(log).read()
+        res = subprocess.run([nvcc_path()] + flags + ["-c", cu, "-o", obj], capture_output=True, text=True)
+        out = res.stdout + res.stderr
+        with open(log, "w") as f:
+            f.write(out)
+        return obj, res.returncode, out
+
+    # heaviest translation units first (the fixed-step and adaptive Tsit5 reverse kernels dominate the build)
+    order = sorted(cus, key=lambda c: 0 if "disp_fixed" in c else 1 if "disp_t5a" in c else 2)
+    with ThreadPoolExecutor(max_workers=min(len(order), os.cpu_count() or 4)) as ex:
+        results = list(ex.map(compile_one, order))
     with open(os.path.join(_PKG, "ptxas.log"), "w") as f:
-        f.write(res.stdout + res.stderr)
+        f.write("".join(r[2] for r in results))
+    bad = [r for r in results if r[1] != 0]
+    if bad:
+        raise RuntimeError("nvcc failed:\n" + "\n".join(r[2][-4000:] for r in bad))
+    res = subprocess.run([nvcc_path(), "-shared", "-o", LIB_PATH] + [r[0] for r in results] + ["-ldl"], capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stderr[-4000:])
+        raise RuntimeError("link failed:\n" + res.stderr[-4000:])
     if verbose:
-        print(res.stderr[-2000:])
+        print("".join(r[2] for r in results)[-2000:])
     return LIB_PATH
 
 

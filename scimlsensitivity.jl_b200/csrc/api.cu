@@ -1,77 +1,12 @@
-// b200adj.cu -- C ABI (include/b200adj.h) of the B200-native ensemble continuous-adjoint engine.
-// Handle management, validation, host<->device staging and kernel dispatch.  No torch types, no CPU fallback.
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-#include <stdlib.h>
-
-#include <string>
-#include <vector>
-
-#include "../../include/b200adj.h"
-#include "ode_tsit5.cuh"
-#include "sde_em.cuh"
-#include "ros23.cuh"
-#include "mlp.cuh"
-#include "tsit5_quad.cuh"
-#include "mlp_umma.cuh"
-#include "mlp_tc.cuh"
-#include "tsit5_adaptive.cuh"
+// api.cu -- C ABI (include/b200adj.h) of the B200-native ensemble continuous-adjoint engine.
+// Handle management, validation, host<->device staging; kernel dispatch goes through handle.h into disp_*.cu.
+// No torch types, no CPU fallback.
+#include "handle.h"
 
 using namespace b200adj;
-
 namespace {
 
 thread_local std::string g_create_error;
-
-struct Handle {
-    b200adj_cfg cfg;
-    std::vector<double> saveat;
-    std::vector<int32_t> save_of_step;
-    int S = 0;
-    int64_t Npad = 0;
-    int block = 64, grid = 0;
-    cudaStream_t stream = nullptr, own_stream = nullptr;
-    // device memory owned by the handle
-    double* d_ckpt = nullptr;         // [S+1][d][N]
-    double* d_noise = nullptr;        // [S][m][N] (SDE, stored-noise mode)
-    double* d_partials = nullptr;     // [grid][P]
-    double* d_adj_dense = nullptr;    // QuadratureAdjoint, fixed-step Tsit5: [S][8][d][Npad]
-    void *d_tapeA = nullptr, *d_tapeB = nullptr; float* d_umma_partials = nullptr; int umma_ctas = 0; int64_t Ktot = 0;   // MLP bf16 mode
-    size_t qpart_blocks_fixed = 0;
-    unsigned long long* d_trace = nullptr;   // [grid][3] block trace (B200ADJ_FLAG_TRACE)
-    unsigned int* d_ticket = nullptr;
-    int32_t* d_save_of_step = nullptr;
-    // adaptive Rosenbrock23 path: per-member dense forward / reverse solutions
-    bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
-    double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
-    bool cont_on = false; double cont_a = 0, cont_b = 0;   // continuous cost family
-    bool mlp_tc = false;              // BF16_F32ACC: every GEMM-shaped piece of the time loop on tcgen05 (mlp_tc.cuh)
-    double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
-    int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
-    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
-    // staging (buffers_on_device == 0)
-    double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
-    int32_t* s_status = nullptr;
-    const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
-    int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr, *d_ev_ps = nullptr, *d_ev_pc = nullptr;      // preset-time events (adaptive Tsit5)
-    bool have_forward = false;
-    bool noise_valid = false;
-    int64_t launches = 0;
-    Tsit5Tables tb;
-    std::string err;
-};
-
-#define CUDA_TRY(h, expr)                                                                      \
-    do {                                                                                       \
-        cudaError_t _e = (expr);                                                               \
-        if (_e != cudaSuccess) {                                                               \
-            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
-            return B200ADJ_ERR_CUDA;                                                           \
-        }                                                                                      \
-    } while (0)
 
 int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
     switch (c.rhs_family) {
@@ -84,10 +19,12 @@ int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
     default: return -1;
     }
 }
+}  // namespace
 
+namespace b200adj {
 // Tsit5 dense-output weights b_j(theta): quartics, expanded once in long double from the published factored form
 // (Tsitouras 2011) and evaluated by Horner.
-void tsit5_weights(double th, double* w, double (*Rout)[4] = nullptr) {
+void tsit5_weights(double th, double* w, double (*Rout)[4]) {
     typedef long double LD;
     static bool init = false;
     static double R[7][5];   // coefficients of theta^0..theta^4
@@ -115,7 +52,9 @@ void tsit5_weights(double th, double* w, double (*Rout)[4] = nullptr) {
     if (Rout) for (int j = 0; j < 7; j++) for (int m = 0; m < 4; m++) Rout[j][m] = R[j][m + 1];
     if (w) for (int j = 0; j < 7; j++) w[j] = (((R[j][4] * th + R[j][3]) * th + R[j][2]) * th + R[j][1]) * th + R[j][0];
 }
+}  // namespace b200adj
 
+namespace {
 // Step-size-scaled Tsit5 tables for one handle (passed to the kernels by value, i.e. through the constant bank).
 void build_tsit5_tables(double h, Tsit5Tables* t) {
     const double A[7][6] = {
@@ -135,186 +74,6 @@ void build_tsit5_tables(double h, Tsit5Tables* t) {
     const double thq[3] = {0.5 * (1.0 - a), 0.5, 0.5 * (1.0 + a)};
     for (int g = 0; g < 3; g++) { tsit5_weights(thq[g], w); for (int j = 0; j < 7; j++) t->hBq[g][j] = h * w[j]; }
     t->hGW[0] = 0.5 * h * (5.0 / 9.0); t->hGW[1] = 0.5 * h * (8.0 / 9.0); t->hGW[2] = 0.5 * h * (5.0 / 9.0);
-}
-
-bool is_sde(const b200adj_cfg& c) { return c.stepper == B200ADJ_ST_EM || c.stepper == B200ADJ_ST_EULER_HEUN; }
-
-// ---------------- kernel dispatch (block size is a runtime value) ----------------
-// Threads per block for `slots` member slots: whole warp rows (multiples of 128 threads) with travelling warp groups
-// in the top row when the slot count would leave the SM's four sub-partitions unbalanced (tsit5_reverse_kernel);
-// B200ADJ_NO_ROTATE=1 launches exactly `slots` threads (tuning / A-B runs).
-static int balanced_threads(int slots) {
-    static const bool no_rotate = getenv("B200ADJ_NO_ROTATE") && atoi(getenv("B200ADJ_NO_ROTATE")) != 0;
-    if (!no_rotate && slots > 128 && (slots % 128) != 0) return ((slots + 127) / 128) * 128;
-    return slots;
-}
-template <class Fam>
-int launch_fwd(Handle* h, const OdeFwdArgs& a) {
-    if (h->cfg.shared_p) tsit5_forward_kernel<Fam, true><<<h->grid, h->block, 0, h->stream>>>(a);
-    else tsit5_forward_kernel<Fam, false><<<h->grid, h->block, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-// ---- fp32 variant of the fixed-step path (LV / Lorenz; Interpolating / Gauss / Backsolve; no continuous cost) ----
-template <class T, class S> static void cast_tables(const S& src, T* dst) {
-    for (int i = 0; i < 7; i++) for (int j = 0; j < 6; j++) dst->hA[i][j] = (float)src.hA[i][j];
-    for (int i = 0; i < 4; i++) for (int j = 0; j < 7; j++) dst->hBst[i][j] = (float)src.hBst[i][j];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 7; j++) dst->hBq[i][j] = (float)src.hBq[i][j];
-    for (int i = 0; i < 3; i++) dst->hGW[i] = (float)src.hGW[i];
-}
-template <class Fam>
-int launch_fwd_f32(Handle* h, const OdeFwdArgsT<float>& a) {
-    if (h->cfg.shared_p) tsit5_forward_kernel<Fam, true, float><<<h->grid, h->block, 0, h->stream>>>(a);
-    else tsit5_forward_kernel<Fam, false, float><<<h->grid, h->block, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-template <class Fam, int SA, bool SHARED_P, int COST>
-int launch_rev_f32_b(Handle* h, OdeRevArgsT<float> a) {
-    a.slots = h->block;
-    const int threads = SA == SA_BACKSOLVE ? h->block : balanced_threads(h->block);
-    const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D, float>(h->block);
-    if (smem > 30 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-    tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false, float><<<h->grid, threads, smem, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-template <class Fam, int SA>
-int launch_rev_f32_sa(Handle* h, const OdeRevArgsT<float>& a) {
-    const bool sp = h->cfg.shared_p;
-    const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (sp) return ex ? launch_rev_f32_b<Fam, SA, true, COST_EXPLICIT>(h, a) : launch_rev_f32_b<Fam, SA, true, COST_AFFINE>(h, a);
-    return ex ? launch_rev_f32_b<Fam, SA, false, COST_EXPLICIT>(h, a) : launch_rev_f32_b<Fam, SA, false, COST_AFFINE>(h, a);
-}
-template <class Fam>
-int launch_rev_f32(Handle* h, const OdeRevArgsT<float>& a) {
-    switch (h->cfg.sensealg) {
-    case B200ADJ_SA_INTERPOLATING: return launch_rev_f32_sa<Fam, SA_INTERP>(h, a);
-    case B200ADJ_SA_GAUSS: return launch_rev_f32_sa<Fam, SA_GAUSS>(h, a);
-    case B200ADJ_SA_BACKSOLVE: return launch_rev_f32_sa<Fam, SA_BACKSOLVE>(h, a);
-    default: return B200ADJ_ERR_UNSUPPORTED;
-    }
-}
-template <class Fam, int SA, bool SHARED_P, int COST>
-int launch_rev_b(Handle* h, const OdeRevArgs& a0) {
-    OdeRevArgs a = a0;
-    a.slots = h->block;
-    const int threads = SA == SA_BACKSOLVE ? h->block : balanced_threads(h->block);
-    const size_t smem = SA == SA_BACKSOLVE ? 0 : rev_smem_bytes<Fam::D>(h->block);
-    // the continuous-cost variant is a separate instantiation: the headline kernel keeps its register budget
-    if (h->cont_on) {
-        if (smem > 30 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, true><<<h->grid, threads, smem, h->stream>>>(a);
-    } else {
-        // static smem (barriers, reduction scratch, 12 KB hand-over buffers of the travelling groups) rides on top of the
-        // dynamic tile: opt in well below the 48 KB default limit
-        if (smem > 30 * 1024 && cudaFuncSetAttribute(tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        tsit5_reverse_kernel<Fam, SA, SHARED_P, COST, false><<<h->grid, threads, smem, h->stream>>>(a);
-    }
-    h->launches++;
-    return 0;
-}
-template <class Fam, int SA>
-int launch_rev_sa(Handle* h, const OdeRevArgs& a) {
-    const bool sp = h->cfg.shared_p;
-    const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (sp) return ex ? launch_rev_b<Fam, SA, true, COST_EXPLICIT>(h, a) : launch_rev_b<Fam, SA, true, COST_AFFINE>(h, a);
-    return ex ? launch_rev_b<Fam, SA, false, COST_EXPLICIT>(h, a) : launch_rev_b<Fam, SA, false, COST_AFFINE>(h, a);
-}
-template <class Fam>
-int launch_rev(Handle* h, const OdeRevArgs& a) {
-    switch (h->cfg.sensealg) {
-    case B200ADJ_SA_INTERPOLATING: return launch_rev_sa<Fam, SA_INTERP>(h, a);
-    case B200ADJ_SA_GAUSS: return launch_rev_sa<Fam, SA_GAUSS>(h, a);
-    case B200ADJ_SA_BACKSOLVE: return launch_rev_sa<Fam, SA_BACKSOLVE>(h, a);
-    case B200ADJ_SA_QUADRATURE: {
-        const b200adj_cfg& c = h->cfg;
-        const size_t N = (size_t)c.N;
-        // lazily allocate the dense reverse solution and the quadgk scratch (only QuadratureAdjoint needs them)
-        if (!h->d_adj_dense && cudaMalloc(&h->d_adj_dense, (size_t)h->S * 8 * c.d * (size_t)h->Npad * sizeof(double)) != cudaSuccess) return B200ADJ_ERR_OOM;
-        if (!h->r_qseg) {
-            h->maxseg = 4096;
-            if (cudaMalloc(&h->r_qseg, (size_t)h->maxseg * (2 + c.P) * N * sizeof(double)) != cudaSuccess) return B200ADJ_ERR_OOM;
-            if (cudaMalloc(&h->r_qkey, (size_t)h->maxseg * N * sizeof(double)) != cudaSuccess) return B200ADJ_ERR_OOM;
-            if (cudaMalloc(&h->r_qidx, (size_t)h->maxseg * N * sizeof(int32_t)) != cudaSuccess) return B200ADJ_ERR_OOM;
-            if (!h->d_saveat && cudaMalloc(&h->d_saveat, sizeof(double) * (size_t)(c.K > 0 ? c.K : 1)) != cudaSuccess) return B200ADJ_ERR_OOM;
-        }
-        if (c.K > 0) {
-            if (h->saveat_dev_K < c.K) { cudaFree(h->d_saveat); h->d_saveat = nullptr; if (cudaMalloc(&h->d_saveat, sizeof(double) * (size_t)c.K) != cudaSuccess) return B200ADJ_ERR_OOM; h->saveat_dev_K = c.K; }
-            if (cudaMemcpyAsync(h->d_saveat, h->saveat.data(), sizeof(double) * (size_t)c.K, cudaMemcpyHostToDevice, h->stream) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        }
-        OdeRevArgs ar = a; ar.adj_dense = h->d_adj_dense;
-        int rc = launch_rev_sa<Fam, SA_QUAD>(h, ar);
-        if (rc) return rc;
-        Tsit5QuadArgs q;
-        memset(&q, 0, sizeof(q));
-        q.ckpt = h->d_ckpt; q.adj_dense = h->d_adj_dense; q.p = a.p; q.saveat = h->d_saveat;
-        q.dp_members = a.dp_members; q.partials = h->d_partials; q.dp = a.dp; q.ticket = h->d_ticket;
-        q.qseg = h->r_qseg; q.qkey = h->r_qkey; q.qidx = h->r_qidx; q.maxseg = h->maxseg;
-        q.N = c.N; q.Npad = h->Npad; q.S = h->S; q.K = c.K; q.t0 = c.t0; q.t1 = c.t1; q.h = c.dt;
-        q.quad_abstol = c.quad_abstol; q.quad_reltol = c.quad_reltol; q.tb = h->tb;
-        tsit5_weights(0.0, nullptr, q.R);
-        const int qb = 128, qg = (int)((c.N + 3) / 4);
-        if (c.shared_p) tsit5_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(q);
-        else tsit5_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(q);
-        h->launches++;
-        return 0;
-    }
-    default: return B200ADJ_ERR_UNSUPPORTED;
-    }
-}
-
-template <class Fam, bool EH>
-int launch_sde_fwd_f(Handle* h, const SdeFwdArgs& a) {
-    if (h->cfg.shared_p) sde_forward_kernel<Fam, EH, true><<<h->grid, h->block, 0, h->stream>>>(a);
-    else sde_forward_kernel<Fam, EH, false><<<h->grid, h->block, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-template <class Fam, bool EH, bool SHARED_P, int COST, bool INTERP>
-int launch_sde_rev_b(Handle* h, const SdeRevArgs& a) {
-    sde_backsolve_kernel<Fam, EH, SHARED_P, COST, INTERP><<<h->grid, h->block, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-template <class Fam, bool EH, bool INTERP>
-int launch_sde_rev_f(Handle* h, const SdeRevArgs& a) {
-    const bool sp = h->cfg.shared_p;
-    const bool ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (sp) return ex ? launch_sde_rev_b<Fam, EH, true, COST_EXPLICIT, INTERP>(h, a) : launch_sde_rev_b<Fam, EH, true, COST_AFFINE, INTERP>(h, a);
-    return ex ? launch_sde_rev_b<Fam, EH, false, COST_EXPLICIT, INTERP>(h, a) : launch_sde_rev_b<Fam, EH, false, COST_AFFINE, INTERP>(h, a);
-}
-
-template <class Fam>
-int launch_ros_fwd(Handle* h, const RosArgs& a) {
-    if (h->cfg.shared_p) ros23_forward_kernel<Fam, true><<<h->grid, h->block, 0, h->stream>>>(a);
-    else ros23_forward_kernel<Fam, false><<<h->grid, h->block, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-template <class Fam, int SA>
-int launch_ros_rev_sa(Handle* h, const RosArgs& a) {
-    const bool sp = h->cfg.shared_p, ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (sp) { if (ex) ros23_reverse_kernel<Fam, SA, true, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
-              else ros23_reverse_kernel<Fam, SA, true, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
-    else { if (ex) ros23_reverse_kernel<Fam, SA, false, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
-           else ros23_reverse_kernel<Fam, SA, false, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
-    h->launches++;
-    return 0;
-}
-template <class Fam>
-int launch_ros_rev(Handle* h, const RosArgs& a) {
-    if (h->cfg.sensealg == B200ADJ_SA_GAUSS) return launch_ros_rev_sa<Fam, SA_GAUSS>(h, a);
-    if (h->cfg.sensealg == B200ADJ_SA_GAUSSKRONROD) return launch_ros_rev_sa<Fam, SA_GK>(h, a);
-    if (h->cfg.sensealg != B200ADJ_SA_QUADRATURE) return B200ADJ_ERR_UNSUPPORTED;
-    int rc = launch_ros_rev_sa<Fam, SA_QUAD>(h, a);
-    if (rc) return rc;
-    const int qb = 128, qg = (int)((h->cfg.N + (qb / 32) - 1) / (qb / 32));      // one warp per member
-    if ((size_t)qg > h->qpartials_blocks) return B200ADJ_ERR_INVALID;
-    if (h->cfg.shared_p) ros23_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(a);
-    else ros23_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
 }
 T5aArgs t5a_args(Handle* h) {
     const b200adj_cfg& c = h->cfg;
@@ -345,44 +104,6 @@ T5aArgs t5a_args(Handle* h) {
     a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
     return a;
 }
-template <class Fam>
-int launch_t5a_fwd(Handle* h, const T5aArgs& a) {
-    if (h->cfg.shared_p) t5a_forward_kernel<Fam, true><<<h->grid, h->block, 0, h->stream>>>(a);
-    else t5a_forward_kernel<Fam, false><<<h->grid, h->block, 0, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-template <class Fam, int SA>
-int launch_t5a_rev_sa(Handle* h, const T5aArgs& a) {
-    const bool sp = h->cfg.shared_p, ex = h->cfg.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (sp) { if (ex) t5a_reverse_kernel<Fam, SA, true, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
-              else t5a_reverse_kernel<Fam, SA, true, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
-    else { if (ex) t5a_reverse_kernel<Fam, SA, false, COST_EXPLICIT><<<h->grid, h->block, 0, h->stream>>>(a);
-           else t5a_reverse_kernel<Fam, SA, false, COST_AFFINE><<<h->grid, h->block, 0, h->stream>>>(a); }
-    h->launches++;
-    return 0;
-}
-template <class Fam>
-int launch_t5a_rev(Handle* h, const T5aArgs& a) {
-    switch (h->cfg.sensealg) {
-    case B200ADJ_SA_INTERPOLATING: return launch_t5a_rev_sa<Fam, SA_INTERP>(h, a);
-    case B200ADJ_SA_GAUSS: return launch_t5a_rev_sa<Fam, SA_GAUSS>(h, a);
-    case B200ADJ_SA_BACKSOLVE: return launch_t5a_rev_sa<Fam, SA_BACKSOLVE>(h, a);
-    case B200ADJ_SA_GAUSSKRONROD: return launch_t5a_rev_sa<Fam, SA_GK>(h, a);
-    case B200ADJ_SA_QUADRATURE: {
-        int rc = launch_t5a_rev_sa<Fam, SA_QUAD>(h, a);
-        if (rc) return rc;
-        const int qb = 128, qg = (int)((h->cfg.N + 3) / 4);
-        if ((size_t)qg > h->qpartials_blocks) return B200ADJ_ERR_INVALID;
-        if (h->cfg.shared_p) t5a_quadrature_kernel<Fam, true><<<qg, qb, 0, h->stream>>>(a);
-        else t5a_quadrature_kernel<Fam, false><<<qg, qb, 0, h->stream>>>(a);
-        h->launches++;
-        return 0;
-    }
-    default: return B200ADJ_ERR_UNSUPPORTED;
-    }
-}
-
 RosArgs ros_args(Handle* h) {
     const b200adj_cfg& c = h->cfg;
     RosArgs a;
@@ -396,89 +117,11 @@ RosArgs ros_args(Handle* h) {
     a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
     return a;
 }
-
-template <class T>
-int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
-    MlpArgs<T> a;
-    memset(&a, 0, sizeof(a));
-    a.u0 = (const T*)u0; a.p = (const T*)p; a.ckpt = (T*)h->d_ckpt; a.saved = (T*)saved; a.save_of_step = h->d_save_of_step;
-    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
-    const size_t smem = sizeof(MlpSmem<T>);
-    if (cudaFuncSetAttribute(mlp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-    mlp_forward_kernel<T><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-int mlp_tc_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
-    MlpArgs<float> a;
-    memset(&a, 0, sizeof(a));
-    a.u0 = (const float*)u0; a.p = (const float*)p; a.ckpt = (float*)h->d_ckpt; a.saved = (float*)saved; a.save_of_step = h->d_save_of_step;
-    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
-    const size_t smem = sizeof(TcSmem) + 128;
-    if (cudaFuncSetAttribute(mlp_tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-    mlp_tc_forward_kernel<<<(int)((h->cfg.N + TC_M - 1) / TC_M), TC_M, smem, h->stream>>>(a);
-    h->launches++;
-    return 0;
-}
-int mlp_tc_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
-    const b200adj_cfg& c = h->cfg;
-    MlpArgs<float> a;
-    memset(&a, 0, sizeof(a));
-    a.p = (const float*)h->cur_p; a.ckpt = (float*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const float*)dLdu;
-    a.du0 = (float*)du0; a.partials = (float*)h->d_partials; a.dp = (float*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
-    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
-    const size_t smem = sizeof(TcSmem) + 128;
-    const int grid = (int)((c.N + TC_M - 1) / TC_M);
-    if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
-        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_EXPLICIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        mlp_tc_reverse_kernel<COST_EXPLICIT><<<grid, TC_M, smem, h->stream>>>(a);
-    } else {
-        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        mlp_tc_reverse_kernel<COST_AFFINE><<<grid, TC_M, smem, h->stream>>>(a);
-    }
-    mlp_reduce_kernel<float><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const float*)h->d_partials, (float*)dp, grid);
-    h->launches += 2;
-    return 0;
-}
-template <class T>
-int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
-    const b200adj_cfg& c = h->cfg;
-    MlpArgs<T> a;
-    memset(&a, 0, sizeof(a));
-    a.p = (const T*)h->cur_p; a.ckpt = (T*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const T*)dLdu;
-    a.du0 = (T*)du0; a.partials = (T*)h->d_partials; a.dp = (T*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
-    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
-    const size_t smem = sizeof(MlpSmem<T>);
-    a.tapeA = h->d_tapeA; a.tapeB = h->d_tapeB; a.Ktot = h->Ktot; a.Npad = h->Npad;
-    const bool tape = h->d_tapeA != nullptr;
-#define B200_MLP_REV(COSTV, TAPEV)                                                                                          \
-    do {                                                                                                                    \
-        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COSTV, TAPEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA; \
-        mlp_reverse_kernel<T, COSTV, TAPEV><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);                                  \
-    } while (0)
-    const bool ex = c.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (tape) { if (ex) B200_MLP_REV(COST_EXPLICIT, true); else B200_MLP_REV(COST_AFFINE, true); }
-    else { if (ex) B200_MLP_REV(COST_EXPLICIT, false); else B200_MLP_REV(COST_AFFINE, false); }
-#undef B200_MLP_REV
-    mlp_reduce_kernel<T><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const T*)h->d_partials, (T*)dp, h->grid);
-    h->launches += 2;
-    if (tape) {
-        // hidden-layer weight gradient on the tensor cores: dW2 = TA x TB' over K = 6 S Npad (bf16 in, fp32 TMEM accumulate)
-        UmmaArgs u; u.TA = (const __nv_bfloat16*)h->d_tapeA; u.TB = (const __nv_bfloat16*)h->d_tapeB; u.partials = h->d_umma_partials; u.Ktot = h->Ktot;
-        mlp_dw2_umma_kernel<<<h->umma_ctas, 128, 0, h->stream>>>(u);
-        mlp_dw2_reduce_kernel<<<16, 256, 0, h->stream>>>(h->d_umma_partials, (float*)dp + MLP_OW2, h->umma_ctas);
-        h->launches += 2;
-    }
-    return 0;
-}
-
-size_t esz(const b200adj_cfg& c) { return c.dtype == B200ADJ_F64 ? sizeof(double) : sizeof(float); }   // BF16_F32ACC: fp32 buffers at the ABI
-
 void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
-    cudaFree(h->d_tapeA); cudaFree(h->d_tapeB); cudaFree(h->d_umma_partials); cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
+    cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -654,18 +297,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     CREATE_TRY(cudaMalloc(&h->d_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
     CREATE_TRY(cudaMemcpy(h->d_save_of_step, sos.data(), ((size_t)S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (sde) CREATE_TRY(cudaMalloc(&h->d_noise, (size_t)S * m * N * e));
-    // BF16_F32ACC = mlp_tc.cuh (member and gradient GEMMs in the loop on tcgen05, no tapes).  B200ADJ_MLP_TC=0 selects the
-    // earlier formulation (CUDA-core mat-mat products in the loop, bf16 operand tapes, one tcgen05 GEMM for dW2 afterwards).
-    if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC) { const char* e_ = getenv("B200ADJ_MLP_TC"); h->mlp_tc = !(e_ && atoi(e_) == 0); }
-    if (mlp && cfg->dtype == B200ADJ_BF16_F32ACC && !h->mlp_tc) {
-        h->Ktot = (int64_t)6 * S * (int64_t)Npad;                              // Npad is a multiple of 32 => Ktot % 64 == 0
-        // several CTAs per SM (24.7 KB smem, 64 TMEM columns each): the single-stage load->MMA->wait loop of one CTA is
-        // latency-bound, co-resident CTAs overlap each other's phases
-        { const char* e_ = getenv("B200ADJ_UMMA_CTAS_PER_SM"); h->umma_ctas = nsm * (e_ ? atoi(e_) : 4); }
-        CREATE_TRY(cudaMalloc(&h->d_tapeA, (size_t)64 * h->Ktot * 2));
-        CREATE_TRY(cudaMalloc(&h->d_tapeB, (size_t)64 * h->Ktot * 2));
-        CREATE_TRY(cudaMalloc(&h->d_umma_partials, (size_t)h->umma_ctas * 4096 * sizeof(float)));
-    }
+    // BF16_F32ACC = mlp_tc.cuh: member and gradient GEMMs in the time loop on tcgen05, accumulators in TMEM
+    h->mlp_tc = mlp && cfg->dtype == B200ADJ_BF16_F32ACC;
     if (cfg->flags & B200ADJ_FLAG_TRACE) {
         CREATE_TRY(cudaMalloc(&h->d_trace, (size_t)h->grid * 3 * sizeof(unsigned long long)));
         CREATE_TRY(cudaMemset(h->d_trace, 0, (size_t)h->grid * 3 * sizeof(unsigned long long)));
@@ -714,7 +347,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
         if (!c.buffers_on_device && cost_kind == B200ADJ_COST_EXPLICIT && c.K > 0 && !h->s_dLdu)
             CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)c.K * c.d * (size_t)c.N * esz(c)));
         c.sensealg = sensealg; c.cost_kind = cost_kind; c.cost_a = cost_a; c.cost_b = cost_b;
-        c.flags = (c.flags & (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE)) | (flags & ~(B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE));
+        c.flags = (c.flags & B200ADJ_CREATE_FLAGS) | (flags & ~B200ADJ_CREATE_FLAGS);
         return B200ADJ_OK;
     }
     if (K >= 0) {
@@ -741,7 +374,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
         CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)c.K * c.d * (size_t)c.N * esz(c)));
     }
     c.sensealg = sensealg; c.cost_kind = cost_kind; c.cost_a = cost_a; c.cost_b = cost_b;
-    c.flags = (c.flags & (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE)) | (flags & ~(B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE));
+    c.flags = (c.flags & B200ADJ_CREATE_FLAGS) | (flags & ~B200ADJ_CREATE_FLAGS);
     return B200ADJ_OK;
 }
 
@@ -864,9 +497,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = h->mlp_tc ? mlp_tc_forward_launch(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
-           : c.dtype != B200ADJ_F64 ? mlp_forward_launch<float>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus)
-                                    : mlp_forward_launch<double>(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
+        rc = mlp_forward_dispatch(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         OdeFwdArgsT<float> a;
         a.u0 = (const float*)du0; a.p = (const float*)dp; a.ckpt = (float*)h->d_ckpt; a.saved = c.K > 0 ? (float*)dsaved : nullptr;
@@ -904,12 +535,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         } else {
             h->noise_valid = false;
         }
-        const bool eh = c.stepper == B200ADJ_ST_EULER_HEUN;
-        switch (c.rhs_family) {
-        case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_fwd_f<SdeLotkaVolterra<false>, true>(h, a) : launch_sde_fwd_f<SdeLotkaVolterra<false>, false>(h, a); break;
-        case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_fwd_f<SdeLinear2<false>, true>(h, a) : launch_sde_fwd_f<SdeLinear2<false>, false>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
-        }
+        rc = sde_forward_dispatch(h, a);
     }
     if (rc) { h->err = "forward dispatch failed"; return rc; }
     CUDA_TRY(h, cudaGetLastError());
@@ -965,8 +591,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = h->mlp_tc ? mlp_tc_reverse_launch(h, dL, ddu0, ddp)
-           : c.dtype != B200ADJ_F64 ? mlp_reverse_launch<float>(h, dL, ddu0, ddp) : mlp_reverse_launch<double>(h, dL, ddu0, ddp);
+        rc = mlp_reverse_dispatch(h, dL, ddu0, ddp);
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         if (h->cont_on) { h->err = "continuous cost: F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
         OdeRevArgsT<float> a;
@@ -1004,22 +629,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         a.flags = ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) | ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
         a.seed = c.seed; a.traj_offset = c.traj_offset;
         a.noise = h->noise_valid ? h->d_noise : nullptr;
-        const bool eh = c.stepper == B200ADJ_ST_EULER_HEUN;
-        const bool interp = c.sensealg == B200ADJ_SA_INTERPOLATING;
-        // Backsolve + Ito solver (EM): transformed drift; InterpolatingAdjoint: the problem's own drift
-        if (interp) {
-            switch (c.rhs_family) {
-            case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_rev_f<SdeLotkaVolterra<false>, true, true>(h, a) : launch_sde_rev_f<SdeLotkaVolterra<false>, false, true>(h, a); break;
-            case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_rev_f<SdeLinear2<false>, true, true>(h, a) : launch_sde_rev_f<SdeLinear2<false>, false, true>(h, a); break;
-            default: rc = B200ADJ_ERR_UNSUPPORTED;
-            }
-        } else {
-            switch (c.rhs_family) {
-            case B200ADJ_FAM_SDE_LV: rc = eh ? launch_sde_rev_f<SdeLotkaVolterra<false>, true, false>(h, a) : launch_sde_rev_f<SdeLotkaVolterra<true>, false, false>(h, a); break;
-            case B200ADJ_FAM_SDE_LINEAR: rc = eh ? launch_sde_rev_f<SdeLinear2<false>, true, false>(h, a) : launch_sde_rev_f<SdeLinear2<true>, false, false>(h, a); break;
-            default: rc = B200ADJ_ERR_UNSUPPORTED;
-            }
-        }
+        rc = sde_reverse_dispatch(h, a);
     }
     if (rc) { h->err = "reverse dispatch failed (sensealg/family not built)"; return rc; }
     CUDA_TRY(h, cudaGetLastError());
@@ -1042,8 +652,7 @@ int32_t b200adj_get_noise(void* handle, void* dW_out) {
         // regenerate from the Philox counter into the handle's buffer
         SdeNoiseArgs a; a.out = h->d_noise; a.N = c.N; a.S = h->S; a.h = c.dt; a.seed = c.seed; a.traj_offset = c.traj_offset; a.m = c.m;
         const int64_t total = (int64_t)h->S * c.N;
-        sde_noise_kernel<<<(unsigned)((total + 255) / 256), 256, 0, h->stream>>>(a);
-        h->launches++;
+        sde_noise_launch(h, a, total);
         CUDA_TRY(h, cudaGetLastError());
     }
     CUDA_TRY(h, cudaMemcpyAsync(dW_out, h->d_noise, bytes, c.buffers_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));

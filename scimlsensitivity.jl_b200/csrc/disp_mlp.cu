@@ -1,0 +1,82 @@
+// disp_mlp.cu -- launchers of the MLP-family kernels: CUDA-core fp64 / fp32 (mlp.cuh) and the tcgen05 bf16 path (mlp_tc.cuh)
+#include "handle.h"
+namespace b200adj {
+namespace {
+template <class T>
+int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
+    MlpArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.u0 = (const T*)u0; a.p = (const T*)p; a.ckpt = (T*)h->d_ckpt; a.saved = (T*)saved; a.save_of_step = h->d_save_of_step;
+    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
+    const size_t smem = sizeof(MlpSmem<T>);
+    if (cudaFuncSetAttribute(mlp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+    mlp_forward_kernel<T><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+int mlp_tc_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
+    MlpArgs<float> a;
+    memset(&a, 0, sizeof(a));
+    a.u0 = (const float*)u0; a.p = (const float*)p; a.ckpt = (float*)h->d_ckpt; a.saved = (float*)saved; a.save_of_step = h->d_save_of_step;
+    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
+    const size_t smem = sizeof(TcSmem) + 128;
+    if (cudaFuncSetAttribute(mlp_tc_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+    mlp_tc_forward_kernel<0><<<(int)((h->cfg.N + TC_M - 1) / TC_M), TC_M, smem, h->stream>>>(a);
+    h->launches++;
+    return 0;
+}
+int mlp_tc_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
+    const b200adj_cfg& c = h->cfg;
+    MlpArgs<float> a;
+    memset(&a, 0, sizeof(a));
+    a.p = (const float*)h->cur_p; a.ckpt = (float*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const float*)dLdu;
+    a.du0 = (float*)du0; a.partials = (float*)h->d_partials; a.dp = (float*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
+    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    const size_t smem = sizeof(TcSmem) + 128;
+    const int grid = (int)((c.N + TC_M - 1) / TC_M);
+    if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
+        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_EXPLICIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_tc_reverse_kernel<COST_EXPLICIT><<<grid, TC_M, smem, h->stream>>>(a);
+    } else {
+        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_tc_reverse_kernel<COST_AFFINE><<<grid, TC_M, smem, h->stream>>>(a);
+    }
+    mlp_reduce_kernel<float><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const float*)h->d_partials, (float*)dp, grid);
+    h->launches += 2;
+    return 0;
+}
+template <class T>
+int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
+    const b200adj_cfg& c = h->cfg;
+    MlpArgs<T> a;
+    memset(&a, 0, sizeof(a));
+    a.p = (const T*)h->cur_p; a.ckpt = (T*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const T*)dLdu;
+    a.du0 = (T*)du0; a.partials = (T*)h->d_partials; a.dp = (T*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
+    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    const size_t smem = sizeof(MlpSmem<T>);
+    a.Npad = h->Npad;
+#define B200_MLP_REV(COSTV, TAPEV)                                                                                          \
+    do {                                                                                                                    \
+        if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COSTV, TAPEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA; \
+        mlp_reverse_kernel<T, COSTV, TAPEV><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);                                  \
+    } while (0)
+    const bool ex = c.cost_kind == B200ADJ_COST_EXPLICIT;
+    if (ex) B200_MLP_REV(COST_EXPLICIT, false); else B200_MLP_REV(COST_AFFINE, false);
+#undef B200_MLP_REV
+    mlp_reduce_kernel<T><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const T*)h->d_partials, (T*)dp, h->grid);
+    h->launches += 2;
+    return 0;
+}
+}  // namespace
+
+int mlp_forward_dispatch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
+    const b200adj_cfg& c = h->cfg;
+    return h->mlp_tc ? mlp_tc_forward_launch(h, u0, p, saved, status)
+         : c.dtype != B200ADJ_F64 ? mlp_forward_launch<float>(h, u0, p, saved, status) : mlp_forward_launch<double>(h, u0, p, saved, status);
+}
+int mlp_reverse_dispatch(Handle* h, const void* dLdu, void* du0, void* dp) {
+    const b200adj_cfg& c = h->cfg;
+    return h->mlp_tc ? mlp_tc_reverse_launch(h, dLdu, du0, dp)
+         : c.dtype != B200ADJ_F64 ? mlp_reverse_launch<float>(h, dLdu, du0, dp) : mlp_reverse_launch<double>(h, dLdu, du0, dp);
+}
+}  // namespace b200adj

@@ -1,0 +1,108 @@
+// handle.h -- the state behind one b200adj handle and the kernel-dispatch entry points shared by the translation
+// units of libb200adj.so.  api.cu owns the C ABI (include/b200adj.h); every disp_*.cu instantiates the kernels of one
+// stepper (x one RHS family) so the library builds in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/b200adj.h"
+#include "ode_tsit5.cuh"
+#include "sde_em.cuh"
+#include "ros23.cuh"
+#include "mlp.cuh"
+#include "tsit5_quad.cuh"
+#include "mlp_tc.cuh"
+#include "tsit5_adaptive.cuh"
+
+namespace b200adj {
+
+struct NcclApi;      // dlopen'ed libnccl entry points (comm.cu)
+
+struct Handle {
+    b200adj_cfg cfg;
+    std::vector<double> saveat;
+    std::vector<int32_t> save_of_step;
+    int S = 0;
+    int64_t Npad = 0;
+    int block = 64, grid = 0;
+    int ckpt_every = 1;               // fixed-step Tsit5: forward states kept every C steps, segments re-solved in the reverse pass
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    // device memory owned by the handle
+    double* d_ckpt = nullptr;         // [S/C+1][d][Npad]
+    double* d_noise = nullptr;        // [S][m][N] (SDE, stored-noise mode)
+    double* d_partials = nullptr;     // [grid][P]
+    double* d_adj_dense = nullptr;    // QuadratureAdjoint, fixed-step Tsit5: [S][8][d][Npad]
+    int64_t Ktot = 0;
+    size_t qpart_blocks_fixed = 0;
+    unsigned long long* d_trace = nullptr;   // [grid][3] block trace (B200ADJ_FLAG_TRACE)
+    unsigned int* d_ticket = nullptr;
+    int32_t* d_save_of_step = nullptr;
+    // adaptive path: per-member dense forward / reverse solutions
+    bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
+    double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
+    bool cont_on = false; double cont_a = 0, cont_b = 0, cont_c = 0, cont_e = 0;   // continuous cost family
+    double dgdp_c = 0, dgdp_e = 0;    // discrete cost's parameter part: dgdp_discrete = c p + e at every save time
+    bool mlp_tc = false;              // BF16_F32ACC: every GEMM-shaped piece of the time loop on tcgen05 (mlp_tc.cuh)
+    double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
+    int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
+    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
+    // forward save table (the primal output of b200adj_forward) kept apart from the reverse pass' jump times
+    int fwd_K = 0; std::vector<double> fwd_saveat; std::vector<int32_t> fwd_save_of_step; int32_t* d_fwd_save_of_step = nullptr; double* d_fwd_saveat = nullptr;
+    // staging (buffers_on_device == 0)
+    double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
+    int32_t* s_status = nullptr;
+    const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
+    int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr, *d_ev_ps = nullptr, *d_ev_pc = nullptr;      // preset-time events
+    bool have_forward = false;
+    bool noise_valid = false;
+    int64_t launches = 0;
+    Tsit5Tables tb;
+    // multi-GPU (comm.cu): one NCCL communicator per handle, dp all-reduced on the handle's stream
+    void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+    std::string err;
+};
+
+#define CUDA_TRY(h, expr)                                                                      \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+            return B200ADJ_ERR_CUDA;                                                           \
+        }                                                                                      \
+    } while (0)
+
+inline bool is_sde(const b200adj_cfg& c) { return c.stepper == B200ADJ_ST_EM || c.stepper == B200ADJ_ST_EULER_HEUN; }
+inline size_t esz(const b200adj_cfg& c) { return c.dtype == B200ADJ_F64 ? sizeof(double) : sizeof(float); }   // BF16_F32ACC: fp32 buffers at the ABI
+
+void tsit5_weights(double th, double* w, double (*Rout)[4] = nullptr);
+template <class T, class S> inline void cast_tables(const S& src, T* dst) {
+    for (int i = 0; i < 7; i++) for (int j = 0; j < 6; j++) dst->hA[i][j] = (float)src.hA[i][j];
+    for (int i = 0; i < 4; i++) for (int j = 0; j < 7; j++) dst->hBst[i][j] = (float)src.hBst[i][j];
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 7; j++) dst->hBq[i][j] = (float)src.hBq[i][j];
+    for (int i = 0; i < 3; i++) dst->hGW[i] = (float)src.hGW[i];
+}
+
+
+// ---- dispatch entry points, one explicit instantiation per family in disp_*.cu ----
+template <class Fam> int launch_fwd(Handle* h, const OdeFwdArgs& a);
+template <class Fam> int launch_rev(Handle* h, const OdeRevArgs& a);
+template <class Fam> int launch_fwd_f32(Handle* h, const OdeFwdArgsT<float>& a);
+template <class Fam> int launch_rev_f32(Handle* h, const OdeRevArgsT<float>& a);
+template <class Fam> int launch_t5a_fwd(Handle* h, const T5aArgs& a);
+template <class Fam> int launch_t5a_rev(Handle* h, const T5aArgs& a);
+template <class Fam> int launch_ros_fwd(Handle* h, const RosArgs& a);
+template <class Fam> int launch_ros_rev(Handle* h, const RosArgs& a);
+int sde_forward_dispatch(Handle* h, const SdeFwdArgs& a);
+int sde_reverse_dispatch(Handle* h, const SdeRevArgs& a);
+int sde_noise_launch(Handle* h, const SdeNoiseArgs& a, int64_t total);
+int mlp_forward_dispatch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status);
+int mlp_reverse_dispatch(Handle* h, const void* dLdu, void* du0, void* dp);
+
+}  // namespace b200adj

@@ -67,6 +67,7 @@ __device__ __forceinline__ void wiener_increment(uint64_t seed, uint64_t member,
     }
 }
 
+template <int UNUSED = 0>
 __global__ void sde_noise_kernel(SdeNoiseArgs a) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)a.S * a.N) return;
