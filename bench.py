@@ -4,17 +4,26 @@ Lorenz d=3 P=3, N=65536 members per GPU, GaussAdjoint, Tsit5 fixed dt=0.01, T=10
 cotangent dgdu = u - 2, fp64, shared p, synthetic u0 = [1,0,0] + 0.1 z.
 
 One "step" = one full gradient evaluation of the ensemble: forward solve + fused reverse adjoint pass + dG/dp
-reduction (+ one all-reduce of dp over ranks for N>1; members are sharded, weak scaling: 65536 per GPU).
+reduction (+ the one all-reduce of dp over ranks for N>1, issued by b200adj_reverse itself through the handle's NCCL
+communicator; members are sharded, weak scaling: 65536 per GPU).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--members M]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-`value`   : members/s with inputs resident in HBM (device pointers through the C ABI), CUDA-event timed, max over ranks.
-`e2e`     : same metric through the public API (solve + adjoint_sensitivities) with HOST buffers: pinned u0 H2D and
+Keys of the one JSON line (rank 0):
+`value`     members/s with inputs resident in HBM (device pointers through the C ABI), CUDA-event timed, max over ranks.
+`e2e`       same metric through the public API (solve + adjoint_sensitivities(AffineCost)) with HOST buffers: pinned u0 H2D and
             du0/dp D2H inside the timed region every step.
-`roofline`: the reverse kernel (dominant) against the measured HBM peak, algorithmic bytes = 122.4 B per member-step
-             x N x S per launch.
-`cpu_baseline`: the C oracle (a PORT of the reference algorithm; Julia cannot run here) on the host cores, bounded sample.
+`e2e_rrule` same metric through the plugin seam `_concrete_solve_adjoint` (src/concrete_solve.jl:523-543, 776-1040):
+            host primal sol.u[K,d,N] OUT (D2H) and host cotangent Delta[K,d,N] IN (H2D) every step.
+`roofline`  the reverse kernel (dominant): SURVEY 8d's per-step algorithmic bytes against the measured HBM peak, the
+            compulsory (really moved) bytes, and the fp64-pipe figure that actually bounds the kernel.
+`parity`    device gradient vs the CPU oracle on a bounded sub-ensemble, sharded exactly like the timed run (every rank
+            owns a slice, dp all-reduced behind the C ABI); the run exits non-zero above 1e-8.
+`strong`    (N>1) the metric's fixed total N=65536 split over the ranks.
+`secondary` BASELINE configs C4 (bf16 tensor-core neural ODE) and C5 (SDE) sharded over the same ranks, each timed,
+            roofline'd and oracle-checked.
+`cpu_baseline` the C oracle (a PORT of the reference algorithm; Julia cannot run here) on the host cores.
 """
 import argparse
 import json
@@ -31,6 +40,9 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(family="lorenz", sensealg="gauss", stepper="tsit5_fixed", T=10.0, dt=0.01, nsave=101,
                 members_per_gpu=65536, cost=(1.0, -2.0), seed=20260923)
 ALG_BYTES_PER_MEMBER_STEP = 8 * (3 + 2 * 6 + 101.0 / 1000.0 * 3)   # 122.4 B
+# fp64 work of one reverse member-step (cuobjdump -sass of tsit5_reverse_kernel<Lorenz,GAUSS>)
+DP_INSTR_PER_MEMBER_STEP = dict(dfma=366, dmul=33, dadd=27)
+PARITY_TOL = 1e-8
 
 
 def make_inputs(N, offset=0):
@@ -38,6 +50,16 @@ def make_inputs(N, offset=0):
     u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N))
     p = np.array([10.0, 28.0, 8.0 / 3.0])
     return np.ascontiguousarray(u0), p
+
+
+def c2_config(world, members_per_gpu, block):
+    """identical for `--impl ours` and `--impl reference` (the driver compares the two arms' config)"""
+    W = WORKLOAD
+    return {"workload": "C2 Lorenz d=3 P=3 N=65536/GPU GaussAdjoint Tsit5 fixed dt=0.01 T=10 saveat=0.1 dgdu=u-2 shared p",
+            "members_per_gpu": members_per_gpu, "S": int(round(W["T"] / W["dt"])), "K": W["nsave"],
+            "parallelism": f"ensemble-shard x{world}",
+            "l2": "per-step working set = 1.57 GB of checkpoints per GPU (>> 126 MB L2), no explicit flush",
+            "block_threads": block or "auto: ceil32(N / (n_SM * waves)) = 448, one block per SM"}
 
 
 def host_cores():
@@ -77,25 +99,37 @@ def best_threads():
     return _BEST_THREADS
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the reverse kernel from the committed ncu summary (per launch)"""
-    path = os.path.join(ROOT, "profiles", "r1_reverse_ncu_summary.json")
+def profile_metric(fname, *names):
+    """metrics of a committed ncu summary (profiles/*.json, written by profiles/summarize.py); None when absent"""
     try:
-        with open(path) as f:
+        with open(os.path.join(ROOT, "profiles", fname)) as f:
             m = json.load(f)
-        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-        r, w = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
-        return r["value"] * scale[r["unit"]] + w["value"] * scale[w["unit"]]
+        scale = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "%": 1.0}
+        out = []
+        for n in names:
+            v = m[n]
+            out.append(v["value"] * scale.get(v.get("unit", ""), 1.0))
+        return out
     except Exception:
         return None
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the reverse kernel per launch, from the committed ncu capture"""
+    for f in ("r2_reverse_ncu_summary.json", "r1_reverse_ncu_summary.json"):
+        v = profile_metric(f, "dram__bytes_read.sum", "dram__bytes_write.sum")
+        if v is not None:
+            return v[0] + v[1], f"profiles/{f} (ncu --set full of this command; not re-measured in this run)"
+    return None, None
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as f:
-            return json.load(f).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            m = json.load(f)
+        return m.get("hbm_gbs", 6650.0), m.get("bf16_tflops_sustained", 1426.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1426.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -170,12 +204,13 @@ def cpu_oracle_rate(sample_members, threads, repeats=1):
 
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation (oracle port; Julia is not installed, so the
-    reference itself cannot run) on all host cores, bounded sample per step."""
+    reference itself cannot run) on all host cores.  Every step is ONE gradient of the same 65536-member ensemble the
+    GPU arm evaluates per GPU (same config dict); under torchrun only rank 0 works."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = best_threads()
-    sample = args.members or 8192
+    sample = args.members or WORKLOAD["members_per_gpu"]
     times = []
     for i in range(args.warmup + args.steps):
         rate, dt = cpu_oracle_rate(sample, threads)
@@ -183,19 +218,172 @@ def run_reference(args):
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
     value = sample / (ms * 1e-3)
-    W = WORKLOAD
     line = {
         "impl": "reference", "metric": "ensemble adjoint trajectories/sec", "value": value, "unit": "trajectories/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 Lorenz d=3 P=3 GaussAdjoint Tsit5 fixed dt=0.01 T=10 saveat=0.1 dgdu=u-2 (bounded sample)",
-                   "members_per_step": sample, "S": int(round(W["T"] / W["dt"])), "K": W["nsave"]},
+        "config": c2_config(args.gpus, sample, args.block),
         "cpu_baseline": {"value": value, "unit": "trajectories/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} members of the C2 workload per step, OpenMP over members"},
+                         "sample": f"{sample} members of the C2 workload per step (one GPU's share), OpenMP over members"},
         "e2e": {"value": value, "unit": "trajectories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# secondary BASELINE configs (C4, C5) and the generic sharded timing / parity machinery
+# ------------------------------------------------------------------------------------------------------------------
+def _mlp_params(rng, H=64):
+    return np.concatenate([(rng.standard_normal((H, 2)) / np.sqrt(2)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                           (rng.standard_normal((H, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                           (rng.standard_normal((2, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(2)])
+
+
+def spec_c4(dtype="bf16_f32acc"):
+    T, dt = 1.5, 0.05
+    p = _mlp_params(np.random.default_rng(WORKLOAD["seed"]))
+    return dict(name="C4 MLP 2->64->64->2 shared weights P=4482, InterpolatingAdjoint, Tsit5 fixed dt=0.05, T=1.5, 30 saves, bf16 tensor-core VJP",
+                family="mlp", sensealg="interpolating", stepper="tsit5_fixed", T=T, dt=dt, saveat=np.linspace(0.05, T, 30),
+                cost=(1.0, -0.5), dtype=dtype, shared_p=True, okw=dict(mlp_hidden=64), ekw={}, tol=2e-2 if dtype == "bf16_f32acc" else 1e-4,
+                inputs=lambda n, off: (np.random.default_rng(1000 + off).uniform(-2, 2, (2, n)), p), parity_members=128,
+                # 156 672 flop per member-step of the reverse pass (6 stages x (fwd + 2 VJP GEMM passes))
+                roofline=lambda n, S, rev_s, hbm, tf: {"bound": "tensor", "kernel": "mlp_tc_reverse_kernel", "achieved": 156672.0 * n * S / rev_s / 1e12,
+                                                       "peak": tf, "unit": "TFLOP/s", "frac": 156672.0 * n * S / rev_s / 1e12 / tf,
+                                                       "algorithmic_flops_per_launch": 156672.0 * n * S})
+
+
+def spec_c5():
+    T, dt = 1.0, 0.01
+    p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
+    return dict(name="C5 SDE-LV diag noise d=2 P=6, BacksolveAdjoint (Ito transformed drift), EM dt=0.01, T=1, saveat 0.01, Philox noise regenerated in reverse",
+                family="sde_lv", sensealg="backsolve", stepper="em", T=T, dt=dt, saveat=np.linspace(0.0, T, 101), cost=(0.0, 1.0),
+                dtype="f64", shared_p=True, okw={}, ekw=dict(seed=20260923), tol=1e-8,
+                inputs=lambda n, off: (np.ones((2, n)), p), parity_members=1024,
+                # 176 B per member-step (z = [lam; mu; y] read+write, checkpoint reset read); compulsory: 16 B
+                roofline=lambda n, S, rev_s, hbm, tf: {"bound": "hbm", "kernel": "sde_backsolve_kernel", "achieved": 176.0 * n * S / rev_s / 1e9,
+                                                       "peak": hbm, "unit": "GB/s", "frac": 176.0 * n * S / rev_s / 1e9 / hbm,
+                                                       "algorithmic_bytes_per_launch": 176.0 * n * S,
+                                                       "compulsory_bytes_per_launch": 8.0 * (2 * (S + 1) + 2) * n,
+                                                       "note": "per-step accounting (state as if it lived in HBM between steps) is not a bound for an "
+                                                               "in-kernel time loop: frac may exceed 1; the compulsory stream is 16 B per member-step"})
+
+
+def spec_c2(T=None):
+    W = WORKLOAD
+    T = T or W["T"]
+    nsave = int(round(T / 0.1)) + 1
+    return dict(name="C2", family=W["family"], sensealg=W["sensealg"], stepper=W["stepper"], T=T, dt=W["dt"], saveat=np.linspace(0.0, T, nsave),
+                cost=W["cost"], dtype="f64", shared_p=True, okw={}, ekw={}, tol=PARITY_TOL,
+                inputs=lambda n, off: make_inputs(n, off), parity_members=256)
+
+
+class Shard:
+    """one rank's device-resident engine for a workload spec (+ NCCL communicator behind the C ABI when world > 1)"""
+
+    def __init__(self, spec, n_local, rank, world, local, block=0):
+        import torch
+        import scimlsensitivity_jl_b200 as b
+        from scimlsensitivity_jl_b200 import distributed as D
+        self.spec, self.n, self.torch = spec, n_local, torch
+        self.eng = b.DeviceEnsemble(spec["family"], spec["sensealg"], spec["stepper"], n_local, spec["saveat"], (0.0, spec["T"]), spec["dt"],
+                                    on_device=True, device=local, dtype=spec["dtype"], cost=b.AffineCost(*spec["cost"]),
+                                    traj_offset=rank * n_local, block_threads=block, **spec["ekw"])
+        self.eng.use_current_torch_stream()
+        if world > 1:
+            D.attach_comm(self.eng)
+        u0, p = spec["inputs"](n_local, rank)
+        self.u0_h, self.p_h = u0, p
+        td = torch.float64 if spec["dtype"] == "f64" else torch.float32
+        dev = f"cuda:{local}"
+        self.u0 = torch.tensor(u0, device=dev, dtype=td); self.p = torch.tensor(p, device=dev, dtype=td)
+        self.du0 = torch.empty(u0.shape, dtype=td, device=dev); self.dp = torch.empty(p.shape, dtype=td, device=dev)
+
+    def step(self):
+        self.eng.handle.forward(self.u0, self.p, None, None, None)
+        self.eng.handle.reverse(None, self.du0, self.dp)
+
+    def close(self):
+        self.eng.close()
+
+
+def timed(shard, steps, warmup, barrier, world, dev):
+    """W warm-up + K timed gradients; CUDA events on the launching stream; max over ranks -> (ms/step, fwd ms, rev ms)"""
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        shard.step()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        shard.eng.handle.forward(shard.u0, shard.p, None, None, None); ev[2 * i + 1].record()
+        shard.eng.handle.reverse(None, shard.du0, shard.dp); ev[2 * i + 2].record()
+    barrier()
+    t = torch.tensor([ev[0].elapsed_time(ev[-1]) / steps,
+                      float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(steps)])),
+                      float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(steps)]))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return tuple(float(x) for x in t.cpu())
+
+
+def parity_pass(spec, rank, world, local, threads):
+    """Sub-ensemble of spec['parity_members'] members per rank, sharded exactly like the timed run: every rank computes its
+    slice's gradient, dp is all-reduced behind the C ABI; rank 0 recomputes ALL slices with the CPU oracle and compares the
+    reduced dp and its own du0.  Returns {dp_rel, du0_rel, members} on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from oracle import oracle as O
+    n = spec["parity_members"]
+    sh = Shard(spec, n, rank, world, local)
+    sh.step()
+    torch.cuda.synchronize()
+    dp = sh.dp.double().cpu().numpy(); du0 = sh.du0.double().cpu().numpy()
+    dW_all = None
+    if spec["stepper"] in ("em", "euler_heun"):
+        dW = sh.eng.noise()                                    # the Philox increments this shard used (global member index keyed)
+        if world > 1:
+            parts = [torch.empty_like(dW) for _ in range(world)]
+            dist.all_gather(parts, dW.contiguous())
+            dW_all = torch.cat(parts, dim=2).cpu().numpy()
+        else:
+            dW_all = dW.cpu().numpy()
+    sh.close()
+    if rank != 0:
+        return None
+    u0s, p = zip(*[spec["inputs"](n, r) for r in range(world)])
+    u0 = np.concatenate(u0s, axis=1)
+    cfg = O.make_cfg(spec["family"], spec["sensealg"], spec["stepper"], n * world, spec["saveat"], 0.0, spec["T"], dt=spec["dt"],
+                     cost=("affine",) + tuple(spec["cost"]), **spec["okw"])
+    ref = O.gradient(cfg, spec["saveat"], u0, p[0], dW=dW_all, want_saved=False, nthreads=threads)
+    dp_rel = float(np.abs(dp - ref["dp"]).max() / np.abs(ref["dp"]).max())
+    du0_rel = float(np.abs(du0 - ref["du0"][:, :n]).max() / np.abs(ref["du0"]).max())
+    return {"dp_rel": dp_rel, "du0_rel": du0_rel, "members": n * world, "tol": spec["tol"], "ok": bool(dp_rel <= spec["tol"] and du0_rel <= spec["tol"]),
+            "against": "CPU oracle (oracle/adjoint_oracle.c) on the same members; dp all-reduced over the ranks by b200adj_reverse"}
+
+
+def secondary_leg(spec, n_total, rank, world, local, steps, warmup, barrier, threads, with_parity=True):
+    import torch
+    hbm, tf, _ = peaks()
+    dev = f"cuda:{local}"
+    n_local = n_total // world
+    sh = Shard(spec, n_local, rank, world, local)
+    l0 = sh.eng.handle.launch_count
+    ms, fwd, rev = timed(sh, steps, warmup, barrier, world, dev)
+    launches = sh.eng.handle.launch_count - l0
+    sh.close()
+    par = parity_pass(spec, rank, world, local, threads) if with_parity else None
+    if rank != 0:
+        return None
+    S = int(round(spec["T"] / spec["dt"]))
+    out = {"workload": spec["name"], "members_total": n_local * world, "members_per_gpu": n_local, "dtype": spec["dtype"],
+           "value": n_local * world / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms,
+           "phases_ms": {"forward": fwd, "reverse_incl_allreduce": rev}, "gpu_launches_per_step": launches / max(1, steps + warmup),
+           "roofline": spec["roofline"](n_local, S, rev * 1e-3, hbm, tf)}
+    if par is not None:
+        out["parity"] = par
+    return out
 
 
 def run_ours(args):
@@ -216,53 +404,39 @@ def run_ours(args):
     N = args.members or W["members_per_gpu"]       # per GPU (weak scaling)
     S = int(round(W["T"] / W["dt"]))
     saveat = np.linspace(0.0, W["T"], W["nsave"])
-    u0_h, p_h = make_inputs(N, offset=rank)
     cost = b.AffineCost(*W["cost"])
     dev = f"cuda:{local}"
-
-    # ---------------- device-resident arm (`value`) ----------------
-    eng = b.DeviceEnsemble(W["family"], W["sensealg"], W["stepper"], N, saveat, (0.0, W["T"]), W["dt"], on_device=True,
-                           device=local, cost=cost, traj_offset=rank * N, block_threads=args.block)
-    eng.use_current_torch_stream()
-    u0_d = torch.tensor(u0_h, device=dev); p_d = torch.tensor(p_h, device=dev)
-    du0_d = torch.empty((3, N), dtype=torch.float64, device=dev); dp_d = torch.empty(3, dtype=torch.float64, device=dev)
-
-    def step_device():
-        eng.handle.forward(u0_d, p_d, None, None, None)
-        eng.handle.reverse(None, du0_d, dp_d)
-        if world > 1:
-            dist.all_reduce(dp_d)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---------------- device-resident arm (`value`) ----------------
+    main = Shard(spec_c2(), N, rank, world, local, block=args.block)
+    eng, u0_h, p_h = main.eng, main.u0_h, main.p_h
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     for _ in range(args.warmup):
-        step_device()
+        main.step()
     barrier()
     launches0 = eng.handle.launch_count
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 1)]
     barrier()
     wall0 = time.time()
     ev[0].record()
     for i in range(args.steps):
-        eng.handle.forward(u0_d, p_d, None, None, None)
-        ev[3 * i + 1].record()
-        eng.handle.reverse(None, du0_d, dp_d)
-        ev[3 * i + 2].record()
-        if world > 1:
-            dist.all_reduce(dp_d)
-        ev[3 * i + 3].record()
+        eng.handle.forward(main.u0, main.p, None, None, None)
+        ev[2 * i + 1].record()
+        eng.handle.reverse(None, main.du0, main.dp)            # N>1: ends with the NCCL all-reduce of dp on the same stream
+        ev[2 * i + 2].record()
     barrier()
     wall1 = time.time()
     total_ms = ev[0].elapsed_time(ev[-1])
-    fwd_ms = float(np.mean([ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(args.steps)]))
-    rev_ms = float(np.mean([ev[3 * i + 1].elapsed_time(ev[3 * i + 2]) for i in range(args.steps)]))
-    launches = eng.handle.launch_count - launches0 + (args.steps if world > 1 else 0)
+    fwd_ms = float(np.mean([ev[2 * i].elapsed_time(ev[2 * i + 1]) for i in range(args.steps)]))
+    rev_ms = float(np.mean([ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]))
+    launches = eng.handle.launch_count - launches0
     clocks = sampler.stop(wall0, wall1) if rank == 0 else None
     t = torch.tensor([total_ms, fwd_ms, rev_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -270,79 +444,148 @@ def run_ours(args):
     total_ms, fwd_ms, rev_ms = (float(x) for x in t.cpu())
     ms_per_step = total_ms / args.steps
     value = N * world / (ms_per_step * 1e-3)
-    dp_check = dp_d.cpu().numpy().tolist()
+    dp_check = main.dp.cpu().numpy().tolist()
+    main.close()
 
-    # ---------------- end-to-end arm (`e2e`): public API, host buffers ----------------
+    # ---------------- end-to-end arms: public API, host buffers ----------------
     u0_pin = torch.tensor(u0_h).pin_memory(); p_pin = torch.tensor(p_h).pin_memory()
     prob = b.EnsembleProblem(b.ODEProblem(W["family"], u0_h[:, 0], (0.0, W["T"]), p_pin.numpy()), u0s=u0_pin.numpy())
     ealg = b.EnsembleB200(device=local, buffers_on_device=False, reuse_handle=True, presharded=True, pin_outputs=True)   # each rank owns its members
     alg = b.Tsit5(dt=W["dt"])
+    sens = b.B200Adjoint(b.GaussAdjoint(), block_threads=args.block)
 
     def step_e2e():
-        sol = b.solve(prob, alg, ealg, saveat=saveat, sensealg=b.B200Adjoint(b.GaussAdjoint(), block_threads=args.block),
-                      save_on=False)
+        sol = b.solve(prob, alg, ealg, saveat=saveat, sensealg=sens, save_on=False)
         return b.adjoint_sensitivities(sol, alg, t=saveat, dgdu_discrete=cost, sensealg=b.GaussAdjoint())
 
+    def time_host(fn, nsteps, nwarm):
+        for _ in range(nwarm):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(nsteps):
+            out = fn()
+        barrier()
+        s = (time.perf_counter() - t0) / nsteps
+        te = torch.tensor([s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        return float(te.cpu()[0]), out
+
     e2e_steps = max(1, min(args.steps, 10))
-    for _ in range(max(1, min(args.warmup, 3))):
-        step_e2e()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        du0_e, dp_e = step_e2e()
-    barrier()
-    e2e_s = (time.perf_counter() - t0) / e2e_steps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.cpu()[0])
+    e2e_s, (du0_e, dp_e) = time_host(step_e2e, e2e_steps, max(1, min(args.warmup, 3)))
     e2e_value = N * world / e2e_s
     h2d = u0_h.nbytes + p_h.nbytes
     d2h = 3 * N * 8 + 3 * 8
     e2e_ok = bool(np.allclose(np.asarray(dp_e).ravel(), np.asarray(dp_check), rtol=1e-12))
 
+    # the plugin seam: _concrete_solve_adjoint -> (primal on the host, pullback(Delta on the host))
+    delta_pin = torch.empty((W["nsave"], 3, N), dtype=torch.float64).pin_memory()
+
+    def step_rrule(fill=False):
+        out, pullback = b._concrete_solve_adjoint(prob, alg, sens, u0_pin.numpy(), p_pin.numpy(), b.ChainRulesOriginator(),
+                                                  saveat=saveat, ensemblealg=ealg)
+        if fill:                                                    # the user's loss gradient dL/du(t_k) = u - 2, computed once
+            np.subtract(out.u, 2.0, out=delta_pin.numpy())
+        return pullback(delta_pin.numpy())
+
+    step_rrule(fill=True)
+    rr_steps = max(1, min(args.steps, 5))
+    rr_s, tang = time_host(step_rrule, rr_steps, 1)
+    rr_ok = bool(np.allclose(np.asarray(tang[4]).ravel(), np.asarray(dp_check), rtol=1e-10))
+    kd = W["nsave"] * 3 * N * 8
+    b.clear_handle_cache()                                          # frees the host-mode handle (1.6 GB of checkpoints + staging)
+
+    # ---------------- parity of the sharded run against the oracle ----------------
+    threads = best_threads() if rank == 0 else 1
+    parity = parity_pass(spec_c2(T=2.0), rank, world, local, threads)
+
+    # ---------------- strong scaling of the metric's fixed N = 65536 (N > 1) ----------------
+    strong = None
+    if world > 1 and not args.members:
+        ntot = W["members_per_gpu"]
+        sh = Shard(spec_c2(), ntot // world, rank, world, local)
+        s_ms, s_f, s_r = timed(sh, args.steps, args.warmup, barrier, world, dev)
+        sh.close()
+        strong = {"members_total": ntot, "members_per_gpu": ntot // world, "ms_per_step": s_ms, "value": ntot / (s_ms * 1e-3),
+                  "unit": "trajectories/s", "phases_ms": {"forward": s_f, "reverse_incl_allreduce": s_r}}
+
+    # ---------------- secondary BASELINE configs, sharded over the same ranks ----------------
+    secondary = {}
+    if not args.no_secondary and not args.members:
+        sec_steps, sec_warm = max(5, min(args.steps, 20)), 3
+        secondary["c4"] = secondary_leg(spec_c4(), 4096, rank, world, local, sec_steps, sec_warm, barrier, threads)
+        secondary["c4_full"] = secondary_leg(spec_c4(), 18944 * world, rank, world, local, sec_steps, sec_warm, barrier, threads, with_parity=False)
+        secondary["c5"] = secondary_leg(spec_c5(), 131072, rank, world, local, sec_steps, sec_warm, barrier, threads)
+
     if rank == 0:
-        peak, peak_src = peaks()
+        hbm, tf, peak_src = peaks()
         alg_bytes = ALG_BYTES_PER_MEMBER_STEP * N * S
         achieved = alg_bytes / (rev_ms * 1e-3) / 1e9
-        compulsory = 8.0 * (S * 3 + 3 + W["nsave"] * 0) * N     # checkpoint read + du0 write (affine cost: no cotangent read)
-        threads = best_threads()
-        cpu_sample = 8192
+        compulsory = 8.0 * (S * 3 + 3) * N                       # checkpoint read + du0 write (affine cost: no cotangent read)
+        I = DP_INSTR_PER_MEMBER_STEP
+        flops = (2 * I["dfma"] + I["dmul"] + I["dadd"]) * float(N) * S
+        dp_issue = (I["dfma"] + I["dmul"] + I["dadd"]) * float(N) * S            # thread-level fp64 instructions per launch
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        nsm = torch.cuda.get_device_properties(local).multi_processor_count
+        fp64_peak_tf = nsm * 64 * 2 * sm_mhz * 1e6 / 1e12                         # 64 DFMA/clk/SM
+        pipe = profile_metric("r2_reverse_ncu_summary.json", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active") or \
+            profile_metric("r1_reverse_ncu_summary.json", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+        traffic, traffic_src = ncu_traffic() if N == W["members_per_gpu"] else (None, None)
+        cpu_sample = W["members_per_gpu"]
         cpu_oracle_rate(256, threads)                      # warm the library / thread pool
         cpu_rate, cpu_s = cpu_oracle_rate(cpu_sample, threads)
         line = {
             "metric": "ensemble adjoint trajectories/sec", "value": value, "unit": "trajectories/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C2 Lorenz d=3 P=3 N=65536/GPU GaussAdjoint Tsit5 fixed dt=0.01 T=10 saveat=0.1 dgdu=u-2 shared p",
-                       "members_per_gpu": N, "S": S, "K": W["nsave"], "parallelism": f"ensemble-shard x{world}",
-                       "l2": "per-step working set = 1.57 GB of checkpoints per GPU (>> 126 MB L2), no explicit flush",
-                       "block_threads": args.block or "auto: ceil32(N / (n_SM * waves)) = 448, one block per SM"},
-            "phases_ms": {"forward": fwd_ms, "reverse": rev_ms, "allreduce": max(0.0, ms_per_step - fwd_ms - rev_ms)},
-            "roofline": {"bound": "hbm", "kernel": "tsit5_reverse_kernel<Lorenz,GAUSS>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic() if (N == W["members_per_gpu"]) else None, "peak_source": peak_src,
+            "config": c2_config(world, N, args.block),
+            "phases_ms": {"forward": fwd_ms, "reverse_incl_allreduce": rev_ms},
+            "roofline": {"bound": "hbm", "kernel": "tsit5_reverse_kernel<Lorenz,GAUSS>", "achieved": achieved, "peak": hbm,
+                         "unit": "GB/s", "frac": achieved / hbm,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_member_step": ALG_BYTES_PER_MEMBER_STEP,
                          "compulsory_bytes_per_launch": compulsory,
+                         "compulsory_frac": compulsory / (rev_ms * 1e-3) / 1e9 / hbm,
+                         "fp64": {"tflops": flops / (rev_ms * 1e-3) / 1e12, "peak_tflops": fp64_peak_tf,
+                                  "frac": dp_issue / (rev_ms * 1e-3) / (nsm * 64 * sm_mhz * 1e6),
+                                  "pipe_active_pct_ncu": None if pipe is None else pipe[0],
+                                  "note": "fp64 pipe: 64 DFMA/clk/SM at the SM clock sampled in this run; frac = issued DFMA+DMUL+DADD / pipe slots "
+                                          "(426 per member-step, counted in SASS); pipe_active from the committed ncu capture"},
                          "note": "per-step accounting of SURVEY 8d (state counted as if it lived in HBM between steps); the time "
-                                 "loop is in-kernel so real DRAM traffic is ~ the compulsory bytes; the kernel is fp64-FMA bound"},
+                                 "loop is in-kernel so real DRAM traffic is the compulsory stream (compulsory_frac of the HBM peak); "
+                                 "the binding resource is the fp64 FMA pipe (fp64.frac)"},
             "cpu_baseline": {"value": cpu_rate, "unit": "trajectories/s", "cores": threads, "kind": "port",
-                             "sample": f"{cpu_sample} members of the same C2 workload, one gradient, {cpu_s:.2f} s wall"},
+                             "sample": f"{cpu_sample} members of the same C2 workload (one GPU's share), one gradient, {cpu_s:.2f} s wall"},
             "e2e": {"value": e2e_value, "unit": "trajectories/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_s * 1e3, "steps": e2e_steps, "api": "solve(EnsembleProblem, Tsit5, EnsembleB200) + adjoint_sensitivities(AffineCost)",
                     "matches_device_arm": e2e_ok},
+            "e2e_rrule": {"value": N * world / rr_s, "unit": "trajectories/s", "h2d_bytes_per_step": h2d + kd, "d2h_bytes_per_step": d2h + kd,
+                          "ms_per_step": rr_s * 1e3, "steps": rr_steps,
+                          "api": "_concrete_solve_adjoint(prob, Tsit5, B200Adjoint(GaussAdjoint)) -> host primal sol.u[K,d,N]; pullback(host Delta[K,d,N])",
+                          "matches_device_arm": rr_ok},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "dp": dp_check,
+            "parity": parity,
         }
+        if strong is not None:
+            line["strong"] = strong
+        if secondary:
+            line["secondary"] = secondary
         emit(line)
-    eng.close()
+        bad = [k for k, v in [("c2", parity)] + [(k, (v or {}).get("parity")) for k, v in secondary.items()] if v is not None and not v["ok"]]
+        if bad or not e2e_ok or not rr_ok:
+            sys.stderr.write(f"[bench] PARITY FAILURE: {bad} e2e_ok={e2e_ok} rrule_ok={rr_ok}\n")
+            if world > 1:
+                dist.destroy_process_group()
+            sys.exit(3)
     if world > 1:
         dist.destroy_process_group()
 
 
 def run_secondary(args):
-    """--workload c2f32|c3|c4|c5: the other BASELINE configs (parity-test cases; reported for context, same JSON shape)."""
+    """--workload c2f32|c3|c4|c5: one BASELINE config alone on one GPU (profiling / tuning; same JSON shape)."""
     import torch
     import scimlsensitivity_jl_b200 as b
     from oracle import oracle as O
@@ -377,9 +620,7 @@ def run_secondary(args):
         saveat = np.linspace(0.05, T, 30)
         u0 = rng.uniform(-2, 2, (2, N))
         H = 64
-        p = np.concatenate([(rng.standard_normal((H, 2)) / np.sqrt(2)).ravel(order="F"), 0.1 * rng.standard_normal(H),
-                            (rng.standard_normal((H, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(H),
-                            (rng.standard_normal((2, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(2)])
+        p = _mlp_params(rng, H)
         dtype = args.dtype or "bf16_f32acc"       # bf16_f32acc (the named config: tensor-core VJP) | f32 | f64
         eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, on_device=True, dtype=dtype, cost=b.AffineCost(1.0, -0.5))
         ocfg = lambda n: O.make_cfg("mlp", "interpolating", "tsit5_fixed", n, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
@@ -420,7 +661,7 @@ def run_secondary(args):
     pc = p if p.ndim == 1 else p[:, :sample]
     O.gradient(ocfg(min(sample, 16)), saveat, u0[:, :min(sample, 16)], p if p.ndim == 1 else p[:, :min(sample, 16)], dW=None if dW is None else dW[:, :, :min(sample, 16)], want_saved=False, nthreads=threads)
     t0 = time.perf_counter()
-    ref = O.gradient(cfgs, saveat, u0[:, :sample], pc, dW=dW, want_saved=False, nthreads=threads)
+    O.gradient(cfgs, saveat, u0[:, :sample], pc, dW=dW, want_saved=False, nthreads=threads)
     cpu_s = time.perf_counter() - t0
     line = {"metric": "ensemble adjoint trajectories/sec", "value": N / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -463,6 +704,7 @@ def main():
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (multiple of 32, <= 512)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c2f32", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
     ap.add_argument("--dtype", default="", help="c4 only: bf16_f32acc (default), f32 or f64")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the sharded C4 / C5 legs (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -86,10 +86,15 @@ typedef struct b200adj_cfg {
     double  cost_a, cost_b;
     uint64_t seed;                   /* Philox seed for SDE Wiener increments                              */
     int64_t traj_offset;             /* global index of member 0 (keeps Philox streams shard-independent)  */
-    int32_t checkpoint_every;        /* reserved (1 = every step)                                          */
+    int32_t checkpoint_every;        /* fixed-step Tsit5: keep the forward state every C steps only; the reverse pass re-solves each */
+                                     /* C-step segment into shared memory (CheckpointSolution, src/interpolating_adjoint.jl:54-112,  */
+                                     /* 206-278; src/gauss_adjoint.jl:57-95, 167-212).  0 or 1 = every step                          */
     uint32_t flags;
     int32_t mlp_hidden;              /* FAM_MLP hidden width                                               */
     int32_t block_threads;           /* 0 = library default; tuning knob                                   */
+    int32_t max_steps;               /* adaptive steppers: per-member step capacity of the dense forward / reverse solutions */
+                                     /* (the reference's maxiters); 0 = 4096                                */
+    int32_t reserved0;               /* must be 0                                                          */
 } b200adj_cfg;
 
 /* create: validates cfg, allocates checkpoints/partials on cfg.device, uploads tableaux.  Replaces the set-up done
@@ -158,6 +163,19 @@ int32_t b200adj_get_step_counts(void* handle, int32_t* fwd_steps, int32_t* rev_s
 /* tracing (needs B200ADJ_FLAG_TRACE at create): out[nblocks][3] = (SM id, %globaltimer ns at block start, at block end)
  * of the last reverse launch; call with out = NULL to query nblocks.  Host pointer always. */
 int32_t b200adj_get_block_trace(void* handle, uint64_t* out, int32_t* nblocks);
+
+/* ---- multi-GPU (SURVEY.md 8b "multi-GPU handle owns ... one NCCL communicator", 8e) ----
+ * One handle per GPU (one process per GPU, or several handles in one process); each handle owns cfg.N members of the
+ * ensemble (cfg.traj_offset = global index of its first member).  Rank 0 obtains a 128-byte id, the host broadcasts it over
+ * its own channel (Distributed.jl / MPI / a file), every rank attaches its handle.  From then on b200adj_reverse sums dp over
+ * the ranks (ncclAllReduce on the handle's stream, before the D2H copy) whenever shared_p = 1: the single collective of the
+ * path.  du0 and per-member dp stay sharded.  NCCL is bound with dlopen at the first call; without a usable libnccl.so.2
+ * these return B200ADJ_ERR_UNSUPPORTED and single-GPU use is unaffected. */
+int32_t b200adj_comm_unique_id(void* id_out /* 128 bytes */);
+int32_t b200adj_comm_init(void* handle, int32_t nranks, int32_t rank, const void* unique_id /* 128 bytes; NULL if nranks == 1 */);
+/* in-place sum of `count` reals (cfg.dtype's ABI element type) over the ranks, on the handle's stream; device pointer */
+int32_t b200adj_comm_allreduce(void* handle, void* buf, int64_t count);
+int32_t b200adj_comm_size(void* handle, int32_t* nranks, int32_t* rank);
 
 int32_t b200adj_destroy(void* handle);
 const char* b200adj_last_error(void* handle);   /* handle may be NULL: last create() error of this thread */

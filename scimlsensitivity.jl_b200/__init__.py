@@ -7,7 +7,7 @@ reference's `sensealg=` plugin surface.  Import as `scimlsensitivity_jl_b200` (t
 from . import _lib
 from ._lib import B200AdjError, build
 from .concrete_solve import (ChainRulesOriginator, NoTangent, ReverseDiffOriginator, TrackerOriginator,
-                             _concrete_solve_adjoint, solve)
+                             _concrete_solve_adjoint, clear_handle_cache, solve)
 from .distributed import allreduce_dp, shard_bounds
 from .engine import DeviceEnsemble
 from .problems import (EM, AdjointSensitivityParameterCompatibilityError, AffineAffect, AffineCost, PresetTimeCallback, EnsembleB200, EnsembleProblem,

@@ -18,12 +18,13 @@ SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kr
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
 DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
 COST = {"explicit": 0, "affine": 1}
-FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE = 1, 2, 4, 8, 16
+FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE, FLAG_NO_ROTATE = 1, 2, 4, 8, 16, 32
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
 EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_events", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
-           "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg"]
+           "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg",
+           "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_allreduce", "b200adj_comm_size"]
 
 
 class B200AdjError(RuntimeError):
@@ -45,6 +46,7 @@ class Cfg(C.Structure):
         ("cost_a", C.c_double), ("cost_b", C.c_double),
         ("seed", C.c_uint64), ("traj_offset", C.c_int64),
         ("checkpoint_every", C.c_int32), ("flags", C.c_uint32), ("mlp_hidden", C.c_int32), ("block_threads", C.c_int32),
+        ("max_steps", C.c_int32), ("reserved0", C.c_int32),
     ]
 
 
@@ -144,6 +146,14 @@ def load():
         lib.b200adj_get_block_trace.restype = C.c_int32
         lib.b200adj_destroy.argtypes = [C.c_void_p]
         lib.b200adj_destroy.restype = C.c_int32
+        lib.b200adj_comm_unique_id.argtypes = [C.c_void_p]
+        lib.b200adj_comm_unique_id.restype = C.c_int32
+        lib.b200adj_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        lib.b200adj_comm_init.restype = C.c_int32
+        lib.b200adj_comm_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+        lib.b200adj_comm_allreduce.restype = C.c_int32
+        lib.b200adj_comm_size.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.b200adj_comm_size.restype = C.c_int32
         lib.b200adj_last_error.argtypes = [C.c_void_p]
         lib.b200adj_last_error.restype = C.c_char_p
         lib.b200adj_version.restype = C.c_uint32
@@ -163,6 +173,15 @@ def _addr(x):
     if hasattr(x, "data_ptr"):
         return x.data_ptr()
     return x.ctypes.data
+
+
+def comm_unique_id():
+    """128-byte NCCL unique id (call on rank 0, broadcast over the host's own channel)."""
+    buf = C.create_string_buffer(128)
+    rc = load().b200adj_comm_unique_id(buf)
+    if rc != 0:
+        raise B200AdjError(rc, "b200adj_comm_unique_id failed (libnccl.so.2 not loadable?)")
+    return buf.raw
 
 
 class Handle:
@@ -235,6 +254,21 @@ class Handle:
         out = np.zeros((n.value, 3), dtype=np.uint64)
         self._check(self._lib.b200adj_get_block_trace(self._h, out.ctypes.data, C.byref(n)))
         return out
+
+    def comm_init(self, nranks, rank, unique_id):
+        """Attach this handle to an NCCL communicator of `nranks` handles (one per GPU); b200adj_reverse then sums dp over
+        the ranks itself.  unique_id: the 128 bytes of comm_unique_id() from rank 0."""
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        self._check(self._lib.b200adj_comm_init(self._h, int(nranks), int(rank), buf))
+
+    def comm_allreduce(self, buf, count):
+        self._check(self._lib.b200adj_comm_allreduce(self._h, _addr(buf), int(count)))
+
+    @property
+    def comm_size(self):
+        n, r = C.c_int32(), C.c_int32()
+        self._check(self._lib.b200adj_comm_size(self._h, C.byref(n), C.byref(r)))
+        return n.value, r.value
 
     def set_stream(self, stream_ptr):
         self._check(self._lib.b200adj_set_stream(self._h, stream_ptr))

@@ -70,6 +70,13 @@ def _step_size(alg, kwargs):
 _HANDLE_CACHE = {}
 
 
+def clear_handle_cache():
+    """Destroy the device handles kept by `EnsembleB200(reuse_handle=True)` solves."""
+    for eng in list(_HANDLE_CACHE.values()):
+        eng.close()
+    _HANDLE_CACHE.clear()
+
+
 def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sensealg=None, save_start=True,
           save_end=True, save_on=True, u0=None, p=None, **kwargs):
     """Batched forward solve of an EnsembleProblem on the device; keeps the checkpoints for a later adjoint."""
@@ -130,9 +137,10 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else (sensealg or InterpolatingAdjoint())
     block = getattr(sensealg, "block_threads", 0) if isinstance(sensealg, B200Adjoint) else 0
     stored = getattr(sensealg, "stored_noise", False) if isinstance(sensealg, B200Adjoint) else False
+    ckpt_every = getattr(sensealg, "checkpoint_every", 1) if isinstance(sensealg, B200Adjoint) else 1
     ev = callback.tables(d, P) if callback is not None else None
     key = (prob.f, alg.code, hi - lo, ts.tobytes(), tuple(prob.tspan), _step_size(alg, kwargs), shared_p, on_device, device,
-           getattr(prob, "seed", 0), lo, block, stored, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3),
+           getattr(prob, "seed", 0), lo, block, stored, ckpt_every, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3),
            None if ev is None else tuple(x.tobytes() for x in ev))
     eng = _HANDLE_CACHE.get(key) if ensemblealg.reuse_handle else None
     if eng is None:
@@ -141,9 +149,12 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
                              seed=getattr(prob, "seed", 0), traj_offset=lo, block_threads=block, stored_noise=stored,
                              quad_abstol=getattr(inner, "abstol", 1e-6), quad_reltol=getattr(inner, "reltol", 1e-3),
                              abstol=kwargs.get("abstol", 1e-6), reltol=kwargs.get("reltol", 1e-3),
-                             max_steps=kwargs.get("maxiters", 0), pin_outputs=ensemblealg.pin_outputs)
+                             max_steps=kwargs.get("maxiters", 0), pin_outputs=ensemblealg.pin_outputs,
+                             checkpoint_every=ckpt_every)
         if ev is not None:
             eng.set_events(*ev)
+        if world > 1 and shared_p:
+            distributed.attach_comm(eng)           # the one all-reduce of dp then runs inside b200adj_reverse (csrc/comm.cu)
         if ensemblealg.reuse_handle:
             _HANDLE_CACHE[key] = eng
     dW = getattr(prob, "noise", None)
@@ -154,7 +165,7 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
 
 
 def _concrete_solve_adjoint(prob, alg, sensealg, u0, p, originator=None, *args, save_start=True, save_end=True,
-                            saveat=None, save_idxs=None, **kwargs):
+                            saveat=None, save_idxs=None, ensemblealg=None, **kwargs):
     """-> (out, pullback).  `sensealg` is B200Adjoint(inner) (or a bare continuous adjoint)."""
     inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else sensealg
     if not isinstance(inner, (BacksolveAdjoint, InterpolatingAdjoint, QuadratureAdjoint, GaussAdjoint, GaussKronrodAdjoint)):
@@ -164,7 +175,7 @@ def _concrete_solve_adjoint(prob, alg, sensealg, u0, p, originator=None, *args, 
     d = FAMILIES[eprob.prob.f][0]
     u0_shape = tuple(u0.shape)
     u0m = u0.reshape(d, -1)                                            # u0 any shape -> vec (:978)
-    sol = solve(eprob, alg, EnsembleB200(), saveat=saveat, sensealg=sensealg, save_start=save_start,
+    sol = solve(eprob, alg, ensemblealg or EnsembleB200(), saveat=saveat, sensealg=sensealg, save_start=save_start,
                 save_end=save_end, u0=u0m, p=p, **kwargs)
     ts = sol.t
     only_end = len(ts) == 1 and ts[0] == eprob.prob.tspan[1]           # :716

@@ -121,7 +121,7 @@ void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
     cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
-    cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step);
+    cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step); cudaFree(h->d_fwd_save_of_step); cudaFree(h->d_fwd_saveat);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -131,7 +131,7 @@ void free_all(Handle* h) {
 
 extern "C" {
 
-uint32_t b200adj_version(void) { return 0x000100u; }
+uint32_t b200adj_version(void) { return 0x000200u; }
 uint32_t b200adj_sizeof_cfg(void) { return (uint32_t)sizeof(b200adj_cfg); }
 
 const char* b200adj_last_error(void* handle) {
@@ -188,7 +188,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true; h->nk = t5a ? 7 : 2;
         h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
         h->cfg.saveat = h->saveat.data();
-        h->maxs = cfg->checkpoint_every > 1 ? cfg->checkpoint_every : 4096;      // per-member step capacity (forward and dense reverse)
+        h->maxs = cfg->max_steps > 0 ? cfg->max_steps : 4096;      // per-member step capacity (forward and dense reverse)
         h->block = cfg->block_threads ? cfg->block_threads : 128;
         if (h->block < 32 || h->block > 256 || (h->block % 32)) { g_create_error = "block_threads must be a multiple of 32 in [32, 256] for Rosenbrock23"; delete h; return B200ADJ_ERR_INVALID; }
         h->grid = (int)((cfg->N + h->block - 1) / h->block);
@@ -216,6 +216,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         CREATE_TRY(cudaMalloc(&h->r_qidx, (size_t)h->maxseg * N * sizeof(int32_t)));
         CREATE_TRY(cudaMalloc(&h->d_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
         if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
+        // the forward pass keeps its own save table: set_reverse_options may re-target the reverse pass' jump times
+        h->fwd_K = cfg->K; h->fwd_saveat = h->saveat;
+        CREATE_TRY(cudaMalloc(&h->d_fwd_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
+        if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_fwd_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
         h->qpartials_blocks = (N + 3) / 4 + 1;                                  // quadrature kernel: 4 members (warps) per block
         CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpartials_blocks > (size_t)h->grid ? h->qpartials_blocks : (size_t)h->grid) * P * sizeof(double)));
         CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
@@ -296,6 +300,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
     CREATE_TRY(cudaMalloc(&h->d_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
     CREATE_TRY(cudaMemcpy(h->d_save_of_step, sos.data(), ((size_t)S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    // the forward pass keeps its own save table: set_reverse_options may re-target the reverse pass' jump times
+    h->fwd_K = cfg->K; h->fwd_saveat = h->saveat; h->fwd_save_of_step = sos;
+    CREATE_TRY(cudaMalloc(&h->d_fwd_save_of_step, ((size_t)S + 1) * sizeof(int32_t)));
+    CREATE_TRY(cudaMemcpy(h->d_fwd_save_of_step, sos.data(), ((size_t)S + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
     if (sde) CREATE_TRY(cudaMalloc(&h->d_noise, (size_t)S * m * N * e));
     // BF16_F32ACC = mlp_tc.cuh: member and gradient GEMMs in the time loop on tcgen05, accumulators in TMEM
     h->mlp_tc = mlp && cfg->dtype == B200ADJ_BF16_F32ACC;
@@ -473,14 +481,15 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         CUDA_TRY(h, cudaMemcpyAsync(h->s_u0, u0, c.d * N * e, cudaMemcpyHostToDevice, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(h->s_p, p, pn * e, cudaMemcpyHostToDevice, h->stream));
         du0 = h->s_u0; dp = h->s_p;
-        dsaved = (saved && c.K > 0) ? h->s_saved : nullptr;
+        dsaved = (saved && h->fwd_K > 0) ? h->s_saved : nullptr;
         dstatus = status ? h->s_status : nullptr;
     }
     h->cur_p = dp;
     int rc = 0;
     if (h->adaptive && c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE) {
         T5aArgs a = t5a_args(h);
-        a.u0 = du0; a.p = dp; a.saved = c.K > 0 ? dsaved : nullptr; a.status = dstatus;
+        a.saveat = h->d_fwd_saveat; a.K = h->fwd_K;
+        a.u0 = du0; a.p = dp; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.status = dstatus;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_t5a_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_fwd<Lorenz>(h, a); break;
@@ -489,7 +498,8 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         }
     } else if (h->adaptive) {
         RosArgs a = ros_args(h);
-        a.u0 = du0; a.p = dp; a.saved = c.K > 0 ? dsaved : nullptr; a.status = dstatus;
+        a.saveat = h->d_fwd_saveat; a.K = h->fwd_K;
+        a.u0 = du0; a.p = dp; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.status = dstatus;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_ros_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_ros_fwd<Lorenz>(h, a); break;
@@ -497,11 +507,11 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         default: rc = B200ADJ_ERR_UNSUPPORTED;
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
-        rc = mlp_forward_dispatch(h, du0, dp, c.K > 0 ? dsaved : nullptr, dstatus);
+        rc = mlp_forward_dispatch(h, du0, dp, h->fwd_K > 0 ? dsaved : nullptr, dstatus);
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         OdeFwdArgsT<float> a;
-        a.u0 = (const float*)du0; a.p = (const float*)dp; a.ckpt = (float*)h->d_ckpt; a.saved = c.K > 0 ? (float*)dsaved : nullptr;
-        a.save_of_step = h->d_save_of_step; a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S;
+        a.u0 = (const float*)du0; a.p = (const float*)dp; a.ckpt = (float*)h->d_ckpt; a.saved = h->fwd_K > 0 ? (float*)dsaved : nullptr;
+        a.save_of_step = h->d_fwd_save_of_step; a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S;
         cast_tables(h->tb, &a.tb);
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_fwd_f32<LotkaVolterra>(h, a); break;
@@ -510,7 +520,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         }
     } else if (!is_sde(c)) {
         OdeFwdArgs a;
-        a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
+        a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.save_of_step = h->d_fwd_save_of_step;
         a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_fwd<LotkaVolterra>(h, a); break;
@@ -520,7 +530,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         }
     } else {
         SdeFwdArgs a;
-        a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = c.K > 0 ? dsaved : nullptr; a.save_of_step = h->d_save_of_step;
+        a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.save_of_step = h->d_fwd_save_of_step;
         a.status = dstatus; a.N = c.N; a.S = h->S; a.h = c.dt; a.seed = c.seed; a.traj_offset = c.traj_offset;
         // noise: (1) caller-supplied increments (parity tests, reference-style NoiseGrid) are copied into the handle;
         // (2) STORED_NOISE: Philox increments are written out by the forward kernel; (3) default: Philox, regenerated
@@ -540,7 +550,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     if (rc) { h->err = "forward dispatch failed"; return rc; }
     CUDA_TRY(h, cudaGetLastError());
     if (!c.buffers_on_device) {
-        if (saved && c.K > 0) CUDA_TRY(h, cudaMemcpyAsync(saved, h->s_saved, (size_t)c.K * c.d * N * e, cudaMemcpyDeviceToHost, h->stream));
+        if (saved && h->fwd_K > 0) CUDA_TRY(h, cudaMemcpyAsync(saved, h->s_saved, (size_t)h->fwd_K * c.d * N * e, cudaMemcpyDeviceToHost, h->stream));
         if (status) CUDA_TRY(h, cudaMemcpyAsync(status, h->s_status, N * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     }
@@ -633,6 +643,8 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
     }
     if (rc) { h->err = "reverse dispatch failed (sensealg/family not built)"; return rc; }
     CUDA_TRY(h, cudaGetLastError());
+    // multi-GPU: the ONE collective of the path -- dG/dp summed over the ranks (shared parameters only)
+    if (c.shared_p && h->nranks > 1) { rc = comm_allreduce(h, ddp, (size_t)c.P); if (rc) return rc; }
     if (!c.buffers_on_device) {
         CUDA_TRY(h, cudaMemcpyAsync(du0, h->s_du0, c.d * N * e, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(dp, h->s_dp, pn * e, cudaMemcpyDeviceToHost, h->stream));
@@ -677,6 +689,7 @@ int32_t b200adj_destroy(void* handle) {
     Handle* h = (Handle*)handle;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->stream);
+    comm_release(h);
     free_all(h);
     delete h;
     return B200ADJ_OK;

@@ -1,0 +1,119 @@
+// comm.cu -- multi-GPU behind the C ABI: one handle per GPU (one process per GPU, or several handles
+// in one process), ensemble members sharded over the handles, and exactly ONE collective per gradient -- the sum of
+// dG/dp over the ranks when the parameters are shared -- issued by b200adj_reverse itself on the handle's stream.
+//
+// NCCL is bound at run time with dlopen("libnccl.so.2") (the copy a host process already carries -- PyTorch's bundled
+// one, or the system library for a Julia host), so libb200adj.so has no link-time dependency on it and single-GPU users
+// never load it.  The unique id travels through the host's own channel (MPI / Distributed.jl / torch.distributed store):
+//   rank 0: b200adj_comm_unique_id(id)  ->  broadcast the 128 bytes  ->  every rank: b200adj_comm_init(h, nranks, rank, id).
+#include <dlfcn.h>
+
+#include "handle.h"
+
+using namespace b200adj;
+
+namespace {
+
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm_t;
+enum { NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+struct Nccl {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+
+// loaded once per process; immutable afterwards (the "no global state" rule of the ABI is about mutable solver state)
+Nccl* nccl() {
+    static Nccl n;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
+        if (!n.lib) { n.err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return &n; }
+        n.GetUniqueId = (int (*)(nccl_uid*))dlsym(n.lib, "ncclGetUniqueId");
+        n.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid, int))dlsym(n.lib, "ncclCommInitRank");
+        n.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(n.lib, "ncclAllReduce");
+        n.CommDestroy = (int (*)(nccl_comm_t))dlsym(n.lib, "ncclCommDestroy");
+        n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+        if (!n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.CommDestroy) { n.err = "libnccl: missing symbols"; n.lib = nullptr; }
+    }
+    return &n;
+}
+
+}  // namespace
+
+namespace b200adj {
+
+// sum `count` reals (the handle's ABI element type) over the ranks, in place, on the handle's stream
+int comm_allreduce(Handle* h, void* buf, size_t count) {
+    if (!h->nccl_comm || h->nranks <= 1) return B200ADJ_OK;
+    Nccl* n = nccl();
+    const int dt = esz(h->cfg) == sizeof(double) ? NCCL_FLOAT64 : NCCL_FLOAT32;
+    const int rc = n->AllReduce(buf, buf, count, dt, NCCL_SUM, (nccl_comm_t)h->nccl_comm, h->stream);
+    if (rc != 0) { h->err = std::string("ncclAllReduce: ") + (n->GetErrorString ? n->GetErrorString(rc) : "error"); return B200ADJ_ERR_CUDA; }
+    h->launches++;
+    return B200ADJ_OK;
+}
+
+void comm_release(Handle* h) {
+    if (h->nccl_comm) { Nccl* n = nccl(); if (n->lib) n->CommDestroy((nccl_comm_t)h->nccl_comm); h->nccl_comm = nullptr; }
+    h->nranks = 1; h->rank = 0;
+}
+
+}  // namespace b200adj
+
+extern "C" {
+
+int32_t b200adj_comm_unique_id(void* id_out) {
+    if (!id_out) return B200ADJ_ERR_INVALID;
+    Nccl* n = nccl();
+    if (!n->lib) return B200ADJ_ERR_UNSUPPORTED;
+    nccl_uid id;
+    if (n->GetUniqueId(&id) != 0) return B200ADJ_ERR_CUDA;
+    memcpy(id_out, &id, sizeof(id));
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_comm_init(void* handle, int32_t nranks, int32_t rank, const void* unique_id) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && !unique_id)) { h->err = "comm_init: bad nranks/rank/id"; return B200ADJ_ERR_INVALID; }
+    comm_release(h);
+    if (nranks == 1) return B200ADJ_OK;
+    Nccl* n = nccl();
+    if (!n->lib) { h->err = n->err; return B200ADJ_ERR_UNSUPPORTED; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    nccl_uid id;
+    memcpy(&id, unique_id, sizeof(id));
+    nccl_comm_t comm = nullptr;
+    const int rc = n->CommInitRank(&comm, nranks, id, rank);
+    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (n->GetErrorString ? n->GetErrorString(rc) : "error"); return B200ADJ_ERR_CUDA; }
+    h->nccl_comm = comm; h->nranks = nranks; h->rank = rank;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_comm_allreduce(void* handle, void* buf, int64_t count) {
+    if (!handle || !buf || count < 0) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    if (h->nranks <= 1) return B200ADJ_OK;
+    if (!h->cfg.buffers_on_device) { h->err = "comm_allreduce: device buffers only (host results are reduced inside b200adj_reverse)"; return B200ADJ_ERR_INVALID; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    return comm_allreduce(h, buf, (size_t)count);
+}
+
+int32_t b200adj_comm_size(void* handle, int32_t* nranks, int32_t* rank) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    if (nranks) *nranks = h->nranks;
+    if (rank) *rank = h->rank;
+    return B200ADJ_OK;
+}
+
+}  // extern "C"

@@ -6,7 +6,7 @@ template <class T>
 int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
     MlpArgs<T> a;
     memset(&a, 0, sizeof(a));
-    a.u0 = (const T*)u0; a.p = (const T*)p; a.ckpt = (T*)h->d_ckpt; a.saved = (T*)saved; a.save_of_step = h->d_save_of_step;
+    a.u0 = (const T*)u0; a.p = (const T*)p; a.ckpt = (T*)h->d_ckpt; a.saved = (T*)saved; a.save_of_step = h->d_fwd_save_of_step;
     a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
     const size_t smem = sizeof(MlpSmem<T>);
     if (cudaFuncSetAttribute(mlp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
@@ -17,7 +17,7 @@ int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, in
 int mlp_tc_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
     MlpArgs<float> a;
     memset(&a, 0, sizeof(a));
-    a.u0 = (const float*)u0; a.p = (const float*)p; a.ckpt = (float*)h->d_ckpt; a.saved = (float*)saved; a.save_of_step = h->d_save_of_step;
+    a.u0 = (const float*)u0; a.p = (const float*)p; a.ckpt = (float*)h->d_ckpt; a.saved = (float*)saved; a.save_of_step = h->d_fwd_save_of_step;
     a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
     const size_t smem = sizeof(TcSmem) + 128;
     if (cudaFuncSetAttribute(mlp_tc_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;

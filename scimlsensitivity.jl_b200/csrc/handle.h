@@ -23,8 +23,6 @@
 
 namespace b200adj {
 
-struct NcclApi;      // dlopen'ed libnccl entry points (comm.cu)
-
 struct Handle {
     b200adj_cfg cfg;
     std::vector<double> saveat;
@@ -104,5 +102,7 @@ int sde_reverse_dispatch(Handle* h, const SdeRevArgs& a);
 int sde_noise_launch(Handle* h, const SdeNoiseArgs& a, int64_t total);
 int mlp_forward_dispatch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status);
 int mlp_reverse_dispatch(Handle* h, const void* dLdu, void* du0, void* dp);
+int comm_allreduce(Handle* h, void* buf, size_t count);     // comm.cu: in-place sum over ranks on h->stream (no-op without a communicator)
+void comm_release(Handle* h);
 
 }  // namespace b200adj

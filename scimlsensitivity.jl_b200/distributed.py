@@ -1,6 +1,11 @@
-"""Multi-GPU: one process per GPU (torch.distributed), ensemble members sharded contiguously over ranks, exactly one
-all-reduce(sum) of dG/dp per gradient when the parameters are shared.  No collective runs during
-time stepping: members are independent (that is what EnsembleProblem means, test/Core4/ensembles.jl:22-31).
+"""Multi-GPU: one process per GPU, ensemble members sharded contiguously over ranks, exactly one all-reduce(sum) of
+dG/dp per gradient when the parameters are shared.  No collective runs during time stepping: members are
+independent (that is what EnsembleProblem means, test/Core4/ensembles.jl:22-31).
+
+The collective itself lives BEHIND the C ABI (b200adj_comm_init / b200adj_reverse, csrc/comm.cu: ncclAllReduce on the
+handle's stream); torch.distributed is only the host channel that carries the 128-byte NCCL id from rank 0 to the
+others (what Distributed.jl / MPI would do for a Julia host).  `allreduce_dp` remains as the host-side fallback for
+handles without a communicator (the gloo CPU tests).
 """
 import numpy as np
 
@@ -28,10 +33,25 @@ def shard_bounds(N, rank=None, world_size=None):
     return (rank * N) // world_size, ((rank + 1) * N) // world_size
 
 
-def allreduce_dp(dp, eng=None):
-    """Sum the shared-parameter gradient over ranks (NCCL for CUDA tensors, gloo for host arrays)."""
+def attach_comm(eng):
+    """Give the engine's handle an NCCL communicator spanning all ranks (id broadcast through torch.distributed's store);
+    afterwards b200adj_reverse reduces dp itself.  No-op for world size 1."""
     d = _dist()
-    if d is None or d.get_world_size() == 1 or (eng is not None and not eng.shared_p):
+    if d is None or d.get_world_size() == 1 or getattr(eng, "comm_attached", False):
+        return eng
+    from . import _lib
+    box = [_lib.comm_unique_id() if d.get_rank() == 0 else None]
+    d.broadcast_object_list(box, src=0)
+    eng.handle.comm_init(d.get_world_size(), d.get_rank(), box[0])
+    eng.comm_attached = True
+    return eng
+
+
+def allreduce_dp(dp, eng=None):
+    """Sum the shared-parameter gradient over ranks on the host side (NCCL for CUDA tensors, gloo for host arrays).
+    Skipped when the handle owns a communicator: b200adj_reverse already returned the reduced gradient."""
+    d = _dist()
+    if d is None or d.get_world_size() == 1 or (eng is not None and (not eng.shared_p or getattr(eng, "comm_attached", False))):
         return dp
     import torch
     if hasattr(dp, "data_ptr"):

@@ -19,7 +19,8 @@ class DeviceEnsemble:
     def __init__(self, family, sensealg, stepper, N, saveat, tspan, dt, *, shared_p=True, cost=None,
                  on_device=False, device=0, no_start=False, checkpointing=True, ckpt_every_step=False,
                  stored_noise=False, seed=0, traj_offset=0, block_threads=0, abstol=1e-6, reltol=1e-3,
-                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False, max_steps=0, pin_outputs=False):
+                 quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False, max_steps=0, pin_outputs=False,
+                 checkpoint_every=1, no_rotate=False):
         d, P, m = FAMILIES[family]
         cfg = _lib.Cfg()
         cfg.rhs_family, cfg.sensealg, cfg.stepper, cfg.dtype = _lib.FAM[family], _lib.SA[sensealg], _lib.ST[stepper], _lib.DTYPE[dtype]
@@ -35,7 +36,8 @@ class DeviceEnsemble:
         cfg.mlp_hidden = 64 if family == "mlp" else 0
         self.dtype = dtype
         self.np_dtype = np.float64 if dtype == "f64" else np.float32      # bf16_f32acc: fp32 buffers at the ABI
-        cfg.checkpoint_every = int(max_steps) if max_steps else 1      # adaptive handles: per-member step capacity
+        cfg.max_steps = int(max_steps or 0)                  # adaptive handles: per-member step capacity (0 = 4096)
+        cfg.checkpoint_every = int(checkpoint_every or 1)    # fixed-step Tsit5: interval checkpointing
         flags = 0
         if no_start:
             flags |= _lib.FLAG_NO_START
@@ -47,6 +49,8 @@ class DeviceEnsemble:
             flags |= _lib.FLAG_STORED_NOISE
         if trace:
             flags |= _lib.FLAG_TRACE
+        if no_rotate:
+            flags |= _lib.FLAG_NO_ROTATE
         cfg.flags, cfg.block_threads = flags, int(block_threads)
         self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
         self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)
@@ -54,6 +58,8 @@ class DeviceEnsemble:
         self.events = None
         self.S = 0 if self.adaptive else int(round((cfg.t1 - cfg.t0) / cfg.dt))
         self.saveat = np.ascontiguousarray(saveat, dtype=np.float64)
+        # the forward pass keeps the create-time save table; set_reverse(t=...) only re-targets the reverse pass
+        self.fwd_saveat, self.fwd_K = self.saveat.copy(), len(self.saveat)
         self.handle = _lib.Handle(cfg, self.saveat)
         self._keep = []
         self.pin_outputs, self._pinned = bool(pin_outputs), {}
@@ -63,16 +69,17 @@ class DeviceEnsemble:
             self.use_current_torch_stream()
 
     # ---- buffers ----
-    def _empty(self, *shape, dtype="real"):
+    def _empty(self, *shape, dtype="real", role=""):
         if self.on_device:
             import torch
             td = torch.int32 if dtype == "i32" else (torch.float64 if self.dtype == "f64" else torch.float32)
             return torch.empty(shape, dtype=td, device=f"cuda:{self.device}")
         npdt = np.int32 if dtype == "i32" else self.np_dtype
         if self.pin_outputs:
-            # page-locked result buffers, allocated once per shape and REUSED by later calls on this handle (true async D2H
-            # instead of a staged pageable copy); callers that keep results across calls must copy them
-            key = (tuple(shape), np.dtype(npdt).str)
+            # page-locked result buffers, allocated once per (role, shape) and REUSED by later calls on this handle (true
+            # async D2H instead of a staged pageable copy); callers that keep results across calls must copy them.  The role
+            # keeps two outputs of one call apart when their shapes coincide (du0 / dp with P == d and per-member p).
+            key = (role, tuple(shape), np.dtype(npdt).str)
             if key not in self._pinned:
                 import torch
                 self._pinned[key] = torch.empty(tuple(shape), dtype=getattr(torch, np.dtype(npdt).name), pin_memory=True)
@@ -104,8 +111,8 @@ class DeviceEnsemble:
         p = self._prep(p, (self.P,) if self.shared_p else (self.P, self.N))
         if dW is not None:
             dW = self._prep(dW, (self.S, self.m, self.N))
-        saved = saved_out if saved_out is not None else (self._empty(self.K, self.d, self.N) if (want_saved and self.K > 0) else None)
-        status = self._empty(self.N, dtype="i32") if want_status else None
+        saved = saved_out if saved_out is not None else (self._empty(self.fwd_K, self.d, self.N, role="saved") if (want_saved and self.fwd_K > 0) else None)
+        status = self._empty(self.N, dtype="i32", role="status") if want_status else None
         self._keep = [u0, p, dW]                      # p must stay alive until reverse (device mode reads it in place)
         self.handle.forward(u0, p, saved, status, dW)
         return saved, status
@@ -113,8 +120,8 @@ class DeviceEnsemble:
     def reverse(self, dLdu=None, du0_out=None, dp_out=None):
         if dLdu is not None:
             dLdu = self._prep(dLdu, (self.K, self.d, self.N))
-        du0 = du0_out if du0_out is not None else self._empty(self.d, self.N)
-        dp = dp_out if dp_out is not None else (self._empty(self.P) if self.shared_p else self._empty(self.P, self.N))
+        du0 = du0_out if du0_out is not None else self._empty(self.d, self.N, role="du0")
+        dp = dp_out if dp_out is not None else (self._empty(self.P, role="dp") if self.shared_p else self._empty(self.P, self.N, role="dp"))
         self.handle.reverse(dLdu, du0, dp)
         return du0, dp
 
@@ -157,12 +164,12 @@ class DeviceEnsemble:
 
     def step_counts(self):
         """(forward, reverse) accepted-step counts per member of an adaptive handle."""
-        f, r = self._empty(self.N, dtype="i32"), self._empty(self.N, dtype="i32")
+        f, r = self._empty(self.N, dtype="i32", role="fwd_n"), self._empty(self.N, dtype="i32", role="rev_n")
         self.handle.step_counts(f, r)
         return f, r
 
     def noise(self):
-        out = self._empty(self.S, self.m, self.N)
+        out = self._empty(self.S, self.m, self.N, role="noise")
         self.handle.get_noise(out)
         return out
 

@@ -117,6 +117,8 @@ class B200Adjoint(AbstractAdjointSensitivityAlgorithm):
     inner: Any = None
     block_threads: int = 0
     stored_noise: bool = False
+    checkpoint_every: int = 1     # fixed-step Tsit5 with inner.checkpointing: keep the forward state every C steps and re-solve
+                                  # each segment in the reverse pass (the reference's `checkpoints` grid, src/interpolating_adjoint.jl:54-112)
 
     def __post_init__(self):
         if self.inner is None:

@@ -28,6 +28,8 @@ def main():
     lo, hi = b.shard_bounds(N)
     assert sol.u.shape == (21, 3, hi - lo)
     du0, dp = b.adjoint_sensitivities(sol, b.Tsit5(dt=dt), t=t, dgdu_discrete=b.AffineCost(1.0, -2.0), sensealg=b.GaussAdjoint())
+    # the all-reduce ran behind the C ABI (b200adj_comm_init + ncclAllReduce inside b200adj_reverse), not in torch.distributed
+    assert sol.engine.comm_attached and sol.engine.handle.comm_size == (world, rank)
     cfg = O.make_cfg("lorenz", "gauss", "tsit5_fixed", N, t, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0))
     ref = O.gradient(cfg, t, u0, p)
     e_dp = np.abs(dp.ravel() - ref["dp"]).max() / np.abs(ref["dp"]).max()

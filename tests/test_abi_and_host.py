@@ -37,7 +37,7 @@ def test_cfg_struct_layout_matches_header():
     names = re.findall(r"(\w+)\s*(?:,|;)", re.sub(r"/\*.*?\*/", "", body, flags=re.S))
     fields = [n for n, _ in _lib.Cfg._fields_]
     assert [n for n in names if n in fields] == fields
-    assert C.sizeof(_lib.Cfg) == _lib.load().b200adj_sizeof_cfg() == 168
+    assert C.sizeof(_lib.Cfg) == _lib.load().b200adj_sizeof_cfg() == 176
 
 
 @pytest.mark.skipif(_has_gpu(), reason="checks the no-device behaviour")

@@ -127,3 +127,49 @@ def test_travelling_warp_groups_all_remainders(per_sm, sa):
         _, dps = e1.reverse(); _, dpm = e2.reverse()
         assert _rel(np.asarray(dps), np.asarray(dpm).sum(axis=1)) < 1e-11
         e1.close(); e2.close()
+
+
+def test_pinned_outputs_do_not_alias_when_shapes_coincide():
+    """pin_outputs=True with per-member parameters and P == d (Lorenz): du0 and dp are distinct page-locked buffers
+    (the cache is keyed by role), and so are the two step-count arrays of an adaptive handle."""
+    N = 40
+    saveat = np.linspace(0.0, 1.0, 11)
+    rng = np.random.default_rng(3)
+    u0 = np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N))
+    p = np.array([10.0, 28.0, 8.0 / 3.0])[:, None] * np.exp(0.01 * rng.standard_normal((3, N)))
+    eng = b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", N, saveat, (0.0, 1.0), 0.01, shared_p=False,
+                           cost=b.AffineCost(1.0, -2.0), pin_outputs=True)
+    eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    assert du0.ctypes.data != dp.ctypes.data
+    cfg = O.make_cfg("lorenz", "gauss", "tsit5_fixed", N, saveat, 0.0, 1.0, dt=0.01, cost=("affine", 1.0, -2.0), shared_p=False)
+    ref = O.gradient(cfg, saveat, u0, p, want_saved=False)
+    assert _rel(du0, ref["du0"]) < 1e-9 and _rel(dp, ref["dp"]) < 1e-9
+    eng.close()
+    eng = b.DeviceEnsemble("lv", "gauss", "tsit5_adaptive", 8, saveat, (0.0, 1.0), 0.0, cost=b.AffineCost(0.0, 1.0),
+                           abstol=1e-8, reltol=1e-8, pin_outputs=True)
+    eng.forward(np.ones((2, 8)), P_LV)
+    eng.reverse()
+    f, r = eng.step_counts()
+    assert f.ctypes.data != r.ctypes.data and (f > 0).all() and (r > 0).all()
+    eng.close()
+
+
+def test_finer_reverse_times_do_not_disturb_the_forward_save_table():
+    """adjoint_sensitivities(sol, t = finer grid) re-targets the reverse pass only: a later forward pass on the same handle
+    still writes the create-time K save points (no overflow of the staging buffer, sol.t matches sol.u)."""
+    N = 50
+    coarse, fine = np.linspace(0.0, 1.0, 3), np.linspace(0.0, 1.0, 21)
+    rng = np.random.default_rng(5)
+    u0 = np.exp(0.1 * rng.standard_normal((2, N)))
+    for stepper, dt, kw in (("tsit5_fixed", 0.01, {}), ("tsit5_adaptive", 0.0, dict(abstol=1e-9, reltol=1e-9))):
+        eng = b.DeviceEnsemble("lv", "gauss", stepper, N, coarse, (0.0, 1.0), dt, cost=b.AffineCost(1.0, 0.0), **kw)
+        s1, _ = eng.forward(u0, P_LV)
+        eng.set_reverse("gauss", cost=b.AffineCost(1.0, 0.0), t=fine)
+        du0, dp = eng.reverse()
+        cfg = O.make_cfg("lv", "gauss", stepper, N, fine, 0.0, 1.0, dt=dt, cost=("affine", 1.0, 0.0), **kw)
+        ref = O.gradient(cfg, fine, u0, P_LV, want_saved=False)
+        assert _rel(du0, ref["du0"]) < 1e-7 and _rel(dp, ref["dp"]) < 1e-7
+        s2, _ = eng.forward(u0, P_LV)
+        assert s2.shape == (3, 2, N) and np.array_equal(np.asarray(s1), np.asarray(s2))
+        eng.close()
