@@ -274,13 +274,22 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     }
     if (block < 32 || block > 512 || (block % 32) != 0) { g_create_error = "block_threads must be a multiple of 32 in [32, 512]"; return B200ADJ_ERR_INVALID; }
     if (mlp) block = MLP_TB;      // members per block (the kernels run MLP_THREADS threads per block)
+    // interval checkpointing (a14): forward states every C steps, segments re-solved by the reverse kernel
+    int ckpt_every = cfg->checkpoint_every > 1 ? cfg->checkpoint_every : 1;
+    if (ckpt_every > 1) {
+        if (mlp || sde || (cfg->sensealg != B200ADJ_SA_INTERPOLATING && cfg->sensealg != B200ADJ_SA_GAUSS)) {
+            g_create_error = "checkpoint_every > 1: fixed-step Tsit5 with InterpolatingAdjoint / GaussAdjoint (the sensealgs that checkpoint in the reference)"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (ckpt_every > S) ckpt_every = (int)S;
+        const size_t need = (size_t)ckpt_every * d * block * esz(*cfg);
+        if (need > 160 * 1024) { g_create_error = "checkpoint_every * d * block_threads * sizeof(real) exceeds 160 KB of shared memory: lower checkpoint_every or block_threads"; return B200ADJ_ERR_INVALID; }
+    }
 
     Handle* h = new Handle();
     h->cfg = *cfg; h->cfg.m = m;
     h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
     h->cfg.saveat = h->saveat.data();
     h->save_of_step = sos;
-    h->S = (int)S; h->block = block;
+    h->S = (int)S; h->block = block; h->ckpt_every = ckpt_every;
     h->grid = (int)((cfg->N + block - 1) / block);
 #define CREATE_TRY(expr)                                                                         \
     do { cudaError_t _e = (expr); if (_e != cudaSuccess) {                                       \
@@ -293,7 +302,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     const size_t N = (size_t)cfg->N, e = esz(*cfg);
     const size_t Npad = ((N + block - 1) / block) * block;     // padded checkpoint pitch (whole TMA rows per block)
     h->Npad = (int64_t)Npad;
-    CREATE_TRY(cudaMalloc(&h->d_ckpt, ((size_t)S + 1) * d * Npad * e));
+    const size_t ckpt_rows = ckpt_every > 1 ? ((size_t)S + ckpt_every - 1) / ckpt_every + 1 : (size_t)S + 1;
+    CREATE_TRY(cudaMalloc(&h->d_ckpt, ckpt_rows * d * Npad * e));
     h->qpart_blocks_fixed = (N + 3) / 4 + 1;
     CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpart_blocks_fixed > (size_t)h->grid ? h->qpart_blocks_fixed : (size_t)h->grid) * P * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
@@ -336,6 +346,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     b200adj_cfg& c = h->cfg;
     if (sensealg < 0 || sensealg > 4 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
     if (sensealg == B200ADJ_SA_GAUSSKRONROD && !h->adaptive) { h->err = "GaussKronrodAdjoint: built for the adaptive steppers"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (h->ckpt_every > 1 && sensealg != B200ADJ_SA_INTERPOLATING && sensealg != B200ADJ_SA_GAUSS) { h->err = "checkpoint_every > 1: InterpolatingAdjoint / GaussAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (h->nev > 0 && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: QuadratureAdjoint has no callback support"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -511,7 +522,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         OdeFwdArgsT<float> a;
         a.u0 = (const float*)du0; a.p = (const float*)dp; a.ckpt = (float*)h->d_ckpt; a.saved = h->fwd_K > 0 ? (float*)dsaved : nullptr;
-        a.save_of_step = h->d_fwd_save_of_step; a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S;
+        a.save_of_step = h->d_fwd_save_of_step; a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.ckpt_every = h->ckpt_every;
         cast_tables(h->tb, &a.tb);
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_fwd_f32<LotkaVolterra>(h, a); break;
@@ -521,7 +532,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     } else if (!is_sde(c)) {
         OdeFwdArgs a;
         a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.save_of_step = h->d_fwd_save_of_step;
-        a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb;
+        a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.ckpt_every = h->ckpt_every;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_fwd<Lorenz>(h, a); break;

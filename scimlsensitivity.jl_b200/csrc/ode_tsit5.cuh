@@ -49,6 +49,7 @@ template <class R> struct OdeFwdArgsT {
     int64_t N;
     int64_t Npad;            // checkpoint row pitch: N rounded up to the block size (every block owns full 16B-aligned rows)
     int32_t S;
+    int32_t ckpt_every;      // C: row m of ckpt holds u_{mC} (m < ceil(S/C)), row ceil(S/C) holds u_S; C = 1: every step
     Tsit5TablesT<R> tb;
 };
 using OdeFwdArgs = OdeFwdArgsT<double>;
@@ -67,6 +68,7 @@ template <class R> struct OdeRevArgsT {
     int64_t Npad;            // checkpoint row pitch
     int32_t S;
     int32_t slots;           // member slots per block (= checkpoint tile width); blockDim.x > slots => the top warp row rotates
+    int32_t ckpt_every;      // C > 1 (SEG kernels): forward states kept every C steps, each segment re-solved into shared memory
     R cost_a, cost_b;
     R cont_a, cont_b;   // continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u):  dlam -= dgdu_continuous(y)  (flags bit3)
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step, bit3 continuous cost
@@ -152,6 +154,7 @@ __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constan
     R u[D], k[7][D], tmp[D];
     load_state<D>(a.u0, a.N, i, u);
     const int64_t stride = (int64_t)D * a.N, cstride = (int64_t)D * a.Npad;
+    const int CK = a.ckpt_every > 1 ? a.ckpt_every : 1;
     // checkpoints: padded pitch, threads past N shadow member N-1 and fill the pad columns (keeps TMA rows whole)
     store_state<D>(a.ckpt, a.Npad, gi, u);
     if (active && a.saved) { int ks = a.save_of_step[0]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
@@ -168,7 +171,11 @@ __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constan
 #pragma unroll
         for (int j = 0; j < D; j++) u[j] = tmp[j];
         Fam::f(u, p, k[0]);                      // FSAL: k7 of this step = k1 of the next
-        store_state<D>(a.ckpt + (int64_t)(n + 1) * cstride, a.Npad, gi, u);
+        // checkpoints: every step, or every C-th step plus the final state (CheckpointSolution grid of the reference,
+        // src/interpolating_adjoint.jl:54-112: the reverse pass re-solves each segment from its left checkpoint)
+        if (CK == 1) store_state<D>(a.ckpt + (int64_t)(n + 1) * cstride, a.Npad, gi, u);
+        else if ((n + 1) % CK == 0) store_state<D>(a.ckpt + (int64_t)((n + 1) / CK) * cstride, a.Npad, gi, u);
+        else if (n + 1 == a.S) store_state<D>(a.ckpt + (int64_t)((a.S + CK - 1) / CK) * cstride, a.Npad, gi, u);
         if (active && a.saved) { int ks = a.save_of_step[n + 1]; if (ks >= 0) store_state<D>(a.saved + (int64_t)ks * stride, a.N, i, u); }
     }
     if (active && a.status) {
@@ -255,7 +262,9 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
 constexpr int REV_CH = REV_CH_DEF, REV_NST = 2;     // TMA pipeline: steps per stage (= block barrier period), stages in flight
 static_assert(REV_CH_DEF <= 4, "hand-over barrier ids are keyed by step & 3: the block barrier period must not exceed 4 steps");
 template <int D, class R = double> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(R); }
-template <class Fam, int SA, bool SHARED_P, int COST, bool CONT, class R = double>
+// SEG kernels (interval checkpointing): one re-solved segment of C states per member slot instead of the TMA stages
+template <int D, class R = double> constexpr size_t rev_seg_smem_bytes(int block, int C) { return (size_t)C * D * block * sizeof(R); }
+template <class Fam, int SA, bool SHARED_P, int COST, bool CONT, class R = double, bool SEG = false>
 __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgsT<R> a) {
     constexpr int D = Fam::D, P = Fam::P;
     // BLOCK = member slots of this block.  When the slot count is not a multiple of 4 warps the SM's four sub-partitions
@@ -369,12 +378,20 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
                     tma_load_1d(&s_ck[(size_t)((st * CH + j) * D + dd) * BLOCK], ck_col + ((int64_t)nn * D + dd) * Npad, row_bytes, &s_bar[st]);
             }
         };
-        if (threadIdx.x == 0) {
-            for (int st = 0; st < NST; st++) mbar_init(&s_bar[st], 1);
-            mbar_fence_init();
+        if (!SEG) {
+            if (threadIdx.x == 0) {
+                for (int st = 0; st < NST; st++) mbar_init(&s_bar[st], 1);
+                mbar_fence_init();
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) for (int k = 0; k < NST && k < NC; k++) issue_chunk(k);
         }
-        __syncthreads();
-        if (threadIdx.x == 0) for (int k = 0; k < NST && k < NC; k++) issue_chunk(k);
+        // SEG (checkpoint_every = C > 1; CheckpointSolution machinery of src/interpolating_adjoint.jl:54-112, 206-278 and
+        // src/gauss_adjoint.jl:57-95, 167-212): only u_{mC} is in HBM.  When the reverse solve enters segment m (its first step
+        // is n = min((m+1)C, S) - 1) the member's forward solve is repeated from u_{mC} and the C states land in this slot's
+        // own shared-memory column; the steps of the segment then read them back exactly as the TMA path reads its tile.
+        const int CK = SEG ? a.ckpt_every : 1;
+        const int MROW = SEG ? (a.S + CK - 1) / CK : a.S;          // checkpoint row holding u_S
 
         constexpr int NV = 4 * D + P;          // rotating state: lam, mu, ka[0], kf[6], uhi
         __shared__ R s_mig[3 * NV * 32];
@@ -383,7 +400,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #pragma unroll
             for (int q = 0; q < P; q++) s_migp[((grp - q4) * P + q) * 32 + (threadIdx.x & 31)] = p[q];
         }
-        load_state<D>(a.ckpt + (int64_t)a.S * cstride, Npad, grp >= 0 ? gi : 0, uhi);
+        load_state<D>(a.ckpt + (int64_t)MROW * cstride, Npad, grp >= 0 ? gi : 0, uhi);
         {
             // jump at t = T (PresetTimeCallback fires at initialisation when T is a save time)
             int ks = a.save_of_step[a.S];
@@ -412,14 +429,44 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
                     }
                 }
             }
-            if (jj == 0) mbar_wait(&s_bar[st], (uint32_t)((k / NST) & 1));
-            if (grp >= 0) {
+            if (!SEG) {
+                if (jj == 0) mbar_wait(&s_bar[st], (uint32_t)((k / NST) & 1));
+                if (grp >= 0) {
 #pragma unroll
-                for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[(size_t)((st * CH + jj) * D + dd) * BLOCK + grp * 32 + (threadIdx.x & 31)];
-            }
-            if (jj == CH - 1 || n == 0) {
-                __syncthreads();               // every thread has read this stage: hand it back to the TMA producer
-                if (threadIdx.x == 0 && k + NST < NC) issue_chunk(k + NST);
+                    for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[(size_t)((st * CH + jj) * D + dd) * BLOCK + grp * 32 + (threadIdx.x & 31)];
+                }
+                if (jj == CH - 1 || n == 0) {
+                    __syncthreads();               // every thread has read this stage: hand it back to the TMA producer
+                    if (threadIdx.x == 0 && k + NST < NC) issue_chunk(k + NST);
+                }
+            } else {
+                const int m = n / CK, js = n - m * CK;
+                const int slot = grp * 32 + (int)(threadIdx.x & 31);
+                if (grp >= 0 && (n == a.S - 1 || js == CK - 1)) {
+                    // entering segment m: forward re-solve u_{mC} -> u_{mC + cnt - 1} into this slot's column
+                    const int cnt = min(CK, a.S - m * CK);
+                    R us[D], ts[D];
+                    load_state<D>(a.ckpt + (int64_t)m * cstride, Npad, member_gi(), us);
+#pragma unroll
+                    for (int dd = 0; dd < D; dd++) s_ck[(size_t)dd * BLOCK + slot] = us[dd];
+                    Fam::f(us, p, kf[0]);
+                    for (int q = 1; q < cnt; q++) {
+                        tsit5_stage<D, 1>(tb, us, kf, ts); Fam::f(ts, p, kf[1]);
+                        tsit5_stage<D, 2>(tb, us, kf, ts); Fam::f(ts, p, kf[2]);
+                        tsit5_stage<D, 3>(tb, us, kf, ts); Fam::f(ts, p, kf[3]);
+                        tsit5_stage<D, 4>(tb, us, kf, ts); Fam::f(ts, p, kf[4]);
+                        tsit5_stage<D, 5>(tb, us, kf, ts); Fam::f(ts, p, kf[5]);
+                        tsit5_stage<D, 6>(tb, us, kf, ts);
+#pragma unroll
+                        for (int dd = 0; dd < D; dd++) { us[dd] = ts[dd]; s_ck[(size_t)(q * D + dd) * BLOCK + slot] = ts[dd]; }
+                        Fam::f(us, p, kf[0]);
+                    }
+                }
+                if (grp >= 0) {
+#pragma unroll
+                    for (int dd = 0; dd < D; dd++) ulo[dd] = s_ck[(size_t)(js * D + dd) * BLOCK + slot];
+                }
+                if (jj == CH - 1 || n == 0) __syncthreads();       // lockstep only (see above)
             }
             if (grp < 0) continue;             // resting warp of the rotating row: barriers only
 
