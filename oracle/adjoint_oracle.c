@@ -792,6 +792,9 @@ static void gk15(integrand_fn f, void* ctx, int P, double a, double b, double* I
 }
 /* QuadGK.jl's adapt loop: pop the largest-error segment, bisect, and update the running totals INCREMENTALLY
  * (I = (I - s.I) + s1.I + s2.I, E likewise); the running I is what is returned. */
+/* diagnostics: integrand evaluations spent by all quadgk calls since the last reset (sizing of the device kernel) */
+static long g_quadgk_evals = 0;
+long oracle_quadgk_evals(int reset) { long v = g_quadgk_evals; if (reset) g_quadgk_evals = 0; return v; }
 long oracle_quadgk(integrand_fn f, void* ctx, int P, double a, double b, double atol, double rtol, double* out) {
     int cap = 64, n = 1; long evals = 15;
     gkseg* S = (gkseg*)malloc(sizeof(gkseg) * cap);
@@ -821,6 +824,8 @@ long oracle_quadgk(integrand_fn f, void* ctx, int P, double a, double b, double 
     }
     for (int i = 0; i < n; i++) free(S[i].I);
     free(S); free(w1);
+#pragma omp atomic
+    g_quadgk_evals += evals;
     return evals;
 }
 typedef struct { const family_t* F; const double* p; const dense_t* sol; const adjdense_t* adj; double* y; double* lam; double* dl; } quad_ctx;

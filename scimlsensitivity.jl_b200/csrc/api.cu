@@ -81,8 +81,8 @@ T5aArgs t5a_args(Handle* h) {
     memset(&a, 0, sizeof(a));
     a.saveat = h->d_saveat; a.partials = h->d_partials; a.ticket = h->d_ticket;
     a.ft = h->r_ft; a.fu = h->r_fu; a.fk = h->r_fk; a.fn = h->r_fn;
-    a.rt0 = h->r_rt0; a.rh = h->r_rh; a.rz = h->r_rz; a.rk = h->r_rk; a.rn = h->r_rn;
-    a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.qidx = h->r_qidx; a.maxseg = h->maxseg;
+    a.rrec = h->r_rrec; a.rend = h->r_rend; a.ftT = h->r_ftT; a.frecT = h->r_frecT; a.rn = h->r_rn;
+    a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.maxseg = h->maxseg;
     a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.dt0 = c.dt; a.abstol = c.abstol; a.reltol = c.reltol;
     a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
     a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
@@ -110,8 +110,8 @@ RosArgs ros_args(Handle* h) {
     memset(&a, 0, sizeof(a));
     a.saveat = h->d_saveat; a.partials = h->d_partials; a.ticket = h->d_ticket;
     a.ft = h->r_ft; a.fu = h->r_fu; a.fk = h->r_fk; a.fn = h->r_fn;
-    a.rt0 = h->r_rt0; a.rh = h->r_rh; a.rz = h->r_rz; a.rk = h->r_rk; a.rn = h->r_rn;
-    a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.qidx = h->r_qidx; a.maxseg = h->maxseg;
+    a.rrec = h->r_rrec; a.rend = h->r_rend; a.ftT = h->r_ftT; a.frecT = h->r_frecT; a.rn = h->r_rn;
+    a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.maxseg = h->maxseg;
     a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.abstol = c.abstol; a.reltol = c.reltol;
     a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
     a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
@@ -119,8 +119,8 @@ RosArgs ros_args(Handle* h) {
 }
 void free_all(Handle* h) {
     cudaSetDevice(h->cfg.device);
-    cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rt0); cudaFree(h->r_rh); cudaFree(h->r_rz); cudaFree(h->r_rk);
-    cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey); cudaFree(h->r_qidx);
+    cudaFree(h->r_ft); cudaFree(h->r_fu); cudaFree(h->r_fk); cudaFree(h->r_rrec); cudaFree(h->r_rend); cudaFree(h->r_ftT); cudaFree(h->r_frecT);
+    cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey);
     cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step); cudaFree(h->d_fwd_save_of_step); cudaFree(h->d_fwd_saveat);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
@@ -128,6 +128,26 @@ void free_all(Handle* h) {
 }
 
 }  // namespace
+
+namespace b200adj {
+// QuadratureAdjoint on an adaptive handle: the dense reverse solution, the member-major copy of the forward one and the
+// quadgk scratch are only needed by this sensealg -- allocate them at its first reverse pass
+int ensure_quad_buffers(Handle* h) {
+    if (h->r_rrec) return B200ADJ_OK;
+    const b200adj_cfg& c = h->cfg;
+    const size_t N = (size_t)c.N, MS = (size_t)h->maxs, e = sizeof(double);
+    const size_t RWP = quad_pad(3 + (1 + h->nk) * c.d), FWP = quad_pad((1 + h->nk) * c.d + 3);
+    if (cudaMalloc(&h->r_rrec, N * MS * RWP * e) != cudaSuccess || cudaMalloc(&h->r_rend, N * MS * e) != cudaSuccess ||
+        cudaMalloc(&h->r_ftT, N * (MS + 1) * e) != cudaSuccess || cudaMalloc(&h->r_frecT, N * MS * FWP * e) != cudaSuccess ||
+        cudaMalloc(&h->r_qseg, quad_seg_doubles(c.P, h->maxseg, h->qgrid) * e) != cudaSuccess ||
+        cudaMalloc(&h->r_qkey, (size_t)h->qgrid * QUAD_WARPS * h->maxseg * e) != cudaSuccess) {
+        cudaGetLastError();
+        h->err = "out of device memory for the QuadratureAdjoint buffers (dense reverse solution: N * max_steps records)";
+        return B200ADJ_ERR_OOM;
+    }
+    return B200ADJ_OK;
+}
+}  // namespace b200adj
 
 extern "C" {
 
@@ -205,22 +225,19 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         CREATE_TRY(cudaMalloc(&h->r_fu, (MS + 1) * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_fk, MS * h->nk * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_fn, N * sizeof(int32_t)));
-        CREATE_TRY(cudaMalloc(&h->r_rt0, MS * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_rh, MS * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_rz, MS * d * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_rk, MS * h->nk * d * N * e));
         CREATE_TRY(cudaMalloc(&h->r_rn, N * sizeof(int32_t)));
-        h->maxseg = 2 * h->maxs;                                              // quadgk segment capacity per member
-        CREATE_TRY(cudaMalloc(&h->r_qseg, (size_t)h->maxseg * (2 + P) * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_qkey, (size_t)h->maxseg * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_qidx, (size_t)h->maxseg * N * sizeof(int32_t)));
+        h->maxseg = 2 * h->maxs;                                              // quadgk segment capacity per data interval (multiple of 32)
+        {
+            cudaDeviceGetAttribute(&h->nsm, cudaDevAttrMultiProcessorCount, cfg->device);
+            h->qgrid = quad_grid(cfg->N, h->nsm);
+        }
         CREATE_TRY(cudaMalloc(&h->d_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
         if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
         // the forward pass keeps its own save table: set_reverse_options may re-target the reverse pass' jump times
         h->fwd_K = cfg->K; h->fwd_saveat = h->saveat;
         CREATE_TRY(cudaMalloc(&h->d_fwd_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
         if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_fwd_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
-        h->qpartials_blocks = (N + 3) / 4 + 1;                                  // quadrature kernel: 4 members (warps) per block
+        h->qpartials_blocks = (size_t)h->qgrid + 1;                              // quadrature kernel: persistent grid
         CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpartials_blocks > (size_t)h->grid ? h->qpartials_blocks : (size_t)h->grid) * P * sizeof(double)));
         CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
         CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
@@ -304,7 +321,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     h->Npad = (int64_t)Npad;
     const size_t ckpt_rows = ckpt_every > 1 ? ((size_t)S + ckpt_every - 1) / ckpt_every + 1 : (size_t)S + 1;
     CREATE_TRY(cudaMalloc(&h->d_ckpt, ckpt_rows * d * Npad * e));
-    h->qpart_blocks_fixed = (N + 3) / 4 + 1;
+    h->nsm = nsm; h->qgrid = quad_grid(cfg->N, nsm);
+    h->qpart_blocks_fixed = (size_t)h->qgrid + 1;
     CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpart_blocks_fixed > (size_t)h->grid ? h->qpart_blocks_fixed : (size_t)h->grid) * P * sizeof(double)));
     CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
     CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));

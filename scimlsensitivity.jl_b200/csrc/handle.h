@@ -29,7 +29,7 @@ struct Handle {
     std::vector<int32_t> save_of_step;
     int S = 0;
     int64_t Npad = 0;
-    int block = 64, grid = 0;
+    int block = 64, grid = 0, nsm = 148;
     int ckpt_every = 1;               // fixed-step Tsit5: forward states kept every C steps, segments re-solved in the reverse pass
     cudaStream_t stream = nullptr, own_stream = nullptr;
     // device memory owned by the handle
@@ -48,9 +48,13 @@ struct Handle {
     bool cont_on = false; double cont_a = 0, cont_b = 0, cont_c = 0, cont_e = 0;   // continuous cost family
     double dgdp_c = 0, dgdp_e = 0;    // discrete cost's parameter part: dgdp_discrete = c p + e at every save time
     bool mlp_tc = false;              // BF16_F32ACC: every GEMM-shaped piece of the time loop on tcgen05 (mlp_tc.cuh)
-    double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *r_rt0 = nullptr, *r_rh = nullptr, *r_rz = nullptr, *r_rk = nullptr, *d_saveat = nullptr;
-    int32_t *r_fn = nullptr, *r_rn = nullptr, *r_qidx = nullptr;
-    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
+    double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *d_saveat = nullptr;
+    // QuadratureAdjoint on the adaptive steppers (allocated at the first Quadrature reverse pass): member-major reverse dense
+    // solution + member-major copy of the forward one (quadgk.cuh)
+    double *r_rrec = nullptr, *r_rend = nullptr, *r_ftT = nullptr, *r_frecT = nullptr;
+    int32_t *r_fn = nullptr, *r_rn = nullptr;
+    // quadgk scratch of the QuadratureAdjoint kernels, sized per RESIDENT warp of the persistent grid qgrid (quadgk.cuh)
+    double *r_qseg = nullptr, *r_qkey = nullptr; int maxseg = 0; int qgrid = 0; size_t qpartials_blocks = 0; int saveat_dev_K = 0;
     // forward save table (the primal output of b200adj_forward) kept apart from the reverse pass' jump times
     int fwd_K = 0; std::vector<double> fwd_saveat; std::vector<int32_t> fwd_save_of_step; int32_t* d_fwd_save_of_step = nullptr; double* d_fwd_saveat = nullptr;
     // staging (buffers_on_device == 0)
@@ -104,5 +108,19 @@ int mlp_forward_dispatch(Handle* h, const void* u0, const void* p, void* saved, 
 int mlp_reverse_dispatch(Handle* h, const void* dLdu, void* du0, void* dp);
 int comm_allreduce(Handle* h, void* buf, size_t count);     // comm.cu: in-place sum over ranks on h->stream (no-op without a communicator)
 void comm_release(Handle* h);
+
+// persistent grid of the quadrature kernels and the dynamic shared memory (block maxima of the key array) per block
+inline int quad_grid(int64_t N, int nsm) { const int64_t g = (N + QUAD_WARPS - 1) / QUAD_WARPS, cap = (int64_t)nsm * QUAD_BLOCKS_PER_SM; return (int)(g < cap ? g : cap); }
+// blocks actually launched: what is resident at once (a static member -> warp assignment must not queue a second, partial wave)
+template <class K> inline int quad_launch_grid(const Handle* h, K kernel, size_t smem) {
+    int nb = 0;
+    if (smem > 32 * 1024) cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   // static smem rides on top
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, QUAD_WARPS * 32, smem) != cudaSuccess || nb < 1) nb = 1;
+    const int cap = nb * h->nsm;
+    return h->qgrid < cap ? h->qgrid : cap;
+}
+int ensure_quad_buffers(Handle* h);      // api.cu: lazily allocates the buffers above and the quadgk scratch
+inline size_t quad_smem(int maxseg) { return (size_t)QUAD_WARPS * (QUAD_SKEYS + (maxseg >> 5)) * sizeof(double); }
+inline size_t quad_seg_doubles(int P, int maxseg, int qgrid) { return (size_t)qgrid * QUAD_WARPS * maxseg * (size_t)(((P + 4 + 3) / 4) * 4); }
 
 }  // namespace b200adj

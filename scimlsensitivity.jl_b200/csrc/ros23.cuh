@@ -18,6 +18,7 @@
 #include <stdint.h>
 #include "families.cuh"
 #include "ode_tsit5.cuh"
+#include "quadgk.cuh"
 
 namespace b200adj {
 
@@ -30,9 +31,13 @@ struct RosArgs {
     double* du0; double* dp_members; double* partials; double* dp; unsigned int* ticket;
     // forward dense solution (handle-owned)
     double* ft; double* fu; double* fk; int32_t* fn;              // [MAXS+1][N], [MAXS+1][D][N], [MAXS][2][D][N], [N]
-    // reverse dense solution (QuadratureAdjoint)
-    double* rt0; double* rh; double* rz; double* rk; int32_t* rn; // [MAXS][N], [MAXS][N], [MAXS][D][N], [MAXS][2][D][N], [N]
-    double* qseg; double* qkey; int32_t* qidx; int32_t maxseg;   // quadgk segment store [maxseg][2+P][N], heap [maxseg][N]
+    // reverse dense solution (QuadratureAdjoint), MEMBER-MAJOR: only the warp-per-member quadrature kernel reads it.
+    // rrec[N][MAXS][RWP] = (t_start, h, z[D], k1[D], k2[D]) per accepted step, rend[N][MAXS] = t_start + h (the search keys)
+    double* rrec; double* rend; int32_t* rn;
+    // member-major copy of the forward dense solution for the same kernel (quad_transpose_fwd_kernel):
+    // ftT[N][MAXS+1] knots, frecT[N][MAXS][FWP] = (u[D], k1[D], k2[D])
+    double* ftT; double* frecT;
+    double* qseg; double* qkey; int32_t maxseg;                  // quadgk scratch per resident warp: segments [maxseg][SEGW], keys [maxseg] (quadgk.cuh)
     int64_t N; int32_t K; int32_t maxs;
     double t0, t1, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
     uint32_t flags;                                               // bit0 no_start
@@ -94,11 +99,22 @@ __device__ __forceinline__ double tstop_snap(double tnext, double tstop) {
 template <int D>
 struct FwdDense {
     const double* ft; const double* fu; const double* fk; int64_t N, i; int n;
+    // The adjoint solve walks the forward solution monotonically, so the interval index is kept as a CURSOR and moved by
+    // linear steps (same result as a bisection over the knots, but 1-2 loads -- the two knots the interpolation needs
+    // anyway -- instead of log2(n) dependent ones).
+    mutable int cur = 0;
     __device__ __forceinline__ double T(int idx) const { return ft[(int64_t)idx * N + i]; }
     __device__ __forceinline__ void eval(double t, bool right, double* y, double* yd) const {
-        int lo = 0, hi = n, iv;
-        if (right) { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) <= t) lo = mid; else hi = mid; } iv = lo; if (iv > n - 1) iv = n - 1; }
-        else { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) >= t) hi = mid; else lo = mid; } iv = hi - 1; if (iv < 0) iv = 0; }
+        int iv = cur < n - 1 ? cur : n - 1;
+        if (iv < 0) iv = 0;
+        if (right) {        // largest idx with T(idx) <= t, clamped to [0, n-1]   (sol(t), continuity = :right)
+            while (iv > 0 && T(iv) > t) iv--;
+            while (iv < n - 1 && T(iv + 1) <= t) iv++;
+        } else {            // (smallest idx with T(idx) >= t) - 1, clamped           (continuity = :left)
+            while (iv > 0 && T(iv) >= t) iv--;
+            while (iv < n - 1 && T(iv + 1) < t) iv++;
+        }
+        cur = iv;
         const double ta = T(iv), h = T(iv + 1) - ta;
         const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
         const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
@@ -277,6 +293,7 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
 #pragma unroll
     for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; acc[q] = 0.0; }
     FwdDense<D> sol{a.ft, a.fu, a.fk, N, i, a.fn[i]};
+    sol.cur = sol.n - 1;                  // the reverse solve starts at T
     double z[D], zn[D], f0[D], k1[D], k2[D], k3[D], f1[D], fnr[D], tmp[D], W[D][D], dT[D];
     int piv[D];
 #pragma unroll
@@ -377,13 +394,11 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
             };
             integrate_gk_step<P, 1>(node, t, tn, acc);
         } else if (active) {
-            a.rt0[(int64_t)nrev * N + i] = t; a.rh[(int64_t)nrev * N + i] = hs;
+            double* rec = a.rrec + ((int64_t)i * a.maxs + nrev) * quad_pad(3 + 3 * D);
+            rec[0] = t; rec[1] = hs; rec[2 + 3 * D] = 1.0 / hs;
+            a.rend[(int64_t)i * a.maxs + nrev] = t + hs;
 #pragma unroll
-            for (int j = 0; j < D; j++) {
-                a.rz[((int64_t)nrev * D + j) * N + i] = z[j];
-                a.rk[(((int64_t)nrev * 2 + 0) * D + j) * N + i] = k1[j];
-                a.rk[(((int64_t)nrev * 2 + 1) * D + j) * N + i] = k2[j];
-            }
+            for (int j = 0; j < D; j++) { rec[2 + j] = z[j]; rec[2 + D + j] = k1[j]; rec[2 + 2 * D + j] = k2[j]; }
         }
         nrev++;
 #pragma unroll
@@ -412,201 +427,77 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
     }
 }
 
-// ---- QuadGK (7,15) ----
-__device__ const double XGK[8] = {0.991455371120812639206854697526329, 0.949107912342758524526189684047851,
-    0.864864423359769072789712788640926, 0.741531185599394439863864773280788, 0.586087235467691130294144838258730,
-    0.405845151377397166906606412076961, 0.207784955007898467600689403773245, 0.0};
-__device__ const double WGK[8] = {0.022935322010529224963732008058970, 0.063092092629978553290700663189204,
-    0.104790010322250183839876322541518, 0.140653259715525918745189590510238, 0.169004726639267902826583426598550,
-    0.190350578064785409913256402421014, 0.204432940075298892414161999234649, 0.209482141084727828012999174891714};
-__device__ const double WG[4] = {0.129484966168869693270611432679082, 0.279705391489276667901467771423780,
-    0.381830050505118944950369775488975, 0.417959183673469387755102040816327};
-
+// QuadratureAdjoint integrand on the two dense solutions (AdjointSensitivityIntegrand, src/quadrature_adjoint.jl:486-502):
+// out = (df/dp)(y(t))' lam(t), y left-continuous from the forward dense solution, lam from the dense reverse solution.
+// The lookups are warp-cooperative inside the segment's index brackets (quadgk.cuh).
 template <class Fam, int D, int P>
-struct QuadCtx {
-    FwdDense<D> sol; const double* rt0; const double* rh; const double* rz; const double* rk; int nrev; int64_t N, i; const double* p;
-    // AdjointSensitivityIntegrand: out = (df/dp)(y(t))' lam(t), y left-continuous, lam from the dense reverse solution
-    __device__ __forceinline__ void operator()(double t, double* out) const {
+struct RosQuadCtx {
+    static constexpr int FWP = quad_pad(3 * D + 3), RWP = quad_pad(3 + 3 * D);
+    const double* ftT; const double* frecT; const double* rrec; const double* rend;      // this member's rows
+    int nf, nrev; double p[P];
+    __device__ __forceinline__ bool valid() const { return nrev >= 0; }
+    __device__ __forceinline__ bool empty() const { return nrev == 0; }
+    __device__ __forceinline__ QuadBracket root() const { return QuadBracket{0, nf - 1, 0, nrev - 1}; }
+    __device__ __forceinline__ void eval(double t, const QuadBracket& br, int lane, double* out, int* fiv, int* riv) const {
         double y[D], lam[D];
-        sol.eval(t, false, y, nullptr);
-        int lo = 0, hi = nrev - 1;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (rt0[(int64_t)mid * N + i] + rh[(int64_t)mid * N + i] <= t) hi = mid; else lo = mid + 1; }
-        const double ts = rt0[(int64_t)lo * N + i], h = rh[(int64_t)lo * N + i], th = (t - ts) / h;
-        const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
+        constexpr double IC = 1.0 / (1 - 2 * ROS_D);
+        // forward: iv = #{interior knots < t} (sol(y, t, continuity = :left))
+        const int iv = br.flo + coop_count<true>([&](int j) { return __ldg(ftT + j); }, br.flo + 1, br.fhi - br.flo, t, lane);
+        // reverse: the step whose end is the first <= t; ends descend with the step index
+        const int lo = br.rlo + coop_count<false>([&](int j) { return __ldg(rend + j); }, br.rlo, br.rhi - br.rlo, t, lane);
+        *fiv = iv; *riv = lo;
+        {
+            const double* r = frecT + iv * FWP;                  // (u[D], k1[D], k2[D], t_a, h, 1/h)
+            const double ta = __ldg(r + 3 * D), h = __ldg(r + 3 * D + 1), ih = __ldg(r + 3 * D + 2);
+            const double th = (h == 0.0) ? 1.0 : (t - ta) * ih;
+            const double c1 = th * (1 - th) * IC, c2 = th * (th - 2 * ROS_D) * IC;
 #pragma unroll
-        for (int j = 0; j < D; j++)
-            lam[j] = rz[((int64_t)lo * D + j) * N + i] + h * (c1 * rk[(((int64_t)lo * 2 + 0) * D + j) * N + i] + c2 * rk[(((int64_t)lo * 2 + 1) * D + j) * N + i]);
+            for (int j = 0; j < D; j++) y[j] = __ldg(r + j) + h * (c1 * __ldg(r + D + j) + c2 * __ldg(r + 2 * D + j));
+        }
+        {
+            const double* r = rrec + lo * RWP;                   // (t_start, h, z[D], k1[D], k2[D], 1/h)
+            const double ts = __ldg(r), h = __ldg(r + 1), th = (t - ts) * __ldg(r + 2 + 3 * D);
+            const double c1 = th * (1 - th) * IC, c2 = th * (th - 2 * ROS_D) * IC;
+#pragma unroll
+            for (int j = 0; j < D; j++) lam[j] = __ldg(r + 2 + j) + h * (c1 * __ldg(r + 2 + D + j) + c2 * __ldg(r + 2 + 2 * D + j));
+        }
         Fam::vjp_p(y, p, lam, out);
     }
 };
 
-// ---- warp-cooperative Gauss-Kronrod: one WARP per member ----
-// A bisection evaluates the (7,15) rule on both halves = 30 integrand evaluations: lanes 0..14 take the 15 Kronrod nodes
-// of the left half, lanes 16..30 those of the right half (lanes 15, 31 idle), each with its own dense-solution lookup;
-// the weighted sums are reduced with shuffles inside each 16-lane half.  Node order inside a half: lane l -> abscissa
-// sign(l-7) * XGK[min(l,14-l)] (ascending in t).
-template <int P, class F>
-__device__ __forceinline__ void gk15_pair(const F& f, double a0, double b0, double a1, double b1, int lane,
-                                          double* I0, double* e0, double* I1, double* e1) {
-    const int half = lane >> 4, l = lane & 15;
-    const double a = half ? a1 : a0, b = half ? b1 : b0;
-    const double c = 0.5 * (a + b), hl = 0.5 * (b - a);
-    double vk[P], vg[P];
-#pragma unroll
-    for (int q = 0; q < P; q++) { vk[q] = 0; vg[q] = 0; }
-    if (l < 15) {
-        const int j = l < 7 ? l : 14 - l;                      // 0..7 (7 = centre)
-        const double x = (l < 7 ? -XGK[j] : XGK[j]);
-        double w[P];
-        f(c + hl * x, w);
-        const double wk = WGK[j], wg = (j == 7) ? WG[3] : ((j & 1) ? WG[j >> 1] : 0.0);
-#pragma unroll
-        for (int q = 0; q < P; q++) { vk[q] = wk * w[q]; vg[q] = wg * w[q]; }
-    }
-#pragma unroll
-    for (int q = 0; q < P; q++) {
-#pragma unroll
-        for (int off = 8; off > 0; off >>= 1) { vk[q] += __shfl_xor_sync(0xffffffffu, vk[q], off); vg[q] += __shfl_xor_sync(0xffffffffu, vg[q], off); }
-    }
-    double e2 = 0;
-#pragma unroll
-    for (int q = 0; q < P; q++) { vk[q] *= hl; vg[q] *= hl; e2 += (vk[q] - vg[q]) * (vk[q] - vg[q]); }
-    const double e = sqrt(e2);
-    // broadcast both halves' results to every lane
-#pragma unroll
-    for (int q = 0; q < P; q++) { I0[q] = __shfl_sync(0xffffffffu, vk[q], 0); I1[q] = __shfl_sync(0xffffffffu, vk[q], 16); }
-    *e0 = __shfl_sync(0xffffffffu, e, 0); *e1 = __shfl_sync(0xffffffffu, e, 16);
-}
-
-// Segment store of one member's adaptive quadrature, in a handle-owned global scratch (member-minor):
-//   seg [maxseg][2+P][N] = (a, b, I[P]) per segment id, key [maxseg][N] / idx [maxseg][N] = binary max-heap on the error.
-// QuadGK bisects the largest-error segment; a heap gives the same argmax as the oracle's linear scan (no ties in
-// practice) at O(log n) per bisection -- the dense reverse solution is only C1 at step boundaries, so a 1e-10 tolerance
-// drives thousands of segments per data interval.  All lanes of the warp run the heap logic on identical values
-// (uniform loads); lane 0 does the stores.
-struct QuadScratch { double* seg; double* key; int32_t* idx; int maxseg; int64_t N, i; };
-
-// adaptive quadgk over [a,b] by one warp: bisect the largest-error segment until E <= max(atol, rtol*|I|) (2-norm);
-// running totals updated incrementally and returned (QuadGK.jl).  false = out of segment capacity.
-template <int P, class F>
-__device__ bool quadgk_warp(const F& f, double a, double b, double atol, double rtol, double* out, const QuadScratch& q, int lane) {
-    const int64_t N = q.N, i = q.i;
-    auto SEG = [&](int k, int c) -> double* { return &q.seg[((int64_t)k * (2 + P) + c) * N + i]; };
-    auto KEY = [&](int k) -> double* { return &q.key[(int64_t)k * N + i]; };
-    auto IDX = [&](int k) -> int32_t* { return &q.idx[(int64_t)k * N + i]; };
-    const bool wr = lane == 0;
-    double I[P], Idummy[P], Itot[P], e, edummy, Etot;
-    gk15_pair<P>(f, a, b, a, b, lane, I, &e, Idummy, &edummy);
-    if (wr) { *SEG(0, 0) = a; *SEG(0, 1) = b; *KEY(0) = e; *IDX(0) = 0; }
-#pragma unroll
-    for (int c = 0; c < P; c++) { if (wr) *SEG(0, 2 + c) = I[c]; Itot[c] = I[c]; }
-    Etot = e;
-    int nseg = 1;
-    bool ok = true;
-    __syncwarp();
-    for (;;) {
-        double nI = 0;
-#pragma unroll
-        for (int c = 0; c < P; c++) nI += Itot[c] * Itot[c];
-        nI = sqrt(nI);
-        if (Etot <= fmax(atol, rtol * nI)) break;
-        if (nseg + 1 > q.maxseg) { ok = false; break; }
-        const int w = *IDX(0);
-        const double aw = *SEG(w, 0), bw = *SEG(w, 1), ew = *KEY(0);
-        const double mid = 0.5 * (aw + bw);
-        if (!(mid > fmin(aw, bw) && mid < fmax(aw, bw))) break;
-        double Il[P], Ir[P], el, er;
-        gk15_pair<P>(f, aw, mid, mid, bw, lane, Il, &el, Ir, &er);
-        Etot += (el + er) - ew;
-#pragma unroll
-        for (int c = 0; c < P; c++) {
-            Itot[c] += (Il[c] + Ir[c]) - *SEG(w, 2 + c);
-        }
-        __syncwarp();
-        if (wr) {
-#pragma unroll
-            for (int c = 0; c < P; c++) { *SEG(w, 2 + c) = Il[c]; *SEG(nseg, 2 + c) = Ir[c]; }
-            *SEG(w, 1) = mid; *SEG(nseg, 0) = mid; *SEG(nseg, 1) = bw;
-            // root <- left half, sift down
-            int hpos = 0; double hk = el; int hid = w;
-            for (;;) {
-                int l = 2 * hpos + 1, r = l + 1, m = hpos; double mk = hk;
-                if (l < nseg) { const double kl = *KEY(l); if (kl > mk) { m = l; mk = kl; } }
-                if (r < nseg) { const double kr = *KEY(r); if (kr > mk) { m = r; mk = kr; } }
-                if (m == hpos) break;
-                *KEY(hpos) = *KEY(m); *IDX(hpos) = *IDX(m); hpos = m;
-            }
-            *KEY(hpos) = hk; *IDX(hpos) = hid;
-            // push right half, sift up
-            hpos = nseg; hk = er; hid = nseg;
-            while (hpos > 0) {
-                int par = (hpos - 1) >> 1;
-                if (*KEY(par) >= hk) break;
-                *KEY(hpos) = *KEY(par); *IDX(hpos) = *IDX(par); hpos = par;
-            }
-            *KEY(hpos) = hk; *IDX(hpos) = hid;
-        }
-        __syncwarp();
-        nseg++;
-    }
-#pragma unroll
-    for (int c = 0; c < P; c++) out[c] = Itot[c];
-    return ok;
-}
-
-// one warp per member; block = 4 warps
+// persistent grid of 4-warp blocks, one warp per member at a time (quadgk.cuh::quad_member_loop)
 template <class Fam, bool SHARED_P>
-__global__ void __launch_bounds__(128) ros23_quadrature_kernel(RosArgs a) {
+__global__ void __launch_bounds__(QUAD_WARPS * 32) ros23_quadrature_kernel(RosArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
+    extern __shared__ double s_quad_l1[];
     const int lane = threadIdx.x & 31;
-    const int64_t gi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);   // member index of this warp
-    const bool active = gi < a.N;
-    const int64_t i = active ? gi : a.N - 1;
     const int64_t N = a.N;
-    double p[P], res[P], part[P];
+    double acc[P];
 #pragma unroll
-    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i]; res[q] = 0.0; }
-    QuadCtx<Fam, D, P> ctx{FwdDense<D>{a.ft, a.fu, a.fk, N, i, a.fn[i]}, a.rt0, a.rh, a.rz, a.rk, a.rn[i], N, i, p};
-    const int K = a.K;
-    const QuadScratch qs{a.qseg, a.qkey, a.qidx, a.maxseg, N, i};
-    bool ok = true;
-    // warps past N shadow member N-1 for the block reduction only: they must NOT run the quadrature (they would share
-    // member N-1's segment scratch with its real warp)
-    if (!active) {
-    } else if (ctx.nrev < 0) {
+    for (int q = 0; q < P; q++) acc[q] = 0.0;
+    auto make = [&](int64_t i) {
+        RosQuadCtx<Fam, D, P> c{a.ftT + (int64_t)i * (a.maxs + 1), a.frecT + (int64_t)i * a.maxs * quad_pad(3 * D + 3),
+                                a.rrec + (int64_t)i * a.maxs * quad_pad(3 + 3 * D), a.rend + (int64_t)i * a.maxs, a.fn[i], a.rn[i], {}};
 #pragma unroll
-        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
-    } else if (ctx.nrev > 0) {
-        if (K == 0) { ok = quadgk_warp<P>(ctx, a.t0, a.t1, a.quad_abstol, a.quad_reltol, res, qs, lane); }
-        else {
-            if (a.saveat[K - 1] != a.t1) { ok = quadgk_warp<P>(ctx, a.saveat[K - 1], a.t1, a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
+        for (int q = 0; q < P; q++) c.p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+        return c;
+    };
+    auto sink = [&](int64_t i, const double* res) {
+        if (SHARED_P) {
 #pragma unroll
-                for (int q = 0; q < P; q++) res[q] += part[q]; }
-            for (int k = K - 2; k >= 0; k--) {
-                if (a.saveat[k] == a.saveat[k + 1]) continue;
-                ok = quadgk_warp<P>(ctx, a.saveat[k], a.saveat[k + 1], a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
+            for (int q = 0; q < P; q++) acc[q] += res[q];
+        } else if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < P; q++) res[q] += part[q];
-            }
-            if (a.saveat[0] != a.t0) { ok = quadgk_warp<P>(ctx, a.t0, a.saveat[0], a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
-#pragma unroll
-                for (int q = 0; q < P; q++) res[q] += part[q]; }
+            for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = res[q];
         }
-    }
-    if (!ok) {           // out of segment capacity: fail loudly
-#pragma unroll
-        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
-    }
-    // lane 0 of every warp holds the member's result: per-member store, or a block/grid reduction over the lane-0 values
+    };
+    quad_member_loop<P>(N, a.K, a.saveat, a.t0, a.t1, a.quad_abstol, a.quad_reltol, a.qseg, a.qkey, a.maxseg, s_quad_l1, make, sink);
     if (SHARED_P) {
-        if (!active || lane != 0) {
+        if (lane != 0) {
 #pragma unroll
-            for (int q = 0; q < P; q++) res[q] = 0.0;
+            for (int q = 0; q < P; q++) acc[q] = 0.0;
         }
-        reduce_dp<P>(res, a.partials, a.dp, a.ticket);
-    } else if (active && lane == 0) {
-#pragma unroll
-        for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = res[q];
+        reduce_dp<P>(acc, a.partials, a.dp, a.ticket);
     }
 }
 

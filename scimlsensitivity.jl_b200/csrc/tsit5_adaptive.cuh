@@ -21,8 +21,9 @@ struct T5aArgs {
     double* saved; int32_t* status;
     double* du0; double* dp_members; double* partials; double* dp; unsigned int* ticket;
     double* ft; double* fu; double* fk; int32_t* fn;              // forward dense: [MAXS+1][N], [MAXS+1][D][N], [MAXS][7][D][N], [N]
-    double* rt0; double* rh; double* rz; double* rk; int32_t* rn; // reverse dense (Quadrature): [MAXS][N] x2, [MAXS][D][N], [MAXS][7][D][N], [N]
-    double* qseg; double* qkey; int32_t* qidx; int32_t maxseg;
+    double* rrec; double* rend; int32_t* rn;                      // reverse dense (Quadrature), member-major: [N][MAXS][RWP] = (t, h, z[D], k[7][D]), [N][MAXS] = t + h
+    double* ftT; double* frecT;                                   // member-major copy of the forward dense solution: [N][MAXS+1], [N][MAXS][FWP] = (u[D], k[7][D])
+    double* qseg; double* qkey; int32_t maxseg;
     int64_t N; int32_t K; int32_t maxs;
     double t0, t1, dt0, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
     uint32_t flags;
@@ -58,11 +59,15 @@ __device__ __forceinline__ void t5_event_params(const T5aArgs& a, int upto, cons
 template <int D>
 struct T5Dense {
     const T5aArgs& a; int64_t i; int n;
+    mutable int cur = 0;
     __device__ __forceinline__ double T(int idx) const { return a.ft[(int64_t)idx * a.N + i]; }
     __device__ __forceinline__ void eval(double t, bool right, double* y) const {
-        int lo = 0, hi = n, iv;
-        if (right) { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) <= t) lo = mid; else hi = mid; } iv = lo; if (iv > n - 1) iv = n - 1; }
-        else { while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (T(mid) >= t) hi = mid; else lo = mid; } iv = hi - 1; if (iv < 0) iv = 0; }
+        // cursor instead of a bisection over the knots: the adjoint solve visits the forward solution monotonically
+        int iv = cur < n - 1 ? cur : n - 1;
+        if (iv < 0) iv = 0;
+        if (right) { while (iv > 0 && T(iv) > t) iv--; while (iv < n - 1 && T(iv + 1) <= t) iv++; }
+        else { while (iv > 0 && T(iv) >= t) iv--; while (iv < n - 1 && T(iv + 1) < t) iv++; }
+        cur = iv;
         const double ta = T(iv), h = T(iv + 1) - ta;
         const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
         double w[7];
@@ -224,6 +229,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         t5_event_params<P>(a, a.nev, p0, p);
     }
     T5Dense<D> sol{a, i, a.fn[i]};
+    sol.cur = sol.n - 1;
     double z[L], zn[L], k[7][L];
 #pragma unroll
     for (int c = 0; c < L; c++) z[c] = 0.0;
@@ -390,13 +396,15 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
             };
             integrate_gk_step<P, 3>(node, t, tn, acc);
         } else if (SA == SA_QUAD && active) {
-            a.rt0[(int64_t)nrev * N + i] = t; a.rh[(int64_t)nrev * N + i] = hs;
+            double* rec = a.rrec + ((int64_t)i * a.maxs + nrev) * quad_pad(3 + 8 * D);
+            rec[0] = t; rec[1] = hs; rec[2 + 8 * D] = 1.0 / hs;
+            a.rend[(int64_t)i * a.maxs + nrev] = t + hs;
 #pragma unroll
-            for (int j = 0; j < D; j++) a.rz[((int64_t)nrev * D + j) * N + i] = z[j];
+            for (int j = 0; j < D; j++) rec[2 + j] = z[j];
 #pragma unroll
             for (int s = 0; s < 7; s++)
 #pragma unroll
-                for (int j = 0; j < D; j++) a.rk[(((int64_t)nrev * 7 + s) * D + j) * N + i] = k[s][j];
+                for (int j = 0; j < D; j++) rec[2 + (1 + s) * D + j] = k[s][j];
         }
         nrev++;
 #pragma unroll
@@ -430,68 +438,80 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     }
 }
 
-// QuadratureAdjoint integrand on the two dense solutions
+// QuadratureAdjoint integrand on the two dense solutions (warp-cooperative lookups inside the segment's brackets, quadgk.cuh)
 template <class Fam, int D, int P>
 struct T5aQuadCtx {
-    const T5aArgs& a; T5Dense<D> sol; int nrev; int64_t i; const double* p;
-    __device__ __forceinline__ void operator()(double t, double* out) const {
+    static constexpr int FWP = quad_pad(8 * D + 3), RWP = quad_pad(3 + 8 * D);
+    const T5aArgs& a; const double* ftT; const double* frecT; const double* rrec; const double* rend;      // this member's rows
+    int nf, nrev; double p[P];
+    __device__ __forceinline__ bool valid() const { return nrev >= 0; }
+    __device__ __forceinline__ bool empty() const { return nrev == 0; }
+    __device__ __forceinline__ QuadBracket root() const { return QuadBracket{0, nf - 1, 0, nrev - 1}; }
+    __device__ __forceinline__ void eval(double t, const QuadBracket& br, int lane, double* out, int* fiv, int* riv) const {
         double y[D], lam[D], w[7];
-        sol.eval(t, false, y);
-        int lo = 0, hi = nrev - 1;
-        while (lo < hi) { int mid = (lo + hi) >> 1; if (a.rt0[(int64_t)mid * a.N + i] + a.rh[(int64_t)mid * a.N + i] <= t) hi = mid; else lo = mid + 1; }
-        const double ts = a.rt0[(int64_t)lo * a.N + i], h = a.rh[(int64_t)lo * a.N + i];
-        t5_weights(a, (t - ts) / h, w);
+        const int iv = br.flo + coop_count<true>([&](int j) { return __ldg(ftT + j); }, br.flo + 1, br.fhi - br.flo, t, lane);
+        const int lo = br.rlo + coop_count<false>([&](int j) { return __ldg(rend + j); }, br.rlo, br.rhi - br.rlo, t, lane);
+        *fiv = iv; *riv = lo;
+        {
+            const double* r = frecT + iv * FWP;                  // (u[D], k[7][D], t_a, h, 1/h)
+            const double ta = __ldg(r + 8 * D), h = __ldg(r + 8 * D + 1);
+            t5_weights(a, (h == 0.0) ? 1.0 : (t - ta) * __ldg(r + 8 * D + 2), w);
 #pragma unroll
-        for (int j = 0; j < D; j++) {
-            double s_ = 0.0;
+            for (int j = 0; j < D; j++) {
+                double acc = 0.0;
 #pragma unroll
-            for (int s = 0; s < 7; s++) s_ += w[s] * a.rk[(((int64_t)lo * 7 + s) * D + j) * a.N + i];
-            lam[j] = a.rz[((int64_t)lo * D + j) * a.N + i] + h * s_;
+                for (int s = 0; s < 7; s++) acc += w[s] * __ldg(r + (1 + s) * D + j);
+                y[j] = __ldg(r + j) + h * acc;
+            }
+        }
+        {
+            const double* r = rrec + lo * RWP;                   // (t_start, h, z[D], k[7][D], 1/h)
+            const double ts = __ldg(r), h = __ldg(r + 1);
+            t5_weights(a, (t - ts) * __ldg(r + 2 + 8 * D), w);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                double s_ = 0.0;
+#pragma unroll
+                for (int s = 0; s < 7; s++) s_ += w[s] * __ldg(r + 2 + (1 + s) * D + j);
+                lam[j] = __ldg(r + 2 + j) + h * s_;
+            }
         }
         Fam::vjp_p(y, p, lam, out);
     }
 };
 
 template <class Fam, bool SHARED_P>
-__global__ void __launch_bounds__(128) t5a_quadrature_kernel(const __grid_constant__ T5aArgs a) {
+__global__ void __launch_bounds__(QUAD_WARPS * 32) t5a_quadrature_kernel(const __grid_constant__ T5aArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
+    extern __shared__ double s_quad_l1[];
     const int lane = threadIdx.x & 31;
-    const int64_t gi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const bool active = gi < a.N;
-    const int64_t i = active ? gi : a.N - 1;
-    double p[P], res[P], part[P];
+    const int64_t N = a.N;
+    double acc[P];
 #pragma unroll
-    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * a.N + i]; res[q] = 0.0; }
-    T5aQuadCtx<Fam, D, P> ctx{a, T5Dense<D>{a, i, a.fn[i]}, a.rn[i], i, p};
-    const QuadScratch qs{a.qseg, a.qkey, a.qidx, a.maxseg, a.N, i};
-    const int K = a.K;
-    bool ok = ctx.nrev >= 0;
-    auto add = [&](double lo, double hi) {
-        ok = quadgk_warp<P>(ctx, lo, hi, a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
+    for (int q = 0; q < P; q++) acc[q] = 0.0;
+    auto make = [&](int64_t i) {
+        T5aQuadCtx<Fam, D, P> c{a, a.ftT + (int64_t)i * (a.maxs + 1), a.frecT + (int64_t)i * a.maxs * quad_pad(8 * D + 3),
+                                a.rrec + (int64_t)i * a.maxs * quad_pad(3 + 8 * D), a.rend + (int64_t)i * a.maxs, a.fn[i], a.rn[i], {}};
 #pragma unroll
-        for (int q = 0; q < P; q++) res[q] += part[q];
+        for (int q = 0; q < P; q++) c.p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+        return c;
     };
-    if (active && ctx.nrev > 0) {       // warps past N only take part in the block reduction
-        if (K == 0) add(a.t0, a.t1);
-        else {
-            if (a.saveat[K - 1] != a.t1) add(a.saveat[K - 1], a.t1);
-            for (int k = K - 2; k >= 0; k--) if (a.saveat[k] != a.saveat[k + 1]) add(a.saveat[k], a.saveat[k + 1]);
-            if (a.saveat[0] != a.t0) add(a.t0, a.saveat[0]);
-        }
-    }
-    if (!ok) {
+    auto sink = [&](int64_t i, const double* res) {
+        if (SHARED_P) {
 #pragma unroll
-        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
-    }
+            for (int q = 0; q < P; q++) acc[q] += res[q];
+        } else if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = res[q];
+        }
+    };
+    quad_member_loop<P>(N, a.K, a.saveat, a.t0, a.t1, a.quad_abstol, a.quad_reltol, a.qseg, a.qkey, a.maxseg, s_quad_l1, make, sink);
     if (SHARED_P) {
-        if (!active || lane != 0) {
+        if (lane != 0) {
 #pragma unroll
-            for (int q = 0; q < P; q++) res[q] = 0.0;
+            for (int q = 0; q < P; q++) acc[q] = 0.0;
         }
-        reduce_dp<P>(res, a.partials, a.dp, a.ticket);
-    } else if (active && lane == 0) {
-#pragma unroll
-        for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * a.N + i] = res[q];
+        reduce_dp<P>(acc, a.partials, a.dp, a.ticket);
     }
 }
 

@@ -13,7 +13,7 @@ namespace b200adj {
 struct Tsit5QuadArgs {
     const double* ckpt; const double* adj_dense; const double* p; const double* saveat;
     double* dp_members; double* partials; double* dp; unsigned int* ticket;
-    double* qseg; double* qkey; int32_t* qidx; int32_t maxseg;
+    double* qseg; double* qkey; int32_t maxseg;
     int64_t N, Npad; int32_t S, K;
     double t0, t1, h, quad_abstol, quad_reltol;
     double R[7][4];          // dense-output polynomials b_j(theta) = sum_m R[j][m] theta^(m+1)
@@ -22,12 +22,16 @@ struct Tsit5QuadArgs {
 
 template <class Fam, int D, int P>
 struct Tsit5QuadCtx {
-    const Tsit5QuadArgs& a; int64_t i; const double* p;
+    const Tsit5QuadArgs& a; int64_t i; double p[P];
     __device__ __forceinline__ void weights(double th, double* w) const {
 #pragma unroll
         for (int j = 0; j < 7; j++) w[j] = a.h * (th * (a.R[j][0] + th * (a.R[j][1] + th * (a.R[j][2] + th * a.R[j][3]))));
     }
-    __device__ __forceinline__ void operator()(double t, double* out) const {
+    __device__ __forceinline__ bool valid() const { return true; }
+    __device__ __forceinline__ bool empty() const { return false; }
+    __device__ __forceinline__ QuadBracket root() const { return QuadBracket{0, 0, 0, 0}; }      // uniform grid: no search, no brackets
+    __device__ __forceinline__ void eval(double t, const QuadBracket&, int, double* out, int* fiv, int* riv) const {
+        *fiv = 0; *riv = 0;
         const int64_t cs = (int64_t)D * a.Npad;
         int n = (int)floor((t - a.t0) / a.h);
         if (n < 0) n = 0;
@@ -61,45 +65,36 @@ struct Tsit5QuadCtx {
 };
 
 template <class Fam, bool SHARED_P>
-__global__ void __launch_bounds__(128) tsit5_quadrature_kernel(const __grid_constant__ Tsit5QuadArgs a) {
+__global__ void __launch_bounds__(QUAD_WARPS * 32) tsit5_quadrature_kernel(const __grid_constant__ Tsit5QuadArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
+    extern __shared__ double s_quad_l1[];
     const int lane = threadIdx.x & 31;
-    const int64_t gi = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const bool active = gi < a.N;
-    const int64_t i = active ? gi : a.N - 1;
-    double p[P], res[P], part[P];
+    const int64_t N = a.N;
+    double acc[P];
 #pragma unroll
-    for (int q = 0; q < P; q++) { p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * a.N + i]; res[q] = 0.0; }
-    Tsit5QuadCtx<Fam, D, P> ctx{a, i, p};
-    const QuadScratch qs{a.qseg, a.qkey, a.qidx, a.maxseg, a.N, i};
-    const int K = a.K;
-    bool ok = true;
-    auto add = [&](double lo, double hi) {
-        ok = quadgk_warp<P>(ctx, lo, hi, a.quad_abstol, a.quad_reltol, part, qs, lane) && ok;
+    for (int q = 0; q < P; q++) acc[q] = 0.0;
+    auto make = [&](int64_t i) {
+        Tsit5QuadCtx<Fam, D, P> c{a, i, {}};
 #pragma unroll
-        for (int q = 0; q < P; q++) res[q] += part[q];
+        for (int q = 0; q < P; q++) c.p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+        return c;
     };
-    // warps past N only take part in the block reduction (they would share member N-1's segment scratch otherwise)
-    if (!active) {
-    } else if (K == 0) add(a.t0, a.t1);
-    else {
-        if (a.saveat[K - 1] != a.t1) add(a.saveat[K - 1], a.t1);
-        for (int k = K - 2; k >= 0; k--) if (a.saveat[k] != a.saveat[k + 1]) add(a.saveat[k], a.saveat[k + 1]);
-        if (a.saveat[0] != a.t0) add(a.t0, a.saveat[0]);
-    }
-    if (!ok) {
+    auto sink = [&](int64_t i, const double* res) {
+        if (SHARED_P) {
 #pragma unroll
-        for (int q = 0; q < P; q++) res[q] = __longlong_as_double(0x7ff8000000000000LL);
-    }
-    if (SHARED_P) {
-        if (!active || lane != 0) {
+            for (int q = 0; q < P; q++) acc[q] += res[q];
+        } else if (lane == 0) {
 #pragma unroll
-            for (int q = 0; q < P; q++) res[q] = 0.0;
+            for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = res[q];
         }
-        reduce_dp<P>(res, a.partials, a.dp, a.ticket);
-    } else if (active && lane == 0) {
+    };
+    quad_member_loop<P>(N, a.K, a.saveat, a.t0, a.t1, a.quad_abstol, a.quad_reltol, a.qseg, a.qkey, a.maxseg, s_quad_l1, make, sink);
+    if (SHARED_P) {
+        if (lane != 0) {
 #pragma unroll
-        for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * a.N + i] = res[q];
+            for (int q = 0; q < P; q++) acc[q] = 0.0;
+        }
+        reduce_dp<P>(acc, a.partials, a.dp, a.ticket);
     }
 }
 

@@ -54,7 +54,11 @@ def test_c3_robertson_full_size():
                      t, u0[:, idx], k[:, idx])
     assert _rel(du0[:, idx], ref["du0"]) < 1e-7
     err = np.abs(dp[:, idx] - ref["dp"]) / (np.abs(ref["dp"]).max(axis=1, keepdims=True))
-    assert np.median(err) < 1e-7 and err.max() < 5e-5        # adaptive-quadrature path dependence
+    # BASELINE bound for C3: 1e-5.  Observed 3e-9 median / 3e-8 worst row: the device bisects the same segments in the same
+    # order as the oracle (arg-max ties resolve to the lowest segment index on both sides)
+    assert np.median(err) < 1e-7 and err.max() < 1e-6
+    nrm = np.linalg.norm(dp[:, idx] - ref["dp"], axis=0) / np.linalg.norm(ref["dp"], axis=0)      # the norm quadgk controls
+    assert nrm.max() < 1e-6
     eng.close()
 
 
