@@ -139,6 +139,34 @@ def test_lv_all_sensealgs_agree_and_match_differentiation_through_solver():
     assert abs(res["interpolating"]["dp"][0] - 8.3053) < 5e-4
 
 
+def test_lv_reference_held_number_adaptive_tsit5_tol_1e12():
+    """The ONE family of numbers the reference holds for this path (test/Core6/forward_prob_kwargs.jl:28-30, LV u0 = [1, 1],
+    p = [1.5, 1, 3, 1], T = 10, saveat = 0.1, Tsit5 at abstol = reltol = 1e-12, loss = sum(sol), derivative wrt p1):
+        FiniteDiff 8.305557728239275, ForwardDiff 8.305305252400714, Zygote 8.305266428305409   (comments in the file; its
+    asserts are res ~ res2 ~ res3).  The three printed values disagree among themselves at 3.5e-5, so none of them can pin
+    anything tighter than that; what can be pinned tightly is the quantity they all approximate.  An integrator we did not
+    write (SciPy DOP853 on the forward-sensitivity system, rtol = atol = 1e-13) gives 8.30536266229, and every sensealg of the
+    oracle's error-controlled Tsit5 at the reference's tolerances reproduces it to 1e-9; that value lies inside the interval
+    spanned by the reference's own printed numbers."""
+    from scipy.integrate import solve_ivp
+    saveat = np.linspace(0, 10, 101)
+    p = LV_P
+
+    def rhs(t, z):
+        x, y, sx, sy = z
+        return [p[0] * x - p[1] * x * y, -p[2] * y + p[3] * x * y,
+                (p[0] - p[1] * y) * sx - p[1] * x * sy + x, p[3] * y * sx + (-p[2] + p[3] * x) * sy]
+    s = solve_ivp(rhs, (0, 10), [1, 1, 0, 0], method="DOP853", rtol=1e-13, atol=1e-13, t_eval=saveat)
+    truth = s.y[2].sum() + s.y[3].sum()
+    assert abs(truth - 8.30536266229) < 1e-9
+    for sa in SENSEALGS:
+        cfg = O.make_cfg("lv", sa, "tsit5_adaptive", 1, saveat, 0.0, 10.0, abstol=1e-12, reltol=1e-12, cost=("affine", 0.0, 1.0),
+                         quad_abstol=1e-13, quad_reltol=1e-13)
+        g = O.gradient(cfg, saveat, LV_U0, LV_P)["dp"][0]
+        assert abs(g - truth) < 1e-9 * abs(truth), (sa, g)
+        assert 8.305266428305409 - 1e-9 < g < 8.305557728239275 + 1e-9          # inside the reference's own spread
+
+
 def test_lv_adaptive_tsit5_converges_to_same_gradient():
     """C1: adaptive Tsit5 at tol 1e-10 (reference tests use 1e-10..1e-14, test/Core3/adjoint.jl:55-63)."""
     saveat = np.linspace(0, 10, 101)
