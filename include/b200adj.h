@@ -129,8 +129,21 @@ int32_t b200adj_set_tolerances(void* handle, double adj_abstol, double adj_relto
 /* Continuous cost functional (dgdu_continuous / dgdp_continuous of adjoint_sensitivities; accumulate_cost!,
  * src/derivative_wrappers.jl:1411-1442): named family g(u) = a/2 |u|^2 + b sum(u), i.e. dgdu_continuous = a u + b,
  * dgdp_continuous = 0, added to the adjoint RHS of the NEXT reverse pass (on top of the discrete cost, if any).
- * Built for the Tsit5 paths (fixed step: all four sensealgs; adaptive: + GaussKronrod); enabled = 0 switches it off. */
+ * Built for the Tsit5 paths (fixed step: all four sensealgs; adaptive: + GaussKronrod); enabled = 0 switches it off.
+ * Per-component coefficients and dgdp_continuous: b200adj_set_cost_family(which = 1). */
 int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b);
+
+/* Per-component coefficients of the named cost family and its PARAMETER part (dgdp_discrete / dgdp_continuous / g of
+ * adjoint_sensitivities, src/sensitivity_interface.jl:373-526; test/Core7/mixed_costs.jl:19-330 uses g = u1^2 + p1, i.e.
+ * a = [2, 0], e = [1, 0, 0, 0]):
+ *   which = 0, discrete:   l(u, p) = sum_j a_j/2 u_j^2 + b_j u_j + sum_q c_q/2 p_q^2 + e_q p_q  at every save time
+ *                          dgdu_discrete = a .* u + b (needs cost_kind = AFFINE), dgdp_discrete = c .* p + e
+ *   which = 1, continuous: the same expression as running cost g(u, p) (enables it like b200adj_set_continuous_cost)
+ * a, b: [d] or NULL (keep the current, e.g. the scalars of cfg / set_reverse_options); c, e: [P] or NULL (zero).  Host
+ * pointers.  The parameter part is built for P <= 8 and is reset by b200adj_set_reverse_options / b200adj_set_continuous_cost
+ * (call this after them).  Per save time the discrete dgdp joins the gradient exactly where the reference's
+ * ReverseLossCallback adds it (src/adjoint_common.jl:771-783; QuadratureAdjoint: src/quadrature_adjoint.jl:547-553). */
+int32_t b200adj_set_cost_family(void* handle, int32_t which, const double* a, const double* b, const double* c, const double* e);
 
 /* Preset-time events of the hybrid system (DiscreteCallback / PresetTimeCallback of the reference with
  * save_positions = (false, false); reverse-pass treatment of src/callback_tracking.jl:232-480): at each times[e] the state

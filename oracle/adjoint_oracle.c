@@ -70,7 +70,16 @@ typedef struct {
     const double* ev_shift;                 /* [E][d] */
     const double* ev_pscale;                /* [E][P] or NULL: parameter-changing affect p <- pscale .* p + pshift        */
     const double* ev_pshift;                /* (integrator.p .= 2 .* integrator.p .- 0.5, discrete_callbacks.jl:294-303)  */
+    /* per-component coefficients of the named cost family (NULL: the scalars above / zero):
+     *   discrete  l(u, p) = sum_j cost_av_j/2 u_j^2 + cost_bv_j u_j + sum_q dgdp_c_q/2 p_q^2 + dgdp_e_q p_q      at every save time
+     *   running   g(u, p) = sum_j cont_av_j/2 u_j^2 + cont_bv_j u_j + sum_q cdgdp_c_q/2 p_q^2 + cdgdp_e_q p_q
+     * dgdu = a .* u + b, dgdp = c .* p + e  (test/Core7/mixed_costs.jl: g = u1^2 + p1 is a = [2, 0], e = [1, 0, 0, 0]). */
+    const double *cost_av, *cost_bv, *cont_av, *cont_bv, *dgdp_c, *dgdp_e, *cdgdp_c, *cdgdp_e;
 } oracle_cfg;
+#define COST_A(c, j) ((c)->cost_av ? (c)->cost_av[j] : (c)->cost_a)
+#define COST_B(c, j) ((c)->cost_bv ? (c)->cost_bv[j] : (c)->cost_b)
+#define CONT_A(c, j) ((c)->cont_av ? (c)->cont_av[j] : (c)->cont_a)
+#define CONT_B(c, j) ((c)->cont_bv ? (c)->cont_bv[j] : (c)->cont_b)
 /* parameters in force after the first `upto` events */
 static void event_params(const oracle_cfg* c, int P, int upto, const double* p0, double* out) {
     for (int q = 0; q < P; q++) out[q] = p0[q];
@@ -657,7 +666,7 @@ typedef struct {
     int sensealg; int ito;
     double* y; double* dgtmp;
     long nrhs;
-    int cont; double ca, cb;      /* continuous cost: dlam -= dgdu_continuous(y) (src/derivative_wrappers.jl:1411-1442) */
+    int cont; double ca[8], cb[8];   /* continuous cost: dlam -= dgdu_continuous(y) = ca .* y + cb (src/derivative_wrappers.jl:1411-1442) */
     double tev;                   /* event time the reverse solve has just crossed: y(tev) is the LEFT limit from here on */
 } adj_ctx;
 
@@ -670,7 +679,7 @@ static void adj_rhs(double t, const double* z, double* dz, void* c) {
         const double* y = z + d + P;                       /* y read from the state (backsolve_adjoint.jl:78-90) */
         vjp(y, x->p, t, z, dz, dz + d, &F->ctx);
         for (int i = 0; i < d + P; i++) dz[i] = -dz[i];      /* :56-57 */
-        if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca * y[i] + x->cb;
+        if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca[i] * y[i] + x->cb[i];
         (x->ito ? F->f_ito : F->f)(y, x->p, t, dz + d + P, &F->ctx);  /* dy = f(y) */
     } else {
         dense_eval(x->sol, t, t != x->tev, x->y, NULL);    /* sol(y,t,continuity=:right); the left limit at an event just crossed */
@@ -681,7 +690,7 @@ static void adj_rhs(double t, const double* z, double* dz, void* c) {
             vjp(x->y, x->p, t, z, dz, NULL, &F->ctx);        /* gauss_adjoint.jl:123, quadrature_adjoint.jl:41 */
             for (int i = 0; i < d; i++) dz[i] = -dz[i];
         }
-        if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca * x->y[i] + x->cb;   /* accumulate_cost!: dlam -= g_u */
+        if (x->cont) for (int i = 0; i < d; i++) dz[i] -= x->ca[i] * x->y[i] + x->cb[i];   /* accumulate_cost!: dlam -= g_u */
     }
 }
 /* Jacobian and time derivative of adj_rhs for Rosenbrock23 on the adjoint ODE (Gauss/Quad state = lam):
@@ -701,7 +710,7 @@ static void adj_jac(double t, const double* z, double* Jout, double* dT, void* c
         for (int j = 0; j < d; j++) {               /* column of d/dy_j: Hessian contractions with lam */
             double e[8] = {0}; e[j] = 1.0;
             fam_djac(F, x->p, e, dJ); fam_dpjac(F, yy, e, dF);
-            for (int i = 0; i < d; i++) { double a = 0; for (int k = 0; k < d; k++) a -= dJ[k * d + i] * z[k]; Jout[i * L + (d + P + j)] = a - (x->cont && i == j ? x->ca : 0.0); }
+            for (int i = 0; i < d; i++) { double a = 0; for (int k = 0; k < d; k++) a -= dJ[k * d + i] * z[k]; Jout[i * L + (d + P + j)] = a - (x->cont && i == j ? x->ca[i] : 0.0); }
             for (int q = 0; q < P; q++) { double a = 0; for (int k = 0; k < d; k++) a -= dF[k * P + q] * z[k]; Jout[(d + q) * L + (d + P + j)] = a; }
         }
         return;
@@ -713,7 +722,7 @@ static void adj_jac(double t, const double* z, double* Jout, double* dT, void* c
     for (int i = 0; i < d; i++) {
         double s = 0;
         for (int j = 0; j < d; j++) { Jout[i * L + j] = -J[j * d + i]; s -= dJ[j * d + i] * z[j]; }
-        dT[i] = s - (x->cont ? x->ca * yd[i] : 0.0);          /* d/dt of -(ca y(t) + cb) */
+        dT[i] = s - (x->cont ? x->ca[i] * yd[i] : 0.0);          /* d/dt of -(ca y(t) + cb) */
     }
     if (L > d) {                                   /* InterpolatingAdjoint: mu' = -F(y(t))' lam */
         fam_pjac(F, y, Fm); fam_dpjac(F, y, yd, dF);
@@ -728,7 +737,7 @@ static void adj_jac(double t, const double* z, double* Jout, double* dT, void* c
 /* cotangent at save index k for one trajectory (dgdu_discrete; src/concrete_solve.jl:778-947 or user dg) */
 static void cost_grad(const oracle_cfg* c, const double* dLdu_k /* [d] gathered or NULL */, const double* y, double* out) {
     if (c->cost_kind == COST_EXPLICIT) for (int i = 0; i < c->d; i++) out[i] = dLdu_k[i];
-    else for (int i = 0; i < c->d; i++) out[i] = c->cost_a * y[i] + c->cost_b;
+    else for (int i = 0; i < c->d; i++) out[i] = COST_A(c, i) * y[i] + COST_B(c, i);
 }
 
 /* ---- adjoint dense record (QuadratureAdjoint keeps adj_sol with save_everystep) ---- */
@@ -911,7 +920,8 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     double* k = (double*)malloc(sizeof(double) * 7 * L);
     double* ybuf = (double*)malloc(sizeof(double) * (d + 2 * P + 4 * d + 8));
     double* gu = ybuf + d, *lamq = gu + d, *dlq = lamq + d, *integ = dlq + d, *acc = integ + P;
-    adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0, cfg->cont_cost, cfg->cont_a, cfg->cont_b, INFINITY};
+    adj_ctx ctx = {F, p, sol, sa, 0, ybuf, NULL, 0, cfg->cont_cost, {0}, {0}, INFINITY};
+    for (int j = 0; j < d && j < 8; j++) { ctx.ca[j] = CONT_A(cfg, j); ctx.cb[j] = CONT_B(cfg, j); }
     int evc = cfg->n_events - 1;     /* next event below t */
     if (cfg->n_events > 0 && ((cfg->stepper != ST_TSIT5_ADAPTIVE && cfg->stepper != ST_TSIT5_FIXED) || sa == SA_QUADRATURE)) return -11;
     for (int q = 0; q < P; q++) acc[q] = 0;
@@ -1230,6 +1240,17 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
             free(us); free(dWm);
         }
         if (r == 0 && du0) for (int j = 0; j < d; j++) du0[(size_t)j * N + i] = du[j];
+        if (r == 0 && du0 && (cfg->dgdp_c || cfg->dgdp_e || cfg->cdgdp_c || cfg->cdgdp_e)) {
+            /* parameter part of the cost family: dgdp_discrete = c .* p + e joins the gradient at every save time whose jump is
+             * applied (ReverseLossCallback, src/adjoint_common.jl:771-783; quadrature_adjoint.jl:547-553, 601-605), dgdp_continuous
+             * integrates to (T - t0)(cc .* p + ce) (accumulate_cost!, src/derivative_wrappers.jl:1411-1442) */
+            int njump = K;
+            if (cfg->no_start && cfg->sensealg != SA_BACKSOLVE && K > 0 && saveat[0] == cfg->t0) njump--;
+            for (int q = 0; q < P; q++) {
+                dpm[q] += njump * ((cfg->dgdp_c ? cfg->dgdp_c[q] * pm[q] : 0.0) + (cfg->dgdp_e ? cfg->dgdp_e[q] : 0.0));
+                if (cfg->cont_cost) dpm[q] += (cfg->t1 - cfg->t0) * ((cfg->cdgdp_c ? cfg->cdgdp_c[q] * pm[q] : 0.0) + (cfg->cdgdp_e ? cfg->cdgdp_e[q] : 0.0));
+            }
+        }
         if (r) {
 #pragma omp atomic write
             err = r;
@@ -1253,11 +1274,11 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
 
 /* scalar loss of COST_AFFINE, L = sum_k sum_j (a/2 u^2 + b u), and explicit-cotangent-free forward solve:
  * used by the tests to differentiate THROUGH the solver by finite differences (the ForwardDiff relation). */
-typedef struct { const dense_t* sol; double ca, cb; int d; double* y; } gint_ctx;
+typedef struct { const dense_t* sol; const oracle_cfg* cfg; int d; double* y; } gint_ctx;
 static void g_integrand(double t, double* out, void* c) {
     gint_ctx* x = (gint_ctx*)c; double s = 0;
     dense_eval(x->sol, t, 0, x->y, NULL);
-    for (int j = 0; j < x->d; j++) s += 0.5 * x->ca * x->y[j] * x->y[j] + x->cb * x->y[j];
+    for (int j = 0; j < x->d; j++) s += 0.5 * CONT_A(x->cfg, j) * x->y[j] * x->y[j] + CONT_B(x->cfg, j) * x->y[j];
     out[0] = s;
 }
 /* integral of the continuous cost along one member's dense forward solution (quadgk per step, tight tolerance) */
@@ -1273,9 +1294,11 @@ int oracle_continuous_loss(const oracle_cfg* cfg, const double* u0, const double
         for (int q = 0; q < P && q < 16; q++) pm[q] = cfg->shared_p ? p[q] : p[(size_t)q * N + i];
         for (int j = 0; j < d; j++) um[j] = u0[(size_t)j * N + i];
         forward_dense_member(cfg, &F, pm, um, &sol);
-        gint_ctx gc = {&sol, cfg->cont_a, cfg->cont_b, d, y};
+        gint_ctx gc = {&sol, cfg, d, y};
         double tot = 0;
         for (int n = 0; n < sol.n; n++) { oracle_quadgk(g_integrand, &gc, 1, sol.t[n], sol.t[n + 1], 1e-14, 1e-13, &part); tot += part; }
+        /* parameter part of the running cost: constant along the trajectory */
+        for (int q = 0; q < P && q < 16; q++) tot += (cfg->t1 - cfg->t0) * ((cfg->cdgdp_c ? 0.5 * cfg->cdgdp_c[q] * pm[q] * pm[q] : 0.0) + (cfg->cdgdp_e ? cfg->cdgdp_e[q] * pm[q] : 0.0));
         out_members[i] = tot;
         dense_free(&sol);
     }
@@ -1289,7 +1312,11 @@ int oracle_ensemble_loss(const oracle_cfg* cfg, const double* saveat, const doub
     int rc = oracle_ensemble_gradient(cfg, saveat, u0, p, dW, NULL, saved, NULL, NULL, NULL, nthreads);
     for (int64_t i = 0; i < N; i++) {
         double s = 0;
-        for (int k = 0; k < K; k++) for (int j = 0; j < d; j++) { double u = saved[((size_t)k * d + j) * N + i]; s += 0.5 * cfg->cost_a * u * u + cfg->cost_b * u; }
+        for (int k = 0; k < K; k++) for (int j = 0; j < d; j++) { double u = saved[((size_t)k * d + j) * N + i]; s += 0.5 * COST_A(cfg, j) * u * u + COST_B(cfg, j) * u; }
+        for (int q = 0; q < cfg->P && (cfg->dgdp_c || cfg->dgdp_e); q++) {          /* parameter part, once per save time */
+            const double pq = cfg->shared_p ? p[q] : p[(size_t)q * N + i];
+            s += K * ((cfg->dgdp_c ? 0.5 * cfg->dgdp_c[q] * pq * pq : 0.0) + (cfg->dgdp_e ? cfg->dgdp_e[q] * pq : 0.0));
+        }
         loss_members[i] = s;
     }
     free(saved);

@@ -34,6 +34,8 @@ class OracleCfg(C.Structure):
         ("n_events", C.c_int32), ("_pad", C.c_int32),
         ("ev_times", C.c_void_p), ("ev_scale", C.c_void_p), ("ev_shift", C.c_void_p),
         ("ev_pscale", C.c_void_p), ("ev_pshift", C.c_void_p),
+        ("cost_av", C.c_void_p), ("cost_bv", C.c_void_p), ("cont_av", C.c_void_p), ("cont_bv", C.c_void_p),
+        ("dgdp_c", C.c_void_p), ("dgdp_e", C.c_void_p), ("cdgdp_c", C.c_void_p), ("cdgdp_e", C.c_void_p),
     ]
 
 
@@ -63,7 +65,7 @@ def _ptr(a):
 
 def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, reltol=1e-3, quad_abstol=1e-10,
              quad_reltol=1e-10, cost=("explicit",), shared_p=True, no_start=False, checkpointing=True,
-             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None):
+             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None, cost_vec=None, cont_vec=None):
     if family == "mlp":
         d = 2
         H = mlp_hidden
@@ -84,6 +86,24 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
     cfg.backsolve_ckpt_every_step, cfg.mlp_hidden = int(ckpt_every_step), mlp_hidden
     if cont_cost is not None:      # continuous cost g(u) = a/2 |u|^2 + b sum(u)
         cfg.cont_cost, cfg.cont_a, cfg.cont_b = 1, float(cont_cost[0]), float(cont_cost[1])
+    # per-component cost coefficients (a[d], b[d], c[P] or None, e[P] or None): dgdu = a .* u + b, dgdp = c .* p + e
+    keep = []
+
+    def _vec(x, n):
+        if x is None:
+            return None
+        v = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (n,)))
+        keep.append(v)
+        return v.ctypes.data
+    if cost_vec is not None:
+        a, b, c, e = (tuple(cost_vec) + (None, None))[:4]
+        cfg.cost_kind = 1
+        cfg.cost_av, cfg.cost_bv, cfg.dgdp_c, cfg.dgdp_e = _vec(a, d), _vec(b, d), _vec(c, P), _vec(e, P)
+    if cont_vec is not None:
+        a, b, c, e = (tuple(cont_vec) + (None, None))[:4]
+        cfg.cont_cost = 1
+        cfg.cont_av, cfg.cont_bv, cfg.cdgdp_c, cfg.cdgdp_e = _vec(a, d), _vec(b, d), _vec(c, P), _vec(e, P)
+    cfg._keep_cost = keep
     if events is not None:         # preset-time events: (times[E], scale[E, d], shift[E, d]), u <- scale * u + shift
         et, es, ec = (np.ascontiguousarray(x, dtype=np.float64) for x in events[:3])
         assert es.shape == (len(et), d) and ec.shape == (len(et), d)

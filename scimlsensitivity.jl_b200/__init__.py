@@ -11,7 +11,7 @@ from .concrete_solve import (ChainRulesOriginator, NoTangent, ReverseDiffOrigina
 from .distributed import allreduce_dp, shard_bounds
 from .engine import DeviceEnsemble
 from .problems import (EM, AdjointSensitivityParameterCompatibilityError, AffineAffect, AffineCost, PresetTimeCallback, EnsembleB200, EnsembleProblem,
-                       EnsembleSolution, EulerHeun, FAMILIES, ODEProblem, QuadraticRunningCost, Rosenbrock23, SDEProblem, Tsit5)
+                       EnsembleSolution, EulerHeun, FAMILIES, ODEProblem, ParamAffine, QuadraticRunningCost, Rosenbrock23, SDEProblem, Tsit5)
 from .sensitivity_algorithms import (B200Adjoint, B200VJP, BacksolveAdjoint, EnzymeVJP, GaussAdjoint, GaussKronrodAdjoint,
                                      InterpolatingAdjoint, MooncakeVJP, QuadratureAdjoint, ReactantVJP,
                                      ReverseDiffVJP, TrackerVJP, VJPChoice, ZygoteVJP, alg_autodiff, diff_type,

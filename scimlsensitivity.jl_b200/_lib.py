@@ -21,7 +21,7 @@ COST = {"explicit": 0, "affine": 1}
 FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE, FLAG_NO_ROTATE = 1, 2, 4, 8, 16, 32
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
-EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_events", "b200adj_get_noise", "b200adj_set_stream",
+EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_set_events", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg",
            "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_allreduce", "b200adj_comm_size"]
@@ -130,6 +130,8 @@ def load():
         lib.b200adj_set_tolerances.restype = C.c_int32
         lib.b200adj_set_continuous_cost.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_double]
         lib.b200adj_set_continuous_cost.restype = C.c_int32
+        lib.b200adj_set_cost_family.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200adj_set_cost_family.restype = C.c_int32
         lib.b200adj_set_events.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200adj_set_events.restype = C.c_int32
         lib.b200adj_get_noise.argtypes = [C.c_void_p, C.c_void_p]
@@ -223,6 +225,13 @@ class Handle:
 
     def set_continuous_cost(self, enabled, a=0.0, b=0.0):
         self._check(self._lib.b200adj_set_continuous_cost(self._h, int(bool(enabled)), float(a), float(b)))
+
+    def set_cost_family(self, which, a=None, b=None, c=None, e=None):
+        """Per-component coefficients of the named cost family (which = 0 discrete, 1 continuous): dgdu = a .* u + b,
+        dgdp = c .* p + e; None keeps (a, b) / zeroes (c, e)."""
+        import numpy as np
+        arrs = [None if x is None else np.ascontiguousarray(x, dtype=np.float64).reshape(-1) for x in (a, b, c, e)]
+        self._check(self._lib.b200adj_set_cost_family(self._h, int(which), *[None if x is None else x.ctypes.data for x in arrs]))
 
     def set_events(self, times, scale, shift, pscale=None, pshift=None):
         """Preset-time events u <- scale[e] * u + shift[e] (and optionally p <- pscale[e] * p + pshift[e]) at times[e]

@@ -84,7 +84,8 @@ T5aArgs t5a_args(Handle* h) {
     a.rrec = h->r_rrec; a.rend = h->r_rend; a.ftT = h->r_ftT; a.frecT = h->r_frecT; a.rn = h->r_rn;
     a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.maxseg = h->maxseg;
     a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.dt0 = c.dt; a.abstol = c.abstol; a.reltol = c.reltol;
-    a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+    a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol;
+    for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; }
     a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
               ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
     const double A[7][6] = {
@@ -100,7 +101,7 @@ T5aArgs t5a_args(Handle* h) {
                           0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
     memcpy(a.A, A, sizeof(A)); memcpy(a.C, C, sizeof(C)); memcpy(a.BT, BT, sizeof(BT));
     tsit5_weights(0.0, nullptr, a.R);
-    if (h->cont_on) { a.flags |= 8u; a.cont_a = h->cont_a; a.cont_b = h->cont_b; }
+    if (h->cont_on) { a.flags |= 8u; for (int j = 0; j < 4; j++) { a.cont_a[j] = h->cont_av[j]; a.cont_b[j] = h->cont_bv[j]; } }
     a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
     return a;
 }
@@ -113,8 +114,10 @@ RosArgs ros_args(Handle* h) {
     a.rrec = h->r_rrec; a.rend = h->r_rend; a.ftT = h->r_ftT; a.frecT = h->r_frecT; a.rn = h->r_rn;
     a.qseg = h->r_qseg; a.qkey = h->r_qkey; a.maxseg = h->maxseg;
     a.N = c.N; a.K = c.K; a.maxs = h->maxs; a.t0 = c.t0; a.t1 = c.t1; a.abstol = c.abstol; a.reltol = c.reltol;
-    a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
-    a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    a.quad_abstol = c.quad_abstol; a.quad_reltol = c.quad_reltol;
+    for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; }
+    a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
+              ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
     return a;
 }
 void free_all(Handle* h) {
@@ -127,6 +130,27 @@ void free_all(Handle* h) {
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
+}  // namespace
+
+namespace {
+// dp += coef_c .* p + coef_e per member (shared parameters: N times, once)
+struct DgdpArgs { double c[8], e[8]; const void* p; void* dp; int64_t N; int32_t P, shared_p, f32; };
+__global__ void dgdp_add_kernel(DgdpArgs g) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g.shared_p) {
+        if (i != 0) return;
+        for (int q = 0; q < g.P; q++) {
+            if (g.f32) { float* dp = (float*)g.dp; const float* p = (const float*)g.p; dp[q] = (float)((double)dp[q] + (double)g.N * (g.c[q] * (double)p[q] + g.e[q])); }
+            else { double* dp = (double*)g.dp; const double* p = (const double*)g.p; dp[q] += (double)g.N * (g.c[q] * p[q] + g.e[q]); }
+        }
+        return;
+    }
+    if (i >= g.N) return;
+    for (int q = 0; q < g.P; q++) {
+        if (g.f32) { float* dp = (float*)g.dp; const float* p = (const float*)g.p; dp[(int64_t)q * g.N + i] += (float)(g.c[q] * (double)p[(int64_t)q * g.N + i] + g.e[q]); }
+        else { double* dp = (double*)g.dp; const double* p = (const double*)g.p; dp[(int64_t)q * g.N + i] += g.c[q] * p[(int64_t)q * g.N + i] + g.e[q]; }
+    }
+}
 }  // namespace
 
 namespace b200adj {
@@ -195,8 +219,6 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
         if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (ros && !t5a && (cfg->sensealg == B200ADJ_SA_INTERPOLATING || cfg->sensealg == B200ADJ_SA_BACKSOLVE)) {
-            g_create_error = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     }
     if (ros) {
         // adaptive path: save times are arbitrary ascending points of [t0, t1] (tstops of the reverse solve)
@@ -254,6 +276,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
             }
         }
 #undef CREATE_TRY
+        for (int j = 0; j < 4; j++) { h->cost_av[j] = cfg->cost_a; h->cost_bv[j] = cfg->cost_b; }
         *handle = h;
         return B200ADJ_OK;
     }
@@ -353,6 +376,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     }
 #undef CREATE_TRY
     if (!sde) build_tsit5_tables(cfg->dt, &h->tb);
+    for (int j = 0; j < 4; j++) { h->cost_av[j] = cfg->cost_a; h->cost_bv[j] = cfg->cost_b; }
     *handle = h;
     return B200ADJ_OK;
 }
@@ -371,8 +395,6 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (c.dtype == B200ADJ_F32 && c.rhs_family != B200ADJ_FAM_MLP && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "F32: QuadratureAdjoint is F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     if (h->adaptive) {
-        if ((sensealg == B200ADJ_SA_BACKSOLVE || sensealg == B200ADJ_SA_INTERPOLATING) && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) {
-            h->err = "Rosenbrock23: GaussAdjoint / QuadratureAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
         if (K >= 0) {
             for (int k = 0; k < K; k++)
                 if (t[k] < c.t0 || t[k] > c.t1 || (k > 0 && !(t[k] > t[k - 1]))) { h->err = "t must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }
@@ -384,6 +406,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
         if (!c.buffers_on_device && cost_kind == B200ADJ_COST_EXPLICIT && c.K > 0 && !h->s_dLdu)
             CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)c.K * c.d * (size_t)c.N * esz(c)));
         c.sensealg = sensealg; c.cost_kind = cost_kind; c.cost_a = cost_a; c.cost_b = cost_b;
+        for (int j = 0; j < 4; j++) { h->cost_av[j] = cost_a; h->cost_bv[j] = cost_b; }
+        h->has_dgdp = false;
         c.flags = (c.flags & B200ADJ_CREATE_FLAGS) | (flags & ~B200ADJ_CREATE_FLAGS);
         return B200ADJ_OK;
     }
@@ -411,6 +435,8 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
         CUDA_TRY(h, cudaMalloc(&h->s_dLdu, (size_t)c.K * c.d * (size_t)c.N * esz(c)));
     }
     c.sensealg = sensealg; c.cost_kind = cost_kind; c.cost_a = cost_a; c.cost_b = cost_b;
+    for (int j = 0; j < 4; j++) { h->cost_av[j] = cost_a; h->cost_bv[j] = cost_b; }
+    h->has_dgdp = false;
     c.flags = (c.flags & B200ADJ_CREATE_FLAGS) | (flags & ~B200ADJ_CREATE_FLAGS);
     return B200ADJ_OK;
 }
@@ -420,7 +446,27 @@ int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, dou
     Handle* h = (Handle*)handle;
     if (enabled && ((h->adaptive && h->cfg.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
         h->err = "continuous cost: built for the Tsit5 ODE paths (fixed step and adaptive)"; return B200ADJ_ERR_UNSUPPORTED; }
-    h->cont_on = enabled != 0; h->cont_a = a; h->cont_b = b;
+    h->cont_on = enabled != 0;
+    for (int j = 0; j < 4; j++) { h->cont_av[j] = a; h->cont_bv[j] = b; }
+    h->has_cdgdp = false;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_cost_family(void* handle, int32_t which, const double* a, const double* b, const double* c, const double* e) {
+    if (!handle || (which != 0 && which != 1)) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& cf = h->cfg;
+    if ((c || e) && (cf.P > 8 || cf.rhs_family == B200ADJ_FAM_MLP)) { h->err = "cost family: the parameter part (dgdp) is built for P <= 8"; return B200ADJ_ERR_UNSUPPORTED; }
+    if ((c || e) && h->d_ev_ps) { h->err = "cost family: dgdp together with parameter-changing events is not built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (which == 1) {
+        int32_t rc = b200adj_set_continuous_cost(handle, 1, 0.0, 0.0);       // same support matrix as the scalar entry point
+        if (rc) return rc;
+    } else if (cf.cost_kind != B200ADJ_COST_AFFINE && (a || b)) { h->err = "cost family: per-component dgdu_discrete needs cost_kind = AFFINE"; return B200ADJ_ERR_INVALID; }
+    double* av = which ? h->cont_av : h->cost_av; double* bv = which ? h->cont_bv : h->cost_bv;
+    double* cv = which ? h->cdgdp_c : h->dgdp_c; double* ev = which ? h->cdgdp_e : h->dgdp_e;
+    for (int j = 0; j < 4; j++) { if (a) av[j] = j < cf.d ? a[j] : 0.0; if (b) bv[j] = j < cf.d ? b[j] : 0.0; }
+    for (int q = 0; q < 8; q++) { cv[q] = (c && q < cf.P) ? c[q] : 0.0; ev[q] = (e && q < cf.P) ? e[q] : 0.0; }
+    (which ? h->has_cdgdp : h->has_dgdp) = (c != nullptr || e != nullptr);
     return B200ADJ_OK;
 }
 
@@ -637,7 +683,8 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         memset(&a, 0, sizeof(a));
         a.ckpt = (const float*)h->d_ckpt; a.p = (const float*)h->cur_p; a.dLdu = (const float*)dL; a.save_of_step = h->d_save_of_step;
         a.du0 = (float*)ddu0; a.dp_members = (float*)ddp; a.partials = h->d_partials; a.dp = (float*)ddp; a.ticket = h->d_ticket;
-        a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.cost_a = (float)c.cost_a; a.cost_b = (float)c.cost_b; a.trace = h->d_trace;
+        a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.trace = h->d_trace;
+        for (int j = 0; j < 4; j++) { a.cost_a[j] = (float)h->cost_av[j]; a.cost_b[j] = (float)h->cost_bv[j]; }
         cast_tables(h->tb, &a.tb);
         a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
                   ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
@@ -650,10 +697,10 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         OdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
-        a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.trace = h->d_trace;
+        a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.trace = h->d_trace;
+        for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; a.cont_a[j] = h->cont_av[j]; a.cont_b[j] = h->cont_bv[j]; }
         a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) |
                   ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u) | (h->cont_on ? 8u : 0u);
-        a.cont_a = h->cont_a; a.cont_b = h->cont_b;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_rev<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_rev<Lorenz>(h, a); break;
@@ -664,7 +711,8 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         SdeRevArgs a;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
-        a.N = c.N; a.S = h->S; a.h = c.dt; a.cost_a = c.cost_a; a.cost_b = c.cost_b;
+        a.N = c.N; a.S = h->S; a.h = c.dt;
+        for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; }
         a.flags = ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) | ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
         a.seed = c.seed; a.traj_offset = c.traj_offset;
         a.noise = h->noise_valid ? h->d_noise : nullptr;
@@ -672,6 +720,24 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
     }
     if (rc) { h->err = "reverse dispatch failed (sensealg/family not built)"; return rc; }
     CUDA_TRY(h, cudaGetLastError());
+    // parameter part of the cost family (dgdp_discrete at every applied jump, dgdp_continuous over the horizon): independent of
+    // the state, so it joins dp after the reverse kernels (ReverseLossCallback src/adjoint_common.jl:771-783, accumulate_cost!
+    // src/derivative_wrappers.jl:1411-1442, QuadratureAdjoint src/quadrature_adjoint.jl:547-553, 601-605)
+    if (h->has_dgdp || (h->has_cdgdp && h->cont_on)) {
+        DgdpArgs g;
+        memset(&g, 0, sizeof(g));
+        int njump = c.K;
+        if ((c.flags & B200ADJ_FLAG_NO_START) && c.sensealg != B200ADJ_SA_BACKSOLVE && c.K > 0 && h->saveat[0] == c.t0) njump--;
+        for (int q = 0; q < 8; q++) {
+            g.c[q] = (h->has_dgdp ? njump * h->dgdp_c[q] : 0.0) + ((h->has_cdgdp && h->cont_on) ? (c.t1 - c.t0) * h->cdgdp_c[q] : 0.0);
+            g.e[q] = (h->has_dgdp ? njump * h->dgdp_e[q] : 0.0) + ((h->has_cdgdp && h->cont_on) ? (c.t1 - c.t0) * h->cdgdp_e[q] : 0.0);
+        }
+        g.p = h->cur_p; g.dp = ddp; g.N = c.N; g.P = c.P; g.shared_p = c.shared_p; g.f32 = c.dtype != B200ADJ_F64;
+        const int64_t work = c.shared_p ? 1 : c.N;
+        dgdp_add_kernel<<<(unsigned)((work + 127) / 128), 128, 0, h->stream>>>(g);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+    }
     // multi-GPU: the ONE collective of the path -- dG/dp summed over the ranks (shared parameters only)
     if (c.shared_p && h->nranks > 1) { rc = comm_allreduce(h, ddp, (size_t)c.P); if (rc) return rc; }
     if (!c.buffers_on_device) {

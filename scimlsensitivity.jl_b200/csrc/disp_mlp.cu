@@ -31,7 +31,7 @@ int mlp_tc_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
     memset(&a, 0, sizeof(a));
     a.p = (const float*)h->cur_p; a.ckpt = (float*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const float*)dLdu;
     a.du0 = (float*)du0; a.partials = (float*)h->d_partials; a.dp = (float*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
-    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; } a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
     const size_t smem = sizeof(TcSmem) + 128;
     const int grid = (int)((c.N + TC_M - 1) / TC_M);
     if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
@@ -52,7 +52,7 @@ int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
     memset(&a, 0, sizeof(a));
     a.p = (const T*)h->cur_p; a.ckpt = (T*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const T*)dLdu;
     a.du0 = (T*)du0; a.partials = (T*)h->d_partials; a.dp = (T*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
-    a.cost_a = c.cost_a; a.cost_b = c.cost_b; a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
+    for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; } a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
     const size_t smem = sizeof(MlpSmem<T>);
     a.Npad = h->Npad;
 #define B200_MLP_REV(COSTV, TAPEV)                                                                                          \

@@ -31,6 +31,12 @@ struct LotkaVolterra {
         J[0][0] = -p[1] * yd[1]; J[0][1] = -p[1] * yd[0];
         J[1][0] = p[3] * yd[1];  J[1][1] = p[3] * yd[0];
     }
+    // directional derivative of vjp_p with respect to u along ud (Rosenbrock23 on the augmented adjoint states: the time
+    // derivative -(dF/dt)'lam with ud = ydot, and the Jacobian block d(F'lam)/dy of BacksolveAdjoint)
+    template <class T> __device__ __forceinline__ static void dvjp_p(const T* u, const T* p, const T* ud, const T* l, T* dg) {
+        const T dxy = ud[0] * u[1] + u[0] * ud[1];
+        dg[0] = ud[0] * l[0]; dg[1] = -dxy * l[0]; dg[2] = -ud[1] * l[1]; dg[3] = dxy * l[1];
+    }
 };
 
 struct Lorenz {
@@ -57,6 +63,9 @@ struct Lorenz {
         J[0][0] = 0;      J[0][1] = 0;     J[0][2] = 0;
         J[1][0] = -yd[2]; J[1][1] = 0;     J[1][2] = -yd[0];
         J[2][0] = yd[1];  J[2][1] = yd[0]; J[2][2] = 0;
+    }
+    template <class T> __device__ __forceinline__ static void dvjp_p(const T* u, const T* p, const T* ud, const T* l, T* dg) {
+        dg[0] = (ud[1] - ud[0]) * l[0]; dg[1] = ud[0] * l[1]; dg[2] = -ud[2] * l[2];
     }
 };
 
@@ -87,6 +96,11 @@ struct Robertson {
         J[0][0] = 0; J[0][1] = k[2] * yd[2];                     J[0][2] = k[2] * yd[1];
         J[1][0] = 0; J[1][1] = -2 * k[1] * yd[1] - k[2] * yd[2]; J[1][2] = -k[2] * yd[1];
         J[2][0] = 0; J[2][1] = 2 * k[1] * yd[1];                 J[2][2] = 0;
+    }
+    template <class T> __device__ __forceinline__ static void dvjp_p(const T* y, const T* k, const T* yd, const T* l, T* dg) {
+        dg[0] = -yd[0] * l[0] + yd[0] * l[1];
+        dg[1] = 2 * y[1] * yd[1] * (l[2] - l[1]);
+        dg[2] = (yd[1] * y[2] + y[1] * yd[2]) * (l[0] - l[1]);
     }
 };
 

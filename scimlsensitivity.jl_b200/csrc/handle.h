@@ -45,8 +45,13 @@ struct Handle {
     // adaptive path: per-member dense forward / reverse solutions
     bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
-    bool cont_on = false; double cont_a = 0, cont_b = 0, cont_c = 0, cont_e = 0;   // continuous cost family
-    double dgdp_c = 0, dgdp_e = 0;    // discrete cost's parameter part: dgdp_discrete = c p + e at every save time
+    // named cost family, per component (b200adj_set_cost_family; the scalar entry points broadcast):
+    //   discrete (COST_AFFINE)  dgdu = cost_av .* u + cost_bv,  dgdp = dgdp_c .* p + dgdp_e   at every save time
+    //   continuous              dgdu = cont_av .* u + cont_bv,  dgdp = cdgdp_c .* p + cdgdp_e
+    bool cont_on = false;
+    double cost_av[4] = {0, 0, 0, 0}, cost_bv[4] = {0, 0, 0, 0}, cont_av[4] = {0, 0, 0, 0}, cont_bv[4] = {0, 0, 0, 0};
+    bool has_dgdp = false, has_cdgdp = false;
+    double dgdp_c[8] = {0}, dgdp_e[8] = {0}, cdgdp_c[8] = {0}, cdgdp_e[8] = {0};
     bool mlp_tc = false;              // BF16_F32ACC: every GEMM-shaped piece of the time loop on tcgen05 (mlp_tc.cuh)
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *d_saveat = nullptr;
     // QuadratureAdjoint on the adaptive steppers (allocated at the first Quadrature reverse pass): member-major reverse dense

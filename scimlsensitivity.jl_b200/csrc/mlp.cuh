@@ -28,7 +28,7 @@ constexpr int MLP_OW1 = 0, MLP_OB1 = MLP_H * MLP_D, MLP_OW2 = MLP_OB1 + MLP_H, M
 template <class T> struct MlpArgs {
     const T* u0; const T* p; T* ckpt; T* saved; const int32_t* save_of_step; int32_t* status;
     const T* dLdu; T* du0; T* partials; T* dp;     // partials [grid][P]
-    int64_t N; int32_t S; double cost_a, cost_b; uint32_t flags;
+    int64_t N; int32_t S; double cost_a[4], cost_b[4]; uint32_t flags;
     void* tapeA; void* tapeB; int64_t Ktot, Npad;     // bf16 mode: K-major operand tapes [64][Ktot], Ktot = 6 S Npad
     Tsit5Tables tb;
 };
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
     auto cotangent = [&](int ks, const T (*yy)[MLP_TB]) {      // lam += dgdu at save index ks (owner threads)
         if (own) {
             if (COST == COST_EXPLICIT) s.lam[c][b] += a.dLdu[((int64_t)ks * MLP_D + c) * N + col];
-            else s.lam[c][b] += (T)(a.cost_a * (double)yy[c][b] + a.cost_b);
+            else s.lam[c][b] += (T)(a.cost_a[c] * (double)yy[c][b] + a.cost_b[c]);
         }
     };
     if (own) { s.lam[c][b] = 0; s.uhi[c][b] = a.ckpt[((int64_t)a.S * MLP_D + c) * N + col]; s.y[c][b] = s.uhi[c][b]; }

@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(TC_M) mlp_tc_reverse_kernel(const __grid_const
     float lam[2] = {0.0f, 0.0f}, uhi[2], ulo[2], kf[7][2], ka[6][2], H2[64], F[2], J[2];
     auto cotangent = [&](int ks, const float* yy) {
         if (COST == COST_EXPLICIT) { lam[0] += a.dLdu[((int64_t)ks * 2) * N + col]; lam[1] += a.dLdu[((int64_t)ks * 2 + 1) * N + col]; }
-        else { lam[0] += (float)(a.cost_a * (double)yy[0] + a.cost_b); lam[1] += (float)(a.cost_a * (double)yy[1] + a.cost_b); }
+        else { lam[0] += (float)(a.cost_a[0] * (double)yy[0] + a.cost_b[0]); lam[1] += (float)(a.cost_a[1] * (double)yy[1] + a.cost_b[1]); }
     };
     uhi[0] = a.ckpt[((int64_t)a.S * 2) * N + col]; uhi[1] = a.ckpt[((int64_t)a.S * 2 + 1) * N + col];
     { const int ks = a.save_of_step[a.S]; if (ks >= 0) cotangent(ks, uhi); }

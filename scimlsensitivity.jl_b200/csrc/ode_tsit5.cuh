@@ -69,8 +69,8 @@ template <class R> struct OdeRevArgsT {
     int32_t S;
     int32_t slots;           // member slots per block (= checkpoint tile width); blockDim.x > slots => the top warp row rotates
     int32_t ckpt_every;      // C > 1 (SEG kernels): forward states kept every C steps, each segment re-solved into shared memory
-    R cost_a, cost_b;
-    R cont_a, cont_b;   // continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u):  dlam -= dgdu_continuous(y)  (flags bit3)
+    R cost_a[4], cost_b[4];   // COST_AFFINE, per component: dgdu_discrete = cost_a .* u(t_k) + cost_b
+    R cont_a[4], cont_b[4];   // continuous cost g = sum_j cont_a_j/2 u_j^2 + cont_b_j u_j:  dlam -= dgdu_continuous(y)  (flags bit3)
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step, bit3 continuous cost
     R* adj_dense;       // SA_QUAD: [S][8][D][Npad] = (lambda at the start of reverse step n, ka'[0..6]) per step
     unsigned long long* trace;   // optional [gridDim][3] = (smid, globaltimer at block start, at block end) or null
@@ -233,7 +233,7 @@ template <int D, bool CONT, class Args, class R>
 __device__ __forceinline__ void add_continuous(const Args& a, const R* y, R* ka) {
     if (CONT) {
 #pragma unroll
-        for (int j = 0; j < D; j++) ka[j] += fma(a.cont_a, y[j], a.cont_b);
+        for (int j = 0; j < D; j++) ka[j] += fma(a.cont_a[j], y[j], a.cont_b[j]);
     }
 }
 
@@ -244,7 +244,7 @@ __device__ __forceinline__ void add_cotangent(const Args& a, int ks, int64_t str
         for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
     } else {
 #pragma unroll
-        for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a, y[j], a.cost_b);
+        for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a[j], y[j], a.cost_b[j]);
     }
 }
 

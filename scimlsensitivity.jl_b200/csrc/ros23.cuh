@@ -39,7 +39,7 @@ struct RosArgs {
     double* ftT; double* frecT;
     double* qseg; double* qkey; int32_t maxseg;                  // quadgk scratch per resident warp: segments [maxseg][SEGW], keys [maxseg] (quadgk.cuh)
     int64_t N; int32_t K; int32_t maxs;
-    double t0, t1, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
+    double t0, t1, abstol, reltol, quad_abstol, quad_reltol, cost_a[4], cost_b[4];
     uint32_t flags;                                               // bit0 no_start
 };
 
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
                 } else {
                     sol.eval(a.saveat[cur], true, y, nullptr);
 #pragma unroll
-                    for (int j = 0; j < D; j++) z[j] += a.cost_a * y[j] + a.cost_b;
+                    for (int j = 0; j < D; j++) z[j] += a.cost_a[j] * y[j] + a.cost_b[j];
                 }
             }
             cur--; fsal_ok = false;
@@ -424,6 +424,219 @@ __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
 #pragma unroll
             for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = acc[q];
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Rosenbrock23 on the AUGMENTED adjoint states: InterpolatingAdjoint z = [lam; mu] and BacksolveAdjoint z = [lam; mu; y]
+// (src/interpolating_adjoint.jl:150-174, src/backsolve_adjoint.jl:32-61; the reference runs every sensealg with stiff solvers,
+// test/Core2/stiff_adjoints.jl:204-252).  W = I - h d (d rhs / dz) is block triangular, so the linear solves are the 3 x 3 LU
+// of the lambda block (and of the y block for Backsolve) plus substitutions:
+//   Interpolating   W = [[I + hd J', 0], [hd F', I]]                         dT = [-(dJ/dt)'lam, -(dF/dt)'lam]   (ydot from sol)
+//   Backsolve       W = [[I + hd J', 0, hd H], [hd F', I, hd G], [0, 0, I - hd J]]   autonomous: dT = 0
+//                   H v = d(J'lam)/dy [v], G v = d(F'lam)/dy [v]  (families.cuh::djac, dvjp_p)
+// Error norm over all components of z (the reference's augmented state).  Checkpoints / jumps as in t5a_reverse_kernel.
+// ------------------------------------------------------------------------------------------------------------
+template <class Fam, int SA, bool SHARED_P, int COST>
+__global__ void __launch_bounds__(256) ros23_aug_reverse_kernel(RosArgs a) {
+    static_assert(SA == SA_INTERP || SA == SA_BACKSOLVE, "augmented states only");
+    constexpr int D = Fam::D, P = Fam::P, L = (SA == SA_INTERP) ? D + P : 2 * D + P, YO = D + P;
+    const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = gi < a.N;
+    const int64_t i = active ? gi : a.N - 1;
+    const int64_t N = a.N;
+    double p[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+    FwdDense<D> sol{a.ft, a.fu, a.fk, N, i, a.fn[i]};
+    sol.cur = sol.n - 1;
+    double z[L], zn[L], f0[L], k1[L], k2[L], k3[L], f1[L], fnr[L], tmp[L], dT[L];
+    double Wl[D][D], Wy[D][D], yj[D], lamj[D];            // Jacobian point of the current step (y, lam at t)
+    int pivl[D], pivy[D];
+#pragma unroll
+    for (int c = 0; c < L; c++) { z[c] = 0.0; dT[c] = 0.0; }
+    auto rhs = [&](double tt, const double* x, double* dx) {
+        double y[D], dg[P];
+        if (SA == SA_BACKSOLVE) {
+#pragma unroll
+            for (int j = 0; j < D; j++) y[j] = x[YO + j];
+        } else sol.eval(tt, true, y, nullptr);
+        Fam::vjp_u(y, p, x, dx);
+        Fam::vjp_p(y, p, x, dg);
+#pragma unroll
+        for (int j = 0; j < D; j++) dx[j] = -dx[j];
+#pragma unroll
+        for (int q = 0; q < P; q++) dx[D + q] = -dg[q];
+        if (SA == SA_BACKSOLVE) Fam::f(y, p, dx + YO);
+    };
+    double hd = 0.0;                                     // hs * d of the current step
+    auto solveW = [&](double* b) {
+        double dg[P];
+        if (SA == SA_BACKSOLVE) {
+            lu_solve<D>(Wy, pivy, b + YO);
+            double dJ[D][D];
+            Fam::djac(p, b + YO, dJ);
+#pragma unroll
+            for (int r = 0; r < D; r++) {
+                double s = 0;
+#pragma unroll
+                for (int c = 0; c < D; c++) s += dJ[c][r] * lamj[c];
+                b[r] -= hd * s;
+            }
+        }
+        lu_solve<D>(Wl, pivl, b);
+        Fam::vjp_p(yj, p, b, dg);
+#pragma unroll
+        for (int q = 0; q < P; q++) b[D + q] -= hd * dg[q];
+        if (SA == SA_BACKSOLVE) {
+            Fam::dvjp_p(yj, p, b + YO, lamj, dg);
+#pragma unroll
+            for (int q = 0; q < P; q++) b[D + q] -= hd * dg[q];
+        }
+    };
+    const double T = a.t1, t0 = a.t0;
+    double t = T;
+    int cur = a.K - 1, ck = sol.n;
+    bool fsal_ok = false, failed = false;
+    const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
+    if (SA == SA_BACKSOLVE) {
+#pragma unroll
+        for (int j = 0; j < D; j++) z[YO + j] = a.fu[((int64_t)sol.n * D + j) * N + i];     // y(T) = sol.u[end]
+    }
+    auto ckpt_if_at = [&](double tt) {                   // Backsolve checkpoint callback: y <- sol(t) (runs before the loss jump)
+        if (SA != SA_BACKSOLVE || !ckpt_on) return;
+        const double tol = EPS100 * fmax(fabs(tt), 1.0);
+        if (every) {
+            while (ck >= 0 && sol.T(ck) > tt + tol) ck--;
+            if (ck >= 0 && fabs(sol.T(ck) - tt) <= tol) {
+#pragma unroll
+                for (int j = 0; j < D; j++) z[YO + j] = a.fu[((int64_t)ck * D + j) * N + i];
+                fsal_ok = false;
+            }
+        } else if (cur >= 0 && fabs(a.saveat[cur] - tt) <= tol) {
+            double y[D];
+            sol.eval(a.saveat[cur], true, y, nullptr);
+#pragma unroll
+            for (int j = 0; j < D; j++) z[YO + j] = y[j];
+            fsal_ok = false;
+        }
+    };
+    auto jump_if_at = [&](double tt) {
+        while (cur >= 0 && fabs(a.saveat[cur] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
+            if (!((a.flags & 1u) && cur == 0 && SA != SA_BACKSOLVE)) {
+                if (COST == COST_EXPLICIT) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[j] += a.dLdu[((int64_t)cur * D + j) * N + i];
+                } else {
+                    double y[D];
+                    if (SA == SA_BACKSOLVE) {
+#pragma unroll
+                        for (int j = 0; j < D; j++) y[j] = z[YO + j];
+                    } else sol.eval(a.saveat[cur], true, y, nullptr);
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[j] += a.cost_a[j] * y[j] + a.cost_b[j];
+                }
+            }
+            cur--; fsal_ok = false;
+        }
+    };
+    ckpt_if_at(t);
+    jump_if_at(t);
+    double h = -1e-4 * (T - t0);
+    long iters = 0;
+    while (t > t0 && sol.n > 0) {
+        if (++iters > 50000000L) { failed = true; break; }
+        double tstop = t0;
+        if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
+        if (SA == SA_BACKSOLVE && ckpt_on && every) {            // every forward knot is a tstop of the reverse solve
+            int c2 = ck;
+            while (c2 >= 0 && sol.T(c2) >= t - EPS100 * fmax(fabs(t), 1.0)) c2--;
+            if (c2 >= 0 && sol.T(c2) > tstop) tstop = sol.T(c2);
+        }
+        double tn = tstop_snap(t + h, tstop);
+        if (tn < tstop) tn = tstop;
+        const double hs = tn - t;
+        hd = hs * ROS_D;
+        if (!fsal_ok) rhs(t, z, f0);
+        {   // Jacobian blocks and the time derivative at (t, z)
+            double yd[D], J[D][D], dJ[D][D], dg[P];
+            if (SA == SA_BACKSOLVE) {
+#pragma unroll
+                for (int j = 0; j < D; j++) { yj[j] = z[YO + j]; yd[j] = 0.0; }
+            } else sol.eval(t, true, yj, yd);
+#pragma unroll
+            for (int j = 0; j < D; j++) lamj[j] = z[j];
+            Fam::jac(yj, p, J);
+#pragma unroll
+            for (int r = 0; r < D; r++)
+#pragma unroll
+                for (int c = 0; c < D; c++) { Wl[r][c] = (r == c ? 1.0 : 0.0) + hd * J[c][r]; Wy[r][c] = (r == c ? 1.0 : 0.0) - hd * J[r][c]; }
+            if (SA == SA_INTERP) {
+                Fam::djac(p, yd, dJ);
+                Fam::dvjp_p(yj, p, yd, lamj, dg);
+#pragma unroll
+                for (int r = 0; r < D; r++) {
+                    double s = 0;
+#pragma unroll
+                    for (int c = 0; c < D; c++) s -= dJ[c][r] * lamj[c];
+                    dT[r] = s;
+                }
+#pragma unroll
+                for (int q = 0; q < P; q++) dT[D + q] = -dg[q];
+            }
+        }
+        if (!lu_factor<D>(Wl, pivl) || (SA == SA_BACKSOLVE && !lu_factor<D>(Wy, pivy))) { failed = true; break; }
+#pragma unroll
+        for (int c = 0; c < L; c++) k1[c] = f0[c] + hd * dT[c];
+        solveW(k1);
+#pragma unroll
+        for (int c = 0; c < L; c++) tmp[c] = z[c] + 0.5 * hs * k1[c];
+        rhs(t + 0.5 * hs, tmp, f1);
+#pragma unroll
+        for (int c = 0; c < L; c++) k2[c] = f1[c] - k1[c];
+        solveW(k2);
+#pragma unroll
+        for (int c = 0; c < L; c++) { k2[c] += k1[c]; zn[c] = z[c] + hs * k2[c]; }
+        rhs(t + hs, zn, fnr);
+#pragma unroll
+        for (int c = 0; c < L; c++) k3[c] = fnr[c] - ROS_E32 * (k2[c] - f1[c]) - 2 * (k1[c] - f0[c]) + hd * dT[c];
+        solveW(k3);
+        double e2 = 0;
+#pragma unroll
+        for (int c = 0; c < L; c++) {
+            const double e = hs / 6.0 * (k1[c] - 2 * k2[c] + k3[c]);
+            const double sc = a.abstol + a.reltol * fmax(fabs(z[c]), fabs(zn[c]));
+            e2 += (e / sc) * (e / sc);
+        }
+        const double EEst = sqrt(e2 / L);
+        if (!isfinite(EEst)) { failed = true; break; }           // e.g. Backsolve blowing up backwards on a stiff problem
+        const double q = step_factor_I(EEst);
+        if (EEst > 1.0) { h = hs / q; fsal_ok = true; continue; }
+        h = hs / q;
+#pragma unroll
+        for (int c = 0; c < L; c++) { z[c] = zn[c]; f0[c] = fnr[c]; }
+        fsal_ok = true;
+        t = tn;
+        ckpt_if_at(t);
+        jump_if_at(t);
+    }
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    if (active) {
+#pragma unroll
+        for (int j = 0; j < D; j++) a.du0[(int64_t)j * N + i] = failed ? qnan : z[j];
+    }
+    double out[P];
+#pragma unroll
+    for (int q = 0; q < P; q++) out[q] = failed ? qnan : z[D + q];
+    if (SHARED_P) {
+        if (!active) {
+#pragma unroll
+            for (int q = 0; q < P; q++) out[q] = 0.0;
+        }
+        reduce_dp<P>(out, a.partials, a.dp, a.ticket);
+    } else if (active) {
+#pragma unroll
+        for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = out[q];
     }
 }
 

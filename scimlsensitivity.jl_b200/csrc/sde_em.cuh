@@ -27,7 +27,7 @@ struct SdeRevArgs {
     const double* ckpt; const double* p; const double* dLdu; const int32_t* save_of_step;
     double* du0; double* dp_members; double* partials; double* dp; unsigned int* ticket;
     const double* noise;      // [S][M][N] or null (regenerate)
-    int64_t N; int32_t S; double h; double cost_a, cost_b; uint32_t flags; uint64_t seed; int64_t traj_offset;
+    int64_t N; int32_t S; double h; double cost_a[4], cost_b[4]; uint32_t flags; uint64_t seed; int64_t traj_offset;
 };
 struct SdeNoiseArgs { double* out; int64_t N; int32_t S; double h; uint64_t seed; int64_t traj_offset; int32_t m; };
 
@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(512) sde_backsolve_kernel(SdeRevArgs a) {
                 for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);
             } else {
 #pragma unroll
-                for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a, y[j], a.cost_b);
+                for (int j = 0; j < D; j++) lam[j] += fma(a.cost_a[j], y[j], a.cost_b[j]);
             }
         }
         if (n == 0) break;

@@ -25,12 +25,12 @@ struct T5aArgs {
     double* ftT; double* frecT;                                   // member-major copy of the forward dense solution: [N][MAXS+1], [N][MAXS][FWP] = (u[D], k[7][D])
     double* qseg; double* qkey; int32_t maxseg;
     int64_t N; int32_t K; int32_t maxs;
-    double t0, t1, dt0, abstol, reltol, quad_abstol, quad_reltol, cost_a, cost_b;
+    double t0, t1, dt0, abstol, reltol, quad_abstol, quad_reltol, cost_a[4], cost_b[4];
     uint32_t flags;
     // preset-time events u <- scale .* u + shift (the hybrid-system adjoint of src/callback_tracking.jl:232-480 for the
     // affine affect family, save_positions = (false, false)): same events for every member, times ascending in (t0, t1)
     int32_t nev; const double* ev_t; const double* ev_s; const double* ev_c;      // [E], [E][D], [E][D]
-    double cont_a, cont_b;  // flags bit3: continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u), dlam -= dgdu_continuous(y) (accumulate_cost!)
+    double cont_a[4], cont_b[4];  // flags bit3: continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u), dlam -= dgdu_continuous(y) (accumulate_cost!)
     const double* ev_ps; const double* ev_pc;     // [E][P] or null: parameter-changing affect p <- ps .* p + pc (reset_p of the reference)
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         for (int j = 0; j < D; j++) dx[j] = -dx[j];
         if (a.flags & 8u) {                                          // src/derivative_wrappers.jl:1411-1442
 #pragma unroll
-            for (int j = 0; j < D; j++) dx[j] -= a.cont_a * y[j] + a.cont_b;
+            for (int j = 0; j < D; j++) dx[j] -= a.cont_a[j] * y[j] + a.cont_b[j];
         }
         if (SA == SA_INTERP || SA == SA_BACKSOLVE) {
             double dg[P];
@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
                     } else
                     sol.eval(a.saveat[cur], true, y);
 #pragma unroll
-                    for (int j = 0; j < D; j++) z[j] += a.cost_a * y[j] + a.cost_b;
+                    for (int j = 0; j < D; j++) z[j] += a.cost_a[j] * y[j] + a.cost_b[j];
                 }
             }
             cur--; fsal_ok = false;

@@ -6,7 +6,7 @@ is in libb200adj.so.
 import numpy as np
 
 from . import _lib
-from .problems import FAMILIES, AffineCost
+from .problems import FAMILIES, AffineCost, ParamAffine
 
 
 def _is_torch(x):
@@ -29,7 +29,8 @@ class DeviceEnsemble:
         cfg.abstol, cfg.reltol, cfg.quad_abstol, cfg.quad_reltol = abstol, reltol, quad_abstol, quad_reltol
         cfg.shared_p, cfg.buffers_on_device, cfg.device = int(shared_p), int(on_device), int(device)
         if isinstance(cost, AffineCost):
-            cfg.cost_kind, cfg.cost_a, cfg.cost_b = _lib.COST["affine"], float(cost.a), float(cost.b)
+            cfg.cost_kind = _lib.COST["affine"]
+            cfg.cost_a, cfg.cost_b = (float(cost.a), float(cost.b)) if cost.is_scalar else (0.0, 0.0)
         else:
             cfg.cost_kind = _lib.COST["explicit"]
         cfg.seed, cfg.traj_offset = int(seed), int(traj_offset)
@@ -61,6 +62,8 @@ class DeviceEnsemble:
         # the forward pass keeps the create-time save table; set_reverse(t=...) only re-targets the reverse pass
         self.fwd_saveat, self.fwd_K = self.saveat.copy(), len(self.saveat)
         self.handle = _lib.Handle(cfg, self.saveat)
+        if isinstance(cost, AffineCost) and not cost.is_scalar:
+            self.handle.set_cost_family(0, np.broadcast_to(np.asarray(cost.a, dtype=np.float64), (d,)), np.broadcast_to(np.asarray(cost.b, dtype=np.float64), (d,)))
         self._keep = []
         self.pin_outputs, self._pinned = bool(pin_outputs), {}
         if self.on_device:
@@ -144,8 +147,9 @@ class DeviceEnsemble:
         self.handle.set_events(times, scale, shift, pscale, pshift)
         self.events = (times, scale, shift, pscale, pshift)
 
-    def set_reverse(self, sensealg, cost=None, no_start=False, checkpointing=True, ckpt_every_step=False, t=None):
-        """Re-target the next reverse pass (sensealg / cost / save times) without re-running the forward pass."""
+    def set_reverse(self, sensealg, cost=None, no_start=False, checkpointing=True, ckpt_every_step=False, t=None, dgdp=None):
+        """Re-target the next reverse pass (sensealg / cost / save times) without re-running the forward pass.
+        dgdp: ParamAffine, the parameter part of the discrete cost (dgdp_discrete)."""
         flags = 0
         if no_start:
             flags |= _lib.FLAG_NO_START
@@ -153,11 +157,16 @@ class DeviceEnsemble:
             flags |= _lib.FLAG_NO_CHECKPOINTING
         if ckpt_every_step:
             flags |= _lib.FLAG_CKPT_EVERY_STEP
+        vec = isinstance(cost, AffineCost) and not cost.is_scalar
         if isinstance(cost, AffineCost):
-            ck, a, b = _lib.COST["affine"], float(cost.a), float(cost.b)
+            ck, a, b = (_lib.COST["affine"], 0.0, 0.0) if vec else (_lib.COST["affine"], float(cost.a), float(cost.b))
         else:
             ck, a, b = _lib.COST["explicit"], 0.0, 0.0
         self.handle.set_reverse_options(_lib.SA[sensealg], ck, a, b, flags, t)
+        if vec or dgdp is not None:
+            bc = lambda x, n: None if x is None else np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (n,)))
+            self.handle.set_cost_family(0, bc(cost.a, self.d) if vec else None, bc(cost.b, self.d) if vec else None,
+                                        bc(getattr(dgdp, "c", None), self.P), bc(getattr(dgdp, "e", None), self.P))
         if t is not None:
             self.saveat = np.ascontiguousarray(t, dtype=np.float64)
             self.K = len(self.saveat)

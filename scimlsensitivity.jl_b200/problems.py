@@ -124,19 +124,37 @@ class EnsembleSolution:
 
 @dataclass(frozen=True)
 class AffineCost:
-    """dgdu_discrete(out, u, p, t, i) = a*u + b evaluated in-kernel; `dg(out,u,p,t,i) = out .= u .- 2`
-    (test/Core3/adjoint.jl:1169-1171) is AffineCost(1.0, -2.0).  Loss = sum_k sum_j (a/2 u^2 + b u)."""
-    a: float = 0.0
-    b: float = 1.0
+    """dgdu_discrete(out, u, p, t, i) = a .* u .+ b evaluated in-kernel (a, b scalars or one entry per state component);
+    `dg(out,u,p,t,i) = out .= u .- 2` (test/Core3/adjoint.jl:1169-1171) is AffineCost(1.0, -2.0), the `out[1] = 2u[1];
+    out[2] = 0` of test/Core7/mixed_costs.jl:226-230 is AffineCost([2, 0], 0).  Loss = sum_k sum_j (a_j/2 u_j^2 + b_j u_j)."""
+    a: Any = 0.0
+    b: Any = 1.0
+
+    @property
+    def is_scalar(self):
+        return np.ndim(self.a) == 0 and np.ndim(self.b) == 0
+
+
+@dataclass(frozen=True)
+class ParamAffine:
+    """dgdp_discrete(out, u, p, t, i) / dgdp_continuous(out, u, p, t) = c .* p .+ e: the parameter part of the named cost
+    family (cost term sum_q c_q/2 p_q^2 + e_q p_q).  `out[1] = 1; out[2:4] .= 0` of test/Core7/mixed_costs.jl:50-56, 231-237
+    (g = u1^2 + p1) is ParamAffine(0, [1, 0, 0, 0])."""
+    c: Any = 0.0
+    e: Any = 0.0
 
 
 @dataclass(frozen=True)
 class QuadraticRunningCost:
-    """Continuous cost g(u, p, t) = a/2 |u|^2 + b sum(u): dgdu_continuous = a u + b, dgdp_continuous = 0, evaluated
-    in-kernel at every adjoint stage (accumulate_cost!, src/derivative_wrappers.jl:1411-1442;
-    test/Core7/mixed_costs.jl:19-110).  Loss contribution = integral of g over the time span."""
-    a: float = 0.0
-    b: float = 0.0
+    """Continuous cost g(u, p, t) = sum_j a_j/2 u_j^2 + b_j u_j (+ sum_q c_q/2 p_q^2 + e_q p_q): dgdu_continuous = a .* u + b,
+    dgdp_continuous = c .* p + e, evaluated in-kernel at every adjoint stage (accumulate_cost!,
+    src/derivative_wrappers.jl:1411-1442; test/Core7/mixed_costs.jl:19-110).  Pass it as `dgdu_continuous=` (with
+    `dgdp_continuous=ParamAffine(c, e)` if the cost depends on p) or alone as `g=` (both gradients derived from it, the
+    "without dgdu_continuous, dgdp_continuous" call of mixed_costs.jl:188-196).  Loss contribution = integral of g."""
+    a: Any = 0.0
+    b: Any = 0.0
+    c: Any = None
+    e: Any = None
 
 
 def saveat_to_times(saveat, tspan):

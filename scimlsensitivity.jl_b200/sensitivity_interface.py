@@ -8,7 +8,7 @@ src/sensitivity_interface.jl:503-507).  For an ensemble `du0` is [d, N]; with pe
 """
 import numpy as np
 
-from .problems import AdjointSensitivityParameterCompatibilityError, AffineCost, QuadraticRunningCost
+from .problems import AdjointSensitivityParameterCompatibilityError, AffineCost, ParamAffine, QuadraticRunningCost
 from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, GaussKronrodAdjoint, InterpolatingAdjoint,
                                      QuadratureAdjoint, sensealg_name)
 
@@ -47,12 +47,27 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
                                   "B200 path (SURVEY.md App. E): delegate to the reference implementation")
     if getattr(sol.engine, "events", None) is not None and isinstance(inner, QuadratureAdjoint):
         raise NotImplementedError("QuadratureAdjoint does not support callbacks")
-    if dgdp_continuous is not None or g is not None:
-        raise NotImplementedError("dgdp_continuous / g are not built on the B200 path (named cost families only)")
+    # cost functions are members of the NAMED cost family (the device evaluates them in-kernel): dgdu = a .* u + b,
+    # dgdp = c .* p + e.  `g` alone (no dgdu_continuous / dgdp_continuous) has both gradients derived from it, as the
+    # reference does by AD (src/derivative_wrappers.jl:1427-1440).
+    if g is not None:
+        if not isinstance(g, QuadraticRunningCost):
+            raise NotImplementedError("g must be a QuadraticRunningCost on the B200 path (named cost families only)")
+        if dgdu_continuous is None:
+            dgdu_continuous = g
+        if dgdp_continuous is None and (g.c is not None or g.e is not None):
+            dgdp_continuous = ParamAffine(0.0 if g.c is None else g.c, 0.0 if g.e is None else g.e)
     if dgdu_continuous is not None and not isinstance(dgdu_continuous, QuadraticRunningCost):
         raise NotImplementedError("dgdu_continuous must be a QuadraticRunningCost on the B200 path")
-    if dgdp_discrete is not None:
-        raise NotImplementedError("dgdp_discrete is not built on the B200 path yet")
+    if dgdp_continuous is None and isinstance(dgdu_continuous, QuadraticRunningCost) and (dgdu_continuous.c is not None or dgdu_continuous.e is not None):
+        dgdp_continuous = ParamAffine(0.0 if dgdu_continuous.c is None else dgdu_continuous.c, 0.0 if dgdu_continuous.e is None else dgdu_continuous.e)
+    for nm, fn in (("dgdp_discrete", dgdp_discrete), ("dgdp_continuous", dgdp_continuous)):
+        if fn is not None and not isinstance(fn, ParamAffine):
+            raise NotImplementedError(f"{nm} must be a ParamAffine on the B200 path (named cost families only)")
+    if dgdp_continuous is not None and dgdu_continuous is None:
+        dgdu_continuous = QuadraticRunningCost(0.0, 0.0)
+    if dgdp_discrete is not None and dgdu_discrete is None:
+        dgdu_discrete = AffineCost(0.0, 0.0)
     if dgdu_discrete is None and dgdu_continuous is None:
         # src/interpolating_adjoint.jl:321-326
         raise ValueError("Either `dgdu_discrete`, `dgdp_discrete`, `dgdu_continuous`, `dgdp_continuous`, or `g` "
@@ -75,9 +90,14 @@ def adjoint_sensitivities(sol, alg=None, *, sensealg=None, t=None, dgdu_discrete
     cost = dgdu_discrete if isinstance(dgdu_discrete, AffineCost) else None
     if dgdu_discrete is None:
         cost = AffineCost(0.0, 0.0)
-    eng.set_reverse(name, cost=cost, no_start=no_start, checkpointing=checkpointing, ckpt_every_step=every, t=ts)
+    eng.set_reverse(name, cost=cost, no_start=no_start, checkpointing=checkpointing, ckpt_every_step=every, t=ts, dgdp=dgdp_discrete)
     if dgdu_continuous is not None or getattr(eng, "_cont_on", False):
-        eng.handle.set_continuous_cost(dgdu_continuous is not None, getattr(dgdu_continuous, "a", 0.0), getattr(dgdu_continuous, "b", 0.0))
+        bc = lambda x, n: None if x is None else np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), (n,)))
+        if dgdu_continuous is None:
+            eng.handle.set_continuous_cost(False, 0.0, 0.0)
+        else:
+            eng.handle.set_cost_family(1, bc(dgdu_continuous.a, eng.d), bc(dgdu_continuous.b, eng.d),
+                                       bc(getattr(dgdp_continuous, "c", None), eng.P), bc(getattr(dgdp_continuous, "e", None), eng.P))
         eng._cont_on = dgdu_continuous is not None
     # adjoint solve tolerances are keywords of adjoint_sensitivities (src/sensitivity_interface.jl:432; used by the adaptive
     # steppers only); quadgk tolerances come from the sensealg (src/quadrature_adjoint.jl:517)

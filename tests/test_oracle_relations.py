@@ -527,3 +527,22 @@ def test_events_on_the_fixed_step_grid_oracle_only():
     for sa, every in (("interpolating", False), ("gauss", False), ("backsolve", True)):
         r = O.gradient(O.make_cfg("lv", sa, "tsit5_fixed", 1, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0), events=ev, ckpt_every_step=every), t, LV_U0, LV_P)
         assert np.max(np.abs(r["dp"] - gp)) < 1e-7 * np.max(np.abs(gp)), sa
+
+
+def test_mixed_cost_family_with_parameter_part_matches_finite_differences():
+    """test/Core7/mixed_costs.jl:19-330: cost g(u, p, t) = u1^2 + p1, continuous (integral over [0, 10]) and discrete (sum
+    over t = 1..9), dgdu = [2 u1, 0], dgdp = [1, 0, 0, 0]; the reference compares every sensealg with ForwardDiff of the cost.
+    Here: every sensealg of the oracle vs central differences of the oracle's own loss."""
+    ts = np.arange(1.0, 10.0)
+    A, E = [2.0, 0.0], [1.0, 0.0, 0.0, 0.0]
+    kw = dict(abstol=1e-12, reltol=1e-12, quad_abstol=1e-12, quad_reltol=1e-12)
+    for sa in SENSEALGS:
+        cfg = O.make_cfg("lv", sa, "tsit5_adaptive", 1, ts, 0.0, 10.0, cost_vec=(A, 0.0, None, E), **kw)
+        r = O.gradient(cfg, ts, LV_U0, LV_P)
+        gp = _fd_grad(lambda q: O.loss(cfg, ts, LV_U0, q)[0], LV_P)
+        gu = _fd_grad(lambda u: O.loss(cfg, ts, u, LV_P)[0], LV_U0)
+        assert np.allclose(r["dp"], gp, rtol=1e-7, atol=1e-6) and np.allclose(r["du0"].ravel(), gu.ravel(), rtol=1e-7, atol=1e-6), sa
+        cfgc = O.make_cfg("lv", sa, "tsit5_adaptive", 1, np.zeros(0), 0.0, 10.0, cost=("affine", 0.0, 0.0), cont_vec=(A, 0.0, None, E), **kw)
+        rc = O.gradient(cfgc, np.zeros(0), LV_U0, LV_P)
+        gpc = _fd_grad(lambda q: O.loss(cfgc, np.zeros(0), LV_U0, q)[0], LV_P)
+        assert np.allclose(rc["dp"], gpc, rtol=1e-7, atol=1e-6), sa
