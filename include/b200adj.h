@@ -186,6 +186,10 @@ int32_t b200adj_get_block_trace(void* handle, uint64_t* out, int32_t* nblocks);
  * these return B200ADJ_ERR_UNSUPPORTED and single-GPU use is unaffected. */
 int32_t b200adj_comm_unique_id(void* id_out /* 128 bytes */);
 int32_t b200adj_comm_init(void* handle, int32_t nranks, int32_t rank, const void* unique_id /* 128 bytes; NULL if nranks == 1 */);
+/* single-process host driving several GPUs: handles[0..n-1] (one per device) become ranks 0..n-1 of one communicator (the
+ * ncclCommInitRank calls are grouped, so one thread may issue this).  The per-gradient b200adj_reverse calls of the n handles
+ * must then be issued concurrently (one host thread per handle, e.g. Threads.@threads), as for any NCCL collective. */
+int32_t b200adj_comm_init_all(void** handles, int32_t n);
 /* in-place sum of `count` reals (cfg.dtype's ABI element type) over the ranks, on the handle's stream; device pointer */
 int32_t b200adj_comm_allreduce(void* handle, void* buf, int64_t count);
 int32_t b200adj_comm_size(void* handle, int32_t* nranks, int32_t* rank);

@@ -24,7 +24,7 @@ ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -
 EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_set_events", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg",
-           "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_allreduce", "b200adj_comm_size"]
+           "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_init_all", "b200adj_comm_allreduce", "b200adj_comm_size"]
 
 
 class B200AdjError(RuntimeError):
@@ -152,6 +152,8 @@ def load():
         lib.b200adj_comm_unique_id.restype = C.c_int32
         lib.b200adj_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         lib.b200adj_comm_init.restype = C.c_int32
+        lib.b200adj_comm_init_all.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+        lib.b200adj_comm_init_all.restype = C.c_int32
         lib.b200adj_comm_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         lib.b200adj_comm_allreduce.restype = C.c_int32
         lib.b200adj_comm_size.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
@@ -184,6 +186,15 @@ def comm_unique_id():
     if rc != 0:
         raise B200AdjError(rc, "b200adj_comm_unique_id failed (libnccl.so.2 not loadable?)")
     return buf.raw
+
+
+def comm_init_all(handles):
+    """One process driving several GPUs: the handles (one per device) become ranks 0..n-1 of one NCCL communicator.
+    Their reverse() calls must then run concurrently (one host thread per handle)."""
+    arr = (C.c_void_p * len(handles))(*[h._h for h in handles])
+    rc = load().b200adj_comm_init_all(arr, len(handles))
+    if rc != 0:
+        raise B200AdjError(rc, load().b200adj_last_error(handles[0]._h).decode())
 
 
 class Handle:

@@ -92,8 +92,8 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
                                       "(SURVEY.md App. E); delegate other callbacks to the reference implementation")
         if tuple(callback.save_positions) != (False, False):
             raise NotImplementedError("PresetTimeCallback: save_positions = (false, false) only")
-        if not (isinstance(alg, Tsit5) and alg.adaptive):
-            raise NotImplementedError("PresetTimeCallback: built for the adaptive Tsit5 stepper")
+        if not isinstance(alg, Tsit5):
+            raise NotImplementedError("PresetTimeCallback: built for the Tsit5 steppers (adaptive, or fixed step with event times on the dt grid)")
     kwargs.pop("tstops", None)                     # the callback's own times are the tstops
     if getattr(prob, "mass_matrix", None) is not None:
         raise NotImplementedError("mass matrices / DAEs are not supported on the B200 path")

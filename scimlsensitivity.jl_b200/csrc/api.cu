@@ -126,7 +126,7 @@ void free_all(Handle* h) {
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey);
     cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step); cudaFree(h->d_fwd_save_of_step); cudaFree(h->d_fwd_saveat);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
-    cudaFree(h->s_status); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
+    cudaFree(h->s_status); cudaFree(h->d_event_of_step); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -215,7 +215,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     } else {
         if (m != 0) { g_create_error = "ODE stepper with an SDE family"; return B200ADJ_ERR_INVALID; }
         if (cfg->sensealg < 0 || cfg->sensealg > 4) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
-        if (cfg->sensealg == B200ADJ_SA_GAUSSKRONROD && !ros) { g_create_error = "GaussKronrodAdjoint: built for the adaptive steppers (Tsit5 adaptive, Rosenbrock23)"; return B200ADJ_ERR_UNSUPPORTED; }
+        if (cfg->sensealg == B200ADJ_SA_GAUSSKRONROD && (mlp || cfg->dtype != B200ADJ_F64)) { g_create_error = "GaussKronrodAdjoint: F64, named ODE families"; return B200ADJ_ERR_UNSUPPORTED; }
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
         if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -387,7 +387,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     Handle* h = (Handle*)handle;
     b200adj_cfg& c = h->cfg;
     if (sensealg < 0 || sensealg > 4 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
-    if (sensealg == B200ADJ_SA_GAUSSKRONROD && !h->adaptive) { h->err = "GaussKronrodAdjoint: built for the adaptive steppers"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (sensealg == B200ADJ_SA_GAUSSKRONROD && (is_sde(c) || c.rhs_family == B200ADJ_FAM_MLP || c.dtype != B200ADJ_F64)) { h->err = "GaussKronrodAdjoint: F64, named ODE families"; return B200ADJ_ERR_UNSUPPORTED; }
     if (h->ckpt_every > 1 && sensealg != B200ADJ_SA_INTERPOLATING && sensealg != B200ADJ_SA_GAUSS) { h->err = "checkpoint_every > 1: InterpolatingAdjoint / GaussAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -476,7 +476,20 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
     Handle* h = (Handle*)handle;
     const b200adj_cfg& c = h->cfg;
     if (E < 0 || (E > 0 && (!times || !scale || !shift)) || ((pscale == nullptr) != (pshift == nullptr))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
-    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) { h->err = "events: built for the adaptive Tsit5 stepper"; return B200ADJ_ERR_UNSUPPORTED; }
+    const bool fixed = c.stepper == B200ADJ_ST_TSIT5_FIXED && c.rhs_family != B200ADJ_FAM_MLP && c.dtype == B200ADJ_F64;
+    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !fixed) { h->err = "events: built for the Tsit5 steppers (adaptive; fixed step in F64)"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (E > 0 && fixed && h->ckpt_every > 1) { h->err = "events together with checkpoint_every > 1 are not built"; return B200ADJ_ERR_UNSUPPORTED; }
+    std::vector<int32_t> eos;
+    if (fixed) {
+        // fixed step: every event time must be a grid point (the affect is applied between two steps)
+        eos.assign((size_t)h->S + 1, -1);
+        for (int e = 0; e < E; e++) {
+            const long long n = llround((times[e] - c.t0) / c.dt);
+            if (n <= 0 || n >= h->S || fabs(c.t0 + n * c.dt - times[e]) > 1e-9 * fmax(1.0, fabs(times[e]))) { h->err = "events: fixed-step Tsit5 needs event times on the dt grid, strictly inside (t0, t1)"; return B200ADJ_ERR_UNSUPPORTED; }
+            if (eos[n] != -1) { h->err = "events: duplicate event times"; return B200ADJ_ERR_INVALID; }
+            eos[n] = e;
+        }
+    }
     if (E > 0 && c.sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: Interpolating / Gauss / Backsolve (QuadratureAdjoint has no callback support)"; return B200ADJ_ERR_UNSUPPORTED; }
     for (int e = 0; e < E; e++)
         if (!(times[e] > c.t0 && times[e] < c.t1) || (e > 0 && !(times[e] > times[e - 1]))) { h->err = "events: times must be ascending and strictly inside (t0, t1)"; return B200ADJ_ERR_INVALID; }
@@ -498,6 +511,10 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
             CUDA_TRY(h, cudaMemcpy(h->d_ev_pc, pshift, (size_t)E * c.P * sizeof(double), cudaMemcpyHostToDevice));
         }
         h->nev = E;
+    }
+    if (fixed) {
+        if (!h->d_event_of_step) CUDA_TRY(h, cudaMalloc(&h->d_event_of_step, ((size_t)h->S + 1) * sizeof(int32_t)));
+        CUDA_TRY(h, cudaMemcpy(h->d_event_of_step, eos.data(), eos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
     return B200ADJ_OK;
 }
@@ -585,6 +602,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         rc = mlp_forward_dispatch(h, du0, dp, h->fwd_K > 0 ? dsaved : nullptr, dstatus);
     } else if (!is_sde(c) && c.dtype == B200ADJ_F32) {
         OdeFwdArgsT<float> a;
+        memset(&a, 0, sizeof(a));
         a.u0 = (const float*)du0; a.p = (const float*)dp; a.ckpt = (float*)h->d_ckpt; a.saved = h->fwd_K > 0 ? (float*)dsaved : nullptr;
         a.save_of_step = h->d_fwd_save_of_step; a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.ckpt_every = h->ckpt_every;
         cast_tables(h->tb, &a.tb);
@@ -595,8 +613,10 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         }
     } else if (!is_sde(c)) {
         OdeFwdArgs a;
+        memset(&a, 0, sizeof(a));
         a.u0 = du0; a.p = dp; a.ckpt = h->d_ckpt; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.save_of_step = h->d_fwd_save_of_step;
         a.status = dstatus; a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.ckpt_every = h->ckpt_every;
+        a.event_of_step = h->d_event_of_step; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc; a.nev = h->nev;
         switch (c.rhs_family) {
         case B200ADJ_FAM_LV: rc = launch_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_fwd<Lorenz>(h, a); break;
@@ -695,6 +715,9 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         }
     } else if (!is_sde(c)) {
         OdeRevArgs a;
+        memset(&a, 0, sizeof(a));
+        a.event_of_step = h->d_event_of_step; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc; a.nev = h->nev;
+        tsit5_weights(0.0, nullptr, a.Rpoly); a.hstep = c.dt;
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
         a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.trace = h->d_trace;

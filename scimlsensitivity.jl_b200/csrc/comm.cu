@@ -24,6 +24,8 @@ struct Nccl {
     int (*CommInitRank)(nccl_comm_t*, int, nccl_uid, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
     std::string err;
 };
@@ -42,6 +44,8 @@ Nccl* nccl() {
         n.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(n.lib, "ncclAllReduce");
         n.CommDestroy = (int (*)(nccl_comm_t))dlsym(n.lib, "ncclCommDestroy");
         n.GetErrorString = (const char* (*)(int))dlsym(n.lib, "ncclGetErrorString");
+        n.GroupStart = (int (*)())dlsym(n.lib, "ncclGroupStart");
+        n.GroupEnd = (int (*)())dlsym(n.lib, "ncclGroupEnd");
         if (!n.GetUniqueId || !n.CommInitRank || !n.AllReduce || !n.CommDestroy) { n.err = "libnccl: missing symbols"; n.lib = nullptr; }
     }
     return &n;
@@ -96,6 +100,31 @@ int32_t b200adj_comm_init(void* handle, int32_t nranks, int32_t rank, const void
     const int rc = n->CommInitRank(&comm, nranks, id, rank);
     if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (n->GetErrorString ? n->GetErrorString(rc) : "error"); return B200ADJ_ERR_CUDA; }
     h->nccl_comm = comm; h->nranks = nranks; h->rank = rank;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_comm_init_all(void** handles, int32_t n) {
+    // single-process hosts (one Julia / Python process driving all GPUs of the box): the n handles become ranks 0..n-1 of one
+    // communicator; the ncclCommInitRank calls are grouped so that one thread can issue them
+    if (!handles || n < 1) return B200ADJ_ERR_INVALID;
+    for (int i = 0; i < n; i++) if (!handles[i]) return B200ADJ_ERR_INVALID;
+    if (n == 1) { comm_release((Handle*)handles[0]); return B200ADJ_OK; }
+    Nccl* nc = nccl();
+    Handle* h0 = (Handle*)handles[0];
+    if (!nc->lib || !nc->GroupStart || !nc->GroupEnd) { h0->err = nc->err.empty() ? "libnccl: ncclGroupStart missing" : nc->err; return B200ADJ_ERR_UNSUPPORTED; }
+    nccl_uid id;
+    if (nc->GetUniqueId(&id) != 0) { h0->err = "ncclGetUniqueId failed"; return B200ADJ_ERR_CUDA; }
+    std::vector<nccl_comm_t> comms((size_t)n, nullptr);
+    for (int i = 0; i < n; i++) comm_release((Handle*)handles[i]);
+    int rc = nc->GroupStart();
+    for (int i = 0; i < n && rc == 0; i++) {
+        Handle* h = (Handle*)handles[i];
+        if (cudaSetDevice(h->cfg.device) != cudaSuccess) { rc = -1; break; }
+        rc = nc->CommInitRank(&comms[i], n, id, i);
+    }
+    const int rc2 = nc->GroupEnd();
+    if (rc != 0 || rc2 != 0) { h0->err = std::string("ncclCommInitRank (grouped): ") + (nc->GetErrorString ? nc->GetErrorString(rc ? rc : rc2) : "error"); return B200ADJ_ERR_CUDA; }
+    for (int i = 0; i < n; i++) { Handle* h = (Handle*)handles[i]; h->nccl_comm = comms[i]; h->nranks = n; h->rank = i; }
     return B200ADJ_OK;
 }
 

@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "families.cuh"
+#include "quadgk.cuh"
 
 namespace b200adj {
 
@@ -50,6 +51,9 @@ template <class R> struct OdeFwdArgsT {
     int64_t Npad;            // checkpoint row pitch: N rounded up to the block size (every block owns full 16B-aligned rows)
     int32_t S;
     int32_t ckpt_every;      // C: row m of ckpt holds u_{mC} (m < ceil(S/C)), row ceil(S/C) holds u_S; C = 1: every step
+    // preset-time events on the dt grid (EV kernels): event_of_step[n] = e when the affect u <- ev_s[e] .* u + ev_c[e]
+    // (and p <- ev_ps[e] .* p + ev_pc[e]) fires at t_n, else -1
+    const int32_t* event_of_step; const double* ev_s; const double* ev_c; const double* ev_ps; const double* ev_pc; int32_t nev;
     Tsit5TablesT<R> tb;
 };
 using OdeFwdArgs = OdeFwdArgsT<double>;
@@ -74,6 +78,9 @@ template <class R> struct OdeRevArgsT {
     uint32_t flags;          // bit0 no_start, bit1 no checkpointing (backsolve), bit2 ckpt every step, bit3 continuous cost
     R* adj_dense;       // SA_QUAD: [S][8][D][Npad] = (lambda at the start of reverse step n, ka'[0..6]) per step
     unsigned long long* trace;   // optional [gridDim][3] = (smid, globaltimer at block start, at block end) or null
+    const int32_t* event_of_step; const double* ev_s; const double* ev_c; const double* ev_ps; const double* ev_pc; int32_t nev;   // EV kernels
+    R Rpoly[7][4];               // SA_GK: dense-output polynomials b_j(theta) = sum_m Rpoly[j][m] theta^(m+1)
+    R hstep;                     // SA_GK: the step size
     Tsit5TablesT<R> tb;
 };
 using OdeRevArgs = OdeRevArgsT<double>;
@@ -142,7 +149,19 @@ __device__ __forceinline__ void named_bar_arrive(int id, int nthreads) { asm vol
 // Forward ensemble solve, fixed-step Tsit5, writes every step's state (the dense solution is NOT stored: the
 // reverse pass recomputes the 6 stages from u_n, 24 B/step instead of 192 B/step of HBM traffic).
 // ------------------------------------------------------------------------------------------------------------
-template <class Fam, bool SHARED_P, class R = double>
+// parameters in force after the first `upto` events (p0 = the caller's parameters of this member)
+template <int P, class R>
+__device__ __forceinline__ void fixed_event_params(const double* ev_ps, const double* ev_pc, int upto, const R* p0, R* p) {
+#pragma unroll
+    for (int q = 0; q < P; q++) p[q] = p0[q];
+    if (!ev_ps) return;
+    for (int e = 0; e < upto; e++) {
+#pragma unroll
+        for (int q = 0; q < P; q++) p[q] = (R)ev_ps[e * P + q] * p[q] + (R)ev_pc[e * P + q];
+    }
+}
+
+template <class Fam, bool SHARED_P, class R = double, bool EV = false>
 __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constant__ OdeFwdArgsT<R> a) {
     constexpr int D = Fam::D, P = Fam::P;
     const int64_t gi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -170,6 +189,19 @@ __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constan
         tsit5_stage<D, 6>(a.tb, u, k, tmp);
 #pragma unroll
         for (int j = 0; j < D; j++) u[j] = tmp[j];
+        if (EV) {
+            // preset-time event at t_{n+1}: u <- s .* u + c, p <- ps .* p + pc (PresetTimeCallback, save_positions = (false,
+            // false)); the checkpoint and a coinciding save point record the POST-event state, FSAL is recomputed from it
+            const int e = a.event_of_step[n + 1];
+            if (e >= 0 && n + 1 < a.S) {
+#pragma unroll
+                for (int j = 0; j < D; j++) u[j] = (R)a.ev_s[e * D + j] * u[j] + (R)a.ev_c[e * D + j];
+                if (a.ev_ps) {
+#pragma unroll
+                    for (int q = 0; q < P; q++) p[q] = (R)a.ev_ps[e * P + q] * p[q] + (R)a.ev_pc[e * P + q];
+                }
+            }
+        }
         Fam::f(u, p, k[0]);                      // FSAL: k7 of this step = k1 of the next
         // checkpoints: every step, or every C-th step plus the final state (CheckpointSolution grid of the reference,
         // src/interpolating_adjoint.jl:54-112: the reverse pass re-solves each segment from its left checkpoint)
@@ -264,7 +296,7 @@ static_assert(REV_CH_DEF <= 4, "hand-over barrier ids are keyed by step & 3: the
 template <int D, class R = double> constexpr size_t rev_smem_bytes(int block) { return (size_t)REV_NST * REV_CH * D * block * sizeof(R); }
 // SEG kernels (interval checkpointing): one re-solved segment of C states per member slot instead of the TMA stages
 template <int D, class R = double> constexpr size_t rev_seg_smem_bytes(int block, int C) { return (size_t)C * D * block * sizeof(R); }
-template <class Fam, int SA, bool SHARED_P, int COST, bool CONT, class R = double, bool SEG = false>
+template <class Fam, int SA, bool SHARED_P, int COST, bool CONT, class R = double, bool SEG = false, bool EV = false>
 __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_constant__ OdeRevArgsT<R> a) {
     constexpr int D = Fam::D, P = Fam::P;
     // BLOCK = member slots of this block.  When the slot count is not a multiple of 4 warps the SM's four sub-partitions
@@ -303,6 +335,26 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #pragma unroll
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * N + i);
 
+    if (EV && a.ev_ps) {               // the reverse solve starts on the last segment: parameters after all events
+        R p0[P];
+#pragma unroll
+        for (int q = 0; q < P; q++) p0[q] = p[q];
+        fixed_event_params<P>(a.ev_ps, a.ev_pc, a.nev, p0, p);
+    }
+    // reverse affect of a preset-time event at t_n (after the checkpoint reset and the loss jump of the same time):
+    // lam(tau-) = s .* lam(tau+), dG/dp scaled by ps, parameters of the segment below re-derived from the caller's p
+    auto reverse_affect = [&](int e, R* lam_, R* mu_, int64_t mi) {
+#pragma unroll
+        for (int j = 0; j < D; j++) lam_[j] *= (R)a.ev_s[e * D + j];
+        if (a.ev_ps) {
+#pragma unroll
+            for (int q = 0; q < P; q++) mu_[q] *= (R)a.ev_ps[e * P + q];
+            R p0[P];
+#pragma unroll
+            for (int q = 0; q < P; q++) p0[q] = SHARED_P ? __ldg(a.p + q) : __ldg(a.p + (int64_t)q * N + mi);
+            fixed_event_params<P>(a.ev_ps, a.ev_pc, e, p0, p);
+        }
+    };
     R lam[D], mu[P];                 // mu: dG/dp accumulator (Gauss quadrature sum, or the augmented state)
 #pragma unroll
     for (int j = 0; j < D; j++) lam[j] = 0.0;
@@ -347,6 +399,24 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             const int ks = a.save_of_step[n];
             if (ckpt_on && (every || ks >= 0)) { load_state<D>(a.ckpt + (int64_t)n * cstride, Npad, gi, y); fsal = false; }
             if (ks >= 0) { add_cotangent<D, COST>(a, ks, stride, N, i, y, lam); fsal = false; }
+            if (EV) {
+                const int e = a.event_of_step[n];
+                if (e >= 0 && n > 0) {
+                    reverse_affect(e, lam, mu, i);
+                    // y(tau-): the forward step below the event, re-solved from its checkpoint with the pre-event parameters
+                    // (the reference keeps it as `uleft` of the tracked affect)
+                    R ub[D], kk[7][D], tt_[D];
+                    load_state<D>(a.ckpt + (int64_t)(n - 1) * cstride, Npad, gi, ub);
+                    Fam::f(ub, p, kk[0]);
+                    tsit5_stage<D, 1>(tb, ub, kk, tt_); Fam::f(tt_, p, kk[1]);
+                    tsit5_stage<D, 2>(tb, ub, kk, tt_); Fam::f(tt_, p, kk[2]);
+                    tsit5_stage<D, 3>(tb, ub, kk, tt_); Fam::f(tt_, p, kk[3]);
+                    tsit5_stage<D, 4>(tb, ub, kk, tt_); Fam::f(tt_, p, kk[4]);
+                    tsit5_stage<D, 5>(tb, ub, kk, tt_); Fam::f(tt_, p, kk[5]);
+                    tsit5_stage<D, 6>(tb, ub, kk, y);
+                    fsal = false;
+                }
+            }
         }
     } else {
         R kf[7][D];                       // forward stages of the current step; kf[6] = f(u_{n+1}) carried over
@@ -409,6 +479,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             Fam::vjp_u(uhi, p, lam, ka[0]);    // y(T) = u_S
             add_continuous<D, CONT>(a, uhi, ka[0]);
         }
+        bool need_left = false;
         for (int n = a.S - 1; n >= 0; n--) {
             const int c = a.S - 1 - n, k = c / CH, jj = c % CH, st = k % NST;
             if (top) {
@@ -479,6 +550,15 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             tsit5_stage<D, 4>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[4]);
             tsit5_stage<D, 5>(tb, ulo, kf, tmp); Fam::f(tmp, p, kf[5]);
 
+            if (EV && need_left) {
+                // the step above ended with an event at t_{n+1}: the first adjoint stage sees the LEFT limit there -- the end
+                // state of this forward step (pre-event), its k7 = f(u-) and the adjoint derivative at (u-, lam-)
+                tsit5_stage<D, 6>(tb, ulo, kf, uhi);
+                Fam::f(uhi, p, kf[6]);
+                Fam::vjp_u(uhi, p, lam, ka[0]);
+                add_continuous<D, CONT>(a, uhi, ka[0]);
+                need_left = false;
+            }
 #ifdef REV_MIDSYNC
             __syncthreads();
 #endif
@@ -519,6 +599,31 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
 #pragma unroll
                     for (int j = 0; j < D; j++) row[((int64_t)(1 + s_) * D + j) * Npad] = ka[s_][j];
             }
+            if (SA == SA_GK) {
+                // GaussKronrodAdjoint on the fixed grid (src/gauss_adjoint.jl:820-825, IntegratingGKSumCallback): error-
+                // controlled G3/K7 quadrature of this step, bisected while sum|K - G| >= 1e-7; lam from the adjoint step's own
+                // dense output, y from the forward dense output, both at arbitrary theta.  Local time s in [h, 0] above t_n.
+                auto node = [&](double sj, double* out) {
+                    const R thf = (R)(sj / (double)a.hstep), tha = (R)1 - thf;
+                    R wf[7], wa[7], lq[D], yq[D], dgq[P];
+#pragma unroll
+                    for (int j = 0; j < 7; j++) {
+                        wf[j] = a.hstep * (thf * (a.Rpoly[j][0] + thf * (a.Rpoly[j][1] + thf * (a.Rpoly[j][2] + thf * a.Rpoly[j][3]))));
+                        wa[j] = a.hstep * (tha * (a.Rpoly[j][0] + tha * (a.Rpoly[j][1] + tha * (a.Rpoly[j][2] + tha * a.Rpoly[j][3]))));
+                    }
+                    tsit5_dense<D>(lam, ka, wa, lq);
+                    tsit5_dense<D>(ulo, kf, wf, yq);
+                    Fam::vjp_p(yq, p, lq, dgq);
+#pragma unroll
+                    for (int q = 0; q < P; q++) out[q] = -(double)dgq[q];
+                };
+                double accd[P];
+#pragma unroll
+                for (int q = 0; q < P; q++) accd[q] = 0.0;
+                integrate_gk_step<P, 3>(node, (double)a.hstep, 0.0, accd);
+#pragma unroll
+                for (int q = 0; q < P; q++) mu[q] += (R)accd[q];
+            }
             if (SA == SA_GAUSS) {
                 // 3-point Gauss-Legendre over this step, pre-jump lambda from the adjoint step's own dense output,
                 // y from the forward dense output: dp += (h/2) w_q (df/dp)'(y_q) lam_q  (gauss_adjoint.jl:745-759)
@@ -544,6 +649,10 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
             }
 #pragma unroll
             for (int j = 0; j < D; j++) uhi[j] = ulo[j];
+            if (EV) {
+                const int e = a.event_of_step[n];
+                if (e >= 0 && n > 0) { reverse_affect(e, lam, mu, member_i()); need_left = true; }
+            }
             if (top && n > 0) {                // hand the group on to the next warp of the ring
                 const int lane = (int)(threadIdx.x & 31);
                 R* m = s_mig + (size_t)(grp - q4) * NV * 32 + lane;

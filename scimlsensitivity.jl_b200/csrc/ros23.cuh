@@ -229,59 +229,6 @@ __device__ __forceinline__ void adj_rhs(const FwdDense<D>& sol, const double* p,
     for (int j = 0; j < D; j++) out[j] = -out[j];
 }
 
-// ---- GaussKronrodAdjoint: IntegratingGKSumCallback [UPSTREAM DiffEqCallbacks, restated; gauss_adjoint.jl:820-825].
-// After every accepted reverse step the integrand is integrated over [tprev, t] with a Gauss-Kronrod pair of
-// ORDER = div(alg_order + 1, 2) Gauss points (Tsit5: G3/K7, Rosenbrock23: G1/K3); if sum|K - G| >= 1e-7 the interval is
-// bisected and both halves are integrated (left first), otherwise K joins the running sum.  The recursion is an explicit
-// depth-first stack here, visiting the intervals in the recursion's order (same summation order as the oracle). ----
-template <int P, int ORDER, class NODE>
-__device__ __forceinline__ void integrate_gk_step(const NODE& node, double bl, double br, double* acc) {
-    constexpr int NP = 2 * ORDER + 1;
-    constexpr double X7[7] = {-0.960491268708020283423507092629080, -0.774596669241483377035853079956480, -0.405845151377397166906606412076961, 0.0,
-                              0.405845151377397166906606412076961, 0.774596669241483377035853079956480, 0.960491268708020283423507092629080};
-    constexpr double W7[7] = {0.104656226026467265193823857192073, 0.268488089868333440728569280666710, 0.401397414775962222905051818618432,
-                              0.450916538658474142345110087045571, 0.401397414775962222905051818618432, 0.268488089868333440728569280666710,
-                              0.104656226026467265193823857192073};
-    constexpr double G3[3] = {0.555555555555555555555555555555556, 0.888888888888888888888888888888889, 0.555555555555555555555555555555556};
-    constexpr double X3[3] = {-0.774596669241483377035853079956480, 0.0, 0.774596669241483377035853079956480};
-    constexpr double G1[1] = {2.0};
-    double sl[32], sr[32];
-    int sd[32], sp = 1;
-    sl[0] = bl; sr[0] = br; sd[0] = 0;
-    while (sp > 0) {
-        sp--;
-        const double l = sl[sp], r = sr[sp];
-        const int dep = sd[sp];
-        double K[P], G[P], v[P];
-#pragma unroll
-        for (int q = 0; q < P; q++) { K[q] = 0.0; G[q] = 0.0; }
-#pragma unroll
-        for (int i = 0; i < NP; i++) {
-            const double x = ORDER == 3 ? X7[i < 7 ? i : 0] : X3[i < 3 ? i : 0];
-            const double w = ORDER == 3 ? W7[i < 7 ? i : 0] : G3[i < 3 ? i : 0];          // K3 weights = the 3-point Gauss weights
-            node(0.5 * (r - l) * x + 0.5 * (l + r), v);
-#pragma unroll
-            for (int q = 0; q < P; q++) K[q] += w * v[q];
-            if (i & 1) {
-                const double g = ORDER == 3 ? G3[(i / 2) < 3 ? i / 2 : 0] : G1[0];
-#pragma unroll
-                for (int q = 0; q < P; q++) G[q] += g * v[q];
-            }
-        }
-        double err = 0.0;
-#pragma unroll
-        for (int q = 0; q < P; q++) { K[q] *= 0.5 * (r - l); G[q] *= 0.5 * (r - l); err += fabs(K[q] - G[q]); }
-        if (err < 1e-7 || dep >= 30) {
-#pragma unroll
-            for (int q = 0; q < P; q++) acc[q] += K[q];
-        } else {
-            const double mid = 0.5 * (l + r);
-            sl[sp] = mid; sr[sp] = r; sd[sp] = dep + 1; sp++;      // right half waits
-            sl[sp] = l; sr[sp] = mid; sd[sp] = dep + 1; sp++;      // left half next
-        }
-    }
-}
-
 template <class Fam, int SA, bool SHARED_P, int COST>
 __global__ void __launch_bounds__(256) ros23_reverse_kernel(RosArgs a) {
     constexpr int D = Fam::D, P = Fam::P;

@@ -132,8 +132,8 @@ def test_preset_time_callback_tables_and_host_side_rejections():
     with pytest.raises(NotImplementedError):          # extra saved points are not carried
         b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=True), b.EnsembleB200(), trajectories=2, saveat=ts,
                 callback=b.PresetTimeCallback([5.0], b.AffineAffect(1.0, 0.0), save_positions=(True, True)))
-    with pytest.raises(NotImplementedError):          # fixed-step stepper
-        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=False, dt=0.01), b.EnsembleB200(), trajectories=2, saveat=ts,
+    with pytest.raises(NotImplementedError):          # a stepper without an event path
+        b.solve(b.EnsembleProblem(prob), b.Rosenbrock23(), b.EnsembleB200(), trajectories=2, saveat=ts, abstol=1e-6, reltol=1e-6,
                 callback=b.PresetTimeCallback([5.0], b.AffineAffect(1.0, 0.0)))
 
 

@@ -1,4 +1,4 @@
-"""Preset-time events (DiscreteCallback / PresetTimeCallback) on the adaptive Tsit5 path: device vs oracle, and the
+"""Preset-time events (DiscreteCallback / PresetTimeCallback) on the Tsit5 paths (adaptive, and fixed step): device vs oracle, and the
 reference's own relations (test/Callbacks1/discrete_callbacks.jl:200-231): every sensealg agrees with differentiation
 through the solver, Backsolve == Interpolating == Gauss."""
 import os
@@ -106,8 +106,51 @@ def test_events_public_api_and_rejections():
     assert _rel(np.asarray(dp).reshape(-1), ref["dp"]) < 1e-7
     with pytest.raises(NotImplementedError):
         b.adjoint_sensitivities(sol, b.Tsit5(adaptive=True), sensealg=b.QuadratureAdjoint(), t=t, dgdu_discrete=b.AffineCost(0.0, 1.0))
-    with pytest.raises(NotImplementedError):
-        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=False, dt=0.01), b.EnsembleB200(), trajectories=3, saveat=t, callback=cb)
+    with pytest.raises(b.B200AdjError):      # fixed step: event times must lie on the dt grid
+        b.solve(b.EnsembleProblem(prob), b.Tsit5(adaptive=False, dt=0.01), b.EnsembleB200(), trajectories=3, saveat=t,
+                callback=b.PresetTimeCallback([5.005], b.AffineAffect([1.0, 1.0], [2.0, 0.0])))
     with pytest.raises(Exception):       # event time outside (t0, t1)
         eng = b.DeviceEnsemble("lv", "gauss", "tsit5_adaptive", 4, t, (0.0, 10.0), 0.0)
         eng.set_events([10.0], [[1.0, 1.0]], [[0.0, 0.0]])
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("sa,every", [("interpolating", False), ("gauss", False), ("gauss_kronrod", False), ("backsolve", True), ("backsolve", False)])
+def test_events_on_the_fixed_step_grid(case, sa, every):
+    """The same event cases on the FIXED-step Tsit5 path (event times are dt-grid points: 2.03 = 203 dt): EV instantiations of
+    tsit5_forward_kernel / tsit5_reverse_kernel against the oracle (test_oracle_relations.py pins the oracle's fixed-grid events
+    by finite differences through the hybrid solve)."""
+    ev = CASES[case]
+    N, dt = 70, 0.01
+    rng = np.random.default_rng(21)
+    u0 = 1.0 + 0.05 * rng.standard_normal((2, N))
+    p = np.array([1.5, 1.0, 3.0, 1.0])
+    t = np.arange(0.0, 10.0001, 0.5)
+    eng = b.DeviceEnsemble("lv", sa, "tsit5_fixed", N, t, (0.0, 10.0), dt, cost=b.AffineCost(0.0, 1.0), ckpt_every_step=every)
+    eng.set_events(*ev)
+    saved, status = eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    cfg = O.make_cfg("lv", sa, "tsit5_fixed", N, t, 0.0, 10.0, dt=dt, cost=("affine", 0.0, 1.0), ckpt_every_step=every, events=ev)
+    ref = O.gradient(cfg, t, u0, p)
+    assert (np.asarray(status) == 0).all()
+    assert _rel(saved, ref["saved"]) < 1e-10
+    tol = 1e-6 if sa == "gauss_kronrod" else 1e-8
+    assert _rel(du0, ref["du0"]) < tol and _rel(dp, ref["dp"]) < tol, (_rel(du0, ref["du0"]), _rel(dp, ref["dp"]))
+    if case == "set_single":
+        assert np.allclose(np.asarray(saved)[10, 0, :], 2.0, atol=1e-12)
+    eng.close()
+
+
+def test_fixed_step_events_through_the_public_api_per_member_parameters():
+    t = np.arange(0.0, 10.0001, 0.5)
+    N = 12
+    rng = np.random.default_rng(5)
+    u0 = 1.0 + 0.05 * rng.standard_normal((2, N))
+    p = np.array([1.5, 1.0, 3.0, 1.0])[:, None] * np.exp(0.02 * rng.standard_normal((4, N)))
+    cb = b.PresetTimeCallback([2.03, 5.1], [b.AffineAffect([1.0, 1.0], [2.0, 0.0]), b.AffineAffect(1.0, 0.0, p_scale=[2.0, 1.0, 0.5, 1.0], p_shift=[-0.5, 0.0, 0.1, 0.0])])
+    prob = b.EnsembleProblem(b.ODEProblem("lv", u0[:, 0], (0.0, 10.0), p[:, 0]), u0s=u0, ps=p)
+    sol = b.solve(prob, b.Tsit5(dt=0.01), b.EnsembleB200(), saveat=t, callback=cb)
+    du0, dp = b.adjoint_sensitivities(sol, b.Tsit5(dt=0.01), sensealg=b.InterpolatingAdjoint(), t=t, dgdu_discrete=b.AffineCost(0.0, 1.0))
+    cfg = O.make_cfg("lv", "interpolating", "tsit5_fixed", N, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0), shared_p=False, events=CASES["mixed"])
+    ref = O.gradient(cfg, t, u0, p)
+    assert _rel(du0, ref["du0"]) < 1e-8 and _rel(dp, ref["dp"]) < 1e-8

@@ -96,3 +96,51 @@ def test_lorenz_ros23_nonstiff_and_public_api():
         assert _rel(du0, ref["du0"]) < 1e-7 and _rel(dp.ravel(), ref["dp"]) < (1e-5 if name == "quadrature" else 1e-7)
         res[name] = dp.ravel()
     assert _rel(res["gauss"], res["quadrature"]) < 1e-2
+
+
+@pytest.mark.parametrize("sensealg", ["interpolating", "backsolve"])
+@pytest.mark.parametrize("family", ["lv", "lorenz"])
+def test_rosenbrock23_on_the_augmented_adjoint_states(family, sensealg):
+    """InterpolatingAdjoint z = [lam; mu] and BacksolveAdjoint z = [lam; mu; y] integrated by Rosenbrock23 on the device (the
+    reference runs its stiff-solver matrix over all sensealgs, test/Core2/stiff_adjoints.jl:204-252, agreement rtol 1e-2):
+    block-triangular W-solves on the device against the oracle's dense LU of the full augmented Jacobian."""
+    N = 96
+    rng = np.random.default_rng(12)
+    if family == "lv":
+        T, u0, p = 5.0, np.exp(0.05 * rng.standard_normal((2, N))), np.array([1.5, 1.0, 3.0, 1.0])
+    else:
+        T, u0, p = 1.0, np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N)), np.array([10.0, 28.0, 8.0 / 3.0])
+    t = np.linspace(0.0, T, 11)
+    kw = dict(abstol=1e-8, reltol=1e-8)
+    for every in ((False, True) if sensealg == "backsolve" else (False,)):
+        eng = b.DeviceEnsemble(family, sensealg, "rosenbrock23", N, t, (0.0, T), 0.0, cost=b.AffineCost(1.0, -0.5), ckpt_every_step=every, **kw)
+        saved, status = eng.forward(u0, p)
+        du0, dp = eng.reverse()
+        ref = O.gradient(O.make_cfg(family, sensealg, "rosenbrock23", N, t, 0.0, T, cost=("affine", 1.0, -0.5), ckpt_every_step=every, **kw), t, u0, p)
+        assert int(np.asarray(status).sum()) == 0 and np.abs(np.asarray(saved) - ref["saved"]).max() < 1e-9
+        assert _rel(du0, ref["du0"]) < 1e-6 and _rel(dp, ref["dp"]) < 1e-6, (every, _rel(du0, ref["du0"]), _rel(dp, ref["dp"]))
+        eng.close()
+    # the sensealgs agree with each other far inside the reference's rtol 1e-2
+    g = O.gradient(O.make_cfg(family, "gauss", "rosenbrock23", N, t, 0.0, T, cost=("affine", 1.0, -0.5), **kw), t, u0, p)
+    assert _rel(dp, g["dp"]) < 1e-3
+
+
+def test_rosenbrock23_interpolating_robertson_per_member_and_explicit_cotangent():
+    """The stiff case: Robertson with per-member rate constants, InterpolatingAdjoint (mu' = -F'lam inside the Rosenbrock
+    step), explicit cotangents; Backsolve on this problem blows up backwards (the reference's own warning, src/
+    sensitivity_algorithms.jl:212-228) and must fail loudly: NaN gradient, never a silent partial."""
+    N, T = 64, 100.0
+    rng = np.random.default_rng(13)
+    t = np.logspace(-2, 2, 10); t[-1] = T
+    u0 = np.repeat(np.array([[1.0], [0.0], [0.0]]), N, 1)
+    k = np.array([0.04, 3e7, 1e4])[:, None] * np.exp(0.05 * rng.standard_normal((3, N)))
+    dL = rng.standard_normal((10, 3, N))
+    kw = dict(abstol=1e-8, reltol=1e-8)
+    eng = b.DeviceEnsemble("robertson", "interpolating", "rosenbrock23", N, t, (0.0, T), 0.0, shared_p=False, max_steps=8192, **kw)
+    eng.forward(u0, k)
+    du0, dp = eng.reverse(dL)
+    ref = O.gradient(O.make_cfg("robertson", "interpolating", "rosenbrock23", N, t, 0.0, T, shared_p=False, **kw), t, u0, k, dLdu=dL)
+    assert _rel(du0, ref["du0"]) < 1e-6
+    err = np.abs(np.asarray(dp) - ref["dp"]) / np.abs(ref["dp"]).max(axis=1, keepdims=True)
+    assert err.max() < 1e-5, err.max()
+    eng.close()

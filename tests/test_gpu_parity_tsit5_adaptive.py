@@ -119,5 +119,30 @@ def test_gauss_kronrod_adjoint(family, stepper, shared_p):
     _, dpg = eng.reverse()
     assert _rel(dpg, dp) < 1e-3
     eng.close()
-    with pytest.raises(Exception):
-        b.DeviceEnsemble("lv", "gauss_kronrod", "tsit5_fixed", 8, t, (0.0, T), 0.01)
+    with pytest.raises(Exception):           # GaussKronrodAdjoint is an F64 path
+        b.DeviceEnsemble("lv", "gauss_kronrod", "tsit5_fixed", 8, t, (0.0, T), 0.01, dtype="f32")
+
+
+@pytest.mark.parametrize("family", ["lv", "lorenz"])
+@pytest.mark.parametrize("shared_p", [True, False])
+def test_gauss_kronrod_adjoint_fixed_step(family, shared_p):
+    """GaussKronrodAdjoint with fixed-step Tsit5: the G3/K7 rule with bisection inside tsit5_reverse_kernel<SA_GK> (general-theta
+    dense outputs of the adjoint and the forward step) vs the oracle; re-targeting the same handle to GaussAdjoint."""
+    N = 150
+    rng = np.random.default_rng(31)
+    if family == "lv":
+        T, dt, u0, p = 4.0, 0.05, np.exp(0.05 * rng.standard_normal((2, N))), np.array([1.5, 1.0, 3.0, 1.0])
+    else:
+        T, dt, u0, p = 1.0, 0.01, np.array([1.0, 0.0, 0.0])[:, None] + 0.1 * rng.standard_normal((3, N)), np.array([10.0, 28.0, 8.0 / 3.0])
+    if not shared_p:
+        p = p[:, None] * np.exp(0.02 * rng.standard_normal((len(p), N)))
+    t = np.linspace(0.0, T, 11)
+    eng = b.DeviceEnsemble(family, "gauss_kronrod", "tsit5_fixed", N, t, (0.0, T), dt, shared_p=shared_p, cost=b.AffineCost(1.0, -0.5))
+    eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    ref = O.gradient(O.make_cfg(family, "gauss_kronrod", "tsit5_fixed", N, t, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), shared_p=shared_p), t, u0, p)
+    assert _rel(du0, ref["du0"]) < 1e-9 and _rel(dp, ref["dp"]) < 1e-6
+    eng.set_reverse("gauss", cost=b.AffineCost(1.0, -0.5), t=t)
+    _, dpg = eng.reverse()
+    assert _rel(dpg, dp) < 1e-3
+    eng.close()
