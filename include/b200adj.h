@@ -59,8 +59,11 @@ enum { B200ADJ_COST_EXPLICIT = 0, B200ADJ_COST_AFFINE = 1 };
 
 #define B200ADJ_FLAG_TRACE              16u   /* record (smid, start, end) of every block of the reverse kernel      */
 #define B200ADJ_FLAG_NO_ROTATE          32u   /* tuning: launch exactly block_threads threads, no travelling warp groups */
+#define B200ADJ_FLAG_DENSE_FORWARD      64u   /* fixed-step Tsit5: keep the DENSE forward solution (k1..k7 per step, per member) so   */
+                                              /* that save / jump times may lie off the dt grid (chosen automatically when cfg.saveat */
+                                              /* has off-grid entries; set it to re-target the reverse pass to off-grid times later)  */
 /* flags fixed at create (the others can be changed per reverse pass by b200adj_set_reverse_options) */
-#define B200ADJ_CREATE_FLAGS (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE | B200ADJ_FLAG_NO_ROTATE)
+#define B200ADJ_CREATE_FLAGS (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE | B200ADJ_FLAG_NO_ROTATE | B200ADJ_FLAG_DENSE_FORWARD)
 
 /* error codes */
 #define B200ADJ_OK                 0

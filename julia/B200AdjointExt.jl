@@ -142,18 +142,19 @@ function b200_solve_adjoint(prob, alg, sensealg::B200Adjoint, U::AbstractMatrix{
     # every solver step is an output (:740-750) -- only the fixed-step grid is known before the solve
     ts = if saveat isa Number
         r = collect(t0:saveat:t1); r[end] == t1 || push!(r, t1); r
-    elseif isempty(saveat)
+    elseif saveat isa AbstractArray && isempty(saveat)
         adaptive && throw(B200Unsupported("adaptive solve without saveat: the step sequence is per member"))
         collect(t0:dt:t1)
     else
         sort(collect(Float64, saveat))
     end
-    no_start = !save_start && !isempty(ts) && ts[1] == t0                                    # concrete_solve.jl:962
-    if isempty(saveat) || saveat isa Number                                                  # :740-750 drop the end points
+    # end points: dropped only for an EMPTY saveat (:740-750) and for Backsolve, whose forward solve keeps the solver's own
+    # saving behaviour (:713-717); with a number or an array the output keeps t0 / t1 and `no_start` ignores the cotangent at t0
+    if (saveat isa AbstractArray && isempty(saveat)) || sensealg.inner isa BacksolveAdjoint
         save_start || (!isempty(ts) && ts[1] == t0 && popfirst!(ts))
         save_end || (!isempty(ts) && ts[end] == t1 && pop!(ts))
-        no_start = false
     end
+    no_start = !save_start && !isempty(ts) && ts[1] == t0                                    # concrete_solve.jl:962
     d, N = size(U)
     shared = p isa AbstractVector
     P = shared ? length(p) : size(p, 1)

@@ -1138,8 +1138,11 @@ static int adjoint_sde_member(const oracle_cfg* cfg, const family_t* F, const do
         int is_save = (cur >= 0 && fabs(ts[cur] - t) <= 1e-9 * fmax(1.0, fabs(t)));
         if (interp || (cfg->checkpointing && (cfg->backsolve_ckpt_every_step || is_save))) memcpy(z + d + P, us + (size_t)n * d, sizeof(double) * d);
         if (is_save) {
-            cost_grad(cfg, dL ? dL + (size_t)cur * d : NULL, z + d + P, gu);
-            for (int i = 0; i < d; i++) z[i] += gu[i];
+            /* no_start skips the jump of the first save time for every sensealg but Backsolve (src/adjoint_common.jl:761) */
+            if (!(cfg->no_start && cur == 0 && interp)) {
+                cost_grad(cfg, dL ? dL + (size_t)cur * d : NULL, z + d + P, gu);
+                for (int i = 0; i < d; i++) z[i] += gu[i];
+            }
             cur--;
         }
         if (n == 0) break;

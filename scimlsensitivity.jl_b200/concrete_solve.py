@@ -78,8 +78,11 @@ def clear_handle_cache():
 
 
 def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sensealg=None, save_start=True,
-          save_end=True, save_on=True, u0=None, p=None, **kwargs):
-    """Batched forward solve of an EnsembleProblem on the device; keeps the checkpoints for a later adjoint."""
+          save_end=True, save_on=True, u0=None, p=None, _rrule=False, **kwargs):
+    """Batched forward solve of an EnsembleProblem on the device; keeps the checkpoints for a later adjoint.
+    `_rrule=True` (set by _concrete_solve_adjoint): output times follow the reference's rrule, not the plain solver --
+    for the non-Backsolve adjoints save_start / save_end only drop end points when `saveat` is empty; with a number or an
+    array the output keeps t0 / t1 and `no_start` ignores the cotangent at t0 instead (src/concrete_solve.jl:713-770, 962)."""
     if not isinstance(eprob, EnsembleProblem):
         eprob = EnsembleProblem(eprob)
     ensemblealg = ensemblealg or EnsembleB200()
@@ -113,10 +116,12 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     if saveat is None and (isinstance(alg, Rosenbrock23) or (isinstance(alg, Tsit5) and alg.adaptive)):
         raise ValueError("adaptive solve on the B200 path needs explicit saveat times")
     ts = saveat_to_times(saveat if saveat is not None else _step_size(alg, kwargs), prob.tspan)
-    if not save_start and len(ts) and ts[0] == prob.tspan[0]:
-        ts = ts[1:]
-    if not save_end and len(ts) and ts[-1] == prob.tspan[1]:
-        ts = ts[:-1]
+    _inner = sensealg.inner if isinstance(sensealg, B200Adjoint) else sensealg
+    if not _rrule or saveat is None or isinstance(_inner, BacksolveAdjoint):
+        if not save_start and len(ts) and ts[0] == prob.tspan[0]:
+            ts = ts[1:]
+        if not save_end and len(ts) and ts[-1] == prob.tspan[1]:
+            ts = ts[:-1]
     on_device = ensemblealg.buffers_on_device if ensemblealg.buffers_on_device is not None else _is_torch(u0)
     rank, world = distributed.world()
     if ensemblealg.presharded:
@@ -176,7 +181,7 @@ def _concrete_solve_adjoint(prob, alg, sensealg, u0, p, originator=None, *args, 
     u0_shape = tuple(u0.shape)
     u0m = u0.reshape(d, -1)                                            # u0 any shape -> vec (:978)
     sol = solve(eprob, alg, ensemblealg or EnsembleB200(), saveat=saveat, sensealg=sensealg, save_start=save_start,
-                save_end=save_end, u0=u0m, p=p, **kwargs)
+                save_end=save_end, u0=u0m, p=p, _rrule=True, **kwargs)
     ts = sol.t
     only_end = len(ts) == 1 and ts[0] == eprob.prob.tspan[1]           # :716
     out_u = sol.u

@@ -101,6 +101,7 @@ T5aArgs t5a_args(Handle* h) {
                           0.5823571654525552, -0.45808210592918697, 0.015151515151515152};
     memcpy(a.A, A, sizeof(A)); memcpy(a.C, C, sizeof(C)); memcpy(a.BT, BT, sizeof(BT));
     tsit5_weights(0.0, nullptr, a.R);
+    if (h->fixed_dt) a.flags |= 16u;          // constant step, no error control (fixed-step Tsit5 on the dense framework)
     if (h->cont_on) { a.flags |= 8u; for (int j = 0; j < 4; j++) { a.cont_a[j] = h->cont_av[j]; a.cont_b[j] = h->cont_bv[j]; } }
     a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
     return a;
@@ -194,7 +195,20 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     int d, P, m;
     if (fam_dims(*cfg, &d, &P, &m)) { g_create_error = "rhs_family not built (MLP / unknown)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->d != d || cfg->P != P) { g_create_error = "cfg.d / cfg.P do not match rhs_family"; return B200ADJ_ERR_INVALID; }
-    const bool t5a = cfg->stepper == B200ADJ_ST_TSIT5_ADAPTIVE;
+    // Fixed-step Tsit5 with save times OFF the dt grid (or B200ADJ_FLAG_DENSE_FORWARD): the reference interpolates the dense
+    // forward solution at saveat (src/concrete_solve.jl:752-769) and the jump times become tstops of the fixed-dt reverse
+    // solve, whose grid then shifts.  That needs the dense forward solution (k1..k7 per step) and general-theta lookups: the
+    // per-member framework of the adaptive steppers run with a constant step (t5a kernels, T5A_FLAG_FIXED_DT).
+    bool dense_fixed = false;
+    if (cfg->stepper == B200ADJ_ST_TSIT5_FIXED && cfg->dtype == B200ADJ_F64 && cfg->rhs_family != B200ADJ_FAM_MLP && cfg->dt > 0) {
+        dense_fixed = (cfg->flags & B200ADJ_FLAG_DENSE_FORWARD) != 0;
+        for (int k = 0; k < cfg->K && cfg->saveat && !dense_fixed; k++) {
+            const long long n = llround((cfg->saveat[k] - cfg->t0) / cfg->dt);
+            if (fabs(cfg->t0 + n * cfg->dt - cfg->saveat[k]) > 1e-9 * fmax(1.0, fabs(cfg->saveat[k]))) dense_fixed = true;
+        }
+        if (dense_fixed && cfg->checkpoint_every > 1) { g_create_error = "checkpoint_every > 1 needs save times on the dt grid"; return B200ADJ_ERR_UNSUPPORTED; }
+    }
+    const bool t5a = cfg->stepper == B200ADJ_ST_TSIT5_ADAPTIVE || dense_fixed;
     const bool ros = cfg->stepper == B200ADJ_ST_ROSENBROCK23 || t5a;      // per-member adaptive framework
     if (cfg->N <= 0 || cfg->K < 0 || (cfg->K > 0 && !cfg->saveat) || (!ros && !(cfg->dt > 0)) || !(cfg->t1 > cfg->t0)) {
         g_create_error = "bad N/K/saveat/dt/tspan"; return B200ADJ_ERR_INVALID; }
@@ -217,7 +231,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (cfg->sensealg < 0 || cfg->sensealg > 4) { g_create_error = "bad sensealg"; return B200ADJ_ERR_INVALID; }
         if (cfg->sensealg == B200ADJ_SA_GAUSSKRONROD && (mlp || cfg->dtype != B200ADJ_F64)) { g_create_error = "GaussKronrodAdjoint: F64, named ODE families"; return B200ADJ_ERR_UNSUPPORTED; }
         if (cfg->stepper != B200ADJ_ST_TSIT5_FIXED && !ros) { g_create_error = "stepper not built on device yet"; return B200ADJ_ERR_UNSUPPORTED; }
-        if (ros && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
+        if (ros && !dense_fixed && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
     }
     if (ros) {
@@ -227,10 +241,18 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
                 g_create_error = "saveat must be ascending inside [t0, t1]"; return B200ADJ_ERR_INVALID; }
         }
         Handle* h = new Handle();
-        h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true; h->nk = t5a ? 7 : 2;
+        h->cfg = *cfg; h->cfg.m = 0; h->adaptive = true; h->nk = t5a ? 7 : 2; h->fixed_dt = dense_fixed;
         h->saveat.assign(cfg->saveat, cfg->saveat + cfg->K);
         h->cfg.saveat = h->saveat.data();
         h->maxs = cfg->max_steps > 0 ? cfg->max_steps : 4096;      // per-member step capacity (forward and dense reverse)
+        if (dense_fixed) {
+            // constant step: S forward steps; the reverse solve adds at most one clipped step per tstop (save times, events)
+            const long long S_ = llround((cfg->t1 - cfg->t0) / cfg->dt);
+            if (S_ < 1 || fabs(S_ * cfg->dt - (cfg->t1 - cfg->t0)) > 1e-9 * fmax(1.0, fabs(cfg->t1 - cfg->t0))) {
+                g_create_error = "(t1-t0) is not a whole number of dt steps"; delete h; return B200ADJ_ERR_UNSUPPORTED; }
+            const long long need = S_ + cfg->K + 64;
+            if (h->maxs < need) h->maxs = (int)(((need + 31) / 32) * 32);
+        }
         h->block = cfg->block_threads ? cfg->block_threads : 128;
         if (h->block < 32 || h->block > 256 || (h->block % 32)) { g_create_error = "block_threads must be a multiple of 32 in [32, 256] for Rosenbrock23"; delete h; return B200ADJ_ERR_INVALID; }
         h->grid = (int)((cfg->N + h->block - 1) / h->block);
@@ -444,7 +466,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
 int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, double b) {
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
-    if (enabled && ((h->adaptive && h->cfg.stepper != B200ADJ_ST_TSIT5_ADAPTIVE) || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
+    if (enabled && ((h->adaptive && h->cfg.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !h->fixed_dt) || is_sde(h->cfg) || h->cfg.rhs_family == B200ADJ_FAM_MLP)) {
         h->err = "continuous cost: built for the Tsit5 ODE paths (fixed step and adaptive)"; return B200ADJ_ERR_UNSUPPORTED; }
     h->cont_on = enabled != 0;
     for (int j = 0; j < 4; j++) { h->cont_av[j] = a; h->cont_bv[j] = b; }
@@ -476,8 +498,8 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
     Handle* h = (Handle*)handle;
     const b200adj_cfg& c = h->cfg;
     if (E < 0 || (E > 0 && (!times || !scale || !shift)) || ((pscale == nullptr) != (pshift == nullptr))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
-    const bool fixed = c.stepper == B200ADJ_ST_TSIT5_FIXED && c.rhs_family != B200ADJ_FAM_MLP && c.dtype == B200ADJ_F64;
-    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !fixed) { h->err = "events: built for the Tsit5 steppers (adaptive; fixed step in F64)"; return B200ADJ_ERR_UNSUPPORTED; }
+    const bool fixed = c.stepper == B200ADJ_ST_TSIT5_FIXED && c.rhs_family != B200ADJ_FAM_MLP && c.dtype == B200ADJ_F64 && !h->fixed_dt;
+    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !fixed && !h->fixed_dt) { h->err = "events: built for the Tsit5 steppers (adaptive; fixed step in F64)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (E > 0 && fixed && h->ckpt_every > 1) { h->err = "events together with checkpoint_every > 1 are not built"; return B200ADJ_ERR_UNSUPPORTED; }
     std::vector<int32_t> eos;
     if (fixed) {
@@ -578,7 +600,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
     }
     h->cur_p = dp;
     int rc = 0;
-    if (h->adaptive && c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE) {
+    if (h->adaptive && (c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE || h->fixed_dt)) {
         T5aArgs a = t5a_args(h);
         a.saveat = h->d_fwd_saveat; a.K = h->fwd_K;
         a.u0 = du0; a.p = dp; a.saved = h->fwd_K > 0 ? dsaved : nullptr; a.status = dstatus;
@@ -673,7 +695,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         ddu0 = h->s_du0; ddp = h->s_dp;
     }
     int rc = 0;
-    if (h->adaptive && c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE) {
+    if (h->adaptive && (c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE || h->fixed_dt)) {
         T5aArgs a = t5a_args(h);
         a.p = h->cur_p; a.dLdu = dL; a.du0 = ddu0; a.dp_members = ddp; a.dp = ddp;
         if (h->adj_abstol > 0) a.abstol = h->adj_abstol;
@@ -736,7 +758,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
         a.N = c.N; a.S = h->S; a.h = c.dt;
         for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; }
-        a.flags = ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) | ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
+        a.flags = ((c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u) | ((c.flags & B200ADJ_FLAG_NO_CHECKPOINTING) ? 2u : 0u) | ((c.flags & B200ADJ_FLAG_CKPT_EVERY_STEP) ? 4u : 0u);
         a.seed = c.seed; a.traj_offset = c.traj_offset;
         a.noise = h->noise_valid ? h->d_noise : nullptr;
         rc = sde_reverse_dispatch(h, a);

@@ -43,6 +43,7 @@ struct Handle {
     unsigned int* d_ticket = nullptr;
     int32_t* d_save_of_step = nullptr;
     // adaptive path: per-member dense forward / reverse solutions
+    bool fixed_dt = false;            // fixed-step Tsit5 routed to the dense per-member framework (off-grid save times)
     bool adaptive = false; int maxs = 0; int nk = 2;     // nk: dense-output stages stored per step (Rosenbrock23 2, Tsit5 7)
     double adj_abstol = 0, adj_reltol = 0;   // <= 0: use the forward tolerances
     // named cost family, per component (b200adj_set_cost_family; the scalar entry points broadcast):

@@ -169,7 +169,8 @@ __global__ void __launch_bounds__(512) sde_backsolve_kernel(SdeRevArgs a) {
         // callbacks at grid point n: checkpoint reset, then the loss jump
         const int ks = a.save_of_step[n];
         if (INTERP || (ckpt_on && (every || ks >= 0))) load_state<D>(a.ckpt + (int64_t)n * stride, N, i, y);
-        if (ks >= 0) {
+        // no_start skips the jump of the first save time for every sensealg but Backsolve (src/adjoint_common.jl:761)
+        if (ks >= 0 && !(INTERP && (a.flags & 1u) && ks == 0)) {
             if (COST == COST_EXPLICIT) {
 #pragma unroll
                 for (int j = 0; j < D; j++) lam[j] += __ldg(a.dLdu + (int64_t)ks * stride + (int64_t)j * N + i);

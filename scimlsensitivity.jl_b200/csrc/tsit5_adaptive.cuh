@@ -141,13 +141,19 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
         ksave++;
     }
     int ev = 0;                                   // next event ahead of t (event times are tstops of the forward solve)
+    const bool fixed = (a.flags & 16u) != 0;      // constant step dt0, no error control (fixed-step Tsit5 with off-grid save times)
     while (t < a.t1) {
         if (++iters > 10000000L || n >= a.maxs) { stat = 2; break; }
         bool last = false;
         const double tend = ev < a.nev ? a.ev_t[ev] : a.t1;
         if (t + h >= tend || fabs(t + h - tend) < 100 * 2.22e-16 * fabs(tend)) { h = tend - t; last = true; }
         t5_step<D>(a, rhs, t, h, u, k, un);
-        const double EEst = t5_error<D>(a, h, u, un, k);
+        const double EEst = fixed ? 0.0 : t5_error<D>(a, h, u, un, k);
+        if (!isfinite(EEst)) {                    // a trial step that overflowed: shrink (OrdinaryDiffEq does), give up below dtmin
+            h *= 0.25;
+            if (!(fabs(h) > 1e-14 * fmax(fabs(t), fabs(a.t1 - a.t0)))) { stat = 1; break; }
+            continue;
+        }
         const double q11 = pow(fmax(EEst, 1e-300), 7.0 / 50.0);
         double q = q11 / pow(qold, 2.0 / 25.0);
         q = fmax(1.0 / 10.0, fmin(5.0, q / 0.9));
@@ -193,7 +199,7 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
             t = tn; a.ft[(int64_t)(n + 1) * N + i] = t;
             n++;
             qold = fmax(EEst, 1e-4);
-            h = h / q;
+            h = fixed ? a.dt0 : h / q;            // constant step: back to dt after a step clipped at an event (dtcache)
         } else {
             h = h / fmin(5.0, q11 / 0.9);
         }
@@ -335,6 +341,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     ckpt_if_at(t);
     jump_if_at(t);
     double h = a.dt0 > 0 ? -a.dt0 : -1e-4 * (T - t0), qold = 1e-4;
+    const bool fixed = (a.flags & 16u) != 0;
     long iters = 0;
     while (t > t0 && sol.n > 0) {
         if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) { overflow = true; break; }
@@ -351,11 +358,16 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         const double hs = tn - t;
         if (!fsal_ok) rhs(t, z, k[0]);
         t5_step<L>(a, rhs, t, hs, z, k, zn);
-        const double EEst = t5_error<L>(a, hs, z, zn, k);
+        const double EEst = fixed ? 0.0 : t5_error<L>(a, hs, z, zn, k);
+        if (!isfinite(EEst)) {
+            h = 0.25 * hs; fsal_ok = true;
+            if (!(fabs(h) > 1e-14 * fmax(fabs(t), fabs(T - t0)))) { overflow = true; break; }
+            continue;
+        }
         const double q11 = pow(fmax(EEst, 1e-300), 7.0 / 50.0);
         const double q = fmax(0.1, fmin(5.0, q11 / pow(qold, 2.0 / 25.0) / 0.9));
         if (EEst > 1.0) { h = hs / fmin(5.0, q11 / 0.9); fsal_ok = true; continue; }
-        qold = fmax(EEst, 1e-4); h = hs / q;
+        qold = fmax(EEst, 1e-4); h = fixed ? -a.dt0 : hs / q;      // constant step: back to dt after a step clipped at a tstop
         if (SA == SA_GAUSS) {
             const double gx[3] = {-0.7745966692414834, 0.0, 0.7745966692414834};
             const double gw[3] = {0.5555555555555556, 0.8888888888888888, 0.5555555555555556};

@@ -31,17 +31,34 @@ def test_single_member_and_only_end_vector_cotangent():
 
 
 def test_save_start_save_end_false_and_saveat_number():
+    """The rrule keeps t0 and t1 in the output when saveat is a number or an array (src/concrete_solve.jl:718-735, 752-769);
+    save_start = false only makes the pullback ignore the cotangent at t0 (`no_start`, :962); with an EMPTY saveat the end
+    points are dropped (:740-750); BacksolveAdjoint keeps the plain solver's saving behaviour (:713-717)."""
     N = 7
     rng = np.random.default_rng(0)
     u0 = np.exp(0.1 * rng.standard_normal((2, N)))
     prob = b.ODEProblem("lv", u0[:, 0], (0.0, 1.0), P_LV)
     out, pullback = b._concrete_solve_adjoint(prob, b.Tsit5(dt=0.01), b.B200Adjoint(b.GaussAdjoint()), u0, P_LV, None,
                                               saveat=0.25, save_start=False, save_end=False)
-    assert np.allclose(out.t, [0.25, 0.5, 0.75]) and out.u.shape == (3, 2, N)
+    assert np.allclose(out.t, [0.0, 0.25, 0.5, 0.75, 1.0]) and out.u.shape == (5, 2, N)
     tang = pullback(2.0 * out.u)
-    cfg = O.make_cfg("lv", "gauss", "tsit5_fixed", N, out.t, 0.0, 1.0, dt=0.01, cost=("affine", 2.0, 0.0))
+    cfg = O.make_cfg("lv", "gauss", "tsit5_fixed", N, out.t, 0.0, 1.0, dt=0.01, cost=("affine", 2.0, 0.0), no_start=True)
     ref = O.gradient(cfg, out.t, u0, P_LV)
     assert _rel(tang[3], ref["du0"]) < 1e-9 and _rel(tang[4], ref["dp"]) < 1e-9
+    # an explicit array that contains t0: the same (sorted, t0 kept, its cotangent ignored)
+    out2, pullback2 = b._concrete_solve_adjoint(prob, b.Tsit5(dt=0.01), b.B200Adjoint(b.InterpolatingAdjoint()), u0, P_LV, None,
+                                                saveat=[0.5, 0.0, 1.0], save_start=False)
+    assert np.allclose(out2.t, [0.0, 0.5, 1.0])
+    tang2 = pullback2(np.ones_like(out2.u))
+    ref2 = O.gradient(O.make_cfg("lv", "interpolating", "tsit5_fixed", N, out2.t, 0.0, 1.0, dt=0.01, cost=("affine", 0.0, 1.0), no_start=True), out2.t, u0, P_LV)
+    assert _rel(tang2[3], ref2["du0"]) < 1e-9 and _rel(tang2[4], ref2["dp"]) < 1e-9
+    # Backsolve: the forward solve's own saving behaviour (end points dropped)
+    out3, _ = b._concrete_solve_adjoint(prob, b.Tsit5(dt=0.01), b.B200Adjoint(b.BacksolveAdjoint()), u0, P_LV, None,
+                                        saveat=0.25, save_start=False, save_end=False)
+    assert np.allclose(out3.t, [0.25, 0.5, 0.75])
+    # empty saveat: every step is an output, end points dropped
+    out4, _ = b._concrete_solve_adjoint(prob, b.Tsit5(dt=0.25), b.B200Adjoint(b.GaussAdjoint()), u0, P_LV, None, save_start=False, save_end=False)
+    assert np.allclose(out4.t, [0.25, 0.5, 0.75])
 
 
 def test_ragged_block_boundaries_and_matrix_u0():

@@ -198,3 +198,49 @@ def test_fp32_rejects_quadrature_and_continuous_cost():
         b.DeviceEnsemble("lorenz", "quadrature", "tsit5_fixed", 64, t, (0.0, 1.0), 0.01, dtype="f32")
     with pytest.raises(Exception):
         b.DeviceEnsemble("robertson", "gauss", "tsit5_fixed", 64, t, (0.0, 1.0), 0.01, dtype="f32")
+
+
+@pytest.mark.parametrize("sensealg,every", [("interpolating", False), ("gauss", False), ("gauss_kronrod", False), ("quadrature", False),
+                                            ("backsolve", False), ("backsolve", True)])
+def test_fixed_step_off_grid_save_times(sensealg, every):
+    """Save / jump times OFF the dt grid with fixed-step Tsit5 (src/concrete_solve.jl:752-769: the primal is the dense forward
+    solution interpolated at saveat; the jump times are tstops of the fixed-dt reverse solve, whose grid then shifts): the
+    handle is routed to the dense per-member framework run with a constant step.  Device vs oracle, which is pinned against
+    finite differences through the solve for exactly this case (test_oracle_relations.py)."""
+    N, T, dt = 130, 3.0, 0.01
+    rng = np.random.default_rng(41)
+    u0 = np.exp(0.05 * rng.standard_normal((2, N)))
+    p = np.array([1.5, 1.0, 3.0, 1.0])
+    t = np.array([0.013, 0.5, 1.2345, 2.0, 2.999])
+    kw = dict(quad_abstol=1e-12, quad_reltol=1e-12)
+    eng = b.DeviceEnsemble("lv", sensealg, "tsit5_fixed", N, t, (0.0, T), dt, cost=b.AffineCost(1.0, -0.5), ckpt_every_step=every, **kw)
+    saved, status = eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    ref = O.gradient(O.make_cfg("lv", sensealg, "tsit5_fixed", N, t, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), ckpt_every_step=every, **kw), t, u0, p)
+    assert int(np.asarray(status).sum()) == 0 and np.abs(np.asarray(saved) - ref["saved"]).max() < 1e-11
+    tol = 1e-6 if sensealg == "gauss_kronrod" else 1e-8
+    assert _rel(du0, ref["du0"]) < tol and _rel(dp, ref["dp"]) < tol, (_rel(du0, ref["du0"]), _rel(dp, ref["dp"]))
+    eng.close()
+
+
+def test_dense_forward_flag_allows_retargeting_to_off_grid_times():
+    """adjoint_sensitivities(sol, t = off-grid times) on a grid-aligned handle needs the dense forward solution: without
+    B200ADJ_FLAG_DENSE_FORWARD the C ABI says UNSUPPORTED, with it the reverse pass stops at the requested times."""
+    N, T, dt = 33, 2.0, 0.01
+    rng = np.random.default_rng(42)
+    u0 = np.exp(0.05 * rng.standard_normal((2, N)))
+    p = np.array([1.5, 1.0, 3.0, 1.0])
+    grid, off = np.linspace(0.0, T, 5), np.array([0.333, 1.0, 1.777])
+    eng = b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", N, grid, (0.0, T), dt, cost=b.AffineCost(1.0, 0.0))
+    eng.forward(u0, p)
+    with pytest.raises(b.B200AdjError) as ei:
+        eng.set_reverse("gauss", cost=b.AffineCost(1.0, 0.0), t=off)
+    assert ei.value.code == -2
+    eng.close()
+    eng = b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", N, grid, (0.0, T), dt, cost=b.AffineCost(1.0, 0.0), dense_forward=True)
+    eng.forward(u0, p)
+    eng.set_reverse("interpolating", cost=b.AffineCost(1.0, 0.0), t=off)
+    du0, dp = eng.reverse()
+    ref = O.gradient(O.make_cfg("lv", "interpolating", "tsit5_fixed", N, off, 0.0, T, dt=dt, cost=("affine", 1.0, 0.0)), off, u0, p)
+    assert _rel(du0, ref["du0"]) < 1e-8 and _rel(dp, ref["dp"]) < 1e-8
+    eng.close()

@@ -112,3 +112,27 @@ def test_sde_closed_form_stratonovich():
     assert _rel(dp[0], dp0) < 5e-3 and _rel(dp[1], dp1) < 1e-2
     assert _rel(du0, (uex ** 2 / u0[None]).sum(0)) < 5e-3
     eng.close()
+
+
+@pytest.mark.parametrize("stepper", ["em", "euler_heun"])
+def test_sde_interpolating_no_start(stepper):
+    """no_start skips the cotangent of the first save time for every sensealg but Backsolve (src/adjoint_common.jl:761): the
+    SDE InterpolatingAdjoint path honours the flag, BacksolveAdjoint ignores it."""
+    N, T, dt = 120, 1.0, 0.01
+    saveat = np.linspace(0.0, T, 11)
+    p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
+    u0 = np.ones((2, N))
+    out = {}
+    for sa in ("interpolating", "backsolve"):
+        for ns in (False, True):
+            eng = b.DeviceEnsemble("sde_lv", sa, stepper, N, saveat, (0.0, T), dt, cost=b.AffineCost(1.0, 0.5), seed=5, no_start=ns, stored_noise=True)
+            eng.forward(u0, p)
+            dW = eng.noise()
+            du0, dp = eng.reverse()
+            ref = O.gradient(O.make_cfg("sde_lv", sa, stepper, N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, 0.5), no_start=ns), saveat, u0, p, dW=np.asarray(dW))
+            assert _rel(du0, ref["du0"]) < 1e-9 and _rel(dp, ref["dp"]) < 1e-9
+            out[(sa, ns)] = np.array(du0)
+            eng.close()
+    # the skipped jump is exactly the cotangent at t0: a u0 + b = 1.5
+    assert np.allclose(out[("interpolating", False)] - out[("interpolating", True)], 1.5, atol=1e-12)
+    assert np.array_equal(out[("backsolve", False)], out[("backsolve", True)])

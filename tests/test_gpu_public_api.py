@@ -68,11 +68,12 @@ def test_concrete_solve_adjoint_save_idxs_and_no_start():
     prob = b.ODEProblem("lorenz", u0[:, 0], (0.0, T), p)
     out, pullback = b._concrete_solve_adjoint(prob, b.Tsit5(dt=dt), b.B200Adjoint(b.GaussAdjoint()), u0, p, None,
                                               saveat=0.1, save_idxs=[0, 2], save_start=False)
-    assert out.u.shape == (10, 2, N) and out.t[0] == pytest.approx(0.1)
+    # saveat::Number: the rrule's output keeps t0 (src/concrete_solve.jl:718-735); save_start = false => no_start (:962)
+    assert out.u.shape == (11, 2, N) and out.t[0] == 0.0
     tang = pullback(np.ones_like(out.u))
-    saveat = np.linspace(0.1, T, 10)
-    dL = np.zeros((10, 3, N)); dL[:, [0, 2], :] = 1.0
-    cfg = O.make_cfg("lorenz", "gauss", "tsit5_fixed", N, saveat, 0.0, T, dt=dt)
+    saveat = np.linspace(0.0, T, 11)
+    dL = np.zeros((11, 3, N)); dL[:, [0, 2], :] = 1.0
+    cfg = O.make_cfg("lorenz", "gauss", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, no_start=True)
     ref = O.gradient(cfg, saveat, u0, p, dLdu=dL)
     assert _rel(tang[3], ref["du0"]) < 1e-8 and _rel(tang[4], ref["dp"]) < 1e-8
 
@@ -94,8 +95,10 @@ def test_sde_public_api_backsolve():
 def test_unsupported_configs_fail_loudly():
     u0, p = _lorenz(8)
     prob = b.EnsembleProblem(b.ODEProblem("lorenz", u0[:, 0], (0.0, 1.0), p), u0s=u0)
-    with pytest.raises(b.B200AdjError) as ei:                   # off-grid save time -> delegate to the reference
-        b.solve(prob, b.Tsit5(dt=0.01), saveat=[0.005, 0.5])
+    sol = b.solve(prob, b.Tsit5(dt=0.01), saveat=[0.005, 0.5])   # off-grid save times: the dense per-member framework takes over
+    assert sol.u.shape == (2, 3, 8) and int(np.asarray(sol.retcode).sum()) == 0
+    with pytest.raises(b.B200AdjError) as ei:                   # ... which is an F64 path
+        b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", 8, [0.005, 0.5], (0.0, 1.0), 0.01, dtype="f32")
     assert ei.value.code == -2
     with pytest.raises(b.B200AdjError):                          # horizon not a whole number of steps
         b.solve(prob, b.Tsit5(dt=0.03), saveat=[0.3])
