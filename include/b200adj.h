@@ -36,6 +36,15 @@ enum {
     B200ADJ_FAM_MLP = 4,        /* 2 -> H -> H -> 2 tanh MLP (docs/src/Benchmark.md:49-52), P = H*H+6H+2        */
     B200ADJ_FAM_SDE_LINEAR = 5  /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
 };
+/* User RHS families (replaces the user `ODEFunction(f; vjp, vjp_p, jac, paramjac)` seam of
+ * src/derivative_wrappers.jl:284-359, test/Core3/user_vjp.jl:14-38): a family PLUG-IN is a shared library built from a
+ * header with one struct of the shape of csrc/families.cuh (see csrc/family_plugin.inc; python -m
+ * scimlsensitivity_jl_b200.family_plugin builds it).  Registering it yields a family id for cfg.rhs_family.  F64; fixed-step
+ * and adaptive Tsit5 with all sensealgs and events; Rosenbrock23 when the struct also supplies jac / djac / dvjp_p. */
+#define B200ADJ_FAM_USER_BASE 100
+int32_t b200adj_register_family(const char* plugin_path, int32_t* family_id);
+int32_t b200adj_family_info(int32_t family_id, int32_t* d, int32_t* P, const char** name);
+
 /* sensealg: which *SensitivityFunction / driver is run (src/sensitivity_algorithms.jl:254-278,378-405,486-510,591-611) */
 enum { B200ADJ_SA_INTERPOLATING = 0, B200ADJ_SA_GAUSS = 1, B200ADJ_SA_QUADRATURE = 2, B200ADJ_SA_BACKSOLVE = 3,
        B200ADJ_SA_GAUSSKRONROD = 4 /* GaussKronrodAdjoint (src/sensitivity_algorithms.jl:689-703, src/gauss_adjoint.jl:820-825): adaptive steppers */ };

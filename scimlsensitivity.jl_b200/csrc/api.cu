@@ -1,6 +1,8 @@
 // api.cu -- C ABI (include/b200adj.h) of the B200-native ensemble continuous-adjoint engine.
 // Handle management, validation, host<->device staging; kernel dispatch goes through handle.h into disp_*.cu.
 // No torch types, no CPU fallback.
+#include <dlfcn.h>
+
 #include "handle.h"
 
 using namespace b200adj;
@@ -8,7 +10,11 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// registered plug-in families (append-only; a registration is as global as the dlopen behind it)
+std::vector<const FamilyVTable*>& family_registry() { static std::vector<const FamilyVTable*> r; return r; }
+
 int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
+    if (const FamilyVTable* vt = family_lookup(c.rhs_family)) { *d = vt->d; *P = vt->P; *m = 0; return 0; }
     switch (c.rhs_family) {
     case B200ADJ_FAM_LV: *d = 2; *P = 4; *m = 0; return 0;
     case B200ADJ_FAM_LORENZ: *d = 3; *P = 3; *m = 0; return 0;
@@ -153,6 +159,14 @@ __global__ void dgdp_add_kernel(DgdpArgs g) {
     }
 }
 }  // namespace
+
+namespace b200adj {
+const FamilyVTable* family_lookup(int id) {
+    auto& r = family_registry();
+    const int k = id - B200ADJ_FAM_USER_BASE_ID;
+    return (k >= 0 && k < (int)r.size()) ? r[k] : nullptr;
+}
+}  // namespace b200adj
 
 namespace b200adj {
 // QuadratureAdjoint on an adaptive handle: the dense reverse solution, the member-major copy of the forward one and the
@@ -474,6 +488,32 @@ int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, dou
     return B200ADJ_OK;
 }
 
+int32_t b200adj_register_family(const char* plugin_path, int32_t* family_id) {
+    if (!plugin_path || !family_id) { g_create_error = "register_family: null argument"; return B200ADJ_ERR_INVALID; }
+    void* lib = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) { g_create_error = std::string("register_family: dlopen failed: ") + (dlerror() ? dlerror() : "?"); return B200ADJ_ERR_INVALID; }
+    typedef const FamilyVTable* (*entry_t)(void);
+    entry_t entry = (entry_t)dlsym(lib, "b200adj_family_plugin");
+    if (!entry) { g_create_error = "register_family: the library does not export b200adj_family_plugin"; return B200ADJ_ERR_INVALID; }
+    const FamilyVTable* vt = entry();
+    if (!vt || vt->abi != B200ADJ_PLUGIN_ABI) { g_create_error = "register_family: plug-in built against other headers (ABI tag mismatch): rebuild it"; return B200ADJ_ERR_INVALID; }
+    if (vt->d < 1 || vt->d > 4 || vt->P < 1 || vt->P > 8) { g_create_error = "register_family: 1 <= D <= 4 and 1 <= P <= 8"; return B200ADJ_ERR_UNSUPPORTED; }
+    auto& r = family_registry();
+    for (size_t k = 0; k < r.size(); k++) if (r[k] == vt) { *family_id = B200ADJ_FAM_USER_BASE_ID + (int)k; return B200ADJ_OK; }
+    r.push_back(vt);
+    *family_id = B200ADJ_FAM_USER_BASE_ID + (int)r.size() - 1;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_family_info(int32_t family_id, int32_t* d, int32_t* P, const char** name) {
+    const FamilyVTable* vt = family_lookup(family_id);
+    if (!vt) return B200ADJ_ERR_INVALID;
+    if (d) *d = vt->d;
+    if (P) *P = vt->P;
+    if (name) *name = vt->name;
+    return B200ADJ_OK;
+}
+
 int32_t b200adj_set_cost_family(void* handle, int32_t which, const double* a, const double* b, const double* c, const double* e) {
     if (!handle || (which != 0 && which != 1)) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
@@ -608,7 +648,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         case B200ADJ_FAM_LV: rc = launch_t5a_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_fwd<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_fwd<Robertson>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->t5a_fwd) ? vt->t5a_fwd(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (h->adaptive) {
         RosArgs a = ros_args(h);
@@ -618,7 +658,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         case B200ADJ_FAM_LV: rc = launch_ros_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_ros_fwd<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_ros_fwd<Robertson>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->ros_fwd) ? vt->ros_fwd(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
         rc = mlp_forward_dispatch(h, du0, dp, h->fwd_K > 0 ? dsaved : nullptr, dstatus);
@@ -643,7 +683,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         case B200ADJ_FAM_LV: rc = launch_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_fwd<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_fwd<Robertson>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->fwd) ? vt->fwd(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else {
         SdeFwdArgs a;
@@ -704,7 +744,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         case B200ADJ_FAM_LV: rc = launch_t5a_rev<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_rev<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_rev<Robertson>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->t5a_rev) ? vt->t5a_rev(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (h->adaptive) {
         RosArgs a = ros_args(h);
@@ -715,7 +755,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         case B200ADJ_FAM_LV: rc = launch_ros_rev<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_ros_rev<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_ros_rev<Robertson>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->ros_rev) ? vt->ros_rev(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (c.rhs_family == B200ADJ_FAM_MLP) {
         rc = mlp_reverse_dispatch(h, dL, ddu0, ddp);
@@ -750,7 +790,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         case B200ADJ_FAM_LV: rc = launch_rev<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_rev<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_rev<Robertson>(h, a); break;
-        default: rc = B200ADJ_ERR_UNSUPPORTED;
+        default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->rev) ? vt->rev(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else {
         SdeRevArgs a;

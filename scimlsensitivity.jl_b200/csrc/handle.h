@@ -99,6 +99,26 @@ template <class T, class S> inline void cast_tables(const S& src, T* dst) {
 }
 
 
+// ---- family registry (the seam user-supplied ODEFunction(f; vjp, vjp_p, jac, paramjac) occupies in the
+// reference, src/derivative_wrappers.jl:284-359, test/Core3/user_vjp.jl:14-38).  A family PLUG-IN is a shared library built from
+// a user header that defines one struct with the shape of families.cuh (D, P, f, vjp_u, vjp_p [, jac, djac, dvjp_p]); the
+// plug-in instantiates the same kernel templates for it and exports this table of launchers (family_plugin.inc).
+// b200adj_register_family(path) loads it and hands out a family id >= B200ADJ_FAM_USER_BASE. ----
+struct FamilyVTable {
+    uint32_t abi;                 // B200ADJ_PLUGIN_ABI of the headers the plug-in was built from
+    int32_t d, P;
+    const char* name;
+    int (*fwd)(Handle*, const OdeFwdArgs&);          // fixed-step Tsit5
+    int (*rev)(Handle*, const OdeRevArgs&);
+    int (*t5a_fwd)(Handle*, const T5aArgs&);         // adaptive Tsit5 / dense fixed-step framework
+    int (*t5a_rev)(Handle*, const T5aArgs&);
+    int (*ros_fwd)(Handle*, const RosArgs&);         // Rosenbrock23 (null when the family has no jac / djac / dvjp_p)
+    int (*ros_rev)(Handle*, const RosArgs&);
+};
+constexpr uint32_t B200ADJ_PLUGIN_ABI = 0x00020000u ^ (uint32_t)sizeof(Handle) ^ ((uint32_t)sizeof(OdeRevArgs) << 8) ^ ((uint32_t)sizeof(T5aArgs) << 16);
+constexpr int B200ADJ_FAM_USER_BASE_ID = 100;
+const FamilyVTable* family_lookup(int id);          // api.cu: registered plug-in families
+
 // ---- dispatch entry points, one explicit instantiation per family in disp_*.cu ----
 template <class Fam> int launch_fwd(Handle* h, const OdeFwdArgs& a);
 template <class Fam> int launch_rev(Handle* h, const OdeRevArgs& a);
