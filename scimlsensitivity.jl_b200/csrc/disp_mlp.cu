@@ -14,14 +14,24 @@ int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, in
     h->launches++;
     return 0;
 }
+// BF16_F32ACC: two layouts of the same tensor-core kernels.  32 members per CTA (mlp_tc.cuh: 4x more CTAs, a quarter of the
+// per-thread work per stage) while its CTAs fit in one wave of 2 per SM; 128 members per CTA (mlp_tc_wide.cuh: highest
+// throughput) beyond that.
+static bool mlp_tc_narrow(const Handle* h) { return (h->cfg.N + TC_MEM - 1) / TC_MEM <= 2 * (int64_t)h->nsm; }
 int mlp_tc_forward_launch(Handle* h, const void* u0, const void* p, void* saved, int32_t* status) {
     MlpArgs<float> a;
     memset(&a, 0, sizeof(a));
     a.u0 = (const float*)u0; a.p = (const float*)p; a.ckpt = (float*)h->d_ckpt; a.saved = (float*)saved; a.save_of_step = h->d_fwd_save_of_step;
-    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
-    const size_t smem = sizeof(TcSmem) + 128;
-    if (cudaFuncSetAttribute(mlp_tc_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-    mlp_tc_forward_kernel<0><<<(int)((h->cfg.N + TC_M - 1) / TC_M), TC_M, smem, h->stream>>>(a);
+    a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb; a.kst = h->d_kst;
+    if (mlp_tc_narrow(h)) {
+        const size_t smem = sizeof(TcSmem) + 128;
+        if (cudaFuncSetAttribute(mlp_tc_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_tc_forward_kernel<0><<<(int)((h->cfg.N + TC_MEM - 1) / TC_MEM), TC_M, smem, h->stream>>>(a);
+    } else {
+        const size_t smem = sizeof(TcwSmem) + 128;
+        if (cudaFuncSetAttribute(mlp_tcw_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
+        mlp_tcw_forward_kernel<0><<<(int)((h->cfg.N + TCW_M - 1) / TCW_M), TCW_M, smem, h->stream>>>(a);
+    }
     h->launches++;
     return 0;
 }
@@ -30,17 +40,19 @@ int mlp_tc_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
     MlpArgs<float> a;
     memset(&a, 0, sizeof(a));
     a.p = (const float*)h->cur_p; a.ckpt = (float*)h->d_ckpt; a.save_of_step = h->d_save_of_step; a.dLdu = (const float*)dLdu;
-    a.du0 = (float*)du0; a.partials = (float*)h->d_partials; a.dp = (float*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb;
+    a.du0 = (float*)du0; a.partials = (float*)h->d_partials; a.dp = (float*)dp; a.N = c.N; a.S = h->S; a.tb = h->tb; a.kst = h->d_kst;
     for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; } a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
-    const size_t smem = sizeof(TcSmem) + 128;
-    const int grid = (int)((c.N + TC_M - 1) / TC_M);
-    if (c.cost_kind == B200ADJ_COST_EXPLICIT) {
-        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_EXPLICIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        mlp_tc_reverse_kernel<COST_EXPLICIT><<<grid, TC_M, smem, h->stream>>>(a);
-    } else {
-        if (cudaFuncSetAttribute(mlp_tc_reverse_kernel<COST_AFFINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
-        mlp_tc_reverse_kernel<COST_AFFINE><<<grid, TC_M, smem, h->stream>>>(a);
-    }
+    const bool narrow = mlp_tc_narrow(h), ex = c.cost_kind == B200ADJ_COST_EXPLICIT;
+    const size_t smem = (narrow ? sizeof(TcSmem) : sizeof(TcwSmem)) + 128;
+    const int grid = narrow ? (int)((c.N + TC_MEM - 1) / TC_MEM) : (int)((c.N + TCW_M - 1) / TCW_M);
+#define B200_TC_REV(KERNEL, THREADS)                                                                                         \
+    do {                                                                                                                     \
+        if (cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA; \
+        KERNEL<<<grid, THREADS, smem, h->stream>>>(a);                                                                       \
+    } while (0)
+    if (narrow) { if (ex) B200_TC_REV(mlp_tc_reverse_kernel<COST_EXPLICIT>, TC_M); else B200_TC_REV(mlp_tc_reverse_kernel<COST_AFFINE>, TC_M); }
+    else { if (ex) B200_TC_REV(mlp_tcw_reverse_kernel<COST_EXPLICIT>, TCW_M); else B200_TC_REV(mlp_tcw_reverse_kernel<COST_AFFINE>, TCW_M); }
+#undef B200_TC_REV
     mlp_reduce_kernel<float><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const float*)h->d_partials, (float*)dp, grid);
     h->launches += 2;
     return 0;

@@ -19,6 +19,7 @@
 #include "mlp.cuh"
 #include "tsit5_quad.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc_wide.cuh"
 #include "tsit5_adaptive.cuh"
 
 namespace b200adj {
@@ -53,6 +54,7 @@ struct Handle {
     double cost_av[4] = {0, 0, 0, 0}, cost_bv[4] = {0, 0, 0, 0}, cont_av[4] = {0, 0, 0, 0}, cont_bv[4] = {0, 0, 0, 0};
     bool has_dgdp = false, has_cdgdp = false;
     double dgdp_c[8] = {0}, dgdp_e[8] = {0}, cdgdp_c[8] = {0}, cdgdp_e[8] = {0};
+    float* d_kst = nullptr;           // tensor-core MLP path: the forward stages of every step ([S][7][2][N] floats)
     bool mlp_tc = false;              // BF16_F32ACC: every GEMM-shaped piece of the time loop on tcgen05 (mlp_tc.cuh)
     double *r_ft = nullptr, *r_fu = nullptr, *r_fk = nullptr, *d_saveat = nullptr;
     // QuadratureAdjoint on the adaptive steppers (allocated at the first Quadrature reverse pass): member-major reverse dense

@@ -29,7 +29,8 @@ template <class T> struct MlpArgs {
     const T* u0; const T* p; T* ckpt; T* saved; const int32_t* save_of_step; int32_t* status;
     const T* dLdu; T* du0; T* partials; T* dp;     // partials [grid][P]
     int64_t N; int32_t S; double cost_a[4], cost_b[4]; uint32_t flags;
-    void* tapeA; void* tapeB; int64_t Ktot, Npad;     // bf16 mode: K-major operand tapes [64][Ktot], Ktot = 6 S Npad
+    void* tapeA; void* tapeB; int64_t Ktot, Npad;     // (superseded bf16 tape formulation: unused)
+    float* kst;                                       // tensor-core path: forward stages k1..k7 per step, [S][7][2][N] (or null: recompute)
     Tsit5Tables tb;
 };
 

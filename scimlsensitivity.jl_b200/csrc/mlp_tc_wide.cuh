@@ -1,0 +1,352 @@
+// mlp_tc_wide.cuh -- the WIDE layout of the tensor-core neural-ODE kernels (mlp_tc.cuh): one CTA = 128 ensemble members = the
+// 128 rows (TMEM lanes) of every MMA, one thread per member (64 tanh per layer and thread).  Highest throughput once every SM
+// has work (N >= 2 x 148 x 32 members); below that the 32-member layout of mlp_tc.cuh has 4x more CTAs and shorter stages.
+// The GEMMs, tiles and descriptors are those of mlp_tc.cuh (all 128 rows are distinct members here).
+#pragma once
+#include "mlp_tc.cuh"
+
+namespace b200adj {
+
+constexpr int TCW_M = 128;                                   // members per CTA
+
+struct TcwSmem {
+    alignas(128) unsigned char TA[TCW_M * TC_TA_F * 2];      // [member][wt dZ2 (64) | wt dZ1 (64)]
+    alignas(128) unsigned char TH[TCW_M * TC_TA_F * 2];      // [member][H2 (64) | 1 | 0 ...]
+    alignas(128) unsigned char TB[TCW_M * TC_TB_F * 2];      // [member][H1 (64) | y0 y1 1 | 0 ...]
+    alignas(128) unsigned char TC[TCW_M * TC_TC_F * 2];      // [member][wt L0, wt L1 | 0 ...]
+    alignas(128) unsigned char W2[64 * 64 * 2];             // (n = out i, k = in j)  = W2[i][j]
+    alignas(128) unsigned char W2T[64 * 64 * 2];            // (n = in j,  k = out i) = W2[i][j]
+    float W1a[64], W1b[64], b1[64], b2[64], W3a[64], W3b[64], b3[2];
+    alignas(8) uint64_t barM, barG;
+    uint32_t tmem;
+};
+
+struct TcwState {               // per-thread pipeline bookkeeping (identical in all threads)
+    uint32_t phM = 0, phG = 0;
+    bool gpend = false, gfirst = true;
+};
+
+__device__ __forceinline__ void tcw_setup(TcwSmem& s, const float* p) {
+    const int t = threadIdx.x;
+    for (int x = t; x < 64 * 64; x += TCW_M) {
+        const int j = x / 64, i = x % 64;                                     // p[OW2 + j*64 + i] = W2[i][j]
+        const __nv_bfloat16 w = __float2bfloat16(p[MLP_OW2 + x]);
+        *reinterpret_cast<__nv_bfloat16*>(s.W2 + (i >> 3) * 1024 + (j >> 3) * 128 + (i & 7) * 16 + (j & 7) * 2) = w;
+        *reinterpret_cast<__nv_bfloat16*>(s.W2T + (j >> 3) * 1024 + (i >> 3) * 128 + (j & 7) * 16 + (i & 7) * 2) = w;
+    }
+    if (t < 64) {
+        s.W1a[t] = p[MLP_OW1 + t]; s.W1b[t] = p[MLP_OW1 + 64 + t]; s.b1[t] = p[MLP_OB1 + t]; s.b2[t] = p[MLP_OB2 + t];
+        s.W3a[t] = p[MLP_OW3 + t * 2]; s.W3b[t] = p[MLP_OW3 + t * 2 + 1];
+    }
+    if (t < 2) s.b3[t] = p[MLP_OB3 + t];
+    // constant parts of the tiles: TH features 64.. = [1, 0, ...], TB features 72..79 = 0, TC features 8..15 = 0
+    const uint4 zero = make_uint4(0, 0, 0, 0);
+    *tc_chunk<TC_TA_F>(s.TH, t, 8) = make_uint4(0x00003F80u, 0, 0, 0);       // bf16(1.0) = 0x3F80
+#pragma unroll
+    for (int kc = 9; kc < 16; kc++) *tc_chunk<TC_TA_F>(s.TH, t, kc) = zero;
+    *tc_chunk<TC_TB_F>(s.TB, t, 8) = zero;
+    *tc_chunk<TC_TB_F>(s.TB, t, 9) = zero;
+    *tc_chunk<TC_TC_F>(s.TC, t, 0) = zero;
+    *tc_chunk<TC_TC_F>(s.TC, t, 1) = zero;
+    if ((t >> 5) == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s.tmem)), "r"(TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (t == 0) { mbar_init(&s.barM, 1); mbar_init(&s.barG, 1); mbar_fence_init(); }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+__device__ __forceinline__ void tcw_wait_grad(TcwSmem& s, TcwState& st) {
+    if (st.gpend) { mbar_wait(&s.barG, st.phG); st.phG ^= 1; st.gpend = false; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+}
+
+// F = f(y); leaves H1 (bf16) in this member's TB row and H2 in registers
+template <bool GRAD>
+__device__ __forceinline__ void tcw_forward(TcwSmem& s, TcwState& st, float y0, float y1, float* F, float* H2) {
+    const int t = threadIdx.x;
+    uint4 row[8];                                        // H1 of this member, bf16, computed while the previous stage's
+#pragma unroll                                           // gradient GEMMs may still be reading the tiles
+    for (int kc = 0; kc < 8; kc++) {
+        float h[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) { const int j = kc * 8 + q; h[q] = tanh_fast(fmaf(s.W1a[j], y0, fmaf(s.W1b[j], y1, s.b1[j]))); }
+        row[kc] = make_uint4(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]), pack_bf16(h[4], h[5]), pack_bf16(h[6], h[7]));
+    }
+    if (GRAD) tcw_wait_grad(s, st);
+#pragma unroll
+    for (int kc = 0; kc < 8; kc++) *tc_chunk<TC_TB_F>(s.TB, t, kc) = row[kc];
+    if (GRAD) *tc_chunk<TC_TB_F>(s.TB, t, 8) = make_uint4(pack_bf16(y0, y1), pack_bf16(1.0f, 0.0f), 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            umma_f16(s.tmem + TC_COL_D, umma_smem_desc(smem_u32(s.TB) + k * 256, 128, (TC_TB_F / 8) * 128),
+                     umma_smem_desc(smem_u32(s.W2) + k * 256, 128, 1024), tc_idesc(128, 64, 0, 0), k > 0);
+        umma_commit(&s.barM);
+    }
+    mbar_wait(&s.barM, st.phM); st.phM ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float f0 = s.b3[0], f1 = s.b3[1];
+    const uint32_t lane_base = s.tmem + ((uint32_t)((t >> 5) * 32) << 16) + TC_COL_D;
+#pragma unroll
+    for (int cb = 0; cb < 64; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + cb, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int n = cb + q;
+            const float h2 = tanh_fast(__uint_as_float(r[q]) + s.b2[n]);
+            H2[n] = h2;
+            f0 = fmaf(s.W3a[n], h2, f0); f1 = fmaf(s.W3b[n], h2, f1);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    F[0] = f0; F[1] = f1;
+}
+
+// J = (df/dy)' L at the point of the last tcw_forward; issues the gradient GEMMs with weight wt (members with valid = false
+// contribute nothing)
+__device__ __forceinline__ void tcw_backward(TcwSmem& s, TcwState& st, float wt, float L0, float L1, bool valid, const float* H2, float* J) {
+    const int t = threadIdx.x;
+    const float wv = valid ? wt : 0.0f;
+#pragma unroll
+    for (int kc = 0; kc < 8; kc++) {
+        float dz[8], hh[8];
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int n = kc * 8 + q;
+            hh[q] = H2[n];
+            dz[q] = wv * fmaf(s.W3a[n], L0, s.W3b[n] * L1) * (1.0f - hh[q] * hh[q]);
+        }
+        *tc_chunk<TC_TA_F>(s.TA, t, kc) = make_uint4(pack_bf16(dz[0], dz[1]), pack_bf16(dz[2], dz[3]), pack_bf16(dz[4], dz[5]), pack_bf16(dz[6], dz[7]));
+        *tc_chunk<TC_TA_F>(s.TH, t, kc) = make_uint4(pack_bf16(hh[0], hh[1]), pack_bf16(hh[2], hh[3]), pack_bf16(hh[4], hh[5]), pack_bf16(hh[6], hh[7]));
+    }
+    *tc_chunk<TC_TC_F>(s.TC, t, 0) = make_uint4(pack_bf16(wv * L0, wv * L1), 0, 0, 0);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            umma_f16(s.tmem + TC_COL_D, umma_smem_desc(smem_u32(s.TA) + k * 256, 128, (TC_TA_F / 8) * 128),
+                     umma_smem_desc(smem_u32(s.W2T) + k * 256, 128, 1024), tc_idesc(128, 64, 0, 0), k > 0);
+        umma_commit(&s.barM);
+    }
+    mbar_wait(&s.barM, st.phM); st.phM ^= 1;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float j0 = 0.0f, j1 = 0.0f;
+    const uint32_t lane_base = s.tmem + ((uint32_t)((t >> 5) * 32) << 16) + TC_COL_D;
+#pragma unroll
+    for (int cb = 0; cb < 64; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + cb, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float dz1[16];
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const uint4 hv = *tc_chunk<TC_TB_F>(s.TB, t, cb / 8 + half);      // this member's H1 (bf16), features cb + 8 half ..
+            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int j = cb + half * 8 + q;
+                const float h1 = __uint_as_float((q & 1) ? (hw[q >> 1] & 0xFFFF0000u) : (hw[q >> 1] << 16));
+                const float d = __uint_as_float(r[half * 8 + q]) * (1.0f - h1 * h1);      // wt dZ1
+                dz1[half * 8 + q] = d;
+                j0 = fmaf(s.W1a[j], d, j0); j1 = fmaf(s.W1b[j], d, j1);
+            }
+        }
+        *tc_chunk<TC_TA_F>(s.TA, t, 8 + cb / 8) = make_uint4(pack_bf16(dz1[0], dz1[1]), pack_bf16(dz1[2], dz1[3]), pack_bf16(dz1[4], dz1[5]), pack_bf16(dz1[6], dz1[7]));
+        *tc_chunk<TC_TA_F>(s.TA, t, 9 + cb / 8) = make_uint4(pack_bf16(dz1[8], dz1[9]), pack_bf16(dz1[10], dz1[11]), pack_bf16(dz1[12], dz1[13]), pack_bf16(dz1[14], dz1[15]));
+    }
+    const float inv = 1.0f / wt;
+    J[0] = j0 * inv; J[1] = j1 * inv;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (t == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t acc0 = st.gfirst ? 0u : 1u;
+#pragma unroll
+        for (int k = 0; k < 8; k++)        // K = 16 members per MMA = 2 member groups of 8
+            umma_f16(s.tmem + TC_COL_G1, umma_smem_desc(smem_u32(s.TA) + k * 2 * (TC_TA_F / 8) * 128, (TC_TA_F / 8) * 128, 128),
+                     umma_smem_desc(smem_u32(s.TB) + k * 2 * (TC_TB_F / 8) * 128, (TC_TB_F / 8) * 128, 128), tc_idesc(128, TC_TB_F, 1, 1), (k > 0) ? 1u : acc0);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            umma_f16(s.tmem + TC_COL_G2, umma_smem_desc(smem_u32(s.TH) + k * 2 * (TC_TA_F / 8) * 128, (TC_TA_F / 8) * 128, 128),
+                     umma_smem_desc(smem_u32(s.TC) + k * 2 * (TC_TC_F / 8) * 128, (TC_TC_F / 8) * 128, 128), tc_idesc(128, TC_TC_F, 1, 1), (k > 0) ? 1u : acc0);
+        umma_commit(&s.barG);
+    }
+    st.gfirst = false; st.gpend = true;
+}
+
+__device__ __forceinline__ void tcw_teardown(TcwSmem& s) {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(s.tmem), "r"(TC_TMEM_COLS) : "memory");
+}
+
+// ---- forward ensemble solve (fixed-step Tsit5) ----
+template <int UNUSED = 0>
+__global__ void __launch_bounds__(TCW_M) mlp_tcw_forward_kernel(const __grid_constant__ MlpArgs<float> a) {
+    extern __shared__ __align__(128) unsigned char tcw_smem_raw[];
+    TcwSmem& s = *reinterpret_cast<TcwSmem*>(tcw_smem_raw);
+    const int64_t N = a.N, base = (int64_t)blockIdx.x * TCW_M;
+    const int t = threadIdx.x;
+    const bool live = base + t < N;
+    const int64_t col = live ? base + t : N - 1;
+    tcw_setup(s, a.p);
+    TcwState st;
+    float u[2], kf[7][2], H2[64], F[2];
+    u[0] = a.u0[col]; u[1] = a.u0[N + col];
+    if (live) {
+        a.ckpt[col] = u[0]; a.ckpt[N + col] = u[1];
+        if (a.saved) { const int ks = a.save_of_step[0]; if (ks >= 0) { a.saved[((int64_t)ks * 2) * N + col] = u[0]; a.saved[((int64_t)ks * 2 + 1) * N + col] = u[1]; } }
+    }
+    tcw_forward<false>(s, st, u[0], u[1], kf[0], H2);
+    for (int n = 0; n < a.S; n++) {
+        float y[2];
+#pragma unroll 1
+        for (int sg = 1; sg <= 6; sg++) {
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                double acc = (double)u[c];
+                for (int j = 0; j < sg; j++) acc = fma(a.tb.hA[sg][j], (double)kf[j][c], acc);
+                y[c] = (float)acc;
+            }
+            tcw_forward<false>(s, st, y[0], y[1], F, H2);
+            if (sg < 6) { kf[sg][0] = F[0]; kf[sg][1] = F[1]; }
+        }
+        if (live && a.kst) {
+            // the dense forward solution of this step (k1..k6, k7 = f(u_{n+1})): the reverse pass reads it back instead of
+            // repeating the six stage evaluations (6 of its 18 tensor-core round trips per step), 56 B per member-step
+            float* ks_ = a.kst + ((int64_t)n * 14) * N + col;
+#pragma unroll
+            for (int j = 0; j < 6; j++) { ks_[(int64_t)(2 * j) * N] = kf[j][0]; ks_[(int64_t)(2 * j + 1) * N] = kf[j][1]; }
+            ks_[(int64_t)12 * N] = F[0]; ks_[(int64_t)13 * N] = F[1];
+        }
+        u[0] = y[0]; u[1] = y[1]; kf[0][0] = F[0]; kf[0][1] = F[1];         // FSAL: f(u_{n+1})
+        if (live) {
+            a.ckpt[((int64_t)(n + 1) * 2) * N + col] = u[0]; a.ckpt[((int64_t)(n + 1) * 2 + 1) * N + col] = u[1];
+            if (a.saved) { const int ks = a.save_of_step[n + 1]; if (ks >= 0) { a.saved[((int64_t)ks * 2) * N + col] = u[0]; a.saved[((int64_t)ks * 2 + 1) * N + col] = u[1]; } }
+        }
+    }
+    if (live && a.status) a.status[col] = (isfinite(u[0]) && isfinite(u[1])) ? 0 : 1;
+    tcw_teardown(s);
+}
+
+// ---- fused reverse pass, InterpolatingAdjoint (same stage sequence as mlp_reverse_kernel) ----
+template <int COST>
+__global__ void __launch_bounds__(TCW_M) mlp_tcw_reverse_kernel(const __grid_constant__ MlpArgs<float> a) {
+    extern __shared__ __align__(128) unsigned char tcw_smem_raw[];
+    TcwSmem& s = *reinterpret_cast<TcwSmem*>(tcw_smem_raw);
+    const int64_t N = a.N, base = (int64_t)blockIdx.x * TCW_M;
+    const int t = threadIdx.x;
+    const bool live = base + t < N;
+    const int64_t col = live ? base + t : N - 1;
+    const Tsit5Tables& tb = a.tb;
+    tcw_setup(s, a.p);
+    TcwState st;
+    float lam[2] = {0.0f, 0.0f}, uhi[2], ulo[2], kf[7][2], ka[6][2], H2[64], F[2], J[2];
+    auto cotangent = [&](int ks, const float* yy) {
+        if (COST == COST_EXPLICIT) { lam[0] += a.dLdu[((int64_t)ks * 2) * N + col]; lam[1] += a.dLdu[((int64_t)ks * 2 + 1) * N + col]; }
+        else { lam[0] += (float)(a.cost_a[0] * (double)yy[0] + a.cost_b[0]); lam[1] += (float)(a.cost_a[1] * (double)yy[1] + a.cost_b[1]); }
+    };
+    uhi[0] = a.ckpt[((int64_t)a.S * 2) * N + col]; uhi[1] = a.ckpt[((int64_t)a.S * 2 + 1) * N + col];
+    { const int ks = a.save_of_step[a.S]; if (ks >= 0) cotangent(ks, uhi); }
+    if (!a.kst) tcw_forward<true>(s, st, uhi[0], uhi[1], kf[6], H2);    // f(u_S) = forward k7 of the last step
+    for (int n = a.S - 1; n >= 0; n--) {
+        ulo[0] = a.ckpt[((int64_t)n * 2) * N + col]; ulo[1] = a.ckpt[((int64_t)n * 2 + 1) * N + col];
+        // ---- forward stages k1..k7 of [t_n, t_{n+1}]: read back from the forward pass (a.kst) or recomputed ----
+        if (a.kst) {
+            const float* ks_ = a.kst + ((int64_t)n * 14) * N + col;
+#pragma unroll
+            for (int j = 0; j < 7; j++) { kf[j][0] = ks_[(int64_t)(2 * j) * N]; kf[j][1] = ks_[(int64_t)(2 * j + 1) * N]; }
+        } else {
+            tcw_forward<true>(s, st, ulo[0], ulo[1], kf[0], H2);
+#pragma unroll 1
+            for (int sg = 1; sg <= 5; sg++) {
+                float y[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    double acc = (double)ulo[c];
+                    for (int j = 0; j < sg; j++) acc = fma(tb.hA[sg][j], (double)kf[j][c], acc);
+                    y[c] = (float)acc;
+                }
+                tcw_forward<true>(s, st, y[0], y[1], kf[sg], H2);
+            }
+        }
+        // ---- adjoint stages 0..5 ----
+#pragma unroll 1
+        for (int sg = 0; sg <= 5; sg++) {
+            float L[2], y[2];
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                double l = (double)lam[c];
+                for (int j = 0; j < sg; j++) l = fma(tb.hA[sg][j], (double)ka[j][c], l);
+                L[c] = (float)l;
+                double yv;
+                if (sg == 0) yv = (double)uhi[c];
+                else if (sg == 5) yv = (double)ulo[c];
+                else { yv = (double)ulo[c]; for (int j = 0; j < 7; j++) yv = fma(tb.hBst[sg - 1][j], (double)kf[j][c], yv); }
+                y[c] = (float)yv;
+            }
+            tcw_forward<true>(s, st, y[0], y[1], F, H2);
+            tcw_backward(s, st, (float)tb.hA[6][sg], L[0], L[1], live, H2, J);
+            ka[sg][0] = J[0]; ka[sg][1] = J[1];
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            double l = (double)lam[c];
+            for (int j = 0; j < 6; j++) l = fma(tb.hA[6][j], (double)ka[j][c], l);
+            lam[c] = (float)l;
+        }
+        { const int ks = a.save_of_step[n]; if (ks >= 0 && !((a.flags & 1u) && n == 0)) cotangent(ks, ulo); }
+        uhi[0] = ulo[0]; uhi[1] = ulo[1];
+        if (!a.kst) { kf[6][0] = kf[0][0]; kf[6][1] = kf[0][1]; }
+    }
+    if (live) { a.du0[col] = lam[0]; a.du0[N + col] = lam[1]; }
+    // ---- parameter gradient of this CTA out of TMEM: thread t = row t of G1 / G2 ----
+    tcw_wait_grad(s, st);
+    float* out = a.partials + (int64_t)blockIdx.x * MLP_P;
+    const uint32_t lane_base = s.tmem + ((uint32_t)((t >> 5) * 32) << 16);
+    const bool any = a.S > 0;
+#pragma unroll 1
+    for (int cb = 0; cb < TC_TB_F; cb += 16) {
+        uint32_t r[16];
+        tmem_ld16(lane_base + TC_COL_G1 + cb, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int q = 0; q < 16; q++) {
+            const int g = cb + q;
+            const float v = any ? __uint_as_float(r[q]) : 0.0f;
+            if (t < 64) {                    // row i = t: dW2[i][g] (g < 64), db2[i] (g = 66)
+                if (g < 64) out[MLP_OW2 + g * 64 + t] = v;
+                else if (g == 66) out[MLP_OB2 + t] = v;
+            } else {                         // row 64 + j: dW1[j][c] (g = 64 + c), db1[j] (g = 66)
+                const int j = t - 64;
+                if (g == 64) out[MLP_OW1 + j] = v;
+                else if (g == 65) out[MLP_OW1 + 64 + j] = v;
+                else if (g == 66) out[MLP_OB1 + j] = v;
+            }
+        }
+    }
+    {
+        uint32_t r[16];
+        tmem_ld16(lane_base + TC_COL_G2, r);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const float v0 = any ? __uint_as_float(r[0]) : 0.0f, v1 = any ? __uint_as_float(r[1]) : 0.0f;
+        if (t < 64) { out[MLP_OW3 + t * 2] = v0; out[MLP_OW3 + t * 2 + 1] = v1; }      // dW3[c][n = t]
+        else if (t == 64) { out[MLP_OB3] = v0; out[MLP_OB3 + 1] = v1; }
+    }
+    tcw_teardown(s);
+}
+
+}  // namespace b200adj
