@@ -492,7 +492,7 @@ int32_t b200adj_set_continuous_cost(void* handle, int32_t enabled, double a, dou
 int32_t b200adj_register_family(const char* plugin_path, int32_t* family_id) {
     if (!plugin_path || !family_id) { g_create_error = "register_family: null argument"; return B200ADJ_ERR_INVALID; }
     void* lib = dlopen(plugin_path, RTLD_NOW | RTLD_LOCAL);
-    if (!lib) { g_create_error = std::string("register_family: dlopen failed: ") + (dlerror() ? dlerror() : "?"); return B200ADJ_ERR_INVALID; }
+    if (!lib) { const char* e = dlerror(); g_create_error = std::string("register_family: dlopen failed: ") + (e ? e : "?"); return B200ADJ_ERR_INVALID; }
     typedef const FamilyVTable* (*entry_t)(void);
     entry_t entry = (entry_t)dlsym(lib, "b200adj_family_plugin");
     if (!entry) { dlclose(lib); g_create_error = "register_family: the library does not export b200adj_family_plugin"; return B200ADJ_ERR_INVALID; }

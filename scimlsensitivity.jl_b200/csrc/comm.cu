@@ -38,7 +38,7 @@ Nccl* nccl() {
         tried = true;
         const char* names[] = {"libnccl.so.2", "libnccl.so"};
         for (const char* nm : names) { n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (n.lib) break; }
-        if (!n.lib) { n.err = std::string("dlopen(libnccl.so.2) failed: ") + (dlerror() ? dlerror() : "?"); return &n; }
+        if (!n.lib) { const char* e = dlerror(); n.err = std::string("dlopen(libnccl.so.2) failed: ") + (e ? e : "?"); return &n; }
         n.GetUniqueId = (int (*)(nccl_uid*))dlsym(n.lib, "ncclGetUniqueId");
         n.CommInitRank = (int (*)(nccl_comm_t*, int, nccl_uid, int))dlsym(n.lib, "ncclCommInitRank");
         n.AllReduce = (int (*)(const void*, void*, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(n.lib, "ncclAllReduce");
