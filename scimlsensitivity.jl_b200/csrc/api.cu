@@ -233,8 +233,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
     if (f32_ode && cfg->sensealg == B200ADJ_SA_QUADRATURE) { g_create_error = "F32: Interpolating / Gauss / Backsolve (QuadratureAdjoint is F64 only)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->dtype != B200ADJ_F64 && !f32_ode && !(mlp && (cfg->dtype == B200ADJ_F32 || cfg->dtype == B200ADJ_BF16_F32ACC))) {
         g_create_error = "dtype: F64 (all families), F32 (MLP; LV / Lorenz with fixed-step Tsit5), BF16_F32ACC (MLP) are built"; return B200ADJ_ERR_UNSUPPORTED; }
-    if (mlp && (cfg->stepper != B200ADJ_ST_TSIT5_FIXED || cfg->sensealg != B200ADJ_SA_INTERPOLATING || !cfg->shared_p)) {
-        g_create_error = "MLP family: InterpolatingAdjoint + fixed-step Tsit5 + shared parameters are built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (mlp && (cfg->stepper != B200ADJ_ST_TSIT5_FIXED || (cfg->sensealg != B200ADJ_SA_INTERPOLATING && cfg->sensealg != B200ADJ_SA_GAUSS) || !cfg->shared_p)) {
+        g_create_error = "MLP family: InterpolatingAdjoint / GaussAdjoint + fixed-step Tsit5 + shared parameters are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->cost_kind != B200ADJ_COST_EXPLICIT && cfg->cost_kind != B200ADJ_COST_AFFINE) { g_create_error = "bad cost_kind"; return B200ADJ_ERR_INVALID; }
     const bool sde = is_sde(*cfg);
     if (sde) {
@@ -427,7 +427,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     if (sensealg == B200ADJ_SA_GAUSSKRONROD && (is_sde(c) || c.rhs_family == B200ADJ_FAM_MLP || c.dtype != B200ADJ_F64)) { h->err = "GaussKronrodAdjoint: F64, named ODE families"; return B200ADJ_ERR_UNSUPPORTED; }
     if (h->ckpt_every > 1 && sensealg != B200ADJ_SA_INTERPOLATING && sensealg != B200ADJ_SA_GAUSS) { h->err = "checkpoint_every > 1: InterpolatingAdjoint / GaussAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
-    if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "MLP family: only InterpolatingAdjoint is built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (c.rhs_family == B200ADJ_FAM_MLP && sensealg != B200ADJ_SA_INTERPOLATING && sensealg != B200ADJ_SA_GAUSS) { h->err = "MLP family: InterpolatingAdjoint / GaussAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
     if (h->nev > 0 && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "events: QuadratureAdjoint has no callback support"; return B200ADJ_ERR_UNSUPPORTED; }
     if (c.dtype == B200ADJ_F32 && c.rhs_family != B200ADJ_FAM_MLP && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "F32: QuadratureAdjoint is F64 only"; return B200ADJ_ERR_UNSUPPORTED; }
     CUDA_TRY(h, cudaSetDevice(c.device));

@@ -50,8 +50,12 @@ int mlp_tc_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
         if (cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA; \
         KERNEL<<<grid, THREADS, smem, h->stream>>>(a);                                                                       \
     } while (0)
-    if (narrow) { if (ex) B200_TC_REV(mlp_tc_reverse_kernel<COST_EXPLICIT>, TC_M); else B200_TC_REV(mlp_tc_reverse_kernel<COST_AFFINE>, TC_M); }
-    else { if (ex) B200_TC_REV(mlp_tcw_reverse_kernel<COST_EXPLICIT>, TCW_M); else B200_TC_REV(mlp_tcw_reverse_kernel<COST_AFFINE>, TCW_M); }
+#define B200_TC_REV2(COSTV, GAUSSV)                                                                                      \
+    do { if (narrow) B200_TC_REV((mlp_tc_reverse_kernel<COSTV, GAUSSV>), TC_M); else B200_TC_REV((mlp_tcw_reverse_kernel<COSTV, GAUSSV>), TCW_M); } while (0)
+    const bool gauss = c.sensealg == B200ADJ_SA_GAUSS;
+    if (gauss) { if (ex) B200_TC_REV2(COST_EXPLICIT, true); else B200_TC_REV2(COST_AFFINE, true); }
+    else { if (ex) B200_TC_REV2(COST_EXPLICIT, false); else B200_TC_REV2(COST_AFFINE, false); }
+#undef B200_TC_REV2
 #undef B200_TC_REV
     mlp_reduce_kernel<float><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const float*)h->d_partials, (float*)dp, grid);
     h->launches += 2;
@@ -73,7 +77,8 @@ int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
         mlp_reverse_kernel<T, COSTV, TAPEV><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);                                  \
     } while (0)
     const bool ex = c.cost_kind == B200ADJ_COST_EXPLICIT;
-    if (ex) B200_MLP_REV(COST_EXPLICIT, false); else B200_MLP_REV(COST_AFFINE, false);
+    if (c.sensealg == B200ADJ_SA_GAUSS) { if (ex) B200_MLP_REV(COST_EXPLICIT, true); else B200_MLP_REV(COST_AFFINE, true); }
+    else { if (ex) B200_MLP_REV(COST_EXPLICIT, false); else B200_MLP_REV(COST_AFFINE, false); }
 #undef B200_MLP_REV
     mlp_reduce_kernel<T><<<(MLP_P + 255) / 256, 256, 0, h->stream>>>((const T*)h->d_partials, (T*)dp, h->grid);
     h->launches += 2;

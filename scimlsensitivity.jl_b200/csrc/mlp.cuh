@@ -225,9 +225,13 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_forward_kernel(const __grid_c
     if (live && c == 0 && a.status) a.status[col] = (isfinite((double)s.ulo[0][b]) && isfinite((double)s.ulo[1][b])) ? 0 : 1;
 }
 
-// ---- fused reverse pass, InterpolatingAdjoint ----
-template <class T, int COST, bool TAPE>
+// ---- fused reverse pass.  GAUSS = false: InterpolatingAdjoint (mu integrated with the adjoint tableau); GAUSS = true:
+// GaussAdjoint (the reference's default once length(u0) + length(p) > 100, src/concrete_solve.jl:291-316): state lambda only,
+// dp += (h/2) w_g F(y_g)' lam_g at the three Gauss-Legendre nodes of every step, lam_g from the adjoint step's own dense
+// output and y_g from the forward dense output (src/gauss_adjoint.jl:745-759) ----
+template <class T, int COST, bool GAUSS>
 __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_constant__ MlpArgs<T> a) {
+    constexpr bool TAPE = false;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     MlpSmem<T>& s = *reinterpret_cast<MlpSmem<T>*>(smem_raw);
     const int64_t N = a.N, base = (int64_t)blockIdx.x * MLP_TB;
@@ -274,16 +278,17 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
             if (own) s.kf[st][c][b] = s.F[c][b];
             __syncthreads();
         }
-        // ---- adjoint stages 0..5 (b7 = 0: the 7th stage carries no mu weight and its derivative is never used) ----
+        // ---- adjoint stages 0..5 (b7 = 0: the 7th stage carries no mu weight; GaussAdjoint needs its derivative for the
+        //      dense output of the adjoint step, so it runs stage 6 as well) ----
 #pragma unroll 1
-        for (int st = 0; st <= 5; st++) {
+        for (int st = 0; st <= (GAUSS ? 6 : 5); st++) {
             if (own) {
                 double l = (double)s.lam[c][b];
-                for (int j = 0; j < st; j++) l = fma(tb.hA[st][j], (double)s.ka[j][c][b], l);
+                for (int j = 0; j < st && j < 6; j++) l = fma(tb.hA[st][j], (double)s.ka[j][c][b], l);
                 s.L[c][b] = (T)l;
                 double yv;
                 if (st == 0) yv = (double)s.uhi[c][b];
-                else if (st == 5) yv = (double)s.ulo[c][b];
+                else if (st >= 5) yv = (double)s.ulo[c][b];
                 else { yv = (double)s.ulo[c][b]; for (int j = 0; j < 7; j++) yv = fma(tb.hBst[st - 1][j], (double)s.kf[j][c][b], yv); }
                 s.y[c][b] = (T)yv;
             }
@@ -291,9 +296,24 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
             mlp_forward<T>(s);
             mlp_backward<T>(s);
             if (own) s.ka[st][c][b] = s.JTL[c][b];
-            mlp_accumulate<T, TAPE>(s, g, (T)tb.hA[6][st], nvalid, (__nv_bfloat16*)a.tapeA, (__nv_bfloat16*)a.tapeB, a.Ktot,
-                                    ((int64_t)(a.S - 1 - n) * 6 + st) * a.Npad + base);
+            if (!GAUSS) mlp_accumulate<T, TAPE>(s, g, (T)tb.hA[6][st], nvalid, (__nv_bfloat16*)a.tapeA, (__nv_bfloat16*)a.tapeB, a.Ktot,
+                                                ((int64_t)(a.S - 1 - n) * 6 + st) * a.Npad + base);
             __syncthreads();
+        }
+        if (GAUSS) {
+#pragma unroll 1
+            for (int gq = 0; gq < 3; gq++) {
+                if (own) {
+                    double l = (double)s.lam[c][b], yv = (double)s.ulo[c][b];
+                    for (int j = 0; j < 7; j++) { l = fma(tb.hBq[gq][j], (double)s.ka[j][c][b], l); yv = fma(tb.hBq[2 - gq][j], (double)s.kf[j][c][b], yv); }
+                    s.L[c][b] = (T)l; s.y[c][b] = (T)yv;
+                }
+                __syncthreads();
+                mlp_forward<T>(s);
+                mlp_backward<T>(s);
+                mlp_accumulate<T, TAPE>(s, g, (T)tb.hGW[gq], nvalid, nullptr, nullptr, 0, 0);
+                __syncthreads();
+            }
         }
         // lambda(t_n) = lam + sum_j h b_j ka_j ; jump at t_n ; shift
         if (own) {

@@ -113,6 +113,7 @@ __device__ __forceinline__ void tcw_forward(TcwSmem& s, TcwState& st, float y0, 
 
 // J = (df/dy)' L at the point of the last tcw_forward; issues the gradient GEMMs with weight wt (members with valid = false
 // contribute nothing)
+template <bool GRAD = true>
 __device__ __forceinline__ void tcw_backward(TcwSmem& s, TcwState& st, float wt, float L0, float L1, bool valid, const float* H2, float* J) {
     const int t = threadIdx.x;
     const float wv = valid ? wt : 0.0f;
@@ -171,7 +172,7 @@ __device__ __forceinline__ void tcw_backward(TcwSmem& s, TcwState& st, float wt,
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (t == 0) {
+    if (GRAD && t == 0) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t acc0 = st.gfirst ? 0u : 1u;
 #pragma unroll
@@ -184,7 +185,7 @@ __device__ __forceinline__ void tcw_backward(TcwSmem& s, TcwState& st, float wt,
                      umma_smem_desc(smem_u32(s.TC) + k * 2 * (TC_TC_F / 8) * 128, (TC_TC_F / 8) * 128, 128), tc_idesc(128, TC_TC_F, 1, 1), (k > 0) ? 1u : acc0);
         umma_commit(&s.barG);
     }
-    st.gfirst = false; st.gpend = true;
+    if (GRAD) { st.gfirst = false; st.gpend = true; }
 }
 
 __device__ __forceinline__ void tcw_teardown(TcwSmem& s) {
@@ -242,8 +243,10 @@ __global__ void __launch_bounds__(TCW_M) mlp_tcw_forward_kernel(const __grid_con
     tcw_teardown(s);
 }
 
-// ---- fused reverse pass, InterpolatingAdjoint (same stage sequence as mlp_reverse_kernel) ----
-template <int COST>
+// ---- fused reverse pass (same stage sequence as mlp_reverse_kernel): InterpolatingAdjoint, or GaussAdjoint (GAUSS: seven
+// adjoint stages without gradient GEMMs, then the gradient GEMMs at the three Gauss-Legendre nodes of the step, weight (h/2) w_g,
+// accumulated in the same TMEM tiles) ----
+template <int COST, bool GAUSS = false>
 __global__ void __launch_bounds__(TCW_M) mlp_tcw_reverse_kernel(const __grid_constant__ MlpArgs<float> a) {
     extern __shared__ __align__(128) unsigned char tcw_smem_raw[];
     TcwSmem& s = *reinterpret_cast<TcwSmem*>(tcw_smem_raw);
@@ -254,7 +257,7 @@ __global__ void __launch_bounds__(TCW_M) mlp_tcw_reverse_kernel(const __grid_con
     const Tsit5Tables& tb = a.tb;
     tcw_setup(s, a.p);
     TcwState st;
-    float lam[2] = {0.0f, 0.0f}, uhi[2], ulo[2], kf[7][2], ka[6][2], H2[64], F[2], J[2];
+    float lam[2] = {0.0f, 0.0f}, uhi[2], ulo[2], kf[7][2], ka[7][2], H2[64], F[2], J[2];
     auto cotangent = [&](int ks, const float* yy) {
         if (COST == COST_EXPLICIT) { lam[0] += a.dLdu[((int64_t)ks * 2) * N + col]; lam[1] += a.dLdu[((int64_t)ks * 2 + 1) * N + col]; }
         else { lam[0] += (float)(a.cost_a[0] * (double)yy[0] + a.cost_b[0]); lam[1] += (float)(a.cost_a[1] * (double)yy[1] + a.cost_b[1]); }
@@ -283,24 +286,39 @@ __global__ void __launch_bounds__(TCW_M) mlp_tcw_reverse_kernel(const __grid_con
                 tcw_forward<true>(s, st, y[0], y[1], kf[sg], H2);
             }
         }
-        // ---- adjoint stages 0..5 ----
+        // ---- adjoint stages 0..5 (GaussAdjoint: 0..6, the 7th derivative feeds the dense output of the adjoint step) ----
 #pragma unroll 1
-        for (int sg = 0; sg <= 5; sg++) {
+        for (int sg = 0; sg <= (GAUSS ? 6 : 5); sg++) {
             float L[2], y[2];
 #pragma unroll
             for (int c = 0; c < 2; c++) {
                 double l = (double)lam[c];
-                for (int j = 0; j < sg; j++) l = fma(tb.hA[sg][j], (double)ka[j][c], l);
+                for (int j = 0; j < sg && j < 6; j++) l = fma(tb.hA[sg][j], (double)ka[j][c], l);
                 L[c] = (float)l;
                 double yv;
                 if (sg == 0) yv = (double)uhi[c];
-                else if (sg == 5) yv = (double)ulo[c];
+                else if (sg >= 5) yv = (double)ulo[c];
                 else { yv = (double)ulo[c]; for (int j = 0; j < 7; j++) yv = fma(tb.hBst[sg - 1][j], (double)kf[j][c], yv); }
                 y[c] = (float)yv;
             }
             tcw_forward<true>(s, st, y[0], y[1], F, H2);
-            tcw_backward(s, st, (float)tb.hA[6][sg], L[0], L[1], live, H2, J);
+            if (GAUSS) tcw_backward<false>(s, st, 1.0f, L[0], L[1], live, H2, J);
+            else tcw_backward<true>(s, st, (float)tb.hA[6][sg], L[0], L[1], live, H2, J);
             ka[sg][0] = J[0]; ka[sg][1] = J[1];
+        }
+        if (GAUSS) {
+#pragma unroll 1
+            for (int gq = 0; gq < 3; gq++) {
+                float L[2], y[2];
+#pragma unroll
+                for (int c = 0; c < 2; c++) {
+                    double l = (double)lam[c], yv = (double)ulo[c];
+                    for (int j = 0; j < 7; j++) { l = fma(tb.hBq[gq][j], (double)ka[j][c], l); yv = fma(tb.hBq[2 - gq][j], (double)kf[j][c], yv); }
+                    L[c] = (float)l; y[c] = (float)yv;
+                }
+                tcw_forward<true>(s, st, y[0], y[1], F, H2);
+                tcw_backward<true>(s, st, (float)tb.hGW[gq], L[0], L[1], live, H2, J);
+            }
         }
 #pragma unroll
         for (int c = 0; c < 2; c++) {

@@ -30,15 +30,18 @@ def _rel(a, ref):
 @pytest.mark.parametrize("dtype,tol_u,tol_p", [("f64", 1e-9, 1e-9), ("f32", 2e-5, 1e-5)])
 @pytest.mark.parametrize("cost", ["affine", "explicit"])
 @pytest.mark.parametrize("N", [100, 4096])
-def test_mlp_interpolating_parity(dtype, tol_u, tol_p, cost, N):
+@pytest.mark.parametrize("sensealg", ["interpolating", "gauss"])
+def test_mlp_interpolating_parity(dtype, tol_u, tol_p, cost, N, sensealg):
+    """InterpolatingAdjoint, and GaussAdjoint -- the reference's default choice once length(u0) + length(p) > 100
+    (src/concrete_solve.jl:291-316; P = 4482 here)."""
     T, dt = 1.5, 0.05
     saveat = np.linspace(0.05, T, 30)
     rng = np.random.default_rng(0)
     u0 = rng.uniform(-2, 2, (2, N)); p = _weights()
     assert p.size == P
-    cfg = O.make_cfg("mlp", "interpolating", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
+    cfg = O.make_cfg("mlp", sensealg, "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H)
     ref = O.gradient(cfg, saveat, u0, p)
-    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype=dtype,
+    eng = b.DeviceEnsemble("mlp", sensealg, "tsit5_fixed", N, saveat, (0.0, T), dt, dtype=dtype,
                            cost=b.AffineCost(1.0, -0.5) if cost == "affine" else None)
     saved, status = eng.forward(u0, p)
     assert (status == 0).all()
@@ -54,9 +57,10 @@ BLOCKS = {"W1": slice(0, 2 * H), "b1": slice(2 * H, 3 * H), "W2": slice(3 * H, 3
           "W3": slice(4 * H + H * H, 6 * H + H * H), "b3": slice(6 * H + H * H, P)}
 
 
-@pytest.mark.parametrize("N", [100, 4096])
+@pytest.mark.parametrize("N", [100, 4096, 12000])
 @pytest.mark.parametrize("cost", ["affine", "explicit"])
-def test_mlp_bf16_tensor_core_path(N, cost):
+@pytest.mark.parametrize("sensealg", ["interpolating", "gauss"])
+def test_mlp_bf16_tensor_core_path(N, cost, sensealg):
     """dtype = bf16_f32acc (csrc/mlp_tc.cuh): every GEMM-shaped piece of the time loop -- the hidden-layer products of f and
     of its VJP, and ALL parameter-gradient contractions over the members -- runs on tcgen05 with bf16 operands and fp32 TMEM
     accumulators.  BASELINE C4: <= 2e-2 relative to the fp64 oracle for the bf16 path (observed 1e-3 .. 7e-3)."""
@@ -65,9 +69,10 @@ def test_mlp_bf16_tensor_core_path(N, cost):
     rng = np.random.default_rng(0)
     u0 = rng.uniform(-2, 2, (2, N)); p = _weights()
     dL = None if cost == "affine" else rng.standard_normal((30, 2, N))
-    cfg = O.make_cfg("mlp", "interpolating", "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5) if cost == "affine" else ("explicit",), mlp_hidden=H)
+    # N = 100, 4096: the 32-member layout (mlp_tc.cuh); N = 12000 (> 2 x 148 x 32): the 128-member layout (mlp_tc_wide.cuh)
+    cfg = O.make_cfg("mlp", sensealg, "tsit5_fixed", N, saveat, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5) if cost == "affine" else ("explicit",), mlp_hidden=H)
     ref = O.gradient(cfg, saveat, u0, p, dLdu=dL)
-    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", N, saveat, (0.0, T), dt, dtype="bf16_f32acc",
+    eng = b.DeviceEnsemble("mlp", sensealg, "tsit5_fixed", N, saveat, (0.0, T), dt, dtype="bf16_f32acc",
                            cost=b.AffineCost(1.0, -0.5) if cost == "affine" else None)
     saved, status = eng.forward(u0, p)
     assert (np.asarray(status) == 0).all()
@@ -101,7 +106,7 @@ def test_mlp_bf16_members_not_a_multiple_of_the_tile():
 def test_mlp_unsupported_combinations_fail_loudly():
     saveat = np.linspace(0.05, 1.5, 30)
     with pytest.raises(b.B200AdjError) as ei:
-        b.DeviceEnsemble("mlp", "gauss", "tsit5_fixed", 64, saveat, (0.0, 1.5), 0.05)
+        b.DeviceEnsemble("mlp", "backsolve", "tsit5_fixed", 64, saveat, (0.0, 1.5), 0.05)
     assert ei.value.code == -2
     with pytest.raises(b.B200AdjError):
         b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", 64, saveat, (0.0, 1.5), 0.05, shared_p=False)

@@ -104,5 +104,5 @@ def test_unsupported_configs_fail_loudly():
         b.solve(prob, b.Tsit5(dt=0.03), saveat=[0.3])
     mprob = b.EnsembleProblem(b.ODEProblem("mlp", np.zeros(2), (0.0, 1.0), np.zeros(4482)), u0s=np.zeros((2, 8)))
     msol = b.solve(mprob, b.Tsit5(dt=0.05), saveat=0.5)
-    with pytest.raises(b.B200AdjError):                          # GaussAdjoint is not built for the MLP family
-        b.adjoint_sensitivities(msol, b.Tsit5(dt=0.05), t=msol.t, dgdu_discrete=b.AffineCost(1.0, 0.0), sensealg=b.GaussAdjoint())
+    with pytest.raises(b.B200AdjError):                          # QuadratureAdjoint is not built for the MLP family
+        b.adjoint_sensitivities(msol, b.Tsit5(dt=0.05), t=msol.t, dgdu_discrete=b.AffineCost(1.0, 0.0), sensealg=b.QuadratureAdjoint())
