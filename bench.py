@@ -281,6 +281,8 @@ def spec_c2(T=None):
 class Shard:
     """one rank's device-resident engine for a workload spec (+ NCCL communicator behind the C ABI when world > 1)"""
 
+    nccl_allreduce = False        # --nccl-allreduce: A/B against the all-reduce fused into the reverse kernel
+
     def __init__(self, spec, n_local, rank, world, local, block=0):
         import torch
         import scimlsensitivity_jl_b200 as b
@@ -288,7 +290,7 @@ class Shard:
         self.spec, self.n, self.torch = spec, n_local, torch
         self.eng = b.DeviceEnsemble(spec["family"], spec["sensealg"], spec["stepper"], n_local, spec["saveat"], (0.0, spec["T"]), spec["dt"],
                                     on_device=True, device=local, dtype=spec["dtype"], cost=b.AffineCost(*spec["cost"]),
-                                    traj_offset=rank * n_local, block_threads=block, **spec["ekw"])
+                                    traj_offset=rank * n_local, block_threads=block, nccl_allreduce=Shard.nccl_allreduce, **spec["ekw"])
         self.eng.use_current_torch_stream()
         if world > 1:
             D.attach_comm(self.eng)
@@ -541,6 +543,8 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": c2_config(world, N, args.block),
             "phases_ms": {"forward": fwd_ms, "reverse_incl_allreduce": rev_ms},
+            "allreduce": None if world == 1 else ("ncclAllReduce (flag)" if args.nccl_allreduce else
+                                                  "fused into the reverse kernel (peer-memory mailboxes) when the GPUs map each other, else ncclAllReduce"),
             "roofline": {"bound": "hbm", "kernel": "tsit5_reverse_kernel<Lorenz,GAUSS>", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
@@ -705,9 +709,11 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c2f32", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
     ap.add_argument("--dtype", default="", help="c4 only: bf16_f32acc (default), f32 or f64")
     ap.add_argument("--no-secondary", action="store_true", help="skip the sharded C4 / C5 legs (profiling runs)")
+    ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1: ncclAllReduce instead of the fused peer-memory all-reduce (A/B)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    Shard.nccl_allreduce = args.nccl_allreduce
     _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)

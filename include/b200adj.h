@@ -71,8 +71,10 @@ enum { B200ADJ_COST_EXPLICIT = 0, B200ADJ_COST_AFFINE = 1 };
 #define B200ADJ_FLAG_DENSE_FORWARD      64u   /* fixed-step Tsit5: keep the DENSE forward solution (k1..k7 per step, per member) so   */
                                               /* that save / jump times may lie off the dt grid (chosen automatically when cfg.saveat */
                                               /* has off-grid entries; set it to re-target the reverse pass to off-grid times later)  */
+#define B200ADJ_FLAG_NCCL_ALLREDUCE    128u   /* multi-GPU: sum dp with ncclAllReduce instead of the all-reduce fused into the reverse    */
+                                              /* kernel over peer-memory mailboxes (the default whenever the GPUs can map each other)    */
 /* flags fixed at create (the others can be changed per reverse pass by b200adj_set_reverse_options) */
-#define B200ADJ_CREATE_FLAGS (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE | B200ADJ_FLAG_NO_ROTATE | B200ADJ_FLAG_DENSE_FORWARD)
+#define B200ADJ_CREATE_FLAGS (B200ADJ_FLAG_STORED_NOISE | B200ADJ_FLAG_TRACE | B200ADJ_FLAG_NO_ROTATE | B200ADJ_FLAG_DENSE_FORWARD | B200ADJ_FLAG_NCCL_ALLREDUCE)
 
 /* error codes */
 #define B200ADJ_OK                 0
@@ -193,8 +195,11 @@ int32_t b200adj_get_block_trace(void* handle, uint64_t* out, int32_t* nblocks);
  * One handle per GPU (one process per GPU, or several handles in one process); each handle owns cfg.N members of the
  * ensemble (cfg.traj_offset = global index of its first member).  Rank 0 obtains a 128-byte id, the host broadcasts it over
  * its own channel (Distributed.jl / MPI / a file), every rank attaches its handle.  From then on b200adj_reverse sums dp over
- * the ranks (ncclAllReduce on the handle's stream, before the D2H copy) whenever shared_p = 1: the single collective of the
- * path.  du0 and per-member dp stay sharded.  NCCL is bound with dlopen at the first call; without a usable libnccl.so.2
+ * the ranks whenever shared_p = 1: the single collective of the path.  When the GPUs can map each other's memory (CUDA IPC /
+ * peer access over NVLink) the sum is FUSED into the fixed-step reverse kernel: its last block stores its dp into a mailbox
+ * in every peer's HBM, publishes an epoch flag, waits for the peers' flags and adds the slots in rank order -- no collective
+ * launch at all (csrc/ode_tsit5.cuh::reduce_dp, csrc/comm.cu).  Otherwise, and for the other steppers, ncclAllReduce on the
+ * handle's stream before the D2H copy.  du0 and per-member dp stay sharded.  NCCL is bound with dlopen at the first call; without a usable libnccl.so.2
  * these return B200ADJ_ERR_UNSUPPORTED and single-GPU use is unaffected. */
 int32_t b200adj_comm_unique_id(void* id_out /* 128 bytes */);
 int32_t b200adj_comm_init(void* handle, int32_t nranks, int32_t rank, const void* unique_id /* 128 bytes; NULL if nranks == 1 */);
@@ -205,6 +210,8 @@ int32_t b200adj_comm_init_all(void** handles, int32_t n);
 /* in-place sum of `count` reals (cfg.dtype's ABI element type) over the ranks, on the handle's stream; device pointer */
 int32_t b200adj_comm_allreduce(void* handle, void* buf, int64_t count);
 int32_t b200adj_comm_size(void* handle, int32_t* nranks, int32_t* rank);
+/* 1 when the peer mailboxes are mapped and the fixed-step reverse kernel reduces dp itself (no collective launch), else 0 */
+int32_t b200adj_comm_is_fused(void* handle);
 
 int32_t b200adj_destroy(void* handle);
 const char* b200adj_last_error(void* handle);   /* handle may be NULL: last create() error of this thread */

@@ -5,6 +5,7 @@ hand-written sm_100a CUDA kernels behind a C ABI (include/b200adj.h), with this 
 reference's `sensealg=` plugin surface.  Import as `scimlsensitivity_jl_b200` (the directory name carries a dot).
 """
 from . import _lib
+from . import distributed
 from ._lib import B200AdjError, build
 from .concrete_solve import (ChainRulesOriginator, NoTangent, ReverseDiffOriginator, TrackerOriginator,
                              _concrete_solve_adjoint, clear_handle_cache, solve)

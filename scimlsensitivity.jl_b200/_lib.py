@@ -18,13 +18,13 @@ SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kr
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
 DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
 COST = {"explicit": 0, "affine": 1}
-FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE, FLAG_NO_ROTATE, FLAG_DENSE_FORWARD = 1, 2, 4, 8, 16, 32, 64
+FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE, FLAG_NO_ROTATE, FLAG_DENSE_FORWARD, FLAG_NCCL_ALLREDUCE = 1, 2, 4, 8, 16, 32, 64, 128
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
 EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_register_family", "b200adj_family_info", "b200adj_set_events", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg",
-           "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_init_all", "b200adj_comm_allreduce", "b200adj_comm_size"]
+           "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_init_all", "b200adj_comm_allreduce", "b200adj_comm_size", "b200adj_comm_is_fused"]
 
 
 class B200AdjError(RuntimeError):
@@ -160,6 +160,8 @@ def load():
         lib.b200adj_comm_init_all.restype = C.c_int32
         lib.b200adj_comm_allreduce.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
         lib.b200adj_comm_allreduce.restype = C.c_int32
+        lib.b200adj_comm_is_fused.argtypes = [C.c_void_p]
+        lib.b200adj_comm_is_fused.restype = C.c_int32
         lib.b200adj_comm_size.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         lib.b200adj_comm_size.restype = C.c_int32
         lib.b200adj_last_error.argtypes = [C.c_void_p]
@@ -287,6 +289,10 @@ class Handle:
 
     def comm_allreduce(self, buf, count):
         self._check(self._lib.b200adj_comm_allreduce(self._h, _addr(buf), int(count)))
+
+    @property
+    def comm_is_fused(self):
+        return bool(self._lib.b200adj_comm_is_fused(self._h))
 
     @property
     def comm_size(self):

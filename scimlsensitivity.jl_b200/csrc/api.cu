@@ -737,6 +737,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         ddu0 = h->s_du0; ddp = h->s_dp;
     }
     int rc = 0;
+    bool fused_allreduce = false;
     if (h->adaptive && (c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE || h->fixed_dt)) {
         T5aArgs a = t5a_args(h);
         a.p = h->cur_p; a.dLdu = dL; a.du0 = ddu0; a.dp_members = ddp; a.dp = ddp;
@@ -782,6 +783,10 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         memset(&a, 0, sizeof(a));
         a.event_of_step = h->d_event_of_step; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc; a.nev = h->nev;
         tsit5_weights(0.0, nullptr, a.Rpoly); a.hstep = c.dt;
+        if (c.shared_p && comm_fused_ready(h) && !(c.flags & B200ADJ_FLAG_NCCL_ALLREDUCE) && c.sensealg != B200ADJ_SA_QUADRATURE && !h->has_dgdp && !(h->has_cdgdp && h->cont_on)) {
+            // the all-reduce of dp is fused into this kernel's last block (peer-memory mailboxes): no collective launch
+            a.p2p = h->p2p; a.p2p.epoch = ++h->p2p_epoch; fused_allreduce = true;
+        }
         a.ckpt = h->d_ckpt; a.p = h->cur_p; a.dLdu = dL; a.save_of_step = h->d_save_of_step;
         a.du0 = ddu0; a.dp_members = ddp; a.partials = h->d_partials; a.dp = ddp; a.ticket = h->d_ticket;
         a.N = c.N; a.Npad = h->Npad; a.S = h->S; a.tb = h->tb; a.trace = h->d_trace;
@@ -826,7 +831,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         CUDA_TRY(h, cudaGetLastError());
     }
     // multi-GPU: the ONE collective of the path -- dG/dp summed over the ranks (shared parameters only)
-    if (c.shared_p && h->nranks > 1) { rc = comm_allreduce(h, ddp, (size_t)c.P); if (rc) return rc; }
+    if (c.shared_p && h->nranks > 1 && !fused_allreduce) { rc = comm_allreduce(h, ddp, (size_t)c.P); if (rc) return rc; }
     if (!c.buffers_on_device) {
         CUDA_TRY(h, cudaMemcpyAsync(du0, h->s_du0, c.d * N * e, cudaMemcpyDeviceToHost, h->stream));
         CUDA_TRY(h, cudaMemcpyAsync(dp, h->s_dp, pn * e, cudaMemcpyDeviceToHost, h->stream));

@@ -77,6 +77,11 @@ struct Handle {
     Tsit5Tables tb;
     // multi-GPU (comm.cu): one NCCL communicator per handle, dp all-reduced on the handle's stream
     void* nccl_comm = nullptr; int nranks = 1, rank = 0;
+    // fused all-reduce over peer memory (ode_tsit5.cuh::reduce_dp): this handle's mailbox, the peers' mailboxes mapped here
+    P2PComm p2p = {};                 // p2p.nranks > 1 once the mailboxes are exchanged
+    void* p2p_mailbox = nullptr;      // owned
+    void* p2p_ipc_open[P2P_MAXRANKS] = {nullptr};   // cudaIpcOpenMemHandle mappings to close
+    unsigned long long p2p_epoch = 0;
     std::string err;
 };
 
@@ -137,6 +142,7 @@ int mlp_forward_dispatch(Handle* h, const void* u0, const void* p, void* saved, 
 int mlp_reverse_dispatch(Handle* h, const void* dLdu, void* du0, void* dp);
 int comm_allreduce(Handle* h, void* buf, size_t count);     // comm.cu: in-place sum over ranks on h->stream (no-op without a communicator)
 void comm_release(Handle* h);
+bool comm_fused_ready(const Handle* h);    // the peer mailboxes of the fused all-reduce are mapped
 
 // persistent grid of the quadrature kernels and the dynamic shared memory (block maxima of the key array) per block
 inline int quad_grid(int64_t N, int nsm) { const int64_t g = (N + QUAD_WARPS - 1) / QUAD_WARPS, cap = (int64_t)nsm * QUAD_BLOCKS_PER_SM; return (int)(g < cap ? g : cap); }

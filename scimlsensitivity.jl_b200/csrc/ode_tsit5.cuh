@@ -37,6 +37,15 @@ template <class R> struct Tsit5TablesT {
 };
 using Tsit5Tables = Tsit5TablesT<double>;
 
+// mailboxes of the fused cross-GPU all-reduce of dG/dp (see reduce_dp below)
+constexpr int P2P_PMAX = 8, P2P_MAXRANKS = 8;
+struct P2PComm {
+    double* slots[P2P_MAXRANKS];              // slots[r]: mailbox of rank r as seen from this device
+    unsigned long long* flags[P2P_MAXRANKS];  // flags[r]: epoch counters of rank r's mailbox
+    int32_t nranks, rank;                     // nranks <= 1: not used
+    unsigned long long epoch;                 // this gradient's epoch (1, 2, ...: every rank launches the same sequence)
+};
+
 enum { SA_INTERP = 0, SA_GAUSS = 1, SA_QUAD = 2, SA_BACKSOLVE = 3, SA_GK = 4 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
 
@@ -81,6 +90,7 @@ template <class R> struct OdeRevArgsT {
     const int32_t* event_of_step; const double* ev_s; const double* ev_c; const double* ev_ps; const double* ev_pc; int32_t nev;   // EV kernels
     R Rpoly[7][4];               // SA_GK: dense-output polynomials b_j(theta) = sum_m Rpoly[j][m] theta^(m+1)
     R hstep;                     // SA_GK: the step size
+    P2PComm p2p;                 // fused cross-GPU all-reduce of dp (nranks <= 1: off)
     Tsit5TablesT<R> tb;
 };
 using OdeRevArgs = OdeRevArgsT<double>;
@@ -218,10 +228,21 @@ __global__ void __launch_bounds__(512) tsit5_forward_kernel(const __grid_constan
     }
 }
 
+// ---- fused all-reduce of dG/dp over the GPUs of one box ("fuse the last reverse-step block reduction with the
+// allreduce") ----  Every rank owns a MAILBOX in its HBM: slots[2 parities][nranks][P2P_PMAX] doubles + flags[nranks] epoch
+// counters, mapped into every peer (CUDA IPC / peer access over NVLink; comm.cu).  The last block of the reverse kernel
+// writes its dG/dp into slot [rank] of EVERY mailbox (peer stores), publishes the epoch in every mailbox' flags[rank]
+// (st.release.sys), waits until its own mailbox shows the epoch from all ranks (ld.acquire.sys) and sums the slots in rank
+// order -- the same bits on every rank, no collective kernel, no extra launch.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { unsigned long long v; asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+
 // deterministic block reduction of P per-thread values -> partials[block][P]; the last block to finish sums the
 // partials in index order (fixed order => bitwise reproducible for a given grid), no floating-point atomics.
+// pc (optional): the fused cross-GPU all-reduce above.
 template <int P, class RO>
-__device__ __forceinline__ void reduce_dp(const double* acc, double* partials, RO* dp, unsigned int* ticket) {
+__device__ __forceinline__ void reduce_dp(const double* acc, double* partials, RO* dp, unsigned int* ticket, const P2PComm* pc = nullptr) {
     __shared__ double s_red[16 * P];               // up to 512 threads per block
     const int nwarps = (int)(blockDim.x >> 5);
     __shared__ bool s_last;
@@ -254,7 +275,33 @@ __device__ __forceinline__ void reduce_dp(const double* acc, double* partials, R
             for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(partials + (int64_t)b * P + q);
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-            if (lane == 0) dp[q] = (RO)v;
+            if (lane == 0) {
+                if (pc && pc->nranks > 1) {
+                    const int par = (int)(pc->epoch & 1ull);
+                    for (int r = 0; r < pc->nranks; r++) pc->slots[r][(size_t)(par * pc->nranks + pc->rank) * P2P_PMAX + q] = v;     // peer stores
+                } else dp[q] = (RO)v;
+            }
+        }
+        if (pc && pc->nranks > 1) {
+            __syncthreads();                      // every slot of this rank is on its way
+            if (threadIdx.x == 0) {
+                __threadfence_system();
+                for (int r = 0; r < pc->nranks; r++) st_release_sys(pc->flags[r] + pc->rank, pc->epoch);
+                bool ok = true;
+                const long long t0 = clock64();
+                for (int r = 0; r < pc->nranks; r++)
+                    while (ld_acquire_sys(pc->flags[pc->rank] + r) < pc->epoch) {
+                        if (clock64() - t0 > 8000000000LL) { ok = false; break; }      // ~4 s: a peer that never launched -- fail loudly
+                    }
+                s_last = ok;                      // reuse: false => poison the result
+            }
+            __syncthreads();
+            if (threadIdx.x < P) {
+                const int par = (int)(pc->epoch & 1ull);
+                double tot = 0.0;
+                for (int r = 0; r < pc->nranks; r++) tot += ld_relaxed_sys_f64(pc->slots[pc->rank] + (size_t)(par * pc->nranks + r) * P2P_PMAX + threadIdx.x);
+                dp[threadIdx.x] = s_last ? (RO)tot : (RO)__longlong_as_double(0x7ff8000000000000LL);
+            }
         }
         if (threadIdx.x == 0) *ticket = 0;   // re-arm for the next launch
     }
@@ -681,7 +728,7 @@ __global__ void __maxnreg__(B200_REV_MAXREG) tsit5_reverse_kernel(const __grid_c
         double mud[P];                         // block / grid reduction in fp64 for both precisions
 #pragma unroll
         for (int q = 0; q < P; q++) mud[q] = (double)mu[q];
-        reduce_dp<P>(mud, a.partials, a.dp, a.ticket);
+        reduce_dp<P>(mud, a.partials, a.dp, a.ticket, &a.p2p);
     } else if (active) {
 #pragma unroll
         for (int q = 0; q < P; q++) a.dp_members[(int64_t)q * N + i] = mu[q];

@@ -20,7 +20,7 @@ class DeviceEnsemble:
                  on_device=False, device=0, no_start=False, checkpointing=True, ckpt_every_step=False,
                  stored_noise=False, seed=0, traj_offset=0, block_threads=0, abstol=1e-6, reltol=1e-3,
                  quad_abstol=1e-6, quad_reltol=1e-3, dtype="f64", trace=False, max_steps=0, pin_outputs=False,
-                 checkpoint_every=1, no_rotate=False, dense_forward=False):
+                 checkpoint_every=1, no_rotate=False, dense_forward=False, nccl_allreduce=False):
         d, P, m = FAMILIES[family]
         cfg = _lib.Cfg()
         cfg.rhs_family, cfg.sensealg, cfg.stepper, cfg.dtype = _lib.FAM[family], _lib.SA[sensealg], _lib.ST[stepper], _lib.DTYPE[dtype]
@@ -54,6 +54,8 @@ class DeviceEnsemble:
             flags |= _lib.FLAG_NO_ROTATE
         if dense_forward:
             flags |= _lib.FLAG_DENSE_FORWARD
+        if nccl_allreduce:
+            flags |= _lib.FLAG_NCCL_ALLREDUCE
         cfg.flags, cfg.block_threads = flags, int(block_threads)
         self.family, self.d, self.P, self.m, self.N, self.K = family, d, P, m, int(N), len(saveat)
         self.shared_p, self.on_device, self.device = bool(shared_p), bool(on_device), int(device)

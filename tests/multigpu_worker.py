@@ -30,6 +30,18 @@ def main():
     du0, dp = b.adjoint_sensitivities(sol, b.Tsit5(dt=dt), t=t, dgdu_discrete=b.AffineCost(1.0, -2.0), sensealg=b.GaussAdjoint())
     # the all-reduce ran behind the C ABI (b200adj_comm_init + ncclAllReduce inside b200adj_reverse), not in torch.distributed
     assert sol.engine.comm_attached and sol.engine.handle.comm_size == (world, rank)
+    fused = sol.engine.handle.comm_is_fused       # peer-memory mailboxes mapped: the reverse kernel reduced dp itself
+    # the same gradient through ncclAllReduce (flag) must agree to the last bits of a 2-term sum
+    eng_n = b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", hi - lo, t, (0.0, T), dt, cost=b.AffineCost(1.0, -2.0), device=local, nccl_allreduce=True)
+    b.distributed.attach_comm(eng_n)
+    assert not eng_n.handle.comm_is_fused
+    eng_n.forward(u0[:, lo:hi], p)
+    _, dp_n = eng_n.reverse()
+    assert np.allclose(np.asarray(dp_n).ravel(), np.asarray(dp).ravel(), rtol=1e-13, atol=0)
+    for _ in range(3):                             # repeated gradients on one handle: epochs / parities of the mailboxes
+        _, dp_again = b.adjoint_sensitivities(sol, b.Tsit5(dt=dt), t=t, dgdu_discrete=b.AffineCost(1.0, -2.0), sensealg=b.GaussAdjoint())
+        assert np.array_equal(np.asarray(dp_again), np.asarray(dp))
+    eng_n.close()
     cfg = O.make_cfg("lorenz", "gauss", "tsit5_fixed", N, t, 0.0, T, dt=dt, cost=("affine", 1.0, -2.0))
     ref = O.gradient(cfg, t, u0, p)
     e_dp = np.abs(dp.ravel() - ref["dp"]).max() / np.abs(ref["dp"]).max()
@@ -47,7 +59,7 @@ def main():
         scfg = O.make_cfg("sde_lv", "backsolve", "em", N, ssol.t, 0.0, 1.0, dt=0.01, cost=("affine", 0.0, 1.0))
         sref = O.gradient(scfg, ssol.t, np.ones((2, N)), np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1]), dW=Wfull)
         e_s = np.abs(sdp.ravel() - sref["dp"]).max() / np.abs(sref["dp"]).max()
-        print(f"MULTIGPU world={world} dp_err={e_dp:.2e} du0_err={e_u:.2e} sde_dp_err={e_s:.2e}")
+        print(f"MULTIGPU world={world} fused_allreduce={fused} dp_err={e_dp:.2e} du0_err={e_u:.2e} sde_dp_err={e_s:.2e}")
         ok = e_dp < 1e-8 and e_u < 1e-8 and e_s < 1e-9
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)
