@@ -41,7 +41,7 @@
 #endif
 
 /* ---- enums: values shared (by convention, not by include) with include/b200adj.h ---- */
-enum { FAM_LV = 0, FAM_LORENZ = 1, FAM_ROBERTSON = 2, FAM_SDE_LV = 3, FAM_MLP = 4, FAM_SDE_LINEAR = 5 };
+enum { FAM_LV = 0, FAM_LORENZ = 1, FAM_ROBERTSON = 2, FAM_SDE_LV = 3, FAM_MLP = 4, FAM_SDE_LINEAR = 5, FAM_BALL = 6 };
 enum { SA_INTERPOLATING = 0, SA_GAUSS = 1, SA_QUADRATURE = 2, SA_BACKSOLVE = 3, SA_GAUSSKRONROD = 4 };
 enum { ST_TSIT5_FIXED = 0, ST_ROSENBROCK23 = 1, ST_EM = 2, ST_EULER_HEUN = 3, ST_TSIT5_ADAPTIVE = 4 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
@@ -75,6 +75,14 @@ typedef struct {
      *   running   g(u, p) = sum_j cont_av_j/2 u_j^2 + cont_bv_j u_j + sum_q cdgdp_c_q/2 p_q^2 + cdgdp_e_q p_q
      * dgdu = a .* u + b, dgdp = c .* p + e  (test/Core7/mixed_costs.jl: g = u1^2 + p1 is a = [2, 0], e = [1, 0, 0, 0]). */
     const double *cost_av, *cost_bv, *cont_av, *cont_bv, *dgdp_c, *dgdp_e, *cdgdp_c, *cdgdp_e;
+    /* continuous (root-finding) callback of the named family "coordinate crossing + affine affect" (ContinuousCallback,
+     * src/callback_tracking.jl:232-480; docs/src/examples/hybrid_jump/bouncing_ball.md): condition u[cc_idx] - cc_level
+     * crossing zero in direction cc_dir (-1 down, +1 up, 0 either); affect u <- cc_scale .* u + cc_shift and, when
+     * cc_pcomp >= 0, u[cc_pcomp] <- cc_psign * p[cc_pparam] * u[cc_pcomp] ("v = -e v").  Adaptive Tsit5.  The per-member
+     * event times found by the forward solve are returned through cc_found_* (member-local copies of the cfg). */
+    int32_t cc_on, cc_idx, cc_dir, cc_pcomp, cc_pparam, cc_found;
+    double cc_level, cc_psign;
+    const double *cc_scale, *cc_shift;
 } oracle_cfg;
 #define COST_A(c, j) ((c)->cost_av ? (c)->cost_av[j] : (c)->cost_a)
 #define COST_B(c, j) ((c)->cost_bv ? (c)->cost_bv[j] : (c)->cost_b)
@@ -104,6 +112,17 @@ static void vjp_lv(const double* u, const double* p, double t, const double* l, 
     dl[0] = l[0] * (p[0] - p[1] * y) + l[1] * p[3] * y;
     dl[1] = -l[0] * p[1] * x + l[1] * (-p[2] + p[3] * x);
     if (dg) { dg[0] = x * l[0]; dg[1] = -x * y * l[0]; dg[2] = -y * l[1]; dg[3] = x * y * l[1]; }
+}
+/* bouncing ball (docs/src/examples/hybrid_jump/bouncing_ball.md): x' = v, v' = -p1; p = [gravity, restitution] (the
+ * restitution coefficient only enters through the callback's affect) */
+static void f_ball(const double* u, const double* p, double t, double* du, const fam_ctx* c) {
+    (void)t; (void)c;
+    du[0] = u[1]; du[1] = -p[0];
+}
+static void vjp_ball(const double* u, const double* p, double t, const double* l, double* dl, double* dg, const fam_ctx* c) {
+    (void)t; (void)c; (void)u; (void)p;
+    dl[0] = 0.0; dl[1] = l[0];
+    if (dg) { dg[0] = -l[1]; dg[1] = 0.0; }
 }
 static void f_lorenz(const double* u, const double* p, double t, double* du, const fam_ctx* c) {
     (void)t; (void)c;
@@ -259,6 +278,7 @@ static int family_init(family_t* F, const oracle_cfg* c) {
     switch (c->family) {
     case FAM_LV:        F->d = 2; F->P = 4; F->f = f_lv; F->vjp = vjp_lv; break;
     case FAM_LORENZ:    F->d = 3; F->P = 3; F->f = f_lorenz; F->vjp = vjp_lorenz; break;
+    case FAM_BALL:      F->d = 2; F->P = 2; F->f = f_ball; F->vjp = vjp_ball; break;
     case FAM_ROBERTSON: F->d = 3; F->P = 3; F->f = f_rober; F->vjp = vjp_rober; break;
     case FAM_SDE_LV:    F->d = 2; F->P = 6; F->m = 2; F->f = f_sdelv; F->vjp = vjp_sdelv; F->f_ito = fito_sdelv; F->vjp_ito = vjpito_sdelv; break;
     case FAM_MLP:       F->d = 2; F->P = c->P; F->f = f_mlp; F->vjp = vjp_mlp;
@@ -516,8 +536,18 @@ static void forward_tsit5_fixed(const family_t* F, const double* p, const double
 
 /* Adaptive Tsit5 forward solve (PI controller beta1=7/50, beta2=2/25, gamma=0.9, qmin=1/5, qmax=10;
  * [UPSTREAM OrdinaryDiffEq defaults], error norm = RMS of err/(abstol+reltol*max(|u|,|unew|))). */
+/* member-local event list a forward solve with a continuous callback produces */
+typedef struct { int n, cap; double *t, *scale, *shift; } cc_events;
+static void cc_push(cc_events* E, int d, double tau, const double* sc, const double* sh) {
+    if (E->n == E->cap) { E->cap = E->cap ? 2 * E->cap : 16; E->t = (double*)realloc(E->t, sizeof(double) * E->cap);
+        E->scale = (double*)realloc(E->scale, sizeof(double) * E->cap * d); E->shift = (double*)realloc(E->shift, sizeof(double) * E->cap * d); }
+    E->t[E->n] = tau; memcpy(E->scale + (size_t)E->n * d, sc, sizeof(double) * d); memcpy(E->shift + (size_t)E->n * d, sh, sizeof(double) * d); E->n++;
+}
+static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const double* u0, double t0, double t1,
+                                     double abstol, double reltol, double dt0, dense_t* S, const oracle_cfg* evc, cc_events* found);
 static int forward_tsit5_adaptive(const family_t* F, const double* p, const double* u0, double t0, double t1,
                                   double abstol, double reltol, double dt0, dense_t* S, const oracle_cfg* evc) {
+    if (evc && evc->cc_on) return forward_tsit5_adaptive_cc(F, p, u0, t0, t1, abstol, reltol, dt0, S, evc, NULL);
     int d = F->d;
     double pcur[64];                                   /* parameters in force (events may change them) */
     for (int q = 0; q < F->P && q < 64; q++) pcur[q] = p[q];
@@ -566,6 +596,90 @@ static int forward_tsit5_adaptive(const family_t* F, const double* p, const doub
         } else {
             h = h / fmin(1.0 / (1.0 / 5.0), q11 / 0.9);
         }
+    }
+    free(k); free(tmp); free(un);
+    return 0;
+}
+
+/* Adaptive Tsit5 with ONE continuous callback (root-finding on the step's dense output, ContinuousCallback [UPSTREAM
+ * OrdinaryDiffEq/DiffEqBase]): after an accepted step [t, t+h] whose end points straddle the condition in the requested
+ * direction, the crossing theta* of the interpolant is bisected to the last bit, the step is REDONE with h' = theta* h (so the
+ * stored dense data belong to [t, tau]; this is what reeval_internals_due_to_modification! amounts to), the affect is applied
+ * to its end state and the post-event state starts the next step (FSAL re-evaluated, controller proposal of the original
+ * step kept).  The knot at tau stores the post-event state, k7 = f(u-) stays with the step (as for preset-time events). */
+static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const double* u0, double t0, double t1,
+                                     double abstol, double reltol, double dt0, dense_t* S, const oracle_cfg* evc, cc_events* found) {
+    int d = F->d;
+    fwd_ctx c = {F, p, 0};
+    dense_init(S, d, DENSE_TSIT5, 256);
+    double* k = (double*)malloc(sizeof(double) * 7 * d), *tmp = (double*)malloc(sizeof(double) * d), *un = (double*)malloc(sizeof(double) * d);
+    double sc[8], sh[8], yb[8];
+    memcpy(S->u, u0, sizeof(double) * d); S->t[0] = t0;
+    fwd_rhs(t0, u0, k, &c);
+    double t = t0, h = dt0 > 0 ? dt0 : 1e-3 * (t1 - t0), qold = 1e-4;
+    int n = 0, iters = 0, after_event = 0; const int ci = evc->cc_idx;
+    while (t < t1) {
+        if (++iters > 10000000) { free(k); free(tmp); free(un); return -1; }
+        int last = 0;
+        if (t + h >= t1 || fabs(t + h - t1) < 100 * 2.22e-16 * fabs(t1)) { h = t1 - t; last = 1; }
+        dense_grow(S);
+        const double* u = S->u + (size_t)n * d;
+        tsit5_step(fwd_rhs, &c, d, t, h, u, k, un, tmp);
+        double e2 = 0;
+        for (int i = 0; i < d; i++) {
+            double e = 0; for (int j = 0; j < 7; j++) e += TS_BT[j] * k[j * d + i];
+            e *= h;
+            double scl = abstol + reltol * fmax(fabs(u[i]), fabs(un[i]));
+            e2 += (e / scl) * (e / scl);
+        }
+        double EEst = sqrt(e2 / d);
+        double q11 = pow(fmax(EEst, 1e-300), 7.0 / 50.0);
+        double q = q11 / pow(qold, 2.0 / 25.0);
+        q = fmax(1.0 / 10.0, fmin(5.0, q / 0.9));
+        if (EEst > 1.0) { h = h / fmin(5.0, q11 / 0.9); continue; }
+        /* sign changes of the condition on the step's dense output, sampled at theta = j / 10 (interp_points = 10 of
+         * ContinuousCallback): a long step may hold a whole flight.  Right after an event the start value is ~0 with a random
+         * sign: the first sample decides the side the solution is on. */
+        double gprev = u[ci] - evc->cc_level, thprev = 0.0, lo = 0.0, hi = 1.0;
+        int hit = 0;
+        for (int j = 1; j <= 10 && !hit; j++) {
+            const double th = j == 10 ? 1.0 : 0.1 * j;
+            double gj;
+            if (j == 10) gj = un[ci] - evc->cc_level; else { tsit5_dense(d, th, h, u, k, yb); gj = yb[ci] - evc->cc_level; }
+            if (after_event && j == 1) { gprev = gj; thprev = th; continue; }       /* skip the start point */
+            if ((evc->cc_dir <= 0 && gprev > 0 && gj <= 0) || (evc->cc_dir >= 0 && gprev < 0 && gj >= 0)) { hit = 1; lo = thprev; hi = th; }
+            else { gprev = gj; thprev = th; }
+        }
+        after_event = 0;
+        double tn = last ? t1 : t + h;
+        if (hit) {
+            const int pos = gprev > 0;                                  /* g(lo) has the sign of gprev */
+            for (int it = 0; it < 200; it++) {
+                const double mid = 0.5 * (lo + hi);
+                if (!(mid > lo && mid < hi)) break;
+                tsit5_dense(d, mid, h, u, k, yb);
+                const double gm = yb[ci] - evc->cc_level;
+                if ((gm > 0) == pos && gm != 0) lo = mid; else hi = mid;
+            }
+            const double hh = hi * h;                                  /* first representable theta at / past the crossing */
+            tsit5_step(fwd_rhs, &c, d, t, hh, u, k, un, tmp);          /* k[0] = f(u) is still valid */
+            tn = t + hh;
+        }
+        memcpy(S->k + (size_t)n * 7 * d, k, sizeof(double) * 7 * d);
+        t = tn; S->t[n + 1] = t;
+        memcpy(k, k + 6 * d, sizeof(double) * d);
+        if (hit) {
+            for (int i = 0; i < d; i++) { sc[i] = evc->cc_scale ? evc->cc_scale[i] : 1.0; sh[i] = evc->cc_shift ? evc->cc_shift[i] : 0.0; }
+            if (evc->cc_pcomp >= 0) { sc[evc->cc_pcomp] = evc->cc_psign * p[evc->cc_pparam]; sh[evc->cc_pcomp] = 0.0; }
+            for (int i = 0; i < d; i++) un[i] = sc[i] * un[i] + sh[i];
+            if (found) cc_push(found, d, t, sc, sh);
+            fwd_rhs(t, un, k, &c);
+            after_event = 1;
+        }
+        memcpy(S->u + (size_t)(n + 1) * d, un, sizeof(double) * d);
+        n++; S->n = n;
+        qold = fmax(EEst, 1e-4);
+        h = h / q;
     }
     free(k); free(tmp); free(un);
     return 0;
@@ -924,6 +1038,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
     for (int j = 0; j < d && j < 8; j++) { ctx.ca[j] = CONT_A(cfg, j); ctx.cb[j] = CONT_B(cfg, j); }
     int evc = cfg->n_events - 1;     /* next event below t */
     if (cfg->n_events > 0 && ((cfg->stepper != ST_TSIT5_ADAPTIVE && cfg->stepper != ST_TSIT5_FIXED) || sa == SA_QUADRATURE)) return -11;
+    if (cfg->cc_on && (cfg->stepper != ST_TSIT5_ADAPTIVE || sa == SA_QUADRATURE)) return -12;
     for (int q = 0; q < P; q++) acc[q] = 0;
     adjdense_t adj; int have_adj = (sa == SA_QUADRATURE);
     if (have_adj) adjdense_init(&adj, L, ros ? DENSE_ROS23 : DENSE_TSIT5);
@@ -960,6 +1075,22 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
      * Runs after the checkpoint reset and the loss jump of the same time (the saved state at tau is post-event). */
 #define APPLY_EVENT_IF_AT(tt)                                                                              \
     while (evc >= 0 && fabs(cfg->ev_times[evc] - (tt)) <= 100 * 2.220446049250313e-16 * fmax(fabs(tt), 1.0)) { \
+        if (cfg->cc_on) {                                                                                  \
+            /* state-dependent event time (src/callback_tracking.jl:232-480, the implicit correction): with u+ = a(u-, p),   \
+             * g(u-) = 0:  lam- = A'lam+ - dg' [(A f- - f+)' lam+] / (dg . f-),  dG/dp += (da/dp)' lam+ */                  \
+            double um[8], up[8], fm[8], fp_[8]; double wl = 0;                                             \
+            dense_eval(sol, cfg->ev_times[evc], 0, um, NULL); dense_eval(sol, cfg->ev_times[evc], 1, up, NULL); \
+            F->f(um, p, (tt), fm, &F->ctx); F->f(up, p, (tt), fp_, &F->ctx);                               \
+            for (int i = 0; i < d; i++) wl += (cfg->ev_scale[(size_t)evc * d + i] * fm[i] - fp_[i]) * z[i]; \
+            if (cfg->cc_pcomp >= 0) {                                                                      \
+                const double gpar = cfg->cc_psign * um[cfg->cc_pcomp] * z[cfg->cc_pcomp];                  \
+                if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) z[d + cfg->cc_pparam] += gpar; else acc[cfg->cc_pparam] += gpar; \
+            }                                                                                              \
+            for (int i = 0; i < d; i++) z[i] *= cfg->ev_scale[(size_t)evc * d + i];                        \
+            z[cfg->cc_idx] -= wl / fm[cfg->cc_idx];                                                        \
+            if (sa == SA_BACKSOLVE) memcpy(z + d + P, um, sizeof(double) * d);                             \
+            ctx.tev = (tt); evc--; fsal_ok = 0; continue;                                                  \
+        }                                                                                                  \
         for (int i = 0; i < d; i++) z[i] *= cfg->ev_scale[(size_t)evc * d + i];                            \
         if (sa == SA_BACKSOLVE) dense_eval(sol, cfg->ev_times[evc], 0, z + d + P, NULL);                   \
         if (p_events) {   /* p+ = s_p .* p- + c_p: dG/dp- = s_p .* dG/dp+ (+ what accumulates below tau with p-) */ \
@@ -1205,13 +1336,24 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
         int r = 0;
         if (!is_sde(cfg)) {
             dense_t sol;
+            /* continuous callback: the forward solve FINDS this member's event times; the reverse pass sees them as a
+             * member-local event list (times, effective affine affect) */
+            cc_events found = {0, 0, NULL, NULL, NULL};
+            oracle_cfg mcfg = *cfg;
+            if (cfg->cc_on) {
+                if (cfg->stepper != ST_TSIT5_ADAPTIVE) r = -12;
+                else r = forward_tsit5_adaptive_cc(&F, pm, um, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, cfg->dt, &sol, cfg, &found);
+                mcfg.n_events = found.n; mcfg.ev_times = found.t; mcfg.ev_scale = found.scale; mcfg.ev_shift = found.shift;
+                mcfg.ev_pscale = NULL; mcfg.ev_pshift = NULL;
+            } else
             r = forward_dense_member(cfg, &F, pm, um, &sol);
+            const oracle_cfg* cfg_m = &mcfg;
             if (r == 0) {
                 if (steps_out) steps_out[i] = sol.n;
                 double y[8];
                 if (saved) for (int k = 0; k < K; k++) {
                     int at_ev = 0;
-                    for (int e = 0; e < cfg->n_events; e++) if (cfg->ev_times[e] == saveat[k]) at_ev = 1;
+                    for (int e = 0; e < cfg_m->n_events; e++) if (cfg_m->ev_times[e] == saveat[k]) at_ev = 1;
                     dense_eval(&sol, saveat[k], at_ev, y, NULL);
                     for (int j = 0; j < d; j++) saved[((size_t)k * d + j) * N + i] = y[j]; }
                 if (du0) {
@@ -1219,10 +1361,11 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
                         dLm = (double*)malloc(sizeof(double) * K * d);
                         for (int k = 0; k < K; k++) for (int j = 0; j < d; j++) dLm[k * d + j] = dLdu[((size_t)k * d + j) * N + i];
                     }
-                    r = adjoint_ode_member(cfg, &F, pm, &sol, saveat, dLm, du, dpm, NULL);
+                    r = adjoint_ode_member(cfg_m, &F, pm, &sol, saveat, dLm, du, dpm, NULL);
                 }
             }
-            dense_free(&sol);
+            if (steps_out && cfg->cc_on) steps_out[i] = sol.n;
+            dense_free(&sol); free(found.t); free(found.scale); free(found.shift);
         } else {
             double* us = (double*)malloc(sizeof(double) * (size_t)(S + 1) * d);
             double* dWm = (double*)malloc(sizeof(double) * (size_t)S * d);

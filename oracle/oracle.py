@@ -14,10 +14,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
-FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5}
+FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5, "ball": 6}
 SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kronrod": 4}
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
-FAM_DIMS = {"lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2)}
+FAM_DIMS = {"lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "ball": (2, 2, 0)}
 
 
 class OracleCfg(C.Structure):
@@ -36,6 +36,8 @@ class OracleCfg(C.Structure):
         ("ev_pscale", C.c_void_p), ("ev_pshift", C.c_void_p),
         ("cost_av", C.c_void_p), ("cost_bv", C.c_void_p), ("cont_av", C.c_void_p), ("cont_bv", C.c_void_p),
         ("dgdp_c", C.c_void_p), ("dgdp_e", C.c_void_p), ("cdgdp_c", C.c_void_p), ("cdgdp_e", C.c_void_p),
+        ("cc_on", C.c_int32), ("cc_idx", C.c_int32), ("cc_dir", C.c_int32), ("cc_pcomp", C.c_int32), ("cc_pparam", C.c_int32), ("cc_found", C.c_int32),
+        ("cc_level", C.c_double), ("cc_psign", C.c_double), ("cc_scale", C.c_void_p), ("cc_shift", C.c_void_p),
     ]
 
 
@@ -65,7 +67,7 @@ def _ptr(a):
 
 def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, reltol=1e-3, quad_abstol=1e-10,
              quad_reltol=1e-10, cost=("explicit",), shared_p=True, no_start=False, checkpointing=True,
-             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None, cost_vec=None, cont_vec=None):
+             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None, cost_vec=None, cont_vec=None, crossing=None):
     if family == "mlp":
         d = 2
         H = mlp_hidden
@@ -104,6 +106,12 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
         cfg.cont_cost = 1
         cfg.cont_av, cfg.cont_bv, cfg.cdgdp_c, cfg.cdgdp_e = _vec(a, d), _vec(b, d), _vec(c, P), _vec(e, P)
     cfg._keep_cost = keep
+    # continuous callback: crossing = dict(idx, level=0, direction=-1, scale=None, shift=None, pcomp=-1, pparam=0, psign=-1)
+    if crossing is not None:
+        cfg.cc_on, cfg.cc_idx, cfg.cc_dir = 1, int(crossing["idx"]), int(crossing.get("direction", -1))
+        cfg.cc_level = float(crossing.get("level", 0.0))
+        cfg.cc_pcomp, cfg.cc_pparam, cfg.cc_psign = int(crossing.get("pcomp", -1)), int(crossing.get("pparam", 0)), float(crossing.get("psign", -1.0))
+        cfg.cc_scale, cfg.cc_shift = _vec(crossing.get("scale", 1.0), d), _vec(crossing.get("shift", 0.0), d)
     if events is not None:         # preset-time events: (times[E], scale[E, d], shift[E, d]), u <- scale * u + shift
         et, es, ec = (np.ascontiguousarray(x, dtype=np.float64) for x in events[:3])
         assert es.shape == (len(et), d) and ec.shape == (len(et), d)

@@ -6,7 +6,7 @@ N = 65536; saveat = np.linspace(0, 10, 101)
 u0, p = bench.make_inputs(N)
 u0d = torch.tensor(u0, device="cuda"); pd = torch.tensor(p, device="cuda")
 ref = None
-for C in (1, 4, 8, 16):
+for C in (1, 4, 8):
     torch.cuda.synchronize(); free0 = torch.cuda.mem_get_info()[0]
     eng = b.DeviceEnsemble("lorenz", "gauss", "tsit5_fixed", N, saveat, (0.0, 10.0), 0.01, on_device=True, cost=b.AffineCost(1.0, -2.0), checkpoint_every=C)
     mem = (free0 - torch.cuda.mem_get_info()[0]) / 1e9
