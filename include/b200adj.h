@@ -34,7 +34,9 @@ enum {
     B200ADJ_FAM_ROBERTSON = 2,  /* Robertson d=3 P=3        (test/Core2/stiff_adjoints.jl:256-263, 3-param)    */
     B200ADJ_FAM_SDE_LV = 3,     /* LV drift + diag noise g_i = p[4+i] u_i, d=2 P=6 m=2 (Core1/...:737-760)      */
     B200ADJ_FAM_MLP = 4,        /* 2 -> H -> H -> 2 tanh MLP (docs/src/Benchmark.md:49-52), P = H*H+6H+2        */
-    B200ADJ_FAM_SDE_LINEAR = 5  /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
+    B200ADJ_FAM_SDE_LINEAR = 5, /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
+    B200ADJ_FAM_BALL = 6        /* bouncing ball x' = v, v' = -p0, p = [gravity, restitution], d=2 P=2
+                                   (docs/src/examples/hybrid_jump/bouncing_ball.md; adaptive Tsit5 only)          */
 };
 /* User RHS families (replaces the user `ODEFunction(f; vjp, vjp_p, jac, paramjac)` seam of
  * src/derivative_wrappers.jl:284-359, test/Core3/user_vjp.jl:14-38): a family PLUG-IN is a shared library built from a
@@ -119,7 +121,8 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle);
 
 /* forward: batched forward solve of all members, keeps per-step checkpoints in HBM, writes the primal at saveat.
  * Replaces the forward solve + sol(ts) of src/concrete_solve.jl:689-770.  saved may be NULL; status[N] (int32,
- * 0 = ok, 1 = non-finite state) may be NULL.  dW_in (SDE only, may be NULL): use these increments instead of Philox. */
+ * 0 = ok, 1 = non-finite state, 2 = step capacity (cfg.max_steps) exhausted, 3 = more state-dependent events than
+ * max_events) may be NULL.  dW_in (SDE only, may be NULL): use these increments instead of Philox. */
 int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void* dW_in, void* saved, int32_t* status);
 
 /* reverse: the fused reverse pass (adjoint RHS + VJPs + quadrature + RK update + jumps, all members), then the
@@ -172,6 +175,24 @@ int32_t b200adj_set_cost_family(void* handle, int32_t which, const double* a, co
  * (the reference's QuadratureAdjoint has no callback support either); call before b200adj_forward. */
 int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift,
                            const double* pscale, const double* pshift);
+
+/* State-dependent event of the hybrid system (ContinuousCallback of the reference; reverse-pass treatment with the implicit
+ * event-time correction of src/callback_tracking.jl:232-480; docs/src/examples/hybrid_jump/bouncing_ball.md,
+ * test/Callbacks1/continuous_callbacks.jl): condition(u) = u[idx] - level, fired when it crosses zero in `direction`
+ * (-1: from positive to non-positive only -- affect_neg! = nothing --, +1: upwards only, 0: both); the affect is of the named
+ * affine family u <- scale .* u + shift (NULL = 1 / 0), followed, when pcomp >= 0, by u[pcomp] <- psign * p[pparam] * u[pcomp]
+ * ("v = -p[2] * v": pcomp = 1, pparam = 1, psign = -1), save_positions = (false, false).  Each member finds its OWN event
+ * times: the forward kernel samples the condition on the dense output of every accepted step (interp_points = 10), bisects
+ * the crossing to the last bit and re-takes the step up to it; the reverse kernel uses the member's event list as tstops and
+ * applies  lam- = A'lam+ - e_idx [(A f(u-) - f(u+))'lam+] / f(u-)[idx],  dG/dp[pparam] += psign u-[pcomp] lam+[pcomp].
+ * Adaptive Tsit5, Interpolating / Gauss / GaussKronrod / Backsolve (QuadratureAdjoint has no callback support in the
+ * reference either); not together with b200adj_set_events.  max_events = per-member capacity of the event list (status 3
+ * when exceeded).  enabled = 0 removes the callback.  Call before b200adj_forward. */
+int32_t b200adj_set_continuous_callback(void* handle, int32_t enabled, int32_t idx, double level, int32_t direction,
+                                        const double* scale, const double* shift, int32_t pcomp, int32_t pparam, double psign,
+                                        int32_t max_events);
+/* event lists found by the last forward pass: counts[N] (host, may be NULL), times[max_events][N] (host, may be NULL) */
+int32_t b200adj_event_times(void* handle, int32_t* counts, double* times);
 
 /* SDE helper for parity tests: copy out the Wiener increments the forward pass used, dW[S][m][N]. */
 int32_t b200adj_get_noise(void* handle, void* dW_out);

@@ -19,7 +19,7 @@ import ChainRulesCore: NoTangent
 const libb200adj = get(ENV, "B200ADJ_LIB", "libb200adj.so")      # where the shared library lives (not a behaviour switch)
 
 # ---- enums / cfg: field-for-field mirror of b200adj_cfg (176 bytes; checked against b200adj_sizeof_cfg) ----
-@enum Family::Int32 FAM_LV = 0 FAM_LORENZ = 1 FAM_ROBERTSON = 2 FAM_SDE_LV = 3 FAM_MLP = 4 FAM_SDE_LINEAR = 5
+@enum Family::Int32 FAM_LV = 0 FAM_LORENZ = 1 FAM_ROBERTSON = 2 FAM_SDE_LV = 3 FAM_MLP = 4 FAM_SDE_LINEAR = 5 FAM_BALL = 6
 const SA_CODE = Dict(InterpolatingAdjoint => Int32(0), GaussAdjoint => Int32(1), QuadratureAdjoint => Int32(2),
     BacksolveAdjoint => Int32(3), GaussKronrodAdjoint => Int32(4))
 const ST_TSIT5_FIXED, ST_ROSENBROCK23, ST_EM, ST_EULER_HEUN, ST_TSIT5_ADAPTIVE = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
@@ -41,6 +41,23 @@ struct B200PresetAffine
     pscale::Union{Nothing, Matrix{Float64}}; pshift::Union{Nothing, Matrix{Float64}}
 end
 B200PresetAffine(t, s, c; pscale = nothing, pshift = nothing) = B200PresetAffine(collect(Float64, t), s, c, pscale, pshift)
+
+"""
+    B200Crossing(idx, level = 0.0, direction = -1; scale = nothing, shift = nothing, pcomp = 0, pparam = 0, psign = 1.0, max_events = 64)
+
+The state-dependent callback family of the device path: `ContinuousCallback(condition, affect!)` with
+`condition(u, t, integrator) = u[idx] - level` (direction -1: `affect_neg!`-style downward crossings only, +1 upward, 0 both) and
+`affect!`: `u .= scale .* u .+ shift`, then `u[pcomp] = psign * p[pparam] * u[pcomp]` when `pcomp > 0` (1-based here, 0-based at the
+ABI).  The bouncing ball of docs/src/examples/hybrid_jump/bouncing_ball.md is `B200Crossing(1, 0.0, -1; pcomp = 2, pparam = 2,
+psign = -1.0)`.  Adaptive Tsit5; every ensemble member finds its own event times on the device.
+"""
+struct B200Crossing
+    idx::Int; level::Float64; direction::Int
+    scale::Union{Nothing, Vector{Float64}}; shift::Union{Nothing, Vector{Float64}}
+    pcomp::Int; pparam::Int; psign::Float64; max_events::Int
+end
+B200Crossing(idx, level = 0.0, direction = -1; scale = nothing, shift = nothing, pcomp = 0, pparam = 0, psign = 1.0, max_events = 64) =
+    B200Crossing(idx, level, direction, scale, shift, pcomp, pparam, psign, max_events)
 
 struct B200Cfg
     rhs_family::Int32; sensealg::Int32; stepper::Int32; dtype::Int32
@@ -132,9 +149,12 @@ function b200_solve_adjoint(prob, alg, sensealg::B200Adjoint, U::AbstractMatrix{
     sde = is_sde_alg(alg)
     adaptive = !sde && get(kwargs, :adaptive, true)                  # OrdinaryDiffEq default; fixed step needs dt
     (adaptive || dt !== nothing) || throw(B200Unsupported("fixed-step solve without dt"))
-    events = nothing
-    if callback !== nothing
-        (callback isa B200PresetAffine && nameof(typeof(alg)) === :Tsit5) || throw(B200Unsupported("callback outside the preset-time affine family"))
+    events = nothing; crossing = nothing
+    if callback isa B200Crossing
+        (nameof(typeof(alg)) === :Tsit5 && adaptive) || throw(B200Unsupported("state-dependent events: adaptive Tsit5"))
+        crossing = callback
+    elseif callback !== nothing
+        (callback isa B200PresetAffine && nameof(typeof(alg)) === :Tsit5) || throw(B200Unsupported("callback outside the preset-time affine / crossing families"))
         events = callback
     end
     t0, t1 = prob.tspan
@@ -188,6 +208,15 @@ function b200_solve_adjoint(prob, alg, sensealg::B200Adjoint, U::AbstractMatrix{
             GC.@preserve events sc sh psm pcm check(s.h.ptr, ccall((:b200adj_set_events, libb200adj), Int32,
                 (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 s.h.ptr, E, events.tstops, sc, sh, psm === nothing ? C_NULL : pointer(psm), pcm === nothing ? C_NULL : pointer(pcm)))
+        end
+    end
+    if crossing !== nothing      # ContinuousCallback of the crossing family: each member finds its own event times in b200adj_forward
+        c = crossing
+        for s in shards
+            GC.@preserve c check(s.h.ptr, ccall((:b200adj_set_continuous_callback, libb200adj), Int32,
+                (Ptr{Cvoid}, Int32, Int32, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Int32),
+                s.h.ptr, 1, c.idx - 1, c.level, c.direction, c.scale === nothing ? C_NULL : pointer(c.scale),
+                c.shift === nothing ? C_NULL : pointer(c.shift), c.pcomp - 1, max(c.pparam - 1, 0), c.psign, c.max_events))
         end
     end
     # forward: every shard on its own host thread (the calls block until the D2H copies are done)

@@ -11,7 +11,7 @@ import numpy as np
 
 from . import distributed
 from .engine import DeviceEnsemble, _is_torch
-from .problems import (EM, AffineCost, PresetTimeCallback, EnsembleB200, EnsembleProblem, EnsembleSolution, EulerHeun, FAMILIES, ODEProblem,
+from .problems import (EM, AffineCost, ContinuousCallback, PresetTimeCallback, EnsembleB200, EnsembleProblem, EnsembleSolution, EulerHeun, FAMILIES, ODEProblem,
                        Rosenbrock23, SDEProblem, Tsit5, saveat_to_times)
 from .sensitivity_algorithms import (B200Adjoint, BacksolveAdjoint, GaussAdjoint, GaussKronrodAdjoint, InterpolatingAdjoint,
                                      QuadratureAdjoint, sensealg_name)
@@ -88,11 +88,19 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     ensemblealg = ensemblealg or EnsembleB200()
     prob = eprob.prob
     callback = kwargs.pop("callback", None) or prob.callback
+    ccb = None
+    if isinstance(callback, ContinuousCallback):
+        # state-dependent event of the named condition / affect family: adaptive Tsit5, every member finds its own event times
+        if tuple(callback.save_positions) != (False, False):
+            raise NotImplementedError("ContinuousCallback: save_positions = (false, false) only")
+        if not (isinstance(alg, Tsit5) and alg.code == "tsit5_adaptive"):
+            raise NotImplementedError("ContinuousCallback: built for the adaptive Tsit5 stepper")
+        ccb, callback = callback, None
     if callback is not None:
-        # the device path carries one callback family: preset-time affine affects on the adaptive Tsit5 stepper
+        # preset-time affine affects on the Tsit5 steppers
         if not isinstance(callback, PresetTimeCallback):
-            raise NotImplementedError("callbacks: only PresetTimeCallback(tstops, AffineAffect) is carried on the B200 path "
-                                      "(SURVEY.md App. E); delegate other callbacks to the reference implementation")
+            raise NotImplementedError("callbacks: PresetTimeCallback(tstops, AffineAffect) and ContinuousCallback(idx, ...) are carried on "
+                                      "the B200 path (SURVEY.md App. E); delegate other callbacks to the reference implementation")
         if tuple(callback.save_positions) != (False, False):
             raise NotImplementedError("PresetTimeCallback: save_positions = (false, false) only")
         if not isinstance(alg, Tsit5):
@@ -146,7 +154,7 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     ev = callback.tables(d, P) if callback is not None else None
     key = (prob.f, alg.code, hi - lo, ts.tobytes(), tuple(prob.tspan), _step_size(alg, kwargs), shared_p, on_device, device,
            getattr(prob, "seed", 0), lo, block, stored, ckpt_every, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3),
-           None if ev is None else tuple(x.tobytes() for x in ev))
+           None if ev is None else tuple(x.tobytes() for x in ev), None if ccb is None else ccb.key())
     eng = _HANDLE_CACHE.get(key) if ensemblealg.reuse_handle else None
     if eng is None:
         eng = DeviceEnsemble(prob.f, sensealg_name(inner), alg.code, hi - lo, ts, prob.tspan, _step_size(alg, kwargs),
@@ -158,6 +166,8 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
                              checkpoint_every=ckpt_every)
         if ev is not None:
             eng.set_events(*ev)
+        if ccb is not None:
+            eng.set_continuous_callback(ccb)
         if world > 1 and shared_p:
             distributed.attach_comm(eng)           # the one all-reduce of dp then runs inside b200adj_reverse (csrc/comm.cu)
         if ensemblealg.reuse_handle:

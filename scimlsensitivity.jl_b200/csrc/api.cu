@@ -21,6 +21,7 @@ int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
     case B200ADJ_FAM_ROBERTSON: *d = 3; *P = 3; *m = 0; return 0;
     case B200ADJ_FAM_SDE_LV: *d = 2; *P = 6; *m = 2; return 0;
     case B200ADJ_FAM_SDE_LINEAR: *d = 2; *P = 2; *m = 2; return 0;
+    case B200ADJ_FAM_BALL: *d = 2; *P = 2; *m = 0; return 0;
     case B200ADJ_FAM_MLP: if (c.mlp_hidden != MLP_H) return -1; *d = MLP_D; *P = MLP_P; *m = 0; return 0;
     default: return -1;
     }
@@ -110,6 +111,11 @@ T5aArgs t5a_args(Handle* h) {
     if (h->fixed_dt) a.flags |= 16u;          // constant step, no error control (fixed-step Tsit5 on the dense framework)
     if (h->cont_on) { a.flags |= 8u; for (int j = 0; j < 4; j++) { a.cont_a[j] = h->cont_av[j]; a.cont_b[j] = h->cont_bv[j]; } }
     a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
+    if (h->cc_on) {
+        a.cc_on = 1; a.cc_idx = h->cc_idx; a.cc_dir = h->cc_dir; a.cc_pcomp = h->cc_pcomp; a.cc_pparam = h->cc_pparam; a.cc_maxev = h->cc_maxev;
+        a.cc_level = h->cc_level; a.cc_psign = h->cc_psign; a.cc_t = h->d_cc_t; a.cc_n = h->d_cc_n;
+        for (int j = 0; j < 4; j++) { a.cc_scale[j] = h->cc_scale[j]; a.cc_shift[j] = h->cc_shift[j]; }
+    }
     return a;
 }
 RosArgs ros_args(Handle* h) {
@@ -133,6 +139,7 @@ void free_all(Handle* h) {
     cudaFree(h->d_saveat); cudaFree(h->r_fn); cudaFree(h->r_rn); cudaFree(h->r_qseg); cudaFree(h->r_qkey);
     cudaFree(h->d_kst); cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step); cudaFree(h->d_fwd_save_of_step); cudaFree(h->d_fwd_saveat);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
+    cudaFree(h->d_cc_t); cudaFree(h->d_cc_n);
     cudaFree(h->s_status); cudaFree(h->d_event_of_step); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
@@ -248,6 +255,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (ros && !dense_fixed && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
     }
+    if (cfg->rhs_family == B200ADJ_FAM_BALL && !t5a) { g_create_error = "BouncingBall family: Tsit5 on the per-member dense framework (adaptive, or fixed step with B200ADJ_FLAG_DENSE_FORWARD)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (ros) {
         // adaptive path: save times are arbitrary ascending points of [t0, t1] (tstops of the reverse solve)
         for (int k = 0; k < cfg->K; k++) {
@@ -424,6 +432,7 @@ int32_t b200adj_set_reverse_options(void* handle, int32_t sensealg, int32_t cost
     Handle* h = (Handle*)handle;
     b200adj_cfg& c = h->cfg;
     if (sensealg < 0 || sensealg > 4 || (cost_kind != B200ADJ_COST_EXPLICIT && cost_kind != B200ADJ_COST_AFFINE)) { h->err = "bad sensealg/cost_kind"; return B200ADJ_ERR_INVALID; }
+    if (h->cc_on && sensealg == B200ADJ_SA_QUADRATURE) { h->err = "continuous callback: QuadratureAdjoint has no callback support"; return B200ADJ_ERR_UNSUPPORTED; }
     if (sensealg == B200ADJ_SA_GAUSSKRONROD && (is_sde(c) || c.rhs_family == B200ADJ_FAM_MLP || c.dtype != B200ADJ_F64)) { h->err = "GaussKronrodAdjoint: F64, named ODE families"; return B200ADJ_ERR_UNSUPPORTED; }
     if (h->ckpt_every > 1 && sensealg != B200ADJ_SA_INTERPOLATING && sensealg != B200ADJ_SA_GAUSS) { h->err = "checkpoint_every > 1: InterpolatingAdjoint / GaussAdjoint only"; return B200ADJ_ERR_UNSUPPORTED; }
     if (is_sde(c) && sensealg != B200ADJ_SA_BACKSOLVE && sensealg != B200ADJ_SA_INTERPOLATING) { h->err = "SDE: BacksolveAdjoint / InterpolatingAdjoint are built"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -540,6 +549,7 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
     Handle* h = (Handle*)handle;
     const b200adj_cfg& c = h->cfg;
     if (E < 0 || (E > 0 && (!times || !scale || !shift)) || ((pscale == nullptr) != (pshift == nullptr))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
+    if (E > 0 && h->cc_on) { h->err = "events: preset-time events together with a continuous callback are not built"; return B200ADJ_ERR_UNSUPPORTED; }
     const bool fixed = c.stepper == B200ADJ_ST_TSIT5_FIXED && c.rhs_family != B200ADJ_FAM_MLP && c.dtype == B200ADJ_F64 && !h->fixed_dt;
     if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !fixed && !h->fixed_dt) { h->err = "events: built for the Tsit5 steppers (adaptive; fixed step in F64)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (E > 0 && fixed && h->ckpt_every > 1) { h->err = "events together with checkpoint_every > 1 are not built"; return B200ADJ_ERR_UNSUPPORTED; }
@@ -580,6 +590,48 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
         if (!h->d_event_of_step) CUDA_TRY(h, cudaMalloc(&h->d_event_of_step, ((size_t)h->S + 1) * sizeof(int32_t)));
         CUDA_TRY(h, cudaMemcpy(h->d_event_of_step, eos.data(), eos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_continuous_callback(void* handle, int32_t enabled, int32_t idx, double level, int32_t direction,
+                                        const double* scale, const double* shift, int32_t pcomp, int32_t pparam, double psign,
+                                        int32_t max_events) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (!enabled) {
+        cudaFree(h->d_cc_t); cudaFree(h->d_cc_n); h->d_cc_t = nullptr; h->d_cc_n = nullptr; h->cc_on = false; h->have_forward = false;
+        return B200ADJ_OK;
+    }
+    if (c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE || h->fixed_dt || c.dtype != B200ADJ_F64) { h->err = "continuous callback: built for the adaptive Tsit5 stepper (F64)"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (c.sensealg == B200ADJ_SA_QUADRATURE) { h->err = "continuous callback: Interpolating / Gauss / GaussKronrod / Backsolve (QuadratureAdjoint has no callback support)"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (h->nev > 0) { h->err = "continuous callback together with preset-time events is not built"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (c.d > 4) { h->err = "continuous callback: d <= 4"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (idx < 0 || idx >= c.d || direction < -1 || direction > 1 || pcomp >= c.d || (pcomp >= 0 && (pparam < 0 || pparam >= c.P)) || max_events < 1 ||
+        !std::isfinite(level) || !std::isfinite(psign)) { h->err = "continuous callback: bad idx / direction / pcomp / pparam / max_events"; return B200ADJ_ERR_INVALID; }
+    if ((size_t)max_events != (size_t)h->cc_maxev || !h->d_cc_t) {
+        cudaFree(h->d_cc_t); cudaFree(h->d_cc_n); h->d_cc_t = nullptr; h->d_cc_n = nullptr; h->cc_on = false;
+        CUDA_TRY(h, cudaMalloc(&h->d_cc_t, (size_t)max_events * (size_t)c.N * sizeof(double)));
+        CUDA_TRY(h, cudaMalloc(&h->d_cc_n, (size_t)c.N * sizeof(int32_t)));
+    }
+    CUDA_TRY(h, cudaMemsetAsync(h->d_cc_n, 0, (size_t)c.N * sizeof(int32_t), h->stream));
+    h->cc_on = true; h->cc_idx = idx; h->cc_dir = direction; h->cc_pcomp = pcomp < 0 ? -1 : pcomp; h->cc_pparam = pcomp < 0 ? 0 : pparam;
+    h->cc_maxev = max_events; h->cc_level = level; h->cc_psign = psign;
+    for (int j = 0; j < 4; j++) { h->cc_scale[j] = (scale && j < c.d) ? scale[j] : 1.0; h->cc_shift[j] = (shift && j < c.d) ? shift[j] : 0.0; }
+    h->have_forward = false;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_event_times(void* handle, int32_t* counts, double* times) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    if (!h->cc_on || !h->have_forward) { h->err = "event_times: needs a continuous callback and a forward pass"; return B200ADJ_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (counts) CUDA_TRY(h, cudaMemcpy(counts, h->d_cc_n, (size_t)h->cfg.N * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (times) CUDA_TRY(h, cudaMemcpy(times, h->d_cc_t, (size_t)h->cc_maxev * (size_t)h->cfg.N * sizeof(double), cudaMemcpyDeviceToHost));
     return B200ADJ_OK;
 }
 
@@ -650,6 +702,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         case B200ADJ_FAM_LV: rc = launch_t5a_fwd<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_fwd<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_fwd<Robertson>(h, a); break;
+        case B200ADJ_FAM_BALL: rc = launch_t5a_fwd<BouncingBall>(h, a); break;
         default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->t5a_fwd) ? vt->t5a_fwd(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (h->adaptive) {
@@ -747,6 +800,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         case B200ADJ_FAM_LV: rc = launch_t5a_rev<LotkaVolterra>(h, a); break;
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_rev<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_rev<Robertson>(h, a); break;
+        case B200ADJ_FAM_BALL: rc = launch_t5a_rev<BouncingBall>(h, a); break;
         default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->t5a_rev) ? vt->t5a_rev(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (h->adaptive) {

@@ -104,6 +104,18 @@ struct Robertson {
     }
 };
 
+// bouncing ball (docs/src/examples/hybrid_jump/bouncing_ball.md; test/callbacks/continuous_callbacks.jl): x' = v, v' = -p0;
+// p = [gravity, restitution] -- the restitution coefficient enters through the event affect v <- -p1 v only
+struct BouncingBall {
+    static constexpr int D = 2, P = 2, M = 0;
+    template <class T> __device__ __forceinline__ static void f(const T* u, const T* p, T* du) { du[0] = u[1]; du[1] = -p[0]; }
+    template <class T> __device__ __forceinline__ static void vjp_u(const T* u, const T* p, const T* l, T* dl) { dl[0] = T(0); dl[1] = l[0]; }
+    template <class T> __device__ __forceinline__ static void vjp_p(const T* u, const T* p, const T* l, T* dg) { dg[0] = -l[1]; dg[1] = T(0); }
+    template <class T> __device__ __forceinline__ static void jac(const T* u, const T* p, T (*J)[2]) { J[0][0] = 0; J[0][1] = 1; J[1][0] = 0; J[1][1] = 0; }
+    template <class T> __device__ __forceinline__ static void djac(const T* p, const T* yd, T (*J)[2]) { J[0][0] = 0; J[0][1] = 0; J[1][0] = 0; J[1][1] = 0; }
+    template <class T> __device__ __forceinline__ static void dvjp_p(const T* u, const T* p, const T* ud, const T* l, T* dg) { dg[0] = T(0); dg[1] = T(0); }
+};
+
 // SDE Lotka-Volterra with diagonal noise g_i = p[4+i] u_i.  ITO selects the reference's transformed drift
 // f - (dg/du)' g (src/sde_tools.jl:29-66, chosen at src/backsolve_adjoint.jl:327-345 for Ito solvers like EM).
 template <bool ITO>

@@ -71,6 +71,10 @@ struct Handle {
     const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
     int32_t* d_event_of_step = nullptr;     // fixed-step Tsit5: event index at grid point n, or -1
     int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr, *d_ev_ps = nullptr, *d_ev_pc = nullptr;      // preset-time events
+    // state-dependent event (b200adj_set_continuous_callback): per-member event lists cc_t[cc_maxev][N], cc_n[N]
+    bool cc_on = false; int cc_idx = 0, cc_dir = 0, cc_pcomp = -1, cc_pparam = 0, cc_maxev = 0;
+    double cc_level = 0, cc_psign = 1, cc_scale[4] = {1, 1, 1, 1}, cc_shift[4] = {0, 0, 0, 0};
+    double* d_cc_t = nullptr; int32_t* d_cc_n = nullptr;
     bool have_forward = false;
     bool noise_valid = false;
     int64_t launches = 0;

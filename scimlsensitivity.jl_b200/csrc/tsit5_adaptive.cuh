@@ -32,6 +32,13 @@ struct T5aArgs {
     int32_t nev; const double* ev_t; const double* ev_s; const double* ev_c;      // [E], [E][D], [E][D]
     double cont_a[4], cont_b[4];  // flags bit3: continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u), dlam -= dgdu_continuous(y) (accumulate_cost!)
     const double* ev_ps; const double* ev_pc;     // [E][P] or null: parameter-changing affect p <- ps .* p + pc (reset_p of the reference)
+    // state-dependent event (ContinuousCallback, src/callback_tracking.jl:232-480; docs/src/examples/hybrid_jump/bouncing_ball.md):
+    // condition u[cc_idx] - cc_level crossing zero in direction cc_dir (-1 down, +1 up, 0 both); affect u <- cc_scale .* u +
+    // cc_shift, then u[cc_pcomp] <- cc_psign * p[cc_pparam] * u[cc_pcomp] (cc_pcomp < 0: none).  The forward kernel (CC = true)
+    // FINDS each member's event times: cc_t[cc_maxev][N], cc_n[N]; the reverse kernel reads them as member-local tstops.
+    int32_t cc_on, cc_idx, cc_dir, cc_pcomp, cc_pparam, cc_maxev;
+    double cc_level, cc_psign, cc_scale[4], cc_shift[4];
+    double* cc_t; int32_t* cc_n;
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
     double BT[7];           // embedded error weights b - bhat
@@ -117,7 +124,28 @@ __device__ __forceinline__ double t5_error(const T5aArgs& a, double h, const dou
     return sqrt(e2 / L);
 }
 
-template <class Fam, bool SHARED_P>
+// effective affine affect of the state-dependent event for a member with parameters p (constant along the solve)
+template <int D, int P>
+__device__ __forceinline__ void t5_cc_affect(const T5aArgs& a, const double* p, double* sc, double* sh) {
+    double pv = 0.0;
+#pragma unroll
+    for (int q = 0; q < P; q++) if (q == a.cc_pparam) pv = p[q];
+#pragma unroll
+    for (int j = 0; j < D; j++) {
+        const bool pc = (j == a.cc_pcomp);
+        sc[j] = pc ? a.cc_psign * pv : a.cc_scale[j];
+        sh[j] = pc ? 0.0 : a.cc_shift[j];
+    }
+}
+template <int D>
+__device__ __forceinline__ double t5_pick(const double* v, int idx) {
+    double r = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; j++) if (j == idx) r = v[j];
+    return r;
+}
+
+template <class Fam, bool SHARED_P, bool CC = false>
 __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant__ T5aArgs a) {
     constexpr int D = Fam::D, P = Fam::P;
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,10 +170,26 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
     }
     int ev = 0;                                   // next event ahead of t (event times are tstops of the forward solve)
     const bool fixed = (a.flags & 16u) != 0;      // constant step dt0, no error control (fixed-step Tsit5 with off-grid save times)
+    bool after_event = false;                     // CC: the step starts on an event (condition ~0 with a random sign)
+    int nfound = 0;
+    // component cc_idx of the step's dense output at theta (k1..k7 in registers)
+    auto cond_at = [&](double th, double hh) {
+        double w[7];
+        t5_weights(a, th, w);
+        double r = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 7; s++) acc += w[s] * k[s][j];
+            if (j == a.cc_idx) r = u[j] + hh * acc;
+        }
+        return r - a.cc_level;
+    };
     while (t < a.t1) {
         if (++iters > 10000000L || n >= a.maxs) { stat = 2; break; }
         bool last = false;
-        const double tend = ev < a.nev ? a.ev_t[ev] : a.t1;
+        const double tend = (!CC && ev < a.nev) ? a.ev_t[ev] : a.t1;
         if (t + h >= tend || fabs(t + h - tend) < 100 * 2.22e-16 * fabs(tend)) { h = tend - t; last = true; }
         t5_step<D>(a, rhs, t, h, u, k, un);
         const double EEst = fixed ? 0.0 : t5_error<D>(a, h, u, un, k);
@@ -158,8 +202,40 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
         double q = q11 / pow(qold, 2.0 / 25.0);
         q = fmax(1.0 / 10.0, fmin(5.0, q / 0.9));
         if (EEst <= 1.0) {
-            const double tn = last ? tend : t + h;
-            const bool at_event = last && ev < a.nev;
+            double tn = last ? tend : t + h;
+            bool at_event = !CC && last && ev < a.nev;
+            if (CC) {
+                // sign changes of the condition on the dense output, sampled at theta = j / 10 (interp_points = 10 of
+                // ContinuousCallback: a long step may hold a whole flight); right after an event the first sample decides the side
+                double gprev = t5_pick<D>(u, a.cc_idx) - a.cc_level, thprev = 0.0, lo = 0.0, hi = 1.0;
+                bool hit = false;
+                for (int j = 1; j <= 10 && !hit; j++) {
+                    const double th = j == 10 ? 1.0 : 0.1 * j;
+                    const double gj = (j == 10) ? t5_pick<D>(un, a.cc_idx) - a.cc_level : cond_at(th, h);
+                    if (after_event && j == 1) { gprev = gj; thprev = th; continue; }
+                    if ((a.cc_dir <= 0 && gprev > 0 && gj <= 0) || (a.cc_dir >= 0 && gprev < 0 && gj >= 0)) { hit = true; lo = thprev; hi = th; }
+                    else { gprev = gj; thprev = th; }
+                }
+                after_event = false;
+                if (hit) {
+                    // bisection of the crossing to the last bit, then the step is REDONE with h' = theta* h so that the stored
+                    // dense data belong to [t, tau] (k[0] = f(u) is still valid)
+                    const bool pos = gprev > 0;
+                    for (int it = 0; it < 200; it++) {
+                        const double mid = 0.5 * (lo + hi);
+                        if (!(mid > lo && mid < hi)) break;
+                        const double gm = cond_at(mid, h);
+                        if ((gm > 0) == pos && gm != 0) lo = mid; else hi = mid;
+                    }
+                    const double hh = hi * h;
+                    t5_step<D>(a, rhs, t, hh, u, k, un);
+                    tn = t + hh;
+                    at_event = true;
+                    if (nfound >= a.cc_maxev) { stat = 3; break; }
+                    a.cc_t[(int64_t)nfound * N + i] = tn;
+                    nfound++;
+                }
+            }
             // a save time that coincides with an event records the post-event state (saved after the affect, below)
             while (a.saved && ksave < a.K && (a.saveat[ksave] < tn || (a.saveat[ksave] == tn && !at_event))) {
                 const double hh = tn - t, th = (hh == 0.0) ? 1.0 : (a.saveat[ksave] - t) / hh;
@@ -180,14 +256,22 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                 for (int j = 0; j < D; j++) a.fk[(((int64_t)n * 7 + s) * D + j) * N + i] = k[s][j];
             if (at_event) {
                 // affect!: the next step starts from the post-event state; k7 = f(u^-) stays with the step just stored
+                if (CC) {
+                    double sc[D], sh[D];
+                    t5_cc_affect<D, P>(a, p, sc, sh);
+#pragma unroll
+                    for (int j = 0; j < D; j++) un[j] = sc[j] * un[j] + sh[j];
+                    after_event = true;
+                } else {
 #pragma unroll
                 for (int j = 0; j < D; j++) un[j] = a.ev_s[ev * D + j] * un[j] + a.ev_c[ev * D + j];
                 if (a.ev_ps) {
 #pragma unroll
                     for (int q = 0; q < P; q++) p[q] = a.ev_ps[ev * P + q] * p[q] + a.ev_pc[ev * P + q];
                 }
-                Fam::f(un, p, k[6]);
                 ev++;
+                }
+                Fam::f(un, p, k[6]);
                 while (a.saved && ksave < a.K && a.saveat[ksave] == tn) {
 #pragma unroll
                     for (int j = 0; j < D; j++) a.saved[((int64_t)ksave * D + j) * N + i] = un[j];
@@ -205,6 +289,7 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
         }
     }
     a.fn[i] = n;
+    if (CC) a.cc_n[i] = nfound;
     bool ok = true;
 #pragma unroll
     for (int j = 0; j < D; j++) ok = ok && isfinite(u[j]);
@@ -217,7 +302,7 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
 // checkpoints (every forward knot = sol.t, the direct-interface default, or the save times), which are tstops of the reverse
 // solve (src/backsolve_adjoint.jl:32-61, :523-546; src/sensitivity_interface.jl:433, :484-486; the reference's own
 // Lorenz check, test/Core3/adjoint.jl:1157-1241)
-template <class Fam, int SA, bool SHARED_P, int COST>
+template <class Fam, int SA, bool SHARED_P, int COST, bool CC = false>
 __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant__ T5aArgs a) {
     constexpr int D = Fam::D, P = Fam::P, L = (SA == SA_INTERP) ? D + P : (SA == SA_BACKSOLVE ? 2 * D + P : D);
     constexpr int YO = (SA == SA_BACKSOLVE) ? D + P : 0;          // offset of y inside z (Backsolve)
@@ -264,7 +349,9 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     };
     const double T = a.t1, t0 = a.t0;
     double t = T;
-    int cur = a.K - 1, nrev = 0, ck = sol.n, evc = a.nev - 1;
+    // CC: this member's own event list, found by the forward solve
+    auto evt = [&](int e) { return CC ? a.cc_t[(int64_t)e * N + i] : a.ev_t[e]; };
+    int cur = a.K - 1, nrev = 0, ck = sol.n, evc = (CC ? a.cc_n[i] : a.nev) - 1;
     bool fsal_ok = false, overflow = false;
     const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
     if (SA == SA_BACKSOLVE) {
@@ -284,7 +371,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
             }
         } else if (cur >= 0 && fabs(a.saveat[cur] - tt) <= tol) {
             double y[D];
-            sol.eval(a.saveat[cur], evc >= 0 && a.ev_t[evc] == a.saveat[cur], y);      // post-event state at a coinciding event
+            sol.eval(a.saveat[cur], evc >= 0 && evt(evc) == a.saveat[cur], y);      // post-event state at a coinciding event
 #pragma unroll
             for (int j = 0; j < D; j++) z[YO + j] = y[j];
             fsal_ok = false;
@@ -293,12 +380,38 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     // reverse affect of a preset-time event: lam(tau-) = scale .* lam(tau+); Backsolve takes y(tau-) from the forward
     // solution (the reference keeps it as `uleft` of the TrackedAffect).  Runs after the checkpoint reset and the loss jump.
     auto event_if_at = [&](double tt) {
-        while (evc >= 0 && fabs(a.ev_t[evc] - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
+        while (evc >= 0 && fabs(evt(evc) - tt) <= EPS100 * fmax(fabs(tt), 1.0)) {
+            if constexpr (CC) {
+                // state-dependent event time (the implicit correction of src/callback_tracking.jl:232-480): with u+ = A u- + c,
+                // g(u-) = 0:  lam- = A'lam+ - e_ci [(A f- - f+)'lam+] / f-[ci],   dG/dp += (dA/dp u-)'lam+
+                double um[D], up[D], fm[D], fp[D], sc[D], sh[D];
+                const double tau = evt(evc);
+                sol.eval(tau, false, um); sol.eval(tau, true, up);
+                Fam::f(um, p, fm); Fam::f(up, p, fp);
+                t5_cc_affect<D, P>(a, p, sc, sh);
+                double wl = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; j++) wl += (sc[j] * fm[j] - fp[j]) * z[j];
+                if (a.cc_pcomp >= 0) {
+                    const double gpar = a.cc_psign * t5_pick<D>(um, a.cc_pcomp) * t5_pick<D>(z, a.cc_pcomp);
+#pragma unroll
+                    for (int q = 0; q < P; q++) if (q == a.cc_pparam) {
+                        if (SA == SA_INTERP || SA == SA_BACKSOLVE) z[D + (L > D ? q : 0)] += gpar; else acc[q] += gpar;
+                    }
+                }
+                const double corr = wl / t5_pick<D>(fm, a.cc_idx);
+#pragma unroll
+                for (int j = 0; j < D; j++) { z[j] *= sc[j]; if (j == a.cc_idx) z[j] -= corr; }
+                if (SA == SA_BACKSOLVE) {
+#pragma unroll
+                    for (int j = 0; j < D; j++) z[YO + j] = um[j];
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < D; j++) z[j] *= a.ev_s[evc * D + j];
             if (SA == SA_BACKSOLVE) {
                 double y[D];
-                sol.eval(a.ev_t[evc], false, y);
+                sol.eval(evt(evc), false, y);
 #pragma unroll
                 for (int j = 0; j < D; j++) z[YO + j] = y[j];
             }
@@ -314,6 +427,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
 #pragma unroll
                 for (int q = 0; q < P; q++) p0[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
                 t5_event_params<P>(a, evc, p0, p);
+            }
             }
             tev = tt; evc--; fsal_ok = false;
         }
@@ -347,7 +461,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         if (++iters > 50000000L || (SA == SA_QUAD && nrev >= a.maxs)) { overflow = true; break; }
         double tstop = t0;
         if (cur >= 0 && a.saveat[cur] < t && a.saveat[cur] > tstop) tstop = a.saveat[cur];
-        if (evc >= 0 && a.ev_t[evc] < t && a.ev_t[evc] > tstop) tstop = a.ev_t[evc];
+        if (evc >= 0 && evt(evc) < t && evt(evc) > tstop) tstop = evt(evc);
         if (SA == SA_BACKSOLVE && ckpt_on && every) {            // every forward knot is a tstop of the reverse solve
             int c2 = ck;
             while (c2 >= 0 && sol.T(c2) >= t - EPS100 * fmax(fabs(t), 1.0)) c2--;

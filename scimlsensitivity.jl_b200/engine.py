@@ -151,6 +151,25 @@ class DeviceEnsemble:
         self.handle.set_events(times, scale, shift, pscale, pshift)
         self.events = (times, scale, shift, pscale, pshift)
 
+    def set_continuous_callback(self, cb):
+        """State-dependent event (problems.ContinuousCallback) of the hybrid system; call before forward().  None removes it."""
+        if cb is None:
+            self.handle.set_continuous_callback(0, enabled=False)
+            self.continuous_callback = None
+            return
+        if tuple(cb.save_positions) != (False, False):
+            raise NotImplementedError("ContinuousCallback: save_positions = (false, false) is the mode carried on the device")
+        for name, v in (("scale", cb.scale), ("shift", cb.shift)):
+            if v is not None and np.asarray(v).reshape(-1).shape[0] != self.d:
+                raise ValueError(f"ContinuousCallback: {name} must have d entries")
+        self.handle.set_continuous_callback(cb.idx, cb.level, cb.direction, cb.scale, cb.shift, -1 if cb.p_comp is None else cb.p_comp,
+                                            cb.p_param, cb.p_sign, cb.max_events)
+        self.continuous_callback = cb
+
+    def event_times(self):
+        """-> (counts[N], times[max_events, N]): the event lists found by the last forward pass."""
+        return self.handle.event_times(self.N, self.continuous_callback.max_events)
+
     def set_reverse(self, sensealg, cost=None, no_start=False, checkpointing=True, ckpt_every_step=False, t=None, dgdp=None):
         """Re-target the next reverse pass (sensealg / cost / save times) without re-running the forward pass.
         dgdp: ParamAffine, the parameter part of the discrete cost (dgdp_discrete)."""

@@ -14,6 +14,7 @@ import numpy as np
 FAMILIES = {
     # name: (d, P, m)
     "lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "sde_linear": (2, 2, 2),
+    "ball": (2, 2, 0),           # bouncing ball x' = v, v' = -p[0]; p = [gravity, restitution] (adaptive Tsit5; ContinuousCallback)
     "mlp": (2, 4482, 0),         # 2 -> 64 -> 64 -> 2 tanh MLP, p = [W1, b1, W2, b2, W3, b3] column-major flattened
 }
 
@@ -155,6 +156,33 @@ class QuadraticRunningCost:
     b: Any = 0.0
     c: Any = None
     e: Any = None
+
+
+@dataclass(frozen=True)
+class ContinuousCallback:
+    """ContinuousCallback(condition, affect!) of the named family the device path carries (the
+    reference's treatment: src/callback_tracking.jl:232-480, docs/src/examples/hybrid_jump/bouncing_ball.md):
+      condition(u, t, integrator) = u[idx] - level      (fires on a zero crossing; direction -1 = downwards only, i.e.
+                                                         affect_neg! = nothing ..., +1 upwards only, 0 both)
+      affect!(integrator): u .= scale .* u .+ shift, then u[p_comp] = p_sign * p[p_param] * u[p_comp]   (if p_comp is set)
+    The bouncing ball "integrator.u[2] = -integrator.p[2] * integrator.u[2]" when u[1] crosses 0 downwards is
+    ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0).  Indices are 0-based.
+    save_positions = (false, false) only; every ensemble member finds its own event times on the device."""
+    idx: int
+    level: float = 0.0
+    direction: int = -1
+    scale: Any = None
+    shift: Any = None
+    p_comp: Optional[int] = None
+    p_param: int = 0
+    p_sign: float = 1.0
+    max_events: int = 64
+    save_positions: Tuple[bool, bool] = (False, False)
+
+    def key(self):
+        sc = None if self.scale is None else np.asarray(self.scale, dtype=np.float64).tobytes()
+        sh = None if self.shift is None else np.asarray(self.shift, dtype=np.float64).tobytes()
+        return ("cc", self.idx, self.level, self.direction, sc, sh, self.p_comp, self.p_param, self.p_sign, self.max_events)
 
 
 def saveat_to_times(saveat, tspan):

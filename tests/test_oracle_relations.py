@@ -546,3 +546,33 @@ def test_mixed_cost_family_with_parameter_part_matches_finite_differences():
         rc = O.gradient(cfgc, np.zeros(0), LV_U0, LV_P)
         gpc = _fd_grad(lambda q: O.loss(cfgc, np.zeros(0), LV_U0, q)[0], LV_P)
         assert np.allclose(rc["dp"], gpc, rtol=1e-7, atol=1e-6), sa
+
+
+def test_continuous_callback_bouncing_ball_saltation_matches_finite_differences_and_the_closed_form():
+    """State-dependent event (ContinuousCallback, docs/src/examples/hybrid_jump/bouncing_ball.md; reverse-pass treatment of
+    src/callback_tracking.jl:232-480): the oracle's adjoint with the implicit event-time correction vs (a) central differences
+    of the oracle's own hybrid forward solve over several bounces, (b) the closed form of one bounce
+    x(T) = e w s - g s^2 / 2, t* = sqrt(2 x0 / g), w = g t*, s = T - t*."""
+    cr = dict(idx=0, level=0.0, direction=-1, pcomp=1, pparam=1, psign=-1.0)
+    u0 = np.array([[50.0], [0.0]]); p = np.array([9.8, 0.8])
+    ts = np.linspace(0.5, 15.0, 30)
+    kw = dict(abstol=1e-10, reltol=1e-10)
+    for sa in ("interpolating", "gauss", "gauss_kronrod", "backsolve"):
+        cfg = O.make_cfg("ball", sa, "tsit5_adaptive", 1, ts, 0.0, 15.0, cost=("affine", 1.0, 0.0), crossing=cr, ckpt_every_step=True, **kw)
+        r = O.gradient(cfg, ts, u0, p)
+        gp = _fd_grad(lambda q: O.loss(cfg, ts, u0, q)[0], p, h=1e-5)
+        gu = _fd_grad(lambda u: O.loss(cfg, ts, u, p)[0], u0, h=1e-5)
+        assert np.allclose(r["dp"], gp, rtol=1e-6), (sa, r["dp"], gp)
+        assert np.allclose(r["du0"].ravel(), gu.ravel(), rtol=1e-6), sa
+    g, e, T, x0 = 9.8, 0.8, 2.5, 10.0
+    def xT(x0, g, e):
+        tstar = np.sqrt(2 * x0 / g); w = g * tstar; s = T - tstar
+        return e * w * s - 0.5 * g * s * s
+    h = 1e-6
+    cfg = O.make_cfg("ball", "gauss", "tsit5_adaptive", 1, np.array([T]), 0.0, T, crossing=cr, **kw)
+    dL = np.zeros((1, 2, 1)); dL[0, 0, 0] = 1.0
+    r = O.gradient(cfg, np.array([T]), np.array([[x0], [0.0]]), np.array([g, e]), dLdu=dL)
+    assert abs(r["saved"][0, 0, 0] - xT(x0, g, e)) < 1e-8
+    assert abs(r["du0"][0, 0] - (xT(x0 + h, g, e) - xT(x0 - h, g, e)) / (2 * h)) < 1e-6
+    assert abs(r["dp"][0] - (xT(x0, g + h, e) - xT(x0, g - h, e)) / (2 * h)) < 1e-6
+    assert abs(r["dp"][1] - (xT(x0, g, e + h) - xT(x0, g, e - h)) / (2 * h)) < 1e-6
