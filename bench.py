@@ -416,6 +416,7 @@ def run_ours(args):
 
     # ---------------- device-resident arm (`value`) ----------------
     main = Shard(spec_c2(), N, rank, world, local, block=args.block)
+    comm_fused = world > 1 and main.eng.handle.comm_is_fused() and not args.nccl_allreduce
     eng, u0_h, p_h = main.eng, main.u0_h, main.p_h
     sampler = ClockSampler(local)
     if rank == 0:
@@ -543,8 +544,9 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": c2_config(world, N, args.block),
             "phases_ms": {"forward": fwd_ms, "reverse_incl_allreduce": rev_ms},
-            "allreduce": None if world == 1 else ("ncclAllReduce (flag)" if args.nccl_allreduce else
-                                                  "fused into the reverse kernel (peer-memory mailboxes) when the GPUs map each other, else ncclAllReduce"),
+            "allreduce": None if world == 1 else ("ncclAllReduce after the reverse kernel (--nccl-allreduce)" if args.nccl_allreduce else
+                                                  "fused into the reverse kernel (peer-memory mailboxes)" if comm_fused else
+                                                  "ncclAllReduce after the reverse kernel (the GPUs do not map each other)"),
             "roofline": {"bound": "hbm", "kernel": "tsit5_reverse_kernel<Lorenz,GAUSS>", "achieved": achieved, "peak": hbm,
                          "unit": "GB/s", "frac": achieved / hbm,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
