@@ -160,24 +160,28 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             c = [x.strip() for x in line.split(",")]
             if len(c) < 9:
                 continue
             try:
-                if t_begin is not None:
-                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
-                    if ts < t_begin - 0.02 or ts > t_end + 0.02:
-                        continue
-                sm.append(float(c[1])); mx.append(float(c[2]))
+                ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(c[1]), float(c[2]), [name for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9])
+                                                            if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(mx)), reasons=sorted(reasons), samples=len(sm))
+        window = "timed region"
+        sel = rows if t_begin is None else [r for r in rows if t_begin - 0.02 <= r[0] <= t_end + 0.02]
+        if not sel and rows and t_begin is not None:
+            # a timed region shorter than the sampling period (nvidia-smi -lms 20 delivers ~50-100 ms on a busy box): the
+            # nearest samples, taken under the load of the warm-up steps just before / the legs just after
+            mid = 0.5 * (t_begin + t_end)
+            sel = sorted(rows, key=lambda r: abs(r[0] - mid))[:3]
+            window = "nearest samples (%.0f ms from the timed region)" % (1e3 * max(abs(r[0] - mid) for r in sel))
+        if sel:
+            out.update(sm_mhz=float(np.median([r[1] for r in sel])), sm_max_mhz=float(np.max([r[2] for r in sel])),
+                       reasons=sorted({x for r in sel for x in r[3]}), samples=len(sel), window=window)
         try:
             os.remove(self.path)
         except OSError:
@@ -416,7 +420,7 @@ def run_ours(args):
 
     # ---------------- device-resident arm (`value`) ----------------
     main = Shard(spec_c2(), N, rank, world, local, block=args.block)
-    comm_fused = world > 1 and main.eng.handle.comm_is_fused() and not args.nccl_allreduce
+    comm_fused = world > 1 and main.eng.handle.comm_is_fused and not args.nccl_allreduce
     eng, u0_h, p_h = main.eng, main.u0_h, main.p_h
     sampler = ClockSampler(local)
     if rank == 0:
