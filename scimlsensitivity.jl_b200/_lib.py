@@ -99,7 +99,10 @@ def build(force=False, verbose=False):
     bad = [r for r in results if r[1] != 0]
     if bad:
         raise RuntimeError("nvcc failed:\n" + "\n".join(r[2][-4000:] for r in bad))
-    res = subprocess.run([nvcc_path(), "-shared", "-o", LIB_PATH] + [r[0] for r in results] + ["-ldl"], capture_output=True, text=True)
+    # host link with g++ (no -rdc code: nvcc's device-link step would only add an empty default-arch sm_52 stub cubin)
+    cuda_lib = os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc_path()))), "lib64")
+    res = subprocess.run(["g++", "-shared", "-o", LIB_PATH] + [r[0] for r in results] + ["-L" + cuda_lib, "-lcudart_static", "-lrt", "-lpthread", "-ldl"],
+                         capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stderr[-4000:])
     if verbose:
