@@ -595,7 +595,7 @@ def run_ours(args):
 
 
 def run_secondary(args):
-    """--workload c2f32|c3|c4|c5: one BASELINE config alone on one GPU (profiling / tuning; same JSON shape)."""
+    """--workload c1|c2f32|c3|c4|c5: one BASELINE config alone on one GPU (profiling / tuning; same JSON shape)."""
     import torch
     import scimlsensitivity_jl_b200 as b
     from oracle import oracle as O
@@ -614,6 +614,19 @@ def run_secondary(args):
                                cost=b.AffineCost(1.0, 0.0), max_steps=8192, **kw)
         ocfg = lambda n: O.make_cfg("robertson", "quadrature", "rosenbrock23", n, saveat, 0.0, T, cost=("affine", 1.0, 0.0), shared_p=False, **kw)
         name, dtype, sample = "C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves", "f64", 256
+    elif w == "c1":
+        # BASELINE configs[0] (Lotka-Volterra, InterpolatingAdjoint, ADAPTIVE Tsit5 -- the reference's own CPU-runnable case,
+        # test/Core1/concrete_solve_derivatives.jl:106-157) as an ensemble: every member runs its own PI-controlled step sequence
+        N = args.members or 65536
+        T = 10.0
+        saveat = np.linspace(0.0, T, 101)
+        u0 = np.exp(0.2 * rng.standard_normal((2, N)))
+        p = np.array([1.5, 1.0, 3.0, 1.0])
+        kw = dict(abstol=1e-8, reltol=1e-8)
+        eng = b.DeviceEnsemble("lv", "interpolating", "tsit5_adaptive", N, saveat, (0.0, T), 0.0, on_device=True, cost=b.AffineCost(0.0, 1.0),
+                               max_steps=512, **kw)
+        ocfg = lambda n: O.make_cfg("lv", "interpolating", "tsit5_adaptive", n, saveat, 0.0, T, cost=("affine", 0.0, 1.0), **kw)
+        name, dtype, sample = "C1-ensemble Lotka-Volterra d=2 P=4 shared p, InterpolatingAdjoint, adaptive Tsit5 (PI controller) tol 1e-8, T=10, saveat=0.1, loss=sum(sol)", "f64", 4096
     elif w == "c2f32":
         # the fp32 throughput variant of C2: same ensemble, T = 1 (S = 100, K = 11), fp32 state and tables
         N = args.members or 65536
@@ -673,6 +686,13 @@ def run_secondary(args):
     t0 = time.perf_counter()
     O.gradient(cfgs, saveat, u0[:, :sample], pc, dW=dW, want_saved=False, nthreads=threads)
     cpu_s = time.perf_counter() - t0
+    parity = None
+    if w in ("c1", "c3"):           # deterministic inputs: the oracle's gradient of the sample vs the device's rows of the same members
+        refg = O.gradient(cfgs, saveat, u0[:, :sample], pc, want_saved=False, nthreads=threads)
+        du0_h = du0_d.double().cpu().numpy()[:, :sample]
+        parity = {"du0_rel": float(np.abs(du0_h - refg["du0"]).max() / np.abs(refg["du0"]).max()), "members": sample}
+        if p.ndim == 2:
+            parity["dp_rel_worst_member"] = float((np.abs(dp_d.double().cpu().numpy()[:, :sample] - refg["dp"]) / np.abs(refg["dp"]).max(axis=1, keepdims=True)).max())
     line = {"metric": "ensemble adjoint trajectories/sec", "value": N / (ms * 1e-3), "unit": "trajectories/s", "n_gpus": 1,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": dtype, "data": "synthetic", "config": {"workload": name, "members_per_gpu": N},
@@ -680,6 +700,11 @@ def run_secondary(args):
             "cpu_baseline": {"value": sample / cpu_s, "unit": "trajectories/s", "cores": threads, "kind": "port",
                              "sample": f"{sample} members of the same workload, one gradient, {cpu_s:.2f} s wall"},
             "gpu_launches": int(eng.handle.launch_count - l0)}
+    if parity is not None:
+        line["parity"] = parity
+    if w == "c1":
+        fwd_n, rev_n = [x.cpu().numpy() for x in eng.step_counts()]
+        line["steps_per_member"] = {"forward_mean": float(fwd_n.mean()), "forward_max": int(fwd_n.max()), "forward_min": int(fwd_n.min())}
     emit(line)
     eng.close()
 
@@ -712,7 +737,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members", type=int, default=0, help="override members per GPU (default 65536) / reference sample")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (multiple of 32, <= 512)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "c2f32", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "c1", "c2f32", "c3", "c4", "c5"], help="c2 = BASELINE headline (default)")
     ap.add_argument("--dtype", default="", help="c4 only: bf16_f32acc (default), f32 or f64")
     ap.add_argument("--no-secondary", action="store_true", help="skip the sharded C4 / C5 legs (profiling runs)")
     ap.add_argument("--nccl-allreduce", action="store_true", help="N > 1: ncclAllReduce instead of the fused peer-memory all-reduce (A/B)")

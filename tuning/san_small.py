@@ -1,4 +1,4 @@
-"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck): WHAT = ode | mlp | adaptive | sde."""
+"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck): WHAT = ode | mlp | adaptive | sde | r2."""
 import sys, os, numpy as np
 sys.path.insert(0, ".")
 import scimlsensitivity_jl_b200 as b
@@ -28,6 +28,33 @@ elif what == "adaptive":
     for sa in ("gauss", "gauss_kronrod", "quadrature"):
         e = b.DeviceEnsemble("robertson", sa, "rosenbrock23", N, ts, (0, 10.0), 0.0, cost=b.AffineCost(1.0, 0.0), abstol=1e-6, reltol=1e-6)
         e.forward(u0r, k); du0, dp = e.reverse(); print(what, "ros", sa, np.asarray(dp)); e.close()
+elif what == "r2":         # round-2 kernels: SEG (checkpoint_every), EV (events on the dt grid), GK, augmented Rosenbrock23, MLP Gauss, CC, dgdp
+    N = 300; T, dt = 0.4, 0.01; t = np.linspace(0, T, 5)
+    u0 = np.array([1.0, 0, 0])[:, None] + 0.1 * rng.standard_normal((3, N)); p = np.array([10.0, 28.0, 8 / 3])
+    for sa, C in (("gauss", 4), ("interpolating", 8), ("gauss_kronrod", 1)):
+        e = b.DeviceEnsemble("lorenz", sa, "tsit5_fixed", N, t, (0, T), dt, cost=b.AffineCost(1.0, -2.0), checkpoint_every=C)
+        e.forward(u0, p); du0, dp = e.reverse(); print(what, "seg", sa, C, np.asarray(dp)); e.close()
+    ul = 1 + 0.05 * rng.standard_normal((2, N)); pl = np.array([1.5, 1.0, 3.0, 1.0])
+    for sa in ("gauss", "backsolve"):
+        e = b.DeviceEnsemble("lv", sa, "tsit5_fixed", N, np.linspace(0, 1.0, 5), (0, 1.0), 0.01, cost=b.AffineCost(0.0, 1.0))
+        e.set_events([0.3, 0.5], [[1, 1], [1, 1]], [[0.5, 0], [0, 0]], [[1.0] * 4, [2.0, 1, 1, 1]], [[0.0] * 4, [-0.5, 0, 0, 0]])
+        e.forward(ul, pl); du0, dp = e.reverse(); print(what, "ev", sa, np.asarray(dp)); e.close()
+    e = b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", N, [0.013, 0.5, 0.97], (0, 1.0), 0.01, cost=b.AffineCost([2.0, 0.0], 0.0))
+    e.set_reverse("gauss", cost=b.AffineCost([2.0, 0.0], 0.0), dgdp=b.ParamAffine([0.0] * 4, [1.0, 0, 0, 0]))
+    e.forward(ul, pl); du0, dp = e.reverse(); print(what, "offgrid+dgdp", np.asarray(dp)); e.close()
+    ts = np.logspace(-2, 1, 4); u0r = np.repeat(np.array([[1.0], [0], [0]]), 70, 1); k = np.array([0.04, 3e7, 1e4])
+    for sa in ("interpolating", "backsolve"):
+        e = b.DeviceEnsemble("robertson", sa, "rosenbrock23", 70, ts, (0, 10.0), 0.0, cost=b.AffineCost(1.0, 0.0), abstol=1e-6, reltol=1e-6)
+        e.forward(u0r, k); du0, dp = e.reverse(); print(what, "ros-aug", sa, np.asarray(dp)); e.close()
+    pm = 0.3 * rng.standard_normal(4482); um = rng.uniform(-2, 2, (2, 130)); tm = np.linspace(0.05, 0.15, 3)
+    for dt_ in ("bf16_f32acc", "f32", "f64"):
+        e = b.DeviceEnsemble("mlp", "gauss", "tsit5_fixed", 130, tm, (0, 0.15), 0.05, dtype=dt_, cost=b.AffineCost(1.0, -0.5))
+        e.forward(um, pm); du0, dp = e.reverse(); print(what, "mlp-gauss", dt_, np.asarray(dp)[:3]); e.close()
+    ub = np.stack([10.0 + rng.standard_normal(70), np.zeros(70)]); tb = np.linspace(0.5, 5.0, 10)
+    for sa in ("interpolating", "gauss", "gauss_kronrod", "backsolve"):
+        e = b.DeviceEnsemble("ball", sa, "tsit5_adaptive", 70, tb, (0, 5.0), 0.0, cost=b.AffineCost(1.0, 0.0), abstol=1e-8, reltol=1e-8)
+        e.set_continuous_callback(b.ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0, max_events=16))
+        e.forward(ub, np.array([9.8, 0.8])); du0, dp = e.reverse(); print(what, "cc", sa, np.asarray(dp)); e.close()
 else:
     N = 200; t = np.linspace(0, 0.1, 11); u0 = np.ones((2, N)); p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
     for st in ("em", "euler_heun"):
