@@ -4,6 +4,7 @@ summaries under profiles/: key metrics (json + txt) and the top stall sites of t
 usage: python profiles/summarize.py gpurun_out/r1_reverse.ncu-rep profiles/r1_reverse"""
 import collections
 import csv
+import os
 import io
 import json
 import subprocess
@@ -60,6 +61,28 @@ def main(rep, prefix):
     m["opcode_mix_warp_instructions"] = dict(ops.most_common(16))
     m["stall_samples"] = dict(stall_tot.most_common(10))
     m["top_sample_sites"] = [dict(samples=a, addr=b, sass=c) for a, b, c in sorted(sites, reverse=True)[:10]]
+    # CUDA-C correlation of the same page (needs -lineinfo + --import-source on): samples per source line
+    m["top_source_lines"] = []
+    try:
+        cs = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+        agg = collections.Counter()
+        text = {}
+        fname, h3 = "", None
+        for r in csv.reader(io.StringIO(cs)):
+            if len(r) == 2 and r[0] == "File Path":
+                fname, h3 = os.path.basename(r[1]), None
+            elif len(r) > 6 and r[0] == "Line No":
+                h3 = r.index("# Samples")
+            elif h3 is not None and len(r) > h3 and r[0].isdigit():
+                if r[1].strip():
+                    text[(fname, int(r[0]))] = r[1].strip()[:110]
+                try:
+                    agg[(fname, int(r[0]))] += int(r[h3] or 0)
+                except ValueError:
+                    pass
+        m["top_source_lines"] = [dict(samples=n, file=k[0], line=k[1], source=text.get(k, "")) for k, n in agg.most_common(25) if n]
+    except Exception as e:                                   # older ncu: no CUDA correlation
+        m["top_source_lines_error"] = str(e)
     with open(prefix + "_ncu_summary.json", "w") as f:
         json.dump(m, f, indent=1)
     with open(prefix + "_ncu_summary.txt", "w") as f:
@@ -76,6 +99,10 @@ def main(rep, prefix):
         f.write("\n# top sampled instructions\n")
         for s in m["top_sample_sites"]:
             f.write(f"  {s['samples']:7d} {s['addr']} {s['sass']}\n")
+        if m["top_source_lines"]:
+            f.write("\n# top sampled source lines (CUDA-C view)\n")
+            for s_ in m["top_source_lines"]:
+                f.write(f"  {s_['samples']:7d} {s_['file']}:{s_['line']}  {s_['source']}\n")
     print("wrote", prefix + "_ncu_summary.{json,txt}")
 
 

@@ -103,28 +103,39 @@ struct FwdDense {
     // linear steps (same result as a bisection over the knots, but 1-2 loads -- the two knots the interpolation needs
     // anyway -- instead of log2(n) dependent ones).
     mutable int cur = 0;
+    // The interval's record (u_n, k1, k2: 3 D doubles) and its two knots stay in REGISTERS between lookups: the 3-5 lookups of
+    // one adjoint step fall into one or two forward intervals, so most of them touch no memory at all.
+    mutable int civ = -1; mutable double cta = 0.0, ctb = 0.0, cu[D], ck1[D], ck2[D];
     __device__ __forceinline__ double T(int idx) const { return ft[(int64_t)idx * N + i]; }
     __device__ __forceinline__ void eval(double t, bool right, double* y, double* yd) const {
-        int iv = cur < n - 1 ? cur : n - 1;
-        if (iv < 0) iv = 0;
-        if (right) {        // largest idx with T(idx) <= t, clamped to [0, n-1]   (sol(t), continuity = :right)
-            while (iv > 0 && T(iv) > t) iv--;
-            while (iv < n - 1 && T(iv + 1) <= t) iv++;
-        } else {            // (smallest idx with T(idx) >= t) - 1, clamped           (continuity = :left)
-            while (iv > 0 && T(iv) >= t) iv--;
-            while (iv < n - 1 && T(iv + 1) < t) iv++;
+        // the cached interval is the answer exactly when the cursor search would stop on it at once
+        const bool hit = civ >= 0 && (right ? ((civ == 0 || cta <= t) && (civ == n - 1 || ctb > t)) : ((civ == 0 || cta < t) && (civ == n - 1 || ctb >= t)));
+        if (!hit) {
+            int iv = cur < n - 1 ? cur : n - 1;
+            if (iv < 0) iv = 0;
+            if (right) {        // largest idx with T(idx) <= t, clamped to [0, n-1]   (sol(t), continuity = :right)
+                while (iv > 0 && T(iv) > t) iv--;
+                while (iv < n - 1 && T(iv + 1) <= t) iv++;
+            } else {            // (smallest idx with T(idx) >= t) - 1, clamped           (continuity = :left)
+                while (iv > 0 && T(iv) >= t) iv--;
+                while (iv < n - 1 && T(iv + 1) < t) iv++;
+            }
+            cur = iv; civ = iv;
+            cta = T(iv); ctb = T(iv + 1);
+#pragma unroll
+            for (int j = 0; j < D; j++) {
+                cu[j] = fu[((int64_t)iv * D + j) * N + i];
+                ck1[j] = fk[(((int64_t)iv * 2 + 0) * D + j) * N + i]; ck2[j] = fk[(((int64_t)iv * 2 + 1) * D + j) * N + i];
+            }
         }
-        cur = iv;
-        const double ta = T(iv), h = T(iv + 1) - ta;
+        const double ta = cta, h = ctb - ta;
         const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
         const double c1 = th * (1 - th) / (1 - 2 * ROS_D), c2 = th * (th - 2 * ROS_D) / (1 - 2 * ROS_D);
         const double d1 = (1 - 2 * th) / (1 - 2 * ROS_D), d2 = (2 * th - 2 * ROS_D) / (1 - 2 * ROS_D);
 #pragma unroll
         for (int j = 0; j < D; j++) {
-            const double u = fu[((int64_t)iv * D + j) * N + i];
-            const double k1 = fk[(((int64_t)iv * 2 + 0) * D + j) * N + i], k2 = fk[(((int64_t)iv * 2 + 1) * D + j) * N + i];
-            y[j] = u + h * (c1 * k1 + c2 * k2);
-            if (yd) yd[j] = d1 * k1 + d2 * k2;
+            y[j] = cu[j] + h * (c1 * ck1[j] + c2 * ck2[j]);
+            if (yd) yd[j] = d1 * ck1[j] + d2 * ck2[j];
         }
     }
 };
