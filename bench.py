@@ -624,7 +624,7 @@ def run_secondary(args):
         p = np.array([1.5, 1.0, 3.0, 1.0])
         kw = dict(abstol=1e-8, reltol=1e-8)
         eng = b.DeviceEnsemble("lv", "interpolating", "tsit5_adaptive", N, saveat, (0.0, T), 0.0, on_device=True, cost=b.AffineCost(0.0, 1.0),
-                               max_steps=512, **kw)
+                               max_steps=512, block_threads=args.block, **kw)
         ocfg = lambda n: O.make_cfg("lv", "interpolating", "tsit5_adaptive", n, saveat, 0.0, T, cost=("affine", 0.0, 1.0), **kw)
         name, dtype, sample = "C1-ensemble Lotka-Volterra d=2 P=4 shared p, InterpolatingAdjoint, adaptive Tsit5 (PI controller) tol 1e-8, T=10, saveat=0.1, loss=sum(sol)", "f64", 4096
     elif w == "c2f32":

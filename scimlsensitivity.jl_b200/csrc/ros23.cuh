@@ -104,28 +104,48 @@ struct FwdDense {
     // anyway -- instead of log2(n) dependent ones).
     mutable int cur = 0;
     // The interval's record (u_n, k1, k2: 3 D doubles) and its two knots stay in REGISTERS between lookups: the 3-5 lookups of
-    // one adjoint step fall into one or two forward intervals, so most of them touch no memory at all.
-    mutable int civ = -1; mutable double cta = 0.0, ctb = 0.0, cu[D], ck1[D], ck2[D];
+    // one adjoint step fall into one or two forward intervals, so most of them touch no memory at all.  A second register set
+    // holds the interval BELOW (the solve runs downwards): its loads are issued when the current interval is entered and are
+    // first used one or more steps later, so crossing a knot does not wait for global memory either (every lane has its own
+    // step sequence: without this some lane of the warp misses on nearly every lookup).
+    mutable int civ = -1, aiv = -1; mutable double cta = 0.0, ctb = 0.0, cu[D], ck1[D], ck2[D], ata = 0.0, au[D], ak1[D], ak2[D];
     __device__ __forceinline__ double T(int idx) const { return ft[(int64_t)idx * N + i]; }
+    __device__ __forceinline__ bool holds(int iv, double ta, double tb, double t, bool right) const {
+        return right ? ((iv == 0 || ta <= t) && (iv == n - 1 || tb > t)) : ((iv == 0 || ta < t) && (iv == n - 1 || tb >= t));
+    }
     __device__ __forceinline__ void eval(double t, bool right, double* y, double* yd) const {
         // the cached interval is the answer exactly when the cursor search would stop on it at once
-        const bool hit = civ >= 0 && (right ? ((civ == 0 || cta <= t) && (civ == n - 1 || ctb > t)) : ((civ == 0 || cta < t) && (civ == n - 1 || ctb >= t)));
-        if (!hit) {
-            int iv = cur < n - 1 ? cur : n - 1;
-            if (iv < 0) iv = 0;
-            if (right) {        // largest idx with T(idx) <= t, clamped to [0, n-1]   (sol(t), continuity = :right)
-                while (iv > 0 && T(iv) > t) iv--;
-                while (iv < n - 1 && T(iv + 1) <= t) iv++;
-            } else {            // (smallest idx with T(idx) >= t) - 1, clamped           (continuity = :left)
-                while (iv > 0 && T(iv) >= t) iv--;
-                while (iv < n - 1 && T(iv + 1) < t) iv++;
-            }
-            cur = iv; civ = iv;
-            cta = T(iv); ctb = T(iv + 1);
+        if (!(civ >= 0 && holds(civ, cta, ctb, t, right))) {
+            if (aiv >= 0 && holds(aiv, ata, cta, t, right)) {
+                civ = aiv; cur = aiv; ctb = cta; cta = ata;
 #pragma unroll
-            for (int j = 0; j < D; j++) {
-                cu[j] = fu[((int64_t)iv * D + j) * N + i];
-                ck1[j] = fk[(((int64_t)iv * 2 + 0) * D + j) * N + i]; ck2[j] = fk[(((int64_t)iv * 2 + 1) * D + j) * N + i];
+                for (int j = 0; j < D; j++) { cu[j] = au[j]; ck1[j] = ak1[j]; ck2[j] = ak2[j]; }
+            } else {
+                int iv = cur < n - 1 ? cur : n - 1;
+                if (iv < 0) iv = 0;
+                if (right) {        // largest idx with T(idx) <= t, clamped to [0, n-1]   (sol(t), continuity = :right)
+                    while (iv > 0 && T(iv) > t) iv--;
+                    while (iv < n - 1 && T(iv + 1) <= t) iv++;
+                } else {            // (smallest idx with T(idx) >= t) - 1, clamped           (continuity = :left)
+                    while (iv > 0 && T(iv) >= t) iv--;
+                    while (iv < n - 1 && T(iv + 1) < t) iv++;
+                }
+                cur = iv; civ = iv;
+                cta = T(iv); ctb = T(iv + 1);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    cu[j] = fu[((int64_t)iv * D + j) * N + i];
+                    ck1[j] = fk[(((int64_t)iv * 2 + 0) * D + j) * N + i]; ck2[j] = fk[(((int64_t)iv * 2 + 1) * D + j) * N + i];
+                }
+            }
+            aiv = civ - 1;
+            if (aiv >= 0) {       // loads of the interval below: in flight until the solve gets there
+                ata = T(aiv);
+#pragma unroll
+                for (int j = 0; j < D; j++) {
+                    au[j] = fu[((int64_t)aiv * D + j) * N + i];
+                    ak1[j] = fk[(((int64_t)aiv * 2 + 0) * D + j) * N + i]; ak2[j] = fk[(((int64_t)aiv * 2 + 1) * D + j) * N + i];
+                }
             }
         }
         const double ta = cta, h = ctb - ta;

@@ -62,53 +62,45 @@ __device__ __forceinline__ void t5_event_params(const T5aArgs& a, int upto, cons
     }
 }
 
-// forward dense solution of one member.  The reverse solve visits it monotonically and evaluates it 6-9 times per step, mostly
-// inside ONE forward interval: the interval's record (u_n, k1..k7) is kept in the thread's own shared-memory column (`sc`,
-// stride = blockDim.x; 8 D doubles) with its knots in registers, so a lookup touches global memory only when the interval
-// changes (C1-ensemble profile before: 20.5 GB of DRAM reads, long_scoreboard 12.8 -- 6 x 17 dependent loads per step).
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// forward dense solution of one member.  The reverse solve visits it monotonically (downwards) and evaluates it 6-9 times per
+// step, mostly inside ONE forward interval.  The interval's record (u_n, k1..k7, t_n: 8 D + 1 doubles) is kept in the thread's
+// own shared-memory column, double buffered: when a thread enters interval iv it starts an asynchronous copy (cp.async, 8 B per
+// element, no register staging) of interval iv - 1 into the other buffer; by the time the solve crosses the knot the record is
+// there and the buffers swap.  Global memory is waited for only at the start and after a jump over several intervals.
+// Why: every lane of a warp has its own step sequence, so with plain loads SOME lane misses on nearly every lookup and the
+// whole warp pays a dependent global round trip per stage (C1-ensemble profile before: 20.5 GB DRAM reads, long_scoreboard
+// 12.8, 37 k cycles per step and warp).
 template <int D>
 struct T5Dense {
+    static constexpr int REC = 8 * D + 1;                // u[D], k[7][D], t_n
     const T5aArgs& a; int64_t i; int n;
     mutable int cur = 0;
-    double* sc = nullptr; int stride = 0;                // interval cache (null: every lookup reads global memory)
-    mutable int civ = -1; mutable double cta = 0.0, ctb = 0.0;
+    double* sc = nullptr; int stride = 0;                // interval cache: [2][REC][stride] (null: every lookup reads global memory)
+    mutable int cb = 0, civ = -1, aiv = -1;              // current buffer, its interval, the interval (being) prefetched into the other one
+    mutable double cta = 0.0, ctb = 0.0;
     __device__ __forceinline__ double T(int idx) const { return a.ft[(int64_t)idx * a.N + i]; }
+    __device__ __forceinline__ bool holds(int iv, double ta, double tb, double t, bool right) const {
+        // interval iv = [ta, tb] is where the cursor search stops at once
+        return right ? ((iv == 0 || ta <= t) && (iv == n - 1 || tb > t)) : ((iv == 0 || ta < t) && (iv == n - 1 || tb >= t));
+    }
     __device__ __forceinline__ void eval(double t, bool right, double* y) const {
-        // the cached interval is the answer exactly when the cursor search below would stop on it at once
-        const bool hit = sc && civ >= 0 &&
-                         (right ? ((civ == 0 || cta <= t) && (civ == n - 1 || ctb > t)) : ((civ == 0 || cta < t) && (civ == n - 1 || ctb >= t)));
-        if (!hit) {
-            // cursor instead of a bisection over the knots: the adjoint solve visits the forward solution monotonically
+        if (!sc) {                                        // uncached variant (forward-side callers)
             int iv = cur < n - 1 ? cur : n - 1;
             if (iv < 0) iv = 0;
             if (right) { while (iv > 0 && T(iv) > t) iv--; while (iv < n - 1 && T(iv + 1) <= t) iv++; }
             else { while (iv > 0 && T(iv) >= t) iv--; while (iv < n - 1 && T(iv + 1) < t) iv++; }
             cur = iv;
-            cta = T(iv); ctb = T(iv + 1);
-            if (sc) {
-                civ = iv;
-#pragma unroll
-                for (int j = 0; j < D; j++) sc[j * stride] = a.fu[((int64_t)iv * D + j) * a.N + i];
-#pragma unroll
-                for (int s = 0; s < 7; s++)
-#pragma unroll
-                    for (int j = 0; j < D; j++) sc[(D + s * D + j) * stride] = a.fk[(((int64_t)iv * 7 + s) * D + j) * a.N + i];
-            }
-        }
-        const double ta = cta, h = ctb - ta;
-        const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
-        double w[7];
-        t5_weights(a, th, w);
-        if (sc) {
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int s = 0; s < 7; s++) acc += w[s] * sc[(D + s * D + j) * stride];
-                y[j] = sc[j * stride] + h * acc;
-            }
-        } else {
-            const int iv = cur;
+            const double ta = T(iv), h = T(iv + 1) - ta;
+            const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
+            double w[7];
+            t5_weights(a, th, w);
 #pragma unroll
             for (int j = 0; j < D; j++) {
                 double acc = 0.0;
@@ -116,6 +108,55 @@ struct T5Dense {
                 for (int s = 0; s < 7; s++) acc += w[s] * a.fk[(((int64_t)iv * 7 + s) * D + j) * a.N + i];
                 y[j] = a.fu[((int64_t)iv * D + j) * a.N + i] + h * acc;
             }
+            return;
+        }
+        if (!(civ >= 0 && holds(civ, cta, ctb, t, right))) {
+            bool got = false;
+            if (aiv >= 0) {                               // the interval below was requested when this one was entered
+                cp_async_wait_all();
+                const double ata = sc[((cb ^ 1) * REC + 8 * D) * stride];
+                if (holds(aiv, ata, cta, t, right)) { cb ^= 1; civ = aiv; ctb = cta; cta = ata; cur = civ; got = true; }
+            }
+            if (!got) {
+                // cursor instead of a bisection over the knots: the adjoint solve visits the forward solution monotonically
+                int iv = cur < n - 1 ? cur : n - 1;
+                if (iv < 0) iv = 0;
+                if (right) { while (iv > 0 && T(iv) > t) iv--; while (iv < n - 1 && T(iv + 1) <= t) iv++; }
+                else { while (iv > 0 && T(iv) >= t) iv--; while (iv < n - 1 && T(iv + 1) < t) iv++; }
+                cur = iv; civ = iv;
+                cta = T(iv); ctb = T(iv + 1);
+                double* b = sc + cb * REC * stride;
+#pragma unroll
+                for (int j = 0; j < D; j++) b[j * stride] = a.fu[((int64_t)iv * D + j) * a.N + i];
+#pragma unroll
+                for (int s = 0; s < 7; s++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) b[(D + s * D + j) * stride] = a.fk[(((int64_t)iv * 7 + s) * D + j) * a.N + i];
+            }
+            aiv = civ - 1;
+            if (aiv >= 0) {                               // start fetching the interval below into the other buffer
+                double* b = sc + (cb ^ 1) * REC * stride;
+#pragma unroll
+                for (int j = 0; j < D; j++) cp_async8(b + j * stride, a.fu + ((int64_t)aiv * D + j) * a.N + i);
+#pragma unroll
+                for (int s = 0; s < 7; s++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) cp_async8(b + (D + s * D + j) * stride, a.fk + (((int64_t)aiv * 7 + s) * D + j) * a.N + i);
+                cp_async8(b + 8 * D * stride, a.ft + (int64_t)aiv * a.N + i);
+                cp_async_commit();
+            }
+        }
+        const double* b = sc + cb * REC * stride;
+        const double ta = cta, h = ctb - ta;
+        const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
+        double w[7];
+        t5_weights(a, th, w);
+#pragma unroll
+        for (int j = 0; j < D; j++) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 7; s++) acc += w[s] * b[(D + s * D + j) * stride];
+            y[j] = b[j * stride] + h * acc;
         }
     }
 };
@@ -350,7 +391,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         for (int q = 0; q < P; q++) p0[q] = p[q];
         t5_event_params<P>(a, a.nev, p0, p);
     }
-    extern __shared__ double s_t5_dense[];       // [8 D][blockDim.x]: this thread's cached forward interval
+    extern __shared__ double s_t5_dense[];       // [2][8 D + 1][blockDim.x]: this thread's current forward interval and the one below it
     T5Dense<D> sol{a, i, a.fn[i]};
     sol.cur = sol.n - 1;
     sol.sc = s_t5_dense + threadIdx.x; sol.stride = blockDim.x;

@@ -10,7 +10,7 @@ u0 = np.repeat(np.array([[1.0], [0.0], [0.0]]), N, 1)
 p = np.array([0.04, 3e7, 1e4])[:, None] * np.exp(0.05 * rng.standard_normal((3, N)))
 kw = dict(abstol=1e-8, reltol=1e-8, quad_abstol=1e-10, quad_reltol=1e-10)
 eng = b.DeviceEnsemble("robertson", "quadrature", "rosenbrock23", N, saveat, (0.0, T), 0.0, shared_p=False, on_device=True,
-                       cost=b.AffineCost(1.0, 0.0), max_steps=8192, **kw)
+                       cost=b.AffineCost(1.0, 0.0), max_steps=8192, block_threads=int(os.environ.get("BLOCK", "0")), **kw)
 u0d = torch.tensor(u0, device="cuda"); pd = torch.tensor(p, device="cuda")
 du0 = torch.empty_like(u0d); dp = torch.empty_like(pd)
 for _ in range(2):
