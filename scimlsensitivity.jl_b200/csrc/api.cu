@@ -304,7 +304,10 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         CREATE_TRY(cudaMalloc(&h->d_fwd_saveat, (size_t)(cfg->K > 0 ? cfg->K : 1) * e));
         if (cfg->K > 0) CREATE_TRY(cudaMemcpy(h->d_fwd_saveat, cfg->saveat, (size_t)cfg->K * e, cudaMemcpyHostToDevice));
         h->qpartials_blocks = (size_t)h->qgrid + 1;                              // quadrature kernel: persistent grid
-        CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpartials_blocks > (size_t)h->grid ? h->qpartials_blocks : (size_t)h->grid) * P * sizeof(double)));
+        {   // block partials of the dG/dp reduction: the reverse kernels may run with blocks as small as one warp (disp_t5a.inc)
+            const size_t gmax = (size_t)((cfg->N + 31) / 32);
+            CREATE_TRY(cudaMalloc(&h->d_partials, (h->qpartials_blocks > gmax ? h->qpartials_blocks : gmax) * P * sizeof(double)));
+        }
         CREATE_TRY(cudaMalloc(&h->d_ticket, sizeof(unsigned int)));
         CREATE_TRY(cudaMemset(h->d_ticket, 0, sizeof(unsigned int)));
         if (!cfg->buffers_on_device) {

@@ -75,6 +75,7 @@ struct Handle {
     bool cc_on = false; int cc_idx = 0, cc_dir = 0, cc_pcomp = -1, cc_pparam = 0, cc_maxev = 0;
     double cc_level = 0, cc_psign = 1, cc_scale[4] = {1, 1, 1, 1}, cc_shift[4] = {0, 0, 0, 0};
     double* d_cc_t = nullptr; int32_t* d_cc_n = nullptr;
+    int rev_block = 0; const void* rev_block_kernel = nullptr;      // adaptive Tsit5 reverse kernel: block size chosen per instantiation (disp_t5a.inc)
     bool have_forward = false;
     bool noise_valid = false;
     int64_t launches = 0;
