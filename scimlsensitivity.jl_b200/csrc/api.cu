@@ -183,8 +183,9 @@ int ensure_quad_buffers(Handle* h) {
     const b200adj_cfg& c = h->cfg;
     const size_t N = (size_t)c.N, MS = (size_t)h->maxs, e = sizeof(double);
     const size_t RWP = quad_pad(3 + (1 + h->nk) * c.d), FWP = quad_pad((1 + h->nk) * c.d + 3);
+    const bool t5a = h->nk == 7;      // adaptive Tsit5: the forward dense solution is member-major from the start (allocated at create)
     if (cudaMalloc(&h->r_rrec, N * MS * RWP * e) != cudaSuccess || cudaMalloc(&h->r_rend, N * MS * e) != cudaSuccess ||
-        cudaMalloc(&h->r_ftT, N * (MS + 1) * e) != cudaSuccess || cudaMalloc(&h->r_frecT, N * MS * FWP * e) != cudaSuccess ||
+        (!t5a && (cudaMalloc(&h->r_ftT, N * (MS + 1) * e) != cudaSuccess || cudaMalloc(&h->r_frecT, N * MS * FWP * e) != cudaSuccess)) ||
         cudaMalloc(&h->r_qseg, quad_seg_doubles(c.P, h->maxseg, h->qgrid) * e) != cudaSuccess ||
         cudaMalloc(&h->r_qkey, (size_t)h->qgrid * QUAD_WARPS * h->maxseg * e) != cudaSuccess) {
         cudaGetLastError();
@@ -287,9 +288,14 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         CREATE_TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
         h->stream = h->own_stream;
         const size_t N = (size_t)cfg->N, MS = (size_t)h->maxs, e = sizeof(double);
-        CREATE_TRY(cudaMalloc(&h->r_ft, (MS + 1) * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_fu, (MS + 1) * d * N * e));
-        CREATE_TRY(cudaMalloc(&h->r_fk, MS * h->nk * d * N * e));
+        if (t5a) {      // member-major records (u_n, k1..k7, t_n, h, 1/h, t_{n+1}) and knots: tsit5_adaptive.cuh
+            CREATE_TRY(cudaMalloc(&h->r_ftT, N * (MS + 1) * e));
+            CREATE_TRY(cudaMalloc(&h->r_frecT, N * (MS + 1) * (size_t)(8 * d + 4) * e));
+        } else {
+            CREATE_TRY(cudaMalloc(&h->r_ft, (MS + 1) * N * e));
+            CREATE_TRY(cudaMalloc(&h->r_fu, (MS + 1) * d * N * e));
+            CREATE_TRY(cudaMalloc(&h->r_fk, MS * h->nk * d * N * e));
+        }
         CREATE_TRY(cudaMalloc(&h->r_fn, N * sizeof(int32_t)));
         CREATE_TRY(cudaMalloc(&h->r_rn, N * sizeof(int32_t)));
         h->maxseg = 2 * h->maxs;                                              // quadgk segment capacity per data interval (multiple of 32)

@@ -20,9 +20,12 @@ struct T5aArgs {
     const double* u0; const double* p; const double* saveat; const double* dLdu;
     double* saved; int32_t* status;
     double* du0; double* dp_members; double* partials; double* dp; unsigned int* ticket;
-    double* ft; double* fu; double* fk; int32_t* fn;              // forward dense: [MAXS+1][N], [MAXS+1][D][N], [MAXS][7][D][N], [N]
+    double* ft; double* fu; double* fk; int32_t* fn;              // fn[N]: accepted forward steps per member (ft / fu / fk: unused by these kernels)
     double* rrec; double* rend; int32_t* rn;                      // reverse dense (Quadrature), member-major: [N][MAXS][RWP] = (t, h, z[D], k[7][D]), [N][MAXS] = t + h
-    double* ftT; double* frecT;                                   // member-major copy of the forward dense solution: [N][MAXS+1], [N][MAXS][FWP] = (u[D], k[7][D])
+    // THE forward dense solution, member-major: every member has its own step sequence, so its records are contiguous and move
+    // as ONE bulk copy each (TMA): knots ftT[N][MAXS+1]; records frecT[N][MAXS+1][8 D + 4] = (u_n[D], k1..k7[D], t_n, h, 1/h,
+    // t_{n+1}); record fn[i] (the last) holds the final state and time only
+    double* ftT; double* frecT;
     double* qseg; double* qkey; int32_t maxseg;
     int64_t N; int32_t K; int32_t maxs;
     double t0, t1, dt0, abstol, reltol, quad_abstol, quad_reltol, cost_a[4], cost_b[4];
@@ -62,59 +65,56 @@ __device__ __forceinline__ void t5_event_params(const T5aArgs& a, int upto, cons
     }
 }
 
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int D> __host__ __device__ constexpr int t5_rec() { return 8 * D + 4; }      // doubles per record: a multiple of 4 (bulk copies move multiples of 16 B)
+// pitch of the per-thread record buffers in shared memory: 16 B aligned (bulk-copy destination) with pitch / 2 odd, so that the
+// 16 lanes of a half warp reading the same element hit 8 distinct 8-byte banks (2-way conflict; the unpadded pitch gives 4-way)
+template <int D> __host__ __device__ constexpr int t5_pitch() { return 8 * D + 6; }
 
-// forward dense solution of one member.  The reverse solve visits it monotonically (downwards) and evaluates it 6-9 times per
-// step, mostly inside ONE forward interval.  The interval's record (u_n, k1..k7, t_n: 8 D + 1 doubles) is kept in the thread's
-// own shared-memory column, double buffered: when a thread enters interval iv it starts an asynchronous copy (cp.async, 8 B per
-// element, no register staging) of interval iv - 1 into the other buffer; by the time the solve crosses the knot the record is
-// there and the buffers swap.  Global memory is waited for only at the start and after a jump over several intervals.
-// Why: every lane of a warp has its own step sequence, so with plain loads SOME lane misses on nearly every lookup and the
-// whole warp pays a dependent global round trip per stage (C1-ensemble profile before: 20.5 GB DRAM reads, long_scoreboard
-// 12.8, 37 k cycles per step and warp).
+// bulk-copy helpers beside those of ode_tsit5.cuh (SASS: UBLKCP.S.G / UBLKCP.G.S)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_1d(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Forward dense solution of one member, as the reverse solve sees it.  The solve runs downwards and evaluates the interpolant
+// 6-9 times per step, mostly inside ONE forward interval.  Every lane of a warp has its own step sequence, so per-element
+// loads would touch one cache line per lane and instruction (the first version of this kernel was bound by exactly that: the
+// L1 tag stage, 37 k cycles per step and warp on the C1 ensemble).  Instead each THREAD owns two record buffers in shared
+// memory and one mbarrier: entering interval iv it asks the TMA engine for the record of interval iv - 1 (one bulk copy of
+// 8 D + 4 doubles); when the solve crosses the knot the record is there and the buffers swap.  Global memory is waited for
+// only at the start and after a jump over several intervals.
 template <int D>
 struct T5Dense {
-    static constexpr int REC = 8 * D + 1;                // u[D], k[7][D], t_n
-    const T5aArgs& a; int64_t i; int n;
+    static constexpr int REC = t5_rec<D>();
+    const T5aArgs& a;
+    const double* recs; const double* knots; int n;      // this member's records [n + 1][REC] and knots [n + 1]
+    double* sc; int bs; uint64_t* bar;                   // this thread's two record buffers (sc, sc + bs) and its mbarrier (shared memory)
     mutable int cur = 0;
-    double* sc = nullptr; int stride = 0;                // interval cache: [2][REC][stride] (null: every lookup reads global memory)
-    mutable int cb = 0, civ = -1, aiv = -1;              // current buffer, its interval, the interval (being) prefetched into the other one
+    mutable int cb = 0, civ = -1, aiv = -1;              // current buffer, its interval, the interval requested into the other one
+    mutable uint32_t ph = 0;                             // parity of the mbarrier phase the next wait completes
     mutable double cta = 0.0, ctb = 0.0;
-    __device__ __forceinline__ double T(int idx) const { return a.ft[(int64_t)idx * a.N + i]; }
+    __device__ __forceinline__ double T(int idx) const { return knots[idx]; }
+    __device__ __forceinline__ const double* record(int idx) const { return recs + (int64_t)idx * REC; }
     __device__ __forceinline__ bool holds(int iv, double ta, double tb, double t, bool right) const {
         // interval iv = [ta, tb] is where the cursor search stops at once
         return right ? ((iv == 0 || ta <= t) && (iv == n - 1 || tb > t)) : ((iv == 0 || ta < t) && (iv == n - 1 || tb >= t));
     }
+    __device__ __forceinline__ void request(int buf, int iv) const {
+        // (no proxy fence: the buffer was only READ through the generic proxy, and those reads have returned their values --
+        //  the same consumer-release -> producer-load order TMA pipelines rely on)
+        mbar_expect_tx(bar, (uint32_t)(REC * sizeof(double)));
+        tma_load_1d(sc + buf * bs, record(iv), (uint32_t)(REC * sizeof(double)), bar);
+    }
+    __device__ __forceinline__ void arrived() const { mbar_wait(bar, ph); ph ^= 1u; }
     __device__ __forceinline__ void eval(double t, bool right, double* y) const {
-        if (!sc) {                                        // uncached variant (forward-side callers)
-            int iv = cur < n - 1 ? cur : n - 1;
-            if (iv < 0) iv = 0;
-            if (right) { while (iv > 0 && T(iv) > t) iv--; while (iv < n - 1 && T(iv + 1) <= t) iv++; }
-            else { while (iv > 0 && T(iv) >= t) iv--; while (iv < n - 1 && T(iv + 1) < t) iv++; }
-            cur = iv;
-            const double ta = T(iv), h = T(iv + 1) - ta;
-            const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
-            double w[7];
-            t5_weights(a, th, w);
-#pragma unroll
-            for (int j = 0; j < D; j++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int s = 0; s < 7; s++) acc += w[s] * a.fk[(((int64_t)iv * 7 + s) * D + j) * a.N + i];
-                y[j] = a.fu[((int64_t)iv * D + j) * a.N + i] + h * acc;
-            }
-            return;
-        }
         if (!(civ >= 0 && holds(civ, cta, ctb, t, right))) {
             bool got = false;
             if (aiv >= 0) {                               // the interval below was requested when this one was entered
-                cp_async_wait_all();
-                const double ata = sc[((cb ^ 1) * REC + 8 * D) * stride];
+                arrived();
+                const double ata = sc[(cb ^ 1) * bs + 8 * D];
                 if (holds(aiv, ata, cta, t, right)) { cb ^= 1; civ = aiv; ctb = cta; cta = ata; cur = civ; got = true; }
             }
             if (!got) {
@@ -124,29 +124,14 @@ struct T5Dense {
                 if (right) { while (iv > 0 && T(iv) > t) iv--; while (iv < n - 1 && T(iv + 1) <= t) iv++; }
                 else { while (iv > 0 && T(iv) >= t) iv--; while (iv < n - 1 && T(iv + 1) < t) iv++; }
                 cur = iv; civ = iv;
-                cta = T(iv); ctb = T(iv + 1);
-                double* b = sc + cb * REC * stride;
-#pragma unroll
-                for (int j = 0; j < D; j++) b[j * stride] = a.fu[((int64_t)iv * D + j) * a.N + i];
-#pragma unroll
-                for (int s = 0; s < 7; s++)
-#pragma unroll
-                    for (int j = 0; j < D; j++) b[(D + s * D + j) * stride] = a.fk[(((int64_t)iv * 7 + s) * D + j) * a.N + i];
+                request(cb, iv);
+                arrived();
+                cta = sc[cb * bs + 8 * D]; ctb = sc[cb * bs + 8 * D + 3];
             }
             aiv = civ - 1;
-            if (aiv >= 0) {                               // start fetching the interval below into the other buffer
-                double* b = sc + (cb ^ 1) * REC * stride;
-#pragma unroll
-                for (int j = 0; j < D; j++) cp_async8(b + j * stride, a.fu + ((int64_t)aiv * D + j) * a.N + i);
-#pragma unroll
-                for (int s = 0; s < 7; s++)
-#pragma unroll
-                    for (int j = 0; j < D; j++) cp_async8(b + (D + s * D + j) * stride, a.fk + (((int64_t)aiv * 7 + s) * D + j) * a.N + i);
-                cp_async8(b + 8 * D * stride, a.ft + (int64_t)aiv * a.N + i);
-                cp_async_commit();
-            }
+            if (aiv >= 0) request(cb ^ 1, aiv);
         }
-        const double* b = sc + cb * REC * stride;
+        const double* b = sc + cb * bs;
         const double ta = cta, h = ctb - ta;
         const double th = (h == 0.0) ? 1.0 : (t - ta) / h;
         double w[7];
@@ -155,8 +140,8 @@ struct T5Dense {
         for (int j = 0; j < D; j++) {
             double acc = 0.0;
 #pragma unroll
-            for (int s = 0; s < 7; s++) acc += w[s] * b[(D + s * D + j) * stride];
-            y[j] = b[j * stride] + h * acc;
+            for (int s = 0; s < 7; s++) acc += w[s] * b[D + s * D + j];
+            y[j] = b[j] + h * acc;
         }
     }
 };
@@ -226,10 +211,15 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
     double p[P];
 #pragma unroll
     for (int q = 0; q < P; q++) p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
+    constexpr int REC = t5_rec<D>();
+    extern __shared__ __align__(16) double s_t5_stage[];     // [blockDim.x][t5_pitch]: the record of the step this thread has just accepted
+    double* st = s_t5_stage + (size_t)threadIdx.x * t5_pitch<D>();
+    double* recs = a.frecT + (int64_t)i * (a.maxs + 1) * REC;
+    double* knots = a.ftT + (int64_t)i * (a.maxs + 1);
     double u[D], un[D], k[7][D];
 #pragma unroll
-    for (int j = 0; j < D; j++) { u[j] = a.u0[(int64_t)j * N + i]; a.fu[(int64_t)j * N + i] = u[j]; }
-    a.ft[i] = a.t0;
+    for (int j = 0; j < D; j++) u[j] = a.u0[(int64_t)j * N + i];
+    knots[0] = a.t0;
     auto rhs = [&](double, const double* x, double* dx) { Fam::f(x, p, dx); };
     Fam::f(u, p, k[0]);
     double t = a.t0, h = a.dt0 > 0 ? a.dt0 : 1e-3 * (a.t1 - a.t0), qold = 1e-4;
@@ -322,10 +312,20 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                 }
                 ksave++;
             }
+            {   // the step's record (start state, k1..k7, knots): staged in shared memory, then ONE bulk store to this member's row
+                tma_store_wait_read();                                 // the previous record has left the staging buffer
 #pragma unroll
-            for (int s = 0; s < 7; s++)
+                for (int j = 0; j < D; j++) st[j] = u[j];
 #pragma unroll
-                for (int j = 0; j < D; j++) a.fk[(((int64_t)n * 7 + s) * D + j) * N + i] = k[s][j];
+                for (int s = 0; s < 7; s++)
+#pragma unroll
+                    for (int j = 0; j < D; j++) st[D + s * D + j] = k[s][j];
+                const double hrec = tn - t;
+                st[8 * D] = t; st[8 * D + 1] = hrec; st[8 * D + 2] = 1.0 / hrec; st[8 * D + 3] = tn;
+                fence_proxy_async_smem();
+                tma_store_1d(recs + (int64_t)n * REC, st, (uint32_t)(REC * sizeof(double)));
+                tma_store_commit();
+            }
             if (at_event) {
                 // affect!: the next step starts from the post-event state; k7 = f(u^-) stays with the step just stored
                 if (CC) {
@@ -351,8 +351,8 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                 }
             }
 #pragma unroll
-            for (int j = 0; j < D; j++) { a.fu[((int64_t)(n + 1) * D + j) * N + i] = un[j]; u[j] = un[j]; k[0][j] = k[6][j]; }
-            t = tn; a.ft[(int64_t)(n + 1) * N + i] = t;
+            for (int j = 0; j < D; j++) { u[j] = un[j]; k[0][j] = k[6][j]; }
+            t = tn; knots[n + 1] = t;
             n++;
             qold = fmax(EEst, 1e-4);
             h = fixed ? a.dt0 : h / q;            // constant step: back to dt after a step clipped at an event (dtcache)
@@ -361,6 +361,18 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
         }
     }
     a.fn[i] = n;
+    {   // the terminal record: final state and time
+        tma_store_wait_read();
+#pragma unroll
+        for (int j = 0; j < D; j++) st[j] = u[j];
+#pragma unroll
+        for (int c = D; c < REC; c++) st[c] = 0.0;
+        st[8 * D] = t; st[8 * D + 3] = t;
+        fence_proxy_async_smem();
+        tma_store_1d(recs + (int64_t)n * REC, st, (uint32_t)(REC * sizeof(double)));
+        tma_store_commit();
+        tma_store_wait_all();
+    }
     if (CC) a.cc_n[i] = nfound;
     bool ok = true;
 #pragma unroll
@@ -394,10 +406,15 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
         for (int q = 0; q < P; q++) p0[q] = p[q];
         t5_event_params<P>(a, a.nev, p0, p);
     }
-    extern __shared__ double s_t5_dense[];       // [2][8 D + 1][blockDim.x]: this thread's current forward interval and the one below it
-    T5Dense<D> sol{a, i, a.fn[i]};
+    constexpr int REC = t5_rec<D>();
+    extern __shared__ __align__(16) double s_t5_dense[];     // [2][blockDim.x][t5_pitch] record buffers, then [blockDim.x] mbarriers
+    const int bufstride = (int)blockDim.x * t5_pitch<D>();
+    uint64_t* my_bar = reinterpret_cast<uint64_t*>(s_t5_dense + (size_t)2 * bufstride) + threadIdx.x;
+    mbar_init(my_bar, 1);
+    mbar_fence_init();
+    T5Dense<D> sol{a, a.frecT + (int64_t)i * (a.maxs + 1) * REC, a.ftT + (int64_t)i * (a.maxs + 1), a.fn[i],
+                   s_t5_dense + (size_t)threadIdx.x * t5_pitch<D>(), bufstride, my_bar};
     sol.cur = sol.n - 1;
-    sol.sc = s_t5_dense + threadIdx.x; sol.stride = blockDim.x;
     double z[L], zn[L], k[7][L];
 #pragma unroll
     for (int c = 0; c < L; c++) z[c] = 0.0;
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
     const bool ckpt_on = !(a.flags & 2u), every = (a.flags & 4u);
     if (SA == SA_BACKSOLVE) {
 #pragma unroll
-        for (int j = 0; j < D; j++) z[YO + j] = a.fu[((int64_t)sol.n * D + j) * N + i];     // y(T) = sol.u[end]
+        for (int j = 0; j < D; j++) z[YO + j] = sol.record(sol.n)[j];     // y(T) = sol.u[end]
     }
     // Backsolve checkpoint callback (runs before the loss jump, CallbackSet order): y <- sol(t) at a checkpoint
     auto ckpt_if_at = [&](double tt) {
@@ -443,7 +460,7 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
             while (ck >= 0 && sol.T(ck) > tt + tol) ck--;
             if (ck >= 0 && fabs(sol.T(ck) - tt) <= tol) {
 #pragma unroll
-                for (int j = 0; j < D; j++) z[YO + j] = a.fu[((int64_t)ck * D + j) * N + i];
+                for (int j = 0; j < D; j++) z[YO + j] = sol.record(ck)[j];
                 fsal_ok = false;
             }
         } else if (cur >= 0 && fabs(a.saveat[cur] - tt) <= tol) {
@@ -693,7 +710,7 @@ __global__ void __launch_bounds__(QUAD_WARPS * 32) t5a_quadrature_kernel(const _
 #pragma unroll
     for (int q = 0; q < P; q++) acc[q] = 0.0;
     auto make = [&](int64_t i) {
-        T5aQuadCtx<Fam, D, P> c{a, a.ftT + (int64_t)i * (a.maxs + 1), a.frecT + (int64_t)i * a.maxs * quad_pad(8 * D + 3),
+        T5aQuadCtx<Fam, D, P> c{a, a.ftT + (int64_t)i * (a.maxs + 1), a.frecT + (int64_t)i * (a.maxs + 1) * t5_rec<D>(),
                                 a.rrec + (int64_t)i * a.maxs * quad_pad(3 + 8 * D), a.rend + (int64_t)i * a.maxs, a.fn[i], a.rn[i], {}};
 #pragma unroll
         for (int q = 0; q < P; q++) c.p[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
