@@ -386,9 +386,9 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
 // checkpoints (every forward knot = sol.t, the direct-interface default, or the save times), which are tstops of the reverse
 // solve (src/backsolve_adjoint.jl:32-61, :523-546; src/sensitivity_interface.jl:433, :484-486; the reference's own
 // Lorenz check, test/Core3/adjoint.jl:1157-1241)
-// (A register cap -- __maxnreg__(144), 14 warps per SM, the 65 536-member C1 shard in one wave -- was measured and rejected:
-// 10.2 ms against 8.4 ms uncapped.  The kernel is not bound by resident warps but by the L1 tag stage: every lane reads its own
-// member's record, one cache line per lane and instruction)
+// (A register cap -- __maxnreg__(144): 14 warps per SM, the 65 536-member C1 shard in ONE wave instead of two -- was measured
+// twice and rejected: 8.9 ms against 7.25 ms uncapped.  Block sizes 32 / 64 / 128 (8 to 11 resident warps per SM) all give
+// 7.25 ms: the time is two rounds of a latency-bound per-warp chain)
 template <class Fam, int SA, bool SHARED_P, int COST, bool CC = false>
 __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant__ T5aArgs a) {
     constexpr int D = Fam::D, P = Fam::P, L = (SA == SA_INTERP) ? D + P : (SA == SA_BACKSOLVE ? 2 * D + P : D);
