@@ -273,6 +273,24 @@ def spec_c5():
                                                                "in-kernel time loop: frac may exceed 1; the compulsory stream is 16 B per member-step"})
 
 
+def spec_c1():
+    """BASELINE configs[0] (LV, InterpolatingAdjoint, ADAPTIVE Tsit5) as an ensemble: every member its own PI-controlled steps."""
+    T = 10.0
+    p = np.array([1.5, 1.0, 3.0, 1.0])
+    tol = dict(abstol=1e-8, reltol=1e-8)
+    REC = 8 * 2 + 4       # doubles per member-major record (u_n, k1..k7, t_n, h, 1/h, t_{n+1}): written once, read once
+    return dict(name="C1-ensemble Lotka-Volterra d=2 P=4 shared p, InterpolatingAdjoint, adaptive Tsit5 (PI controller) tol 1e-8, T=10, saveat=0.1, loss=sum(sol)",
+                family="lv", sensealg="interpolating", stepper="tsit5_adaptive", T=T, dt=0.0, saveat=np.linspace(0.0, T, 101), cost=(0.0, 1.0),
+                dtype="f64", shared_p=True, okw=dict(tol), ekw=dict(max_steps=512, **tol), tol=1e-7,
+                inputs=lambda n, off: (np.exp(0.2 * np.random.default_rng(3000 + off).standard_normal((2, n))), p), parity_members=256,
+                # compulsory stream: one record per accepted forward step, read once by the reverse solve (TMA bulk copies)
+                roofline=lambda n, S, rev_s, hbm, tf: {"bound": "hbm", "kernel": "t5a_reverse_kernel<LotkaVolterra,INTERP>", "achieved": REC * 8.0 * n * S / rev_s / 1e9,
+                                                       "peak": hbm, "unit": "GB/s", "frac": REC * 8.0 * n * S / rev_s / 1e9 / hbm,
+                                                       "algorithmic_bytes_per_launch": REC * 8.0 * n * S, "mean_forward_steps_per_member": S,
+                                                       "note": "latency bound, not bandwidth bound: every member is a serial chain of dependent fp64 work with its own "
+                                                               "step sequence (DESIGN.md 4.4); the bytes are the compulsory record stream"})
+
+
 def spec_c2(T=None):
     W = WORKLOAD
     T = T or W["T"]
@@ -378,11 +396,12 @@ def secondary_leg(spec, n_total, rank, world, local, steps, warmup, barrier, thr
     l0 = sh.eng.handle.launch_count
     ms, fwd, rev = timed(sh, steps, warmup, barrier, world, dev)
     launches = sh.eng.handle.launch_count - l0
+    S_adaptive = float(sh.eng.step_counts()[0].double().mean().cpu()) if spec["dt"] <= 0 else None      # accepted forward steps per member
     sh.close()
     par = parity_pass(spec, rank, world, local, threads) if with_parity else None
     if rank != 0:
         return None
-    S = int(round(spec["T"] / spec["dt"]))
+    S = int(round(spec["T"] / spec["dt"])) if spec["dt"] > 0 else S_adaptive
     out = {"workload": spec["name"], "members_total": n_local * world, "members_per_gpu": n_local, "dtype": spec["dtype"],
            "value": n_local * world / (ms * 1e-3), "unit": "trajectories/s", "ms_per_step": ms,
            "phases_ms": {"forward": fwd, "reverse_incl_allreduce": rev}, "gpu_launches_per_step": launches / max(1, steps + warmup),
@@ -524,6 +543,7 @@ def run_ours(args):
         secondary["c4"] = secondary_leg(spec_c4(), 4096, rank, world, local, sec_steps, sec_warm, barrier, threads)
         secondary["c4_full"] = secondary_leg(spec_c4(), 18944 * world, rank, world, local, sec_steps, sec_warm, barrier, threads, with_parity=False)
         secondary["c5"] = secondary_leg(spec_c5(), 131072, rank, world, local, sec_steps, sec_warm, barrier, threads)
+        secondary["c1_ensemble"] = secondary_leg(spec_c1(), 65536 * world, rank, world, local, max(3, min(sec_steps, 5)), 2, barrier, threads)
 
     if rank == 0:
         hbm, tf, peak_src = peaks()
