@@ -35,8 +35,10 @@ enum {
     B200ADJ_FAM_SDE_LV = 3,     /* LV drift + diag noise g_i = p[4+i] u_i, d=2 P=6 m=2 (Core1/...:737-760)      */
     B200ADJ_FAM_MLP = 4,        /* 2 -> H -> H -> 2 tanh MLP (docs/src/Benchmark.md:49-52), P = H*H+6H+2        */
     B200ADJ_FAM_SDE_LINEAR = 5, /* du_i = p0 u_i dt + p1 u_i dW_i, any d (test/SDE1/sde_stratonovich.jl:22-31)  */
-    B200ADJ_FAM_BALL = 6        /* bouncing ball x' = v, v' = -p0, p = [gravity, restitution], d=2 P=2
+    B200ADJ_FAM_BALL = 6,       /* bouncing ball x' = v, v' = -p0, p = [gravity, restitution], d=2 P=2
                                    (docs/src/examples/hybrid_jump/bouncing_ball.md; adaptive Tsit5 only)          */
+    B200ADJ_FAM_RELAX = 7       /* u' = p0 - u, p = [steady state, injected amount], d=1 P=2
+                                   (test/Callbacks2/continuous_callbacks.jl:317-324; adaptive Tsit5 only)         */
 };
 /* User RHS families (replaces the user `ODEFunction(f; vjp, vjp_p, jac, paramjac)` seam of
  * src/derivative_wrappers.jl:284-359, test/Core3/user_vjp.jl:14-38): a family PLUG-IN is a shared library built from a
@@ -191,6 +193,13 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
 int32_t b200adj_set_continuous_callback(void* handle, int32_t enabled, int32_t idx, double level, int32_t direction,
                                         const double* scale, const double* shift, int32_t pcomp, int32_t pparam, double psign,
                                         int32_t max_events);
+/* Parameter-dependent condition and additive parameter affect of the callback above (the reference's
+ * test/Callbacks2/continuous_callbacks.jl:317-345: condition(u,t,integrator) = u[1] - 3//4 * integrator.p[1],
+ * affect!(integrator) = integrator.u[1] += integrator.p[2]):  condition = u[idx] - (level + lcoef * p[lparam])  (lparam < 0:
+ * none) and, after the affine part of the affect, u[acomp] += acoef * p[aparam]  (acomp < 0: none).  Reverse pass, with
+ * w = (A f(u-) - f(u+))'lam+:  dG/dp[lparam] += lcoef * w / f(u-)[idx]  (the event time moves with the level) and
+ * dG/dp[aparam] += acoef * lam+[acomp].  Call after b200adj_set_continuous_callback (which resets both to none). */
+int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, double lcoef, int32_t acomp, int32_t aparam, double acoef);
 /* event lists found by the last forward pass: counts[N] (host, may be NULL), times[max_events][N] (host, may be NULL) */
 int32_t b200adj_event_times(void* handle, int32_t* counts, double* times);
 

@@ -19,7 +19,7 @@ import ChainRulesCore: NoTangent
 const libb200adj = get(ENV, "B200ADJ_LIB", "libb200adj.so")      # where the shared library lives (not a behaviour switch)
 
 # ---- enums / cfg: field-for-field mirror of b200adj_cfg (176 bytes; checked against b200adj_sizeof_cfg) ----
-@enum Family::Int32 FAM_LV = 0 FAM_LORENZ = 1 FAM_ROBERTSON = 2 FAM_SDE_LV = 3 FAM_MLP = 4 FAM_SDE_LINEAR = 5 FAM_BALL = 6
+@enum Family::Int32 FAM_LV = 0 FAM_LORENZ = 1 FAM_ROBERTSON = 2 FAM_SDE_LV = 3 FAM_MLP = 4 FAM_SDE_LINEAR = 5 FAM_BALL = 6 FAM_RELAX = 7
 const SA_CODE = Dict(InterpolatingAdjoint => Int32(0), GaussAdjoint => Int32(1), QuadratureAdjoint => Int32(2),
     BacksolveAdjoint => Int32(3), GaussKronrodAdjoint => Int32(4))
 const ST_TSIT5_FIXED, ST_ROSENBROCK23, ST_EM, ST_EULER_HEUN, ST_TSIT5_ADAPTIVE = Int32(0), Int32(1), Int32(2), Int32(3), Int32(4)
@@ -50,14 +50,19 @@ The state-dependent callback family of the device path: `ContinuousCallback(cond
 `affect!`: `u .= scale .* u .+ shift`, then `u[pcomp] = psign * p[pparam] * u[pcomp]` when `pcomp > 0` (1-based here, 0-based at the
 ABI).  The bouncing ball of docs/src/examples/hybrid_jump/bouncing_ball.md is `B200Crossing(1, 0.0, -1; pcomp = 2, pparam = 2,
 psign = -1.0)`.  Adaptive Tsit5; every ensemble member finds its own event times on the device.
+Parameter-dependent level and additive parameter affect (`lparam`, `lcoef`, `acomp`, `aparam`, `acoef`; 1-based, 0 = none):
+`condition = u[1] - 3//4 * p[1]; affect! = u[1] += p[2]` of test/Callbacks2/continuous_callbacks.jl:317-345 is
+`B200Crossing(1, 0.0, 0; lparam = 1, lcoef = 0.75, acomp = 1, aparam = 2, acoef = 1.0)`.
 """
 struct B200Crossing
     idx::Int; level::Float64; direction::Int
     scale::Union{Nothing, Vector{Float64}}; shift::Union{Nothing, Vector{Float64}}
     pcomp::Int; pparam::Int; psign::Float64; max_events::Int
+    lparam::Int; lcoef::Float64; acomp::Int; aparam::Int; acoef::Float64
 end
-B200Crossing(idx, level = 0.0, direction = -1; scale = nothing, shift = nothing, pcomp = 0, pparam = 0, psign = 1.0, max_events = 64) =
-    B200Crossing(idx, level, direction, scale, shift, pcomp, pparam, psign, max_events)
+B200Crossing(idx, level = 0.0, direction = -1; scale = nothing, shift = nothing, pcomp = 0, pparam = 0, psign = 1.0, max_events = 64,
+             lparam = 0, lcoef = 0.0, acomp = 0, aparam = 0, acoef = 0.0) =
+    B200Crossing(idx, level, direction, scale, shift, pcomp, pparam, psign, max_events, lparam, lcoef, acomp, aparam, acoef)
 
 struct B200Cfg
     rhs_family::Int32; sensealg::Int32; stepper::Int32; dtype::Int32
@@ -217,6 +222,9 @@ function b200_solve_adjoint(prob, alg, sensealg::B200Adjoint, U::AbstractMatrix{
                 (Ptr{Cvoid}, Int32, Int32, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Int32),
                 s.h.ptr, 1, c.idx - 1, c.level, c.direction, c.scale === nothing ? C_NULL : pointer(c.scale),
                 c.shift === nothing ? C_NULL : pointer(c.shift), c.pcomp - 1, max(c.pparam - 1, 0), c.psign, c.max_events))
+            (c.lparam > 0 || c.acomp > 0) && check(s.h.ptr, ccall((:b200adj_set_continuous_callback_params, libb200adj), Int32,
+                (Ptr{Cvoid}, Int32, Float64, Int32, Int32, Float64),
+                s.h.ptr, c.lparam - 1, c.lcoef, c.acomp - 1, max(c.aparam - 1, 0), c.acoef))
         end
     end
     # forward: every shard on its own host thread (the calls block until the D2H copies are done)

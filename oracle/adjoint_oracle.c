@@ -41,7 +41,7 @@
 #endif
 
 /* ---- enums: values shared (by convention, not by include) with include/b200adj.h ---- */
-enum { FAM_LV = 0, FAM_LORENZ = 1, FAM_ROBERTSON = 2, FAM_SDE_LV = 3, FAM_MLP = 4, FAM_SDE_LINEAR = 5, FAM_BALL = 6 };
+enum { FAM_LV = 0, FAM_LORENZ = 1, FAM_ROBERTSON = 2, FAM_SDE_LV = 3, FAM_MLP = 4, FAM_SDE_LINEAR = 5, FAM_BALL = 6, FAM_RELAX = 7 };
 enum { SA_INTERPOLATING = 0, SA_GAUSS = 1, SA_QUADRATURE = 2, SA_BACKSOLVE = 3, SA_GAUSSKRONROD = 4 };
 enum { ST_TSIT5_FIXED = 0, ST_ROSENBROCK23 = 1, ST_EM = 2, ST_EULER_HEUN = 3, ST_TSIT5_ADAPTIVE = 4 };
 enum { COST_EXPLICIT = 0, COST_AFFINE = 1 };
@@ -83,7 +83,13 @@ typedef struct {
     int32_t cc_on, cc_idx, cc_dir, cc_pcomp, cc_pparam, cc_found;
     double cc_level, cc_psign;
     const double *cc_scale, *cc_shift;
+    /* parameter-dependent condition and additive parameter affect (test/Callbacks2/continuous_callbacks.jl:317-345:
+     * condition u[1] - 3/4 p[1], affect u[1] += p[2]): the level is cc_level + cc_lcoef * p[cc_lparam] (cc_lparam < 0: none)
+     * and u[cc_acomp] += cc_acoef * p[cc_aparam] (cc_acomp < 0: none) after the affine part */
+    int32_t cc_lparam, cc_acomp, cc_aparam, _pad2;
+    double cc_lcoef, cc_acoef;
 } oracle_cfg;
+#define CC_LEVEL(c, p) ((c)->cc_level + ((c)->cc_lparam >= 0 ? (c)->cc_lcoef * (p)[(c)->cc_lparam] : 0.0))
 #define COST_A(c, j) ((c)->cost_av ? (c)->cost_av[j] : (c)->cost_a)
 #define COST_B(c, j) ((c)->cost_bv ? (c)->cost_bv[j] : (c)->cost_b)
 #define CONT_A(c, j) ((c)->cont_av ? (c)->cont_av[j] : (c)->cont_a)
@@ -123,6 +129,17 @@ static void vjp_ball(const double* u, const double* p, double t, const double* l
     (void)t; (void)c; (void)u; (void)p;
     dl[0] = 0.0; dl[1] = l[0];
     if (dg) { dg[0] = -l[1]; dg[1] = 0.0; }
+}
+/* relaxation towards p1 (test/Callbacks2/continuous_callbacks.jl:317-324: f(D,u,p,t) = (D[1] = p[1] - u[1]); p[2] only enters
+ * through the callback's affect u[1] += p[2]) */
+static void f_relax(const double* u, const double* p, double t, double* du, const fam_ctx* c) {
+    (void)t; (void)c;
+    du[0] = p[0] - u[0];
+}
+static void vjp_relax(const double* u, const double* p, double t, const double* l, double* dl, double* dg, const fam_ctx* c) {
+    (void)t; (void)c; (void)u; (void)p;
+    dl[0] = -l[0];
+    if (dg) { dg[0] = l[0]; dg[1] = 0.0; }
 }
 static void f_lorenz(const double* u, const double* p, double t, double* du, const fam_ctx* c) {
     (void)t; (void)c;
@@ -279,6 +296,7 @@ static int family_init(family_t* F, const oracle_cfg* c) {
     case FAM_LV:        F->d = 2; F->P = 4; F->f = f_lv; F->vjp = vjp_lv; break;
     case FAM_LORENZ:    F->d = 3; F->P = 3; F->f = f_lorenz; F->vjp = vjp_lorenz; break;
     case FAM_BALL:      F->d = 2; F->P = 2; F->f = f_ball; F->vjp = vjp_ball; break;
+    case FAM_RELAX:     F->d = 1; F->P = 2; F->f = f_relax; F->vjp = vjp_relax; break;
     case FAM_ROBERTSON: F->d = 3; F->P = 3; F->f = f_rober; F->vjp = vjp_rober; break;
     case FAM_SDE_LV:    F->d = 2; F->P = 6; F->m = 2; F->f = f_sdelv; F->vjp = vjp_sdelv; F->f_ito = fito_sdelv; F->vjp_ito = vjpito_sdelv; break;
     case FAM_MLP:       F->d = 2; F->P = c->P; F->f = f_mlp; F->vjp = vjp_mlp;
@@ -618,6 +636,7 @@ static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const d
     fwd_rhs(t0, u0, k, &c);
     double t = t0, h = dt0 > 0 ? dt0 : 1e-3 * (t1 - t0), qold = 1e-4;
     int n = 0, iters = 0, after_event = 0; const int ci = evc->cc_idx;
+    const double level = CC_LEVEL(evc, p);
     while (t < t1) {
         if (++iters > 10000000) { free(k); free(tmp); free(un); return -1; }
         int last = 0;
@@ -640,12 +659,12 @@ static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const d
         /* sign changes of the condition on the step's dense output, sampled at theta = j / 10 (interp_points = 10 of
          * ContinuousCallback): a long step may hold a whole flight.  Right after an event the start value is ~0 with a random
          * sign: the first sample decides the side the solution is on. */
-        double gprev = u[ci] - evc->cc_level, thprev = 0.0, lo = 0.0, hi = 1.0;
+        double gprev = u[ci] - level, thprev = 0.0, lo = 0.0, hi = 1.0;
         int hit = 0;
         for (int j = 1; j <= 10 && !hit; j++) {
             const double th = j == 10 ? 1.0 : 0.1 * j;
             double gj;
-            if (j == 10) gj = un[ci] - evc->cc_level; else { tsit5_dense(d, th, h, u, k, yb); gj = yb[ci] - evc->cc_level; }
+            if (j == 10) gj = un[ci] - level; else { tsit5_dense(d, th, h, u, k, yb); gj = yb[ci] - level; }
             if (after_event && j == 1) { gprev = gj; thprev = th; continue; }       /* skip the start point */
             if ((evc->cc_dir <= 0 && gprev > 0 && gj <= 0) || (evc->cc_dir >= 0 && gprev < 0 && gj >= 0)) { hit = 1; lo = thprev; hi = th; }
             else { gprev = gj; thprev = th; }
@@ -658,7 +677,7 @@ static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const d
                 const double mid = 0.5 * (lo + hi);
                 if (!(mid > lo && mid < hi)) break;
                 tsit5_dense(d, mid, h, u, k, yb);
-                const double gm = yb[ci] - evc->cc_level;
+                const double gm = yb[ci] - level;
                 if ((gm > 0) == pos && gm != 0) lo = mid; else hi = mid;
             }
             const double hh = hi * h;                                  /* first representable theta at / past the crossing */
@@ -671,6 +690,7 @@ static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const d
         if (hit) {
             for (int i = 0; i < d; i++) { sc[i] = evc->cc_scale ? evc->cc_scale[i] : 1.0; sh[i] = evc->cc_shift ? evc->cc_shift[i] : 0.0; }
             if (evc->cc_pcomp >= 0) { sc[evc->cc_pcomp] = evc->cc_psign * p[evc->cc_pparam]; sh[evc->cc_pcomp] = 0.0; }
+            if (evc->cc_acomp >= 0) sh[evc->cc_acomp] += evc->cc_acoef * p[evc->cc_aparam];
             for (int i = 0; i < d; i++) un[i] = sc[i] * un[i] + sh[i];
             if (found) cc_push(found, d, t, sc, sh);
             fwd_rhs(t, un, k, &c);
@@ -1086,6 +1106,14 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
                 const double gpar = cfg->cc_psign * um[cfg->cc_pcomp] * z[cfg->cc_pcomp];                  \
                 if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) z[d + cfg->cc_pparam] += gpar; else acc[cfg->cc_pparam] += gpar; \
             }                                                                                              \
+            if (cfg->cc_acomp >= 0) {    /* u+[acomp] += acoef p[aparam]: (da/dp)' lam+ */                    \
+                const double gadd = cfg->cc_acoef * z[cfg->cc_acomp];                                      \
+                if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) z[d + cfg->cc_aparam] += gadd; else acc[cfg->cc_aparam] += gadd; \
+            }                                                                                              \
+            if (cfg->cc_lparam >= 0) {   /* g = u_i - level - lcoef p[lparam]: -(dg/dp) w / (dg/du . f-) */   \
+                const double glev = cfg->cc_lcoef * wl / fm[cfg->cc_idx];                                  \
+                if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) z[d + cfg->cc_lparam] += glev; else acc[cfg->cc_lparam] += glev; \
+            }                                                                                              \
             for (int i = 0; i < d; i++) z[i] *= cfg->ev_scale[(size_t)evc * d + i];                        \
             z[cfg->cc_idx] -= wl / fm[cfg->cc_idx];                                                        \
             if (sa == SA_BACKSOLVE) memcpy(z + d + P, um, sizeof(double) * d);                             \
@@ -1482,5 +1510,23 @@ int oracle_family_eval(const oracle_cfg* cfg, int ito, const double* u, const do
     (ito ? F.f_ito : F.f)(u, p, 0.0, f_out, &F.ctx);
     (ito ? F.vjp_ito : F.vjp)(u, p, 0.0, lam, jtl_out, ftl_out, &F.ctx);
     return 0;
+}
+/* the event list of ONE member's hybrid forward solve (continuous callback): times[max_events], the states left and right of
+ * every event, uminus / uplus [max_events][d].  Returns the number of events (all of them counted, the first max_events
+ * stored) or a negative error.  Unit tests of the event location (test/Callbacks2/continuous_vs_discrete.jl:19-21). */
+int oracle_event_list(const oracle_cfg* cfg, const double* u0, const double* p, int max_events, double* times,
+                      double* uminus, double* uplus) {
+    family_t F; int rc = family_init(&F, cfg); if (rc) return rc;
+    if (!cfg->cc_on || cfg->stepper != ST_TSIT5_ADAPTIVE) return -12;
+    dense_t sol; cc_events found = {0, 0, NULL, NULL, NULL};
+    rc = forward_tsit5_adaptive_cc(&F, p, u0, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, cfg->dt, &sol, cfg, &found);
+    int n = rc ? rc : found.n;
+    for (int e = 0; rc == 0 && e < found.n && e < max_events; e++) {
+        times[e] = found.t[e];
+        if (uminus) dense_eval(&sol, found.t[e], 0, uminus + (size_t)e * F.d, NULL);
+        if (uplus) dense_eval(&sol, found.t[e], 1, uplus + (size_t)e * F.d, NULL);
+    }
+    dense_free(&sol); free(found.t); free(found.scale); free(found.shift);
+    return n;
 }
 int oracle_sizeof_cfg(void) { return (int)sizeof(oracle_cfg); }

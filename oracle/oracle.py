@@ -14,10 +14,10 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.path.join(_HERE, "liboracle.so")
 
-FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5, "ball": 6}
+FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5, "ball": 6, "relax": 7}
 SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kronrod": 4}
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
-FAM_DIMS = {"lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "ball": (2, 2, 0)}
+FAM_DIMS = {"lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "ball": (2, 2, 0), "relax": (1, 2, 0)}
 
 
 class OracleCfg(C.Structure):
@@ -38,6 +38,8 @@ class OracleCfg(C.Structure):
         ("dgdp_c", C.c_void_p), ("dgdp_e", C.c_void_p), ("cdgdp_c", C.c_void_p), ("cdgdp_e", C.c_void_p),
         ("cc_on", C.c_int32), ("cc_idx", C.c_int32), ("cc_dir", C.c_int32), ("cc_pcomp", C.c_int32), ("cc_pparam", C.c_int32), ("cc_found", C.c_int32),
         ("cc_level", C.c_double), ("cc_psign", C.c_double), ("cc_scale", C.c_void_p), ("cc_shift", C.c_void_p),
+        ("cc_lparam", C.c_int32), ("cc_acomp", C.c_int32), ("cc_aparam", C.c_int32), ("_pad2", C.c_int32),
+        ("cc_lcoef", C.c_double), ("cc_acoef", C.c_double),
     ]
 
 
@@ -106,8 +108,12 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
         cfg.cont_cost = 1
         cfg.cont_av, cfg.cont_bv, cfg.cdgdp_c, cfg.cdgdp_e = _vec(a, d), _vec(b, d), _vec(c, P), _vec(e, P)
     cfg._keep_cost = keep
-    # continuous callback: crossing = dict(idx, level=0, direction=-1, scale=None, shift=None, pcomp=-1, pparam=0, psign=-1)
+    # continuous callback: crossing = dict(idx, level=0, direction=-1, scale=None, shift=None, pcomp=-1, pparam=0, psign=-1,
+    #                                       lparam=-1, lcoef=0 (level += lcoef * p[lparam]), acomp=-1, aparam=0, acoef=0 (u[acomp] += acoef * p[aparam]))
+    cfg.cc_lparam, cfg.cc_acomp = -1, -1
     if crossing is not None:
+        cfg.cc_lparam, cfg.cc_lcoef = int(crossing.get("lparam", -1)), float(crossing.get("lcoef", 0.0))
+        cfg.cc_acomp, cfg.cc_aparam, cfg.cc_acoef = int(crossing.get("acomp", -1)), int(crossing.get("aparam", 0)), float(crossing.get("acoef", 0.0))
         cfg.cc_on, cfg.cc_idx, cfg.cc_dir = 1, int(crossing["idx"]), int(crossing.get("direction", -1))
         cfg.cc_level = float(crossing.get("level", 0.0))
         cfg.cc_pcomp, cfg.cc_pparam, cfg.cc_psign = int(crossing.get("pcomp", -1)), int(crossing.get("pparam", 0)), float(crossing.get("psign", -1.0))
@@ -178,6 +184,19 @@ def loss(cfg, saveat, u0, p, dW=None, nthreads=0):
     if rc != 0:
         raise RuntimeError(f"oracle loss failed rc={rc}")
     return out
+
+
+def event_list(cfg, u0, p, max_events=64):
+    """Event times and the states left / right of every event of ONE member's hybrid forward solve (continuous callback)."""
+    d = cfg.d
+    u0 = np.ascontiguousarray(u0, dtype=np.float64).reshape(d)
+    p = np.ascontiguousarray(p, dtype=np.float64)
+    t, um, up = np.zeros(max_events), np.zeros((max_events, d)), np.zeros((max_events, d))
+    n = lib().oracle_event_list(C.byref(cfg), _ptr(u0), _ptr(p), C.c_int(max_events), _ptr(t), _ptr(um), _ptr(up))
+    if n < 0:
+        raise RuntimeError(f"oracle_event_list failed rc={n}")
+    n = min(n, max_events)
+    return t[:n], um[:n], up[:n]
 
 
 def family_eval(family, u, p, lam, ito=False, mlp_hidden=0):

@@ -13,7 +13,7 @@ _ROOT = os.path.dirname(_PKG)
 _CSRC = os.path.join(_PKG, "csrc")
 LIB_PATH = os.environ.get("B200ADJ_LIB", os.path.join(_PKG, "libb200adj.so"))   # env override: tuning experiments only
 
-FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5, "ball": 6}
+FAM = {"lv": 0, "lorenz": 1, "robertson": 2, "sde_lv": 3, "mlp": 4, "sde_linear": 5, "ball": 6, "relax": 7}
 SA = {"interpolating": 0, "gauss": 1, "quadrature": 2, "backsolve": 3, "gauss_kronrod": 4}
 ST = {"tsit5_fixed": 0, "rosenbrock23": 1, "em": 2, "euler_heun": 3, "tsit5_adaptive": 4}
 DTYPE = {"f64": 0, "f32": 1, "bf16_f32acc": 2}
@@ -21,7 +21,7 @@ COST = {"explicit": 0, "affine": 1}
 FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE, FLAG_NO_ROTATE, FLAG_DENSE_FORWARD, FLAG_NCCL_ALLREDUCE = 1, 2, 4, 8, 16, 32, 64, 128
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
-EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_register_family", "b200adj_family_info", "b200adj_set_events", "b200adj_set_continuous_callback", "b200adj_event_times", "b200adj_get_noise", "b200adj_set_stream",
+EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_register_family", "b200adj_family_info", "b200adj_set_events", "b200adj_set_continuous_callback", "b200adj_set_continuous_callback_params", "b200adj_event_times", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg",
            "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_init_all", "b200adj_comm_allreduce", "b200adj_comm_size", "b200adj_comm_is_fused"]
@@ -144,6 +144,8 @@ def load():
         lib.b200adj_set_continuous_callback.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                                         C.c_int32, C.c_int32, C.c_double, C.c_int32]
         lib.b200adj_set_continuous_callback.restype = C.c_int32
+        lib.b200adj_set_continuous_callback_params.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double]
+        lib.b200adj_set_continuous_callback_params.restype = C.c_int32
         lib.b200adj_event_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200adj_event_times.restype = C.c_int32
         lib.b200adj_get_noise.argtypes = [C.c_void_p, C.c_void_p]
@@ -283,6 +285,10 @@ class Handle:
         self._check(self._lib.b200adj_set_continuous_callback(self._h, 1 if enabled else 0, int(idx), float(level), int(direction),
                                                               None if sc is None else sc.ctypes.data, None if sh is None else sh.ctypes.data,
                                                               int(pcomp), int(pparam), float(psign), int(max_events)))
+
+    def set_continuous_callback_params(self, lparam=-1, lcoef=0.0, acomp=-1, aparam=0, acoef=0.0):
+        """Parameter-dependent level (level += lcoef * p[lparam]) and additive parameter affect (u[acomp] += acoef * p[aparam])."""
+        self._check(self._lib.b200adj_set_continuous_callback_params(self._h, int(lparam), float(lcoef), int(acomp), int(aparam), float(acoef)))
 
     def event_times(self, N, max_events):
         """-> (counts[N], times[max_events, N]) found by the last forward pass."""

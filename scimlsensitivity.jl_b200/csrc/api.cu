@@ -22,6 +22,7 @@ int fam_dims(const b200adj_cfg& c, int* d, int* P, int* m) {
     case B200ADJ_FAM_SDE_LV: *d = 2; *P = 6; *m = 2; return 0;
     case B200ADJ_FAM_SDE_LINEAR: *d = 2; *P = 2; *m = 2; return 0;
     case B200ADJ_FAM_BALL: *d = 2; *P = 2; *m = 0; return 0;
+    case B200ADJ_FAM_RELAX: *d = 1; *P = 2; *m = 0; return 0;
     case B200ADJ_FAM_MLP: if (c.mlp_hidden != MLP_H) return -1; *d = MLP_D; *P = MLP_P; *m = 0; return 0;
     default: return -1;
     }
@@ -115,6 +116,7 @@ T5aArgs t5a_args(Handle* h) {
         a.cc_on = 1; a.cc_idx = h->cc_idx; a.cc_dir = h->cc_dir; a.cc_pcomp = h->cc_pcomp; a.cc_pparam = h->cc_pparam; a.cc_maxev = h->cc_maxev;
         a.cc_level = h->cc_level; a.cc_psign = h->cc_psign; a.cc_t = h->d_cc_t; a.cc_n = h->d_cc_n;
         for (int j = 0; j < 4; j++) { a.cc_scale[j] = h->cc_scale[j]; a.cc_shift[j] = h->cc_shift[j]; }
+        a.cc_lparam = h->cc_lparam; a.cc_lcoef = h->cc_lcoef; a.cc_acomp = h->cc_acomp; a.cc_aparam = h->cc_aparam; a.cc_acoef = h->cc_acoef;
     }
     return a;
 }
@@ -198,7 +200,7 @@ int ensure_quad_buffers(Handle* h) {
 
 extern "C" {
 
-uint32_t b200adj_version(void) { return 0x000200u; }
+uint32_t b200adj_version(void) { return 0x000201u; }
 uint32_t b200adj_sizeof_cfg(void) { return (uint32_t)sizeof(b200adj_cfg); }
 
 const char* b200adj_last_error(void* handle) {
@@ -256,6 +258,7 @@ int32_t b200adj_create(const b200adj_cfg* cfg, void** handle) {
         if (ros && !dense_fixed && !(cfg->abstol > 0 && cfg->reltol > 0)) { g_create_error = "adaptive steppers need abstol, reltol > 0"; return B200ADJ_ERR_INVALID; }
         if (ros && mlp) { g_create_error = "MLP family: fixed-step Tsit5 only"; return B200ADJ_ERR_UNSUPPORTED; }
     }
+    if (cfg->rhs_family == B200ADJ_FAM_RELAX && !t5a) { g_create_error = "Relax family: Tsit5 on the per-member dense framework (adaptive, or fixed step with B200ADJ_FLAG_DENSE_FORWARD)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (cfg->rhs_family == B200ADJ_FAM_BALL && !t5a) { g_create_error = "BouncingBall family: Tsit5 on the per-member dense framework (adaptive, or fixed step with B200ADJ_FLAG_DENSE_FORWARD)"; return B200ADJ_ERR_UNSUPPORTED; }
     if (ros) {
         // adaptive path: save times are arbitrary ascending points of [t0, t1] (tstops of the reverse solve)
@@ -628,7 +631,24 @@ int32_t b200adj_set_continuous_callback(void* handle, int32_t enabled, int32_t i
     CUDA_TRY(h, cudaMemsetAsync(h->d_cc_n, 0, (size_t)c.N * sizeof(int32_t), h->stream));
     h->cc_on = true; h->cc_idx = idx; h->cc_dir = direction; h->cc_pcomp = pcomp < 0 ? -1 : pcomp; h->cc_pparam = pcomp < 0 ? 0 : pparam;
     h->cc_maxev = max_events; h->cc_level = level; h->cc_psign = psign;
+    h->cc_lparam = -1; h->cc_lcoef = 0; h->cc_acomp = -1; h->cc_aparam = 0; h->cc_acoef = 0;      // set_continuous_callback_params adds them
     for (int j = 0; j < 4; j++) { h->cc_scale[j] = (scale && j < c.d) ? scale[j] : 1.0; h->cc_shift[j] = (shift && j < c.d) ? shift[j] : 0.0; }
+    h->have_forward = false;
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, double lcoef, int32_t acomp, int32_t aparam, double acoef) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    if (!h->cc_on) { h->err = "continuous callback parameters: call b200adj_set_continuous_callback first"; return B200ADJ_ERR_STATE; }
+    if (lparam >= c.P || (acomp >= 0 && (acomp >= c.d || aparam < 0 || aparam >= c.P)) || !std::isfinite(lcoef) || !std::isfinite(acoef)) {
+        h->err = "continuous callback parameters: bad lparam / acomp / aparam"; return B200ADJ_ERR_INVALID; }
+    if (acomp >= 0 && acomp == h->cc_pcomp) { h->err = "continuous callback parameters: acomp is the component the parameter-scaled affect overwrites"; return B200ADJ_ERR_INVALID; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->cc_lparam = lparam < 0 ? -1 : lparam; h->cc_lcoef = lparam < 0 ? 0.0 : lcoef;
+    h->cc_acomp = acomp < 0 ? -1 : acomp; h->cc_aparam = acomp < 0 ? 0 : aparam; h->cc_acoef = acomp < 0 ? 0.0 : acoef;
     h->have_forward = false;
     return B200ADJ_OK;
 }
@@ -712,6 +732,7 @@ int32_t b200adj_forward(void* handle, const void* u0, const void* p, const void*
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_fwd<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_fwd<Robertson>(h, a); break;
         case B200ADJ_FAM_BALL: rc = launch_t5a_fwd<BouncingBall>(h, a); break;
+        case B200ADJ_FAM_RELAX: rc = launch_t5a_fwd<Relax>(h, a); break;
         default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->t5a_fwd) ? vt->t5a_fwd(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (h->adaptive) {
@@ -810,6 +831,7 @@ int32_t b200adj_reverse(void* handle, const void* dLdu, void* du0, void* dp) {
         case B200ADJ_FAM_LORENZ: rc = launch_t5a_rev<Lorenz>(h, a); break;
         case B200ADJ_FAM_ROBERTSON: rc = launch_t5a_rev<Robertson>(h, a); break;
         case B200ADJ_FAM_BALL: rc = launch_t5a_rev<BouncingBall>(h, a); break;
+        case B200ADJ_FAM_RELAX: rc = launch_t5a_rev<Relax>(h, a); break;
         default: { const FamilyVTable* vt = family_lookup(c.rhs_family); rc = (vt && vt->t5a_rev) ? vt->t5a_rev(h, a) : B200ADJ_ERR_UNSUPPORTED; }
         }
     } else if (h->adaptive) {

@@ -116,6 +116,18 @@ struct BouncingBall {
     template <class T> __device__ __forceinline__ static void dvjp_p(const T* u, const T* p, const T* ud, const T* l, T* dg) { dg[0] = T(0); dg[1] = T(0); }
 };
 
+// relaxation towards p0 (test/Callbacks2/continuous_callbacks.jl:317-324: f(D,u,p,t) = (D[1] = p[1] - u[1])); p1 enters through
+// the event only (condition u - 3/4 p[1], affect u += p[2]: b200adj_set_continuous_callback_params)
+struct Relax {
+    static constexpr int D = 1, P = 2, M = 0;
+    template <class T> __device__ __forceinline__ static void f(const T* u, const T* p, T* du) { du[0] = p[0] - u[0]; }
+    template <class T> __device__ __forceinline__ static void vjp_u(const T* u, const T* p, const T* l, T* dl) { dl[0] = -l[0]; }
+    template <class T> __device__ __forceinline__ static void vjp_p(const T* u, const T* p, const T* l, T* dg) { dg[0] = l[0]; dg[1] = T(0); }
+    template <class T> __device__ __forceinline__ static void jac(const T* u, const T* p, T (*J)[1]) { J[0][0] = -1; }
+    template <class T> __device__ __forceinline__ static void djac(const T* p, const T* yd, T (*J)[1]) { J[0][0] = 0; }
+    template <class T> __device__ __forceinline__ static void dvjp_p(const T* u, const T* p, const T* ud, const T* l, T* dg) { dg[0] = T(0); dg[1] = T(0); }
+};
+
 // SDE Lotka-Volterra with diagonal noise g_i = p[4+i] u_i.  ITO selects the reference's transformed drift
 // f - (dg/du)' g (src/sde_tools.jl:29-66, chosen at src/backsolve_adjoint.jl:327-345 for Ito solvers like EM).
 template <bool ITO>

@@ -42,6 +42,9 @@ struct T5aArgs {
     int32_t cc_on, cc_idx, cc_dir, cc_pcomp, cc_pparam, cc_maxev;
     double cc_level, cc_psign, cc_scale[4], cc_shift[4];
     double* cc_t; int32_t* cc_n;
+    // parameter-dependent condition / additive parameter affect (test/Callbacks2/continuous_callbacks.jl:317-345): the level is
+    // cc_level + cc_lcoef * p[cc_lparam] (cc_lparam < 0: none); u[cc_acomp] += cc_acoef * p[cc_aparam] after the affine part
+    int32_t cc_lparam, cc_acomp, cc_aparam, cc_pad_; double cc_lcoef, cc_acoef;
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
     double BT[7];           // embedded error weights b - bhat
@@ -193,6 +196,23 @@ __device__ __forceinline__ void t5_cc_affect(const T5aArgs& a, const double* p, 
         sc[j] = pc ? a.cc_psign * pv : a.cc_scale[j];
         sh[j] = pc ? 0.0 : a.cc_shift[j];
     }
+    if (a.cc_acomp >= 0) {           // u[acomp] += acoef * p[aparam]
+        double pa = 0.0;
+#pragma unroll
+        for (int q = 0; q < P; q++) if (q == a.cc_aparam) pa = p[q];
+#pragma unroll
+        for (int j = 0; j < D; j++) if (j == a.cc_acomp) sh[j] += a.cc_acoef * pa;
+    }
+}
+// level of the condition u[cc_idx] - level: cc_level + cc_lcoef * p[cc_lparam]
+template <int P>
+__device__ __forceinline__ double t5_cc_level(const T5aArgs& a, const double* p) {
+    double lv = a.cc_level;
+    if (a.cc_lparam >= 0) {
+#pragma unroll
+        for (int q = 0; q < P; q++) if (q == a.cc_lparam) lv += a.cc_lcoef * p[q];
+    }
+    return lv;
 }
 template <int D>
 __device__ __forceinline__ double t5_pick(const double* v, int idx) {
@@ -234,6 +254,7 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
     const bool fixed = (a.flags & 16u) != 0;      // constant step dt0, no error control (fixed-step Tsit5 with off-grid save times)
     bool after_event = false;                     // CC: the step starts on an event (condition ~0 with a random sign)
     int nfound = 0;
+    const double cc_lev = CC ? t5_cc_level<P>(a, p) : 0.0;
     // component cc_idx of the step's dense output at theta (k1..k7 in registers)
     auto cond_at = [&](double th, double hh) {
         double w[7];
@@ -246,7 +267,7 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
             for (int s = 0; s < 7; s++) acc += w[s] * k[s][j];
             if (j == a.cc_idx) r = u[j] + hh * acc;
         }
-        return r - a.cc_level;
+        return r - cc_lev;
     };
     while (t < a.t1) {
         if (++iters > 10000000L || n >= a.maxs) { stat = 2; break; }
@@ -269,11 +290,11 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
             if (CC) {
                 // sign changes of the condition on the dense output, sampled at theta = j / 10 (interp_points = 10 of
                 // ContinuousCallback: a long step may hold a whole flight); right after an event the first sample decides the side
-                double gprev = t5_pick<D>(u, a.cc_idx) - a.cc_level, thprev = 0.0, lo = 0.0, hi = 1.0;
+                double gprev = t5_pick<D>(u, a.cc_idx) - cc_lev, thprev = 0.0, lo = 0.0, hi = 1.0;
                 bool hit = false;
                 for (int j = 1; j <= 10 && !hit; j++) {
                     const double th = j == 10 ? 1.0 : 0.1 * j;
-                    const double gj = (j == 10) ? t5_pick<D>(un, a.cc_idx) - a.cc_level : cond_at(th, h);
+                    const double gj = (j == 10) ? t5_pick<D>(un, a.cc_idx) - cc_lev : cond_at(th, h);
                     if (after_event && j == 1) { gprev = gj; thprev = th; continue; }
                     if ((a.cc_dir <= 0 && gprev > 0 && gj <= 0) || (a.cc_dir >= 0 && gprev < 0 && gj >= 0)) { hit = true; lo = thprev; hi = th; }
                     else { gprev = gj; thprev = th; }
@@ -494,6 +515,20 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
                     }
                 }
                 const double corr = wl / t5_pick<D>(fm, a.cc_idx);
+                if (a.cc_acomp >= 0) {       // u+[acomp] += acoef p[aparam]: (da/dp)'lam+
+                    const double gadd = a.cc_acoef * t5_pick<D>(z, a.cc_acomp);
+#pragma unroll
+                    for (int q = 0; q < P; q++) if (q == a.cc_aparam) {
+                        if (SA == SA_INTERP || SA == SA_BACKSOLVE) z[D + (L > D ? q : 0)] += gadd; else acc[q] += gadd;
+                    }
+                }
+                if (a.cc_lparam >= 0) {      // g = u_i - level - lcoef p[lparam]: -(dg/dp) w / (dg/du . f-)
+                    const double glev = a.cc_lcoef * corr;
+#pragma unroll
+                    for (int q = 0; q < P; q++) if (q == a.cc_lparam) {
+                        if (SA == SA_INTERP || SA == SA_BACKSOLVE) z[D + (L > D ? q : 0)] += glev; else acc[q] += glev;
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < D; j++) { z[j] *= sc[j]; if (j == a.cc_idx) z[j] -= corr; }
                 if (SA == SA_BACKSOLVE) {

@@ -15,6 +15,7 @@ FAMILIES = {
     # name: (d, P, m)
     "lv": (2, 4, 0), "lorenz": (3, 3, 0), "robertson": (3, 3, 0), "sde_lv": (2, 6, 2), "sde_linear": (2, 2, 2),
     "ball": (2, 2, 0),           # bouncing ball x' = v, v' = -p[0]; p = [gravity, restitution] (adaptive Tsit5; ContinuousCallback)
+    "relax": (1, 2, 0),          # u' = p[0] - u; p = [steady state, injected amount] (test/Callbacks2/continuous_callbacks.jl:317-324)
     "mlp": (2, 4482, 0),         # 2 -> 64 -> 64 -> 2 tanh MLP, p = [W1, b1, W2, b2, W3, b3] column-major flattened
 }
 
@@ -165,6 +166,10 @@ class ContinuousCallback:
       condition(u, t, integrator) = u[idx] - level      (fires on a zero crossing; direction -1 = downwards only, i.e.
                                                          affect_neg! = nothing ..., +1 upwards only, 0 both)
       affect!(integrator): u .= scale .* u .+ shift, then u[p_comp] = p_sign * p[p_param] * u[p_comp]   (if p_comp is set)
+    A parameter-dependent level and an additive parameter affect are part of the family: level + level_coef * p[level_param]
+    and u[add_comp] += add_coef * p[add_param] -- "condition = u[1] - 3//4 * p[1]; affect! = u[1] += p[2]"
+    (test/Callbacks2/continuous_callbacks.jl:317-345) is ContinuousCallback(idx=0, direction=0, level_param=0, level_coef=0.75,
+    add_comp=0, add_param=1, add_coef=1.0).
     The bouncing ball "integrator.u[2] = -integrator.p[2] * integrator.u[2]" when u[1] crosses 0 downwards is
     ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0).  Indices are 0-based.
     save_positions = (false, false) only; every ensemble member finds its own event times on the device."""
@@ -178,11 +183,17 @@ class ContinuousCallback:
     p_sign: float = 1.0
     max_events: int = 64
     save_positions: Tuple[bool, bool] = (False, False)
+    level_param: Optional[int] = None
+    level_coef: float = 0.0
+    add_comp: Optional[int] = None
+    add_param: int = 0
+    add_coef: float = 0.0
 
     def key(self):
         sc = None if self.scale is None else np.asarray(self.scale, dtype=np.float64).tobytes()
         sh = None if self.shift is None else np.asarray(self.shift, dtype=np.float64).tobytes()
-        return ("cc", self.idx, self.level, self.direction, sc, sh, self.p_comp, self.p_param, self.p_sign, self.max_events)
+        return ("cc", self.idx, self.level, self.direction, sc, sh, self.p_comp, self.p_param, self.p_sign, self.max_events,
+                self.level_param, self.level_coef, self.add_comp, self.add_param, self.add_coef)
 
 
 def saveat_to_times(saveat, tspan):
