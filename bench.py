@@ -21,8 +21,8 @@ Keys of the one JSON line (rank 0):
 `parity`    device gradient vs the CPU oracle on a bounded sub-ensemble, sharded exactly like the timed run (every rank
             owns a slice, dp all-reduced behind the C ABI); the run exits non-zero above 1e-8.
 `strong`    (N>1) the metric's fixed total N=65536 split over the ranks.
-`secondary` BASELINE configs C4 (bf16 tensor-core neural ODE) and C5 (SDE) sharded over the same ranks, each timed,
-            roofline'd and oracle-checked.
+`secondary` BASELINE configs C4 (bf16 tensor-core neural ODE), C5 (SDE), C1 as a 65536-member adaptive-Tsit5 ensemble and C3
+            (Robertson / Rosenbrock23 / QuadratureAdjoint) sharded over the same ranks, each timed, roofline'd and oracle-checked.
 `cpu_baseline` the C oracle (a PORT of the reference algorithm; Julia cannot run here) on the host cores.
 """
 import argparse
@@ -291,6 +291,29 @@ def spec_c1():
                                                                "step sequence (DESIGN.md 4.4); the bytes are the compulsory record stream"})
 
 
+def spec_c3():
+    """BASELINE configs[2]: Robertson, per-member rate constants, QuadratureAdjoint, adaptive Rosenbrock23."""
+    T = 100.0
+    saveat = np.logspace(-2, 2, 10); saveat[-1] = T
+    tol = dict(abstol=1e-8, reltol=1e-8, quad_abstol=1e-10, quad_reltol=1e-10)
+
+    def inputs(n, off):
+        k = np.array([0.04, 3e7, 1e4])[:, None] * np.exp(0.05 * np.random.default_rng(4000 + off).standard_normal((3, n)))
+        return np.repeat(np.array([[1.0], [0.0], [0.0]]), n, 1), k
+    FWD, REV = 10, 12     # doubles per interval of the dense forward (t, u, k1, k2) / reverse (t, h, z, k1, k2, 1/h) solutions
+    return dict(name="C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves",
+                family="robertson", sensealg="quadrature", stepper="rosenbrock23", T=T, dt=0.0, saveat=saveat, cost=(1.0, 0.0),
+                dtype="f64", shared_p=False, okw=dict(tol), ekw=dict(max_steps=8192, **tol), tol=1e-5,
+                inputs=inputs, parity_members=256,
+                roofline=lambda n, S, rev_s, hbm, tf: {"bound": "hbm", "kernel": "ros23_quadrature_kernel<Robertson> + ros23_reverse_kernel<Robertson,QUAD>",
+                                                       "achieved": (FWD + REV) * 8.0 * n * S / rev_s / 1e9, "peak": hbm, "unit": "GB/s",
+                                                       "frac": (FWD + REV) * 8.0 * n * S / rev_s / 1e9 / hbm,
+                                                       "algorithmic_bytes_per_launch": (FWD + REV) * 8.0 * n * S, "mean_forward_steps_per_member": S,
+                                                       "note": "latency bound (adaptive per-member step sequences, warp-per-member quadgk with data-dependent "
+                                                               "bisection): the bytes are the dense forward + reverse solutions written and read once, taking "
+                                                               "the forward step count for both (DESIGN.md 4.4); BASELINE bound on dp: 1e-5 per member"})
+
+
 def spec_c2(T=None):
     W = WORKLOAD
     T = T or W["T"]
@@ -312,7 +335,8 @@ class Shard:
         self.spec, self.n, self.torch = spec, n_local, torch
         self.eng = b.DeviceEnsemble(spec["family"], spec["sensealg"], spec["stepper"], n_local, spec["saveat"], (0.0, spec["T"]), spec["dt"],
                                     on_device=True, device=local, dtype=spec["dtype"], cost=b.AffineCost(*spec["cost"]),
-                                    traj_offset=rank * n_local, block_threads=block, nccl_allreduce=Shard.nccl_allreduce, **spec["ekw"])
+                                    traj_offset=rank * n_local, block_threads=block, nccl_allreduce=Shard.nccl_allreduce,
+                                    shared_p=spec.get("shared_p", True), **spec["ekw"])
         self.eng.use_current_torch_stream()
         if world > 1:
             D.attach_comm(self.eng)
@@ -378,13 +402,20 @@ def parity_pass(spec, rank, world, local, threads):
         return None
     u0s, p = zip(*[spec["inputs"](n, r) for r in range(world)])
     u0 = np.concatenate(u0s, axis=1)
+    shared = spec.get("shared_p", True)
     cfg = O.make_cfg(spec["family"], spec["sensealg"], spec["stepper"], n * world, spec["saveat"], 0.0, spec["T"], dt=spec["dt"],
-                     cost=("affine",) + tuple(spec["cost"]), **spec["okw"])
-    ref = O.gradient(cfg, spec["saveat"], u0, p[0], dW=dW_all, want_saved=False, nthreads=threads)
-    dp_rel = float(np.abs(dp - ref["dp"]).max() / np.abs(ref["dp"]).max())
+                     cost=("affine",) + tuple(spec["cost"]), shared_p=shared, **spec["okw"])
+    ref = O.gradient(cfg, spec["saveat"], u0, p[0] if shared else np.concatenate(p, axis=1), dW=dW_all, want_saved=False, nthreads=threads)
     du0_rel = float(np.abs(du0 - ref["du0"][:, :n]).max() / np.abs(ref["du0"]).max())
+    if shared:
+        dp_rel = float(np.abs(dp - ref["dp"]).max() / np.abs(ref["dp"]).max())
+        against = "CPU oracle (oracle/adjoint_oracle.c) on the same members; dp all-reduced over the ranks by b200adj_reverse"
+    else:       # per-member parameters: rank 0's rows, worst member, every row of dp scaled by its own magnitude over the sample
+        rdp = ref["dp"][:, :n]
+        dp_rel = float((np.abs(dp - rdp) / np.abs(rdp).max(axis=1, keepdims=True)).max())
+        against = "CPU oracle (oracle/adjoint_oracle.c) on the same members; per-member dp (no reduction), worst member of rank 0's slice"
     return {"dp_rel": dp_rel, "du0_rel": du0_rel, "members": n * world, "tol": spec["tol"], "ok": bool(dp_rel <= spec["tol"] and du0_rel <= spec["tol"]),
-            "against": "CPU oracle (oracle/adjoint_oracle.c) on the same members; dp all-reduced over the ranks by b200adj_reverse"}
+            "against": against}
 
 
 def secondary_leg(spec, n_total, rank, world, local, steps, warmup, barrier, threads, with_parity=True):
@@ -540,10 +571,18 @@ def run_ours(args):
     secondary = {}
     if not args.no_secondary and not args.members:
         sec_steps, sec_warm = max(5, min(args.steps, 20)), 3
-        secondary["c4"] = secondary_leg(spec_c4(), 4096, rank, world, local, sec_steps, sec_warm, barrier, threads)
-        secondary["c4_full"] = secondary_leg(spec_c4(), 18944 * world, rank, world, local, sec_steps, sec_warm, barrier, threads, with_parity=False)
-        secondary["c5"] = secondary_leg(spec_c5(), 131072, rank, world, local, sec_steps, sec_warm, barrier, threads)
-        secondary["c1_ensemble"] = secondary_leg(spec_c1(), 65536 * world, rank, world, local, max(3, min(sec_steps, 5)), 2, barrier, threads)
+        few = max(3, min(sec_steps, 5))
+        legs = [("c4", spec_c4, 4096, sec_steps, sec_warm, True), ("c4_full", spec_c4, 18944 * world, sec_steps, sec_warm, False),
+                ("c5", spec_c5, 131072, sec_steps, sec_warm, True), ("c1_ensemble", spec_c1, 65536 * world, few, 2, True),
+                ("c3", spec_c3, 16384, few, 2, True)]
+        for key, mk, n_total, k_steps, k_warm, with_par in legs:
+            try:
+                secondary[key] = secondary_leg(mk(), n_total, rank, world, local, k_steps, k_warm, barrier, threads, with_parity=with_par)
+            except Exception as exc:        # a secondary leg must not take the headline down; with several ranks a one-sided
+                if world > 1:               # failure would leave the others in a barrier, so there it stays fatal
+                    raise
+                sys.stderr.write(f"[bench] secondary leg {key} failed: {exc!r}\n")
+                secondary[key] = {"error": repr(exc)}
 
     if rank == 0:
         hbm, tf, peak_src = peaks()
@@ -605,6 +644,7 @@ def run_ours(args):
             line["secondary"] = secondary
         emit(line)
         bad = [k for k, v in [("c2", parity)] + [(k, (v or {}).get("parity")) for k, v in secondary.items()] if v is not None and not v["ok"]]
+        bad += [k for k, v in secondary.items() if v is not None and "error" in v]
         if bad or not e2e_ok or not rr_ok:
             sys.stderr.write(f"[bench] PARITY FAILURE: {bad} e2e_ok={e2e_ok} rrule_ok={rr_ok}\n")
             if world > 1:
