@@ -198,8 +198,12 @@ int32_t b200adj_set_continuous_callback(void* handle, int32_t enabled, int32_t i
  * affect!(integrator) = integrator.u[1] += integrator.p[2]):  condition = u[idx] - (level + lcoef * p[lparam])  (lparam < 0:
  * none) and, after the affine part of the affect, u[acomp] += acoef * p[aparam]  (acomp < 0: none).  Reverse pass, with
  * w = (A f(u-) - f(u+))'lam+:  dG/dp[lparam] += lcoef * w / f(u-)[idx]  (the event time moves with the level) and
- * dG/dp[aparam] += acoef * lam+[acomp].  Call after b200adj_set_continuous_callback (which resets both to none). */
-int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, double lcoef, int32_t acomp, int32_t aparam, double acoef);
+ * dG/dp[aparam] += acoef * lam+[acomp].  qcomp >= 0: the NON-LINEAR affect of the reference's tests, u[qcomp] <- qcoef *
+ * u[qcomp]^2 ("integrator.u[2] = integrator.u[2]^2", test/Callbacks2/continuous_callbacks.jl:222-250) in place of that
+ * component's affine map; the reverse pass uses its Jacobian 2 qcoef u-[qcomp] where the affine family has `scale`.
+ * Call after b200adj_set_continuous_callback (which resets all three to none). */
+int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, double lcoef, int32_t acomp, int32_t aparam, double acoef,
+                                               int32_t qcomp, double qcoef);
 /* event lists found by the last forward pass: counts[N] (host, may be NULL), times[max_events][N] (host, may be NULL) */
 int32_t b200adj_event_times(void* handle, int32_t* counts, double* times);
 

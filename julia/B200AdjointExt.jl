@@ -52,17 +52,18 @@ ABI).  The bouncing ball of docs/src/examples/hybrid_jump/bouncing_ball.md is `B
 psign = -1.0)`.  Adaptive Tsit5; every ensemble member finds its own event times on the device.
 Parameter-dependent level and additive parameter affect (`lparam`, `lcoef`, `acomp`, `aparam`, `acoef`; 1-based, 0 = none):
 `condition = u[1] - 3//4 * p[1]; affect! = u[1] += p[2]` of test/Callbacks2/continuous_callbacks.jl:317-345 is
-`B200Crossing(1, 0.0, 0; lparam = 1, lcoef = 0.75, acomp = 1, aparam = 2, acoef = 1.0)`.
+`B200Crossing(1, 0.0, 0; lparam = 1, lcoef = 0.75, acomp = 1, aparam = 2, acoef = 1.0)`; the non-linear affect
+`u[2] = u[2]^2` (:222-250) is `qcomp = 2` (`u[qcomp] = qcoef * u[qcomp]^2`).
 """
 struct B200Crossing
     idx::Int; level::Float64; direction::Int
     scale::Union{Nothing, Vector{Float64}}; shift::Union{Nothing, Vector{Float64}}
     pcomp::Int; pparam::Int; psign::Float64; max_events::Int
-    lparam::Int; lcoef::Float64; acomp::Int; aparam::Int; acoef::Float64
+    lparam::Int; lcoef::Float64; acomp::Int; aparam::Int; acoef::Float64; qcomp::Int; qcoef::Float64
 end
 B200Crossing(idx, level = 0.0, direction = -1; scale = nothing, shift = nothing, pcomp = 0, pparam = 0, psign = 1.0, max_events = 64,
-             lparam = 0, lcoef = 0.0, acomp = 0, aparam = 0, acoef = 0.0) =
-    B200Crossing(idx, level, direction, scale, shift, pcomp, pparam, psign, max_events, lparam, lcoef, acomp, aparam, acoef)
+             lparam = 0, lcoef = 0.0, acomp = 0, aparam = 0, acoef = 0.0, qcomp = 0, qcoef = 1.0) =
+    B200Crossing(idx, level, direction, scale, shift, pcomp, pparam, psign, max_events, lparam, lcoef, acomp, aparam, acoef, qcomp, qcoef)
 
 struct B200Cfg
     rhs_family::Int32; sensealg::Int32; stepper::Int32; dtype::Int32
@@ -222,9 +223,9 @@ function b200_solve_adjoint(prob, alg, sensealg::B200Adjoint, U::AbstractMatrix{
                 (Ptr{Cvoid}, Int32, Int32, Float64, Int32, Ptr{Float64}, Ptr{Float64}, Int32, Int32, Float64, Int32),
                 s.h.ptr, 1, c.idx - 1, c.level, c.direction, c.scale === nothing ? C_NULL : pointer(c.scale),
                 c.shift === nothing ? C_NULL : pointer(c.shift), c.pcomp - 1, max(c.pparam - 1, 0), c.psign, c.max_events))
-            (c.lparam > 0 || c.acomp > 0) && check(s.h.ptr, ccall((:b200adj_set_continuous_callback_params, libb200adj), Int32,
-                (Ptr{Cvoid}, Int32, Float64, Int32, Int32, Float64),
-                s.h.ptr, c.lparam - 1, c.lcoef, c.acomp - 1, max(c.aparam - 1, 0), c.acoef))
+            (c.lparam > 0 || c.acomp > 0 || c.qcomp > 0) && check(s.h.ptr, ccall((:b200adj_set_continuous_callback_params, libb200adj), Int32,
+                (Ptr{Cvoid}, Int32, Float64, Int32, Int32, Float64, Int32, Float64),
+                s.h.ptr, c.lparam - 1, c.lcoef, c.acomp - 1, max(c.aparam - 1, 0), c.acoef, c.qcomp - 1, c.qcoef))
         end
     end
     # forward: every shard on its own host thread (the calls block until the D2H copies are done)

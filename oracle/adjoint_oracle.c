@@ -86,8 +86,12 @@ typedef struct {
     /* parameter-dependent condition and additive parameter affect (test/Callbacks2/continuous_callbacks.jl:317-345:
      * condition u[1] - 3/4 p[1], affect u[1] += p[2]): the level is cc_level + cc_lcoef * p[cc_lparam] (cc_lparam < 0: none)
      * and u[cc_acomp] += cc_acoef * p[cc_aparam] (cc_acomp < 0: none) after the affine part */
-    int32_t cc_lparam, cc_acomp, cc_aparam, _pad2;
+    int32_t cc_lparam, cc_acomp, cc_aparam, cc_qcomp;
     double cc_lcoef, cc_acoef;
+    /* non-linear affect of the reference's tests (test/Callbacks2/continuous_callbacks.jl:222-250, u[2] = u[2]^2):
+     * u[cc_qcomp] <- cc_qcoef * u[cc_qcomp]^2 (cc_qcomp < 0: none) instead of the affine map of that component; the
+     * reverse pass sees its Jacobian 2 cc_qcoef u-[cc_qcomp] as the event's scale */
+    double cc_qcoef;
 } oracle_cfg;
 #define CC_LEVEL(c, p) ((c)->cc_level + ((c)->cc_lparam >= 0 ? (c)->cc_lcoef * (p)[(c)->cc_lparam] : 0.0))
 #define COST_A(c, j) ((c)->cost_av ? (c)->cost_av[j] : (c)->cost_a)
@@ -691,7 +695,11 @@ static int forward_tsit5_adaptive_cc(const family_t* F, const double* p, const d
             for (int i = 0; i < d; i++) { sc[i] = evc->cc_scale ? evc->cc_scale[i] : 1.0; sh[i] = evc->cc_shift ? evc->cc_shift[i] : 0.0; }
             if (evc->cc_pcomp >= 0) { sc[evc->cc_pcomp] = evc->cc_psign * p[evc->cc_pparam]; sh[evc->cc_pcomp] = 0.0; }
             if (evc->cc_acomp >= 0) sh[evc->cc_acomp] += evc->cc_acoef * p[evc->cc_aparam];
+            const double uq = evc->cc_qcomp >= 0 ? un[evc->cc_qcomp] : 0.0;
             for (int i = 0; i < d; i++) un[i] = sc[i] * un[i] + sh[i];
+            if (evc->cc_qcomp >= 0) {       /* u_q <- qcoef u_q^2: Jacobian 2 qcoef u_q- is what the reverse pass needs */
+                un[evc->cc_qcomp] = evc->cc_qcoef * uq * uq; sc[evc->cc_qcomp] = 2.0 * evc->cc_qcoef * uq; sh[evc->cc_qcomp] = 0.0;
+            }
             if (found) cc_push(found, d, t, sc, sh);
             fwd_rhs(t, un, k, &c);
             after_event = 1;

@@ -38,8 +38,8 @@ class OracleCfg(C.Structure):
         ("dgdp_c", C.c_void_p), ("dgdp_e", C.c_void_p), ("cdgdp_c", C.c_void_p), ("cdgdp_e", C.c_void_p),
         ("cc_on", C.c_int32), ("cc_idx", C.c_int32), ("cc_dir", C.c_int32), ("cc_pcomp", C.c_int32), ("cc_pparam", C.c_int32), ("cc_found", C.c_int32),
         ("cc_level", C.c_double), ("cc_psign", C.c_double), ("cc_scale", C.c_void_p), ("cc_shift", C.c_void_p),
-        ("cc_lparam", C.c_int32), ("cc_acomp", C.c_int32), ("cc_aparam", C.c_int32), ("_pad2", C.c_int32),
-        ("cc_lcoef", C.c_double), ("cc_acoef", C.c_double),
+        ("cc_lparam", C.c_int32), ("cc_acomp", C.c_int32), ("cc_aparam", C.c_int32), ("cc_qcomp", C.c_int32),
+        ("cc_lcoef", C.c_double), ("cc_acoef", C.c_double), ("cc_qcoef", C.c_double),
     ]
 
 
@@ -110,8 +110,9 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
     cfg._keep_cost = keep
     # continuous callback: crossing = dict(idx, level=0, direction=-1, scale=None, shift=None, pcomp=-1, pparam=0, psign=-1,
     #                                       lparam=-1, lcoef=0 (level += lcoef * p[lparam]), acomp=-1, aparam=0, acoef=0 (u[acomp] += acoef * p[aparam]))
-    cfg.cc_lparam, cfg.cc_acomp = -1, -1
+    cfg.cc_lparam, cfg.cc_acomp, cfg.cc_qcomp = -1, -1, -1
     if crossing is not None:
+        cfg.cc_qcomp, cfg.cc_qcoef = int(crossing.get("qcomp", -1)), float(crossing.get("qcoef", 1.0))    # u[qcomp] <- qcoef * u[qcomp]^2
         cfg.cc_lparam, cfg.cc_lcoef = int(crossing.get("lparam", -1)), float(crossing.get("lcoef", 0.0))
         cfg.cc_acomp, cfg.cc_aparam, cfg.cc_acoef = int(crossing.get("acomp", -1)), int(crossing.get("aparam", 0)), float(crossing.get("acoef", 0.0))
         cfg.cc_on, cfg.cc_idx, cfg.cc_dir = 1, int(crossing["idx"]), int(crossing.get("direction", -1))

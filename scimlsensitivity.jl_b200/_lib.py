@@ -144,7 +144,7 @@ def load():
         lib.b200adj_set_continuous_callback.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                                         C.c_int32, C.c_int32, C.c_double, C.c_int32]
         lib.b200adj_set_continuous_callback.restype = C.c_int32
-        lib.b200adj_set_continuous_callback_params.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double]
+        lib.b200adj_set_continuous_callback_params.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double]
         lib.b200adj_set_continuous_callback_params.restype = C.c_int32
         lib.b200adj_event_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.b200adj_event_times.restype = C.c_int32
@@ -286,9 +286,11 @@ class Handle:
                                                               None if sc is None else sc.ctypes.data, None if sh is None else sh.ctypes.data,
                                                               int(pcomp), int(pparam), float(psign), int(max_events)))
 
-    def set_continuous_callback_params(self, lparam=-1, lcoef=0.0, acomp=-1, aparam=0, acoef=0.0):
-        """Parameter-dependent level (level += lcoef * p[lparam]) and additive parameter affect (u[acomp] += acoef * p[aparam])."""
-        self._check(self._lib.b200adj_set_continuous_callback_params(self._h, int(lparam), float(lcoef), int(acomp), int(aparam), float(acoef)))
+    def set_continuous_callback_params(self, lparam=-1, lcoef=0.0, acomp=-1, aparam=0, acoef=0.0, qcomp=-1, qcoef=1.0):
+        """Parameter-dependent level (level += lcoef * p[lparam]), additive parameter affect (u[acomp] += acoef * p[aparam]),
+        quadratic affect (u[qcomp] <- qcoef * u[qcomp]^2)."""
+        self._check(self._lib.b200adj_set_continuous_callback_params(self._h, int(lparam), float(lcoef), int(acomp), int(aparam), float(acoef),
+                                                                     int(qcomp), float(qcoef)))
 
     def event_times(self, N, max_events):
         """-> (counts[N], times[max_events, N]) found by the last forward pass."""

@@ -117,6 +117,7 @@ T5aArgs t5a_args(Handle* h) {
         a.cc_level = h->cc_level; a.cc_psign = h->cc_psign; a.cc_t = h->d_cc_t; a.cc_n = h->d_cc_n;
         for (int j = 0; j < 4; j++) { a.cc_scale[j] = h->cc_scale[j]; a.cc_shift[j] = h->cc_shift[j]; }
         a.cc_lparam = h->cc_lparam; a.cc_lcoef = h->cc_lcoef; a.cc_acomp = h->cc_acomp; a.cc_aparam = h->cc_aparam; a.cc_acoef = h->cc_acoef;
+        a.cc_qcomp = h->cc_qcomp; a.cc_qcoef = h->cc_qcoef;
     }
     return a;
 }
@@ -631,13 +632,14 @@ int32_t b200adj_set_continuous_callback(void* handle, int32_t enabled, int32_t i
     CUDA_TRY(h, cudaMemsetAsync(h->d_cc_n, 0, (size_t)c.N * sizeof(int32_t), h->stream));
     h->cc_on = true; h->cc_idx = idx; h->cc_dir = direction; h->cc_pcomp = pcomp < 0 ? -1 : pcomp; h->cc_pparam = pcomp < 0 ? 0 : pparam;
     h->cc_maxev = max_events; h->cc_level = level; h->cc_psign = psign;
-    h->cc_lparam = -1; h->cc_lcoef = 0; h->cc_acomp = -1; h->cc_aparam = 0; h->cc_acoef = 0;      // set_continuous_callback_params adds them
+    h->cc_lparam = -1; h->cc_lcoef = 0; h->cc_acomp = -1; h->cc_aparam = 0; h->cc_acoef = 0; h->cc_qcomp = -1; h->cc_qcoef = 1;   // set_continuous_callback_params adds them
     for (int j = 0; j < 4; j++) { h->cc_scale[j] = (scale && j < c.d) ? scale[j] : 1.0; h->cc_shift[j] = (shift && j < c.d) ? shift[j] : 0.0; }
     h->have_forward = false;
     return B200ADJ_OK;
 }
 
-int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, double lcoef, int32_t acomp, int32_t aparam, double acoef) {
+int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, double lcoef, int32_t acomp, int32_t aparam, double acoef,
+                                               int32_t qcomp, double qcoef) {
     if (!handle) return B200ADJ_ERR_INVALID;
     Handle* h = (Handle*)handle;
     const b200adj_cfg& c = h->cfg;
@@ -645,10 +647,13 @@ int32_t b200adj_set_continuous_callback_params(void* handle, int32_t lparam, dou
     if (lparam >= c.P || (acomp >= 0 && (acomp >= c.d || aparam < 0 || aparam >= c.P)) || !std::isfinite(lcoef) || !std::isfinite(acoef)) {
         h->err = "continuous callback parameters: bad lparam / acomp / aparam"; return B200ADJ_ERR_INVALID; }
     if (acomp >= 0 && acomp == h->cc_pcomp) { h->err = "continuous callback parameters: acomp is the component the parameter-scaled affect overwrites"; return B200ADJ_ERR_INVALID; }
+    if (qcomp >= c.d || !std::isfinite(qcoef) || (qcomp >= 0 && (qcomp == h->cc_pcomp || qcomp == acomp))) {
+        h->err = "continuous callback parameters: bad qcomp (a component no other part of the affect writes)"; return B200ADJ_ERR_INVALID; }
     CUDA_TRY(h, cudaSetDevice(c.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->cc_lparam = lparam < 0 ? -1 : lparam; h->cc_lcoef = lparam < 0 ? 0.0 : lcoef;
     h->cc_acomp = acomp < 0 ? -1 : acomp; h->cc_aparam = acomp < 0 ? 0 : aparam; h->cc_acoef = acomp < 0 ? 0.0 : acoef;
+    h->cc_qcomp = qcomp < 0 ? -1 : qcomp; h->cc_qcoef = qcomp < 0 ? 1.0 : qcoef;
     h->have_forward = false;
     return B200ADJ_OK;
 }

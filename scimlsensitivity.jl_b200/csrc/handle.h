@@ -74,7 +74,7 @@ struct Handle {
     // state-dependent event (b200adj_set_continuous_callback): per-member event lists cc_t[cc_maxev][N], cc_n[N]
     bool cc_on = false; int cc_idx = 0, cc_dir = 0, cc_pcomp = -1, cc_pparam = 0, cc_maxev = 0;
     double cc_level = 0, cc_psign = 1, cc_scale[4] = {1, 1, 1, 1}, cc_shift[4] = {0, 0, 0, 0};
-    int cc_lparam = -1, cc_acomp = -1, cc_aparam = 0; double cc_lcoef = 0, cc_acoef = 0;      // b200adj_set_continuous_callback_params
+    int cc_lparam = -1, cc_acomp = -1, cc_aparam = 0, cc_qcomp = -1; double cc_lcoef = 0, cc_acoef = 0, cc_qcoef = 1;      // b200adj_set_continuous_callback_params
     double* d_cc_t = nullptr; int32_t* d_cc_n = nullptr;
     int rev_block = 0; const void* rev_block_kernel = nullptr;      // adaptive Tsit5 reverse kernel: block size chosen per instantiation (disp_t5a.inc)
     bool have_forward = false;

@@ -44,7 +44,8 @@ struct T5aArgs {
     double* cc_t; int32_t* cc_n;
     // parameter-dependent condition / additive parameter affect (test/Callbacks2/continuous_callbacks.jl:317-345): the level is
     // cc_level + cc_lcoef * p[cc_lparam] (cc_lparam < 0: none); u[cc_acomp] += cc_acoef * p[cc_aparam] after the affine part
-    int32_t cc_lparam, cc_acomp, cc_aparam, cc_pad_; double cc_lcoef, cc_acoef;
+    // and the non-linear affect u[cc_qcomp] <- cc_qcoef * u[cc_qcomp]^2 (:222-250) in place of that component's affine map
+    int32_t cc_lparam, cc_acomp, cc_aparam, cc_qcomp; double cc_lcoef, cc_acoef, cc_qcoef;
     double A[7][6];         // Tsit5 tableau (row 6 = b)
     double C[7];
     double BT[7];           // embedded error weights b - bhat
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                     double sc[D], sh[D];
                     t5_cc_affect<D, P>(a, p, sc, sh);
 #pragma unroll
-                    for (int j = 0; j < D; j++) un[j] = sc[j] * un[j] + sh[j];
+                    for (int j = 0; j < D; j++) un[j] = (j == a.cc_qcomp) ? a.cc_qcoef * un[j] * un[j] : sc[j] * un[j] + sh[j];
                     after_event = true;
                 } else {
 #pragma unroll
@@ -504,6 +505,10 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
                 sol.eval(tau, false, um); sol.eval(tau, true, up);
                 Fam::f(um, p, fm); Fam::f(up, p, fp);
                 t5_cc_affect<D, P>(a, p, sc, sh);
+                if (a.cc_qcomp >= 0) {       // u_q <- qcoef u_q^2: the Jacobian 2 qcoef u_q- takes the place of the scale
+#pragma unroll
+                    for (int j = 0; j < D; j++) if (j == a.cc_qcomp) sc[j] = 2.0 * a.cc_qcoef * um[j];
+                }
                 double wl = 0.0;
 #pragma unroll
                 for (int j = 0; j < D; j++) wl += (sc[j] * fm[j] - fp[j]) * z[j];

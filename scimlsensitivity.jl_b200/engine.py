@@ -164,9 +164,10 @@ class DeviceEnsemble:
                 raise ValueError(f"ContinuousCallback: {name} must have d entries")
         self.handle.set_continuous_callback(cb.idx, cb.level, cb.direction, cb.scale, cb.shift, -1 if cb.p_comp is None else cb.p_comp,
                                             cb.p_param, cb.p_sign, cb.max_events)
-        if cb.level_param is not None or cb.add_comp is not None:
+        if cb.level_param is not None or cb.add_comp is not None or cb.sq_comp is not None:
             self.handle.set_continuous_callback_params(-1 if cb.level_param is None else cb.level_param, cb.level_coef,
-                                                       -1 if cb.add_comp is None else cb.add_comp, cb.add_param, cb.add_coef)
+                                                       -1 if cb.add_comp is None else cb.add_comp, cb.add_param, cb.add_coef,
+                                                       -1 if cb.sq_comp is None else cb.sq_comp, cb.sq_coef)
         self.continuous_callback = cb
 
     def event_times(self):

@@ -169,7 +169,8 @@ class ContinuousCallback:
     A parameter-dependent level and an additive parameter affect are part of the family: level + level_coef * p[level_param]
     and u[add_comp] += add_coef * p[add_param] -- "condition = u[1] - 3//4 * p[1]; affect! = u[1] += p[2]"
     (test/Callbacks2/continuous_callbacks.jl:317-345) is ContinuousCallback(idx=0, direction=0, level_param=0, level_coef=0.75,
-    add_comp=0, add_param=1, add_coef=1.0).
+    add_comp=0, add_param=1, add_coef=1.0).  The non-linear affect of the reference's tests, "integrator.u[2] = integrator.u[2]^2"
+    (:222-250), is sq_comp=1 (u[sq_comp] <- sq_coef * u[sq_comp]^2 in place of that component's affine map).
     The bouncing ball "integrator.u[2] = -integrator.p[2] * integrator.u[2]" when u[1] crosses 0 downwards is
     ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0).  Indices are 0-based.
     save_positions = (false, false) only; every ensemble member finds its own event times on the device."""
@@ -188,12 +189,14 @@ class ContinuousCallback:
     add_comp: Optional[int] = None
     add_param: int = 0
     add_coef: float = 0.0
+    sq_comp: Optional[int] = None
+    sq_coef: float = 1.0
 
     def key(self):
         sc = None if self.scale is None else np.asarray(self.scale, dtype=np.float64).tobytes()
         sh = None if self.shift is None else np.asarray(self.shift, dtype=np.float64).tobytes()
         return ("cc", self.idx, self.level, self.direction, sc, sh, self.p_comp, self.p_param, self.p_sign, self.max_events,
-                self.level_param, self.level_coef, self.add_comp, self.add_param, self.add_coef)
+                self.level_param, self.level_coef, self.add_comp, self.add_param, self.add_coef, self.sq_comp, self.sq_coef)
 
 
 def saveat_to_times(saveat, tspan):

@@ -108,6 +108,33 @@ def test_level_crossing_affine_affect_lv_vs_oracle():
         assert _rel(du0, ref["du0"]) < 1e-6 and _rel(dp, ref["dp"]) < 1e-6, sa
 
 
+@pytest.mark.parametrize("shared_p", [True, False])
+@pytest.mark.parametrize("sa", ["interpolating", "gauss", "gauss_kronrod", "backsolve"])
+def test_non_linear_affect_of_the_reference_tests_vs_oracle(sa, shared_p):
+    """"u[1] += 3; u[2] = u[2]^2" at the impact, MSE loss sum((1 - u)^2) / 2 at saveat 0.5 (test/Callbacks2/continuous_callbacks.jl:
+    240-251; tolerances 1e-12, :6-8): the Jacobian of the quadratic affect takes the place of the affine scale in the reverse
+    kernel.  Members start from their own heights, so the impacts happen at their own times."""
+    N = 40
+    rng = np.random.default_rng(21)
+    u0 = np.stack([5.0 + rng.random(N), 0.2 * rng.standard_normal(N)])
+    p = np.array([9.8, 0.8]) if shared_p else np.stack([9.8 + 0.2 * rng.standard_normal(N), np.full(N, 0.8)])
+    ts = np.arange(0.0, 2.5 + 1e-9, 0.5)
+    kw = dict(abstol=1e-12, reltol=1e-12)
+    cb = b.ContinuousCallback(idx=0, direction=-1, shift=[3.0, 0.0], sq_comp=1, sq_coef=1.0, max_events=8)
+    eng = b.DeviceEnsemble("ball", sa, "tsit5_adaptive", N, ts, (0.0, 2.5), 0.0, cost=b.AffineCost(1.0, -1.0), shared_p=shared_p,
+                           ckpt_every_step=True, **kw)
+    eng.set_continuous_callback(cb)
+    saved, status = eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    counts, times = eng.event_times()
+    cfg = O.make_cfg("ball", sa, "tsit5_adaptive", N, ts, 0.0, 2.5, cost=("affine", 1.0, -1.0), shared_p=shared_p, ckpt_every_step=True,
+                     crossing=dict(idx=0, direction=-1, shift=[3.0, 0.0], qcomp=1, qcoef=1.0), **kw)
+    ref = O.gradient(cfg, ts, u0, p)
+    assert (np.asarray(status) == 0).all() and (counts == 1).all()
+    assert _rel(saved, ref["saved"]) < 1e-9
+    assert _rel(du0, ref["du0"]) < 1e-7 and _rel(dp, ref["dp"]) < 1e-7
+
+
 def test_public_api_bouncing_ball_vs_finite_differences():
     """solve(EnsembleProblem(ODEProblem(ball; callback = ContinuousCallback(...))), Tsit5(), EnsembleB200(); sensealg) and its
     pullback against central differences of the device's own loss (bouncing_ball.md differentiates the final position)."""

@@ -576,3 +576,24 @@ def test_continuous_callback_bouncing_ball_saltation_matches_finite_differences_
     assert abs(r["du0"][0, 0] - (xT(x0 + h, g, e) - xT(x0 - h, g, e)) / (2 * h)) < 1e-6
     assert abs(r["dp"][0] - (xT(x0, g + h, e) - xT(x0, g - h, e)) / (2 * h)) < 1e-6
     assert abs(r["dp"][1] - (xT(x0, g, e + h) - xT(x0, g, e - h)) / (2 * h)) < 1e-6
+
+
+def test_continuous_callback_non_linear_affect_matches_finite_differences():
+    """The reference's non-linear affects (test/Callbacks2/continuous_callbacks.jl:222-250): "u[2] = u[2]^2" on the bouncing
+    ball with the loss sum(sol), and "u[1] += 3; u[2] = u[2]^2" with the MSE loss sum((1 - u)^2) / 2; u0 = [5, 0], tspan (0, 2.5),
+    p = [9.8, 0.8], saveat 0.5, tolerances 1e-12 (:6-8, :21-25).  Every sensealg against differences of the hybrid solve; the
+    reference asks rtol 1e-5 against ForwardDiff (:82-87)."""
+    ts = np.arange(0.0, 2.5 + 1e-9, 0.5)
+    u0 = np.array([[5.0], [0.0]]); p = np.array([9.8, 0.8])
+    cases = ((dict(idx=0, direction=-1, qcomp=1, qcoef=1.0), ("affine", 0.0, 1.0)),
+             (dict(idx=0, direction=-1, shift=[3.0, 0.0], qcomp=1, qcoef=1.0), ("affine", 1.0, -1.0)))
+    for cr, cost in cases:
+        for sa in ("interpolating", "gauss", "gauss_kronrod", "backsolve"):
+            cfg = O.make_cfg("ball", sa, "tsit5_adaptive", 1, ts, 0.0, 2.5, abstol=1e-12, reltol=1e-12, cost=cost, crossing=cr, ckpt_every_step=True)
+            r = O.gradient(cfg, ts, u0, p)
+            gp = _fd_grad(lambda q: O.loss(cfg, ts, u0, q)[0], p, h=1e-5)
+            gu = _fd_grad(lambda u: O.loss(cfg, ts, u, p)[0], u0, h=1e-5)
+            assert np.allclose(r["dp"], gp, rtol=1e-7, atol=1e-9), (sa, r["dp"], gp)
+            assert np.allclose(r["du0"].ravel(), gu.ravel(), rtol=1e-7), (sa, r["du0"].ravel(), gu.ravel())
+    t, um, up = O.event_list(cfg, [5.0, 0.0], p)
+    assert len(t) == 1 and abs(t[0] - np.sqrt(10.0 / 9.8)) < 1e-12 and abs(up[0, 1] - um[0, 1] ** 2) < 1e-10 and abs(up[0, 0] - 3.0) < 1e-12
