@@ -563,8 +563,11 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
     const b200adj_cfg& c = h->cfg;
     if (E < 0 || (E > 0 && (!times || !scale || !shift)) || ((pscale == nullptr) != (pshift == nullptr))) { h->err = "set_events: bad arguments"; return B200ADJ_ERR_INVALID; }
     if (E > 0 && h->cc_on) { h->err = "events: preset-time events together with a continuous callback are not built"; return B200ADJ_ERR_UNSUPPORTED; }
-    const bool fixed = c.stepper == B200ADJ_ST_TSIT5_FIXED && c.rhs_family != B200ADJ_FAM_MLP && c.dtype == B200ADJ_F64 && !h->fixed_dt;
-    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !fixed && !h->fixed_dt) { h->err = "events: built for the Tsit5 steppers (adaptive; fixed step in F64)"; return B200ADJ_ERR_UNSUPPORTED; }
+    // hybrid neural ODE (test/Core5/HybridNODE.jl): the MLP family's CUDA-core kernels (F64 / F32) carry state events on the dt grid
+    const bool mlp_ev = c.rhs_family == B200ADJ_FAM_MLP && !h->mlp_tc && c.stepper == B200ADJ_ST_TSIT5_FIXED;
+    const bool fixed = c.stepper == B200ADJ_ST_TSIT5_FIXED && !h->fixed_dt && ((c.rhs_family != B200ADJ_FAM_MLP && c.dtype == B200ADJ_F64) || mlp_ev);
+    if (E > 0 && c.stepper != B200ADJ_ST_TSIT5_ADAPTIVE && !fixed && !h->fixed_dt) { h->err = "events: built for the Tsit5 steppers (adaptive; fixed step in F64; MLP family: F64 / F32, not the bf16 tensor-core path)"; return B200ADJ_ERR_UNSUPPORTED; }
+    if (E > 0 && mlp_ev && pscale) { h->err = "events: parameter-changing affects are not built for the MLP family"; return B200ADJ_ERR_UNSUPPORTED; }
     if (E > 0 && fixed && h->ckpt_every > 1) { h->err = "events together with checkpoint_every > 1 are not built"; return B200ADJ_ERR_UNSUPPORTED; }
     std::vector<int32_t> eos;
     if (fixed) {

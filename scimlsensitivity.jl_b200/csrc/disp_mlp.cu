@@ -8,6 +8,7 @@ int mlp_forward_launch(Handle* h, const void* u0, const void* p, void* saved, in
     memset(&a, 0, sizeof(a));
     a.u0 = (const T*)u0; a.p = (const T*)p; a.ckpt = (T*)h->d_ckpt; a.saved = (T*)saved; a.save_of_step = h->d_fwd_save_of_step;
     a.status = status; a.N = h->cfg.N; a.S = h->S; a.tb = h->tb;
+    if (h->nev > 0) { a.event_of_step = h->d_event_of_step; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; }
     const size_t smem = sizeof(MlpSmem<T>);
     if (cudaFuncSetAttribute(mlp_forward_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA;
     mlp_forward_kernel<T><<<h->grid, MLP_THREADS, smem, h->stream>>>(a);
@@ -71,6 +72,7 @@ int mlp_reverse_launch(Handle* h, const void* dLdu, void* du0, void* dp) {
     for (int j = 0; j < 4; j++) { a.cost_a[j] = h->cost_av[j]; a.cost_b[j] = h->cost_bv[j]; } a.flags = (c.flags & B200ADJ_FLAG_NO_START) ? 1u : 0u;
     const size_t smem = sizeof(MlpSmem<T>);
     a.Npad = h->Npad;
+    if (h->nev > 0) { a.event_of_step = h->d_event_of_step; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; }
 #define B200_MLP_REV(COSTV, TAPEV)                                                                                          \
     do {                                                                                                                    \
         if (cudaFuncSetAttribute(mlp_reverse_kernel<T, COSTV, TAPEV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return B200ADJ_ERR_CUDA; \

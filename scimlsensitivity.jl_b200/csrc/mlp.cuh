@@ -32,6 +32,9 @@ template <class T> struct MlpArgs {
     void* tapeA; void* tapeB; int64_t Ktot, Npad;     // (superseded bf16 tape formulation: unused)
     float* kst;                                       // tensor-core path: forward stages k1..k7 per step, [S][7][2][N] (or null: recompute)
     Tsit5Tables tb;
+    // hybrid neural ODE (test/Core5/HybridNODE.jl:20-24, PresetTimeCallback on a neural RHS): preset-time events on the dt grid,
+    // event_of_step[n] = e when u <- ev_s[e] .* u + ev_c[e] fires at t_n (else -1); null = none.  CUDA-core kernels (F64 / F32).
+    const int32_t* event_of_step; const double* ev_s; const double* ev_c;
 };
 
 template <class T> __device__ __forceinline__ T tanh_t(T x);
@@ -217,6 +220,18 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_forward_kernel(const __grid_c
             if (own) { if (st < 6) s.kf[st][c][b] = s.F[c][b]; else { s.ulo[c][b] = s.y[c][b]; s.kf[0][c][b] = s.F[c][b]; } }
             __syncthreads();
         }
+        if (a.event_of_step) {
+            // preset-time event at t_{n+1}: the checkpoint and a coinciding save point record the POST-event state, the first
+            // stage of the next step is re-evaluated from it (same convention as tsit5_forward_kernel<..., EV>)
+            const int e = a.event_of_step[n + 1];
+            if (e >= 0 && n + 1 < a.S) {
+                if (own) { s.ulo[c][b] = (T)(a.ev_s[e * MLP_D + c] * (double)s.ulo[c][b] + a.ev_c[e * MLP_D + c]); s.y[c][b] = s.ulo[c][b]; }
+                __syncthreads();
+                mlp_forward<T>(s);
+                if (own) s.kf[0][c][b] = s.F[c][b];
+                __syncthreads();
+            }
+        }
         if (live) {
             a.ckpt[((int64_t)(n + 1) * MLP_D + c) * N + col] = s.ulo[c][b];
             if (a.saved) { int ks = a.save_of_step[n + 1]; if (ks >= 0) a.saved[((int64_t)ks * MLP_D + c) * N + col] = s.ulo[c][b]; }
@@ -259,6 +274,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
     mlp_forward<T>(s);                                          // f(u_S) = forward k7 of the last step
     if (own) s.kf[6][c][b] = s.F[c][b];
     __syncthreads();
+    bool need_left = false;     // the step above ended with an event at t_{n+1}: its right end is the LEFT limit, not the checkpoint
     for (int n = a.S - 1; n >= 0; n--) {
         if (own) { s.ulo[c][b] = a.ckpt[((int64_t)n * MLP_D + c) * N + col]; s.y[c][b] = s.ulo[c][b]; }
         __syncthreads();
@@ -277,6 +293,20 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
             mlp_forward<T>(s);
             if (own) s.kf[st][c][b] = s.F[c][b];
             __syncthreads();
+        }
+        if (need_left) {
+            // event at t_{n+1}: the adjoint step starts from the pre-event end state of this forward step, u- = u_n + h sum b_j k_j,
+            // and the dense output needs k7 = f(u-) (the checkpoint above holds the post-event state)
+            if (own) {
+                double acc = (double)s.ulo[c][b];
+                for (int j = 0; j < 6; j++) acc = fma(tb.hA[6][j], (double)s.kf[j][c][b], acc);
+                s.uhi[c][b] = (T)acc; s.y[c][b] = (T)acc;
+            }
+            __syncthreads();
+            mlp_forward<T>(s);
+            if (own) s.kf[6][c][b] = s.F[c][b];
+            __syncthreads();
+            need_left = false;
         }
         // ---- adjoint stages 0..5 (b7 = 0: the 7th stage carries no mu weight; GaussAdjoint needs its derivative for the
         //      dense output of the adjoint step, so it runs stage 6 as well) ----
@@ -323,6 +353,11 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_reverse_kernel(const __grid_c
         }
         { const int ks = a.save_of_step[n]; if (ks >= 0 && !((a.flags & 1u) && n == 0)) cotangent(ks, s.ulo); }
         if (own) { s.uhi[c][b] = s.ulo[c][b]; s.kf[6][c][b] = s.kf[0][c][b]; }
+        if (a.event_of_step) {
+            // reverse affect of u+ = s .* u- + c at t_n, after the loss jump of the same time: lam- = s .* lam+
+            const int e = a.event_of_step[n];
+            if (e >= 0 && n > 0) { if (own) s.lam[c][b] = (T)(a.ev_s[e * MLP_D + c] * (double)s.lam[c][b]); need_left = true; }
+        }
         __syncthreads();
     }
     if (live) a.du0[(int64_t)c * N + col] = s.lam[c][b];

@@ -154,3 +154,48 @@ def test_fixed_step_events_through_the_public_api_per_member_parameters():
     cfg = O.make_cfg("lv", "interpolating", "tsit5_fixed", N, t, 0.0, 10.0, dt=0.01, cost=("affine", 0.0, 1.0), shared_p=False, events=CASES["mixed"])
     ref = O.gradient(cfg, t, u0, p)
     assert _rel(du0, ref["du0"]) < 1e-8 and _rel(dp, ref["dp"]) < 1e-8
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-8), ("f32", 5e-4)])
+@pytest.mark.parametrize("sa", ["interpolating", "gauss"])
+def test_hybrid_neural_ode_events_on_the_mlp_family(sa, dtype, tol):
+    """test/Core5/HybridNODE.jl:9-24: a neural RHS with an external kick "u[1] += 0.2 * cbinput[k]" at preset times.  The MLP
+    family's CUDA-core kernels (F64 / F32) carry the events on the dt grid; device vs oracle (fp64), which
+    tests/test_oracle_relations.py pins by finite differences through the hybrid solve."""
+    H, N = 64, 100
+    rng = np.random.default_rng(7)
+    p = np.concatenate([(rng.standard_normal((H, 2)) / np.sqrt(2)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                        (rng.standard_normal((H, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                        (rng.standard_normal((2, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(2)])
+    T, dt = 3.0, 0.05
+    ts = np.arange(0.25, T + 1e-9, 0.25)
+    et = np.arange(0.5, T - 1e-9, 0.5)
+    ev = (et, np.ones((len(et), 2)), np.stack([0.2 * rng.random(len(et)), np.zeros(len(et))], 1))
+    u0 = rng.uniform(-1, 1, (2, N))
+    eng = b.DeviceEnsemble("mlp", sa, "tsit5_fixed", N, ts, (0.0, T), dt, cost=b.AffineCost(1.0, -0.5), dtype=dtype)
+    eng.set_events(*ev)
+    saved, status = eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    cfg = O.make_cfg("mlp", sa, "tsit5_fixed", N, ts, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H, events=ev)
+    ref = O.gradient(cfg, ts, u0, p)
+    assert (np.asarray(status) == 0).all()
+    assert _rel(saved, ref["saved"]) < (1e-10 if dtype == "f64" else 5e-5)
+    assert _rel(du0, ref["du0"]) < tol and _rel(dp, ref["dp"]) < tol, (_rel(du0, ref["du0"]), _rel(dp, ref["dp"]))
+    # the kick is visible in the primal: without events the same handle gives a different trajectory
+    eng.set_events([], np.zeros((0, 2)), np.zeros((0, 2)))
+    saved0, _ = eng.forward(u0, p)
+    assert _rel(saved0, ref["saved"]) > 1e-3
+    eng.close()
+
+
+def test_mlp_events_refusals():
+    ts = np.array([0.5, 1.0])
+    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", 64, ts, (0.0, 1.0), 0.05, dtype="bf16_f32acc")
+    with pytest.raises(b.B200AdjError) as ei:        # the tensor-core path does not carry events
+        eng.set_events([0.5], [[1.0, 1.0]], [[0.1, 0.0]])
+    assert ei.value.code == -2
+    eng = b.DeviceEnsemble("mlp", "interpolating", "tsit5_fixed", 64, ts, (0.0, 1.0), 0.05)
+    with pytest.raises(b.B200AdjError):              # parameter-changing affects: not for the MLP family
+        eng.set_events([0.5], [[1.0, 1.0]], [[0.1, 0.0]], np.ones((1, 4482)), np.zeros((1, 4482)))
+    with pytest.raises(b.B200AdjError):              # off the dt grid
+        eng.set_events([0.52], [[1.0, 1.0]], [[0.1, 0.0]])

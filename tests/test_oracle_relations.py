@@ -597,3 +597,29 @@ def test_continuous_callback_non_linear_affect_matches_finite_differences():
             assert np.allclose(r["du0"].ravel(), gu.ravel(), rtol=1e-7), (sa, r["du0"].ravel(), gu.ravel())
     t, um, up = O.event_list(cfg, [5.0, 0.0], p)
     assert len(t) == 1 and abs(t[0] - np.sqrt(10.0 / 9.8)) < 1e-12 and abs(up[0, 1] - um[0, 1] ** 2) < 1e-10 and abs(up[0, 0] - 3.0) < 1e-12
+
+
+def test_hybrid_neural_ode_preset_time_events_match_finite_differences():
+    """Hybrid neural ODE of test/Core5/HybridNODE.jl:9-24: a neural RHS (here the 2 -> 64 -> 64 -> 2 tanh MLP family) whose first
+    component receives an external kick "u[1] += 0.2 * cbinput[k]" at preset times (PresetTimeCallback).  Fixed-step Tsit5 with the
+    event times on the dt grid; Interpolating / Gauss vs differences of the hybrid solve along a random parameter direction."""
+    H = 64
+    rng = np.random.default_rng(7)
+    p = np.concatenate([(rng.standard_normal((H, 2)) / np.sqrt(2)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                        (rng.standard_normal((H, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(H),
+                        (rng.standard_normal((2, H)) / np.sqrt(H)).ravel(order="F"), 0.1 * rng.standard_normal(2)])
+    T, dt = 3.0, 0.05
+    ts = np.arange(0.25, T + 1e-9, 0.25)
+    et = np.arange(0.5, T - 1e-9, 0.5)
+    ev = (et, np.ones((len(et), 2)), np.stack([0.2 * rng.random(len(et)), np.zeros(len(et))], 1))
+    u0 = rng.uniform(-1, 1, (2, 1))
+    v = rng.standard_normal(p.size); v /= np.linalg.norm(v)
+    for sa in ("interpolating", "gauss"):
+        cfg = O.make_cfg("mlp", sa, "tsit5_fixed", 1, ts, 0.0, T, dt=dt, cost=("affine", 1.0, -0.5), mlp_hidden=H, events=ev)
+        r = O.gradient(cfg, ts, u0, p)
+        h = 1e-5
+        L = lambda q: O.loss(cfg, ts, u0, q)[0]
+        fd = (-L(p + 2 * h * v) + 8 * L(p + h * v) - 8 * L(p - h * v) + L(p - 2 * h * v)) / (12 * h)
+        assert abs(r["dp"] @ v - fd) < 1e-7 * max(1.0, abs(fd)), (sa, r["dp"] @ v, fd)
+        gu = _fd_grad(lambda u: O.loss(cfg, ts, u, p)[0], u0, h=1e-5)
+        assert np.allclose(r["du0"].ravel(), gu.ravel(), rtol=1e-7), sa

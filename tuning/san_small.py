@@ -1,4 +1,4 @@
-"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck): WHAT = ode | mlp | adaptive | sde | r2."""
+"""Small end-to-end runs for compute-sanitizer (memcheck / racecheck): WHAT = ode | mlp | adaptive | sde | r2 | r3."""
 import sys, os, numpy as np
 sys.path.insert(0, ".")
 import scimlsensitivity_jl_b200 as b
@@ -55,6 +55,26 @@ elif what == "r2":         # round-2 kernels: SEG (checkpoint_every), EV (events
         e = b.DeviceEnsemble("ball", sa, "tsit5_adaptive", 70, tb, (0, 5.0), 0.0, cost=b.AffineCost(1.0, 0.0), abstol=1e-8, reltol=1e-8)
         e.set_continuous_callback(b.ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0, max_events=16))
         e.forward(ub, np.array([9.8, 0.8])); du0, dp = e.reverse(); print(what, "cc", sa, np.asarray(dp)); e.close()
+elif what == "r3":         # re-entry kernels: Relax (d = 1 TMA records) with a parameter-dependent condition, quadratic affect, MLP events
+    N = 70; tr = np.linspace(0.5, 4.0, 8)
+    cb = b.ContinuousCallback(idx=0, direction=0, level_param=0, level_coef=0.75, add_comp=0, add_param=1, add_coef=1.0, max_events=4)
+    for sa in ("interpolating", "gauss", "gauss_kronrod", "backsolve"):
+        for sp in (True, False):
+            pr = np.array([100.0, 50.0]) if sp else np.stack([100.0 + 5 * rng.random(N), 50.0 + rng.random(N)])
+            e = b.DeviceEnsemble("relax", sa, "tsit5_adaptive", N, tr, (0, 4.0), 0.0, cost=b.AffineCost(1.0, 0.0), shared_p=sp, abstol=1e-8, reltol=1e-8, ckpt_every_step=True)
+            e.set_continuous_callback(cb)
+            e.forward(40.0 * rng.random((1, N)), pr); du0, dp = e.reverse(); print(what, "relax", sa, sp, np.asarray(dp).ravel()[:2]); e.close()
+    ub = np.stack([5.0 + rng.random(N), np.zeros(N)]); tb = np.arange(0.0, 2.51, 0.5)
+    for sa in ("interpolating", "backsolve"):
+        e = b.DeviceEnsemble("ball", sa, "tsit5_adaptive", N, tb, (0, 2.5), 0.0, cost=b.AffineCost(1.0, -1.0), abstol=1e-8, reltol=1e-8)
+        e.set_continuous_callback(b.ContinuousCallback(idx=0, direction=-1, shift=[3.0, 0.0], sq_comp=1, sq_coef=1.0, max_events=8))
+        e.forward(ub, np.array([9.8, 0.8])); du0, dp = e.reverse(); print(what, "sq", sa, np.asarray(dp)); e.close()
+    pm = 0.3 * rng.standard_normal(4482); um = rng.uniform(-2, 2, (2, 130)); tm = np.linspace(0.05, 0.3, 6)
+    for dt_ in ("f32", "f64"):
+        for sa in ("interpolating", "gauss"):
+            e = b.DeviceEnsemble("mlp", sa, "tsit5_fixed", 130, tm, (0, 0.3), 0.05, dtype=dt_, cost=b.AffineCost(1.0, -0.5))
+            e.set_events([0.1, 0.2], [[1, 1], [1, 1]], [[0.1, 0], [0.05, 0]])
+            e.forward(um, pm); du0, dp = e.reverse(); print(what, "mlp-ev", dt_, sa, np.asarray(dp)[:3]); e.close()
 else:
     N = 200; t = np.linspace(0, 0.1, 11); u0 = np.ones((2, N)); p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
     for st in ("em", "euler_heun"):
