@@ -266,8 +266,8 @@ class Handle:
         import numpy as np
         t = np.ascontiguousarray(times, dtype=np.float64).reshape(-1)
         E = len(t)
-        sc = np.ascontiguousarray(scale, dtype=np.float64).reshape(E, -1)
-        sh = np.ascontiguousarray(shift, dtype=np.float64).reshape(E, -1)
+        sc = np.ascontiguousarray(scale, dtype=np.float64).reshape(E, -1) if E else None      # E = 0 removes the events
+        sh = np.ascontiguousarray(shift, dtype=np.float64).reshape(E, -1) if E else None
         ps = pc = None
         if pscale is not None and E:
             ps = np.ascontiguousarray(pscale, dtype=np.float64).reshape(E, -1)
