@@ -250,7 +250,7 @@ def spec_c4(dtype="bf16_f32acc"):
     return dict(name="C4 MLP 2->64->64->2 shared weights P=4482, InterpolatingAdjoint, Tsit5 fixed dt=0.05, T=1.5, 30 saves, bf16 tensor-core VJP",
                 family="mlp", sensealg="interpolating", stepper="tsit5_fixed", T=T, dt=dt, saveat=np.linspace(0.05, T, 30),
                 cost=(1.0, -0.5), dtype=dtype, shared_p=True, okw=dict(mlp_hidden=64), ekw={}, tol=2e-2 if dtype == "bf16_f32acc" else 1e-4,
-                inputs=lambda n, off: (np.random.default_rng(1000 + off).uniform(-2, 2, (2, n)), p), parity_members=128,
+                inputs=lambda n, off: (np.random.default_rng(1000 + off).uniform(-2, 2, (2, n)), p), parity_members=128, cpu_sample=512,
                 # 156 672 flop per member-step of the reverse pass (6 stages x (fwd + 2 VJP GEMM passes))
                 roofline=lambda n, S, rev_s, hbm, tf: {"bound": "tensor", "kernel": "mlp_tc_reverse_kernel", "achieved": 156672.0 * n * S / rev_s / 1e12,
                                                        "peak": tf, "unit": "TFLOP/s", "frac": 156672.0 * n * S / rev_s / 1e12 / tf,
@@ -263,7 +263,7 @@ def spec_c5():
     return dict(name="C5 SDE-LV diag noise d=2 P=6, BacksolveAdjoint (Ito transformed drift), EM dt=0.01, T=1, saveat 0.01, Philox noise regenerated in reverse",
                 family="sde_lv", sensealg="backsolve", stepper="em", T=T, dt=dt, saveat=np.linspace(0.0, T, 101), cost=(0.0, 1.0),
                 dtype="f64", shared_p=True, okw={}, ekw=dict(seed=20260923), tol=1e-8,
-                inputs=lambda n, off: (np.ones((2, n)), p), parity_members=1024,
+                inputs=lambda n, off: (np.ones((2, n)), p), parity_members=1024, cpu_sample=131072,
                 # 176 B per member-step (z = [lam; mu; y] read+write, checkpoint reset read); compulsory: 16 B
                 roofline=lambda n, S, rev_s, hbm, tf: {"bound": "hbm", "kernel": "sde_backsolve_kernel", "achieved": 176.0 * n * S / rev_s / 1e9,
                                                        "peak": hbm, "unit": "GB/s", "frac": 176.0 * n * S / rev_s / 1e9 / hbm,
@@ -282,7 +282,7 @@ def spec_c1():
     return dict(name="C1-ensemble Lotka-Volterra d=2 P=4 shared p, InterpolatingAdjoint, adaptive Tsit5 (PI controller) tol 1e-8, T=10, saveat=0.1, loss=sum(sol)",
                 family="lv", sensealg="interpolating", stepper="tsit5_adaptive", T=T, dt=0.0, saveat=np.linspace(0.0, T, 101), cost=(0.0, 1.0),
                 dtype="f64", shared_p=True, okw=dict(tol), ekw=dict(max_steps=512, **tol), tol=1e-7,
-                inputs=lambda n, off: (np.exp(0.2 * np.random.default_rng(3000 + off).standard_normal((2, n))), p), parity_members=256,
+                inputs=lambda n, off: (np.exp(0.2 * np.random.default_rng(3000 + off).standard_normal((2, n))), p), parity_members=256, cpu_sample=16384,
                 # compulsory stream: one record per accepted forward step, read once by the reverse solve (TMA bulk copies)
                 roofline=lambda n, S, rev_s, hbm, tf: {"bound": "hbm", "kernel": "t5a_reverse_kernel<LotkaVolterra,INTERP>", "achieved": REC * 8.0 * n * S / rev_s / 1e9,
                                                        "peak": hbm, "unit": "GB/s", "frac": REC * 8.0 * n * S / rev_s / 1e9 / hbm,
@@ -304,7 +304,7 @@ def spec_c3():
     return dict(name="C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves",
                 family="robertson", sensealg="quadrature", stepper="rosenbrock23", T=T, dt=0.0, saveat=saveat, cost=(1.0, 0.0),
                 dtype="f64", shared_p=False, okw=dict(tol), ekw=dict(max_steps=8192, **tol), tol=1e-5,
-                inputs=inputs, parity_members=256,
+                inputs=inputs, parity_members=256, cpu_sample=2048,
                 roofline=lambda n, S, rev_s, hbm, tf: {"bound": "hbm", "kernel": "ros23_quadrature_kernel<Robertson> + ros23_reverse_kernel<Robertson,QUAD>",
                                                        "achieved": (FWD + REV) * 8.0 * n * S / rev_s / 1e9, "peak": hbm, "unit": "GB/s",
                                                        "frac": (FWD + REV) * 8.0 * n * S / rev_s / 1e9 / hbm,
@@ -418,6 +418,25 @@ def parity_pass(spec, rank, world, local, threads):
             "against": against}
 
 
+def cpu_leg_baseline(spec, threads):
+    """The C oracle (port of the reference algorithm) on the host cores, on spec['cpu_sample'] members of the same workload."""
+    from oracle import oracle as O
+    n = spec["cpu_sample"]
+    shared = spec.get("shared_p", True)
+    u0, p = spec["inputs"](n, 0)
+    cfg = O.make_cfg(spec["family"], spec["sensealg"], spec["stepper"], n, spec["saveat"], 0.0, spec["T"], dt=spec["dt"],
+                     cost=("affine",) + tuple(spec["cost"]), shared_p=shared, **spec["okw"])
+    dW = None
+    if spec["stepper"] in ("em", "euler_heun"):        # timing only: any increments of the right law
+        S = int(round(spec["T"] / spec["dt"]))
+        dW = np.sqrt(spec["dt"]) * np.random.default_rng(1).standard_normal((S, 2, n))
+    t0 = time.perf_counter()
+    O.gradient(cfg, spec["saveat"], u0, p, dW=dW, want_saved=False, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "trajectories/s", "cores": threads, "kind": "port",
+            "sample": f"{n} members of the same workload, one gradient, {dt:.2f} s wall"}
+
+
 def secondary_leg(spec, n_total, rank, world, local, steps, warmup, barrier, threads, with_parity=True):
     import torch
     hbm, tf, _ = peaks()
@@ -439,6 +458,7 @@ def secondary_leg(spec, n_total, rank, world, local, steps, warmup, barrier, thr
            "roofline": spec["roofline"](n_local, S, rev * 1e-3, hbm, tf)}
     if par is not None:
         out["parity"] = par
+        out["cpu_baseline"] = cpu_leg_baseline(spec, threads)
     return out
 
 
@@ -673,7 +693,7 @@ def run_secondary(args):
         eng = b.DeviceEnsemble("robertson", "quadrature", "rosenbrock23", N, saveat, (0.0, T), 0.0, shared_p=False, on_device=True,
                                cost=b.AffineCost(1.0, 0.0), max_steps=8192, **kw)
         ocfg = lambda n: O.make_cfg("robertson", "quadrature", "rosenbrock23", n, saveat, 0.0, T, cost=("affine", 1.0, 0.0), shared_p=False, **kw)
-        name, dtype, sample = "C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves", "f64", 256
+        name, dtype, sample = "C3 Robertson d=3 P=3 per-member k, QuadratureAdjoint(1e-10), Rosenbrock23 adaptive tol 1e-8, T=100, 10 log-spaced saves", "f64", 2048
     elif w == "c1":
         # BASELINE configs[0] (Lotka-Volterra, InterpolatingAdjoint, ADAPTIVE Tsit5 -- the reference's own CPU-runnable case,
         # test/Core1/concrete_solve_derivatives.jl:106-157) as an ensemble: every member runs its own PI-controlled step sequence
@@ -715,7 +735,7 @@ def run_secondary(args):
         u0 = np.ones((2, N)); p = np.array([1.5, 1.0, 3.0, 1.0, 0.1, 0.1])
         eng = b.DeviceEnsemble("sde_lv", "backsolve", "em", N, saveat, (0.0, T), dt, on_device=True, cost=b.AffineCost(0.0, 1.0), seed=20260923)
         ocfg = lambda n: O.make_cfg("sde_lv", "backsolve", "em", n, saveat, 0.0, T, dt=dt, cost=("affine", 0.0, 1.0))
-        name, dtype, sample = "C5 SDE-LV diag noise d=2 P=6, BacksolveAdjoint (Ito transformed drift), EM dt=0.01, T=1, saveat 0.01, Philox noise regenerated", "f64", 8192
+        name, dtype, sample = "C5 SDE-LV diag noise d=2 P=6, BacksolveAdjoint (Ito transformed drift), EM dt=0.01, T=1, saveat 0.01, Philox noise regenerated", "f64", 131072
     td = torch.float64 if dtype == "f64" else torch.float32
     u0_d = torch.tensor(u0, device="cuda", dtype=td); p_d = torch.tensor(p, device="cuda", dtype=td)
     du0_d = torch.empty(u0.shape, dtype=td, device="cuda"); dp_d = torch.empty(p.shape, dtype=td, device="cuda")
