@@ -178,6 +178,14 @@ int32_t b200adj_set_cost_family(void* handle, int32_t which, const double* a, co
 int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const double* scale, const double* shift,
                            const double* pscale, const double* pshift);
 
+/* Affect that ADDS A PARAMETER to a state at the preset times above (the reference's "Dosing example",
+ * test/Callbacks1/discrete_callbacks.jl:401-427: affect(integrator) = integrator.u[1] += integrator.p[2]): after the affine
+ * part of event e, u[comp[e]] += coef[e] * p[param[e]] with the parameters in force before the event (comp[e] < 0: none for
+ * that event).  Reverse pass: dG/dp[param[e]] += coef[e] * lam(t_e+)[comp[e]].  Host arrays of length E (the E of the last
+ * b200adj_set_events, which also resets this); comp = NULL removes the shifts.  Built on the per-member dense framework
+ * (adaptive Tsit5; fixed-step Tsit5 with B200ADJ_FLAG_DENSE_FORWARD). */
+int32_t b200adj_set_event_param_shift(void* handle, const int32_t* comp, const int32_t* param, const double* coef);
+
 /* State-dependent event of the hybrid system (ContinuousCallback of the reference; reverse-pass treatment with the implicit
  * event-time correction of src/callback_tracking.jl:232-480; docs/src/examples/hybrid_jump/bouncing_ball.md,
  * test/Callbacks1/continuous_callbacks.jl): condition(u) = u[idx] - level, fired when it crosses zero in `direction`

@@ -34,13 +34,18 @@ The callback family the device path carries: at each `tstops[e]` the affect is `
 optionally, `p .= pscale[:, e] .* p .+ pshift[:, e]` (`save_positions = (false, false)`; adaptive Tsit5, or fixed-step Tsit5
 with the event times on the dt grid).  A plain marker object: passed as `callback =` to `solve(...; sensealg =
 B200Adjoint(...))` it is consumed by the method below; for the reference path build the equivalent
-`PresetTimeCallback(tstops, affect!)`.
+`PresetTimeCallback(tstops, affect!)`.  `padd = (comp, param, coef)` (vectors of length E, 1-based indices, 0 = none) adds a
+parameter to a state at event e, `u[comp[e]] += coef[e] * p[param[e]]` -- the "Dosing example" `integrator.u[1] += integrator.p[2]`
+of test/Callbacks1/discrete_callbacks.jl:401-427 is `padd = ([1], [2], [1.0])` (adaptive Tsit5).
 """
 struct B200PresetAffine
     tstops::Vector{Float64}; scale::Matrix{Float64}; shift::Matrix{Float64}
     pscale::Union{Nothing, Matrix{Float64}}; pshift::Union{Nothing, Matrix{Float64}}
+    padd::Union{Nothing, Tuple{Vector{Int32}, Vector{Int32}, Vector{Float64}}}
 end
-B200PresetAffine(t, s, c; pscale = nothing, pshift = nothing) = B200PresetAffine(collect(Float64, t), s, c, pscale, pshift)
+B200PresetAffine(t, s, c; pscale = nothing, pshift = nothing, padd = nothing) =
+    B200PresetAffine(collect(Float64, t), s, c, pscale, pshift,
+                     padd === nothing ? nothing : (Int32.(padd[1]) .- Int32(1), max.(Int32.(padd[2]) .- Int32(1), Int32(0)), Float64.(padd[3])))
 
 """
     B200Crossing(idx, level = 0.0, direction = -1; scale = nothing, shift = nothing, pcomp = 0, pparam = 0, psign = 1.0, max_events = 64)
@@ -214,6 +219,11 @@ function b200_solve_adjoint(prob, alg, sensealg::B200Adjoint, U::AbstractMatrix{
             GC.@preserve events sc sh psm pcm check(s.h.ptr, ccall((:b200adj_set_events, libb200adj), Int32,
                 (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                 s.h.ptr, E, events.tstops, sc, sh, psm === nothing ? C_NULL : pointer(psm), pcm === nothing ? C_NULL : pointer(pcm)))
+            if events.padd !== nothing
+                pa = events.padd
+                GC.@preserve pa check(s.h.ptr, ccall((:b200adj_set_event_param_shift, libb200adj), Int32,
+                    (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}), s.h.ptr, pa[1], pa[2], pa[3]))
+            end
         end
     end
     if crossing !== nothing      # ContinuousCallback of the crossing family: each member finds its own event times in b200adj_forward

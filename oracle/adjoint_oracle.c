@@ -92,7 +92,13 @@ typedef struct {
      * u[cc_qcomp] <- cc_qcoef * u[cc_qcomp]^2 (cc_qcomp < 0: none) instead of the affine map of that component; the
      * reverse pass sees its Jacobian 2 cc_qcoef u-[cc_qcomp] as the event's scale */
     double cc_qcoef;
+    /* preset-time events whose affect ADDS A PARAMETER to a state ("Dosing example", test/Callbacks1/discrete_callbacks.jl:401-427:
+     * affect(integrator) = integrator.u[1] += integrator.p[2]): after the affine part, u[ev_acomp[e]] += ev_acoef[e] * p[ev_aparam[e]]
+     * with the parameters in force before the event (ev_acomp NULL or ev_acomp[e] < 0: none).  Reverse: dG/dp[aparam] += acoef lam+[acomp]. */
+    const int32_t *ev_acomp, *ev_aparam;
+    const double* ev_acoef;
 } oracle_cfg;
+#define EV_PADD(c, e, un, pp) do { if ((c)->ev_acomp && (c)->ev_acomp[e] >= 0) (un)[(c)->ev_acomp[e]] += (c)->ev_acoef[e] * (pp)[(c)->ev_aparam[e]]; } while (0)
 #define CC_LEVEL(c, p) ((c)->cc_level + ((c)->cc_lparam >= 0 ? (c)->cc_lcoef * (p)[(c)->cc_lparam] : 0.0))
 #define COST_A(c, j) ((c)->cost_av ? (c)->cost_av[j] : (c)->cost_a)
 #define COST_B(c, j) ((c)->cost_bv ? (c)->cost_bv[j] : (c)->cost_b)
@@ -546,6 +552,7 @@ static void forward_tsit5_fixed(const family_t* F, const double* p, const double
         memcpy(k, k + 6 * d, sizeof(double) * d);  /* FSAL */
         if (at_ev) {
             for (int i = 0; i < d; i++) un[i] = evc->ev_scale[(size_t)ev * d + i] * un[i] + evc->ev_shift[(size_t)ev * d + i];
+            EV_PADD(evc, ev, un, c.p);
             ev++;
             if (evc->ev_pscale) event_params(evc, F->P, ev, p, pcur);
             fwd_rhs(tn, un, k, &c);
@@ -607,6 +614,7 @@ static int forward_tsit5_adaptive(const family_t* F, const double* p, const doub
             if (last && ev < E) {
                 /* affect!: u <- scale .* u + shift; the next step starts from the post-event state, FSAL re-evaluated */
                 for (int i = 0; i < d; i++) un[i] = evc->ev_scale[(size_t)ev * d + i] * un[i] + evc->ev_shift[(size_t)ev * d + i];
+                EV_PADD(evc, ev, un, c.p);
                 ev++;
                 if (evc->ev_pscale) event_params(evc, F->P, ev, p, pcur);
                 fwd_rhs(t, un, k, &c);
@@ -1127,6 +1135,7 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
             if (sa == SA_BACKSOLVE) memcpy(z + d + P, um, sizeof(double) * d);                             \
             ctx.tev = (tt); evc--; fsal_ok = 0; continue;                                                  \
         }                                                                                                  \
+        const double ev_gadd = (cfg->ev_acomp && cfg->ev_acomp[evc] >= 0) ? cfg->ev_acoef[evc] * z[cfg->ev_acomp[evc]] : 0.0; /* (da/dp)'lam+ */ \
         for (int i = 0; i < d; i++) z[i] *= cfg->ev_scale[(size_t)evc * d + i];                            \
         if (sa == SA_BACKSOLVE) dense_eval(sol, cfg->ev_times[evc], 0, z + d + P, NULL);                   \
         if (p_events) {   /* p+ = s_p .* p- + c_p: dG/dp- = s_p .* dG/dp+ (+ what accumulates below tau with p-) */ \
@@ -1135,6 +1144,9 @@ static int adjoint_ode_member(const oracle_cfg* cfg, const family_t* F, const do
                 else acc[q] *= cfg->ev_pscale[(size_t)evc * P + q];                                        \
             }                                                                                              \
             event_params(cfg, P, evc, p_in, pcur);                                                         \
+        }                                                                                                  \
+        if (cfg->ev_acomp && cfg->ev_acomp[evc] >= 0) {    /* wrt the parameters in force before the event */ \
+            if (sa == SA_INTERPOLATING || sa == SA_BACKSOLVE) z[d + cfg->ev_aparam[evc]] += ev_gadd; else acc[cfg->ev_aparam[evc]] += ev_gadd; \
         }                                                                                                  \
         ctx.tev = (tt); evc--; fsal_ok = 0;                                                                \
     }
@@ -1380,7 +1392,7 @@ int oracle_ensemble_gradient(const oracle_cfg* cfg, const double* saveat, const 
                 if (cfg->stepper != ST_TSIT5_ADAPTIVE) r = -12;
                 else r = forward_tsit5_adaptive_cc(&F, pm, um, cfg->t0, cfg->t1, cfg->abstol, cfg->reltol, cfg->dt, &sol, cfg, &found);
                 mcfg.n_events = found.n; mcfg.ev_times = found.t; mcfg.ev_scale = found.scale; mcfg.ev_shift = found.shift;
-                mcfg.ev_pscale = NULL; mcfg.ev_pshift = NULL;
+                mcfg.ev_pscale = NULL; mcfg.ev_pshift = NULL; mcfg.ev_acomp = NULL;
             } else
             r = forward_dense_member(cfg, &F, pm, um, &sol);
             const oracle_cfg* cfg_m = &mcfg;

@@ -40,6 +40,7 @@ class OracleCfg(C.Structure):
         ("cc_level", C.c_double), ("cc_psign", C.c_double), ("cc_scale", C.c_void_p), ("cc_shift", C.c_void_p),
         ("cc_lparam", C.c_int32), ("cc_acomp", C.c_int32), ("cc_aparam", C.c_int32), ("cc_qcomp", C.c_int32),
         ("cc_lcoef", C.c_double), ("cc_acoef", C.c_double), ("cc_qcoef", C.c_double),
+        ("ev_acomp", C.c_void_p), ("ev_aparam", C.c_void_p), ("ev_acoef", C.c_void_p),
     ]
 
 
@@ -69,7 +70,7 @@ def _ptr(a):
 
 def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, reltol=1e-3, quad_abstol=1e-10,
              quad_reltol=1e-10, cost=("explicit",), shared_p=True, no_start=False, checkpointing=True,
-             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None, cost_vec=None, cont_vec=None, crossing=None):
+             ckpt_every_step=False, d=None, P=None, mlp_hidden=0, cont_cost=None, events=None, cost_vec=None, cont_vec=None, crossing=None, event_padd=None):
     if family == "mlp":
         d = 2
         H = mlp_hidden
@@ -130,6 +131,12 @@ def make_cfg(family, sensealg, stepper, N, saveat, t0, t1, dt=0.0, abstol=1e-6, 
             assert ps.shape == (len(et), P) and pc.shape == (len(et), P)
             cfg._keep += [ps, pc]
             cfg.ev_pscale, cfg.ev_pshift = ps.ctypes.data, pc.ctypes.data
+    if event_padd is not None:     # (comp[E], param[E], coef[E]): u[comp[e]] += coef[e] * p[param[e]] at event e (comp < 0: none)
+        ac, ak = (np.ascontiguousarray(x, dtype=np.int32) for x in event_padd[:2])
+        af = np.ascontiguousarray(event_padd[2], dtype=np.float64)
+        assert len(ac) == len(ak) == len(af) == cfg.n_events
+        cfg._keep_padd = [ac, ak, af]
+        cfg.ev_acomp, cfg.ev_aparam, cfg.ev_acoef = ac.ctypes.data, ak.ctypes.data, af.ctypes.data
     return cfg
 
 

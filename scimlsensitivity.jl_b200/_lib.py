@@ -21,7 +21,7 @@ COST = {"explicit": 0, "affine": 1}
 FLAG_NO_START, FLAG_NO_CHECKPOINTING, FLAG_CKPT_EVERY_STEP, FLAG_STORED_NOISE, FLAG_TRACE, FLAG_NO_ROTATE, FLAG_DENSE_FORWARD, FLAG_NCCL_ALLREDUCE = 1, 2, 4, 8, 16, 32, 64, 128
 ERR = {0: "OK", -1: "INVALID", -2: "UNSUPPORTED", -3: "NO_DEVICE", -4: "CUDA", -5: "STATE", -6: "OOM"}
 
-EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_register_family", "b200adj_family_info", "b200adj_set_events", "b200adj_set_continuous_callback", "b200adj_set_continuous_callback_params", "b200adj_event_times", "b200adj_get_noise", "b200adj_set_stream",
+EXPORTS = ["b200adj_create", "b200adj_forward", "b200adj_reverse", "b200adj_set_reverse_options", "b200adj_set_tolerances", "b200adj_set_continuous_cost", "b200adj_set_cost_family", "b200adj_register_family", "b200adj_family_info", "b200adj_set_events", "b200adj_set_event_param_shift", "b200adj_set_continuous_callback", "b200adj_set_continuous_callback_params", "b200adj_event_times", "b200adj_get_noise", "b200adj_set_stream",
            "b200adj_synchronize", "b200adj_launch_count", "b200adj_get_step_counts", "b200adj_get_block_trace", "b200adj_destroy",
            "b200adj_last_error", "b200adj_version", "b200adj_sizeof_cfg",
            "b200adj_comm_unique_id", "b200adj_comm_init", "b200adj_comm_init_all", "b200adj_comm_allreduce", "b200adj_comm_size", "b200adj_comm_is_fused"]
@@ -144,6 +144,8 @@ def load():
         lib.b200adj_set_continuous_callback.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_void_p, C.c_void_p,
                                                         C.c_int32, C.c_int32, C.c_double, C.c_int32]
         lib.b200adj_set_continuous_callback.restype = C.c_int32
+        lib.b200adj_set_event_param_shift.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.b200adj_set_event_param_shift.restype = C.c_int32
         lib.b200adj_set_continuous_callback_params.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, C.c_int32, C.c_double, C.c_int32, C.c_double]
         lib.b200adj_set_continuous_callback_params.restype = C.c_int32
         lib.b200adj_event_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -275,6 +277,17 @@ class Handle:
         self._check(self._lib.b200adj_set_events(self._h, E, t.ctypes.data if E else None, sc.ctypes.data if E else None,
                                                  sh.ctypes.data if E else None, None if ps is None else ps.ctypes.data,
                                                  None if pc is None else pc.ctypes.data))
+
+    def set_event_param_shift(self, comp, param, coef):
+        """u[comp[e]] += coef[e] * p[param[e]] at preset event e (after set_events; comp = None removes)."""
+        import numpy as np
+        if comp is None:
+            self._check(self._lib.b200adj_set_event_param_shift(self._h, None, None, None))
+            return
+        ac = np.ascontiguousarray(comp, dtype=np.int32).reshape(-1)
+        ak = np.ascontiguousarray(param, dtype=np.int32).reshape(-1)
+        af = np.ascontiguousarray(coef, dtype=np.float64).reshape(-1)
+        self._check(self._lib.b200adj_set_event_param_shift(self._h, ac.ctypes.data, ak.ctypes.data, af.ctypes.data))
 
     def set_continuous_callback(self, idx, level=0.0, direction=-1, scale=None, shift=None, pcomp=-1, pparam=0, psign=1.0,
                                 max_events=64, enabled=True):

@@ -152,9 +152,11 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
     stored = getattr(sensealg, "stored_noise", False) if isinstance(sensealg, B200Adjoint) else False
     ckpt_every = getattr(sensealg, "checkpoint_every", 1) if isinstance(sensealg, B200Adjoint) else 1
     ev = callback.tables(d, P) if callback is not None else None
+    evp = callback.param_shift() if callback is not None else None
     key = (prob.f, alg.code, hi - lo, ts.tobytes(), tuple(prob.tspan), _step_size(alg, kwargs), shared_p, on_device, device,
            getattr(prob, "seed", 0), lo, block, stored, ckpt_every, kwargs.get("abstol", 1e-6), kwargs.get("reltol", 1e-3),
-           None if ev is None else tuple(x.tobytes() for x in ev), None if ccb is None else ccb.key())
+           None if ev is None else tuple(x.tobytes() for x in ev), None if evp is None else tuple(x.tobytes() for x in evp),
+           None if ccb is None else ccb.key())
     eng = _HANDLE_CACHE.get(key) if ensemblealg.reuse_handle else None
     if eng is None:
         eng = DeviceEnsemble(prob.f, sensealg_name(inner), alg.code, hi - lo, ts, prob.tspan, _step_size(alg, kwargs),
@@ -166,6 +168,8 @@ def solve(eprob, alg, ensemblealg=None, *, trajectories=None, saveat=None, sense
                              checkpoint_every=ckpt_every)
         if ev is not None:
             eng.set_events(*ev)
+            if evp is not None:
+                eng.set_event_param_shift(*evp)
         if ccb is not None:
             eng.set_continuous_callback(ccb)
         if world > 1 and shared_p:

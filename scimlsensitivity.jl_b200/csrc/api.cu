@@ -112,6 +112,7 @@ T5aArgs t5a_args(Handle* h) {
     if (h->fixed_dt) a.flags |= 16u;          // constant step, no error control (fixed-step Tsit5 on the dense framework)
     if (h->cont_on) { a.flags |= 8u; for (int j = 0; j < 4; j++) { a.cont_a[j] = h->cont_av[j]; a.cont_b[j] = h->cont_bv[j]; } }
     a.nev = h->nev; a.ev_t = h->d_ev_t; a.ev_s = h->d_ev_s; a.ev_c = h->d_ev_c; a.ev_ps = h->d_ev_ps; a.ev_pc = h->d_ev_pc;
+    a.ev_ac = h->d_ev_ac; a.ev_ak = h->d_ev_ak; a.ev_af = h->d_ev_af;
     if (h->cc_on) {
         a.cc_on = 1; a.cc_idx = h->cc_idx; a.cc_dir = h->cc_dir; a.cc_pcomp = h->cc_pcomp; a.cc_pparam = h->cc_pparam; a.cc_maxev = h->cc_maxev;
         a.cc_level = h->cc_level; a.cc_psign = h->cc_psign; a.cc_t = h->d_cc_t; a.cc_n = h->d_cc_n;
@@ -143,7 +144,7 @@ void free_all(Handle* h) {
     cudaFree(h->d_kst); cudaFree(h->d_adj_dense); cudaFree(h->d_trace); cudaFree(h->d_ckpt); cudaFree(h->d_noise); cudaFree(h->d_partials); cudaFree(h->d_ticket); cudaFree(h->d_save_of_step); cudaFree(h->d_fwd_save_of_step); cudaFree(h->d_fwd_saveat);
     cudaFree(h->s_u0); cudaFree(h->s_p); cudaFree(h->s_saved); cudaFree(h->s_dLdu); cudaFree(h->s_du0); cudaFree(h->s_dp); cudaFree(h->s_dW);
     cudaFree(h->d_cc_t); cudaFree(h->d_cc_n);
-    cudaFree(h->s_status); cudaFree(h->d_event_of_step); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
+    cudaFree(h->s_status); cudaFree(h->d_event_of_step); cudaFree(h->d_ev_ac); cudaFree(h->d_ev_ak); cudaFree(h->d_ev_af); cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
 }
 
@@ -586,6 +587,7 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
     CUDA_TRY(h, cudaSetDevice(c.device));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     cudaFree(h->d_ev_t); cudaFree(h->d_ev_s); cudaFree(h->d_ev_c); cudaFree(h->d_ev_ps); cudaFree(h->d_ev_pc);
+    cudaFree(h->d_ev_ac); cudaFree(h->d_ev_ak); cudaFree(h->d_ev_af); h->d_ev_ac = h->d_ev_ak = nullptr; h->d_ev_af = nullptr;
     h->d_ev_t = h->d_ev_s = h->d_ev_c = h->d_ev_ps = h->d_ev_pc = nullptr; h->nev = 0; h->have_forward = false;
     if (E > 0) {
         CUDA_TRY(h, cudaMalloc(&h->d_ev_t, (size_t)E * sizeof(double)));
@@ -606,6 +608,33 @@ int32_t b200adj_set_events(void* handle, int32_t E, const double* times, const d
         if (!h->d_event_of_step) CUDA_TRY(h, cudaMalloc(&h->d_event_of_step, ((size_t)h->S + 1) * sizeof(int32_t)));
         CUDA_TRY(h, cudaMemcpy(h->d_event_of_step, eos.data(), eos.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
     }
+    return B200ADJ_OK;
+}
+
+int32_t b200adj_set_event_param_shift(void* handle, const int32_t* comp, const int32_t* param, const double* coef) {
+    if (!handle) return B200ADJ_ERR_INVALID;
+    Handle* h = (Handle*)handle;
+    const b200adj_cfg& c = h->cfg;
+    if (h->nev <= 0) { h->err = "event parameter shift: call b200adj_set_events first"; return B200ADJ_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(c.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_ev_ac); cudaFree(h->d_ev_ak); cudaFree(h->d_ev_af); h->d_ev_ac = h->d_ev_ak = nullptr; h->d_ev_af = nullptr;
+    h->have_forward = false;
+    if (!comp) return B200ADJ_OK;                                      // removes the shifts
+    if (!param || !coef) { h->err = "event parameter shift: null argument"; return B200ADJ_ERR_INVALID; }
+    if (!(c.stepper == B200ADJ_ST_TSIT5_ADAPTIVE || h->fixed_dt)) {
+        h->err = "event parameter shift: built on the per-member dense framework (adaptive Tsit5, or fixed step with B200ADJ_FLAG_DENSE_FORWARD)";
+        return B200ADJ_ERR_UNSUPPORTED; }
+    for (int e = 0; e < h->nev; e++)
+        if (comp[e] >= c.d || (comp[e] >= 0 && (param[e] < 0 || param[e] >= c.P || !std::isfinite(coef[e])))) {
+            h->err = "event parameter shift: bad component / parameter index"; return B200ADJ_ERR_INVALID; }
+    const size_t E = (size_t)h->nev;
+    CUDA_TRY(h, cudaMalloc(&h->d_ev_ac, E * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->d_ev_ak, E * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMalloc(&h->d_ev_af, E * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpy(h->d_ev_ac, comp, E * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_ev_ak, param, E * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->d_ev_af, coef, E * sizeof(double), cudaMemcpyHostToDevice));
     return B200ADJ_OK;
 }
 

@@ -69,6 +69,7 @@ struct Handle {
     double *s_u0 = nullptr, *s_p = nullptr, *s_saved = nullptr, *s_dLdu = nullptr, *s_du0 = nullptr, *s_dp = nullptr, *s_dW = nullptr;
     int32_t* s_status = nullptr;
     const double* cur_p = nullptr;    // device pointer to p valid between forward and reverse
+    int32_t* d_ev_ac = nullptr; int32_t* d_ev_ak = nullptr; double* d_ev_af = nullptr;      // b200adj_set_event_param_shift
     int32_t* d_event_of_step = nullptr;     // fixed-step Tsit5: event index at grid point n, or -1
     int nev = 0; double *d_ev_t = nullptr, *d_ev_s = nullptr, *d_ev_c = nullptr, *d_ev_ps = nullptr, *d_ev_pc = nullptr;      // preset-time events
     // state-dependent event (b200adj_set_continuous_callback): per-member event lists cc_t[cc_maxev][N], cc_n[N]

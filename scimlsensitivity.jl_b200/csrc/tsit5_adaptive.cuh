@@ -35,6 +35,9 @@ struct T5aArgs {
     int32_t nev; const double* ev_t; const double* ev_s; const double* ev_c;      // [E], [E][D], [E][D]
     double cont_a[4], cont_b[4];  // flags bit3: continuous cost g(u) = cont_a/2 |u|^2 + cont_b sum(u), dlam -= dgdu_continuous(y) (accumulate_cost!)
     const double* ev_ps; const double* ev_pc;     // [E][P] or null: parameter-changing affect p <- ps .* p + pc (reset_p of the reference)
+    // [E] or null: affect that adds a parameter to a state, u[ev_ac[e]] += ev_af[e] * p[ev_ak[e]] with the parameters in force before
+    // the event ("Dosing example", test/Callbacks1/discrete_callbacks.jl:401-427: integrator.u[1] += integrator.p[2]); ev_ac[e] < 0: none
+    const int32_t* ev_ac; const int32_t* ev_ak; const double* ev_af;
     // state-dependent event (ContinuousCallback, src/callback_tracking.jl:232-480; docs/src/examples/hybrid_jump/bouncing_ball.md):
     // condition u[cc_idx] - cc_level crossing zero in direction cc_dir (-1 down, +1 up, 0 both); affect u <- cc_scale .* u +
     // cc_shift, then u[cc_pcomp] <- cc_psign * p[cc_pparam] * u[cc_pcomp] (cc_pcomp < 0: none).  The forward kernel (CC = true)
@@ -359,6 +362,14 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                 } else {
 #pragma unroll
                 for (int j = 0; j < D; j++) un[j] = a.ev_s[ev * D + j] * un[j] + a.ev_c[ev * D + j];
+                if (a.ev_ac) {
+                    const int ac = a.ev_ac[ev], ak = a.ev_ak[ev];
+                    double pa = 0.0;
+#pragma unroll
+                    for (int q = 0; q < P; q++) if (q == ak) pa = p[q];
+#pragma unroll
+                    for (int j = 0; j < D; j++) if (j == ac) un[j] += a.ev_af[ev] * pa;
+                }
                 if (a.ev_ps) {
 #pragma unroll
                     for (int q = 0; q < P; q++) p[q] = a.ev_ps[ev * P + q] * p[q] + a.ev_pc[ev * P + q];
@@ -541,6 +552,8 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
                     for (int j = 0; j < D; j++) z[YO + j] = um[j];
                 }
             } else {
+            double gadd = 0.0;        // (da/dp)'lam+ of u[ac] += af p[ak], taken before lam is scaled
+            if (a.ev_ac) gadd = a.ev_af[evc] * t5_pick<D>(z, a.ev_ac[evc]);
 #pragma unroll
             for (int j = 0; j < D; j++) z[j] *= a.ev_s[evc * D + j];
             if (SA == SA_BACKSOLVE) {
@@ -561,6 +574,13 @@ __global__ void __launch_bounds__(256) t5a_reverse_kernel(const __grid_constant_
 #pragma unroll
                 for (int q = 0; q < P; q++) p0[q] = SHARED_P ? a.p[q] : a.p[(int64_t)q * N + i];
                 t5_event_params<P>(a, evc, p0, p);
+            }
+            if (a.ev_ac) {            // with respect to the parameters in force before the event
+                const int ak = a.ev_ac[evc] >= 0 ? a.ev_ak[evc] : -1;
+#pragma unroll
+                for (int q = 0; q < P; q++) if (q == ak) {
+                    if (SA == SA_INTERP || SA == SA_BACKSOLVE) z[D + (L > D ? q : 0)] += gadd; else acc[q] += gadd;
+                }
             }
             }
             tev = tt; evc--; fsal_ok = false;

@@ -151,6 +151,10 @@ class DeviceEnsemble:
         self.handle.set_events(times, scale, shift, pscale, pshift)
         self.events = (times, scale, shift, pscale, pshift)
 
+    def set_event_param_shift(self, comp, param, coef):
+        """u[comp[e]] += coef[e] * p[param[e]] at preset event e (the "Dosing example" affect); after set_events."""
+        self.handle.set_event_param_shift(comp, param, coef)
+
     def set_continuous_callback(self, cb):
         """State-dependent event (problems.ContinuousCallback) of the hybrid system; call before forward().  None removes it."""
         if cb is None:

@@ -224,6 +224,11 @@ class AffineAffect:
     shift: Any
     p_scale: Any = None          # parameter-changing affect integrator.p .= p_scale .* integrator.p .+ p_shift
     p_shift: Any = None          # ("p .= 2p .- 0.5" of discrete_callbacks.jl:294-303 is p_scale=2, p_shift=-0.5)
+    # affect that adds a parameter to a state, u[add_comp] += add_coef * p[add_param] (0-based; the "Dosing example"
+    # integrator.u[1] += integrator.p[2] of discrete_callbacks.jl:401-427 is add_comp=0, add_param=1, add_coef=1.0)
+    add_comp: Optional[int] = None
+    add_param: int = 0
+    add_coef: float = 1.0
 
 
 @dataclass(frozen=True)
@@ -249,3 +254,15 @@ class PresetTimeCallback:
             pc = np.stack([np.broadcast_to(np.asarray(0.0 if a.p_shift is None else a.p_shift, dtype=np.float64), (P,)) for a in aff])
             return t[order], sc[order], sh[order], ps[order], pc[order]
         return t[order], sc[order], sh[order]
+
+    def param_shift(self):
+        """(comp[E], param[E], coef[E]) in event-time order for b200adj_set_event_param_shift, or None."""
+        t = np.asarray(self.tstops, dtype=np.float64).reshape(-1)
+        aff = self.affect if isinstance(self.affect, (list, tuple)) else [self.affect] * len(t)
+        if not any(a.add_comp is not None for a in aff):
+            return None
+        order = np.argsort(t, kind="stable")
+        comp = np.array([-1 if a.add_comp is None else a.add_comp for a in aff], dtype=np.int32)[order]
+        par = np.array([a.add_param for a in aff], dtype=np.int32)[order]
+        coef = np.array([a.add_coef for a in aff], dtype=np.float64)[order]
+        return comp, par, coef

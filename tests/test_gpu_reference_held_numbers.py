@@ -135,3 +135,60 @@ def test_continuous_callback_params_are_validated():
     with pytest.raises(Exception):
         eng.handle.set_continuous_callback_params(acomp=1, aparam=0, acoef=1.0)  # d = 1
     eng.handle.set_continuous_callback_params(lparam=0, lcoef=0.75, acomp=0, aparam=1, acoef=1.0)
+
+
+@pytest.mark.parametrize("shared_p", [True, False])
+@pytest.mark.parametrize("sa", SENSEALGS)
+def test_dosing_example_on_the_device(sa, shared_p):
+    """"Dosing example" (test/Callbacks1/discrete_callbacks.jl:401-427): f = p[1] - u, at t = 8 the affect u[1] += p[2], loss u(10).
+    Closed form u(10) = p1 (1 - e^-10) + p2 e^-2 for u0 = 0, so every member's gradient is [1 - e^-10, e^-2]; through the public
+    API (PresetTimeCallback with an AffineAffect that adds a parameter) and against the oracle for random starts."""
+    N = 24
+    ts = np.array([10.0])
+    rng = np.random.default_rng(3)
+    p = np.array([100.0, 50.0]) if shared_p else np.stack([100.0 + 20.0 * rng.random(N), 50.0 + 10.0 * rng.random(N)])
+    exact = np.array([1.0 - np.exp(-10.0), np.exp(-2.0)])
+    kw = dict(abstol=1e-14, reltol=1e-14)
+    eng = b.DeviceEnsemble("relax", sa, "tsit5_adaptive", N, ts, (0.0, 10.0), 0.0, shared_p=shared_p, ckpt_every_step=True, **kw)
+    eng.set_events([8.0], [[1.0]], [[0.0]])
+    eng.set_event_param_shift([0], [1], [1.0])
+    saved, status = eng.forward(np.zeros((1, N)), p)
+    du0, dp = eng.reverse(np.ones((1, 1, N)))
+    dp = np.asarray(dp)
+    assert (np.asarray(status) == 0).all()
+    rtol = 1e-6 if sa == "gauss_kronrod" else 1e-10
+    if shared_p:
+        assert np.allclose(dp.ravel() / N, exact, rtol=rtol, atol=0), dp.ravel() / N - exact
+    else:
+        assert np.allclose(dp, exact[:, None], rtol=rtol, atol=0)
+    # random starts, several save times, a second dose: device vs oracle
+    u0 = 30.0 * rng.random((1, N))
+    t2 = np.linspace(1.0, 10.0, 10)
+    ev = ([3.0, 8.0], [[1.0], [0.5]], [[0.0], [1.0]])
+    eng = b.DeviceEnsemble("relax", sa, "tsit5_adaptive", N, t2, (0.0, 10.0), 0.0, cost=b.AffineCost(1.0, -1.0), shared_p=shared_p,
+                           ckpt_every_step=True, abstol=1e-10, reltol=1e-10)
+    eng.set_events(*ev)
+    eng.set_event_param_shift([0, 0], [1, 0], [1.0, -0.1])
+    saved, status = eng.forward(u0, p)
+    du0, dp = eng.reverse()
+    cfg = O.make_cfg("relax", sa, "tsit5_adaptive", N, t2, 0.0, 10.0, cost=("affine", 1.0, -1.0), shared_p=shared_p, ckpt_every_step=True,
+                     events=ev, event_padd=([0, 0], [1, 0], [1.0, -0.1]), abstol=1e-10, reltol=1e-10)
+    ref = O.gradient(cfg, t2, u0, p)
+    rel = lambda a, r: float(np.max(np.abs(np.asarray(a) - r)) / np.max(np.abs(r)))
+    assert rel(saved, ref["saved"]) < 1e-9 and rel(du0, ref["du0"]) < 1e-7 and rel(dp, ref["dp"]) < 1e-7
+
+
+def test_dosing_through_the_public_api():
+    N = 8
+    ts = np.array([10.0])
+    cb = b.PresetTimeCallback([8.0], b.AffineAffect(1.0, 0.0, add_comp=0, add_param=1, add_coef=1.0))
+    prob = b.EnsembleProblem(b.ODEProblem("relax", [0.0], (0.0, 10.0), [100.0, 50.0], callback=cb), u0s=np.zeros((1, N)))
+    out, pullback = b._concrete_solve_adjoint(prob, b.Tsit5(adaptive=True), b.B200Adjoint(b.BacksolveAdjoint()), np.zeros((1, N)),
+                                              np.array([100.0, 50.0]), None, saveat=ts, abstol=1e-12, reltol=1e-12)
+    tang = pullback(np.ones_like(np.asarray(out.u)))
+    dp = np.asarray(tang[4]).reshape(-1) / N
+    assert np.allclose(dp, [1.0 - np.exp(-10.0), np.exp(-2.0)], rtol=1e-9), dp
+    with pytest.raises(b.B200AdjError):        # the dt-grid kernels do not carry it: the dense framework does
+        eng = b.DeviceEnsemble("lv", "gauss", "tsit5_fixed", 4, [1.0], (0.0, 1.0), 0.01)
+        eng.set_events([0.5], [[1.0, 1.0]], [[0.0, 0.0]])
+        eng.set_event_param_shift([0], [1], [1.0])

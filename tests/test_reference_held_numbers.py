@@ -87,3 +87,18 @@ def test_parameter_dependent_condition_reproduces_gND(sa):
     assert abs(r["saved"][0, 0, 0] - (100.0 + 25.0 * 4.0 * np.exp(-10.0))) < 1e-10
     t, um, up = O.event_list(cfg, [0.0], [100.0, 50.0])
     assert len(t) == 1 and abs(t[0] - np.log(4.0)) < 1e-12 and abs(um[0, 0] - 75.0) < 1e-10 and abs(up[0, 0] - 125.0) < 1e-10
+
+
+@pytest.mark.parametrize("stepper,kw", [("tsit5_adaptive", dict(abstol=1e-14, reltol=1e-14)), ("tsit5_fixed", dict(dt=0.01))])
+@pytest.mark.parametrize("sa", SENSEALGS)
+def test_dosing_example_closed_form(sa, stepper, kw):
+    """"Dosing example" of test/Callbacks1/discrete_callbacks.jl:401-427 (f = p[1] - u, at t = 8 the affect u[1] += p[2], loss
+    u(10), abstol = reltol = 1e-14; the reference asserts ForwardDiff == Zygote through BacksolveAdjoint).  No literal is printed
+    there; the closed form is u(10) = p1 (1 - e^-10) + p2 e^-2, gradient [1 - e^-10, e^-2]."""
+    ts = np.array([10.0])
+    cfg = O.make_cfg("relax", sa, stepper, 1, ts, 0.0, 10.0, events=([8.0], [[1.0]], [[0.0]]), event_padd=([0], [1], [1.0]),
+                     ckpt_every_step=True, **kw)
+    r = O.gradient(cfg, ts, np.array([[0.0]]), np.array([100.0, 50.0]), dLdu=np.ones((1, 1, 1)))
+    exact = np.array([1.0 - np.exp(-10.0), np.exp(-2.0)])
+    assert abs(r["saved"][0, 0, 0] - (100.0 * exact[0] + 50.0 * exact[1])) < 1e-10
+    assert np.allclose(r["dp"], exact, rtol=1e-6 if sa == "gauss_kronrod" else 1e-10, atol=0), r["dp"] - exact
