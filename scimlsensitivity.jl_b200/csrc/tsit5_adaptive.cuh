@@ -23,7 +23,7 @@ struct T5aArgs {
     double* ft; double* fu; double* fk; int32_t* fn;              // fn[N]: accepted forward steps per member (ft / fu / fk: unused by these kernels)
     double* rrec; double* rend; int32_t* rn;                      // reverse dense (Quadrature), member-major: [N][MAXS][RWP] = (t, h, z[D], k[7][D]), [N][MAXS] = t + h
     // THE forward dense solution, member-major: every member has its own step sequence, so its records are contiguous and move
-    // as ONE bulk copy each (TMA): knots ftT[N][MAXS+1]; records frecT[N][MAXS+1][8 D + 4] = (u_n[D], k1..k7[D], t_n, h, 1/h,
+    // as ONE bulk copy each (TMA): knots ftT[N][MAXS+1]; records frecT[N][MAXS+1][8 D + 4] = (u_n[D], c0..c3[D] = the interpolant in powers of theta, 3 D unused, t_n, h, 1/h,
     // t_{n+1}); record fn[i] (the last) holds the final state and time only
     double* ftT; double* frecT;
     double* qseg; double* qkey; int32_t maxseg;
@@ -116,28 +116,8 @@ struct T5Dense {
         tma_load_1d(sc + buf * bs, record(iv), (uint32_t)(REC * sizeof(double)), bar);
     }
     __device__ __forceinline__ void arrived() const { mbar_wait(bar, ph); ph ^= 1u; }
-    // A record is looked up 6-9 times while the solve is inside its interval: on entry its stages k1..k7 are turned IN PLACE
-    // into the coefficients of the interpolant in powers of theta,  y(theta) = u_n + h theta (c0 + theta (c1 + theta (c2 +
-    // theta c3))),  c_m = sum_s R[s][m] k_s  (b_s(theta) = sum_m R[s][m] theta^(m+1)).  A lookup is then 4 D + 2 FMAs instead
-    // of 28 for the seven weights + 7 D for the combination (28 D once per interval).
-    __device__ __forceinline__ void to_powers(int buf) const {
-        double* b = sc + buf * bs;
-#pragma unroll
-        for (int j = 0; j < D; j++) {
-            double kk[7], c[4];
-#pragma unroll
-            for (int s = 0; s < 7; s++) kk[s] = b[D + s * D + j];
-#pragma unroll
-            for (int m = 0; m < 4; m++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int s = 0; s < 7; s++) acc += a.R[s][m] * kk[s];
-                c[m] = acc;
-            }
-#pragma unroll
-            for (int m = 0; m < 4; m++) b[D + m * D + j] = c[m];
-        }
-    }
+    // The records carry the interpolant in powers of theta (written so by the forward kernel):
+    //   y(theta) = u_n + h theta (c0 + theta (c1 + theta (c2 + theta c3)))
     __device__ __forceinline__ void eval(double t, bool right, double* y) const {
         if (!(civ >= 0 && holds(civ, cta, ctb, t, right))) {
             bool got = false;
@@ -146,9 +126,6 @@ struct T5Dense {
                 const double ata = sc[(cb ^ 1) * bs + 8 * D];
                 if (holds(aiv, ata, cta, t, right)) { cb ^= 1; civ = aiv; ctb = cta; cta = ata; cur = civ; got = true; }
             }
-            // this thread has written its buffers through the generic proxy (to_powers): order those stores before the bulk
-            // copies that overwrite them
-            fence_proxy_async_smem();
             if (!got) {
                 // cursor instead of a bisection over the knots: the adjoint solve visits the forward solution monotonically
                 int iv = cur < n - 1 ? cur : n - 1;
@@ -162,7 +139,6 @@ struct T5Dense {
             }
             aiv = civ - 1;
             if (aiv >= 0) request(cb ^ 1, aiv);
-            to_powers(cb);
         }
         const double* b = sc + cb * bs;
         const double h = ctb - cta;
@@ -362,10 +338,22 @@ __global__ void __launch_bounds__(256) t5a_forward_kernel(const __grid_constant_
                 tma_store_wait_read();                                 // the previous record has left the staging buffer
 #pragma unroll
                 for (int j = 0; j < D; j++) st[j] = u[j];
+                // the stages enter the record as the coefficients of the interpolant in powers of theta,
+                //   y(theta) = u_n + h theta (c0 + theta (c1 + theta (c2 + theta c3))),  c_m = sum_s R[s][m] k_s
+                // (b_s(theta) = sum_m R[s][m] theta^(m+1)): computed once here, every lookup of the reverse solve and of the
+                // quadrature is then 4 FMAs per component instead of the seven weights + a 7-term combination
 #pragma unroll
-                for (int s = 0; s < 7; s++)
+                for (int j = 0; j < D; j++) {
 #pragma unroll
-                    for (int j = 0; j < D; j++) st[D + s * D + j] = k[s][j];
+                    for (int m = 0; m < 4; m++) {
+                        double c = 0.0;
+#pragma unroll
+                        for (int s = 0; s < 7; s++) c += a.R[s][m] * k[s][j];
+                        st[D + m * D + j] = c;
+                    }
+#pragma unroll
+                    for (int m = 4; m < 7; m++) st[D + m * D + j] = 0.0;
+                }
                 const double hrec = tn - t;
                 st[8 * D] = t; st[8 * D + 1] = hrec; st[8 * D + 2] = 1.0 / hrec; st[8 * D + 3] = tn;
                 fence_proxy_async_smem();
@@ -754,16 +742,12 @@ struct T5aQuadCtx {
         const int lo = br.rlo + coop_count<false>([&](int j) { return __ldg(rend + j); }, br.rlo, br.rhi - br.rlo, t, lane);
         *fiv = iv; *riv = lo;
         {
-            const double* r = frecT + iv * FWP;                  // (u[D], k[7][D], t_a, h, 1/h)
+            const double* r = frecT + iv * FWP;                  // (u[D], c0..c3[D] (powers of theta), -, t_a, h, 1/h)
             const double ta = __ldg(r + 8 * D), h = __ldg(r + 8 * D + 1);
-            t5_weights(a, (h == 0.0) ? 1.0 : (t - ta) * __ldg(r + 8 * D + 2), w);
+            const double th = (h == 0.0) ? 1.0 : (t - ta) * __ldg(r + 8 * D + 2), g = h * th;
 #pragma unroll
-            for (int j = 0; j < D; j++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int s = 0; s < 7; s++) acc += w[s] * __ldg(r + (1 + s) * D + j);
-                y[j] = __ldg(r + j) + h * acc;
-            }
+            for (int j = 0; j < D; j++)
+                y[j] = fma(g, fma(th, fma(th, fma(th, __ldg(r + 4 * D + j), __ldg(r + 3 * D + j)), __ldg(r + 2 * D + j)), __ldg(r + D + j)), __ldg(r + j));
         }
         {
             const double* r = rrec + lo * RWP;                   // (t_start, h, z[D], k[7][D], 1/h)
