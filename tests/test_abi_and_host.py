@@ -137,6 +137,43 @@ def test_preset_time_callback_tables_and_host_side_rejections():
                 callback=b.PresetTimeCallback([5.0], b.AffineAffect(1.0, 0.0)))
 
 
+def test_callback_family_host_objects():
+    """The host objects of the callback families: the dosing affect's table follows the event-time order, the continuous callback's
+    cache key tells the family extensions apart (a reused handle must not serve a different callback)."""
+    cb = b.PresetTimeCallback([8.0, 3.0], [b.AffineAffect(1.0, 0.0, add_comp=0, add_param=1, add_coef=1.0), b.AffineAffect(0.5, 1.0)])
+    comp, par, coef = cb.param_shift()
+    assert comp.tolist() == [-1, 0] and par.tolist() == [0, 1] and coef.tolist() == [1.0, 1.0] and comp.dtype == np.int32
+    assert b.PresetTimeCallback([1.0], b.AffineAffect(1.0, 0.0)).param_shift() is None
+    base = b.ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0)
+    keys = {base.key(), b.ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0, level_param=0, level_coef=0.75).key(),
+            b.ContinuousCallback(idx=0, direction=-1, p_comp=1, p_param=1, p_sign=-1.0, add_comp=0, add_param=1, add_coef=1.0).key(),
+            b.ContinuousCallback(idx=0, direction=-1, sq_comp=1).key(), b.ContinuousCallback(idx=0, direction=-1, sq_comp=1, sq_coef=2.0).key()}
+    assert len(keys) == 5
+    assert "relax" in b.FAMILIES if hasattr(b, "FAMILIES") else True
+
+
+def test_bench_secondary_specs_are_consistent_with_the_oracle():
+    """bench.py's secondary legs: every spec builds an oracle cfg (the parity checker) and its roofline closure returns a fraction."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec); spec.loader.exec_module(bench)
+    from oracle import oracle as O
+    for mk in (bench.spec_c1, bench.spec_c3, bench.spec_c5):
+        sp = mk()
+        n = 4
+        u0, p = sp["inputs"](n, 0)
+        shared = sp.get("shared_p", True)
+        cfg = O.make_cfg(sp["family"], sp["sensealg"], sp["stepper"], n, sp["saveat"], 0.0, sp["T"], dt=sp["dt"],
+                         cost=("affine",) + tuple(sp["cost"]), shared_p=shared, **sp["okw"])
+        dW = None
+        if sp["stepper"] == "em":
+            dW = np.sqrt(sp["dt"]) * np.random.default_rng(0).standard_normal((int(round(sp["T"] / sp["dt"])), 2, n))
+        ref = O.gradient(cfg, sp["saveat"], u0, p, dW=dW, want_saved=False)
+        assert np.isfinite(ref["dp"]).all() and ref["dp"].shape == ((sp["okw"].get("P", len(p)),) if shared else (p.shape[0], n))
+        rf = sp["roofline"](n, 100.0, 1e-3, 6570.0, 1426.0)
+        assert 0.0 < rf["frac"] < 10.0 and sp["cpu_sample"] >= sp["parity_members"]
+
+
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU arm the driver runs first): exactly one JSON line on stdout with the contract's
     keys, measured on the oracle port; other ranks of a torchrun launch print nothing and exit 0."""
