@@ -6,9 +6,15 @@
  * for the B200 kernels: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it.  The product path (libb200adj.so) never links or calls it.
  *
- * PARITY STATUS: "parity unpinned" at the bit level.  The reference is pure Julia, Julia is not
- * installed in this image, and the reference ships no golden vectors for this path (SURVEY.md
- * finding 5).  The oracle is therefore pinned by the reference's own test RELATIONS
+ * PARITY STATUS: pinned by the literal results the reference itself holds for this path, "parity unpinned"
+ * at the bit level elsewhere.  The reference is pure Julia, Julia is not installed in this image, and the
+ * reference ships no golden VECTORS for this path (SURVEY.md finding 5).  Reference-held numbers reproduced
+ * (tests/test_reference_held_numbers.py): the printed optimum 0.866554105436901 of
+ * docs/src/examples/hybrid_jump/bouncing_ball.md:60 as the root of the adjoint gradient (1e-14), the
+ * first-impact fixture of test/Callbacks2/continuous_vs_discrete.jl:19-21 (4e-15), gND of
+ * test/Callbacks2/continuous_callbacks.jl:343 at the reference's rtol 1e-10 (2e-15), the closed form of the
+ * "Dosing example" (test/Callbacks1/discrete_callbacks.jl:401-427).  For the paths without a reference-held
+ * literal (fixed-step Tsit5, Rosenbrock23, SDE) the oracle is pinned by the reference's own test RELATIONS
  * (tests/test_oracle_relations.py): cross-sensealg agreement (test/Core3/adjoint.jl:366-404),
  * agreement with differentiation through the solver (test/Core3/adjoint.jl:691-705),
  * du0 agreement (:865-908), Lorenz Backsolve==Interpolating (:1157-1241), closed-form linear SDE
