@@ -623,3 +623,28 @@ def test_hybrid_neural_ode_preset_time_events_match_finite_differences():
         assert abs(r["dp"] @ v - fd) < 1e-7 * max(1.0, abs(fd)), (sa, r["dp"] @ v, fd)
         gu = _fd_grad(lambda u: O.loss(cfg, ts, u, p)[0], u0, h=1e-5)
         assert np.allclose(r["du0"].ravel(), gu.ravel(), rtol=1e-7), sa
+
+
+def test_fixed_step_tsit5_adjoints_converge_to_a_closed_form_at_order_five():
+    """The fixed-step Tsit5 path (the headline configuration's stepper) against a CLOSED FORM, with the convergence order as the
+    check: u' = p1 - u has u(t) = p1 + (u0 - p1) e^-t, so for L = sum_k (a/2 u(t_k)^2 + b u(t_k)) the gradient is
+    dL/du0 = sum_k (a u_k + b) e^-t_k, dL/dp1 = sum_k (a u_k + b)(1 - e^-t_k).  Halving dt must divide the error of every
+    sensealg by about 2^5 (Tsit5 is of order 5; the 3-point Gauss rule of order 6)."""
+    T = 2.0
+    ts = np.linspace(0.5, T, 4)
+    u0 = np.array([[0.3]]); p = np.array([1.7, 0.0]); a, b = 1.0, -2.0
+    e = np.exp(-ts); u = p[0] + (u0[0, 0] - p[0]) * e
+    gu, gp = np.sum((a * u + b) * e), np.sum((a * u + b) * (1 - e))
+    for sa in ("interpolating", "gauss", "backsolve", "quadrature", "gauss_kronrod"):
+        errs = []
+        for dt in (0.25, 0.125, 0.0625):
+            cfg = O.make_cfg("relax", sa, "tsit5_fixed", 1, ts, 0.0, T, dt=dt, cost=("affine", a, b), quad_abstol=1e-14, quad_reltol=1e-14)
+            r = O.gradient(cfg, ts, u0, p)
+            errs.append((abs(r["du0"][0, 0] - gu), abs(r["dp"][0] - gp)))
+        errs = np.array(errs)
+        order = np.log2(errs[:-1] / errs[1:])
+        assert errs[-1, 0] < 2e-10 and (order[:, 0] > 4.8).all(), (sa, errs, order)
+        if sa != "gauss_kronrod":        # GaussKronrod: dp is held at its 1e-7 bisection threshold
+            assert errs[-1, 1] < 2e-10 and (order[:, 1] > 4.8).all(), (sa, errs, order)
+        else:
+            assert errs[-1, 1] < 5e-7
